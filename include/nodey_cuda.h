@@ -1,0 +1,134 @@
+/*
+ * nodey_cuda.h -- C ABI of libnodey_cuda.so: the sm_100a kernels behind the Nodey Audio Editor
+ * processor nodes.  This is the drop-in boundary for the offline-render hot path: plain pointers
+ * and sizes, no C++ / torch types.  The reference has no FFI of its own (single C++ process);
+ * each entry point names the reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative NODEY_E_* code otherwise; the message is
+ *    available per thread from nodey_last_error();
+ *  - all sample pointers are DEVICE pointers unless the parameter is documented as host;
+ *  - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default);
+ *  - sample formats use FFmpeg's AVSampleFormat numbering, as stored in the reference's frames
+ *    (AVFrame::format): S16=1 S32=2 FLT=3 S16P=6 S32P=7 FLTP=8;
+ *  - "frames" = samples per channel.
+ */
+#ifndef NODEY_CUDA_H
+#define NODEY_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nodey_stream_t;
+
+enum {
+    NODEY_FMT_U8 = 0, NODEY_FMT_S16 = 1, NODEY_FMT_S32 = 2, NODEY_FMT_FLT = 3, NODEY_FMT_DBL = 4,
+    NODEY_FMT_U8P = 5, NODEY_FMT_S16P = 6, NODEY_FMT_S32P = 7, NODEY_FMT_FLTP = 8, NODEY_FMT_DBLP = 9
+};
+
+enum {
+    NODEY_OK = 0,
+    NODEY_E_INVALID = -1,      /* bad argument */
+    NODEY_E_FORMAT = -2,       /* unsupported sample format (reference: Runtime_error "format is not support") */
+    NODEY_E_CUDA = -3,         /* CUDA runtime error, text in nodey_last_error() */
+    NODEY_E_NOMEM = -4,
+    NODEY_E_RANGE = -5         /* parameter outside the range the reference accepts */
+};
+
+#define NODEY_MAX_MIX_INPUTS 16   /* audio-amix.cpp:342 clamps input_num to 1..16 */
+
+int nodey_version(void);
+const char* nodey_last_error(void);
+/* sm count, cc major, cc minor, total bytes: fails (NODEY_E_CUDA) when no CUDA device is present */
+int nodey_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+
+/* Synthetic source of SURVEY.md 8(d): x = 0.5 sin(2 pi f n / sr) + 0.05 u, bit-identical to the
+ * oracle generator.  dst: interleaved float [nframes][nch]; optional s16 copy clip(lrintf(x*32767)). */
+int nodey_synth(float* dst_f32, int16_t* dst_s16, int64_t nframes, int nch, int sample_rate,
+                int track, int64_t frame0, nodey_stream_t stream);
+
+/* A3  audio_volume_adjust -- change_volume<T>, src/processor/audio-vol.cpp:75-100.
+ * dst[i] = T(src[i] * volume) over n_elems samples of one plane (packed: frames*channels).
+ * Integer formats follow the x86 truncating conversion the reference compiles to (no clamp). */
+int nodey_gain(void* dst, const void* src, int fmt, int64_t n_elems, float volume, nodey_stream_t stream);
+
+/* A8  extract_samples_interleaved, src/processor/audio-velocity.cpp:150-232.
+ * Any of the six formats -> interleaved float, with the reference's four integer scales. */
+int nodey_extract_interleaved(float* dst, const void* plane0, const void* plane1, int fmt,
+                              int64_t nframes, int nch, nodey_stream_t stream);
+
+/* N1  audio_channel_split (new node): stereo -> two mono planes of the same sample
+ * type; pure routing, bit exact. */
+int nodey_split(void* dst_l, void* dst_r, const void* plane0, const void* plane1, int fmt,
+                int64_t nframes, nodey_stream_t stream);
+
+/* swr format conversion + rematrix with no rate change (libswresample audioconvert/rematrix as
+ * configured at audio-amix.cpp:212-243): any format, mono|stereo -> stereo float planar.
+ * mono -> both channels = in * sqrt(1/2). */
+int nodey_to_fltp_stereo(float* dst_l, float* dst_r, const void* plane0, const void* plane1, int fmt,
+                         int nch, int64_t nframes, nodey_stream_t stream);
+
+/* A4  audio_amix mix loop, src/processor/audio-amix.cpp:293-307.
+ * out[j] = ((0 + in0[j]*v0) + in1[j]*v1) + ... in input order; input i contributes zeros for
+ * j >= in_len[i] (the reference's zero-filled temp buffers).  in_l / in_r / in_len / volumes are
+ * HOST arrays of nin entries (device pointers inside). */
+int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r,
+              const int64_t* in_len, const float* volumes, int nin, int64_t nframes,
+              nodey_stream_t stream);
+
+/* A5  audio_bimix mix loop, src/processor/audio-bimix.cpp:310-317.
+ * outL = (ll/2 + lr/2) * (1 - bias), outR = (rl/2 + rr/2) * (1 + bias); zeros past len_l / len_r. */
+int nodey_bimix(float* out_l, float* out_r, const float* ll, const float* lr, int64_t len_l,
+                const float* rl, const float* rr, int64_t len_r, float bias, int64_t nframes,
+                nodey_stream_t stream);
+
+/* A6  audio_bimix_v2 pieces, src/processor/audio-bimix.cpp:625-627 and :777-872.
+ * downmix: dst = (l + r) * 0.5.  merge: interleaved stereo out; for frame j of segment s
+ * (seg_out_start[s] <= j < seg_out_start[s] + seg_len[s]) L = left[seg_l[s] + d] or 0 when
+ * seg_l[s] < 0, same for R.  Segment arrays are HOST arrays (nseg entries). */
+int nodey_downmix_half(float* dst, const float* l, const float* r, int64_t n, nodey_stream_t stream);
+int nodey_merge_segments(float* out_interleaved, const float* left, const float* right,
+                         const int64_t* seg_out_start, const int64_t* seg_len,
+                         const int64_t* seg_l, const int64_t* seg_r, int nseg, nodey_stream_t stream);
+
+/* A7  Audio_resampler / swr_convert rate conversion (src/utility/sw-resample.cpp:8-23,
+ * include/utility/sw-resample.hpp:55-70; call sites audio-amix.cpp:263-290,
+ * audio-bimix.cpp:259-294): libswresample with all-default options -> Kaiser(9) windowed sinc,
+ * 32 taps (more when down-sampling), exact-rational polyphase, mirrored start, reflected flush.
+ * The plan owns the device copy of the filter bank. */
+typedef struct nodey_resampler nodey_resampler;
+int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int index_mask_quirk);
+void nodey_resampler_destroy(nodey_resampler* r);
+/* info[8]: phase_count, filter_length, filter_alloc, dst_incr_div, dst_incr_mod, src_incr, index0, linear */
+int nodey_resampler_info(const nodey_resampler* r, int info[8]);
+/* HOST pointer to the (phase_count+1) x filter_alloc float filter bank */
+const float* nodey_resampler_filter_bank(const nodey_resampler* r);
+/* frames swr would return in total for in_frames of input (flush: after swr_convert(NULL) drain) */
+int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, int flush);
+/* Whole-track conversion: source in its native format (converted on load, mono rematrixed),
+ * stereo float planar out.  out_frames <= nodey_resampler_out_count(). */
+int nodey_resampler_run(const nodey_resampler* r, float* out_l, float* out_r,
+                        const void* plane0, const void* plane1, int fmt, int nch, int64_t in_frames,
+                        int flush, int64_t out_frames, nodey_stream_t stream);
+/* Fused A7 + A4 for inputs that share one plan (same source rate): out = sum_i vol_i * resample(in_i)
+ * in input order, zeros past each input's own length.  Host arrays of nin entries. */
+int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r,
+                       const void* const* plane0, const void* const* plane1, const int* fmt,
+                       const int* nch, const int64_t* in_frames, const int64_t* out_len,
+                       const float* volumes, int nin, int flush, int64_t out_frames,
+                       nodey_stream_t stream);
+
+/* N2  audio_spectrum (new node; FFTW r2c convention, unnormalised):
+ * frame m = x[m*hop .. m*hop+nfft) * periodic Hann, out[m][0..nfft/2] complex64.
+ * nfft must be 4096 in this release. */
+int64_t nodey_stft_frames(int64_t nframes, int nfft, int hop);
+int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nfft, int hop,
+               nodey_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,551 @@
+// resample.cu -- K5: libswresample-equivalent polyphase FIR (A7; call sites audio-amix.cpp:263-290,
+// audio-bimix.cpp:259-294, sw-resample.hpp:63-69) and its fusion with the N-input mix (A4).
+//
+// Output k sits at phase position pos_k = index0 + k*dst_incr_div (+ carry of k*dst_incr_mod) in
+// units of 1/phase_count input samples:  y[k] = sum_i x[pos_k / P - center + i] * h[pos_k % P][i],
+// x mirrored about sample 0 on the left and reflected at the end after a flush.  The accumulation
+// order is the oracle's: one accumulator, ascending taps, fused multiply-add.
+//
+// Two kernels:
+//  * resample_generic_kernel: one thread per output frame, any plan (incl. the interpolating
+//    path when the ratio is not exact), taps and samples straight from global/L1.  Correctness
+//    baseline and fallback.
+//  * resample_tile_kernel: the production path for exact-rational plans.  A CTA owns a tile of
+//    32 periods (period = P outputs <-> D input frames).  The input tile is converted to float
+//    once into shared memory; warp w owns a group of G=8 consecutive phases, lane b owns period b.
+//    A thread keeps G x channels accumulators in registers and walks the union window of its
+//    group once: one shared-memory sample feeds G FMAs, and the G taps of a window position are
+//    a warp-uniform broadcast read (dense per-group tap matrix, zero where a phase's window does
+//    not reach).  That takes shared-memory traffic from ~4 B/FMA to ~0.6 B/FMA, which is what
+//    lets an FP32-co-limited FIR approach the HBM roofline.  Results are staged in
+//    shared memory and leave as coalesced 128-bit stores.  Up to 16 inputs can be accumulated in
+//    input order before the store (audio_amix fused; config 3).
+#include "nodey_common.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+struct nodey_resampler {
+    int in_rate, out_rate;
+    int resample;                       // 0 when rates are equal
+    int phase_count, filter_length, filter_alloc;
+    int src_incr, dst_incr, dst_incr_div, dst_incr_mod;
+    int index0;
+    std::vector<float> bank;            // host copy, (phase_count + 1) * filter_alloc
+    float* d_bank = nullptr;            // device copy
+    // tile kernel tables (exact-rational plans only)
+    int tile_ok = 0;
+    int G = 8, n_groups = 0, wmax = 0, s0 = 0, span = 0;   // span = s_{P-1} - s_0
+    float* d_hq = nullptr;              // [n_groups][wmax][G]
+    int* d_group_start = nullptr;       // [n_groups] : s_{qG} - s_0
+    int device = 0;
+};
+
+namespace nodey {
+
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a < 0 ? -a : a; }
+
+static double bessel_i0(double x)
+{
+    double v = 1, lastv = 0, t = 1;
+    x = x * x / 4;
+    for (int i = 1; v != lastv; i++) {
+        lastv = v;
+        t *= x / ((double)i * (double)i);
+        v += t;
+    }
+    return v;
+}
+
+// Kaiser-windowed sinc, every phase normalised to unit DC gain (libswresample build_filter()).
+static void build_filter(float* bank, double factor, int tap_count, int alloc, int phase_count, double beta)
+{
+    const int center = (tap_count - 1) / 2;
+    std::vector<double> tab((size_t)tap_count);
+    const int ph_nb = (phase_count % 2) ? phase_count : phase_count / 2 + 1;
+    if (factor > 1.0) factor = 1.0;
+    for (int ph = 0; ph < ph_nb; ph++) {
+        double norm = 0;
+        for (int i = 0; i < tap_count; i++) {
+            const double x = M_PI * ((double)(i - center) - (double)ph / phase_count) * factor;
+            double y = (x == 0) ? 1.0 : sin(x) / x;
+            const double w = 2.0 * x / (factor * tap_count * M_PI);
+            const double a = 1 - w * w;
+            y *= bessel_i0(beta * sqrt(a > 0 ? a : 0));
+            tab[(size_t)i] = y;
+            norm += y;
+        }
+        for (int i = 0; i < tap_count; i++) bank[ph * alloc + i] = (float)(tab[(size_t)i] / norm);
+        if (phase_count % 2) continue;
+        for (int i = 0; i < tap_count; i++)
+            bank[(phase_count - ph) * alloc + tap_count - 1 - i] = bank[ph * alloc + i];
+    }
+}
+
+// ---- source access with on-the-fly swr input conversion ------------------------------------------
+struct SrcDesc {
+    const void* p0;
+    const void* p1;
+    long long n;          // real input frames
+    long long reflect;    // reflected frames appended by the flush
+    int fmt, nch, planar;
+};
+
+__device__ __forceinline__ float src_scalar(const void* p, int fmt, long long i)
+{
+    switch (fmt) {
+    case NODEY_FMT_S16: case NODEY_FMT_S16P: return __fmul_rn((float)((const short*)p)[i], 3.0517578125e-05f);
+    case NODEY_FMT_S32: case NODEY_FMT_S32P: return __fmul_rn((float)((const int*)p)[i], 4.656612873077393e-10f);
+    default: return ((const float*)p)[i];
+    }
+}
+
+// extended-signal frame f (mirror / reflection applied) as a stereo pair after rematrix
+__device__ __forceinline__ float2 src_frame(const SrcDesc& s, long long f)
+{
+    if (f < 0) f = -f;
+    if (f >= s.n) f = 2 * s.n - 1 - f;
+    if (f < 0 || f >= s.n) return make_float2(0.f, 0.f);
+    if (s.nch == 1) {
+        const float m = __fmul_rn(src_scalar(s.p0, s.fmt, f), 0.70710678118654752440f);
+        return make_float2(m, m);
+    }
+    if (s.planar) return make_float2(src_scalar(s.p0, s.fmt, f), src_scalar(s.p1, s.fmt, f));
+    if (s.fmt == NODEY_FMT_FLT) return reinterpret_cast<const float2*>(s.p0)[f];
+    return make_float2(src_scalar(s.p0, s.fmt, 2 * f), src_scalar(s.p0, s.fmt, 2 * f + 1));
+}
+
+struct PlanDev {
+    const float* bank;
+    int P, L, alloc, div, mod, src_incr, index0;
+};
+
+// ---- generic kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resample_generic_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                               const SrcDesc s, const PlanDev pl, long long out_frames)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int center = (pl.L - 1) / 2;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < out_frames; k += stride) {
+        const long long f = k * (long long)pl.mod;
+        const long long index = (long long)pl.index0 + k * (long long)pl.div + f / pl.src_incr;
+        const int frac = (int)(f % pl.src_incr);
+        const long long start = index / pl.P - center;
+        const float* taps = pl.bank + (size_t)pl.alloc * (size_t)(index % pl.P);
+        float al = 0.f, ar = 0.f, bl = 0.f, br = 0.f;
+        for (int i = 0; i < pl.L; i++) {
+            const float2 x = src_frame(s, start + i);
+            const float h = __ldg(taps + i);
+            al = __fmaf_rn(x.x, h, al);
+            ar = __fmaf_rn(x.y, h, ar);
+            if (pl.mod) {
+                const float h2 = __ldg(taps + pl.alloc + i);
+                bl = __fmaf_rn(x.x, h2, bl);
+                br = __fmaf_rn(x.y, h2, br);
+            }
+        }
+        if (pl.mod) {
+            // resample_linear: val += (v2 - val) * (float)frac / src_incr
+            al = __fadd_rn(al, __fdiv_rn(__fmul_rn(__fsub_rn(bl, al), (float)frac), (float)pl.src_incr));
+            ar = __fadd_rn(ar, __fdiv_rn(__fmul_rn(__fsub_rn(br, ar), (float)frac), (float)pl.src_incr));
+        }
+        out_l[k] = al;
+        out_r[k] = s.nch == 1 ? al : ar;
+    }
+}
+
+// ---- tile kernel --------------------------------------------------------------------------------------
+constexpr int kG = 8;          // phases per warp group
+constexpr int kNB = 32;        // periods per tile = lanes
+
+struct TileArgs {
+    SrcDesc src[NODEY_MAX_MIX_INPUTS];
+    long long out_len[NODEY_MAX_MIX_INPUTS];   // frames this input contributes (zeros after)
+    float vol[NODEY_MAX_MIX_INPUTS];
+    int nin;
+    int mix;                 // 0: plain resample of src[0] (no volume multiply)
+    const float* hq;         // [n_groups][wmax][G]
+    const int* group_start;  // [n_groups]
+    int P, D, L, center, n_groups, wmax, s0, span;
+    int in_tile;             // frames of input staged per tile
+    int out_stride;          // padded staging row stride (odd)
+    long long out_frames;
+    long long n_tiles;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                            const __grid_constant__ TileArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [hq: n_groups*wmax*G floats][group_start: n_groups ints][stage L: NB*out_stride][stage R][input tile]
+    float* s_hq = reinterpret_cast<float*>(smem_raw);
+    int* s_gs = reinterpret_cast<int*>(s_hq + a.n_groups * a.wmax * kG);
+    float* s_out_l = reinterpret_cast<float*>(s_gs + ((a.n_groups + 3) & ~3));
+    float* s_out_r = s_out_l + kNB * a.out_stride;
+    float* s_in = s_out_r + kNB * a.out_stride;     // CH floats per frame, frame-major
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+
+    for (int i = tid; i < a.n_groups * a.wmax * kG; i += nthr) s_hq[i] = a.hq[i];
+    for (int i = tid; i < a.n_groups; i += nthr) s_gs[i] = a.group_start[i];
+
+    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const long long k0 = tile * (long long)kNB * a.P;               // first output frame of the tile
+        const long long in0 = tile * (long long)kNB * a.D + a.s0 - a.center;  // first staged input frame
+
+        for (int inp = 0; inp < a.nin; inp++) {
+            __syncthreads();   // previous use of s_in (and of the staging rows on a new tile) is over
+            const SrcDesc s = a.src[inp];
+            if (k0 < a.out_len[inp]) {
+                if (CH == 2) {
+                    float2* dst = reinterpret_cast<float2*>(s_in);
+                    for (int f = tid; f < a.in_tile; f += nthr) dst[f] = src_frame(s, in0 + f);
+                } else {
+                    for (int f = tid; f < a.in_tile; f += nthr) s_in[f] = src_frame(s, in0 + f).x;
+                }
+            }
+            __syncthreads();
+            const float vol = a.vol[inp];
+            for (int q = warp; q < a.n_groups; q += nwarps) {
+                float acc[kG][CH];
+#pragma unroll
+                for (int g = 0; g < kG; g++)
+#pragma unroll
+                    for (int c = 0; c < CH; c++) acc[g][c] = 0.f;
+                const long long kq = k0 + (long long)lane * a.P + (long long)q * kG;   // first output of this thread
+                if (k0 < a.out_len[inp] && kq < a.out_frames) {
+                    const float* hq = s_hq + q * a.wmax * kG;
+                    const int base = lane * a.D + s_gs[q];
+                    if (CH == 2) {
+                        const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
+                        for (int m = 0; m < a.wmax; m++) {
+                            const float2 x = x2[m];
+                            const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
+                            const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
+                            acc[0][0] = __fmaf_rn(x.x, h0.x, acc[0][0]); acc[0][CH - 1] = __fmaf_rn(x.y, h0.x, acc[0][CH - 1]);
+                            acc[1][0] = __fmaf_rn(x.x, h0.y, acc[1][0]); acc[1][CH - 1] = __fmaf_rn(x.y, h0.y, acc[1][CH - 1]);
+                            acc[2][0] = __fmaf_rn(x.x, h0.z, acc[2][0]); acc[2][CH - 1] = __fmaf_rn(x.y, h0.z, acc[2][CH - 1]);
+                            acc[3][0] = __fmaf_rn(x.x, h0.w, acc[3][0]); acc[3][CH - 1] = __fmaf_rn(x.y, h0.w, acc[3][CH - 1]);
+                            acc[4][0] = __fmaf_rn(x.x, h1.x, acc[4][0]); acc[4][CH - 1] = __fmaf_rn(x.y, h1.x, acc[4][CH - 1]);
+                            acc[5][0] = __fmaf_rn(x.x, h1.y, acc[5][0]); acc[5][CH - 1] = __fmaf_rn(x.y, h1.y, acc[5][CH - 1]);
+                            acc[6][0] = __fmaf_rn(x.x, h1.z, acc[6][0]); acc[6][CH - 1] = __fmaf_rn(x.y, h1.z, acc[6][CH - 1]);
+                            acc[7][0] = __fmaf_rn(x.x, h1.w, acc[7][0]); acc[7][CH - 1] = __fmaf_rn(x.y, h1.w, acc[7][CH - 1]);
+                        }
+                    } else {
+                        const float* x1 = s_in + base;
+                        for (int m = 0; m < a.wmax; m++) {
+                            const float x = x1[m];
+                            const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
+                            const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
+                            acc[0][0] = __fmaf_rn(x, h0.x, acc[0][0]); acc[1][0] = __fmaf_rn(x, h0.y, acc[1][0]);
+                            acc[2][0] = __fmaf_rn(x, h0.z, acc[2][0]); acc[3][0] = __fmaf_rn(x, h0.w, acc[3][0]);
+                            acc[4][0] = __fmaf_rn(x, h1.x, acc[4][0]); acc[5][0] = __fmaf_rn(x, h1.y, acc[5][0]);
+                            acc[6][0] = __fmaf_rn(x, h1.z, acc[6][0]); acc[7][0] = __fmaf_rn(x, h1.w, acc[7][0]);
+                        }
+                    }
+                }
+                // accumulate into the staging rows in input order: temp += data * volume (audio-amix.cpp:300-304)
+                float* rl = s_out_l + lane * a.out_stride + q * kG;
+                float* rr = s_out_r + lane * a.out_stride + q * kG;
+#pragma unroll
+                for (int g = 0; g < kG; g++) {
+                    if (q * kG + g >= a.P) break;
+                    const bool live = (kq + g) < a.out_len[inp];
+                    float vl = live ? acc[g][0] : 0.f;
+                    float vr = live ? acc[g][CH - 1] : 0.f;
+                    if (a.mix) {
+                        const float pl = inp ? rl[g] : 0.f, pr = inp ? rr[g] : 0.f;
+                        vl = __fadd_rn(pl, __fmul_rn(vl, vol));
+                        vr = __fadd_rn(pr, __fmul_rn(vr, vol));
+                    }
+                    rl[g] = vl;
+                    rr[g] = vr;
+                }
+            }
+        }
+        __syncthreads();
+        // coalesced copy-out of the tile (rows are NB periods of P frames)
+        const long long remain = a.out_frames - k0;
+        const int n_out = (int)(remain < (long long)kNB * a.P ? remain : (long long)kNB * a.P);
+        for (int i = tid; i < n_out; i += nthr) {
+            const int b = i / a.P, t = i - b * a.P;
+            out_l[k0 + i] = s_out_l[b * a.out_stride + t];
+            out_r[k0 + i] = s_out_r[b * a.out_stride + t];
+        }
+    }
+}
+
+static int upload(const void* host, size_t bytes, void** dev)
+{
+    NODEY_CUDA_OK(cudaMalloc(dev, bytes));
+    NODEY_CUDA_OK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return NODEY_OK;
+}
+
+static int64_t plan_pos_index(const nodey_resampler* r, int64_t k)
+{
+    const int64_t f = k * (int64_t)r->dst_incr_mod;
+    return (int64_t)r->index0 + k * (int64_t)r->dst_incr_div + f / r->src_incr;
+}
+
+// outputs available from n real frames plus `reflect` reflected ones
+static int64_t plan_producible(const nodey_resampler* r, int64_t n, int64_t reflect)
+{
+    const int64_t L = r->filter_length, P = r->phase_count, center = (L - 1) / 2;
+    if (n < L + 1) return 0;
+    const int64_t max_s = n + reflect - L + center;
+    if (max_s < 0) return 0;
+    int64_t lo = 0, hi = (max_s + 2) * P / (r->dst_incr_div > 0 ? r->dst_incr_div : 1) + 4;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (plan_pos_index(r, mid) / P <= max_s) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+static int64_t plan_reflect(const nodey_resampler* r, int64_t n, int64_t produced)
+{
+    if (n < r->filter_length + 1) return 0;
+    const int64_t wstart = plan_pos_index(r, produced) / r->phase_count - (r->filter_length - 1) / 2;
+    int64_t held = n - wstart;
+    if (held > r->filter_length) held = r->filter_length;
+    if (held < 0) held = 0;
+    return (held + 1) / 2;
+}
+
+}  // namespace nodey
+
+using namespace nodey;
+
+extern "C" {
+
+int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int index_mask_quirk)
+{
+    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_resampler_create: null out pointer");
+    NODEY_REQUIRE(in_rate > 0 && out_rate > 0, NODEY_E_INVALID, "nodey_resampler_create: bad sample rate");
+    nodey_resampler* r = new nodey_resampler();
+    r->in_rate = in_rate; r->out_rate = out_rate;
+    r->resample = in_rate != out_rate;
+    cudaGetDevice(&r->device);
+    if (!r->resample) {
+        r->phase_count = 1; r->filter_length = 1; r->filter_alloc = 8;
+        r->src_incr = r->dst_incr = 1; r->dst_incr_div = 1; r->dst_incr_mod = 0; r->index0 = 0;
+        *out = r;
+        return NODEY_OK;
+    }
+    // resample_init() with the library defaults the reference leaves untouched
+    double factor = (double)out_rate * 0.97 / in_rate;
+    if (factor > 1.0) factor = 1.0;
+    int phase_count = 1 << 10;
+    int filter_length = (int)ceil(32 / factor);
+    if (filter_length < 1) filter_length = 1;
+    if (filter_length > 1) filter_length = (filter_length + 1) & ~1;
+    {
+        const int64_t g = gcd64(out_rate, in_rate);
+        const int64_t exact = out_rate / g;
+        if (exact <= phase_count) phase_count = (int)exact;
+    }
+    r->phase_count = phase_count;
+    r->filter_length = filter_length;
+    r->filter_alloc = (filter_length + 7) & ~7;
+    r->bank.assign((size_t)r->filter_alloc * (size_t)(phase_count + 1), 0.f);
+    build_filter(r->bank.data(), factor, filter_length, r->filter_alloc, phase_count, 9.0);
+    memcpy(r->bank.data() + (size_t)r->filter_alloc * phase_count + 1, r->bank.data(), sizeof(float) * (size_t)(r->filter_alloc - 1));
+    r->bank[(size_t)r->filter_alloc * phase_count] = r->bank[(size_t)r->filter_alloc - 1];
+    {
+        int64_t num = out_rate, den = (int64_t)in_rate * phase_count;
+        const int64_t g = gcd64(num, den);
+        num /= g; den /= g;
+        while (den < (1 << 20) && num < (1 << 20)) { den *= 2; num *= 2; }
+        r->src_incr = (int)num; r->dst_incr = (int)den;
+    }
+    r->dst_incr_div = r->dst_incr / r->src_incr;
+    r->dst_incr_mod = r->dst_incr % r->src_incr;
+    {
+        const int idx = -phase_count * ((filter_length - 1) / 2);
+        r->index0 = index_mask_quirk ? (idx & (phase_count - 1)) : 0;
+    }
+    int rc = upload(r->bank.data(), r->bank.size() * sizeof(float), (void**)&r->d_bank);
+    if (rc != NODEY_OK) { delete r; return rc; }
+
+    // tile-kernel tables: only for exact plans (no inter-phase interpolation)
+    if (r->dst_incr_mod == 0 && phase_count <= 1024 && filter_length <= 256) {
+        const int P = phase_count, D = r->dst_incr_div, L = filter_length;
+        std::vector<int> s_t((size_t)P), ph_t((size_t)P);
+        for (int t = 0; t < P; t++) {
+            const int64_t pos = (int64_t)r->index0 + (int64_t)t * D;
+            s_t[(size_t)t] = (int)(pos / P);
+            ph_t[(size_t)t] = (int)(pos % P);
+        }
+        r->n_groups = (P + kG - 1) / kG;
+        r->s0 = s_t[0];
+        r->span = s_t[(size_t)P - 1] - s_t[0];
+        int wmax = 0;
+        std::vector<int> gs((size_t)r->n_groups);
+        for (int q = 0; q < r->n_groups; q++) {
+            const int t0 = q * kG, t1 = (t0 + kG - 1 < P ? t0 + kG - 1 : P - 1);
+            const int w = s_t[(size_t)t1] - s_t[(size_t)t0] + L;
+            if (w > wmax) wmax = w;
+            gs[(size_t)q] = s_t[(size_t)t0] - s_t[0];
+        }
+        r->wmax = wmax;
+        std::vector<float> hq((size_t)r->n_groups * (size_t)wmax * kG, 0.f);
+        for (int q = 0; q < r->n_groups; q++)
+            for (int g = 0; g < kG; g++) {
+                const int t = q * kG + g;
+                if (t >= P) break;
+                const int shift = s_t[(size_t)t] - s_t[(size_t)(q * kG)];
+                for (int i = 0; i < L; i++)
+                    hq[((size_t)q * (size_t)wmax + (size_t)(shift + i)) * kG + (size_t)g] =
+                        r->bank[(size_t)r->filter_alloc * (size_t)ph_t[(size_t)t] + (size_t)i];
+            }
+        rc = upload(hq.data(), hq.size() * sizeof(float), (void**)&r->d_hq);
+        if (rc == NODEY_OK) rc = upload(gs.data(), gs.size() * sizeof(int), (void**)&r->d_group_start);
+        if (rc != NODEY_OK) { nodey_resampler_destroy(r); return rc; }
+        r->tile_ok = 1;
+    }
+    *out = r;
+    return NODEY_OK;
+}
+
+void nodey_resampler_destroy(nodey_resampler* r)
+{
+    if (!r) return;
+    if (r->d_bank) cudaFree(r->d_bank);
+    if (r->d_hq) cudaFree(r->d_hq);
+    if (r->d_group_start) cudaFree(r->d_group_start);
+    delete r;
+}
+
+int nodey_resampler_info(const nodey_resampler* r, int info[8])
+{
+    NODEY_REQUIRE(r && info, NODEY_E_INVALID, "nodey_resampler_info: null argument");
+    info[0] = r->phase_count; info[1] = r->filter_length; info[2] = r->filter_alloc;
+    info[3] = r->dst_incr_div; info[4] = r->dst_incr_mod; info[5] = r->src_incr;
+    info[6] = r->index0; info[7] = r->resample && r->dst_incr_mod != 0;
+    return NODEY_OK;
+}
+
+const float* nodey_resampler_filter_bank(const nodey_resampler* r) { return r && r->resample ? r->bank.data() : nullptr; }
+
+int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, int flush)
+{
+    if (!r || in_frames < 0) return NODEY_E_INVALID;
+    if (!r->resample) return in_frames;
+    int64_t n = plan_producible(r, in_frames, 0);
+    if (flush) n = plan_producible(r, in_frames, plan_reflect(r, in_frames, n));
+    return n;
+}
+
+static int fill_src(SrcDesc* s, const nodey_resampler* r, const void* p0, const void* p1, int fmt, int nch,
+                    int64_t in_frames, int flush)
+{
+    NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "Invalid channel layout: %d", nch);
+    NODEY_REQUIRE(fmt_bytes(fmt) != 0, NODEY_E_FORMAT, "resampler: unsupported sample format %d", fmt);
+    NODEY_REQUIRE(in_frames >= 0, NODEY_E_INVALID, "resampler: negative input size");
+    s->p0 = p0; s->p1 = p1; s->n = in_frames; s->fmt = fmt; s->nch = nch; s->planar = fmt_planar(fmt) ? 1 : 0;
+    s->reflect = 0;
+    if (flush && r->resample) s->reflect = plan_reflect(r, in_frames, plan_producible(r, in_frames, 0));
+    return NODEY_OK;
+}
+
+static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, int ch, cudaStream_t st)
+{
+    a.hq = r->d_hq; a.group_start = r->d_group_start;
+    a.P = r->phase_count; a.D = r->dst_incr_div; a.L = r->filter_length; a.center = (r->filter_length - 1) / 2;
+    a.n_groups = r->n_groups; a.wmax = r->wmax; a.s0 = r->s0; a.span = r->span;
+    a.in_tile = (kNB - 1) * a.D + a.span + a.wmax + 1;
+    a.out_stride = (a.n_groups * kG) | 1;
+    a.n_tiles = (a.out_frames + (int64_t)kNB * a.P - 1) / ((int64_t)kNB * a.P);
+    const size_t smem = sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) +
+                                         2 * (size_t)kNB * a.out_stride + (size_t)a.in_tile * ch + 4);
+    NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
+    int threads = 32 * (a.n_groups < 20 ? a.n_groups : 20);
+    const int ctas_per_sm = smem > 113 * 1024 ? 1 : 2;
+    int grid = (int)(a.n_tiles < (int64_t)sm_count() * ctas_per_sm ? a.n_tiles : (int64_t)sm_count() * ctas_per_sm);
+    if (grid < 1) grid = 1;
+    if (ch == 2) {
+        NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_tile_kernel<2><<<grid, threads, smem, st>>>(out_l, out_r, a);
+    } else {
+        NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        resample_tile_kernel<1><<<grid, threads, smem, st>>>(out_l, out_r, a);
+    }
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+// mode: 0 auto, 1 force generic, 2 force tile (testing hook, not in the public header)
+int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_r, const void* p0, const void* p1,
+                             int fmt, int nch, int64_t in_frames, int flush, int64_t out_frames, int mode,
+                             nodey_stream_t stream)
+{
+    NODEY_REQUIRE(r && out_l && out_r, NODEY_E_INVALID, "nodey_resampler_run: null argument");
+    cudaStream_t st = as_stream(stream);
+    if (!r->resample) {
+        NODEY_REQUIRE(out_frames <= in_frames, NODEY_E_RANGE, "nodey_resampler_run: out_frames exceeds input");
+        return nodey_to_fltp_stereo(out_l, out_r, p0, p1, fmt, nch, out_frames, stream);
+    }
+    const int64_t avail = nodey_resampler_out_count(r, in_frames, flush);
+    NODEY_REQUIRE(out_frames >= 0 && out_frames <= avail, NODEY_E_RANGE,
+                  "nodey_resampler_run: out_frames %lld exceeds what swr would produce (%lld)", (long long)out_frames, (long long)avail);
+    if (out_frames == 0) return NODEY_OK;
+    if ((mode == 0 && r->tile_ok) || mode == 2) {
+        NODEY_REQUIRE(r->tile_ok, NODEY_E_RANGE, "tile kernel unavailable for this plan");
+        TileArgs a;
+        memset(&a, 0, sizeof(a));
+        int rc = fill_src(&a.src[0], r, p0, p1, fmt, nch, in_frames, flush);
+        if (rc != NODEY_OK) return rc;
+        a.out_len[0] = out_frames; a.vol[0] = 1.f; a.nin = 1; a.mix = 0; a.out_frames = out_frames;
+        return launch_tile(r, out_l, out_r, a, nch, st);
+    }
+    SrcDesc s;
+    int rc = fill_src(&s, r, p0, p1, fmt, nch, in_frames, flush);
+    if (rc != NODEY_OK) return rc;
+    PlanDev pl{r->d_bank, r->phase_count, r->filter_length, r->filter_alloc, r->dst_incr_div, r->dst_incr_mod, r->src_incr, r->index0};
+    resample_generic_kernel<<<stream_grid(out_frames, 256, 8), 256, 0, st>>>(out_l, out_r, s, pl, out_frames);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_resampler_run(const nodey_resampler* r, float* out_l, float* out_r, const void* p0, const void* p1, int fmt,
+                        int nch, int64_t in_frames, int flush, int64_t out_frames, nodey_stream_t stream)
+{
+    return nodey_resampler_run_mode(r, out_l, out_r, p0, p1, fmt, nch, in_frames, flush, out_frames, 0, stream);
+}
+
+int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r, const void* const* plane0,
+                       const void* const* plane1, const int* fmt, const int* nch, const int64_t* in_frames,
+                       const int64_t* out_len, const float* volumes, int nin, int flush, int64_t out_frames,
+                       nodey_stream_t stream)
+{
+    NODEY_REQUIRE(r && out_l && out_r, NODEY_E_INVALID, "nodey_resample_mix: null argument");
+    NODEY_REQUIRE(nin >= 1 && nin <= NODEY_MAX_MIX_INPUTS, NODEY_E_RANGE, "nodey_resample_mix: input_num %d outside 1..16", nin);
+    NODEY_REQUIRE(r->resample && r->tile_ok, NODEY_E_RANGE, "nodey_resample_mix: plan has no tile kernel (use nodey_resampler_run + nodey_mix)");
+    if (out_frames <= 0) return out_frames == 0 ? NODEY_OK : NODEY_E_INVALID;
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    int ch = nch[0];
+    for (int i = 0; i < nin; i++) {
+        NODEY_REQUIRE(nch[i] == ch, NODEY_E_INVALID, "nodey_resample_mix: inputs must share a channel count");
+        int rc = fill_src(&a.src[i], r, plane0[i], plane1 ? plane1[i] : nullptr, fmt[i], nch[i], in_frames[i], flush);
+        if (rc != NODEY_OK) return rc;
+        const int64_t avail = nodey_resampler_out_count(r, in_frames[i], flush);
+        NODEY_REQUIRE(out_len[i] >= 0 && out_len[i] <= avail, NODEY_E_RANGE,
+                      "nodey_resample_mix: out_len[%d]=%lld exceeds what swr would produce (%lld)", i, (long long)out_len[i], (long long)avail);
+        a.out_len[i] = out_len[i];
+        a.vol[i] = volumes[i];
+    }
+    a.nin = nin; a.mix = 1; a.out_frames = out_frames;
+    return launch_tile(r, out_l, out_r, a, ch, as_stream(stream));
+}
+
+}  // extern "C"

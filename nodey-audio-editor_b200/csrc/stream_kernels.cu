@@ -1,0 +1,582 @@
+// stream_kernels.cu -- the HBM-bound streaming nodes: gain (A3), sample extraction (A8), channel
+// split (N1), swr format conversion / rematrix, N-input mix (A4), stereo merges (A5, A6) and the
+// synthetic source.  One pass over the data, 128-bit accesses, grid = resident CTAs x SM count
+// with a grid-stride loop.  Arithmetic is spelled with *_rn intrinsics so the rounding sequence
+// is exactly the reference's (separate multiply and add, IEEE division).
+#include "nodey_common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+namespace nodey {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorName(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return NODEY_E_NOMEM;
+    return NODEY_E_CUDA;
+}
+
+int sm_count()
+{
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached = n;
+    return n;
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+constexpr int kBlock = 256;
+constexpr int kCtasPerSm = 8;
+
+// ------------------------------------------------------------------------------------------------
+// gain
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) gain_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                          int64_t n, float v, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec ? n / 4 : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        float4 x = ld_stream4(reinterpret_cast<const float4*>(src) + i);
+        x.x = __fmul_rn(x.x, v); x.y = __fmul_rn(x.y, v); x.z = __fmul_rn(x.z, v); x.w = __fmul_rn(x.w, v);
+        st_stream4(reinterpret_cast<float4*>(dst) + i, x);
+    }
+    for (int64_t i = nvec * 4 + tid; i < n; i += stride) dst[i] = __fmul_rn(src[i], v);
+}
+
+__device__ __forceinline__ short gain_s16_one(short s, float v)
+{
+    return (short)(unsigned short)(unsigned)x86_trunc(__fmul_rn((float)s, v));
+}
+
+__global__ void __launch_bounds__(kBlock) gain_s16_kernel(short* __restrict__ dst, const short* __restrict__ src,
+                                                          int64_t n, float v, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec ? n / 8 : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        int4 x = ld_stream4i(reinterpret_cast<const int4*>(src) + i);
+        int* w = reinterpret_cast<int*>(&x);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const short lo = (short)(w[k] & 0xffff), hi = (short)((unsigned)w[k] >> 16);
+            const unsigned rl = (unsigned short)gain_s16_one(lo, v), rh = (unsigned short)gain_s16_one(hi, v);
+            w[k] = (int)(rl | (rh << 16));
+        }
+        st_stream4i(reinterpret_cast<int4*>(dst) + i, x);
+    }
+    for (int64_t i = nvec * 8 + tid; i < n; i += stride) dst[i] = gain_s16_one(src[i], v);
+}
+
+__global__ void __launch_bounds__(kBlock) gain_s32_kernel(int* __restrict__ dst, const int* __restrict__ src,
+                                                          int64_t n, float v, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = vec ? n / 4 : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        int4 x = ld_stream4i(reinterpret_cast<const int4*>(src) + i);
+        x.x = x86_trunc(__fmul_rn((float)x.x, v)); x.y = x86_trunc(__fmul_rn((float)x.y, v));
+        x.z = x86_trunc(__fmul_rn((float)x.z, v)); x.w = x86_trunc(__fmul_rn((float)x.w, v));
+        st_stream4i(reinterpret_cast<int4*>(dst) + i, x);
+    }
+    for (int64_t i = nvec * 4 + tid; i < n; i += stride) dst[i] = x86_trunc(__fmul_rn((float)src[i], v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample extraction -> interleaved float (A8).  One thread = 4 frames.
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ float extract_one(const void* p, int64_t i)
+{
+    if (FMT == NODEY_FMT_S16) return __fdiv_rn((float)((const short*)p)[i], 32768.0f);
+    if (FMT == NODEY_FMT_S16P) return __fdiv_rn((float)((const short*)p)[i], 32767.0f);
+    if (FMT == NODEY_FMT_S32) return __fdiv_rn((float)((const int*)p)[i], 2147483648.0f);
+    if (FMT == NODEY_FMT_S32P) return __double2float_rn(__ddiv_rn((double)((const int*)p)[i], 2147483647.0));
+    return ((const float*)p)[i];
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kBlock) extract_packed_kernel(float* __restrict__ dst, const void* __restrict__ src, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = extract_one<FMT>(src, i);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kBlock) extract_planar_kernel(float* __restrict__ dst, const void* __restrict__ p0,
+                                                                const void* __restrict__ p1, int64_t nframes, int nch)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nframes; i += stride) {
+        if (nch == 2) {
+            float2 v;
+            v.x = extract_one<FMT>(p0, i);
+            v.y = extract_one<FMT>(p1, i);
+            reinterpret_cast<float2*>(dst)[i] = v;
+        } else {
+            dst[i] = extract_one<FMT>(p0, i);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// split (N1): packed stereo -> two planes, by 32-bit or 16-bit word
+// ------------------------------------------------------------------------------------------------
+template <typename W>
+__global__ void __launch_bounds__(kBlock) split_kernel(W* __restrict__ l, W* __restrict__ r, const W* __restrict__ src, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        l[i] = src[2 * i];
+        r[i] = src[2 * i + 1];
+    }
+}
+
+// 4 frames per thread, 2x128-bit loads -> 2x128-bit stores (32-bit samples)
+__global__ void __launch_bounds__(kBlock) split32_vec_kernel(int* __restrict__ l, int* __restrict__ r, const int* __restrict__ src, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = n / 4;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        const int4 a = ld_stream4i(reinterpret_cast<const int4*>(src) + 2 * i);
+        const int4 b = ld_stream4i(reinterpret_cast<const int4*>(src) + 2 * i + 1);
+        st_stream4i(reinterpret_cast<int4*>(l) + i, make_int4(a.x, a.z, b.x, b.z));
+        st_stream4i(reinterpret_cast<int4*>(r) + i, make_int4(a.y, a.w, b.y, b.w));
+    }
+    for (int64_t i = nvec * 4 + tid; i < n; i += stride) { l[i] = src[2 * i]; r[i] = src[2 * i + 1]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// swr audioconvert + rematrix, no rate change
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float swr_in_sample(const void* p, int fmt, int64_t i)
+{
+    switch (fmt) {
+    case NODEY_FMT_S16: case NODEY_FMT_S16P: return __fmul_rn((float)((const short*)p)[i], 3.0517578125e-05f);
+    case NODEY_FMT_S32: case NODEY_FMT_S32P: return __fmul_rn((float)((const int*)p)[i], 4.656612873077393e-10f);
+    default: return ((const float*)p)[i];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) to_fltp_kernel(float* __restrict__ dl, float* __restrict__ dr,
+                                                         const void* __restrict__ p0, const void* __restrict__ p1,
+                                                         int fmt, int planar, int nch, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (nch == 1) {
+            const float m = __fmul_rn(swr_in_sample(p0, fmt, i), 0.70710678118654752440f);
+            dl[i] = m; dr[i] = m;
+        } else if (planar) {
+            dl[i] = swr_in_sample(p0, fmt, i);
+            dr[i] = swr_in_sample(p1, fmt, i);
+        } else {
+            dl[i] = swr_in_sample(p0, fmt, 2 * i);
+            dr[i] = swr_in_sample(p0, fmt, 2 * i + 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// N-input mix (A4): 4 frames per thread and channel, inputs walked in order
+// ------------------------------------------------------------------------------------------------
+struct MixArgs {
+    const float* l[NODEY_MAX_MIX_INPUTS];
+    const float* r[NODEY_MAX_MIX_INPUTS];
+    long long len[NODEY_MAX_MIX_INPUTS];
+    float vol[NODEY_MAX_MIX_INPUTS];
+    int nin;
+    int vec;
+};
+
+__device__ __forceinline__ float4 load4_zero_tail(const float* p, int64_t j, int64_t len, int vec)
+{
+    if (vec && j + 4 <= len) return ld_stream4(reinterpret_cast<const float4*>(p + j));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < len) v.x = p[j];
+    if (j + 1 < len) v.y = p[j + 1];
+    if (j + 2 < len) v.z = p[j + 2];
+    if (j + 3 < len) v.w = p[j + 3];
+    return v;
+}
+
+__device__ __forceinline__ void store4_tail(float* p, int64_t j, int64_t n, float4 v, int vec)
+{
+    if (vec && j + 4 <= n) { st_stream4(reinterpret_cast<float4*>(p + j), v); return; }
+    if (j < n) p[j] = v.x;
+    if (j + 1 < n) p[j + 1] = v.y;
+    if (j + 2 < n) p[j + 2] = v.z;
+    if (j + 3 < n) p[j + 3] = v.w;
+}
+
+__device__ __forceinline__ float4 mac4(float4 acc, float4 x, float v)
+{
+    acc.x = __fadd_rn(acc.x, __fmul_rn(x.x, v));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(x.y, v));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(x.z, v));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(x.w, v));
+    return acc;
+}
+
+__global__ void __launch_bounds__(kBlock) mix_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                     const __grid_constant__ MixArgs a, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t npack = (n + 3) / 4;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npack; pk += stride) {
+        const int64_t j = pk * 4;
+        float4 tl = make_float4(0.f, 0.f, 0.f, 0.f), tr = tl;
+        for (int i = 0; i < a.nin; i++) {
+            const float4 xl = load4_zero_tail(a.l[i], j, a.len[i], a.vec);
+            const float4 xr = load4_zero_tail(a.r[i], j, a.len[i], a.vec);
+            tl = mac4(tl, xl, a.vol[i]);
+            tr = mac4(tr, xr, a.vol[i]);
+        }
+        store4_tail(out_l, j, n, tl, a.vec);
+        store4_tail(out_r, j, n, tr, a.vec);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bimix v1 (A5)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bimix_one(float a, float b, float k)
+{
+    return __fmul_rn(__fadd_rn(__fdiv_rn(a, 2.0f), __fdiv_rn(b, 2.0f)), k);
+}
+
+__global__ void __launch_bounds__(kBlock) bimix_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                       const float* __restrict__ ll, const float* __restrict__ lr, int64_t len_l,
+                                                       const float* __restrict__ rl, const float* __restrict__ rr, int64_t len_r,
+                                                       float bias_minus, float bias_plus, int64_t n, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t npack = (n + 3) / 4;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npack; pk += stride) {
+        const int64_t j = pk * 4;
+        const float4 a = load4_zero_tail(ll, j, len_l, vec), b = load4_zero_tail(lr, j, len_l, vec);
+        const float4 c = load4_zero_tail(rl, j, len_r, vec), d = load4_zero_tail(rr, j, len_r, vec);
+        float4 ol, orr;
+        ol.x = bimix_one(a.x, b.x, bias_minus); ol.y = bimix_one(a.y, b.y, bias_minus);
+        ol.z = bimix_one(a.z, b.z, bias_minus); ol.w = bimix_one(a.w, b.w, bias_minus);
+        orr.x = bimix_one(c.x, d.x, bias_plus); orr.y = bimix_one(c.y, d.y, bias_plus);
+        orr.z = bimix_one(c.z, d.z, bias_plus); orr.w = bimix_one(c.w, d.w, bias_plus);
+        store4_tail(out_l, j, n, ol, vec);
+        store4_tail(out_r, j, n, orr, vec);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bimix v2 pieces (A6)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) downmix_half_kernel(float* __restrict__ dst, const float* __restrict__ l,
+                                                              const float* __restrict__ r, int64_t n, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t npack = (n + 3) / 4;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npack; pk += stride) {
+        const int64_t j = pk * 4;
+        const float4 a = load4_zero_tail(l, j, n, vec), b = load4_zero_tail(r, j, n, vec);
+        float4 o;
+        o.x = __fmul_rn(__fadd_rn(a.x, b.x), 0.5f); o.y = __fmul_rn(__fadd_rn(a.y, b.y), 0.5f);
+        o.z = __fmul_rn(__fadd_rn(a.z, b.z), 0.5f); o.w = __fmul_rn(__fadd_rn(a.w, b.w), 0.5f);
+        store4_tail(dst, j, n, o, vec);
+    }
+}
+
+struct MergeSeg { long long out_start, len, l, r; };
+
+__global__ void __launch_bounds__(kBlock) merge_segments_kernel(float2* __restrict__ out, const float* __restrict__ left,
+                                                                const float* __restrict__ right,
+                                                                const MergeSeg* __restrict__ segs, int nseg, int64_t total)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+        int lo = 0, hi = nseg - 1;       // last segment with out_start <= j
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (segs[mid].out_start <= j) lo = mid; else hi = mid - 1;
+        }
+        const MergeSeg s = segs[lo];
+        const int64_t d = j - s.out_start;
+        float2 v;
+        v.x = s.l >= 0 ? left[s.l + d] : 0.0f;
+        v.y = s.r >= 0 ? right[s.r + d] : 0.0f;
+        out[j] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic source (bit-identical to oracle/nodey_oracle.c orc_synth_f32)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned synth_hash(unsigned seed, unsigned long long n)
+{
+    unsigned long long z = n + ((unsigned long long)seed << 32) + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (unsigned)(z >> 32);
+}
+
+__device__ __forceinline__ float synth_sin_turns(float t)
+{
+    if (t > 0.25f) t = __fsub_rn(0.5f, t);
+    else if (t < -0.25f) t = __fsub_rn(-0.5f, t);
+    const float y = __fmul_rn(6.28318530717958647692f, t);
+    const float y2 = __fmul_rn(y, y);
+    float p = 2.7557319e-6f;
+    p = __fmaf_rn(p, y2, -1.9841270e-4f);
+    p = __fmaf_rn(p, y2, 8.3333333e-3f);
+    p = __fmaf_rn(p, y2, -1.6666667e-1f);
+    p = __fmaf_rn(p, y2, 1.0f);
+    return __fmul_rn(y, p);
+}
+
+__global__ void __launch_bounds__(kBlock) synth_kernel(float* __restrict__ f32, short* __restrict__ s16, int64_t nframes,
+                                                       int nch, unsigned step0, unsigned step1, unsigned seed0, int64_t frame0)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = nframes * nch;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int c = (int)(e % nch);
+        const unsigned long long n = (unsigned long long)(frame0 + e / nch);
+        const unsigned step = c ? step1 : step0;
+        const unsigned ph = (unsigned)(n * (unsigned long long)step);
+        const float t = __fmul_rn(__int2float_rn((int)ph), 2.3283064365386963e-10f);
+        const float s = synth_sin_turns(t);
+        const float u = __fsub_rn(__fmul_rn(__uint2float_rn(synth_hash(seed0 + (unsigned)c, n) >> 8), 1.1920928955078125e-7f), 1.0f);
+        const float x = __fmaf_rn(0.05f, u, __fmul_rn(0.5f, s));
+        if (f32) f32[e] = x;
+        if (s16) {
+            int v = __float2int_rn(__fmul_rn(x, 32767.0f));
+            v = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+            s16[e] = (short)v;
+        }
+    }
+}
+
+}  // namespace nodey
+
+using namespace nodey;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int nodey_version(void) { return 100; }
+
+const char* nodey_last_error(void) { return g_err; }
+
+int nodey_device_info(int* sms, int* major, int* minor, int64_t* total_mem)
+{
+    int dev = 0;
+    NODEY_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    NODEY_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sms) *sms = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+    return NODEY_OK;
+}
+
+int nodey_synth(float* dst_f32, int16_t* dst_s16, int64_t nframes, int nch, int sample_rate, int track,
+                int64_t frame0, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "nodey_synth: nch must be 1 or 2 (got %d)", nch);
+    NODEY_REQUIRE(sample_rate > 0 && nframes >= 0, NODEY_E_INVALID, "nodey_synth: bad size");
+    if (nframes == 0) return NODEY_OK;
+    unsigned step[2];
+    for (int c = 0; c < 2; c++) {
+        const int e = (7 * track + 4 * c) % 36;
+        const double f = 220.0 * pow(2.0, (double)e / 12.0);
+        step[c] = (unsigned)llrint(f / (double)sample_rate * 4294967296.0);
+    }
+    const unsigned seed0 = 0xA0D10u + 131u * (unsigned)track;
+    synth_kernel<<<stream_grid(nframes * nch, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
+        dst_f32, dst_s16, nframes, nch, step[0], step[1], seed0, frame0);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_gain(void* dst, const void* src, int fmt, int64_t n, float volume, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(n >= 0 && (n == 0 || (dst && src)), NODEY_E_INVALID, "nodey_gain: null buffer or negative size");
+    if (n == 0) return NODEY_OK;
+    const int vec = aligned16(dst) && aligned16(src);
+    cudaStream_t st = as_stream(stream);
+    switch (fmt) {
+    case NODEY_FMT_FLT: case NODEY_FMT_FLTP:
+        gain_f32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((float*)dst, (const float*)src, n, volume, vec);
+        break;
+    case NODEY_FMT_S16: case NODEY_FMT_S16P:
+        gain_s16_kernel<<<stream_grid(n / 8 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dst, (const short*)src, n, volume, vec);
+        break;
+    case NODEY_FMT_S32: case NODEY_FMT_S32P:
+        gain_s32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dst, (const int*)src, n, volume, vec);
+        break;
+    default:
+        set_error("Audio format is not support (Include FLT, S16, S32): %d", fmt);
+        return NODEY_E_FORMAT;
+    }
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_extract_interleaved(float* dst, const void* p0, const void* p1, int fmt, int64_t nframes, int nch,
+                              nodey_stream_t stream)
+{
+    NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "nodey_extract_interleaved: nch must be 1 or 2");
+    NODEY_REQUIRE(nframes >= 0, NODEY_E_INVALID, "nodey_extract_interleaved: negative size");
+    if (nframes == 0) return NODEY_OK;
+    cudaStream_t st = as_stream(stream);
+    const int64_t n = nframes * nch;
+    const int g = stream_grid(n, kBlock, kCtasPerSm), gp = stream_grid(nframes, kBlock, kCtasPerSm);
+    switch (fmt) {
+    case NODEY_FMT_FLT:
+        NODEY_CUDA_OK(cudaMemcpyAsync(dst, p0, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+        return NODEY_OK;
+    case NODEY_FMT_S16: extract_packed_kernel<NODEY_FMT_S16><<<g, kBlock, 0, st>>>(dst, p0, n); break;
+    case NODEY_FMT_S32: extract_packed_kernel<NODEY_FMT_S32><<<g, kBlock, 0, st>>>(dst, p0, n); break;
+    case NODEY_FMT_FLTP: extract_planar_kernel<NODEY_FMT_FLTP><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
+    case NODEY_FMT_S16P: extract_planar_kernel<NODEY_FMT_S16P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
+    case NODEY_FMT_S32P: extract_planar_kernel<NODEY_FMT_S32P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
+    default:
+        set_error("Unsupported sample format: %d", fmt);
+        return NODEY_E_FORMAT;
+    }
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_split(void* dl, void* dr, const void* p0, const void* p1, int fmt, int64_t n, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(n >= 0, NODEY_E_INVALID, "nodey_split: negative size");
+    if (n == 0) return NODEY_OK;
+    cudaStream_t st = as_stream(stream);
+    switch (fmt) {
+    case NODEY_FMT_FLT: case NODEY_FMT_S32:
+        if (aligned16(dl) && aligned16(dr) && aligned16(p0))
+            split32_vec_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n);
+        else
+            split_kernel<int><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n);
+        break;
+    case NODEY_FMT_S16:
+        split_kernel<short><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dl, (short*)dr, (const short*)p0, n);
+        break;
+    case NODEY_FMT_FLTP: case NODEY_FMT_S32P: case NODEY_FMT_S16P: {
+        const size_t bytes = (size_t)n * (size_t)fmt_bytes(fmt);
+        NODEY_CUDA_OK(cudaMemcpyAsync(dl, p0, bytes, cudaMemcpyDeviceToDevice, st));
+        NODEY_CUDA_OK(cudaMemcpyAsync(dr, p1, bytes, cudaMemcpyDeviceToDevice, st));
+        return NODEY_OK;
+    }
+    default:
+        set_error("nodey_split: unsupported sample format %d", fmt);
+        return NODEY_E_FORMAT;
+    }
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_to_fltp_stereo(float* dl, float* dr, const void* p0, const void* p1, int fmt, int nch, int64_t n,
+                         nodey_stream_t stream)
+{
+    NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "Invalid channel layout: %d", nch);
+    NODEY_REQUIRE(fmt_bytes(fmt) != 0, NODEY_E_FORMAT, "nodey_to_fltp_stereo: unsupported sample format %d", fmt);
+    if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
+    to_fltp_kernel<<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dl, dr, p0, p1, fmt,
+                                                                                       fmt_planar(fmt) ? 1 : 0, nch, n);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r, const int64_t* in_len,
+              const float* volumes, int nin, int64_t n, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(nin >= 1 && nin <= NODEY_MAX_MIX_INPUTS, NODEY_E_RANGE, "nodey_mix: input_num %d outside 1..16", nin);
+    if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
+    MixArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nin = nin;
+    a.vec = aligned16(out_l) && aligned16(out_r);
+    for (int i = 0; i < nin; i++) {
+        a.l[i] = in_l[i]; a.r[i] = in_r[i]; a.len[i] = in_len[i]; a.vol[i] = volumes[i];
+        a.vec = a.vec && aligned16(in_l[i]) && aligned16(in_r[i]);
+    }
+    mix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(out_l, out_r, a, n);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_bimix(float* out_l, float* out_r, const float* ll, const float* lr, int64_t len_l, const float* rl,
+                const float* rr, int64_t len_r, float bias, int64_t n, nodey_stream_t stream)
+{
+    if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
+    const int vec = aligned16(out_l) && aligned16(out_r) && aligned16(ll) && aligned16(lr) && aligned16(rl) && aligned16(rr);
+    const float bias_minus = 1 - bias, bias_plus = 1 + bias;
+    bimix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
+        out_l, out_r, ll, lr, len_l, rl, rr, len_r, bias_minus, bias_plus, n, vec);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_downmix_half(float* dst, const float* l, const float* r, int64_t n, nodey_stream_t stream)
+{
+    if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
+    const int vec = aligned16(dst) && aligned16(l) && aligned16(r);
+    downmix_half_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dst, l, r, n, vec);
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_merge_segments(float* out, const float* left, const float* right, const int64_t* seg_out_start,
+                         const int64_t* seg_len, const int64_t* seg_l, const int64_t* seg_r, int nseg,
+                         nodey_stream_t stream)
+{
+    NODEY_REQUIRE(nseg >= 0, NODEY_E_INVALID, "nodey_merge_segments: negative segment count");
+    if (nseg == 0) return NODEY_OK;
+    MergeSeg* h = (MergeSeg*)malloc(sizeof(MergeSeg) * (size_t)nseg);
+    NODEY_REQUIRE(h, NODEY_E_NOMEM, "nodey_merge_segments: host allocation failed");
+    int64_t total = 0;
+    for (int i = 0; i < nseg; i++) {
+        h[i].out_start = seg_out_start[i]; h[i].len = seg_len[i]; h[i].l = seg_l[i]; h[i].r = seg_r[i];
+        if (seg_out_start[i] + seg_len[i] > total) total = seg_out_start[i] + seg_len[i];
+    }
+    cudaStream_t st = as_stream(stream);
+    MergeSeg* d = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d, sizeof(MergeSeg) * (size_t)nseg, st);
+    if (e != cudaSuccess) { free(h); return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__); }
+    e = cudaMemcpyAsync(d, h, sizeof(MergeSeg) * (size_t)nseg, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // h is pageable: keep it alive until the copy landed
+    free(h);
+    if (e != cudaSuccess) { cudaFreeAsync(d, st); return cuda_fail(e, "segment upload", __FILE__, __LINE__); }
+    if (total > 0)
+        merge_segments_kernel<<<stream_grid(total, kBlock, kCtasPerSm), kBlock, 0, st>>>((float2*)out, left, right, d, nseg, total);
+    e = cudaPeekAtLastError();
+    cudaFreeAsync(d, st);
+    if (e != cudaSuccess) return cuda_fail(e, "merge_segments_kernel", __FILE__, __LINE__);
+    return NODEY_OK;
+}
+
+}  // extern "C"
