@@ -113,6 +113,11 @@ int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, i
 int nodey_resampler_run(const nodey_resampler* r, float* out_l, float* out_r,
                         const void* plane0, const void* plane1, int fmt, int nch, int64_t in_frames,
                         int flush, int64_t out_frames, nodey_stream_t stream);
+/* Test hook: as nodey_resampler_run with the kernel forced (mode 0 auto, 1 generic one-thread-per-
+ * output kernel, 2 tiled kernel; 2 fails with NODEY_E_RANGE when the plan has no tile tables). */
+int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_r,
+                             const void* plane0, const void* plane1, int fmt, int nch, int64_t in_frames,
+                             int flush, int64_t out_frames, int mode, nodey_stream_t stream);
 /* Fused A7 + A4 for inputs that share one plan (same source rate): out = sum_i vol_i * resample(in_i)
  * in input order, zeros past each input's own length.  Host arrays of nin entries. */
 int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r,
@@ -121,12 +126,35 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r,
                        const float* volumes, int nin, int flush, int64_t out_frames,
                        nodey_stream_t stream);
 
+/* A9  pitch_modifier / velocity_modifier -- soundtouch_process_payload, src/processor/audio-velocity.cpp:265-443:
+ * new SoundTouch; setSampleRate; setChannels; setRate(rate); setPitch(pitch) (:367-390), then
+ * putSamples per frame, receiveSamples, flush (:399-435).  SoundTouch 2.3.2 float build with default
+ * settings (TDStretch WSOLA, 64-tap AA filter, cubic transposer); see SURVEY.md App. B2.
+ *   Pitch_modifier   : rate 1,        pitch powf(2, semitones/12)          (:462-477)
+ *   Velocity_modifier: rate velocity, pitch keep_pitch ? 1/velocity : 1    (:445-460)
+ * The object is the whole-track equivalent of the streaming one: `ntracks` tracks of equal length
+ * (interleaved float, track t at in + t*in_stride floats) are rendered in one call.  frame_size is
+ * the putSamples chunk (it only enters the expected-output bookkeeping of flush()).
+ * offsets (optional, device): the WSOLA offset trace, n_sequences-1 ints per track. */
+typedef struct nodey_soundtouch nodey_soundtouch;
+int nodey_soundtouch_create(nodey_soundtouch** out, int sample_rate, int channels, float rate, float pitch);
+void nodey_soundtouch_destroy(nodey_soundtouch* s);
+/* info_i[8]: overlap, seek_window, seek_length, sample_req, tdstretch_first, prefill, channels, sample_rate
+ * info_d[3]: effective rate, effective tempo, nominal_skip */
+int nodey_soundtouch_info(const nodey_soundtouch* s, int info_i[8], double info_d[3]);
+/* frames the node emits in total for in_frames of input (after flush); n_sequences optional */
+int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t* n_sequences);
+int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
+                         int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                         int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);
+
 /* N2  audio_spectrum (new node; FFTW r2c convention, unnormalised):
- * frame m = x[m*hop .. m*hop+nfft) * periodic Hann, out[m][0..nfft/2] complex64.
- * nfft must be 4096 in this release. */
+ * per channel, frame m = x[m*hop .. m*hop+nfft) * periodic Hann; out[ch][m][0..nfft/2] complex64
+ * (re, im interleaved).  interleaved != 0: sample f of channel c at x[f*nch + c]; otherwise planar
+ * with channel c at x + c*plane_stride.  nfft must be 4096 in this release. */
 int64_t nodey_stft_frames(int64_t nframes, int nfft, int hop);
-int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nfft, int hop,
-               nodey_stream_t stream);
+int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int interleaved,
+               int64_t plane_stride, int nfft, int hop, nodey_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,352 @@
+"""ctypes binding of libnodey_cuda.so -- the C ABI declared in include/nodey_cuda.h.
+
+This is the same boundary the C++ host layer (host/) calls; Python is used by tests/ and bench.py
+only.  torch supplies device memory and streams (plumbing); every computation is a kernel of
+libnodey_cuda.so.  There is NO fallback: a missing library or a failing call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnodey_cuda.so")
+
+FMT_U8, FMT_S16, FMT_S32, FMT_FLT, FMT_DBL, FMT_U8P, FMT_S16P, FMT_S32P, FMT_FLTP, FMT_DBLP = range(10)
+MAX_MIX_INPUTS = 16
+
+# every entry point include/nodey_cuda.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "nodey_version", "nodey_last_error", "nodey_device_info", "nodey_synth", "nodey_gain",
+    "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
+    "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
+    "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
+    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_stft_frames", "nodey_stft",
+    "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
+    "nodey_soundtouch_run",
+]
+
+
+class NodeyError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"nodey error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.nodey_version.restype = i32
+    L.nodey_last_error.restype = C.c_char_p
+    L.nodey_device_info.argtypes = [C.POINTER(i32)] * 3 + [C.POINTER(i64)]
+    L.nodey_synth.argtypes = [vp, vp, i64, i32, i32, i32, i64, vp]
+    L.nodey_gain.argtypes = [vp, vp, i32, i64, C.c_float, vp]
+    L.nodey_extract_interleaved.argtypes = [vp, vp, vp, i32, i64, i32, vp]
+    L.nodey_split.argtypes = [vp, vp, vp, vp, i32, i64, vp]
+    L.nodey_to_fltp_stereo.argtypes = [vp, vp, vp, vp, i32, i32, i64, vp]
+    L.nodey_mix.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_float), i32, i64, vp]
+    L.nodey_bimix.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, C.c_float, i64, vp]
+    L.nodey_downmix_half.argtypes = [vp, vp, vp, i64, vp]
+    L.nodey_merge_segments.argtypes = [vp, vp, vp] + [C.POINTER(i64)] * 4 + [i32, vp]
+    L.nodey_resampler_create.argtypes = [C.POINTER(vp), i32, i32, i32]
+    L.nodey_resampler_destroy.argtypes = [vp]
+    L.nodey_resampler_destroy.restype = None
+    L.nodey_resampler_info.argtypes = [vp, C.POINTER(i32)]
+    L.nodey_resampler_filter_bank.argtypes = [vp]
+    L.nodey_resampler_filter_bank.restype = C.POINTER(C.c_float)
+    L.nodey_resampler_out_count.argtypes = [vp, i64, i32]
+    L.nodey_resampler_out_count.restype = i64
+    L.nodey_resampler_run.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, vp]
+    L.nodey_resampler_run_mode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, i32, vp]
+    L.nodey_resample_mix.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
+                                     C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float), i32, i32, i64, vp]
+    L.nodey_stft_frames.argtypes = [i64, i32, i32]
+    L.nodey_stft_frames.restype = i64
+    L.nodey_stft.argtypes = [vp, vp, i64, i32, i32, i64, i32, i32, vp]
+    L.nodey_soundtouch_create.argtypes = [C.POINTER(vp), i32, i32, C.c_float, C.c_float]
+    L.nodey_soundtouch_destroy.argtypes = [vp]
+    L.nodey_soundtouch_destroy.restype = None
+    L.nodey_soundtouch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_double)]
+    L.nodey_soundtouch_out_frames.argtypes = [vp, i64, i32, C.POINTER(i64)]
+    L.nodey_soundtouch_out_frames.restype = i64
+    L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NodeyError(rc, lib().nodey_last_error().decode("utf-8", "replace"))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _dp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+_TORCH_DT = {FMT_S16: "int16", FMT_S16P: "int16", FMT_S32: "int32", FMT_S32P: "int32",
+             FMT_FLT: "float32", FMT_FLTP: "float32"}
+
+
+def torch_dtype(fmt):
+    return getattr(_torch(), _TORCH_DT[fmt])
+
+
+def is_planar(fmt):
+    return fmt >= FMT_U8P
+
+
+def planes_of(x, fmt):
+    """x: packed -> tensor [frames, ch]; planar -> tensor [ch, frames] (contiguous). (p0, p1, nframes, nch)"""
+    assert x.is_contiguous()
+    if is_planar(fmt):
+        nch, n = x.shape
+        return x[0], (x[1] if nch > 1 else None), n, nch
+    n, nch = x.shape
+    return x, None, n, nch
+
+
+def device_info():
+    a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    check(lib().nodey_device_info(C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+    return {"sm_count": a.value, "cc": (b.value, c.value), "total_mem": d.value}
+
+
+def synth(nframes, nch, sample_rate, track=0, frame0=0, want_s16=False, device="cuda"):
+    t = _torch()
+    f = t.empty((nframes, nch), dtype=t.float32, device=device)
+    s = t.empty((nframes, nch), dtype=t.int16, device=device) if want_s16 else None
+    check(lib().nodey_synth(_dp(f), _dp(s), nframes, nch, sample_rate, track, frame0, _stream()))
+    return (f, s) if want_s16 else f
+
+
+def gain(src, fmt, volume, out=None):
+    t = _torch()
+    dst = t.empty_like(src) if out is None else out
+    check(lib().nodey_gain(_dp(dst), _dp(src), fmt, src.numel(), C.c_float(volume), _stream()))
+    return dst
+
+
+def extract_interleaved(x, fmt):
+    t = _torch()
+    p0, p1, n, nch = planes_of(x, fmt)
+    out = t.empty((n, nch), dtype=t.float32, device=x.device)
+    check(lib().nodey_extract_interleaved(_dp(out), _dp(p0), _dp(p1), fmt, n, nch, _stream()))
+    return out
+
+
+def split(x, fmt):
+    t = _torch()
+    p0, p1, n, nch = planes_of(x, fmt)
+    assert nch == 2
+    l = t.empty(n, dtype=x.dtype, device=x.device)
+    r = t.empty(n, dtype=x.dtype, device=x.device)
+    check(lib().nodey_split(_dp(l), _dp(r), _dp(p0), _dp(p1), fmt, n, _stream()))
+    return l, r
+
+
+def to_fltp_stereo(x, fmt):
+    t = _torch()
+    p0, p1, n, nch = planes_of(x, fmt)
+    out = t.empty((2, n), dtype=t.float32, device=x.device)
+    check(lib().nodey_to_fltp_stereo(_dp(out[0]), _dp(out[1]), _dp(p0), _dp(p1), fmt, nch, n, _stream()))
+    return out
+
+
+def mix(inputs, volumes, nframes=None):
+    """inputs: list of [2, len_i] float32 planar tensors; zeros past each input's own length."""
+    t = _torch()
+    nin = len(inputs)
+    n = max(int(x.shape[1]) for x in inputs) if nframes is None else nframes
+    out = t.empty((2, n), dtype=t.float32, device=inputs[0].device)
+    pl = (C.c_void_p * nin)(*[x[0].data_ptr() for x in inputs])
+    pr = (C.c_void_p * nin)(*[x[1].data_ptr() for x in inputs])
+    ln = (C.c_int64 * nin)(*[int(x.shape[1]) for x in inputs])
+    vol = (C.c_float * nin)(*[float(v) for v in volumes])
+    check(lib().nodey_mix(_dp(out[0]), _dp(out[1]), pl, pr, ln, vol, nin, n, _stream()))
+    return out
+
+
+def bimix(left, right, bias, nframes=None):
+    t = _torch()
+    n = max(left.shape[1], right.shape[1]) if nframes is None else nframes
+    out = t.empty((2, n), dtype=t.float32, device=left.device)
+    check(lib().nodey_bimix(_dp(out[0]), _dp(out[1]), _dp(left[0]), _dp(left[1]), left.shape[1],
+                            _dp(right[0]), _dp(right[1]), right.shape[1], C.c_float(bias), n, _stream()))
+    return out
+
+
+def downmix_half(x):
+    t = _torch()
+    out = t.empty(x.shape[1], dtype=t.float32, device=x.device)
+    check(lib().nodey_downmix_half(_dp(out), _dp(x[0]), _dp(x[1]), x.shape[1], _stream()))
+    return out
+
+
+def merge_segments(left, right, segs):
+    """segs: list of (out_start, length, l_start or -1, r_start or -1)."""
+    t = _torch()
+    total = max(s[0] + s[1] for s in segs) if segs else 0
+    out = t.empty((total, 2), dtype=t.float32, device=left.device)
+    arr = [(C.c_int64 * len(segs))(*[int(s[i]) for s in segs]) for i in range(4)]
+    check(lib().nodey_merge_segments(_dp(out), _dp(left), _dp(right), arr[0], arr[1], arr[2], arr[3], len(segs), _stream()))
+    return out
+
+
+class Resampler:
+    """A7: swr_convert with library defaults (44.1 k -> 48 k: 160 phases x 32 taps)."""
+
+    def __init__(self, in_rate, out_rate=48000, quirk=0):
+        self.h = C.c_void_p()
+        check(lib().nodey_resampler_create(C.byref(self.h), in_rate, out_rate, quirk))
+        self.in_rate, self.out_rate = in_rate, out_rate
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nodey_resampler_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def info(self):
+        a = (C.c_int * 8)()
+        check(lib().nodey_resampler_info(self.h, a))
+        keys = ["phase_count", "filter_length", "filter_alloc", "dst_incr_div", "dst_incr_mod", "src_incr",
+                "index0", "linear"]
+        return dict(zip(keys, list(a)))
+
+    def filter_bank(self):
+        p = self.info()
+        ptr = lib().nodey_resampler_filter_bank(self.h)
+        n = (p["phase_count"] + 1) * p["filter_alloc"]
+        return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(p["phase_count"] + 1, p["filter_alloc"]).copy()
+
+    def out_count(self, in_frames, flush=True):
+        return lib().nodey_resampler_out_count(self.h, in_frames, 1 if flush else 0)
+
+    def run(self, x, fmt, flush=True, out_frames=None, mode=0, out=None):
+        t = _torch()
+        p0, p1, n, nch = planes_of(x, fmt)
+        m = self.out_count(n, flush) if out_frames is None else out_frames
+        if out is None:
+            out = t.empty((2, m), dtype=t.float32, device=x.device)
+        check(lib().nodey_resampler_run_mode(self.h, _dp(out[0]), _dp(out[1]), _dp(p0), _dp(p1), fmt, nch, n,
+                                             1 if flush else 0, m, mode, _stream()))
+        return out
+
+    def resample_mix(self, inputs, fmts, volumes, flush=True, out_lens=None, out_frames=None, out=None):
+        t = _torch()
+        nin = len(inputs)
+        pls = [planes_of(x, f) for x, f in zip(inputs, fmts)]
+        lens = [self.out_count(p[2], flush) for p in pls] if out_lens is None else list(out_lens)
+        m = max(lens) if out_frames is None else out_frames
+        if out is None:
+            out = t.empty((2, m), dtype=t.float32, device=inputs[0].device)
+        p0 = (C.c_void_p * nin)(*[p[0].data_ptr() for p in pls])
+        p1 = (C.c_void_p * nin)(*[(p[1].data_ptr() if p[1] is not None else 0) for p in pls])
+        fm = (C.c_int * nin)(*fmts)
+        ch = (C.c_int * nin)(*[p[3] for p in pls])
+        inf = (C.c_int64 * nin)(*[p[2] for p in pls])
+        ol = (C.c_int64 * nin)(*lens)
+        vol = (C.c_float * nin)(*[float(v) for v in volumes])
+        check(lib().nodey_resample_mix(self.h, _dp(out[0]), _dp(out[1]), p0, p1, fm, ch, inf, ol, vol, nin,
+                                       1 if flush else 0, m, _stream()))
+        return out
+
+
+def stft_frames(n, nfft=4096, hop=1024):
+    return lib().nodey_stft_frames(n, nfft, hop)
+
+
+def stft(x, interleaved, nfft=4096, hop=1024, out=None):
+    """x: [frames, nch] (interleaved) or [nch, frames] (planar) float32 -> complex64 [nch, M, nfft/2+1]."""
+    t = _torch()
+    if interleaved:
+        n, nch = x.shape
+        stride = 0
+    else:
+        nch, n = x.shape
+        stride = x.stride(0)
+    m = stft_frames(n, nfft, hop)
+    if out is None:
+        out = t.empty((nch, m, nfft // 2 + 1), dtype=t.complex64, device=x.device)
+    check(lib().nodey_stft(_dp(out), _dp(x), n, nch, 1 if interleaved else 0, stride, nfft, hop, _stream()))
+    return out
+
+
+class SoundTouch:
+    """A9: the SoundTouch object of pitch_modifier / velocity_modifier as a whole-track batch op."""
+
+    def __init__(self, sample_rate, channels, rate=1.0, pitch=1.0):
+        self.h = C.c_void_p()
+        check(lib().nodey_soundtouch_create(C.byref(self.h), sample_rate, channels, C.c_float(rate), C.c_float(pitch)))
+        self.ch = channels
+
+    @classmethod
+    def pitch_node(cls, sample_rate, channels, semitones):
+        return cls(sample_rate, channels, 1.0, float(np.float32(2.0) ** (np.float32(semitones) / np.float32(12.0))))
+
+    @classmethod
+    def velocity_node(cls, sample_rate, channels, velocity, keep_pitch):
+        p = float(np.float32(1) / np.float32(velocity)) if keep_pitch else 1.0
+        return cls(sample_rate, channels, velocity, p)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nodey_soundtouch_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def info(self):
+        a = (C.c_int * 8)(); d = (C.c_double * 3)()
+        check(lib().nodey_soundtouch_info(self.h, a, d))
+        keys = ["overlap", "seek_window", "seek_length", "sample_req", "tdstretch_first", "prefill", "channels",
+                "sample_rate"]
+        out = dict(zip(keys, list(a)))
+        out.update(rate=d[0], tempo=d[1], nominal_skip=d[2])
+        return out
+
+    def out_frames(self, in_frames, frame_size=1152):
+        nseq = C.c_int64()
+        n = lib().nodey_soundtouch_out_frames(self.h, in_frames, frame_size, C.byref(nseq))
+        if n < 0:
+            raise NodeyError(n, "nodey_soundtouch_out_frames")
+        return n, nseq.value
+
+    def run(self, x, frame_size=1152, want_offsets=False, out=None):
+        """x: [ntracks, frames, ch] or [frames, ch] float32 (interleaved). Returns same rank."""
+        t = _torch()
+        single = x.dim() == 2
+        xb = x.unsqueeze(0) if single else x
+        assert xb.is_contiguous() and xb.shape[2] == self.ch
+        ntr, n, ch = xb.shape
+        m, nseq = self.out_frames(n, frame_size)
+        if out is None:
+            out = t.empty((ntr, m, ch), dtype=t.float32, device=x.device)
+        offs = t.zeros((ntr, max(nseq - 1, 1)), dtype=t.int32, device=x.device) if want_offsets else None
+        check(lib().nodey_soundtouch_run(self.h, _dp(out), out.stride(0), _dp(xb), xb.stride(0), ntr, n, frame_size, m,
+                                         _dp(offs), offs.stride(0) if offs is not None else 0, _stream()))
+        res = out[0] if single else out
+        if want_offsets:
+            o = offs[:, :max(nseq - 1, 0)]
+            return res, (o[0] if single else o)
+        return res

@@ -325,6 +325,17 @@ static int64_t plan_reflect(const nodey_resampler* r, int64_t n, int64_t produce
 
 using namespace nodey;
 
+static size_t tile_geometry(const nodey_resampler* r, TileArgs& a, int ch)
+{
+    a.P = r->phase_count; a.D = r->dst_incr_div; a.L = r->filter_length; a.center = (r->filter_length - 1) / 2;
+    a.n_groups = r->n_groups; a.wmax = r->wmax; a.s0 = r->s0; a.span = r->span;
+    a.in_tile = (kNB - 1) * a.D + a.span + a.wmax + 1;
+    a.out_stride = (a.n_groups * kG) | 1;
+    return sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) +
+                            2 * (size_t)kNB * a.out_stride + (size_t)a.in_tile * ch + 4);
+}
+
+
 extern "C" {
 
 int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int index_mask_quirk)
@@ -410,7 +421,8 @@ int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int
         rc = upload(hq.data(), hq.size() * sizeof(float), (void**)&r->d_hq);
         if (rc == NODEY_OK) rc = upload(gs.data(), gs.size() * sizeof(int), (void**)&r->d_group_start);
         if (rc != NODEY_OK) { nodey_resampler_destroy(r); return rc; }
-        r->tile_ok = 1;
+        TileArgs probe;
+        r->tile_ok = tile_geometry(r, probe, 2) <= 227 * 1024;   // else: generic kernel (plan too big for one SM)
     }
     *out = r;
     return NODEY_OK;
@@ -460,13 +472,8 @@ static int fill_src(SrcDesc* s, const nodey_resampler* r, const void* p0, const 
 static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, int ch, cudaStream_t st)
 {
     a.hq = r->d_hq; a.group_start = r->d_group_start;
-    a.P = r->phase_count; a.D = r->dst_incr_div; a.L = r->filter_length; a.center = (r->filter_length - 1) / 2;
-    a.n_groups = r->n_groups; a.wmax = r->wmax; a.s0 = r->s0; a.span = r->span;
-    a.in_tile = (kNB - 1) * a.D + a.span + a.wmax + 1;
-    a.out_stride = (a.n_groups * kG) | 1;
+    const size_t smem = tile_geometry(r, a, ch);
     a.n_tiles = (a.out_frames + (int64_t)kNB * a.P - 1) / ((int64_t)kNB * a.P);
-    const size_t smem = sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) +
-                                         2 * (size_t)kNB * a.out_stride + (size_t)a.in_tile * ch + 4);
     NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
     int threads = 32 * (a.n_groups < 20 ? a.n_groups : 20);
     const int ctas_per_sm = smem > 113 * 1024 ? 1 : 2;

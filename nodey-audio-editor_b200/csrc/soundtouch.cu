@@ -1,0 +1,759 @@
+// soundtouch.cu -- K6/K7: the SoundTouch 2.3.2 pipeline behind pitch_modifier / velocity_modifier
+// (A9; audio-velocity.cpp:265-443 drives SoundTouch::putSamples / receiveSamples / flush).
+//
+// SoundTouch is FIFO driven, so its output is a pure function of the whole input; the streaming
+// object becomes four whole-track kernels (batched over tracks of equal length):
+//
+//   tds_offsets  TDStretch::seekBestOverlapPositionFull -- the only sequential part.  Input
+//                consumption (skipFract) does not depend on the chosen offsets, so the host lays
+//                out every sequence's input position up front; what remains is the chain
+//                offset_i = argmax_c w(c) * (corr(in[pos_i + c ..], mid_i) + 0.1) with mid_i cut
+//                from the input at the previous offset.  One CTA per track walks that chain.  Per
+//                sequence the search window is staged once into shared memory, de-interleaved
+//                into the four SSE lanes' sample streams; a thread owns one (lane, candidate
+//                class) pair and T consecutive candidates, keeps T correlation and T norm
+//                accumulators in registers and slides one window of samples over them, so a
+//                shared-memory word feeds 2T rounded multiply/adds.  The four lane sums of a
+//                candidate are combined in the SSE build's order ((l0+l1)+l2)+l3 and the arg-max
+//                is first-wins like the scalar loop -- the offset trace is bit-identical.
+//   tds_assemble cross-fade + sequence copy, fully parallel once the offsets are known.
+//   aa_fir       AAFilter, 64 taps, the SSE build's even/odd accumulator order (stereo) or the
+//                double accumulator (mono).
+//   cubic        InterpolateCubic::transpose*.  rate = pitch*rate is a product of two floats, so
+//                fract += rate is exact in double and the read position of output i is the
+//                closed form i*rate in 128-bit fixed point: no sequential pass.
+//
+// Order: rate <= 1: cubic -> aa_fir -> TDStretch; rate > 1: TDStretch -> aa_fir -> cubic
+// (SoundTouch::putSamples).  flush() becomes "extend the input with 128-frame silent blocks
+// until enough output exists, trim to the expected total".
+// Compiled with -fmad=false: every multiply and add rounds separately, as in the reference build.
+#include "nodey_common.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace nodey {
+
+constexpr int kAaLen = 64;
+constexpr int kTdsThreads = 512;
+constexpr int kT = 8;              // candidates per thread
+
+// frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
+// (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks)
+struct View {
+    const float* p;
+    long long n;        // real frames
+    long long prefix;   // silent frames in front
+    long long stride;   // floats between tracks
+};
+
+template <int CH>
+__device__ __forceinline__ float view_sample(const View& v, const float* base, long long frame, int c)
+{
+    const long long f = frame - v.prefix;
+    if (f < 0 || f >= v.n) return 0.f;
+    return base[f * CH + c];
+}
+
+template <int CH>
+__device__ __forceinline__ float2 view_frame2(const View& v, const float* base, long long frame)
+{
+    const long long f = frame - v.prefix;
+    if (f < 0 || f >= v.n) return make_float2(0.f, 0.f);
+    if (CH == 2) return *reinterpret_cast<const float2*>(base + f * 2);
+    return make_float2(base[f], 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TDStretch offsets
+// ---------------------------------------------------------------------------------------------
+struct TdsArgs {
+    View in;
+    const long long* pos;      // [nseq] input frame where sequence i starts
+    int* offs;                 // [ntracks][nseq_stride] offsets of sequences 1..nseq-1 at index i-1
+    long long offs_stride;
+    int nseq;
+    int overlap, seek_window, seek_length;
+    int Q;                     // lane steps = 4 * (CH*overlap/16)
+    int plane_stride;          // floats per de-interleaved plane (== 8 mod 32)
+    int lpad;                  // padded candidate count for the partial-sum arrays
+};
+
+struct ArgMax { double v; int i; };
+
+__device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b)
+{
+    // scalar loop semantics: ascending index, replace only on strictly greater -> ties keep lowest index
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    constexpr int K = 4 / CH;                       // candidate classes per lane
+    float* X = smem;                                // [4][plane_stride]
+    float* Y = X + 4 * a.plane_stride;              // [4][Q]
+    float* PS = Y + 4 * a.Q;                        // [4][lpad] correlation lane sums
+    float* PN = PS + 4 * a.lpad;                    // [4][lpad] norm lane sums
+    __shared__ double red_v[kTdsThreads / 32];
+    __shared__ int red_i[kTdsThreads / 32];
+    __shared__ int s_offset;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const long long track = blockIdx.x;
+    const float* base = a.in.p + track * a.in.stride;
+    int* offs = a.offs + track * a.offs_stride;
+
+    const int L = a.seek_length, ovl = a.overlap, Q = a.Q;
+    const int region = L + ovl;                      // frames staged per sequence
+    const int temp = a.seek_window - 2 * ovl;
+    const int tcount = (L + K - 1) / K;              // candidates per class (upper bound)
+    const int tblocks = (tcount + kT - 1) / kT;
+    const int wpc = (tblocks + 31) / 32;             // warps per (lane, class) combo
+    const int nunits = 4 * K * wpc;
+    const int plane_len = a.plane_stride;
+
+    long long mid_pos = a.pos[0] + temp;             // first sequence: offset 0, no search
+
+    for (int i = 1; i < a.nseq; i++) {
+        const long long p0 = a.pos[i];
+        // L2 prefetch of the next sequence's window (its position does not depend on this search)
+        if (i + 1 < a.nseq) {
+            const long long q0 = a.pos[i + 1] - a.in.prefix;
+            const int lines = (region * CH * 4 + 127) / 128 + 1;
+            for (int t = tid; t < lines; t += blockDim.x) {
+                const long long f = q0 + (long long)t * (32 / CH);
+                if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
+            }
+        }
+        // ---- stage the search window, de-interleaved by float index mod 4 ----
+        if (CH == 2) {
+            for (int f = tid; f < plane_len * 2; f += blockDim.x) {
+                const float2 v = f < region ? view_frame2<2>(a.in, base, p0 + f) : make_float2(0.f, 0.f);
+                const int m = f >> 1, r = (f & 1) * 2;
+                X[r * plane_len + m] = v.x;
+                X[(r + 1) * plane_len + m] = v.y;
+            }
+        } else {
+            for (int f = tid; f < plane_len * 4; f += blockDim.x) {
+                const float v = f < region ? view_sample<1>(a.in, base, p0 + f, 0) : 0.f;
+                X[(f & 3) * plane_len + (f >> 2)] = v;
+            }
+        }
+        // ---- mid buffer (depends on the previous offset), de-interleaved by lane ----
+        for (int j = tid; j < 4 * Q; j += blockDim.x) {
+            const long long fr = mid_pos + j / CH;
+            Y[(j & 3) * Q + (j >> 2)] = view_sample<CH>(a.in, base, fr, j % CH);
+        }
+        __syncthreads();
+
+        // ---- lane sums: thread = (lane l, class kappa, T consecutive candidates of the class) ----
+        for (int unit = warp; unit < nunits; unit += nwarps) {
+            const int combo = unit / wpc, wsub = unit - combo * wpc;
+            const int l = combo & 3, kappa = combo >> 2;
+            const int tb = wsub * 32 + lane;
+            if (tb < tblocks) {
+                const int t0 = tb * kT;
+                const int u0 = CH * kappa + l;
+                const float* xp = X + (u0 & 3) * plane_len + (u0 >> 2) + t0;
+                const float* yp = Y + l * Q;
+                float acc[kT], nrm[kT], w[kT + 4], sq[kT + 4];
+#pragma unroll
+                for (int k = 0; k < kT; k++) { acc[k] = 0.f; nrm[k] = 0.f; }
+#pragma unroll
+                for (int k = 0; k < kT; k++) { w[k] = xp[k]; sq[k] = __fmul_rn(w[k], w[k]); }
+                for (int qb = 0; qb < Q; qb += 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { w[kT + k] = xp[qb + kT + k]; sq[kT + k] = __fmul_rn(w[kT + k], w[kT + k]); }
+                    const float4 y = *reinterpret_cast<const float4*>(yp + qb);
+                    const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+#pragma unroll
+                        for (int k = 0; k < kT; k++) {
+                            acc[k] = __fadd_rn(acc[k], __fmul_rn(w[s + k], yy[s]));
+                            nrm[k] = __fadd_rn(nrm[k], sq[s + k]);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kT; k++) { w[k] = w[k + 4]; sq[k] = sq[k + 4]; }
+                }
+#pragma unroll
+                for (int k = 0; k < kT; k++) {
+                    const int c = kappa + K * (t0 + k);
+                    if (c < L) { PS[l * a.lpad + c] = acc[k]; PN[l * a.lpad + c] = nrm[k]; }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- per candidate: horizontal add in the SSE order, normalise, weight; block arg-max ----
+        ArgMax best; best.v = -1e300; best.i = 0x7fffffff;
+        for (int c = tid; c < L; c += blockDim.x) {
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[c], PS[a.lpad + c]), PS[2 * a.lpad + c]), PS[3 * a.lpad + c]);
+            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[c], PN[a.lpad + c]), PN[2 * a.lpad + c]), PN[3 * a.lpad + c]);
+            const double dn = (double)nr;
+            double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
+            const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
+            corr = __dmul_rn(__dadd_rn(corr, 0.1), __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp)));
+            ArgMax cand; cand.v = corr; cand.i = c;
+            best = argmax_better(best, cand);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ArgMax o;
+            o.v = __shfl_xor_sync(0xffffffffu, best.v, d);
+            o.i = __shfl_xor_sync(0xffffffffu, best.i, d);
+            best = argmax_better(best, o);
+        }
+        if (lane == 0) { red_v[warp] = best.v; red_i[warp] = best.i; }
+        __syncthreads();
+        if (warp == 0) {
+            ArgMax b2; b2.v = lane < nwarps ? red_v[lane] : -1e300; b2.i = lane < nwarps ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                ArgMax o;
+                o.v = __shfl_xor_sync(0xffffffffu, b2.v, d);
+                o.i = __shfl_xor_sync(0xffffffffu, b2.i, d);
+                b2 = argmax_better(b2, o);
+            }
+            if (lane == 0) { s_offset = b2.i; offs[i - 1] = b2.i; }
+        }
+        __syncthreads();
+        mid_pos = p0 + s_offset + ovl + temp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TDStretch assemble: overlap (cross-fade) + copy of every sequence, one CTA per (sequence, track)
+// ---------------------------------------------------------------------------------------------
+struct AsmArgs {
+    View in;
+    float* out; long long out_stride; long long out_cap;   // frames to write at most (trim)
+    const long long* pos;
+    const int* offs; long long offs_stride;
+    const float* fade;          // stereo: [2][overlap] (f1, f2)
+    int nseq, overlap, seek_window;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) tds_assemble_kernel(const __grid_constant__ AsmArgs a)
+{
+    const int i = blockIdx.x;
+    const long long track = blockIdx.y;
+    const float* base = a.in.p + track * a.in.stride;
+    float* out = a.out + track * a.out_stride;
+    const int* offs = a.offs + track * a.offs_stride;
+    const int ovl = a.overlap, temp = a.seek_window - 2 * ovl;
+    if (i == 0) {
+        const long long p0 = a.pos[0];
+        for (int k = threadIdx.x; k < temp; k += blockDim.x) {
+            if (k >= a.out_cap) break;
+#pragma unroll
+            for (int c = 0; c < CH; c++) out[(long long)k * CH + c] = view_sample<CH>(a.in, base, p0 + k, c);
+        }
+        return;
+    }
+    const long long ob = temp + (long long)(i - 1) * (a.seek_window - ovl);
+    const long long src = a.pos[i] + offs[i - 1];
+    const long long mid = (i == 1) ? a.pos[0] + temp : a.pos[i - 1] + offs[i - 2] + ovl + temp;
+    for (int k = threadIdx.x; k < ovl + temp; k += blockDim.x) {
+        const long long o = ob + k;
+        if (o >= a.out_cap) break;
+        if (k < ovl) {
+            if (CH == 2) {
+                const float f1 = a.fade[k], f2 = a.fade[ovl + k];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const float x = view_sample<2>(a.in, base, src + k, c), m = view_sample<2>(a.in, base, mid + k, c);
+                    out[o * 2 + c] = __fadd_rn(__fmul_rn(x, f1), __fmul_rn(m, f2));
+                }
+            } else {
+                const float x = view_sample<1>(a.in, base, src + k, 0), m = view_sample<1>(a.in, base, mid + k, 0);
+                out[o] = __fdiv_rn(__fadd_rn(__fmul_rn(x, (float)k), __fmul_rn(m, (float)(ovl - k))), (float)ovl);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH; c++) out[o * CH + c] = view_sample<CH>(a.in, base, src + k, c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AAFilter FIR (64 taps).  Tile of outputs per CTA, input tile in shared memory, R outputs/thread.
+// ---------------------------------------------------------------------------------------------
+struct FirArgs {
+    View in;
+    float* out; long long out_stride;
+    long long count;            // outputs per track
+    float h[kAaLen];            // coefficients ride in the kernel parameters (constant bank, uniform reads)
+};
+
+constexpr int kFirR = 4;                  // outputs per thread
+constexpr int kFirThreads = 256;
+constexpr int kFirTile = kFirR * kFirThreads;   // 1024 outputs per CTA
+
+template <int CH>
+__global__ void __launch_bounds__(kFirThreads) aa_fir_kernel(const __grid_constant__ FirArgs a)
+{
+    __shared__ __align__(16) float tile[(kFirTile + kAaLen) * CH];
+    const long long track = blockIdx.y;
+    const float* base = a.in.p + track * a.in.stride;
+    float* out = a.out + track * a.out_stride;
+    const float* h = a.h;
+    const long long ntiles = (a.count + kFirTile - 1) / kFirTile;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long n0 = t * kFirTile;
+        __syncthreads();
+        for (int f = threadIdx.x; f < kFirTile + kAaLen; f += blockDim.x) {
+            if (CH == 2) reinterpret_cast<float2*>(tile)[f] = view_frame2<2>(a.in, base, n0 + f);
+            else tile[f] = view_sample<1>(a.in, base, n0 + f, 0);
+        }
+        __syncthreads();
+        // thread owns outputs j = threadIdx.x + r * kFirThreads (conflict-free shared reads)
+        if (CH == 2) {
+            float e0[kFirR], e1[kFirR], o0[kFirR], o1[kFirR];
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) { e0[r] = e1[r] = o0[r] = o1[r] = 0.f; }
+            const float2* tp = reinterpret_cast<const float2*>(tile) + threadIdx.x;
+#pragma unroll 8
+            for (int i = 0; i < kAaLen; i += 2) {
+                const float h0 = h[i], h1 = h[i + 1];
+#pragma unroll
+                for (int r = 0; r < kFirR; r++) {
+                    const float2 x0 = tp[r * kFirThreads + i], x1 = tp[r * kFirThreads + i + 1];
+                    e0[r] = __fadd_rn(e0[r], __fmul_rn(x0.x, h0));
+                    e1[r] = __fadd_rn(e1[r], __fmul_rn(x0.y, h0));
+                    o0[r] = __fadd_rn(o0[r], __fmul_rn(x1.x, h1));
+                    o1[r] = __fadd_rn(o1[r], __fmul_rn(x1.y, h1));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) {
+                const long long n = n0 + threadIdx.x + r * kFirThreads;
+                if (n < a.count) reinterpret_cast<float2*>(out)[n] = make_float2(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]));
+            }
+        } else {
+            double s[kFirR];
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) s[r] = 0.0;
+            const float* tp = tile + threadIdx.x;
+            for (int i = 0; i < kAaLen; i++) {
+                const float hi = h[i];
+#pragma unroll
+                for (int r = 0; r < kFirR; r++) s[r] = __dadd_rn(s[r], (double)__fmul_rn(tp[r * kFirThreads + i], hi));
+            }
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) {
+                const long long n = n0 + threadIdx.x + r * kFirThreads;
+                if (n < a.count) out[n] = (float)s[r];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cubic transposer: output i reads 4 frames at floor(i*rate), fraction (float)frac(i*rate)
+// ---------------------------------------------------------------------------------------------
+struct CubicArgs {
+    View in;
+    float* out; long long out_stride;
+    long long count;
+    unsigned long long R;   // rate = R * 2^-e
+    int e;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256) cubic_kernel(const __grid_constant__ CubicArgs a)
+{
+    const long long track = blockIdx.y;
+    const float* base = a.in.p + track * a.in.stride;
+    float* out = a.out + track * a.out_stride;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double inv = 1.0 / (double)(1ull << a.e);     // exact power of two (e <= 62)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += stride) {
+        const unsigned long long lo = (unsigned long long)i * a.R, hi = __umul64hi((unsigned long long)i, a.R);
+        const long long P = (long long)((lo >> a.e) | (a.e ? (hi << (64 - a.e)) : 0ull));
+        const unsigned long long fb = lo & ((1ull << a.e) - 1ull);
+        const float x2 = (float)((double)fb * inv);
+        const float x1 = __fmul_rn(x2, x2);
+        const float x0 = __fmul_rn(x1, x2);
+        // y_r = ((c0*x0 + c1*x1) + c2*x2) + c3*1, coefficients of InterpolateCubic.cpp
+        const float y0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), __fmul_rn(1.0f, x1)), __fmul_rn(-0.5f, x2)), __fmul_rn(0.0f, 1.0f));
+        const float y1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(1.0f, 1.0f));
+        const float y2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2)), __fmul_rn(0.0f, 1.0f));
+        const float y3 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(0.0f, 1.0f));
+        if (CH == 2) {
+            const float2 p0 = view_frame2<2>(a.in, base, P), p1 = view_frame2<2>(a.in, base, P + 1);
+            const float2 p2 = view_frame2<2>(a.in, base, P + 2), p3 = view_frame2<2>(a.in, base, P + 3);
+            float2 o;
+            o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.x), __fmul_rn(y1, p1.x)), __fmul_rn(y2, p2.x)), __fmul_rn(y3, p3.x));
+            o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.y), __fmul_rn(y1, p1.y)), __fmul_rn(y2, p2.y)), __fmul_rn(y3, p3.y));
+            reinterpret_cast<float2*>(out)[i] = o;
+        } else {
+            const float p0 = view_sample<1>(a.in, base, P, 0), p1 = view_sample<1>(a.in, base, P + 1, 0);
+            const float p2 = view_sample<1>(a.in, base, P + 2, 0), p3 = view_sample<1>(a.in, base, P + 3, 0);
+            out[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0), __fmul_rn(y1, p1)), __fmul_rn(y2, p2)), __fmul_rn(y3, p3));
+        }
+    }
+}
+
+}  // namespace nodey
+
+using namespace nodey;
+
+// ---------------------------------------------------------------------------------------------
+// host plan
+// ---------------------------------------------------------------------------------------------
+struct nodey_soundtouch {
+    int sample_rate = 0, ch = 0;
+    double rate = 1, tempo = 1;
+    int td_first = 0;
+    int overlap = 0, seek_window = 0, seek_length = 0, sample_req = 0;
+    double nominal_skip = 0;
+    unsigned long long R = 0; int e = 0;       // rate = R * 2^-e exactly
+    int prefill = 0;                           // silent frames in front of the RateTransposer input
+    float aa[kAaLen];
+    float* d_fade = nullptr;
+    // sequence start positions (prefix-stable in the input length): grown on demand
+    std::vector<long long> pos;
+    long long pos_valid_for = -1;              // input length the table was built for
+    long long* d_pos = nullptr; size_t d_pos_cap = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+long long tds_build_pos(nodey_soundtouch* s, long long n_in, std::vector<long long>& pos)
+{
+    // TDStretch::processSamples() input bookkeeping (offsets do not influence it)
+    pos.clear();
+    long long consumed = 0;
+    double skip_fract = 0;
+    int beginning = 1;
+    while (n_in - consumed >= s->sample_req) {
+        pos.push_back(consumed);
+        if (beginning) {
+            beginning = 0;
+            const int skip = (int)(s->tempo * s->overlap + 0.5 * s->seek_length + 0.5);
+            skip_fract -= skip;
+            if (skip_fract <= -s->nominal_skip) skip_fract = -s->nominal_skip;
+        }
+        skip_fract += s->nominal_skip;
+        const int ovl_skip = (int)skip_fract;
+        skip_fract -= ovl_skip;
+        if (ovl_skip >= n_in - consumed) consumed = n_in; else consumed += ovl_skip;
+    }
+    return (long long)pos.size();
+}
+
+long long tds_out_frames(const nodey_soundtouch* s, long long nseq)
+{
+    if (nseq <= 0) return 0;
+    return (long long)(s->seek_window - 2 * s->overlap) + (nseq - 1) * (long long)(s->seek_window - s->overlap);
+}
+
+long long fir_count(const nodey_soundtouch* s, long long n)
+{
+    if (n < kAaLen) return 0;
+    if (s->ch == 2) { const long long c = (n - kAaLen) & ~1ll; return c < 2 ? 0 : c; }
+    return n - kAaLen;
+}
+
+// number of outputs i >= 0 with floor(i * rate) < n - 4
+long long cubic_count(const nodey_soundtouch* s, long long n)
+{
+    const long long end = n - 4;
+    if (end <= 0) return 0;
+    // smallest i with i*R >= end * 2^e  ->  ceil(end * 2^e / R)
+    const unsigned __int128 num = (unsigned __int128)end << s->e;
+    return (long long)((num + s->R - 1) / s->R);
+}
+
+struct StageLens { long long n_ext, l1, l2, l3, nseq, tds_in; };
+
+void stage_lengths(nodey_soundtouch* s, long long n_ext, StageLens* L, std::vector<long long>* pos_out)
+{
+    std::vector<long long> tmp;
+    std::vector<long long>& pos = pos_out ? *pos_out : tmp;
+    L->n_ext = n_ext;
+    if (s->td_first) {
+        L->tds_in = n_ext;
+        L->nseq = tds_build_pos(s, n_ext, pos);
+        L->l1 = tds_out_frames(s, L->nseq);
+        L->l2 = fir_count(s, s->prefill + L->l1);
+        L->l3 = cubic_count(s, L->l2);
+    } else {
+        L->l1 = cubic_count(s, s->prefill + n_ext);
+        L->l2 = fir_count(s, L->l1);
+        L->tds_in = L->l2;
+        L->nseq = tds_build_pos(s, L->l2, pos);
+        L->l3 = tds_out_frames(s, L->nseq);
+    }
+}
+
+// SoundTouch::flush(): silent 128-frame blocks until the expected amount exists (at most 200)
+long long plan_total(nodey_soundtouch* s, long long in_frames, int frame_size, StageLens* L, std::vector<long long>* pos)
+{
+    double expected = 0;
+    const double denom = s->rate * s->tempo;
+    for (long long p = 0; p < in_frames; p += frame_size) {
+        const long long n = (in_frames - p) < frame_size ? (in_frames - p) : frame_size;
+        expected += (double)n / denom;
+    }
+    const long long want = (long long)(long)(expected + 0.5);
+    stage_lengths(s, in_frames, L, pos);
+    if (L->l3 >= want) return L->l3;         // nothing left to flush: everything already emitted
+    for (int k = 1; k <= 200; k++) {
+        stage_lengths(s, in_frames + 128ll * k, L, pos);
+        if (L->l3 >= want) return want;
+    }
+    return L->l3;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nodey_soundtouch_create(nodey_soundtouch** out, int sample_rate, int channels, float rate_arg, float pitch_arg)
+{
+    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_soundtouch_create: null out pointer");
+    NODEY_REQUIRE(channels == 1 || channels == 2, NODEY_E_INVALID, "Unsupported channel count: %d", channels);
+    // audio-velocity.cpp:371: SoundTouch is only fed 8 kHz .. 48 kHz
+    NODEY_REQUIRE(sample_rate >= 8000 && sample_rate <= 48000, NODEY_E_RANGE,
+                  "Unsupported sample rate %d (SoundTouch node accepts 8000..48000)", sample_rate);
+    NODEY_REQUIRE(rate_arg > 0.f && pitch_arg > 0.f, NODEY_E_RANGE, "nodey_soundtouch_create: rate and pitch must be positive");
+    nodey_soundtouch* s = new nodey_soundtouch();
+    s->sample_rate = sample_rate; s->ch = channels;
+    const double vrate = (double)rate_arg, vpitch = (double)pitch_arg;
+    s->tempo = 1.0 / vpitch;              // virtualTempo = 1
+    s->rate = vpitch * vrate;
+    s->td_first = !(s->rate <= 1.0f);
+    // TDStretch parameters (setParameters / calcSeqParameters / setTempo), App. B2
+    int ovl = (sample_rate * 8) / 1000;
+    if (ovl < 16) ovl = 16;
+    ovl -= ovl % 8;
+    s->overlap = ovl;
+    double seq = (90.0 - ((40.0 - 90.0) / (2.0 - 0.5)) * 0.5) + ((40.0 - 90.0) / (2.0 - 0.5)) * s->tempo;
+    seq = seq < 40.0 ? 40.0 : (seq > 90.0 ? 90.0 : seq);
+    double seek = (20.0 - ((15.0 - 20.0) / (2.0 - 0.5)) * 0.5) + ((15.0 - 20.0) / (2.0 - 0.5)) * s->tempo;
+    seek = seek < 15.0 ? 15.0 : (seek > 20.0 ? 20.0 : seek);
+    s->seek_window = (sample_rate * (int)(seq + 0.5)) / 1000;
+    if (s->seek_window < 2 * ovl) s->seek_window = 2 * ovl;
+    s->seek_length = (sample_rate * (int)(seek + 0.5)) / 1000;
+    s->nominal_skip = s->tempo * (s->seek_window - ovl);
+    {
+        const int intskip = (int)(s->nominal_skip + 0.5);
+        const int a = intskip + ovl;
+        s->sample_req = (a > s->seek_window ? a : s->seek_window) + s->seek_length;
+    }
+    // rate as an exact dyadic rational: frexp mantissa bits
+    {
+        int ex = 0;
+        const double m = frexp(s->rate, &ex);            // rate = m * 2^ex, 0.5 <= m < 1
+        unsigned long long R = (unsigned long long)ldexp(m, 53);   // 53-bit integer mantissa, exact
+        int e = 53 - ex;
+        while (e > 0 && (R & 1ull) == 0) { R >>= 1; e--; }
+        // exactness of the reference's `fract += rate` in double needs (1 + rate) * 2^e < 2^53
+        if (e < 0 || e > 60 || ldexp(1.0 + s->rate, e) >= 9007199254740992.0) {
+            delete s;
+            set_error("nodey_soundtouch_create: rate %.17g is outside the exactly representable range", vpitch * vrate);
+            return NODEY_E_RANGE;
+        }
+        s->R = R; s->e = e;
+    }
+    s->prefill = (1 + 32) * 2 / channels;     // RateTransposer latency pre-fill, stored as stereo frames
+    // AAFilter::calculateCoeffs(), 64 taps
+    {
+        const double cutoff = s->rate > 1.0 ? 0.5 / s->rate : 0.5 * s->rate;
+        double work[kAaLen], sum = 0;
+        const double wc = 2.0 * M_PI * cutoff;
+        const double temp_coeff = (2 * M_PI) / (double)kAaLen;
+        for (int i = 0; i < kAaLen; i++) {
+            const double cnt = (double)i - (double)(kAaLen / 2);
+            double temp = cnt * wc;
+            const double h = (temp != 0) ? sin(temp) / temp : 1.0;
+            const double w = 0.54 + 0.46 * cos(temp_coeff * cnt);
+            temp = w * h;
+            work[i] = temp;
+            sum += temp;
+        }
+        const double scale = 16384.0f / sum;
+        for (int i = 0; i < kAaLen; i++) {
+            double temp = work[i] * scale;
+            temp += (temp >= 0) ? 0.5 : -0.5;
+            s->aa[i] = (float)temp / 16384.0f;
+        }
+    }
+    // overlapStereo() fade ramps: repeated float adds of 1/overlap
+    {
+        std::vector<float> fade((size_t)2 * ovl);
+        const float scale = 1.0f / (float)ovl;
+        float f1 = 0, f2 = 1.0f;
+        for (int k = 0; k < ovl; k++) { fade[(size_t)k] = f1; fade[(size_t)(ovl + k)] = f2; f1 += scale; f2 -= scale; }
+        cudaError_t err = cudaMalloc((void**)&s->d_fade, sizeof(float) * fade.size());
+        if (err == cudaSuccess) err = cudaMemcpy(s->d_fade, fade.data(), sizeof(float) * fade.size(), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) { if (s->d_fade) cudaFree(s->d_fade); delete s; return cuda_fail(err, "fade table upload", __FILE__, __LINE__); }
+    }
+    *out = s;
+    return NODEY_OK;
+}
+
+void nodey_soundtouch_destroy(nodey_soundtouch* s)
+{
+    if (!s) return;
+    if (s->d_fade) cudaFree(s->d_fade);
+    if (s->d_pos) cudaFree(s->d_pos);
+    delete s;
+}
+
+/* info_i[8]: overlap, seek_window, seek_length, sample_req, tdstretch_first, prefill, channels, sample_rate
+ * info_d[3]: rate, tempo, nominal_skip */
+int nodey_soundtouch_info(const nodey_soundtouch* s, int info_i[8], double info_d[3])
+{
+    NODEY_REQUIRE(s, NODEY_E_INVALID, "nodey_soundtouch_info: null handle");
+    if (info_i) {
+        info_i[0] = s->overlap; info_i[1] = s->seek_window; info_i[2] = s->seek_length; info_i[3] = s->sample_req;
+        info_i[4] = s->td_first; info_i[5] = s->prefill; info_i[6] = s->ch; info_i[7] = s->sample_rate;
+    }
+    if (info_d) { info_d[0] = s->rate; info_d[1] = s->tempo; info_d[2] = s->nominal_skip; }
+    return NODEY_OK;
+}
+
+int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t* n_sequences)
+{
+    if (!s || in_frames < 0 || frame_size <= 0) return NODEY_E_INVALID;
+    std::lock_guard<std::mutex> lock(s->mu);
+    StageLens L;
+    const long long total = plan_total(s, in_frames, frame_size, &L, nullptr);
+    if (n_sequences) *n_sequences = L.nseq;
+    return total;
+}
+
+int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
+                         int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                         int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(s && out && in, NODEY_E_INVALID, "nodey_soundtouch_run: null argument");
+    NODEY_REQUIRE(ntracks >= 1 && in_frames >= 0 && frame_size > 0, NODEY_E_INVALID, "nodey_soundtouch_run: bad size");
+    std::lock_guard<std::mutex> lock(s->mu);
+    cudaStream_t st = as_stream(stream);
+    StageLens L;
+    std::vector<long long> pos;
+    const long long total = plan_total(s, in_frames, frame_size, &L, &pos);
+    NODEY_REQUIRE(out_frames >= 0 && out_frames <= total, NODEY_E_RANGE,
+                  "nodey_soundtouch_run: out_frames %lld exceeds what SoundTouch would produce (%lld)", (long long)out_frames, total);
+    if (out_frames == 0) return NODEY_OK;
+    NODEY_REQUIRE(L.nseq >= 1, NODEY_E_INVALID, "nodey_soundtouch_run: internal: output without a sequence");
+    NODEY_REQUIRE(offsets == nullptr || offsets_stride >= L.nseq - 1, NODEY_E_INVALID, "nodey_soundtouch_run: offsets_stride too small");
+
+    // sequence positions on the device (re-uploaded only when the table changed)
+    if (pos != s->pos || !s->d_pos) {
+        if (pos.size() > s->d_pos_cap) {
+            if (s->d_pos) cudaFree(s->d_pos);
+            s->d_pos = nullptr;
+            s->d_pos_cap = pos.size() + pos.size() / 4 + 64;
+            NODEY_CUDA_OK(cudaMalloc((void**)&s->d_pos, sizeof(long long) * s->d_pos_cap));
+        }
+        s->pos = pos;
+        NODEY_CUDA_OK(cudaMemcpyAsync(s->d_pos, s->pos.data(), sizeof(long long) * s->pos.size(), cudaMemcpyHostToDevice, st));
+    }
+
+    const int CH = s->ch;
+    const long long nseq = L.nseq;
+    // workspace: offsets + two intermediates per track
+    const long long offs_stride_ws = nseq > 1 ? nseq - 1 : 1;
+    int* d_offs = offsets;
+    long long offs_stride = offsets ? offsets_stride : offs_stride_ws;
+    const long long s1 = ((L.l1 * CH + 3) & ~3ll) + 4, s2 = ((L.l2 * CH + 3) & ~3ll) + 4;
+    float* ws = nullptr;
+    int* ws_offs = nullptr;
+    NODEY_CUDA_OK(cudaMallocAsync((void**)&ws, sizeof(float) * (size_t)((s1 + s2) * ntracks), st));
+    if (!offsets) {
+        cudaError_t e = cudaMallocAsync((void**)&ws_offs, sizeof(int) * (size_t)(offs_stride_ws * ntracks), st);
+        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__); }
+        d_offs = ws_offs;
+    }
+    float* b1 = ws;
+    float* b2 = ws + s1 * ntracks;
+
+    auto run_tds = [&](View vin, float* dst, long long dst_stride, long long dst_cap) -> int {
+        TdsArgs ta;
+        ta.in = vin; ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
+        ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
+        ta.Q = 4 * (CH * s->overlap / 16);
+        int plane = (CH * (s->seek_length + s->overlap) + 3) / 4 + 2 * kT + 8;
+        while ((plane & 31) != 8) plane++;
+        ta.plane_stride = plane;
+        ta.lpad = (s->seek_length + 3) & ~3;
+        const size_t smem = sizeof(float) * ((size_t)4 * plane + (size_t)4 * ta.Q + (size_t)8 * ta.lpad);
+        if (nseq > 1) {
+            if (CH == 2) {
+                NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tds_offsets_kernel<2><<<ntracks, kTdsThreads, smem, st>>>(ta);
+            } else {
+                NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tds_offsets_kernel<1><<<ntracks, kTdsThreads, smem, st>>>(ta);
+            }
+            NODEY_LAUNCH_OK();
+        }
+        AsmArgs aa;
+        aa.in = vin; aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = s->d_pos;
+        aa.offs = d_offs; aa.offs_stride = offs_stride; aa.fade = s->d_fade; aa.nseq = (int)nseq;
+        aa.overlap = s->overlap; aa.seek_window = s->seek_window;
+        dim3 grid((unsigned)nseq, (unsigned)ntracks);
+        if (CH == 2) tds_assemble_kernel<2><<<grid, 256, 0, st>>>(aa); else tds_assemble_kernel<1><<<grid, 256, 0, st>>>(aa);
+        NODEY_LAUNCH_OK();
+        return NODEY_OK;
+    };
+    auto run_fir = [&](View vin, float* dst, long long dst_stride, long long count) -> int {
+        if (count <= 0) return NODEY_OK;
+        FirArgs fa; fa.in = vin; fa.out = dst; fa.out_stride = dst_stride; fa.count = count; memcpy(fa.h, s->aa, sizeof(fa.h));
+        long long tiles = (count + kFirTile - 1) / kFirTile;
+        long long gx = tiles < 65535 ? tiles : 65535;
+        dim3 grid((unsigned)gx, (unsigned)ntracks);
+        if (CH == 2) aa_fir_kernel<2><<<grid, kFirThreads, 0, st>>>(fa); else aa_fir_kernel<1><<<grid, kFirThreads, 0, st>>>(fa);
+        NODEY_LAUNCH_OK();
+        return NODEY_OK;
+    };
+    auto run_cubic = [&](View vin, float* dst, long long dst_stride, long long count) -> int {
+        if (count <= 0) return NODEY_OK;
+        CubicArgs ca; ca.in = vin; ca.out = dst; ca.out_stride = dst_stride; ca.count = count; ca.R = s->R; ca.e = s->e;
+        long long blocks = (count + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)ntracks);
+        if (CH == 2) cubic_kernel<2><<<grid, 256, 0, st>>>(ca); else cubic_kernel<1><<<grid, 256, 0, st>>>(ca);
+        NODEY_LAUNCH_OK();
+        return NODEY_OK;
+    };
+
+    int rc = NODEY_OK;
+    if (s->td_first) {
+        View v0{in, in_frames, 0, in_stride};
+        rc = run_tds(v0, b1, s1, L.l1);
+        View v1{b1, L.l1, s->prefill, s1};
+        if (rc == NODEY_OK) rc = run_fir(v1, b2, s2, L.l2);
+        View v2{b2, L.l2, 0, s2};
+        if (rc == NODEY_OK) rc = run_cubic(v2, out, out_stride, out_frames);
+    } else {
+        View v0{in, in_frames, s->prefill, in_stride};
+        rc = run_cubic(v0, b1, s1, L.l1);
+        View v1{b1, L.l1, 0, s1};
+        if (rc == NODEY_OK) rc = run_fir(v1, b2, s2, L.l2);
+        View v2{b2, L.l2, 0, s2};
+        if (rc == NODEY_OK) rc = run_tds(v2, out, out_stride, out_frames);
+    }
+    cudaFreeAsync(ws, st);
+    if (ws_offs) cudaFreeAsync(ws_offs, st);
+    return rc;
+}
+
+}  // extern "C"

@@ -153,7 +153,7 @@ def split(x, fmt):
 
 
 class Swr:
-    def __init__(self, in_rate, out_rate, in_fmt, in_ch, quirk=1):
+    def __init__(self, in_rate, out_rate, in_fmt, in_ch, quirk=0):
         self.h = lib().orc_swr_create(in_rate, out_rate, in_fmt, in_ch, quirk)
         self.fmt, self.ch = in_fmt, in_ch
 
@@ -186,11 +186,11 @@ class Swr:
         return ol[:n], orr[:n]
 
 
-def swr_out_count(in_rate, out_rate, in_frames, flush=True, quirk=1):
+def swr_out_count(in_rate, out_rate, in_frames, flush=True, quirk=0):
     return lib().orc_swr_out_count(in_rate, out_rate, quirk, in_frames, 1 if flush else 0)
 
 
-def swr_whole(x, fmt, in_rate, out_rate=48000, flush=True, quirk=1):
+def swr_whole(x, fmt, in_rate, out_rate=48000, flush=True, quirk=0):
     p0, p1, n, nch = planes_of(x, fmt)
     cap = swr_out_count(in_rate, out_rate, n, True, quirk) + 64
     ol = np.zeros(cap, np.float32); orr = np.zeros(cap, np.float32)
@@ -206,7 +206,7 @@ def make_track(x, fmt, rate, frame_size=1152, pts0=0.0):
     return t
 
 
-def amix(tracks, volumes, quirk=1):
+def amix(tracks, volumes, quirk=0):
     arr = (Track * len(tracks))(*tracks)
     vol = np.ascontiguousarray(volumes, np.float32)
     cap = max(int(t.nframes * 48000 // t.rate) for t in tracks) + 8 * 4096
@@ -215,14 +215,14 @@ def amix(tracks, volumes, quirk=1):
     return ol[:n], orr[:n]
 
 
-def bimix(tl, tr, bias, quirk=1):
+def bimix(tl, tr, bias, quirk=0):
     cap = max(int(t.nframes * 48000 // t.rate) for t in (tl, tr)) + 8 * 4096
     ol = np.zeros(cap, np.float32); orr = np.zeros(cap, np.float32)
     n = lib().orc_bimix(C.byref(tl), C.byref(tr), np.float32(bias), quirk, _p(ol), _p(orr), cap)
     return ol[:n], orr[:n]
 
 
-def bimix_v2(tl, tr, quirk=1):
+def bimix_v2(tl, tr, quirk=0):
     cap = int(max(t.pts0 * 48000 + t.nframes * 48000 // t.rate for t in (tl, tr))) + 8 * 4096
     out = np.zeros((cap, 2), np.float32)
     pts = C.c_double(0)

@@ -1,0 +1,30 @@
+"""pytest configuration: `gpu` marker, import paths for the oracle (checker) and the C-ABI binding."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import oracle as O
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def nd():
+    """The CUDA library binding; a GPU test without the library or a device is an error, not a skip."""
+    import torch
+    import nodey
+    nodey.lib()
+    assert torch.cuda.is_available(), "gpu-marked test started without a CUDA device"
+    return nodey

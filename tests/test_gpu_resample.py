@@ -1,0 +1,118 @@
+"""GPU parity: polyphase resampler (A7) and its fusion with the N-input mix (A4) against the
+oracle's libswresample model, bit exact (same tap order, fused multiply-add) through the C ABI."""
+import numpy as np
+import pytest
+
+from helpers import ALL_FMTS, FMT_FLT, FMT_FLTP, FMT_S16, assert_bit_equal, make_input, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def test_plan_matches_oracle(nd, orc):
+    for in_rate, out_rate in [(44100, 48000), (48000, 44100), (22050, 48000), (96000, 48000), (8000, 48000), (44099, 48000)]:
+        for quirk in (0, 1):
+            r = nd.Resampler(in_rate, out_rate, quirk)
+            o = orc.Swr(in_rate, out_rate, FMT_FLT, 2, quirk)
+            assert r.info() == o.plan(), (in_rate, out_rate)
+            assert_bit_equal(r.filter_bank(), o.filter_bank(), "filter bank")
+            for n in (0, 10, 33, 34, 1000, 44100):
+                for flush in (False, True):
+                    assert r.out_count(n, flush) == orc.swr_out_count(in_rate, out_rate, n, flush, quirk)
+            r.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("fmt", ALL_FMTS)
+@pytest.mark.parametrize("nch", [1, 2])
+def test_resample_441_to_48_bit_exact(nd, orc, mode, fmt, nch):
+    n = 30011
+    x = make_input(orc, fmt, n, nch)
+    rl, rr = orc.swr_whole(x, fmt, 44100, 48000, flush=True, quirk=0)
+    r = nd.Resampler(44100, 48000)
+    got = r.run(to_dev(x), fmt, flush=True, mode=mode).cpu().numpy()
+    assert_bit_equal(got[0], rl, "resample L")
+    assert_bit_equal(got[1], rr, "resample R")
+
+
+@pytest.mark.parametrize("rates", [(48000, 44100), (22050, 48000), (96000, 48000), (32000, 48000), (44099, 48000), (11025, 48000)])
+@pytest.mark.parametrize("flush", [False, True])
+def test_resample_other_rates_bit_exact(nd, orc, rates, flush):
+    n = 20000
+    x = make_input(orc, FMT_FLT, n, 2, rate=rates[0])
+    rl, rr = orc.swr_whole(x, FMT_FLT, rates[0], rates[1], flush=flush, quirk=0)
+    r = nd.Resampler(*rates)
+    got = r.run(to_dev(x), FMT_FLT, flush=flush).cpu().numpy()
+    assert got.shape[1] == len(rl)
+    assert_bit_equal(got[0], rl, "resample L")
+    assert_bit_equal(got[1], rr, "resample R")
+
+
+@pytest.mark.parametrize("n", [0, 1, 32, 33, 34, 100, 147, 4704, 4705])
+def test_resample_short_inputs(nd, orc, n):
+    if n == 0:
+        r = nd.Resampler(44100, 48000)
+        assert r.out_count(0, True) == 0
+        return
+    x = make_input(orc, FMT_FLT, n, 2)
+    rl, rr = orc.swr_whole(x, FMT_FLT, 44100, 48000, flush=True, quirk=0)
+    r = nd.Resampler(44100, 48000)
+    assert r.out_count(n, True) == len(rl)
+    if len(rl):
+        for mode in (1, 2):
+            got = r.run(to_dev(x), FMT_FLT, flush=True, mode=mode).cpu().numpy()
+            assert_bit_equal(got[0], rl, f"short L mode {mode}")
+            assert_bit_equal(got[1], rr, f"short R mode {mode}")
+
+
+def test_resample_quirk_phase(nd, orc):
+    x = make_input(orc, FMT_FLT, 5000, 2)
+    rl, rr = orc.swr_whole(x, FMT_FLT, 44100, 48000, flush=True, quirk=1)
+    r = nd.Resampler(44100, 48000, quirk=1)
+    got = r.run(to_dev(x), FMT_FLT, flush=True).cpu().numpy()
+    assert_bit_equal(got[0], rl, "quirk L")
+
+
+def test_resample_rejects_too_many_frames(nd, orc):
+    x = to_dev(make_input(orc, FMT_FLT, 1000, 2))
+    r = nd.Resampler(44100, 48000)
+    with pytest.raises(nd.NodeyError) as e:
+        r.run(x, FMT_FLT, flush=True, out_frames=r.out_count(1000, True) + 1)
+    assert e.value.code == -5
+
+
+@pytest.mark.parametrize("nin", [1, 2, 16])
+def test_amix_fused_matches_oracle_node(nd, orc, nin):
+    """audio_amix restated frame by frame (orc_amix) == fused resample + ordered mix on the GPU.
+    The oracle output is zero padded to whole 1152-frame iterations; the common prefix must be
+    bit identical and everything after the longest resampled input must be zero."""
+    rng = np.random.default_rng(7 + nin)
+    lens = [int(rng.integers(20000, 40000)) for _ in range(nin)]
+    vols = (rng.uniform(0.1, 1.0, nin)).astype(np.float32)
+    xs = [make_input(orc, FMT_FLT, l, 2, track=i) for i, l in enumerate(lens)]
+    tracks = [orc.make_track(x, FMT_FLT, 44100) for x in xs]
+    rl, rr = orc.amix(tracks, vols, quirk=0)
+    r = nd.Resampler(44100, 48000)
+    got = r.resample_mix([to_dev(x) for x in xs], [FMT_FLT] * nin, vols, flush=True).cpu().numpy()
+    m = got.shape[1]
+    assert m <= len(rl)
+    assert_bit_equal(got[0], rl[:m], "amix L")
+    assert_bit_equal(got[1], rr[:m], "amix R")
+    assert not rl[m:].any() and not rr[m:].any()
+
+
+def test_amix_mixed_formats_unfused(nd, orc):
+    """inputs at different rates/formats: per-input resample, then the ordered mix kernel."""
+    specs = [(FMT_S16, 44100, 2), (FMT_FLTP, 48000, 2), (FMT_FLT, 22050, 1), (FMT_S16, 44100, 1)]
+    xs = [make_input(orc, f, 15000, ch, rate=sr, track=i) for i, (f, sr, ch) in enumerate(specs)]
+    vols = np.array([0.9, 0.5, 0.7, 0.2], np.float32)
+    tracks = [orc.make_track(x, f, sr) for x, (f, sr, ch) in zip(xs, specs)]
+    rl, rr = orc.amix(tracks, vols, quirk=0)
+    outs = []
+    for x, (f, sr, ch) in zip(xs, specs):
+        r = nd.Resampler(sr, 48000)
+        outs.append(r.run(to_dev(x), f, flush=True))
+    got = nd.mix(outs, vols).cpu().numpy()
+    m = got.shape[1]
+    assert_bit_equal(got[0], rl[:m], "amix mixed L")
+    assert_bit_equal(got[1], rr[:m], "amix mixed R")
+    assert not rl[m:].any()

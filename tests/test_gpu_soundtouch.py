@@ -1,0 +1,86 @@
+"""GPU parity: pitch_modifier / velocity_modifier (SoundTouch model) against the oracle.  The WSOLA
+offset trace must be identical and, because every kernel reproduces the oracle's rounding sequence,
+the samples are compared bit for bit (the 1e-5 float bar of BASELINE.json is then trivially met)."""
+import numpy as np
+import pytest
+
+from helpers import assert_bit_equal, to_dev
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (sample_rate, ch, rate_arg, pitch_arg-or-None(semitones), seconds)
+    ("pitch+3", 48000, 2, 1.0, ("st", 3.0), 4.0),
+    ("pitch-3", 48000, 2, 1.0, ("st", -3.0), 4.0),
+    ("tempo1.25keep", 48000, 2, 1.25, ("keep", 1.25), 4.0),
+    ("tempo0.8keep", 48000, 2, 0.8, ("keep", 0.8), 3.0),
+    ("velocity1.25", 48000, 2, 1.25, ("none", 0), 3.0),
+    ("velocity0.7", 44100, 2, 0.7, ("none", 0), 3.0),
+    ("pitch+7 44k", 44100, 2, 1.0, ("st", 7.0), 3.0),
+    ("mono pitch+3", 48000, 1, 1.0, ("st", 3.0), 3.0),
+    ("mono tempo 22k", 22050, 1, 1.5, ("keep", 1.5), 3.0),
+    ("11k stereo", 11025, 2, 1.0, ("st", -5.0), 3.0),
+    ("identity", 48000, 2, 1.0, ("none", 0), 2.0),
+]
+
+
+def _pitch(orc, spec, rate):
+    kind, v = spec
+    if kind == "st":
+        return orc.pitch_node_factor(v)
+    if kind == "keep":
+        return orc.velocity_node_pitch(v, True)
+    return 1.0
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_soundtouch_matches_oracle(nd, orc, case):
+    _, sr, ch, rate, spec, secs = case
+    n = int(sr * secs) + 17
+    x = orc.synth_f32(n, ch, sr, 5)
+    pitch = _pitch(orc, spec, rate)
+    ref, ref_offs, info = orc.soundtouch(x, sr, rate, pitch, 1152)
+    st = nd.SoundTouch(sr, ch, rate, pitch)
+    gi = st.info()
+    for k in ("overlap", "seek_window", "seek_length", "sample_req", "tdstretch_first"):
+        assert gi[k] == getattr(info, k), k
+    assert gi["rate"] == info.rate and gi["tempo"] == info.tempo and gi["nominal_skip"] == info.nominal_skip
+    m, nseq = st.out_frames(n, 1152)
+    assert m == ref.shape[0]
+    assert nseq == info.n_sequences
+    got, offs = st.run(to_dev(x), 1152, want_offsets=True)
+    assert np.array_equal(offs.cpu().numpy(), ref_offs), "WSOLA offset trace differs"
+    assert_bit_equal(got.cpu().numpy(), ref, "soundtouch samples")
+
+
+def test_soundtouch_batch_and_chunking(nd, orc):
+    sr, n = 48000, 48000 * 2
+    xs = np.stack([orc.synth_f32(n, 2, sr, t) for t in range(5)])
+    pitch = orc.pitch_node_factor(3.0)
+    st = nd.SoundTouch(sr, 2, 1.0, pitch)
+    got, offs = st.run(to_dev(xs), 1152, want_offsets=True)
+    for t in range(5):
+        ref, ro, _ = orc.soundtouch(xs[t], sr, 1.0, pitch, 1152)
+        assert np.array_equal(offs[t].cpu().numpy(), ro)
+        assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t}")
+    # putSamples chunking must not change the result (FIFO-driven pipeline)
+    ref4096, _, _ = orc.soundtouch(xs[0], sr, 1.0, pitch, 4096)
+    got4096 = st.run(to_dev(xs[0]), 4096)
+    assert_bit_equal(got4096.cpu().numpy(), ref4096, "frame_size 4096")
+
+
+def test_soundtouch_short_and_errors(nd, orc):
+    st = nd.SoundTouch(48000, 2, 1.0, orc.pitch_node_factor(3.0))
+    for n in (1, 100, 3000, 4704, 6000):
+        x = orc.synth_f32(n, 2, 48000, 1)
+        ref, ro, _ = orc.soundtouch(x, 48000, 1.0, orc.pitch_node_factor(3.0), 1152)
+        m, _ = st.out_frames(n, 1152)
+        assert m == ref.shape[0], n
+        if m:
+            got = st.run(to_dev(x), 1152)
+            assert_bit_equal(got.cpu().numpy(), ref, f"short {n}")
+    with pytest.raises(nd.NodeyError) as e:
+        nd.SoundTouch(96000, 2, 1.0, 1.0)       # audio-velocity.cpp:371 accepts 8 k .. 48 k only
+    assert e.value.code == -5
+    with pytest.raises(nd.NodeyError):
+        nd.SoundTouch(48000, 3, 1.0, 1.0)
