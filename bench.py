@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- offline-render realtime factor of the Nodey processor graph on B200 (BASELINE.json).
+
+Workload (configs[4], the only configuration the metric is quoted on across 1/2/4/8 GPUs and one
+that fits a single GPU): 256 independent 3 min stereo 44.1 kHz tracks through
+resample -> pitch(+3 st) -> tempo(1.25, keep pitch) -> gain -> amix tree -> master bus -> spectrum.
+Tracks are sharded over the ranks in contiguous groups of 16 (strong scaling: 256 tracks in total at
+every N); the only collective is the reduce of the partial master buses.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]       # CPU reference arm (oracle port)
+
+One JSON line on stdout (rank 0).  `value` = audio seconds rendered per second with the inputs
+resident in HBM; `e2e` = the same through host buffers (pinned H2D of every track + D2H of bus and
+spectrum inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
+
+METRIC = "offline render realtime factor (audio-s/s) & HBM GB/s vs 8 TB/s per GPU"
+UNIT = "audio-s/s"
+TRACKS, SECONDS, IN_RATE = 256, 180, 44100
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=TRACKS, help="total tracks (development only; the contract is 256)")
+    ap.add_argument("--seconds", type=int, default=SECONDS, help="track length (development only; the contract is 180)")
+    ap.add_argument("--sub-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"configs[4]: {args.tracks} x {args.seconds} s stereo 44.1 kHz float tracks, full graph "
+                        "(audio_amix(1) resample -> pitch_modifier +3 -> velocity_modifier 1.25 keep_pitch -> "
+                        "audio_volume_adjust -> audio_amix 16x tree -> master bus -> audio_spectrum 4096/1024)",
+            "tracks": args.tracks, "track_seconds": args.seconds, "sharding": f"tracks/{n_gpus} per GPU, contiguous groups of 16",
+            "collective": "ncclReduce(sum) of the partial master bus" if n_gpus > 1 else "none",
+            "audio_seconds_per_step": args.tracks * args.seconds,
+            "l2": "inputs larger than L2 (>= 2 GB per GPU per step), no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference processors on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(n_tracks, seconds, threads):
+    """One pass of the same graph on a bounded sample; returns (audio seconds, wall seconds)."""
+    from oracle import graph_oracle as G
+    from oracle import oracle as O
+    n = IN_RATE * seconds
+    tracks = [O.synth_f32(n, 2, IN_RATE, t) for t in range(n_tracks)]
+    t0 = time.perf_counter()
+    G.render(tracks, threads=threads)
+    return n_tracks * seconds, time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n_tracks, seconds = 16, 20
+    for _ in range(args.warmup):
+        cpu_sample(n_tracks, seconds, cores)
+    audio = wall = 0.0
+    for _ in range(args.steps):
+        a, w = cpu_sample(n_tracks, seconds, cores)
+        audio += a; wall += w
+    value = audio / wall
+    sample = f"{n_tracks} tracks x {seconds} s of the same graph per step (oracle port of the reference processors)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def kernel_algo_bytes(name, r, batch):
+    """ALGORITHMIC bytes one launch of `name` moves in this workload (kernel table):
+    the bytes a perfect implementation must read plus the bytes it must write, per launch."""
+    f8 = 8  # stereo float frame
+    table = {
+        "resample_tile_kernel": r.n_in * f8 + r.total1 * f8,                     # one track: in + out planes
+        "extract_planar_kernel": r.total1 * f8 * 2,
+        "tds_offsets_kernel": None,                                               # filled per node below
+        "tds_assemble_kernel": None,
+        "aa_fir_kernel": None,
+        "cubic_kernel": None,
+        "gain_f32_kernel": r.m2 * f8 * 2,
+        "to_fltp_kernel": r.m2 * f8 * 2,
+        "mix_kernel": 16 * r.m2 * f8 + r.total2 * f8,
+        "stft4096_kernel": r.total2 * f8 + 2 * r.spec_frames * 2049 * 8,
+    }
+    # SoundTouch kernels run once per node per sub-batch; both nodes read ~their input and write ~their output
+    st_in = (r.total1 + r.m1) / 2.0
+    st_out = (r.m1 + r.m2) / 2.0
+    table["tds_offsets_kernel"] = batch * st_in * f8                              # reads every input frame once; output is the trace
+    table["tds_assemble_kernel"] = batch * (st_in + st_out) * f8 / 1.0
+    table["aa_fir_kernel"] = batch * 2 * st_out * f8
+    table["cubic_kernel"] = batch * 2 * st_out * f8
+    return table.get(name)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nodey
+    import pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nodey.lib()   # fails loudly when the CUDA library is missing: there is no fallback path
+
+    n_in = IN_RATE * args.seconds
+    assert args.tracks % (16 * world) == 0, "tracks must split into groups of 16 per rank"
+    t_local = args.tracks // world
+    first = rank * t_local
+    sub = min(args.sub_batch, t_local)
+    r = pipeline.Config5Renderer(n_in, sub_batch=sub, device=dev)
+
+    # synthetic sources, generated on the device by the same generator the oracle uses
+    x_dev = torch.empty((t_local, n_in, 2), dtype=torch.float32, device=dev)
+    for t in range(t_local):
+        nodey.check(nodey.lib().nodey_synth(nodey._dp(x_dev[t]), None, n_in, 2, IN_RATE, first + t, 0, nodey._stream()))
+    torch.cuda.synchronize()
+
+    total3 = [None]
+
+    def reduce_and_spectrum(bus):
+        if world > 1:
+            dist.reduce(bus, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            return r.spectrum(bus)
+        return None
+
+    def step_device():
+        bus = r.render(x_dev, first_track=first)
+        spec = reduce_and_spectrum(bus)
+        return bus, spec
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = nodey.profile_launches()
+    ms_total = timed(step_device, args.steps)
+    launches = nodey.profile_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    audio = args.tracks * args.seconds * args.steps
+    value = audio / (ms_total * 1e-3)
+
+    # ---- per-kernel device time of one step (events around every launch; not part of the timed runs) ----
+    roofline = None
+    nodey.profile_enable(True)
+    step_device()
+    rep = nodey.profile_report()
+    nodey.profile_enable(False)
+    if rank == 0 and rep:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        name, st = top
+        per_launch_ms = st["ms"] / st["launches"]
+        ab = kernel_algo_bytes(name, r, sub)
+        achieved = (ab / (per_launch_ms * 1e-3) / 1e9) if ab else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(name)
+        except Exception:
+            pass
+        step_ms = sum(v["ms"] for v in rep.values())
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "launch_ms": per_launch_ms, "share_of_step": st["ms"] / step_ms if step_ms else None,
+                    "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---- end to end: pinned host inputs -> H2D -> render -> D2H(bus, spectrum) ----
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.empty((t_local, n_in, 2), dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x_dev)
+        torch.cuda.synchronize()
+        del x_dev
+        torch.cuda.empty_cache()
+        stage = [torch.empty((sub, n_in, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        bus_host = spec_host = None
+        h2d = t_local * n_in * 8
+        d2h = [0]
+
+        def step_e2e():
+            nonlocal bus_host, spec_host
+            cur = torch.cuda.current_stream()
+            nsub = t_local // sub
+            buses = []
+
+            def issue(s):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_free[s % 2])
+                    stage[s % 2].copy_(x_host[s * sub:(s + 1) * sub], non_blocking=True)
+                    ev_copied[s % 2].record(copy_stream)
+            issue(0)
+            for s in range(nsub):
+                if s + 1 < nsub:
+                    issue(s + 1)
+                cur.wait_event(ev_copied[s % 2])
+                buses += r.render_groups(stage[s % 2], first + s * sub)
+                ev_free[s % 2].record(cur)
+            bus = r.master(buses)
+            spec = reduce_and_spectrum(bus)
+            if rank == 0:
+                if bus_host is None:
+                    bus_host = torch.empty(bus.shape, dtype=bus.dtype, pin_memory=True)
+                    spec_host = torch.empty(spec.shape, dtype=spec.dtype, pin_memory=True)
+                    d2h[0] = bus.numel() * 4 + spec.numel() * 8
+                bus_host.copy_(bus, non_blocking=True)
+                spec_host.copy_(spec, non_blocking=True)
+
+        for e in ev_free:
+            e.record(torch.cuda.current_stream())
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e = {"value": audio / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h[0], "ms_per_step": ms_e2e / args.steps,
+               "api": "C ABI (include/nodey_cuda.h) sequenced per reference node, pinned host buffers, H2D overlapped per sub-batch"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        a, w = cpu_sample(16, 60, cores)
+        cpu_baseline = {"value": a / w, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "16 tracks x 60 s of the same graph, oracle port of the reference processors, one track chain per host thread"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+               "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

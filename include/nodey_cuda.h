@@ -126,6 +126,32 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r,
                        const float* volumes, int nin, int flush, int64_t out_frames,
                        nodey_stream_t stream);
 
+/* A4  audio_amix frame bookkeeping (host only, no device work), audio-amix.cpp:149-322.  The node pulls
+ * one frame per input and iteration, asks swr for nb = min(frame sizes) frames (1152 once the inputs
+ * ran dry) and zero fills what swr did not deliver, until every input is flushed.  Inputs are
+ * described by their rate and their frame sizes, run-length encoded: input i owns runs
+ * run_off[i] .. run_off[i+1]-1, run r = run_count[r] frames of run_len[r] samples.  Returns the
+ * node's total output frames (whole iterations, i.e. zero padded) and
+ *   - where every input's resampled frames land: segment k copies seg_len[k] frames of input
+ *     seg_input[k], from its resampled frame seg_src_start[k], to output frame seg_out_start[k]
+ *     (up-sampled inputs: one segment from 0; inputs above 48 kHz deliver less than nb per iteration
+ *     and leave gaps -- reference behaviour);
+ *   - the frame sizes of the node's own output stream, run-length encoded (out_run_*).
+ * At most seg_cap / out_run_cap entries are written; *nseg_out / *n_out_runs receive the numbers
+ * needed.  Negative return = error code. */
+int64_t nodey_amix_plan(const int* in_rate, int nin, const int64_t* run_off, const int64_t* run_len,
+                        const int64_t* run_count, int index_mask_quirk,
+                        int32_t* seg_input, int64_t* seg_out_start, int64_t* seg_src_start, int64_t* seg_len,
+                        int64_t seg_cap, int64_t* nseg_out,
+                        int64_t* out_run_len, int64_t* out_run_count, int64_t out_run_cap, int64_t* n_out_runs);
+
+/* Launch accounting: every kernel launch of the library is counted; with profiling enabled each
+ * launch is bracketed by CUDA events on its stream and nodey_profile_report() writes a JSON object
+ * {"kernel": {"launches": n, "ms": device ms, "bytes": 0}} of the launches since the last report. */
+void nodey_profile_enable(int on);
+uint64_t nodey_profile_launches(void);
+int nodey_profile_report(char* buf, int cap);
+
 /* A9  pitch_modifier / velocity_modifier -- soundtouch_process_payload, src/processor/audio-velocity.cpp:265-443:
  * new SoundTouch; setSampleRate; setChannels; setRate(rate); setPitch(pitch) (:367-390), then
  * putSamples per frame, receiveSamples, flush (:399-435).  SoundTouch 2.3.2 float build with default

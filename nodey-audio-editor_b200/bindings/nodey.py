@@ -23,7 +23,8 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run",
+    "nodey_soundtouch_run", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_profile_report",
 ]
 
 
@@ -80,6 +81,14 @@ def lib():
     L.nodey_soundtouch_out_frames.argtypes = [vp, i64, i32, C.POINTER(i64)]
     L.nodey_soundtouch_out_frames.restype = i64
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
+    L.nodey_amix_plan.argtypes = [C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32,
+                                  C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64),
+                                  C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64)]
+    L.nodey_amix_plan.restype = i64
+    L.nodey_profile_enable.argtypes = [i32]
+    L.nodey_profile_enable.restype = None
+    L.nodey_profile_launches.restype = C.c_uint64
+    L.nodey_profile_report.argtypes = [C.c_char_p, i32]
     _lib = L
     return L
 
@@ -290,6 +299,57 @@ def stft(x, interleaved, nfft=4096, hop=1024, out=None):
         out = t.empty((nch, m, nfft // 2 + 1), dtype=t.complex64, device=x.device)
     check(lib().nodey_stft(_dp(out), _dp(x), n, nch, 1 if interleaved else 0, stride, nfft, hop, _stream()))
     return out
+
+
+def uniform_runs(nframes, frame_size=1152):
+    """frame sizes of a stream cut into frame_size chunks, run-length encoded [(len, count), ...]"""
+    q, r = divmod(int(nframes), int(frame_size))
+    runs = []
+    if q:
+        runs.append((frame_size, q))
+    if r:
+        runs.append((r, 1))
+    return runs
+
+
+def amix_plan(in_rates, in_runs, quirk=0, seg_cap=4096, run_cap=4096):
+    """Host-only bookkeeping of audio_amix.  in_runs[i] = [(frame_len, count), ...].
+    Returns (total_out_frames, [(input, out_start, src_start, len), ...], out_runs)."""
+    nin = len(in_rates)
+    off = [0]
+    rl, rc = [], []
+    for runs in in_runs:
+        for l, c in runs:
+            rl.append(int(l)); rc.append(int(c))
+        off.append(len(rl))
+    si = (C.c_int32 * seg_cap)(); so = (C.c_int64 * seg_cap)(); ss = (C.c_int64 * seg_cap)(); sl = (C.c_int64 * seg_cap)()
+    orl = (C.c_int64 * run_cap)(); orc = (C.c_int64 * run_cap)()
+    nseg = C.c_int64(); nrun = C.c_int64()
+    n = max(len(rl), 1)
+    total = lib().nodey_amix_plan((C.c_int * nin)(*in_rates), nin, (C.c_int64 * (nin + 1))(*off),
+                                  (C.c_int64 * n)(*rl), (C.c_int64 * n)(*rc), quirk, si, so, ss, sl, seg_cap,
+                                  C.byref(nseg), orl, orc, run_cap, C.byref(nrun))
+    if total < 0:
+        raise NodeyError(total, lib().nodey_last_error().decode())
+    if nseg.value > seg_cap or nrun.value > run_cap:
+        return amix_plan(in_rates, in_runs, quirk, max(seg_cap, nseg.value), max(run_cap, nrun.value))
+    return (total, [(si[k], so[k], ss[k], sl[k]) for k in range(nseg.value)],
+            [(orl[k], orc[k]) for k in range(nrun.value)])
+
+
+def profile_enable(on):
+    lib().nodey_profile_enable(1 if on else 0)
+
+
+def profile_launches():
+    return int(lib().nodey_profile_launches())
+
+
+def profile_report():
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    lib().nodey_profile_report(buf, len(buf))
+    return json.loads(buf.value.decode())
 
 
 class SoundTouch:

@@ -31,6 +31,22 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (!(cond)) { ::nodey::set_error(__VA_ARGS__); return (code); }           \
     } while (0)
 
+// Every kernel launch site opens one of these: it counts the launch (nodey_profile_launches) and,
+// while profiling is enabled, brackets the launch with CUDA events on the launching stream so that
+// nodey_profile_report() can give per-kernel device time (bench.py's roofline leg).
+struct LaunchScope {
+    LaunchScope(const char* name, cudaStream_t st, double algo_bytes = 0.0);
+    ~LaunchScope();
+    void* rec;
+    cudaStream_t st;
+};
+
+#define NODEY_LAUNCH(name, stream, ...)                                            \
+    do {                                                                           \
+        ::nodey::LaunchScope _ls(name, stream);                                    \
+        __VA_ARGS__;                                                               \
+    } while (0)
+
 // SM count of the current device (cached); grids are sized in multiples of it.
 int sm_count();
 

@@ -325,34 +325,16 @@ static int64_t plan_reflect(const nodey_resampler* r, int64_t n, int64_t produce
 
 using namespace nodey;
 
-static size_t tile_geometry(const nodey_resampler* r, TileArgs& a, int ch)
+// resample_init() with the library defaults the reference leaves untouched (host-only numbers + bank)
+static void plan_init_math(nodey_resampler* r, int index_mask_quirk)
 {
-    a.P = r->phase_count; a.D = r->dst_incr_div; a.L = r->filter_length; a.center = (r->filter_length - 1) / 2;
-    a.n_groups = r->n_groups; a.wmax = r->wmax; a.s0 = r->s0; a.span = r->span;
-    a.in_tile = (kNB - 1) * a.D + a.span + a.wmax + 1;
-    a.out_stride = (a.n_groups * kG) | 1;
-    return sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) +
-                            2 * (size_t)kNB * a.out_stride + (size_t)a.in_tile * ch + 4);
-}
-
-
-extern "C" {
-
-int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int index_mask_quirk)
-{
-    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_resampler_create: null out pointer");
-    NODEY_REQUIRE(in_rate > 0 && out_rate > 0, NODEY_E_INVALID, "nodey_resampler_create: bad sample rate");
-    nodey_resampler* r = new nodey_resampler();
-    r->in_rate = in_rate; r->out_rate = out_rate;
+    const int in_rate = r->in_rate, out_rate = r->out_rate;
     r->resample = in_rate != out_rate;
-    cudaGetDevice(&r->device);
     if (!r->resample) {
         r->phase_count = 1; r->filter_length = 1; r->filter_alloc = 8;
         r->src_incr = r->dst_incr = 1; r->dst_incr_div = 1; r->dst_incr_mod = 0; r->index0 = 0;
-        *out = r;
-        return NODEY_OK;
+        return;
     }
-    // resample_init() with the library defaults the reference leaves untouched
     double factor = (double)out_rate * 0.97 / in_rate;
     if (factor > 1.0) factor = 1.0;
     int phase_count = 1 << 10;
@@ -384,10 +366,41 @@ int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int
         const int idx = -phase_count * ((filter_length - 1) / 2);
         r->index0 = index_mask_quirk ? (idx & (phase_count - 1)) : 0;
     }
+}
+
+static size_t tile_geometry(const nodey_resampler* r, TileArgs& a, int ch)
+{
+    a.P = r->phase_count; a.D = r->dst_incr_div; a.L = r->filter_length; a.center = (r->filter_length - 1) / 2;
+    a.n_groups = r->n_groups; a.wmax = r->wmax; a.s0 = r->s0; a.span = r->span;
+    a.in_tile = (kNB - 1) * a.D + a.span + a.wmax + 1;
+    a.out_stride = (a.n_groups * kG) | 1;
+    return sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) +
+                            2 * (size_t)kNB * a.out_stride + (size_t)a.in_tile * ch + 4);
+}
+
+
+extern "C" {
+
+int nodey_resampler_create(nodey_resampler** out, int in_rate, int out_rate, int index_mask_quirk)
+{
+    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_resampler_create: null out pointer");
+    NODEY_REQUIRE(in_rate > 0 && out_rate > 0, NODEY_E_INVALID, "nodey_resampler_create: bad sample rate");
+    nodey_resampler* r = new nodey_resampler();
+    r->in_rate = in_rate; r->out_rate = out_rate;
+    r->resample = in_rate != out_rate;
+    cudaGetDevice(&r->device);
+    if (!r->resample) {
+        r->phase_count = 1; r->filter_length = 1; r->filter_alloc = 8;
+        r->src_incr = r->dst_incr = 1; r->dst_incr_div = 1; r->dst_incr_mod = 0; r->index0 = 0;
+        *out = r;
+        return NODEY_OK;
+    }
+    plan_init_math(r, index_mask_quirk);
     int rc = upload(r->bank.data(), r->bank.size() * sizeof(float), (void**)&r->d_bank);
     if (rc != NODEY_OK) { delete r; return rc; }
 
     // tile-kernel tables: only for exact plans (no inter-phase interpolation)
+    const int phase_count = r->phase_count, filter_length = r->filter_length;
     if (r->dst_incr_mod == 0 && phase_count <= 1024 && filter_length <= 256) {
         const int P = phase_count, D = r->dst_incr_div, L = filter_length;
         std::vector<int> s_t((size_t)P), ph_t((size_t)P);
@@ -481,10 +494,10 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
     if (grid < 1) grid = 1;
     if (ch == 2) {
         NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_tile_kernel<2><<<grid, threads, smem, st>>>(out_l, out_r, a);
+        NODEY_LAUNCH("resample_tile_kernel", st, resample_tile_kernel<2><<<grid, threads, smem, st>>>(out_l, out_r, a));
     } else {
         NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        resample_tile_kernel<1><<<grid, threads, smem, st>>>(out_l, out_r, a);
+        NODEY_LAUNCH("resample_tile_kernel", st, resample_tile_kernel<1><<<grid, threads, smem, st>>>(out_l, out_r, a));
     }
     NODEY_LAUNCH_OK();
     return NODEY_OK;
@@ -518,7 +531,7 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
     int rc = fill_src(&s, r, p0, p1, fmt, nch, in_frames, flush);
     if (rc != NODEY_OK) return rc;
     PlanDev pl{r->d_bank, r->phase_count, r->filter_length, r->filter_alloc, r->dst_incr_div, r->dst_incr_mod, r->src_incr, r->index0};
-    resample_generic_kernel<<<stream_grid(out_frames, 256, 8), 256, 0, st>>>(out_l, out_r, s, pl, out_frames);
+    NODEY_LAUNCH("resample_generic_kernel", st, resample_generic_kernel<<<stream_grid(out_frames, 256, 8), 256, 0, st>>>(out_l, out_r, s, pl, out_frames));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -553,6 +566,90 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r, con
     }
     a.nin = nin; a.mix = 1; a.out_frames = out_frames;
     return launch_tile(r, out_l, out_r, a, ch, as_stream(stream));
+}
+
+/* audio_amix frame bookkeeping, audio-amix.cpp:149-322 (see nodey_cuda.h) */
+int64_t nodey_amix_plan(const int* in_rate, int nin, const int64_t* run_off, const int64_t* run_len,
+                        const int64_t* run_count, int index_mask_quirk,
+                        int32_t* seg_input, int64_t* seg_out_start, int64_t* seg_src_start, int64_t* seg_len,
+                        int64_t seg_cap, int64_t* nseg_out,
+                        int64_t* out_run_len, int64_t* out_run_count, int64_t out_run_cap, int64_t* n_out_runs)
+{
+    if (!in_rate || !run_off || !run_len || !run_count || nin < 1 || nin > NODEY_MAX_MIX_INPUTS) {
+        set_error("nodey_amix_plan: input_num %d outside 1..16 or null argument", nin);
+        return NODEY_E_RANGE;
+    }
+    struct In {
+        nodey_resampler plan;
+        int64_t run = 0, run_end = 0, left = 0;      // cursor into the frame-size runs
+        int64_t n_in = 0, produced = 0, reflect = 0;
+        int flushed = 0;
+    };
+    std::vector<In> st((size_t)nin);
+    for (int i = 0; i < nin; i++) {
+        In& s = st[(size_t)i];
+        if (in_rate[i] <= 0 || run_off[i + 1] < run_off[i]) { set_error("nodey_amix_plan: bad input %d", i); return NODEY_E_INVALID; }
+        s.plan.in_rate = in_rate[i]; s.plan.out_rate = 48000;
+        plan_init_math(&s.plan, index_mask_quirk);
+        s.run = run_off[i]; s.run_end = run_off[i + 1];
+        while (s.run < s.run_end && (run_count[s.run] <= 0 || run_len[s.run] <= 0)) s.run++;
+        s.left = s.run < s.run_end ? run_count[s.run] : 0;
+    }
+    int64_t written = 0, nseg = 0, nruns = 0;
+    std::vector<int64_t> last_seg((size_t)nin, -1);
+    for (;;) {
+        int64_t nb = INT64_MAX;
+        for (int i = 0; i < nin; i++) {
+            In& s = st[(size_t)i];
+            if (s.run < s.run_end && run_len[s.run] < nb) nb = run_len[s.run];
+        }
+        if (nb == INT64_MAX) nb = 1152;
+        int count = 0;
+        for (int i = 0; i < nin; i++) {
+            In& s = st[(size_t)i];
+            int64_t got;
+            if (s.run < s.run_end) {
+                s.n_in += run_len[s.run];
+                if (--s.left == 0) {
+                    s.run++;
+                    while (s.run < s.run_end && (run_count[s.run] <= 0 || run_len[s.run] <= 0)) s.run++;
+                    s.left = s.run < s.run_end ? run_count[s.run] : 0;
+                }
+                const int64_t avail = s.plan.resample ? plan_producible(&s.plan, s.n_in, 0) : s.n_in;
+                got = avail - s.produced;
+                if (got > nb) got = nb;
+            } else {
+                if (!s.flushed) { s.flushed = 1; if (s.plan.resample) s.reflect = plan_reflect(&s.plan, s.n_in, s.produced); }
+                const int64_t avail = s.plan.resample ? plan_producible(&s.plan, s.n_in, s.reflect) : s.n_in;
+                got = avail - s.produced;
+                if (got > nb) got = nb;
+                if (got < nb) count++;
+            }
+            if (got < 0) got = 0;
+            if (got > 0) {
+                const int64_t ls = last_seg[(size_t)i];
+                if (ls >= 0 && ls < seg_cap && seg_out_start[ls] + seg_len[ls] == written && seg_src_start[ls] + seg_len[ls] == s.produced) {
+                    seg_len[ls] += got;
+                } else {
+                    if (nseg < seg_cap) { seg_input[nseg] = i; seg_out_start[nseg] = written; seg_src_start[nseg] = s.produced; seg_len[nseg] = got; }
+                    last_seg[(size_t)i] = nseg;
+                    nseg++;
+                }
+                s.produced += got;
+            }
+        }
+        // the emitted frame of this iteration has nb samples: run-length encode the frame sizes
+        if (nruns > 0 && nruns <= out_run_cap && out_run_len && out_run_len[nruns - 1] == nb) out_run_count[nruns - 1]++;
+        else {
+            if (out_run_len && nruns < out_run_cap) { out_run_len[nruns] = nb; out_run_count[nruns] = 1; }
+            nruns++;
+        }
+        written += nb;
+        if (count == nin) break;
+    }
+    if (nseg_out) *nseg_out = nseg;
+    if (n_out_runs) *n_out_runs = nruns;
+    return written;
 }
 
 }  // extern "C"

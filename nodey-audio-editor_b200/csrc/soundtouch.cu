@@ -698,10 +698,10 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         if (nseq > 1) {
             if (CH == 2) {
                 NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                tds_offsets_kernel<2><<<ntracks, kTdsThreads, smem, st>>>(ta);
+                NODEY_LAUNCH("tds_offsets_kernel", st, tds_offsets_kernel<2><<<ntracks, kTdsThreads, smem, st>>>(ta));
             } else {
                 NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                tds_offsets_kernel<1><<<ntracks, kTdsThreads, smem, st>>>(ta);
+                NODEY_LAUNCH("tds_offsets_kernel", st, tds_offsets_kernel<1><<<ntracks, kTdsThreads, smem, st>>>(ta));
             }
             NODEY_LAUNCH_OK();
         }
@@ -710,7 +710,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         aa.offs = d_offs; aa.offs_stride = offs_stride; aa.fade = s->d_fade; aa.nseq = (int)nseq;
         aa.overlap = s->overlap; aa.seek_window = s->seek_window;
         dim3 grid((unsigned)nseq, (unsigned)ntracks);
-        if (CH == 2) tds_assemble_kernel<2><<<grid, 256, 0, st>>>(aa); else tds_assemble_kernel<1><<<grid, 256, 0, st>>>(aa);
+        if (CH == 2) NODEY_LAUNCH("tds_assemble_kernel", st, tds_assemble_kernel<2><<<grid, 256, 0, st>>>(aa)); else NODEY_LAUNCH("tds_assemble_kernel", st, tds_assemble_kernel<1><<<grid, 256, 0, st>>>(aa));
         NODEY_LAUNCH_OK();
         return NODEY_OK;
     };
@@ -720,7 +720,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         long long tiles = (count + kFirTile - 1) / kFirTile;
         long long gx = tiles < 65535 ? tiles : 65535;
         dim3 grid((unsigned)gx, (unsigned)ntracks);
-        if (CH == 2) aa_fir_kernel<2><<<grid, kFirThreads, 0, st>>>(fa); else aa_fir_kernel<1><<<grid, kFirThreads, 0, st>>>(fa);
+        if (CH == 2) NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_kernel<2><<<grid, kFirThreads, 0, st>>>(fa)); else NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_kernel<1><<<grid, kFirThreads, 0, st>>>(fa));
         NODEY_LAUNCH_OK();
         return NODEY_OK;
     };
@@ -730,7 +730,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         long long blocks = (count + 255) / 256;
         const long long cap = (long long)sm_count() * 8;
         dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)ntracks);
-        if (CH == 2) cubic_kernel<2><<<grid, 256, 0, st>>>(ca); else cubic_kernel<1><<<grid, 256, 0, st>>>(ca);
+        if (CH == 2) NODEY_LAUNCH("cubic_kernel", st, cubic_kernel<2><<<grid, 256, 0, st>>>(ca)); else NODEY_LAUNCH("cubic_kernel", st, cubic_kernel<1><<<grid, 256, 0, st>>>(ca));
         NODEY_LAUNCH_OK();
         return NODEY_OK;
     };

@@ -239,7 +239,7 @@ int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int
     const int64_t items = frames * nch;
     const int64_t cap = (int64_t)sm_count() * 3;
     const int grid = (int)(items < cap ? items : cap);
-    stft4096_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(a);
+    NODEY_LAUNCH("stft4096_kernel", as_stream(stream), stft4096_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(a));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }

@@ -8,6 +8,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace nodey {
 
@@ -37,6 +42,32 @@ int sm_count()
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
     cached = n;
     return n;
+}
+
+// ---- launch accounting ---------------------------------------------------------------------------
+struct LaunchRec { const char* name; cudaEvent_t a, b; double bytes; };
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_profiling{0};
+static std::mutex g_prof_mu;
+static std::vector<LaunchRec*> g_recs;
+
+LaunchScope::LaunchScope(const char* name, cudaStream_t s, double algo_bytes) : rec(nullptr), st(s)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_profiling.load(std::memory_order_relaxed)) return;
+    LaunchRec* r = new LaunchRec{name, nullptr, nullptr, algo_bytes};
+    if (cudaEventCreate(&r->a) != cudaSuccess || cudaEventCreate(&r->b) != cudaSuccess) { delete r; return; }
+    cudaEventRecord(r->a, st);
+    rec = r;
+}
+
+LaunchScope::~LaunchScope()
+{
+    if (!rec) return;
+    LaunchRec* r = (LaunchRec*)rec;
+    cudaEventRecord(r->b, st);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_recs.push_back(r);
 }
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -388,6 +419,39 @@ int nodey_version(void) { return 100; }
 
 const char* nodey_last_error(void) { return g_err; }
 
+void nodey_profile_enable(int on) { g_profiling.store(on ? 1 : 0); }
+
+uint64_t nodey_profile_launches(void) { return g_launches.load(); }
+
+/* JSON object {"kernel": {"launches": n, "ms": total device ms, "bytes": algorithmic bytes}, ...} of every
+ * launch recorded since the last report; synchronises the device.  Returns the length written. */
+int nodey_profile_report(char* buf, int cap)
+{
+    cudaDeviceSynchronize();
+    std::vector<LaunchRec*> recs;
+    { std::lock_guard<std::mutex> lock(g_prof_mu); recs.swap(g_recs); }
+    struct Agg { unsigned long long n = 0; double ms = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    for (LaunchRec* r : recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess) { Agg& g = agg[r->name]; g.n++; g.ms += ms; g.bytes += r->bytes; }
+        cudaEventDestroy(r->a); cudaEventDestroy(r->b);
+        delete r;
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"bytes\": %.0f}", first ? "" : ", ",
+                 kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", out.c_str()); }
+    return (int)out.size();
+}
+
 int nodey_device_info(int* sms, int* major, int* minor, int64_t* total_mem)
 {
     int dev = 0;
@@ -414,8 +478,8 @@ int nodey_synth(float* dst_f32, int16_t* dst_s16, int64_t nframes, int nch, int 
         step[c] = (unsigned)llrint(f / (double)sample_rate * 4294967296.0);
     }
     const unsigned seed0 = 0xA0D10u + 131u * (unsigned)track;
-    synth_kernel<<<stream_grid(nframes * nch, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
-        dst_f32, dst_s16, nframes, nch, step[0], step[1], seed0, frame0);
+    NODEY_LAUNCH("synth_kernel", as_stream(stream), synth_kernel<<<stream_grid(nframes * nch, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
+        dst_f32, dst_s16, nframes, nch, step[0], step[1], seed0, frame0));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -428,13 +492,13 @@ int nodey_gain(void* dst, const void* src, int fmt, int64_t n, float volume, nod
     cudaStream_t st = as_stream(stream);
     switch (fmt) {
     case NODEY_FMT_FLT: case NODEY_FMT_FLTP:
-        gain_f32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((float*)dst, (const float*)src, n, volume, vec);
+        NODEY_LAUNCH("gain_f32_kernel", st, gain_f32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((float*)dst, (const float*)src, n, volume, vec));
         break;
     case NODEY_FMT_S16: case NODEY_FMT_S16P:
-        gain_s16_kernel<<<stream_grid(n / 8 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dst, (const short*)src, n, volume, vec);
+        NODEY_LAUNCH("gain_s16_kernel", st, gain_s16_kernel<<<stream_grid(n / 8 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dst, (const short*)src, n, volume, vec));
         break;
     case NODEY_FMT_S32: case NODEY_FMT_S32P:
-        gain_s32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dst, (const int*)src, n, volume, vec);
+        NODEY_LAUNCH("gain_s32_kernel", st, gain_s32_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dst, (const int*)src, n, volume, vec));
         break;
     default:
         set_error("Audio format is not support (Include FLT, S16, S32): %d", fmt);
@@ -457,11 +521,11 @@ int nodey_extract_interleaved(float* dst, const void* p0, const void* p1, int fm
     case NODEY_FMT_FLT:
         NODEY_CUDA_OK(cudaMemcpyAsync(dst, p0, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         return NODEY_OK;
-    case NODEY_FMT_S16: extract_packed_kernel<NODEY_FMT_S16><<<g, kBlock, 0, st>>>(dst, p0, n); break;
-    case NODEY_FMT_S32: extract_packed_kernel<NODEY_FMT_S32><<<g, kBlock, 0, st>>>(dst, p0, n); break;
-    case NODEY_FMT_FLTP: extract_planar_kernel<NODEY_FMT_FLTP><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
-    case NODEY_FMT_S16P: extract_planar_kernel<NODEY_FMT_S16P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
-    case NODEY_FMT_S32P: extract_planar_kernel<NODEY_FMT_S32P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch); break;
+    case NODEY_FMT_S16: NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<NODEY_FMT_S16><<<g, kBlock, 0, st>>>(dst, p0, n)); break;
+    case NODEY_FMT_S32: NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<NODEY_FMT_S32><<<g, kBlock, 0, st>>>(dst, p0, n)); break;
+    case NODEY_FMT_FLTP: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_FLTP><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
+    case NODEY_FMT_S16P: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_S16P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
+    case NODEY_FMT_S32P: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_S32P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
     default:
         set_error("Unsupported sample format: %d", fmt);
         return NODEY_E_FORMAT;
@@ -478,12 +542,12 @@ int nodey_split(void* dl, void* dr, const void* p0, const void* p1, int fmt, int
     switch (fmt) {
     case NODEY_FMT_FLT: case NODEY_FMT_S32:
         if (aligned16(dl) && aligned16(dr) && aligned16(p0))
-            split32_vec_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n);
+            NODEY_LAUNCH("split32_vec_kernel", st, split32_vec_kernel<<<stream_grid(n / 4 + 1, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n));
         else
-            split_kernel<int><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n);
+            NODEY_LAUNCH("split_kernel", st, split_kernel<int><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((int*)dl, (int*)dr, (const int*)p0, n));
         break;
     case NODEY_FMT_S16:
-        split_kernel<short><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dl, (short*)dr, (const short*)p0, n);
+        NODEY_LAUNCH("split_kernel", st, split_kernel<short><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>((short*)dl, (short*)dr, (const short*)p0, n));
         break;
     case NODEY_FMT_FLTP: case NODEY_FMT_S32P: case NODEY_FMT_S16P: {
         const size_t bytes = (size_t)n * (size_t)fmt_bytes(fmt);
@@ -505,8 +569,8 @@ int nodey_to_fltp_stereo(float* dl, float* dr, const void* p0, const void* p1, i
     NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "Invalid channel layout: %d", nch);
     NODEY_REQUIRE(fmt_bytes(fmt) != 0, NODEY_E_FORMAT, "nodey_to_fltp_stereo: unsupported sample format %d", fmt);
     if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
-    to_fltp_kernel<<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dl, dr, p0, p1, fmt,
-                                                                                       fmt_planar(fmt) ? 1 : 0, nch, n);
+    NODEY_LAUNCH("to_fltp_kernel", as_stream(stream), to_fltp_kernel<<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dl, dr, p0, p1, fmt,
+                                                                                       fmt_planar(fmt) ? 1 : 0, nch, n));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -524,7 +588,7 @@ int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float*
         a.l[i] = in_l[i]; a.r[i] = in_r[i]; a.len[i] = in_len[i]; a.vol[i] = volumes[i];
         a.vec = a.vec && aligned16(in_l[i]) && aligned16(in_r[i]);
     }
-    mix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(out_l, out_r, a, n);
+    NODEY_LAUNCH("mix_kernel", as_stream(stream), mix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(out_l, out_r, a, n));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -535,8 +599,8 @@ int nodey_bimix(float* out_l, float* out_r, const float* ll, const float* lr, in
     if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
     const int vec = aligned16(out_l) && aligned16(out_r) && aligned16(ll) && aligned16(lr) && aligned16(rl) && aligned16(rr);
     const float bias_minus = 1 - bias, bias_plus = 1 + bias;
-    bimix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
-        out_l, out_r, ll, lr, len_l, rl, rr, len_r, bias_minus, bias_plus, n, vec);
+    NODEY_LAUNCH("bimix_kernel", as_stream(stream), bimix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(
+        out_l, out_r, ll, lr, len_l, rl, rr, len_r, bias_minus, bias_plus, n, vec));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -545,7 +609,7 @@ int nodey_downmix_half(float* dst, const float* l, const float* r, int64_t n, no
 {
     if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
     const int vec = aligned16(dst) && aligned16(l) && aligned16(r);
-    downmix_half_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dst, l, r, n, vec);
+    NODEY_LAUNCH("downmix_half_kernel", as_stream(stream), downmix_half_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dst, l, r, n, vec));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
@@ -572,7 +636,7 @@ int nodey_merge_segments(float* out, const float* left, const float* right, cons
     free(h);
     if (e != cudaSuccess) { cudaFreeAsync(d, st); return cuda_fail(e, "segment upload", __FILE__, __LINE__); }
     if (total > 0)
-        merge_segments_kernel<<<stream_grid(total, kBlock, kCtasPerSm), kBlock, 0, st>>>((float2*)out, left, right, d, nseg, total);
+        NODEY_LAUNCH("merge_segments_kernel", st, merge_segments_kernel<<<stream_grid(total, kBlock, kCtasPerSm), kBlock, 0, st>>>((float2*)out, left, right, d, nseg, total));
     e = cudaPeekAtLastError();
     cudaFreeAsync(d, st);
     if (e != cudaSuccess) return cuda_fail(e, "merge_segments_kernel", __FILE__, __LINE__);

@@ -504,17 +504,36 @@ int64_t orc_swr_out_count(int in_rate, int out_rate, int quirk, int64_t in_frame
 /* frame-stream helpers: the reference moves AVFrames of `frame_size` samples               */
 /* ======================================================================================= */
 static int track_bps(const orc_track* t) { return (t->fmt == ORC_FMT_S16 || t->fmt == ORC_FMT_S16P) ? 2 : 4; }
-static int64_t track_frames(const orc_track* t) { return (t->nframes + t->frame_size - 1) / t->frame_size; }
-static int track_frame_len(const orc_track* t, int64_t f)
+
+/* frame boundaries of a track: uniform frame_size chunks, or the run-length encoded sizes when the
+ * producer was a node whose frames are not uniform (an amix output: nb per iteration) */
+typedef struct { int64_t n; int64_t* start; } frame_index;
+
+static frame_index fi_build(const orc_track* t)
 {
-    const int64_t start = f * t->frame_size;
-    const int64_t n = t->nframes - start;
-    return (int)(n < t->frame_size ? n : t->frame_size);
+    frame_index fi;
+    int64_t n = 0;
+    if (t->nruns > 0) { for (int r = 0; r < t->nruns; r++) if (t->run_len[r] > 0 && t->run_count[r] > 0) n += t->run_count[r]; }
+    else n = (t->nframes + t->frame_size - 1) / t->frame_size;
+    fi.n = n;
+    fi.start = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int64_t pos = 0, k = 0;
+    if (t->nruns > 0) {
+        for (int r = 0; r < t->nruns; r++)
+            for (int64_t c = 0; c < t->run_count[r] && t->run_len[r] > 0; c++) { fi.start[k++] = pos; pos += t->run_len[r]; }
+        fi.start[n] = pos;
+    } else {
+        for (; k < n; k++) { fi.start[k] = pos; pos += t->frame_size; }
+        fi.start[n] = t->nframes;
+    }
+    return fi;
 }
-static void track_frame_ptrs(const orc_track* t, int64_t f, const void** p0, const void** p1)
+static int64_t fi_frames(const frame_index* fi) { return fi->n; }
+static int fi_len(const frame_index* fi, int64_t f) { return (int)(fi->start[f + 1] - fi->start[f]); }
+static void fi_ptrs(const orc_track* t, const frame_index* fi, int64_t f, const void** p0, const void** p1)
 {
     const int planar = t->fmt >= ORC_FMT_U8P;
-    const size_t off = (size_t)f * (size_t)t->frame_size * (size_t)track_bps(t);
+    const size_t off = (size_t)fi->start[f] * (size_t)track_bps(t);
     *p0 = (const char*)t->plane0 + off * (size_t)(planar ? 1 : t->ch);
     *p1 = (planar && t->plane1) ? (const char*)t->plane1 + off : NULL;
 }
@@ -534,10 +553,12 @@ int64_t orc_amix(const orc_track* in, int nin, const float* volumes, int quirk,
     orc_swr** sw = (orc_swr**)calloc((size_t)nin, sizeof(*sw));
     float** dl = (float**)calloc((size_t)nin, sizeof(float*));
     float** dr = (float**)calloc((size_t)nin, sizeof(float*));
+    frame_index* fi = (frame_index*)calloc((size_t)nin, sizeof(*fi));
     int maxfs = 1152;
     for (int i = 0; i < nin; i++) {
         sw[i] = orc_swr_create(in[i].rate, 48000, in[i].fmt, in[i].ch, quirk);
-        if (in[i].frame_size > maxfs) maxfs = in[i].frame_size;
+        fi[i] = fi_build(&in[i]);
+        for (int64_t f = 0; f < fi[i].n; f++) if (fi_len(&fi[i], f) > maxfs) maxfs = fi_len(&fi[i], f);
     }
     for (int i = 0; i < nin; i++) {
         dl[i] = (float*)malloc(sizeof(float) * (size_t)maxfs);
@@ -547,16 +568,16 @@ int64_t orc_amix(const orc_track* in, int nin, const float* volumes, int quirk,
     for (int64_t m = 0;; m++) {
         int nb = INT_MAX;
         for (int i = 0; i < nin; i++)
-            if (m < track_frames(&in[i])) { const int n = track_frame_len(&in[i], m); if (n < nb) nb = n; }
+            if (m < fi_frames(&fi[i])) { const int n = fi_len(&fi[i], m); if (n < nb) nb = n; }
         if (nb == INT_MAX) nb = 1152;
         if (written + nb > out_cap) break;
         int count = 0;
         for (int i = 0; i < nin; i++) {
             memset(dl[i], 0, sizeof(float) * (size_t)nb);
             memset(dr[i], 0, sizeof(float) * (size_t)nb);
-            if (m < track_frames(&in[i])) {
-                const void *p0, *p1; track_frame_ptrs(&in[i], m, &p0, &p1);
-                orc_swr_convert(sw[i], dl[i], dr[i], nb, p0, p1, track_frame_len(&in[i], m));
+            if (m < fi_frames(&fi[i])) {
+                const void *p0, *p1; fi_ptrs(&in[i], &fi[i], m, &p0, &p1);
+                orc_swr_convert(sw[i], dl[i], dr[i], nb, p0, p1, fi_len(&fi[i], m));
             } else {
                 const int c = orc_swr_convert(sw[i], dl[i], dr[i], nb, NULL, NULL, 0);
                 if (c < nb) count++;
@@ -574,8 +595,8 @@ int64_t orc_amix(const orc_track* in, int nin, const float* volumes, int quirk,
         written += nb;
         if (count == nin) break;
     }
-    for (int i = 0; i < nin; i++) { orc_swr_free(sw[i]); free(dl[i]); free(dr[i]); }
-    free(sw); free(dl); free(dr);
+    for (int i = 0; i < nin; i++) { orc_swr_free(sw[i]); free(dl[i]); free(dr[i]); free(fi[i].start); }
+    free(sw); free(dl); free(dr); free(fi);
     return written;
 }
 
@@ -589,28 +610,30 @@ int64_t orc_bimix(const orc_track* l, const orc_track* r, float bias, int quirk,
 {
     orc_swr* sl = orc_swr_create(l->rate, 48000, l->fmt, l->ch, quirk);
     orc_swr* sr = orc_swr_create(r->rate, 48000, r->fmt, r->ch, quirk);
-    int maxfs = l->frame_size > r->frame_size ? l->frame_size : r->frame_size;
-    if (maxfs < 1152) maxfs = 1152;
+    frame_index fl_ = fi_build(l), fr_ = fi_build(r);
+    int maxfs = 1152;
+    for (int64_t f = 0; f < fl_.n; f++) if (fi_len(&fl_, f) > maxfs) maxfs = fi_len(&fl_, f);
+    for (int64_t f = 0; f < fr_.n; f++) if (fi_len(&fr_, f) > maxfs) maxfs = fi_len(&fr_, f);
     float* d1[2]; float* d2[2];
     for (int c = 0; c < 2; c++) { d1[c] = (float*)malloc(sizeof(float) * (size_t)maxfs); d2[c] = (float*)malloc(sizeof(float) * (size_t)maxfs); }
     const float bias_minus = (1 - bias), bias_plus = (1 + bias);
     int64_t written = 0;
     for (int64_t m = 0;; m++) {
-        const int has_l = m < track_frames(l), has_r = m < track_frames(r);
+        const int has_l = m < fi_frames(&fl_), has_r = m < fi_frames(&fr_);
         int nb = 0;
         /* :178-183 -- note the if / if-else-if-else shape: both present => min, then the chain */
-        if (has_r && has_l) { const int a = track_frame_len(r, m), b = track_frame_len(l, m); nb = a < b ? a : b; }
-        if (!has_r && has_l) nb = track_frame_len(l, m);
-        else if (has_r && !has_l) nb = track_frame_len(r, m);
+        if (has_r && has_l) { const int a = fi_len(&fr_, m), b = fi_len(&fl_, m); nb = a < b ? a : b; }
+        if (!has_r && has_l) nb = fi_len(&fl_, m);
+        else if (has_r && !has_l) nb = fi_len(&fr_, m);
         else nb = 1152;
         if (nb > maxfs) nb = maxfs;
         if (written + nb > out_cap) break;
         for (int c = 0; c < 2; c++) { memset(d1[c], 0, sizeof(float) * (size_t)nb); memset(d2[c], 0, sizeof(float) * (size_t)nb); }
         int cl = 0, cr = 0;
         const void *p0, *p1;
-        if (has_l) { track_frame_ptrs(l, m, &p0, &p1); cl = orc_swr_convert(sl, d1[0], d1[1], nb, p0, p1, track_frame_len(l, m)); }
+        if (has_l) { fi_ptrs(l, &fl_, m, &p0, &p1); cl = orc_swr_convert(sl, d1[0], d1[1], nb, p0, p1, fi_len(&fl_, m)); }
         else cl = orc_swr_convert(sl, d1[0], d1[1], nb, NULL, NULL, 0);
-        if (has_r) { track_frame_ptrs(r, m, &p0, &p1); cr = orc_swr_convert(sr, d2[0], d2[1], nb, p0, p1, track_frame_len(r, m)); }
+        if (has_r) { fi_ptrs(r, &fr_, m, &p0, &p1); cr = orc_swr_convert(sr, d2[0], d2[1], nb, p0, p1, fi_len(&fr_, m)); }
         else cl = orc_swr_convert(sr, d2[0], d2[1], nb, NULL, NULL, 0);
         for (int i = 0; i < nb; i++) {
             out_l[written + i] = (d1[0][i] / 2 + d1[1][i] / 2) * bias_minus;
@@ -620,7 +643,7 @@ int64_t orc_bimix(const orc_track* l, const orc_track* r, float bias, int quirk,
         if (cr == 0 && cl == 0) break;
     }
     for (int c = 0; c < 2; c++) { free(d1[c]); free(d2[c]); }
-    orc_swr_free(sl); orc_swr_free(sr);
+    orc_swr_free(sl); orc_swr_free(sr); free(fl_.start); free(fr_.start);
     return written;
 }
 
@@ -653,10 +676,10 @@ static void v2_emit(v2_sink* k, const float* inter, int64_t frames, double t)
     k->n += frames;
 }
 
-static void v2_feed(orc_swr* sw, const orc_track* t, int64_t m, double* time, v2_list* list)
+static void v2_feed(orc_swr* sw, const orc_track* t, const frame_index* fi, int64_t m, double* time, v2_list* list)
 {
-    const void *p0, *p1; track_frame_ptrs(t, m, &p0, &p1);
-    const int n = track_frame_len(t, m);
+    const void *p0, *p1; fi_ptrs(t, fi, m, &p0, &p1);
+    const int n = fi_len(fi, m);
     float* b0 = (float*)malloc(sizeof(float) * 2 * (size_t)n);
     float* b1 = (float*)malloc(sizeof(float) * 2 * (size_t)n);
     const int got = orc_swr_convert(sw, b0, b1, n * 2, p0, p1, n);
@@ -673,6 +696,7 @@ int64_t orc_bimix_v2(const orc_track* l, const orc_track* r, int quirk,
 {
     orc_swr* sl = orc_swr_create(l->rate, 48000, l->fmt, l->ch, quirk);
     orc_swr* sr = orc_swr_create(r->rate, 48000, r->fmt, r->ch, quirk);
+    frame_index fil = fi_build(l), fir = fi_build(r);
     v2_list fl = {0, 0}, fr = {0, 0};
     v2_sink sink = {out, 0, out_cap, 0, 0.0};
     double time_l = l->pts0, time_r = r->pts0;
@@ -681,8 +705,8 @@ int64_t orc_bimix_v2(const orc_track* l, const orc_track* r, int quirk,
     float* tmp = NULL; int64_t tmp_cap = 0;
 #define V2_TMP(nfr) do { if ((nfr) * 2 > tmp_cap) { tmp_cap = (nfr) * 2 + 64; tmp = (float*)realloc(tmp, sizeof(float) * (size_t)tmp_cap); } } while (0)
     for (;;) {
-        if (!eof_l) { if (ml < track_frames(l)) v2_feed(sl, l, ml++, &time_l, &fl); else eof_l = 1; }
-        if (!eof_r) { if (mr < track_frames(r)) v2_feed(sr, r, mr++, &time_r, &fr); else eof_r = 1; }
+        if (!eof_l) { if (ml < fi_frames(&fil)) v2_feed(sl, l, &fil, ml++, &time_l, &fl); else eof_l = 1; }
+        if (!eof_r) { if (mr < fi_frames(&fir)) v2_feed(sr, r, &fir, mr++, &time_r, &fr); else eof_r = 1; }
 
         if (!fl.head && !fr.head && eof_l && eof_r) break;
         if (!fr.head && eof_r) {
@@ -727,7 +751,7 @@ int64_t orc_bimix_v2(const orc_track* l, const orc_track* r, int quirk,
 #undef V2_TMP
     while (fl.head) v2_pop(&fl);
     while (fr.head) v2_pop(&fr);
-    free(tmp); orc_swr_free(sl); orc_swr_free(sr);
+    free(tmp); orc_swr_free(sl); orc_swr_free(sr); free(fil.start); free(fir.start);
     if (out_pts0) *out_pts0 = sink.pts0;
     return sink.n;
 }

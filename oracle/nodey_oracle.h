@@ -70,6 +70,11 @@ typedef struct {
     int64_t nframes;
     int frame_size;       /* decoder frame size, 1152 unless stated */
     double pts0;          /* seconds, start time of frame 0 */
+    /* optional run-length encoded frame sizes (nruns > 0 overrides frame_size): frames of a stream
+     * produced by audio_amix are nb samples long per iteration, not uniform */
+    const int64_t* run_len;
+    const int64_t* run_count;
+    int nruns;
 } orc_track;
 
 /* A4 audio_amix: src/processor/audio-amix.cpp:86-324.  Returns frames written (FLTP, 48 kHz). */

@@ -26,7 +26,8 @@ def build(force=False):
 
 class Track(C.Structure):
     _fields_ = [("plane0", C.c_void_p), ("plane1", C.c_void_p), ("fmt", C.c_int), ("rate", C.c_int),
-                ("ch", C.c_int), ("nframes", C.c_int64), ("frame_size", C.c_int), ("pts0", C.c_double)]
+                ("ch", C.c_int), ("nframes", C.c_int64), ("frame_size", C.c_int), ("pts0", C.c_double),
+                ("run_len", C.POINTER(C.c_int64)), ("run_count", C.POINTER(C.c_int64)), ("nruns", C.c_int)]
 
 
 class StInfo(C.Structure):
@@ -199,9 +200,17 @@ def swr_whole(x, fmt, in_rate, out_rate=48000, flush=True, quirk=0):
     return ol[:got], orr[:got]
 
 
-def make_track(x, fmt, rate, frame_size=1152, pts0=0.0):
+def make_track(x, fmt, rate, frame_size=1152, pts0=0.0, runs=None):
+    """runs: optional [(frame_len, count), ...] frame sizes (e.g. the output frames of an amix node)."""
     p0, p1, n, nch = planes_of(x, fmt)
-    t = Track(_p(p0), _p(p1), fmt, rate, nch, n, frame_size, pts0)
+    if runs:
+        rl = (C.c_int64 * len(runs))(*[int(r[0]) for r in runs])
+        rc = (C.c_int64 * len(runs))(*[int(r[1]) for r in runs])
+        assert sum(int(a) * int(b) for a, b in runs) == n, "frame runs do not cover the track"
+        t = Track(_p(p0), _p(p1), fmt, rate, nch, n, frame_size, pts0, rl, rc, len(runs))
+        t._keep = (x, p0, p1, rl, rc)
+        return t
+    t = Track(_p(p0), _p(p1), fmt, rate, nch, n, frame_size, pts0, None, None, 0)
     t._keep = (x, p0, p1)
     return t
 
