@@ -170,6 +170,9 @@ void nodey_soundtouch_destroy(nodey_soundtouch* s);
 int nodey_soundtouch_info(const nodey_soundtouch* s, int info_i[8], double info_d[3]);
 /* frames the node emits in total for in_frames of input (after flush); n_sequences optional */
 int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t* n_sequences);
+/* Test hook: cluster size of the WSOLA offsets kernel (thread-block cluster of 1, 2 or 4 CTAs per track;
+ * 0 = automatic: the largest that keeps tracks * cluster * 2 <= SM count). */
+int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster);
 int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                          int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                          int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);

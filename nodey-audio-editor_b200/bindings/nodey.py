@@ -23,7 +23,7 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_soundtouch_run", "nodey_soundtouch_set_cluster", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
 ]
 
@@ -80,6 +80,7 @@ def lib():
     L.nodey_soundtouch_info.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_double)]
     L.nodey_soundtouch_out_frames.argtypes = [vp, i64, i32, C.POINTER(i64)]
     L.nodey_soundtouch_out_frames.restype = i64
+    L.nodey_soundtouch_set_cluster.argtypes = [vp, i32]
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
     L.nodey_amix_plan.argtypes = [C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32,
                                   C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64),
@@ -375,6 +376,9 @@ class SoundTouch:
             self.h = None
 
     __del__ = close
+
+    def set_cluster(self, cluster):
+        check(lib().nodey_soundtouch_set_cluster(self.h, cluster))
 
     def info(self):
         a = (C.c_int * 8)(); d = (C.c_double * 3)()

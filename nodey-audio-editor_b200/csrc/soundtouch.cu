@@ -29,6 +29,7 @@
 // Compiled with -fmad=false: every multiply and add rounds separately, as in the reference build.
 #include "nodey_common.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
 #include <mutex>
@@ -42,7 +43,6 @@ namespace nodey {
 
 constexpr int kAaLen = 64;
 constexpr int kTdsThreads = 512;
-constexpr int kT = 8;              // candidates per thread
 
 // frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
 // (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks)
@@ -76,13 +76,14 @@ __device__ __forceinline__ float2 view_frame2(const View& v, const float* base, 
 struct TdsArgs {
     View in;
     const long long* pos;      // [nseq] input frame where sequence i starts
-    int* offs;                 // [ntracks][nseq_stride] offsets of sequences 1..nseq-1 at index i-1
+    int* offs;                 // [ntracks][offs_stride] offsets of sequences 1..nseq-1 at index i-1
     long long offs_stride;
     int nseq;
     int overlap, seek_window, seek_length;
     int Q;                     // lane steps = 4 * (CH*overlap/16)
-    int plane_stride;          // floats per de-interleaved plane (== 8 mod 32)
-    int lpad;                  // padded candidate count for the partial-sum arrays
+    int tb_per;                // candidate blocks per CTA of the cluster
+    int sk;                    // floats per sub-plane
+    int ncand_pad;             // padded candidates per CTA (partial-sum arrays)
 };
 
 struct ArgMax { double v; int i; };
@@ -94,32 +95,108 @@ __device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b)
     return a;
 }
 
-template <int CH>
-__global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+// One group of NS lane steps for KT consecutive candidates of one (lane, class) stream.
+// Window = two blocks of KT samples (w[CUR] current, w[CUR^1] next); sample idx = s + k of the
+// window feeds candidate k at step s.  Block b of a thread's stream lives at
+// plane[((OFF + k) % KT) * sk + (OFF + k) / KT + b]: consecutive threads -> consecutive words.
+template <int KT, int OFF, int CUR, int NS>
+__device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&sq)[2][KT], float (&acc)[KT], float (&nrm)[KT],
+                                          const float* __restrict__ xnext, int sk, const float* __restrict__ yq)
 {
+    constexpr int NXT = CUR ^ 1;
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        const float v = xnext[((OFF + k) % KT) * sk + (OFF + k) / KT];
+        w[NXT][k] = v;
+        sq[NXT][k] = __fmul_rn(v, v);
+    }
+    float y[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(yq + s);
+        y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            const int idx = s + k;
+            const float x = idx < KT ? w[CUR][idx] : w[NXT][idx - KT];
+            const float x2 = idx < KT ? sq[CUR][idx] : sq[NXT][idx - KT];
+            acc[k] = __fadd_rn(acc[k], __fmul_rn(x, y[s]));
+            nrm[k] = __fadd_rn(nrm[k], x2);
+        }
+    }
+}
+
+template <int KT, int OFF>
+__device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int sk, const float* __restrict__ yp, int Q,
+                                              float (&acc)[KT], float (&nrm)[KT])
+{
+    float w[2][KT], sq[2][KT];
+#pragma unroll
+    for (int k = 0; k < KT; k++) { acc[k] = 0.f; nrm[k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        const float v = xb[((OFF + k) % KT) * sk + (OFF + k) / KT];
+        w[0][k] = v; sq[0][k] = __fmul_rn(v, v);
+    }
+    const int NG = Q / KT, tail = Q - NG * KT;      // tail is 0 or 4 (Q is a multiple of 4)
+    int G = 0;
+    for (; G + 2 <= NG; G += 2) {
+        tds_group<KT, OFF, 0, KT>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+        tds_group<KT, OFF, 1, KT>(w, sq, acc, nrm, xb + G + 2, sk, yp + (G + 1) * KT);
+    }
+    if (G < NG) {
+        tds_group<KT, OFF, 0, KT>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+        G++;
+        if (tail) tds_group<KT, OFF, 1, 4>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+    } else if (tail) {
+        tds_group<KT, OFF, 0, 4>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+    }
+}
+
+// grid = ntracks * CL CTAs, launched as clusters of CL: the CTAs of a cluster split one track's
+// candidates (blocks of KT per class) and exchange their local arg-max through distributed
+// shared memory, one cluster barrier per sequence.
+template <int CH, int KT>
+__global__ void __launch_bounds__(kTdsThreads, 1) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CL = cluster.num_blocks(), crank = cluster.block_rank();
+
     extern __shared__ __align__(16) float smem[];
     constexpr int K = 4 / CH;                       // candidate classes per lane
-    float* X = smem;                                // [4][plane_stride]
-    float* Y = X + 4 * a.plane_stride;              // [4][Q]
-    float* PS = Y + 4 * a.Q;                        // [4][lpad] correlation lane sums
-    float* PN = PS + 4 * a.lpad;                    // [4][lpad] norm lane sums
+    const int plane_len = KT * a.sk;
+    float* X = smem;                                // [4 planes][KT sub-planes][sk]
+    float* Y = X + 4 * plane_len;                   // [4][Q]
+    float* PS = Y + 4 * a.Q;                        // [4][ncand_pad] correlation lane sums
+    float* PN = PS + 4 * a.ncand_pad;               // [4][ncand_pad] norm lane sums
     __shared__ double red_v[kTdsThreads / 32];
     __shared__ int red_i[kTdsThreads / 32];
-    __shared__ int s_offset;
+    __shared__ double xch_v[2][8];
+    __shared__ int xch_i[2][8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const long long track = blockIdx.x;
+    const long long track = blockIdx.x / CL;
     const float* base = a.in.p + track * a.in.stride;
     int* offs = a.offs + track * a.offs_stride;
 
     const int L = a.seek_length, ovl = a.overlap, Q = a.Q;
-    const int region = L + ovl;                      // frames staged per sequence
+    const int region = L + ovl;                      // frames of the search window
     const int temp = a.seek_window - 2 * ovl;
-    const int tcount = (L + K - 1) / K;              // candidates per class (upper bound)
-    const int tblocks = (tcount + kT - 1) / kT;
-    const int wpc = (tblocks + 31) / 32;             // warps per (lane, class) combo
+    const int tcount = (L + K - 1) / K;
+    const int tblocks = (tcount + KT - 1) / KT;
+    const int tb_lo = (int)crank * a.tb_per;
+    int ntb = tblocks - tb_lo; if (ntb > a.tb_per) ntb = a.tb_per; if (ntb < 0) ntb = 0;
+    const int wpc = (ntb + 31) / 32;                 // warps per (lane, class) combo
     const int nunits = 4 * K * wpc;
-    const int plane_len = a.plane_stride;
+    const int m_lo = KT * tb_lo;                     // first plane element this CTA stages
+    const int f_lo = 4 * m_lo / CH;                  // ... and the first frame
+    const int nfr = plane_len * 4 / CH;              // frames covered by the staged planes
+    const int c_base = K * KT * tb_lo;               // first candidate of this CTA
+    int ncand = K * KT * ntb; if (c_base + ncand > L) ncand = L - c_base; if (ncand < 0) ncand = 0;
 
     long long mid_pos = a.pos[0] + temp;             // first sequence: offset 0, no search
 
@@ -127,25 +204,29 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         const long long p0 = a.pos[i];
         // L2 prefetch of the next sequence's window (its position does not depend on this search)
         if (i + 1 < a.nseq) {
-            const long long q0 = a.pos[i + 1] - a.in.prefix;
-            const int lines = (region * CH * 4 + 127) / 128 + 1;
+            const long long q0 = a.pos[i + 1] + f_lo - a.in.prefix;
+            const int lines = (nfr * CH * 4 + 127) / 128 + 1;
             for (int t = tid; t < lines; t += blockDim.x) {
                 const long long f = q0 + (long long)t * (32 / CH);
                 if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
             }
         }
-        // ---- stage the search window, de-interleaved by float index mod 4 ----
+        // ---- stage this CTA's slice of the search window: plane = float index mod 4, sub-plane = m mod KT ----
         if (CH == 2) {
-            for (int f = tid; f < plane_len * 2; f += blockDim.x) {
+            for (int fr = tid; fr < nfr; fr += blockDim.x) {
+                const int f = f_lo + fr;
                 const float2 v = f < region ? view_frame2<2>(a.in, base, p0 + f) : make_float2(0.f, 0.f);
-                const int m = f >> 1, r = (f & 1) * 2;
-                X[r * plane_len + m] = v.x;
-                X[(r + 1) * plane_len + m] = v.y;
+                const int m = fr >> 1, r = (fr & 1) * 2;
+                const int ph = (m % KT) * a.sk + m / KT;
+                X[r * plane_len + ph] = v.x;
+                X[(r + 1) * plane_len + ph] = v.y;
             }
         } else {
-            for (int f = tid; f < plane_len * 4; f += blockDim.x) {
+            for (int fr = tid; fr < nfr; fr += blockDim.x) {
+                const int f = f_lo + fr;
                 const float v = f < region ? view_sample<1>(a.in, base, p0 + f, 0) : 0.f;
-                X[(f & 3) * plane_len + (f >> 2)] = v;
+                const int m = fr >> 2;
+                X[(fr & 3) * plane_len + (m % KT) * a.sk + m / KT] = v;
             }
         }
         // ---- mid buffer (depends on the previous offset), de-interleaved by lane ----
@@ -155,51 +236,33 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         }
         __syncthreads();
 
-        // ---- lane sums: thread = (lane l, class kappa, T consecutive candidates of the class) ----
+        // ---- lane sums: thread = (lane l, class kappa, KT consecutive candidates of the class) ----
         for (int unit = warp; unit < nunits; unit += nwarps) {
             const int combo = unit / wpc, wsub = unit - combo * wpc;
             const int l = combo & 3, kappa = combo >> 2;
             const int tb = wsub * 32 + lane;
-            if (tb < tblocks) {
-                const int t0 = tb * kT;
+            if (tb < ntb) {
                 const int u0 = CH * kappa + l;
-                const float* xp = X + (u0 & 3) * plane_len + (u0 >> 2) + t0;
+                const float* xb = X + (u0 & 3) * plane_len + tb;
                 const float* yp = Y + l * Q;
-                float acc[kT], nrm[kT], w[kT + 4], sq[kT + 4];
+                float acc[KT], nrm[KT];
+                if (u0 >> 2) tds_lane_sums<KT, 1>(xb, a.sk, yp, Q, acc, nrm);
+                else tds_lane_sums<KT, 0>(xb, a.sk, yp, Q, acc, nrm);
 #pragma unroll
-                for (int k = 0; k < kT; k++) { acc[k] = 0.f; nrm[k] = 0.f; }
-#pragma unroll
-                for (int k = 0; k < kT; k++) { w[k] = xp[k]; sq[k] = __fmul_rn(w[k], w[k]); }
-                for (int qb = 0; qb < Q; qb += 4) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { w[kT + k] = xp[qb + kT + k]; sq[kT + k] = __fmul_rn(w[kT + k], w[kT + k]); }
-                    const float4 y = *reinterpret_cast<const float4*>(yp + qb);
-                    const float yy[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-#pragma unroll
-                        for (int k = 0; k < kT; k++) {
-                            acc[k] = __fadd_rn(acc[k], __fmul_rn(w[s + k], yy[s]));
-                            nrm[k] = __fadd_rn(nrm[k], sq[s + k]);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < kT; k++) { w[k] = w[k + 4]; sq[k] = sq[k + 4]; }
-                }
-#pragma unroll
-                for (int k = 0; k < kT; k++) {
-                    const int c = kappa + K * (t0 + k);
-                    if (c < L) { PS[l * a.lpad + c] = acc[k]; PN[l * a.lpad + c] = nrm[k]; }
+                for (int k = 0; k < KT; k++) {
+                    const int cc = kappa + K * (KT * tb + k);
+                    if (cc < ncand) { PS[l * a.ncand_pad + cc] = acc[k]; PN[l * a.ncand_pad + cc] = nrm[k]; }
                 }
             }
         }
         __syncthreads();
 
-        // ---- per candidate: horizontal add in the SSE order, normalise, weight; block arg-max ----
+        // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max ----
         ArgMax best; best.v = -1e300; best.i = 0x7fffffff;
-        for (int c = tid; c < L; c += blockDim.x) {
-            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[c], PS[a.lpad + c]), PS[2 * a.lpad + c]), PS[3 * a.lpad + c]);
-            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[c], PN[a.lpad + c]), PN[2 * a.lpad + c]), PN[3 * a.lpad + c]);
+        for (int cc = tid; cc < ncand; cc += blockDim.x) {
+            const int c = c_base + cc, np = a.ncand_pad;
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[cc], PS[np + cc]), PS[2 * np + cc]), PS[3 * np + cc]);
+            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[cc], PN[np + cc]), PN[2 * np + cc]), PN[3 * np + cc]);
             const double dn = (double)nr;
             double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
             const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
@@ -216,6 +279,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         }
         if (lane == 0) { red_v[warp] = best.v; red_i[warp] = best.i; }
         __syncthreads();
+        const int par = i & 1;
         if (warp == 0) {
             ArgMax b2; b2.v = lane < nwarps ? red_v[lane] : -1e300; b2.i = lane < nwarps ? red_i[lane] : 0x7fffffff;
 #pragma unroll
@@ -225,11 +289,22 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
                 o.i = __shfl_xor_sync(0xffffffffu, b2.i, d);
                 b2 = argmax_better(b2, o);
             }
-            if (lane == 0) { s_offset = b2.i; offs[i - 1] = b2.i; }
+            // publish this CTA's best to every CTA of the cluster (own slot included)
+            if (lane < CL) {
+                double* pv = cluster.map_shared_rank(&xch_v[par][crank], lane);
+                int* pi = cluster.map_shared_rank(&xch_i[par][crank], lane);
+                *pv = b2.v; *pi = b2.i;
+            }
         }
-        __syncthreads();
-        mid_pos = p0 + s_offset + ovl + temp;
+        if (CL > 1) cluster.sync(); else __syncthreads();
+        ArgMax fin; fin.v = xch_v[par][0]; fin.i = xch_i[par][0];
+        for (unsigned r = 1; r < CL; r++) { ArgMax o; o.v = xch_v[par][r]; o.i = xch_i[par][r]; fin = argmax_better(fin, o); }
+        if (crank == 0 && tid == 0) offs[i - 1] = fin.i;
+        mid_pos = p0 + fin.i + ovl + temp;
+        // the slots of parity `par` are rewritten two sequences later, after another cluster barrier;
+        // X/Y/PS are rewritten only after the next __syncthreads of this CTA
     }
+    if (CL > 1) cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -421,6 +496,7 @@ struct nodey_soundtouch {
     double nominal_skip = 0;
     unsigned long long R = 0; int e = 0;       // rate = R * 2^-e exactly
     int prefill = 0;                           // silent frames in front of the RateTransposer input
+    int force_cluster = 0;                     // test hook: 0 = automatic cluster size for the offsets kernel
     float aa[kAaLen];
     float* d_fade = nullptr;
     // sequence start positions (prefix-stable in the input length): grown on demand
@@ -607,6 +683,15 @@ int nodey_soundtouch_create(nodey_soundtouch** out, int sample_rate, int channel
     return NODEY_OK;
 }
 
+/* test hook: force the cluster size (1, 2 or 4; 0 = automatic) of the offsets kernel */
+int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster)
+{
+    NODEY_REQUIRE(s && (cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4), NODEY_E_INVALID,
+                  "nodey_soundtouch_set_cluster: cluster must be 0, 1, 2 or 4");
+    s->force_cluster = cluster;
+    return NODEY_OK;
+}
+
 void nodey_soundtouch_destroy(nodey_soundtouch* s)
 {
     if (!s) return;
@@ -690,18 +775,34 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         ta.in = vin; ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
         ta.Q = 4 * (CH * s->overlap / 16);
-        int plane = (CH * (s->seek_length + s->overlap) + 3) / 4 + 2 * kT + 8;
-        while ((plane & 31) != 8) plane++;
-        ta.plane_stride = plane;
-        ta.lpad = (s->seek_length + 3) & ~3;
-        const size_t smem = sizeof(float) * ((size_t)4 * plane + (size_t)4 * ta.Q + (size_t)8 * ta.lpad);
         if (nseq > 1) {
-            if (CH == 2) {
-                NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                NODEY_LAUNCH("tds_offsets_kernel", st, tds_offsets_kernel<2><<<ntracks, kTdsThreads, smem, st>>>(ta));
-            } else {
-                NODEY_CUDA_OK(cudaFuncSetAttribute(tds_offsets_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                NODEY_LAUNCH("tds_offsets_kernel", st, tds_offsets_kernel<1><<<ntracks, kTdsThreads, smem, st>>>(ta));
+            // cluster size: spread one track over CL SMs while the batch leaves SMs idle
+            int CL = 1;
+            while (CL < 4 && (long long)ntracks * CL * 2 <= sm_count()) CL *= 2;
+            if (s->force_cluster > 0) CL = s->force_cluster;
+            const int KT = CL >= 4 ? 4 : 8;
+            const int K = 4 / CH;
+            const int tcount = (s->seek_length + K - 1) / K, tblocks = (tcount + KT - 1) / KT;
+            ta.tb_per = (tblocks + CL - 1) / CL;
+            int sk = ta.tb_per + ta.Q / KT + 4;
+            while ((sk & 7) != 4) sk++;
+            ta.sk = sk;
+            ta.ncand_pad = (K * KT * ta.tb_per + 3) & ~3;
+            const size_t smem = sizeof(float) * ((size_t)4 * KT * sk + (size_t)4 * ta.Q + (size_t)8 * ta.ncand_pad);
+            void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
+                                            : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);
+            NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(ntracks * CL)); cfg.blockDim = dim3(kTdsThreads);
+            cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            {
+                LaunchScope ls("tds_offsets_kernel", st);
+                NODEY_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta));
             }
             NODEY_LAUNCH_OK();
         }

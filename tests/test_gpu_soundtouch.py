@@ -53,6 +53,23 @@ def test_soundtouch_matches_oracle(nd, orc, case):
     assert_bit_equal(got.cpu().numpy(), ref, "soundtouch samples")
 
 
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cfg", [(48000, 2, 1.0, 3.0), (44100, 1, 1.0, -4.0), (11025, 2, 1.0, 2.0)])
+def test_soundtouch_cluster_sizes(nd, orc, cluster, cfg):
+    """the WSOLA search split over a thread-block cluster must give the same trace as one CTA"""
+    sr, ch, rate, st_ = cfg
+    n = sr * 3
+    xs = np.stack([orc.synth_f32(n, ch, sr, t) for t in range(3)])
+    pitch = orc.pitch_node_factor(st_)
+    st = nd.SoundTouch(sr, ch, rate, pitch)
+    st.set_cluster(cluster)
+    got, offs = st.run(to_dev(xs), 1152, want_offsets=True)
+    for t in range(3):
+        ref, ro, _ = orc.soundtouch(xs[t], sr, rate, pitch, 1152)
+        assert np.array_equal(offs[t].cpu().numpy(), ro), f"offset trace, track {t}"
+        assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t}")
+
+
 def test_soundtouch_batch_and_chunking(nd, orc):
     sr, n = 48000, 48000 * 2
     xs = np.stack([orc.synth_f32(n, 2, sr, t) for t in range(5)])
