@@ -183,9 +183,7 @@ def run_ours(args):
     nodey.lib()   # fails loudly when the CUDA library is missing: there is no fallback path
 
     n_in = IN_RATE * args.seconds
-    assert args.tracks % (16 * world) == 0, "tracks must split into groups of 16 per rank"
-    t_local = args.tracks // world
-    first = rank * t_local
+    first, t_local = pipeline.shard_tracks(args.tracks, world, rank)
     sub = min(args.sub_batch, t_local)
     r = pipeline.Config5Renderer(n_in, sub_batch=sub, device=dev)
 

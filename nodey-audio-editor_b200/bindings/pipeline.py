@@ -26,6 +26,16 @@ def track_gain(t):
     return float(np.float32(0.5) + np.float32(0.0625) * np.float32(t % 9))
 
 
+def shard_tracks(total_tracks, world, rank):
+    """Tracks are sharded in contiguous blocks so that every rank owns whole amix groups of 16:
+    returns (first_track, n_tracks) of `rank`.  The master bus is then sum over ranks of the partial
+    level-2 mixes (the only collective of the render)."""
+    if total_tracks % (GROUP * world) != 0:
+        raise ValueError(f"{total_tracks} tracks do not split into groups of {GROUP} over {world} ranks")
+    per = total_tracks // world
+    return rank * per, per
+
+
 class Config5Renderer:
     def __init__(self, n_in, sub_batch=32, frame_size=1152, pitch_semitones=3.0, velocity=1.25, device="cuda"):
         import torch
