@@ -16,13 +16,15 @@
 #ifndef NODEY_CUDA_H
 #define NODEY_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-typedef void* nodey_stream_t;
+typedef void* nodey_stream_t;   /* cudaStream_t */
+typedef void* nodey_event_t;    /* cudaEvent_t */
 
 enum {
     NODEY_FMT_U8 = 0, NODEY_FMT_S16 = 1, NODEY_FMT_S32 = 2, NODEY_FMT_FLT = 3, NODEY_FMT_DBL = 4,
@@ -44,6 +46,32 @@ int nodey_version(void);
 const char* nodey_last_error(void);
 /* sm count, cc major, cc minor, total bytes: fails (NODEY_E_CUDA) when no CUDA device is present */
 int nodey_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem);
+
+/* Device runtime behind the ABI (the reference has none: it is a CPU program).  Host layers bind these
+ * instead of the CUDA runtime so that the only native dependency is this library.
+ * nodey_malloc / nodey_free are stream ordered (cudaMallocAsync / cudaFreeAsync); streams are blocking
+ * streams, i.e. ordered against the legacy default stream (NULL). */
+int nodey_set_device(int ordinal);
+int nodey_get_device(int* ordinal);
+int nodey_device_count(int* count);
+int nodey_device_synchronize(void);
+int nodey_stream_create(nodey_stream_t* out);
+int nodey_stream_destroy(nodey_stream_t s);
+int nodey_stream_synchronize(nodey_stream_t s);
+int nodey_event_create(nodey_event_t* out, int timing);
+int nodey_event_destroy(nodey_event_t e);
+int nodey_event_record(nodey_event_t e, nodey_stream_t s);
+int nodey_event_synchronize(nodey_event_t e);
+int nodey_event_elapsed_ms(float* ms, nodey_event_t start, nodey_event_t stop);
+int nodey_stream_wait_event(nodey_stream_t s, nodey_event_t e);
+int nodey_malloc(void** out, size_t bytes, nodey_stream_t s);
+int nodey_free(void* p, nodey_stream_t s);
+int nodey_memset(void* dst, int value, size_t bytes, nodey_stream_t s);
+int nodey_memcpy_h2d(void* dst, const void* src_host, size_t bytes, nodey_stream_t s);
+int nodey_memcpy_d2h(void* dst_host, const void* src, size_t bytes, nodey_stream_t s);
+int nodey_memcpy_d2d(void* dst, const void* src, size_t bytes, nodey_stream_t s);
+int nodey_host_alloc(void** out, size_t bytes);      /* pinned host memory */
+int nodey_host_free(void* p);
 
 /* Synthetic source of SURVEY.md 8(d): x = 0.5 sin(2 pi f n / sr) + 0.05 u, bit-identical to the
  * oracle generator.  dst: interleaved float [nframes][nch]; optional s16 copy clip(lrintf(x*32767)). */
@@ -108,6 +136,10 @@ int nodey_resampler_info(const nodey_resampler* r, int info[8]);
 const float* nodey_resampler_filter_bank(const nodey_resampler* r);
 /* frames swr would return in total for in_frames of input (flush: after swr_convert(NULL) drain) */
 int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, int flush);
+/* streaming bookkeeping of swr_convert (host only): outputs available from n_in real frames plus
+ * `reflect` reflected ones; reflection length resample_flush() appends once `produced` were taken */
+int64_t nodey_resampler_producible(const nodey_resampler* r, int64_t n_in, int64_t reflect);
+int64_t nodey_resampler_flush_reflect(const nodey_resampler* r, int64_t n_in, int64_t produced);
 /* Whole-track conversion: source in its native format (converted on load, mono rematrixed),
  * stereo float planar out.  out_frames <= nodey_resampler_out_count(). */
 int nodey_resampler_run(const nodey_resampler* r, float* out_l, float* out_r,

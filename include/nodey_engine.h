@@ -1,0 +1,65 @@
+/*
+ * nodey_engine.h -- C facade over the C++ host layer (nodey-audio-editor_b200/host): load a Nodey project
+ * (the JSON written by Graph::serialize, src/infra/graph.cpp:284-372), bind PCM sources to the
+ * audio_input node, run the graph with infra::Runner::create_and_run (src/infra/runner.cpp:142-154) and
+ * read what arrived at audio_output or on any link.  This is what a non-C++ caller (tests, bench.py, a
+ * scripting front end) binds; C++ callers use the infra:: / processor:: classes directly.
+ *
+ * All functions return 0 on success, negative on failure (nodey_engine_last_error() has the text).
+ * Device pointers returned here stay valid until the engine is run again or destroyed.
+ */
+#ifndef NODEY_ENGINE_H
+#define NODEY_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nodey_engine nodey_engine;
+
+const char* nodey_engine_last_error(void);
+
+/* infra::register_all_processors() + Graph::deserialize(Json).  NODEY_ENGINE_E_FILE for Invalid_file_error. */
+int nodey_engine_create(nodey_engine** out, const char* project_json);
+void nodey_engine_destroy(nodey_engine* e);
+
+/* Graph::serialize() with a 2-space indent (src/frontend/app.cpp:837-839).  Returns the length needed. */
+int nodey_engine_serialize(nodey_engine* e, char* buf, int cap);
+/* Graph::check_graph(): 0, or NODEY_ENGINE_E_GRAPH (mismatched pin, multiple input, loop) */
+int nodey_engine_check(nodey_engine* e);
+int nodey_engine_node_count(nodey_engine* e);
+/* k-th node in id order: id, identifier (copied into buf), graph level (-1 when the graph is invalid) */
+int nodey_engine_node_info(nodey_engine* e, int k, int* node_id, char* identifier, int cap, int* level);
+
+/* audio_volume_adjust's gain is not part of the project file: programmatic setter */
+int nodey_engine_set_volume(nodey_engine* e, int node_id, float volume);
+
+/* PCM source for pin output_{index} of the audio_input node (replaces the file decode of
+ * src/processor/audio-io.cpp:69-300).  The memory must stay valid until nodey_engine_run returns;
+ * host memory should be pinned for the upload to overlap.  data1 = second plane of planar stereo. */
+int nodey_engine_bind_source(nodey_engine* e, int index, const void* data, const void* data1, int on_device,
+                             int fmt, int sample_rate, int channels, int64_t frames, int frame_size,
+                             double pts_seconds);
+
+/* Runner::create_and_run + wait.  Errors of nodes (Processor::Runtime_error ...) -> NODEY_ENGINE_E_NODE. */
+int nodey_engine_run(nodey_engine* e);
+
+/* Product on output pin `pin` of node `node_id` after a run (first link on that pin).
+ * kind: 1 = audio stream, 2 = spectrum.  audio: fmt/rate/channels/frames/pts, planes.
+ * spectrum: fmt = 3, channels, frames = STFT frames, plane0 = complex64 [channels][frames][bins], bins in *extra. */
+int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kind, int* fmt, int* sample_rate,
+                         int* channels, int64_t* frames, double* pts_seconds, void** plane0, void** plane1, int* extra);
+/* what arrived at the audio_output sink (same fields) */
+int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames,
+                        double* pts_seconds, void** plane0, void** plane1);
+/* frame sizes (run-length encoded) of an audio product: fills up to cap pairs, returns the count */
+int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap);
+
+enum { NODEY_ENGINE_E_INVALID = -1, NODEY_ENGINE_E_FILE = -2, NODEY_ENGINE_E_GRAPH = -3, NODEY_ENGINE_E_NODE = -4 };
+
+#ifdef __cplusplus
+}
+#endif
+#endif

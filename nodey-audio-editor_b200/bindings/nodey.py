@@ -21,10 +21,14 @@ SYMBOLS = [
     "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
     "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
-    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_stft_frames", "nodey_stft",
+    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
     "nodey_soundtouch_run", "nodey_soundtouch_set_cluster", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
+    "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
+    "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
+    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free",
+    "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
 ]
 
 

@@ -470,6 +470,22 @@ int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, i
     return n;
 }
 
+/* streaming bookkeeping of swr_convert (host only): outputs available from n_in real frames plus `reflect`
+ * reflected ones, and the reflection length resample_flush() appends when `produced` outputs were taken */
+int64_t nodey_resampler_producible(const nodey_resampler* r, int64_t n_in, int64_t reflect)
+{
+    if (!r || n_in < 0 || reflect < 0) return NODEY_E_INVALID;
+    if (!r->resample) return n_in;
+    return plan_producible(r, n_in, reflect);
+}
+
+int64_t nodey_resampler_flush_reflect(const nodey_resampler* r, int64_t n_in, int64_t produced)
+{
+    if (!r || n_in < 0 || produced < 0) return NODEY_E_INVALID;
+    if (!r->resample) return 0;
+    return plan_reflect(r, n_in, produced);
+}
+
 static int fill_src(SrcDesc* s, const nodey_resampler* r, const void* p0, const void* p1, int fmt, int nch,
                     int64_t in_frames, int flush)
 {

@@ -1,0 +1,50 @@
+// infra/exec-context.hpp -- what the level-batched Runner gives a node while it runs: the CUDA stream
+// to launch on and helpers to order work across streams.  (No counterpart in the reference, whose
+// nodes run as Boost fibers on one CPU thread; here a node only ENQUEUES device work.)
+#pragma once
+
+#include <cstdint>
+#include <memory>
+
+namespace infra
+{
+	// opaque handles so that node code does not need the CUDA headers
+	using Stream_handle = void*;   // cudaStream_t
+	using Event_handle = void*;    // cudaEvent_t
+
+	struct Exec_context
+	{
+		Stream_handle stream = nullptr;   // launch everything of the current node (batch) on this stream
+		int level = 0;                    // graph level being executed
+		int lane = 0;                     // index of the stream inside the level
+
+		// the context of the calling thread (set by the Runner around process_payload / process_batch)
+		static Exec_context& current();
+	};
+
+	// reference-counted CUDA event, recorded by a producer, waited on by consumers' streams
+	class Device_event
+	{
+		Event_handle ev = nullptr;
+	  public:
+		Device_event();
+		~Device_event();
+		Device_event(const Device_event&) = delete;
+		Device_event& operator=(const Device_event&) = delete;
+		void record(Stream_handle stream);
+		void wait_on(Stream_handle stream) const;   // cudaStreamWaitEvent
+		void synchronize() const;
+	};
+
+	// owned device allocation (cudaMallocAsync on the current stream; freed stream-ordered)
+	class Device_block
+	{
+	  public:
+		void* ptr = nullptr;
+		size_t bytes = 0;
+		explicit Device_block(size_t bytes);
+		~Device_block();
+		Device_block(const Device_block&) = delete;
+		Device_block& operator=(const Device_block&) = delete;
+	};
+}

@@ -1,0 +1,111 @@
+// processor/audio-stream.hpp -- the product that travels over audio links.
+// Reference: Audio_stream = bounded channel of AVFrame-backed Audio_frames + EOF flag
+// (include/processor/audio-stream.hpp:22-83).  Here a stream is published ONCE as a device-resident
+// whole-track buffer (Audio_buffer): samples in the layout the reference's frames would carry
+// (AVSampleFormat numbering, packed or planar), plus the metadata the reference reads from frames:
+// sample rate, channel count, start pts and the frame sizes (run-length encoded) that the
+// frame-by-frame bookkeeping of amix / bimix depends on.
+#pragma once
+
+#include "infra/exec-context.hpp"
+#include "infra/processor.hpp"
+
+#include <cstdint>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+namespace processor
+{
+	// AVSampleFormat values (libavutil/samplefmt.h), as stored in AVFrame::format by the reference
+	enum Sample_format : int
+	{
+		FMT_U8 = 0, FMT_S16 = 1, FMT_S32 = 2, FMT_FLT = 3, FMT_DBL = 4,
+		FMT_U8P = 5, FMT_S16P = 6, FMT_S32P = 7, FMT_FLTP = 8, FMT_DBLP = 9
+	};
+
+	inline bool format_is_planar(int fmt) { return fmt >= FMT_U8P; }
+	inline int format_bytes(int fmt)
+	{
+		switch (fmt)
+		{
+		case FMT_S16: case FMT_S16P: return 2;
+		case FMT_S32: case FMT_S32P: case FMT_FLT: case FMT_FLTP: return 4;
+		default: return 0;
+		}
+	}
+
+	// frame sizes of a stream, run-length encoded: {samples per frame, number of such frames}
+	using Frame_runs = std::vector<std::pair<int64_t, int64_t>>;
+	Frame_runs uniform_frame_runs(int64_t frames, int64_t frame_size);
+	int64_t frame_runs_total(const Frame_runs& runs);
+
+	struct Audio_buffer
+	{
+		std::shared_ptr<infra::Device_block> block;    // owner of the memory (may be shared by a whole batch)
+		void* plane[2] = {nullptr, nullptr};           // packed: plane[0]; planar: one plane per channel
+		int format = FMT_FLT;
+		int sample_rate = 48000;
+		int channels = 2;
+		int64_t frames = 0;                            // samples per channel
+		Frame_runs runs;                               // how the reference would have cut it into frames
+		double pts_seconds = 0.0;                      // start time of the first frame
+		std::shared_ptr<infra::Device_event> ready;    // recorded after the producing kernels were enqueued
+
+		size_t plane_bytes() const { return (size_t)frames * (size_t)format_bytes(format) * (format_is_planar(format) ? 1u : (size_t)channels); }
+	};
+
+	class Audio_stream : public infra::Processor::Product
+	{
+		mutable std::mutex mutex;
+		std::shared_ptr<const Audio_buffer> buffer;
+		std::atomic<bool> end_of_stream = false;
+
+	  public:
+
+		Audio_stream() = default;
+		Audio_stream(const Audio_stream&) = delete;
+		Audio_stream& operator=(const Audio_stream&) = delete;
+
+		// producer side: hand over the rendered track and close the stream
+		void publish(std::shared_ptr<const Audio_buffer> rendered)
+		{
+			{
+				std::lock_guard lock(mutex);
+				buffer = std::move(rendered);
+			}
+			end_of_stream.store(true);
+		}
+
+		// consumer side: nullptr when the producer closed the stream without data
+		std::shared_ptr<const Audio_buffer> get() const
+		{
+			std::lock_guard lock(mutex);
+			return buffer;
+		}
+
+		bool eof() const { return end_of_stream.load(); }
+		void set_eof() { end_of_stream.store(true); }
+		size_t buffered_count() const { return get() ? 1 : 0; }
+	};
+
+	// product of audio_spectrum: complex64 bins, [channels][frames][fft_size/2+1], device resident
+	struct Spectrum_buffer
+	{
+		std::shared_ptr<infra::Device_block> block;
+		float* data = nullptr;
+		int channels = 0, fft_size = 4096, hop = 1024, sample_rate = 48000;
+		int64_t frames = 0;
+		std::shared_ptr<infra::Device_event> ready;
+	};
+
+	class Spectrum_stream : public infra::Processor::Product
+	{
+		mutable std::mutex mutex;
+		std::shared_ptr<const Spectrum_buffer> buffer;
+
+	  public:
+		void publish(std::shared_ptr<const Spectrum_buffer> b) { std::lock_guard lock(mutex); buffer = std::move(b); }
+		std::shared_ptr<const Spectrum_buffer> get() const { std::lock_guard lock(mutex); return buffer; }
+	};
+}

@@ -1,0 +1,205 @@
+// processor/nodes.hpp -- the node classes.  Class names, identifiers, pin identifiers and JSON keys are
+// the reference's; the two nodes the reference's README promises but never
+// shipped (channel split, spectrum) are added through the same API.
+//   audio_input          Audio_input        include/processor/audio-io.hpp     src/processor/audio-io.cpp:29-338
+//   audio_output         Audio_output       include/processor/audio-io.hpp     src/processor/audio-io.cpp:430-844
+//   audio_volume_adjust  Audio_vol          include/processor/audio-vol.hpp    src/processor/audio-vol.cpp
+//   velocity_modifier    Velocity_modifier  include/processor/audio-velocity.hpp src/processor/audio-velocity.cpp
+//   pitch_modifier       Pitch_modifier     (same files)
+//   audio_amix           Audio_amix         include/processor/audio-amix.hpp   src/processor/audio-amix.cpp
+//   audio_bimix          Audio_bimix        include/processor/audio-bimix.hpp  src/processor/audio-bimix.cpp:26-383
+//   audio_bimix_v2       Audio_bimix_v2     (same files, :387-877)
+//   audio_channel_split  Audio_channel_split  NEW
+//   audio_spectrum       Audio_spectrum       NEW
+#pragma once
+
+#include "infra/processor.hpp"
+#include "processor/audio-stream.hpp"
+
+#include <string>
+#include <vector>
+
+namespace processor
+{
+#define NODEY_NODE_COMMON(Class)                                                                          \
+	Class(const Class&) = delete;                                                                         \
+	Class& operator=(const Class&) = delete;                                                              \
+	static infra::Processor::Info get_processor_info();                                                   \
+	virtual Processor::Info get_processor_info_non_static() const { return get_processor_info(); }        \
+	virtual std::vector<infra::Processor::Pin_attribute> get_pin_attributes() const;                      \
+	virtual void process_payload(                                                                         \
+		const std::map<std::string, std::shared_ptr<infra::Processor::Product>>& input,                   \
+		const std::map<std::string, std::set<std::shared_ptr<infra::Processor::Product>>>& output,        \
+		const std::atomic<bool>& stop_token,                                                              \
+		std::any& user_data                                                                               \
+	);                                                                                                    \
+	virtual void draw_title() {}                                                                          \
+	virtual bool draw_content(bool) { return false; }
+
+	// ---- source ------------------------------------------------------------------------------------
+	// One PCM source per output pin.  The reference demuxes/decodes files with libavformat/libavcodec
+	// (not available here); this engine takes raw PCM handed in through user_data (Pcm_source_list) or
+	// reads canonical RIFF/WAVE files named by file_path (PCM 16/32 bit, IEEE float 32).
+	struct Pcm_source
+	{
+		const void* data = nullptr;     // packed samples (planar: plane 0), host or device memory
+		const void* data1 = nullptr;    // planar channel 1
+		bool on_device = false;
+		int format = FMT_FLT, sample_rate = 48000, channels = 2;
+		int64_t frames = 0;
+		int frame_size = 1152;          // decoder frame size the reference would see (1152 MP3, 1024 WAV, 4096 FLAC)
+		double pts_seconds = 0.0;
+	};
+	struct Pcm_source_list
+	{
+		std::vector<Pcm_source> sources;    // index i feeds pin output_{i}
+	};
+
+	class Audio_input : public infra::Processor
+	{
+		size_t file_count = 1;
+		std::vector<std::string> file_paths = {""};
+
+	  public:
+		Audio_input() = default;
+		virtual ~Audio_input() = default;
+		NODEY_NODE_COMMON(Audio_input)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+		void set_file_count(size_t n);          // programmatic equivalent of the UI's add/remove file buttons
+	};
+
+	// ---- sink --------------------------------------------------------------------------------------
+	class Audio_output : public infra::Processor
+	{
+	  public:
+		// user_data of the sink.  do_export / export_path / time keep the reference's meaning
+		// (audio-io.hpp:62-69); the rendered stream is additionally kept for the caller.
+		struct Process_context
+		{
+			bool do_export = true;
+			std::string export_path = "";                    // "" = keep in memory only; *.wav = write a float WAV
+			size_t kbps = 0;
+			std::shared_ptr<std::atomic<double>> time = std::make_shared<std::atomic<double>>(0.0);
+			std::shared_ptr<const Audio_buffer> rendered;    // OUT: what arrived at the sink (device resident)
+		};
+
+		Audio_output() = default;
+		virtual ~Audio_output() = default;
+		NODEY_NODE_COMMON(Audio_output)
+		virtual Json::Value serialize() const { return {}; }
+		virtual void deserialize(const Json::Value&) {}
+	};
+
+	// ---- gain --------------------------------------------------------------------------------------
+	class Audio_vol : public infra::Processor
+	{
+		float volume = 1.0;
+
+	  public:
+		Audio_vol() = default;
+		virtual ~Audio_vol() = default;
+		NODEY_NODE_COMMON(Audio_vol)
+		virtual Json::Value serialize() const { return {}; }          // the reference never persists the gain (App. C1)
+		virtual void deserialize(const Json::Value& value);           // reads an optional "volume" key if present
+		virtual bool process_batch(const std::vector<Batch_item>& items);
+		void set_volume(float v);                                      // clamped to [0, 10] like the UI slider
+		float get_volume() const { return volume; }
+	};
+
+	// ---- SoundTouch nodes --------------------------------------------------------------------------
+	class Velocity_modifier : public infra::Processor
+	{
+		float velocity = 1;
+		bool keep_pitch = false;
+
+	  public:
+		Velocity_modifier() = default;
+		virtual ~Velocity_modifier() = default;
+		NODEY_NODE_COMMON(Velocity_modifier)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+		virtual bool process_batch(const std::vector<Batch_item>& items);
+		friend struct Soundtouch_params;
+	};
+
+	class Pitch_modifier : public infra::Processor
+	{
+		float pitch = 0;
+
+	  public:
+		Pitch_modifier() = default;
+		virtual ~Pitch_modifier() = default;
+		NODEY_NODE_COMMON(Pitch_modifier)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+		virtual bool process_batch(const std::vector<Batch_item>& items);
+		friend struct Soundtouch_params;
+	};
+
+	// ---- mixers ------------------------------------------------------------------------------------
+	class Audio_amix : public infra::Processor
+	{
+		int input_num = 2;
+		std::vector<float> volumes;
+		std::vector<bool> locks;
+
+	  public:
+		Audio_amix();
+		virtual ~Audio_amix() = default;
+		NODEY_NODE_COMMON(Audio_amix)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+	};
+
+	class Audio_bimix : public infra::Processor
+	{
+		float bias = 0.0f;
+
+	  public:
+		Audio_bimix() = default;
+		virtual ~Audio_bimix() = default;
+		NODEY_NODE_COMMON(Audio_bimix)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+	};
+
+	class Audio_bimix_v2 : public infra::Processor
+	{
+	  public:
+		Audio_bimix_v2() = default;
+		virtual ~Audio_bimix_v2() = default;
+		NODEY_NODE_COMMON(Audio_bimix_v2)
+		virtual Json::Value serialize() const { return {}; }
+		virtual void deserialize(const Json::Value&) {}
+	};
+
+	// ---- new nodes ---------------------------------------------------------------------------------
+	class Audio_channel_split : public infra::Processor
+	{
+	  public:
+		Audio_channel_split() = default;
+		virtual ~Audio_channel_split() = default;
+		NODEY_NODE_COMMON(Audio_channel_split)
+		virtual Json::Value serialize() const { return Json::Value(Json::objectValue); }
+		virtual void deserialize(const Json::Value&) {}
+	};
+
+	class Audio_spectrum : public infra::Processor
+	{
+		int fft_size = 4096, hop = 1024;
+		std::string window = "hann";
+		// The spectrum is usually the end of a branch: with no link on "output" there is no product to
+		// publish to (products exist per link), so the last result is also kept on the node for the host.
+		mutable std::mutex result_mutex;
+		std::shared_ptr<const Spectrum_buffer> result;
+
+	  public:
+		std::shared_ptr<const Spectrum_buffer> get_result() const { std::lock_guard lock(result_mutex); return result; }
+		Audio_spectrum() = default;
+		virtual ~Audio_spectrum() = default;
+		NODEY_NODE_COMMON(Audio_spectrum)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+	};
+}

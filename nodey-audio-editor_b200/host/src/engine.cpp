@@ -1,0 +1,247 @@
+// engine.cpp -- C facade (include/nodey_engine.h) over Graph / Runner / the node classes.
+#include "infra/graph.hpp"
+#include "infra/runner.hpp"
+#include "processor/nodes.hpp"
+
+#include "nodey_engine.h"
+
+#include <cstring>
+
+using namespace infra;
+using namespace processor;
+
+struct nodey_engine
+{
+	Graph graph;
+	Pcm_source_list sources;
+	std::unique_ptr<Runner> runner;
+	std::shared_ptr<std::any> sink_data;
+};
+
+namespace
+{
+	thread_local std::string g_error;
+
+	int fail(int code, const std::string& text)
+	{
+		g_error = text;
+		return code;
+	}
+
+	void copy_text(const std::string& s, char* buf, int cap)
+	{
+		if (!buf || cap <= 0) return;
+		const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+		memcpy(buf, s.data(), n);
+		buf[n] = 0;
+	}
+
+	std::shared_ptr<Processor::Product> find_product(nodey_engine* e, int node_id, const std::string& pin)
+	{
+		if (!e->runner) return nullptr;
+		const auto& res = e->runner->get_processor_resources();
+		const auto it = res.find(node_id);
+		if (it == res.end()) return nullptr;
+		const auto out = it->second->output_payloads.find(pin);
+		if (out == it->second->output_payloads.end() || out->second.empty()) return nullptr;
+		return *out->second.begin();
+	}
+}
+
+extern "C" {
+
+const char* nodey_engine_last_error(void) { return g_error.c_str(); }
+
+int nodey_engine_create(nodey_engine** out, const char* project_json)
+{
+	if (!out || !project_json) return fail(NODEY_ENGINE_E_INVALID, "nodey_engine_create: null argument");
+	try
+	{
+		register_all_processors();
+		Json::Value root;
+		Json::Reader reader;
+		if (!reader.parse(project_json, root)) return fail(NODEY_ENGINE_E_FILE, "Invalid File: " + reader.getFormattedErrorMessages());
+		auto e = std::make_unique<nodey_engine>();
+		e->graph = Graph::deserialize(root);
+		*out = e.release();
+		return 0;
+	}
+	catch (const Graph::Invalid_file_error& err) { return fail(NODEY_ENGINE_E_FILE, err.what()); }
+	catch (const Processor::Runtime_error& err) { return fail(NODEY_ENGINE_E_FILE, err.what()); }
+	catch (const Graph::Mismatched_pin_error& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+	catch (const Graph::Multiple_input_error& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_INVALID, err.what()); }
+}
+
+void nodey_engine_destroy(nodey_engine* e) { delete e; }
+
+int nodey_engine_serialize(nodey_engine* e, char* buf, int cap)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	const std::string text = Json::writeString(e->graph.serialize(), "  ");
+	copy_text(text, buf, cap);
+	return (int)text.size();
+}
+
+int nodey_engine_check(nodey_engine* e)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	try { e->graph.check_graph(); return 0; }
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+}
+
+int nodey_engine_node_count(nodey_engine* e) { return e ? (int)e->graph.nodes.size() : NODEY_ENGINE_E_INVALID; }
+
+int nodey_engine_node_info(nodey_engine* e, int k, int* node_id, char* identifier, int cap, int* level)
+{
+	if (!e || k < 0 || k >= (int)e->graph.nodes.size()) return fail(NODEY_ENGINE_E_INVALID, "node index out of range");
+	auto it = e->graph.nodes.begin();
+	std::advance(it, k);
+	if (node_id) *node_id = it->first;
+	copy_text(it->second.processor->get_processor_info_non_static().identifier, identifier, cap);
+	if (level)
+	{
+		*level = -1;
+		try
+		{
+			const auto levels = e->graph.topological_levels();
+			for (size_t l = 0; l < levels.size(); l++)
+				for (const Id_t id : levels[l])
+					if (id == it->first) *level = (int)l;
+		}
+		catch (const std::exception&) {}
+	}
+	return 0;
+}
+
+int nodey_engine_set_volume(nodey_engine* e, int node_id, float volume)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	const auto it = e->graph.nodes.find(node_id);
+	if (it == e->graph.nodes.end()) return fail(NODEY_ENGINE_E_INVALID, "no such node");
+	auto* vol = dynamic_cast<Audio_vol*>(it->second.processor.get());
+	if (!vol) return fail(NODEY_ENGINE_E_INVALID, "node is not an audio_volume_adjust");
+	vol->set_volume(volume);
+	return 0;
+}
+
+int nodey_engine_bind_source(nodey_engine* e, int index, const void* data, const void* data1, int on_device, int fmt, int sample_rate,
+							 int channels, int64_t frames, int frame_size, double pts_seconds)
+{
+	if (!e || index < 0 || index > 4096) return fail(NODEY_ENGINE_E_INVALID, "bad source index");
+	if ((size_t)index >= e->sources.sources.size()) e->sources.sources.resize((size_t)index + 1);
+	Pcm_source& s = e->sources.sources[(size_t)index];
+	s.data = data; s.data1 = data1; s.on_device = on_device != 0; s.format = fmt; s.sample_rate = sample_rate; s.channels = channels;
+	s.frames = frames; s.frame_size = frame_size > 0 ? frame_size : 1152; s.pts_seconds = pts_seconds;
+	return 0;
+}
+
+int nodey_engine_run(nodey_engine* e)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	try
+	{
+		e->runner.reset();
+		std::map<Id_t, std::shared_ptr<std::any>> node_data;
+		if (const auto in = e->graph.singleton_node_map.find("audio_input"); in != e->graph.singleton_node_map.end())
+			node_data[in->second] = std::make_shared<std::any>(e->sources);
+		if (const auto out = e->graph.singleton_node_map.find("audio_output"); out != e->graph.singleton_node_map.end())
+		{
+			Audio_output::Process_context ctx;
+			ctx.do_export = true;
+			e->sink_data = std::make_shared<std::any>(ctx);
+			node_data[out->second] = e->sink_data;
+		}
+		e->runner = Runner::create_and_run(e->graph, std::move(node_data));
+		e->runner->wait();
+		const std::string err = e->runner->first_error();
+		if (!err.empty()) return fail(NODEY_ENGINE_E_NODE, err);
+		return 0;
+	}
+	catch (const Graph::Mismatched_pin_error& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+	catch (const Graph::Multiple_input_error& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+	catch (const Graph::Loop_detected_error& err) { return fail(NODEY_ENGINE_E_GRAPH, err.what()); }
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_INVALID, err.what()); }
+}
+
+int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kind, int* fmt, int* sample_rate, int* channels, int64_t* frames,
+						 double* pts_seconds, void** plane0, void** plane1, int* extra)
+{
+	if (!e || !pin) return fail(NODEY_ENGINE_E_INVALID, "null argument");
+	auto product = find_product(e, node_id, pin);
+	if (!product && e->runner)
+	{
+		// an unlinked audio_spectrum output: the node keeps its last result for the host
+		const auto node = e->graph.nodes.find(node_id);
+		if (node != e->graph.nodes.end())
+			if (const auto* sp = dynamic_cast<const Audio_spectrum*>(node->second.processor.get()); sp && sp->get_result())
+			{
+				auto holder = std::make_shared<Spectrum_stream>();
+				holder->publish(sp->get_result());
+				product = holder;
+			}
+	}
+	if (!product) return fail(NODEY_ENGINE_E_INVALID, "no product on that pin (not linked, or the engine has not run)");
+	if (const auto audio = std::dynamic_pointer_cast<Audio_stream>(product))
+	{
+		const auto b = audio->get();
+		if (!b) return fail(NODEY_ENGINE_E_NODE, "stream was closed without audio");
+		if (b->ready) b->ready->synchronize();
+		if (kind) *kind = 1;
+		if (fmt) *fmt = b->format;
+		if (sample_rate) *sample_rate = b->sample_rate;
+		if (channels) *channels = b->channels;
+		if (frames) *frames = b->frames;
+		if (pts_seconds) *pts_seconds = b->pts_seconds;
+		if (plane0) *plane0 = b->plane[0];
+		if (plane1) *plane1 = b->plane[1];
+		if (extra) *extra = 0;
+		return 0;
+	}
+	if (const auto spec = std::dynamic_pointer_cast<Spectrum_stream>(product))
+	{
+		const auto b = spec->get();
+		if (!b) return fail(NODEY_ENGINE_E_NODE, "spectrum was not published");
+		if (b->ready) b->ready->synchronize();
+		if (kind) *kind = 2;
+		if (fmt) *fmt = FMT_FLT;
+		if (sample_rate) *sample_rate = b->sample_rate;
+		if (channels) *channels = b->channels;
+		if (frames) *frames = b->frames;
+		if (pts_seconds) *pts_seconds = 0;
+		if (plane0) *plane0 = b->data;
+		if (plane1) *plane1 = nullptr;
+		if (extra) *extra = b->fft_size / 2 + 1;
+		return 0;
+	}
+	return fail(NODEY_ENGINE_E_INVALID, "unknown product type");
+}
+
+int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap)
+{
+	if (!e || !pin) return fail(NODEY_ENGINE_E_INVALID, "null argument");
+	const auto audio = std::dynamic_pointer_cast<Audio_stream>(find_product(e, node_id, pin));
+	if (!audio || !audio->get()) return fail(NODEY_ENGINE_E_INVALID, "no audio product on that pin");
+	const auto& runs = audio->get()->runs;
+	for (int k = 0; k < cap && k < (int)runs.size(); k++) { run_len[k] = runs[(size_t)k].first; run_count[k] = runs[(size_t)k].second; }
+	return (int)runs.size();
+}
+
+int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames, double* pts_seconds, void** plane0,
+						void** plane1)
+{
+	if (!e || !e->sink_data) return fail(NODEY_ENGINE_E_INVALID, "the graph has no audio_output node or has not run");
+	const auto* ctx = std::any_cast<Audio_output::Process_context>(e->sink_data.get());
+	if (!ctx || !ctx->rendered) return fail(NODEY_ENGINE_E_NODE, "nothing arrived at audio_output");
+	const auto& b = ctx->rendered;
+	if (fmt) *fmt = b->format;
+	if (sample_rate) *sample_rate = b->sample_rate;
+	if (channels) *channels = b->channels;
+	if (frames) *frames = b->frames;
+	if (pts_seconds) *pts_seconds = b->pts_seconds;
+	if (plane0) *plane0 = b->plane[0];
+	if (plane1) *plane1 = b->plane[1];
+	return 0;
+}
+
+}  // extern "C"

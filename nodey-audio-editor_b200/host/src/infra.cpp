@@ -1,0 +1,475 @@
+// infra.cpp -- registry, execution context, device handles, graph model and the level-batched Runner.
+#include "infra/exec-context.hpp"
+#include "infra/graph.hpp"
+#include "infra/runner.hpp"
+
+#include "nodey_cuda.h"
+
+#include <algorithm>
+#include <typeindex>
+
+namespace infra
+{
+	std::map<std::string, Processor::Info> Processor::processor_map;
+
+	// ---------------------------------------------------------------------------------------------
+	// device handles over the C ABI
+	// ---------------------------------------------------------------------------------------------
+	static void abi_check(int rc, const char* what)
+	{
+		if (rc == NODEY_OK) return;
+		const std::string text = nodey_last_error();
+		if (rc == NODEY_E_NOMEM) throw std::bad_alloc();
+		throw Processor::Runtime_error("GPU runtime call failed", std::format("{} returned {}", what, rc), text);
+	}
+
+	Exec_context& Exec_context::current()
+	{
+		thread_local Exec_context ctx;
+		return ctx;
+	}
+
+	Device_event::Device_event() { abi_check(nodey_event_create(&ev, 0), "nodey_event_create"); }
+	Device_event::~Device_event() { nodey_event_destroy(ev); }
+	void Device_event::record(Stream_handle stream) { abi_check(nodey_event_record(ev, stream), "nodey_event_record"); }
+	void Device_event::wait_on(Stream_handle stream) const { abi_check(nodey_stream_wait_event(stream, ev), "nodey_stream_wait_event"); }
+	void Device_event::synchronize() const { abi_check(nodey_event_synchronize(ev), "nodey_event_synchronize"); }
+
+	Device_block::Device_block(size_t n) : bytes(n)
+	{
+		abi_check(nodey_malloc(&ptr, n, Exec_context::current().stream), "nodey_malloc");
+	}
+
+	Device_block::~Device_block()
+	{
+		// freed on the legacy default stream: ordered after everything already enqueued on the Runner's
+		// (blocking) streams, so consumers that only enqueued work may drop their reference at once
+		nodey_free(ptr, nullptr);
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// Graph (reference: src/infra/graph.cpp)
+	// ---------------------------------------------------------------------------------------------
+	Id_t Graph::add_node(std::unique_ptr<Processor> processor)
+	{
+		const Id_t id = find_empty(nodes);
+		const auto info = processor->get_processor_info_non_static();
+		Node node;
+		node.processor = std::move(processor);
+		nodes[id] = std::move(node);
+		update_node_pin(id);
+		if (info.singleton) singleton_node_map.emplace(info.identifier, id);
+		modified = true;
+		return id;
+	}
+
+	void Graph::remove_node(Id_t id)
+	{
+		const auto find = nodes.find(id);
+		if (find == nodes.end()) return;
+		const auto info = find->second.processor->get_processor_info_non_static();
+		if (info.singleton)
+		{
+			const auto it = singleton_node_map.find(info.identifier);
+			if (it == singleton_node_map.end()) THROW_LOGIC_ERROR("Singleton node ID not found");
+			if (it->second != id) THROW_LOGIC_ERROR("Singleton node ID mismatch, expected {}, got {}", it->second, id);
+			singleton_node_map.erase(it);
+		}
+		const std::set<Id_t> owned = find->second.pins;
+		for (const Id_t pin : owned) pins.erase(pin);
+		std::erase_if(links, [&owned](const auto& kv) { return owned.contains(kv.second.from) || owned.contains(kv.second.to); });
+		nodes.erase(find);
+		modified = true;
+	}
+
+	void Graph::update_node_pin(Id_t id)
+	{
+		Node& node = nodes[id];
+
+		// remember what the node's current pins were linked to, by pin name
+		std::map<std::string, Id_t> old_inputs;
+		std::map<std::string, std::set<Id_t>> old_outputs;
+		for (auto it = links.begin(); it != links.end();)
+		{
+			const Link link = it->second;
+			if (node.pins.contains(link.from)) { old_outputs[pins.at(link.from).attribute.identifier].insert(link.to); it = links.erase(it); }
+			else if (node.pins.contains(link.to)) { old_inputs[pins.at(link.to).attribute.identifier] = link.from; it = links.erase(it); }
+			else ++it;
+		}
+		for (const Id_t pin : node.pins) pins.erase(pin);
+		node.pins.clear();
+		node.pin_name_map.clear();
+
+		// re-create the pins from the processor's current attributes and restore compatible links
+		for (const auto& attribute : node.processor->get_pin_attributes())
+		{
+			if (node.pin_name_map.contains(attribute.identifier))
+				THROW_LOGIC_ERROR("Pin name {} already exists for node ID {}", attribute.identifier, id);
+			const Id_t pin_id = find_empty(pins);
+			node.pins.insert(pin_id);
+			pins.emplace(pin_id, Pin{.parent = id, .attribute = attribute});
+			node.pin_name_map.emplace(attribute.identifier, pin_id);
+
+			if (const auto in = old_inputs.find(attribute.identifier);
+				in != old_inputs.end() && attribute.type.get() == pins.at(in->second).attribute.type.get())
+				links.emplace(find_empty(links), Link{.from = in->second, .to = pin_id});
+			if (const auto out = old_outputs.find(attribute.identifier); out != old_outputs.end())
+				for (const Id_t to : out->second)
+					if (attribute.type.get() == pins.at(to).attribute.type.get())
+						links.emplace(find_empty(links), Link{.from = pin_id, .to = to});
+		}
+		modified = true;
+	}
+
+	Id_t Graph::add_link(Id_t from, Id_t to)
+	{
+		if (!check_node_type_match(from, to)) throw Mismatched_pin_error{from, to};
+		if (!check_multiple_input(to)) throw Multiple_input_error{to};
+		const Id_t id = find_empty(links);
+		links.insert_or_assign(id, Link{.from = from, .to = to});
+		modified = true;
+		return id;
+	}
+
+	void Graph::remove_link(Id_t id)
+	{
+		links.erase(id);
+		modified = true;
+	}
+
+	void Graph::remove_link(Id_t from, Id_t to)
+	{
+		std::erase_if(links, [&](const auto& kv) { return kv.second.from == from && kv.second.to == to; });
+		modified = true;
+	}
+
+	std::map<Id_t, Id_t> Graph::get_pin_to_node_map() const
+	{
+		std::map<Id_t, Id_t> out;
+		for (const auto& [id, node] : nodes)
+			for (const Id_t pin : node.pins) out[pin] = id;
+		return out;
+	}
+
+	std::map<Id_t, std::set<Id_t>> Graph::get_node_input_map() const
+	{
+		std::map<Id_t, std::set<Id_t>> out;
+		for (const auto& [id, _] : nodes) out.emplace(id, std::set<Id_t>{});
+		for (const auto& [_, link] : links) out[pins.at(link.to).parent].insert(link.from);
+		return out;
+	}
+
+	std::vector<std::vector<Id_t>> Graph::topological_levels() const
+	{
+		std::map<Id_t, std::set<Id_t>> successors;
+		for (const auto& [_, link] : links)
+		{
+			if (!check_node_type_match(link.from, link.to)) throw Mismatched_pin_error{link.from, link.to};
+			if (!check_multiple_input(link.to)) throw Multiple_input_error(link.to);
+			successors[pins.at(link.from).parent].insert(pins.at(link.to).parent);
+		}
+		// Kahn's algorithm on node level: a node is ready when all producer nodes are placed
+		std::map<Id_t, std::set<Id_t>> producers;
+		for (const auto& [_, link] : links) producers[pins.at(link.to).parent].insert(pins.at(link.from).parent);
+		std::map<Id_t, size_t> pending;
+		for (const auto& [id, _] : nodes) pending[id] = producers.contains(id) ? producers.at(id).size() : 0;
+
+		std::vector<std::vector<Id_t>> levels;
+		std::vector<Id_t> frontier;
+		for (const auto& [id, n] : pending)
+			if (n == 0) frontier.push_back(id);
+		if (!nodes.empty() && frontier.empty()) throw Loop_detected_error{};
+		size_t placed = 0;
+		while (!frontier.empty())
+		{
+			levels.push_back(frontier);
+			placed += frontier.size();
+			std::vector<Id_t> next;
+			for (const Id_t id : frontier)
+			{
+				const auto succ = successors.find(id);
+				if (succ == successors.end()) continue;
+				for (const Id_t s : succ->second)
+					if (--pending[s] == 0) next.push_back(s);
+			}
+			std::sort(next.begin(), next.end());
+			frontier = std::move(next);
+		}
+		if (placed != nodes.size()) throw Loop_detected_error{};
+		return levels;
+	}
+
+	void Graph::check_graph() const { (void)topological_levels(); }
+
+	Json::Value Graph::serialize() const
+	{
+		Json::Value node_json(Json::objectValue);
+		for (const auto& [id, node] : nodes)
+		{
+			Json::Value item;
+			item["identifier"] = node.processor->get_processor_info_non_static().identifier;
+			item["info"] = node.processor->serialize();
+			item["position"]["x"] = node.position.x;
+			item["position"]["y"] = node.position.y;
+			node_json[std::to_string(id)] = std::move(item);
+		}
+		Json::Value link_json(Json::arrayValue);
+		for (const auto& [_, link] : links)
+		{
+			const Pin& from_pin = pins.at(link.from);
+			const Pin& to_pin = pins.at(link.to);
+			Json::Value item;
+			item["from"]["node"] = from_pin.parent;
+			item["from"]["pin"] = from_pin.attribute.identifier;
+			item["to"]["node"] = to_pin.parent;
+			item["to"]["pin"] = to_pin.attribute.identifier;
+			link_json.append(std::move(item));
+		}
+		Json::Value result;
+		result["nodes"] = std::move(node_json);
+		result["links"] = std::move(link_json);
+		return result;
+	}
+
+	Graph Graph::deserialize(const Json::Value& value)
+	try
+	{
+		if (!value.isObject()) throw Invalid_file_error("Invalid graph format, expected object");
+		const Json::Value& nodes_json = value["nodes"];
+		const Json::Value& links_json = value["links"];
+		if (!nodes_json.isObject()) throw Invalid_file_error("Invalid nodes format, expected object");
+		if (!links_json.isArray()) throw Invalid_file_error("Invalid links format, expected array");
+
+		Graph graph;
+		for (const auto& key : nodes_json.getMemberNames())
+		{
+			size_t used = 0;
+			Id_t id = 0;
+			try { id = std::stoi(key, &used); } catch (const std::exception&) { used = 0; }
+			if (used != key.length() || key.empty()) throw Invalid_file_error(std::format("Invalid node ID: {}", key));
+
+			const Json::Value& node_json = nodes_json[key];
+			if (!node_json.isObject()) throw Invalid_file_error(std::format("Invalid node JSON format for ID: {}", id));
+			const std::string identifier = node_json["identifier"].asString();
+			const auto meta = Processor::processor_map.find(identifier);
+			if (meta == Processor::processor_map.end())
+				throw Invalid_file_error(std::format("Unknown processor identifier: {}", identifier));
+
+			std::shared_ptr<Processor> processor = meta->second.generate();
+			processor->deserialize(node_json["info"]);
+			if (meta->second.singleton)
+			{
+				if (graph.singleton_node_map.contains(identifier))
+					throw Invalid_file_error(std::format("Duplicating singleton node \"{}\"", identifier));
+				graph.singleton_node_map.emplace(identifier, id);
+			}
+			Node node;
+			node.processor = std::move(processor);
+			node.position = ImVec2(node_json["position"]["x"].asFloat(), node_json["position"]["y"].asFloat());
+			graph.nodes.emplace(id, std::move(node));
+			graph.update_node_pin(id);
+		}
+
+		for (const Json::Value& link : links_json)
+		{
+			if (!link.isObject()) throw Invalid_file_error("Invalid link JSON format, expected object");
+			const Json::Value& from_json = link["from"];
+			const Json::Value& to_json = link["to"];
+			if (!from_json.isObject() || !to_json.isObject())
+				throw Invalid_file_error("Invalid link 'from' or 'to' JSON format, expected object");
+			const Id_t from_node = from_json["node"].asInt(), to_node = to_json["node"].asInt();
+			const std::string from_pin = from_json["pin"].asString(), to_pin = to_json["pin"].asString();
+			if (!graph.nodes.contains(from_node) || !graph.nodes.contains(to_node))
+				throw Invalid_file_error(std::format("Link references non-existent node: {} -> {}", from_node, to_node));
+			const auto& from_map = graph.nodes.at(from_node).pin_name_map;
+			const auto& to_map = graph.nodes.at(to_node).pin_name_map;
+			if (!from_map.contains(from_pin) || !to_map.contains(to_pin))
+				throw Invalid_file_error(
+					std::format("Link references non-existent pin: {}.{} -> {}.{}", from_node, from_pin, to_node, to_pin));
+			graph.add_link(from_map.at(from_pin), to_map.at(to_pin));
+		}
+		return graph;
+	}
+	catch (const Json::Exception& e)
+	{
+		throw Invalid_file_error(std::format("Failed to deserialize graph due to JSON error: {}", e.what()));
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// Runner
+	// ---------------------------------------------------------------------------------------------
+	void Runner::generate_processor_resources(const Graph& graph)
+	{
+		levels = graph.topological_levels();   // = check_graph(), and the schedule
+
+		for (const auto& [id, node] : graph.nodes)
+		{
+			auto resource = std::make_shared<Processor_resource>();
+			resource->processor = node.processor;
+			for (const Id_t pin_id : node.pins)
+			{
+				const auto& attribute = graph.pins.at(pin_id).attribute;
+				if (!attribute.is_input) resource->output_payloads.emplace(attribute.identifier, std::set<std::shared_ptr<Processor::Product>>{});
+			}
+			processor_resources.emplace(id, std::move(resource));
+		}
+
+		// one product per link, generated by the source pin; fan-out = several products on one output pin
+		for (const auto& [idx, link] : graph.links)
+		{
+			const Graph::Pin& from_pin = graph.pins.at(link.from);
+			const Graph::Pin& to_pin = graph.pins.at(link.to);
+			std::shared_ptr<Processor::Product> product = from_pin.attribute.generate_func();
+			processor_resources.at(from_pin.parent)->output_payloads[from_pin.attribute.identifier].insert(product);
+			processor_resources.at(to_pin.parent)->input_payloads.emplace(to_pin.attribute.identifier, product);
+			link_products.emplace(idx, product);
+		}
+	}
+
+	Runner::~Runner()
+	{
+		for (auto& [_, resource] : processor_resources) resource->stop_source = true;
+		if (worker.joinable()) worker.join();
+	}
+
+	void Runner::wait()
+	{
+		if (worker.joinable()) worker.join();
+	}
+
+	std::string Runner::first_error() const
+	{
+		for (const auto& [id, resource] : processor_resources)
+		{
+			if (resource->state != State::Error) continue;
+			const std::string who = std::format("node {} ({}): ", id, resource->processor->get_processor_info_non_static().identifier);
+			if (const auto* e = std::any_cast<Processor::Runtime_error>(&resource->exception)) return who + e->what();
+			if (const auto* e = std::any_cast<std::runtime_error>(&resource->exception)) return who + e->what();
+			if (const auto* e = std::any_cast<std::logic_error>(&resource->exception)) return who + e->what();
+			return who + "unknown exception";
+		}
+		return "";
+	}
+
+	namespace
+	{
+		// the catch ladder of the reference's fiber body (src/infra/runner.cpp:87-136)
+		template <typename F>
+		bool guarded(Runner::Processor_resource& r, F&& body)
+		{
+			const auto name = [&] { return r.processor->get_processor_info_non_static().identifier; };
+			try { body(); return true; }
+			catch (const Processor::Runtime_error& e) { r.exception = e; }
+			catch (const std::bad_any_cast&) { r.exception = std::logic_error(std::format("Bad any cast found in the processor \"{}\"", name())); }
+			catch (const std::bad_alloc&) { r.exception = std::runtime_error(std::format("Memory allocation failed in the processor \"{}\"", name())); }
+			catch (const std::bad_optional_access&) { r.exception = std::logic_error(std::format("Bad optional access found in the processor \"{}\"", name())); }
+			catch (const std::runtime_error& e) { r.exception = e; }
+			catch (const std::logic_error& e) { r.exception = e; }
+			catch (...) { r.exception = std::exception(); }
+			r.state = Runner::State::Error;
+			return false;
+		}
+	}
+
+	void Runner::launch_threads()
+	{
+		constexpr int kLanes = 4;
+		nodey_stream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+		bool failed = false;
+		if (device >= 0 && nodey_set_device(device) != NODEY_OK) failed = true;
+		for (auto& s : lanes)
+			if (nodey_stream_create(&s) != NODEY_OK) failed = true;
+		if (failed)
+		{
+			for (auto& [_, r] : processor_resources)
+			{
+				r->exception = Processor::Runtime_error("No CUDA device", "The render engine needs a CUDA device; there is no CPU fallback.", nodey_last_error());
+				r->state = State::Error;
+			}
+			done = true;
+			return;
+		}
+
+		std::any fallback;
+		int level_index = 0;
+		for (const auto& level : levels)
+		{
+			if (failed) break;
+			// group the level's nodes by class: one batch call per class, on its own stream lane
+			std::map<std::type_index, std::vector<Id_t>> groups;
+			for (const Id_t id : level) groups[std::type_index(typeid(*processor_resources.at(id)->processor))].push_back(id);
+			int lane = 0;
+			for (auto& [_, ids] : groups)
+			{
+				Exec_context& ctx = Exec_context::current();
+				ctx.stream = lanes[lane % kLanes];
+				ctx.level = level_index;
+				ctx.lane = lane % kLanes;
+				lane++;
+
+				std::vector<Processor::Batch_item> items;
+				for (const Id_t id : ids)
+				{
+					Processor_resource& r = *processor_resources.at(id);
+					if (r.stop_source) continue;
+					const auto data = node_data.find(id);
+					items.push_back(Processor::Batch_item{
+						r.processor.get(), &r.input_payloads, &r.output_payloads, &r.stop_source,
+						data == node_data.end() ? &fallback : data->second.get()});
+					r.state = State::Running;
+				}
+				if (items.empty()) continue;
+
+				bool batched = false;
+				if (items.size() > 1)
+				{
+					// a batch failure is reported on every node of the batch
+					Processor_resource& first = *processor_resources.at(ids.front());
+					const bool ok = guarded(first, [&] { batched = items.front().processor->process_batch(items); });
+					if (!ok)
+					{
+						for (const Id_t id : ids)
+						{
+							Processor_resource& r = *processor_resources.at(id);
+							if (&r != &first) { r.exception = first.exception; r.state = State::Error; }
+						}
+						failed = true;
+						break;
+					}
+				}
+				if (batched)
+				{
+					for (const Id_t id : ids) processor_resources.at(id)->state = State::Finished;
+					continue;
+				}
+				for (size_t k = 0; k < items.size() && !failed; k++)
+				{
+					Processor_resource& r = *processor_resources.at(ids[k]);
+					const auto& it = items[k];
+					if (guarded(r, [&] { it.processor->process_payload(*it.input, *it.output, *it.stop_token, *it.user_data); }))
+						r.state = State::Finished;
+					else
+						failed = true;
+				}
+				if (failed) break;
+			}
+			level_index++;
+		}
+		for (auto& s : lanes)
+		{
+			nodey_stream_synchronize(s);
+			nodey_stream_destroy(s);
+		}
+		done = true;
+	}
+
+	std::unique_ptr<Runner> Runner::create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data)
+	{
+		auto runner = std::make_unique<Runner>();
+		runner->node_data = std::move(node_data);
+		runner->generate_processor_resources(graph);
+		if (nodey_get_device(&runner->device) != NODEY_OK) runner->device = -1;
+		runner->worker = std::thread(&Runner::launch_threads, runner.get());
+		return runner;
+	}
+}

@@ -1,0 +1,1145 @@
+// nodes.cpp -- the processor nodes over the C ABI (include/nodey_cuda.h).  A node only plans (pure host
+// arithmetic on lengths and frame sizes) and enqueues kernels on the stream the Runner gave it; the
+// published product carries the event consumers order themselves after.  Reference per node: see
+// include/processor/nodes.hpp.
+#include "processor/nodes.hpp"
+
+#include "nodey_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <tuple>
+
+namespace processor
+{
+	using infra::Exec_context;
+	using infra::Processor;
+	using Runtime_error = infra::Processor::Runtime_error;
+
+	// ---------------------------------------------------------------------------------------------
+	// helpers
+	// ---------------------------------------------------------------------------------------------
+	Frame_runs uniform_frame_runs(int64_t frames, int64_t frame_size)
+	{
+		Frame_runs runs;
+		if (frames <= 0 || frame_size <= 0) return runs;
+		if (frames / frame_size) runs.emplace_back(frame_size, frames / frame_size);
+		if (frames % frame_size) runs.emplace_back(frames % frame_size, 1);
+		return runs;
+	}
+
+	int64_t frame_runs_total(const Frame_runs& runs)
+	{
+		int64_t n = 0;
+		for (const auto& [len, count] : runs) n += len * count;
+		return n;
+	}
+
+	namespace
+	{
+		nodey_stream_t cur_stream() { return Exec_context::current().stream; }
+
+		void abi(int rc, const char* node)
+		{
+			if (rc == NODEY_OK) return;
+			const std::string text = nodey_last_error();
+			if (rc == NODEY_E_NOMEM) throw std::bad_alloc();
+			if (rc == NODEY_E_FORMAT) throw Runtime_error("Unsupported sample format", std::format("{} cannot process this sample format.", node), text);
+			if (rc == NODEY_E_RANGE) throw Runtime_error("Parameter out of range", std::format("{} was given a value the reference rejects too.", node), text);
+			throw Runtime_error("GPU kernel call failed", std::format("{} could not enqueue its work.", node), text);
+		}
+
+		struct Pin_type
+		{
+			static Processor::Pin_attribute audio(std::string id, std::string name, bool is_input)
+			{
+				return {.identifier = std::move(id), .display_name = std::move(name), .type = typeid(Audio_stream), .is_input = is_input,
+						.generate_func = [] { return std::make_shared<Audio_stream>(); }};
+			}
+		};
+
+		// sub-allocator over one Device_block: every product of a batch is a view into the same block
+		struct Arena
+		{
+			std::shared_ptr<infra::Device_block> block;
+			size_t used = 0;
+			explicit Arena(size_t bytes) : block(std::make_shared<infra::Device_block>(bytes + 256)) {}
+			static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+			void* take(size_t bytes)
+			{
+				void* p = (char*)block->ptr + used;
+				used += padded(bytes);
+				if (used > block->bytes) THROW_LOGIC_ERROR("arena overflow: {} of {}", used, block->bytes);
+				return p;
+			}
+		};
+
+		std::shared_ptr<const Audio_buffer> require_input(const Processor::Input_map& input, const std::string& key,
+														   const char* node_title)
+		{
+			const auto item = infra::get_input_item<Audio_stream>(input, key);
+			if (!item.has_value())
+				throw Runtime_error(std::format("{} has no input", node_title),
+									std::format("{} requires an audio stream on pin '{}'.", node_title, key),
+									std::format("Input item '{}' not found", key));
+			auto buffer = item->get().get();
+			if (!buffer)
+				throw Runtime_error(std::format("{} received an empty stream", node_title),
+									"The upstream node closed its stream without publishing audio.", std::format("pin '{}'", key));
+			if (buffer->ready) buffer->ready->wait_on(cur_stream());
+			return buffer;
+		}
+
+		void publish(const Processor::Output_map& output, const std::string& key, const std::shared_ptr<Audio_buffer>& buffer)
+		{
+			if (!buffer->ready)
+			{
+				auto ev = std::make_shared<infra::Device_event>();
+				ev->record(cur_stream());
+				buffer->ready = std::move(ev);
+			}
+			for (auto& stream : infra::get_output_item<Audio_stream>(output, key)) stream->publish(buffer);
+		}
+
+		std::shared_ptr<Audio_buffer> new_buffer(const std::shared_ptr<infra::Device_block>& block, void* p0, void* p1, int fmt, int rate,
+												 int ch, int64_t frames, Frame_runs runs, double pts)
+		{
+			auto b = std::make_shared<Audio_buffer>();
+			b->block = block; b->plane[0] = p0; b->plane[1] = p1; b->format = fmt; b->sample_rate = rate; b->channels = ch;
+			b->frames = frames; b->runs = std::move(runs); b->pts_seconds = pts;
+			return b;
+		}
+
+		void check_channels(const Audio_buffer& b, const char* node)
+		{
+			if (b.channels != 1 && b.channels != 2)
+				throw Runtime_error("Invalid channel layout", std::format("{} handles mono and stereo streams.", node), std::format("channels: {}", b.channels));
+			if (format_bytes(b.format) == 0)
+				throw Runtime_error("Audio format is not support (Include FLT, S16, S32)", std::format("{} cannot process this sample format.", node),
+									std::format("AVSampleFormat {}", b.format));
+		}
+
+		// process-wide plan caches (plans are immutable once built; kernels in flight keep using them)
+		std::mutex plan_mutex;
+
+		nodey_resampler* resampler_for(int in_rate)
+		{
+			static std::map<int, nodey_resampler*> cache;
+			std::lock_guard lock(plan_mutex);
+			const auto it = cache.find(in_rate);
+			if (it != cache.end()) return it->second;
+			nodey_resampler* r = nullptr;
+			abi(nodey_resampler_create(&r, in_rate, 48000, 0), "swresample plan");
+			cache[in_rate] = r;
+			return r;
+		}
+
+		nodey_soundtouch* soundtouch_for(int rate_hz, int ch, float rate, float pitch, int64_t n_in)
+		{
+			static std::map<std::tuple<int, int, uint32_t, uint32_t, int64_t>, nodey_soundtouch*> cache;
+			uint32_t rb, pb;
+			memcpy(&rb, &rate, 4); memcpy(&pb, &pitch, 4);
+			std::lock_guard lock(plan_mutex);
+			const auto key = std::make_tuple(rate_hz, ch, rb, pb, n_in);
+			const auto it = cache.find(key);
+			if (it != cache.end()) return it->second;
+			nodey_soundtouch* s = nullptr;
+			const int rc = nodey_soundtouch_create(&s, rate_hz, ch, rate, pitch);
+			if (rc == NODEY_E_RANGE)
+				throw Runtime_error("Unsupported sample rate", std::format("{} requires a sample rate between 8000 and 48000 Hz.", rate_hz),
+									nodey_last_error());
+			abi(rc, "SoundTouch");
+			cache[key] = s;
+			return s;
+		}
+
+		struct Runs_flat
+		{
+			std::vector<int64_t> off, len, count;
+			explicit Runs_flat(const std::vector<const Frame_runs*>& all)
+			{
+				off.push_back(0);
+				for (const Frame_runs* runs : all)
+				{
+					for (const auto& [l, c] : *runs) { len.push_back(l); count.push_back(c); }
+					off.push_back((int64_t)len.size());
+				}
+				if (len.empty()) { len.push_back(0); count.push_back(0); }
+			}
+		};
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_input
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_input::get_processor_info()
+	{
+		return {.identifier = "audio_input", .display_name = "Audio Input", .singleton = true, .generate = std::make_unique<Audio_input>,
+				.description = "PCM sources of the render: one output pin per file slot. Sources are raw PCM buffers handed in by the host "
+							   "(Pcm_source_list) or RIFF/WAVE files named by file_path."};
+	}
+
+	std::vector<Processor::Pin_attribute> Audio_input::get_pin_attributes() const
+	{
+		std::vector<Processor::Pin_attribute> pins;
+		for (size_t i = 0; i < file_count; i++) pins.push_back(Pin_type::audio(std::format("output_{}", i), std::format("Output {}", i), false));
+		return pins;
+	}
+
+	void Audio_input::set_file_count(size_t n)
+	{
+		file_count = std::max<size_t>(n, 1);
+		file_paths.resize(file_count);
+	}
+
+	Json::Value Audio_input::serialize() const
+	{
+		Json::Value list(Json::arrayValue);
+		for (const auto& path : file_paths) list.append(path);
+		Json::Value value(Json::objectValue);
+		value["file_path"] = list;
+		return value;
+	}
+
+	void Audio_input::deserialize(const Json::Value& value)
+	{
+		const auto bad = [](const char* field) {
+			return Runtime_error("Failed to deserialize JSON file",
+								 "Audio_input failed to serialize the JSON input because of missing or invalid fields.", std::format("Wrong field: {}", field));
+		};
+		if (!value.isObject() || !value.isMember("file_path") || !value["file_path"].isArray()) throw bad("file_path");
+		file_paths.clear();
+		for (const auto& path : value["file_path"])
+		{
+			if (!path.isString()) throw bad("file_path.path");
+			file_paths.push_back(path.asString());
+		}
+		file_count = std::max<size_t>(file_paths.size(), 1);
+		file_paths.resize(file_count);
+	}
+
+	namespace
+	{
+		// canonical RIFF/WAVE reader: PCM 16 / 32 bit and IEEE float 32
+		struct Wav_data { std::vector<char> samples; int format = FMT_S16, rate = 0, channels = 0; int64_t frames = 0; };
+
+		Wav_data read_wav(const std::string& path)
+		{
+			const auto fail = [&](const std::string& why) {
+				return Runtime_error("Cannot open audio file", std::format("'{}' is not a PCM/float RIFF WAVE file this engine can read.", path), why);
+			};
+			std::ifstream f(path, std::ios::binary);
+			if (!f) throw fail("file not found or unreadable");
+			char hdr[12];
+			if (!f.read(hdr, 12) || memcmp(hdr, "RIFF", 4) || memcmp(hdr + 8, "WAVE", 4)) throw fail("missing RIFF/WAVE header");
+			Wav_data w;
+			int tag = 0, bits = 0;
+			bool have_fmt = false;
+			for (;;)
+			{
+				char ck[8];
+				if (!f.read(ck, 8)) break;
+				uint32_t size; memcpy(&size, ck + 4, 4);
+				if (!memcmp(ck, "fmt ", 4))
+				{
+					std::vector<char> b(size);
+					if (!f.read(b.data(), size) || size < 16) throw fail("truncated fmt chunk");
+					uint16_t t, c, bp; uint32_t r;
+					memcpy(&t, b.data(), 2); memcpy(&c, b.data() + 2, 2); memcpy(&r, b.data() + 4, 4); memcpy(&bp, b.data() + 14, 2);
+					if (t == 0xFFFE && size >= 26) memcpy(&t, b.data() + 24, 2);   // WAVE_FORMAT_EXTENSIBLE sub-format
+					tag = t; w.channels = c; w.rate = (int)r; bits = bp; have_fmt = true;
+				}
+				else if (!memcmp(ck, "data", 4))
+				{
+					if (!have_fmt) throw fail("data chunk before fmt chunk");
+					w.samples.resize(size);
+					f.read(w.samples.data(), size);
+					w.samples.resize((size_t)f.gcount());
+					break;
+				}
+				else f.seekg(size + (size & 1), std::ios::cur);
+			}
+			if (!have_fmt || w.channels < 1 || w.channels > 2) throw fail("unsupported channel count");
+			if (tag == 1 && bits == 16) w.format = FMT_S16;
+			else if (tag == 1 && bits == 32) w.format = FMT_S32;
+			else if (tag == 3 && bits == 32) w.format = FMT_FLT;
+			else throw fail(std::format("unsupported encoding (tag {}, {} bits)", tag, bits));
+			w.frames = (int64_t)(w.samples.size() / (size_t)(format_bytes(w.format) * w.channels));
+			return w;
+		}
+	}
+
+	void Audio_input::process_payload(const Input_map&, const Output_map& output, const std::atomic<bool>&, std::any& user_data)
+	{
+		const Pcm_source_list* bound = std::any_cast<Pcm_source_list>(&user_data);
+		if (!bound)
+			if (const auto* sp = std::any_cast<std::shared_ptr<Pcm_source_list>>(&user_data)) bound = sp->get();
+
+		std::vector<Wav_data> files;     // keeps file payloads alive until the copies are enqueued... and landed
+		std::vector<Pcm_source> sources(file_count);
+		for (size_t i = 0; i < file_count; i++)
+		{
+			const auto find = output.find(std::format("output_{}", i));
+			const bool used = find != output.end() && !find->second.empty();
+			if (bound && i < bound->sources.size() && bound->sources[i].data) { sources[i] = bound->sources[i]; continue; }
+			if (!used) continue;
+			if (file_paths[i].empty())
+				throw Runtime_error("No input source", std::format("Output {} of the audio input node is linked but has neither a PCM source nor a file.", i),
+									std::format("pin output_{}", i));
+			files.push_back(read_wav(file_paths[i]));
+			const Wav_data& w = files.back();
+			sources[i].data = w.samples.data(); sources[i].format = w.format; sources[i].sample_rate = w.rate;
+			sources[i].channels = w.channels; sources[i].frames = w.frames; sources[i].frame_size = 1024;
+		}
+
+		// one arena for every host source that has to be uploaded
+		size_t upload_bytes = 0;
+		for (const auto& s : sources)
+			if (s.data && !s.on_device) upload_bytes += Arena::padded((size_t)s.frames * (size_t)format_bytes(s.format) * (size_t)s.channels);
+		std::unique_ptr<Arena> arena;
+		if (upload_bytes) arena = std::make_unique<Arena>(upload_bytes);
+
+		for (size_t i = 0; i < file_count; i++)
+		{
+			const Pcm_source& s = sources[i];
+			const std::string key = std::format("output_{}", i);
+			const auto find = output.find(key);
+			if (!s.data || find == output.end() || find->second.empty()) continue;
+			if (format_bytes(s.format) == 0 || (s.channels != 1 && s.channels != 2))
+				throw Runtime_error("Unsupported sample format", "PCM sources must be S16/S32/FLT (packed or planar), mono or stereo.", key);
+			const size_t plane_bytes = (size_t)s.frames * (size_t)format_bytes(s.format) * (format_is_planar(s.format) ? 1u : (size_t)s.channels);
+			void* p0 = const_cast<void*>(s.data);
+			void* p1 = const_cast<void*>(s.data1);
+			std::shared_ptr<infra::Device_block> owner;
+			if (!s.on_device)
+			{
+				owner = arena->block;
+				const bool planar2 = format_is_planar(s.format) && s.channels == 2;
+				p0 = arena->take(planar2 ? 2 * Arena::padded(plane_bytes) : plane_bytes);
+				abi(nodey_memcpy_h2d(p0, s.data, plane_bytes, cur_stream()), "audio_input");
+				if (planar2)
+				{
+					p1 = (char*)p0 + Arena::padded(plane_bytes);
+					abi(nodey_memcpy_h2d(p1, s.data1, plane_bytes, cur_stream()), "audio_input");
+				}
+			}
+			publish(output, key, new_buffer(owner, p0, p1, s.format, s.sample_rate, s.channels, s.frames,
+											uniform_frame_runs(s.frames, s.frame_size), s.pts_seconds));
+		}
+		// file payloads are pageable host memory: make sure the copies have landed before they are freed
+		if (!files.empty()) abi(nodey_stream_synchronize(cur_stream()), "audio_input");
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_output
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_output::get_processor_info()
+	{
+		return {.identifier = "audio_output", .display_name = "Audio Output", .singleton = true, .generate = std::make_unique<Audio_output>,
+				.description = "Sink of the render: keeps the rendered stream for the host and optionally writes it as a float WAV file."};
+	}
+
+	std::vector<Processor::Pin_attribute> Audio_output::get_pin_attributes() const { return {Pin_type::audio("input", "Input", true)}; }
+
+	void Audio_output::process_payload(const Input_map& input, const Output_map&, const std::atomic<bool>&, std::any& user_data)
+	{
+		auto buffer = require_input(input, "input", "Audio output");
+		Process_context* ctx = std::any_cast<Process_context>(&user_data);
+		if (!ctx) throw std::bad_any_cast();
+		ctx->rendered = buffer;
+		abi(nodey_stream_synchronize(cur_stream()), "audio_output");     // the sink is where the host waits for the device
+		if (!ctx->export_path.empty())
+		{
+			// interleaved float WAV (the reference encodes MP3 with LAME; codec I/O is out of scope here)
+			check_channels(*buffer, "Audio output");
+			infra::Device_block tmp((size_t)buffer->frames * (size_t)buffer->channels * sizeof(float));
+			abi(nodey_extract_interleaved((float*)tmp.ptr, buffer->plane[0], buffer->plane[1], buffer->format, buffer->frames, buffer->channels, cur_stream()),
+				"audio_output");
+			std::vector<float> host((size_t)buffer->frames * (size_t)buffer->channels);
+			abi(nodey_memcpy_d2h(host.data(), tmp.ptr, host.size() * sizeof(float), cur_stream()), "audio_output");
+			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
+			std::ofstream f(ctx->export_path, std::ios::binary);
+			if (!f) throw Runtime_error("Cannot write output file", "The export path could not be opened for writing.", ctx->export_path);
+			const uint32_t data_bytes = (uint32_t)(host.size() * sizeof(float));
+			const uint16_t tag = 3, ch = (uint16_t)buffer->channels, bits = 32, align = (uint16_t)(4 * buffer->channels);
+			const uint32_t rate = (uint32_t)buffer->sample_rate, byte_rate = rate * align, riff = 36 + data_bytes, fmt_size = 16;
+			f.write("RIFF", 4); f.write((const char*)&riff, 4); f.write("WAVEfmt ", 8); f.write((const char*)&fmt_size, 4);
+			f.write((const char*)&tag, 2); f.write((const char*)&ch, 2); f.write((const char*)&rate, 4); f.write((const char*)&byte_rate, 4);
+			f.write((const char*)&align, 2); f.write((const char*)&bits, 2); f.write("data", 4); f.write((const char*)&data_bytes, 4);
+			f.write((const char*)host.data(), data_bytes);
+		}
+		if (ctx->time) ctx->time->store((double)buffer->frames / (double)buffer->sample_rate);
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_volume_adjust  (audio-vol.cpp:75-100, 102-250)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_vol::get_processor_info()
+	{
+		return {.identifier = "audio_volume_adjust", .display_name = "Volume Adjust", .singleton = false, .generate = std::make_unique<Audio_vol>,
+				.description = "Multiplies every sample by the gain (0..10). Integer formats are scaled in float and truncated like the reference; "
+							   "format, layout and rate pass through."};
+	}
+
+	std::vector<Processor::Pin_attribute> Audio_vol::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input", "Input", true)};
+	}
+
+	void Audio_vol::set_volume(float v) { volume = std::clamp(v, 0.0f, 10.0f); }
+
+	void Audio_vol::deserialize(const Json::Value& value)
+	{
+		if (value.isObject() && value.isMember("volume") && value["volume"].isDouble()) set_volume(value["volume"].asFloat());
+	}
+
+	namespace
+	{
+		void gain_into(const Audio_buffer& in, float volume, void* p0, void* p1)
+		{
+			const int64_t n = format_is_planar(in.format) ? in.frames : in.frames * in.channels;
+			abi(nodey_gain(p0, in.plane[0], in.format, n, volume, cur_stream()), "Volume adjust");
+			if (format_is_planar(in.format) && in.channels == 2) abi(nodey_gain(p1, in.plane[1], in.format, n, volume, cur_stream()), "Volume adjust");
+		}
+	}
+
+	bool Audio_vol::process_batch(const std::vector<Batch_item>& items)
+	{
+		std::vector<std::shared_ptr<const Audio_buffer>> ins;
+		size_t bytes = 0;
+		for (const auto& it : items)
+		{
+			ins.push_back(require_input(*it.input, "input", "Volume adjust processor"));
+			check_channels(*ins.back(), "Volume adjust");
+			const bool planar2 = format_is_planar(ins.back()->format) && ins.back()->channels == 2;
+			bytes += Arena::padded(ins.back()->plane_bytes()) * (planar2 ? 2 : 1);
+		}
+		Arena arena(bytes);
+		for (size_t k = 0; k < items.size(); k++)
+		{
+			const Audio_buffer& in = *ins[k];
+			const bool planar2 = format_is_planar(in.format) && in.channels == 2;
+			void* p0 = arena.take(in.plane_bytes());
+			void* p1 = planar2 ? arena.take(in.plane_bytes()) : nullptr;
+			gain_into(in, static_cast<Audio_vol*>(items[k].processor)->volume, p0, p1);
+			publish(*items[k].output, "output", new_buffer(arena.block, p0, p1, in.format, in.sample_rate, in.channels, in.frames, in.runs, in.pts_seconds));
+		}
+		return true;
+	}
+
+	void Audio_vol::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
+	{
+		process_batch({Batch_item{this, &input, &output, &stop, &user_data}});
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// velocity_modifier / pitch_modifier  (audio-velocity.cpp:265-477)
+	// ---------------------------------------------------------------------------------------------
+	struct Soundtouch_params
+	{
+		float rate, pitch;
+		static Soundtouch_params of(const Processor* p)
+		{
+			if (const auto* v = dynamic_cast<const Velocity_modifier*>(p))
+				return {v->velocity, v->keep_pitch ? 1 / v->velocity : 1};                 // audio-velocity.cpp:457
+			const auto* q = dynamic_cast<const Pitch_modifier*>(p);
+			return {1.0f, std::pow(2.0f, q->pitch / 12.0f)};                                // audio-velocity.cpp:473-474
+		}
+	};
+
+	namespace
+	{
+		constexpr int kSoundtouchFrame = 1152;     // canonical putSamples / output chunk
+		constexpr size_t kMaxTracksPerLaunch = 128;
+
+		bool soundtouch_batch(const std::vector<Processor::Batch_item>& items, const char* title)
+		{
+			struct Entry { size_t item; std::shared_ptr<const Audio_buffer> in; Soundtouch_params prm; };
+			std::map<std::tuple<int, int, int64_t, uint32_t, uint32_t>, std::vector<Entry>> groups;
+			for (size_t k = 0; k < items.size(); k++)
+			{
+				auto in = require_input(*items[k].input, "input", title);
+				check_channels(*in, title);
+				const Soundtouch_params prm = Soundtouch_params::of(items[k].processor);
+				uint32_t rb, pb;
+				memcpy(&rb, &prm.rate, 4); memcpy(&pb, &prm.pitch, 4);
+				groups[{in->sample_rate, in->channels, in->frames, rb, pb}].push_back({k, std::move(in), prm});
+			}
+			for (auto& [key, all] : groups)
+			{
+				const auto [rate_hz, ch, n, rb_, pb_] = key;
+				(void)rb_; (void)pb_;
+				nodey_soundtouch* st = soundtouch_for(rate_hz, ch, all.front().prm.rate, all.front().prm.pitch, n);
+				int64_t nseq = 0;
+				const int64_t m = nodey_soundtouch_out_frames(st, n, kSoundtouchFrame, &nseq);
+				if (m < 0) abi((int)m, title);
+				for (size_t first = 0; first < all.size(); first += kMaxTracksPerLaunch)
+				{
+					const size_t cnt = std::min(kMaxTracksPerLaunch, all.size() - first);
+					const size_t in_stride = Arena::padded((size_t)n * ch * sizeof(float)) / sizeof(float);
+					const size_t out_stride = Arena::padded((size_t)std::max<int64_t>(m, 1) * ch * sizeof(float)) / sizeof(float);
+					// A8: extract_samples_interleaved into one contiguous batch, then the whole-track SoundTouch
+					infra::Device_block staging(in_stride * sizeof(float) * cnt);
+					Arena arena(out_stride * sizeof(float) * cnt);
+					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
+					for (size_t k = 0; k < cnt; k++)
+					{
+						const Audio_buffer& in = *all[first + k].in;
+						abi(nodey_extract_interleaved((float*)staging.ptr + k * in_stride, in.plane[0], in.plane[1], in.format, n, ch, cur_stream()), title);
+					}
+					if (m > 0)
+						abi(nodey_soundtouch_run(st, out_base, (int64_t)out_stride, (const float*)staging.ptr, (int64_t)in_stride, (int)cnt, n,
+												 kSoundtouchFrame, m, nullptr, 0, cur_stream()), title);
+					for (size_t k = 0; k < cnt; k++)
+					{
+						const Entry& e = all[first + k];
+						publish(*items[e.item].output, "output",
+								new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m,
+										   uniform_frame_runs(m, kSoundtouchFrame), e.in->pts_seconds));
+					}
+				}
+			}
+			return true;
+		}
+	}
+
+	infra::Processor::Info Velocity_modifier::get_processor_info()
+	{
+		return {.identifier = "velocity_modifier", .display_name = "Velocity Modifier", .singleton = false,
+				.generate = std::make_unique<Velocity_modifier>,
+				.description = "Changes playback speed (0.5x..3x) with SoundTouch's rate transposer and WSOLA time stretcher; "
+							   "'keep_pitch' compensates the pitch change. Output: 32-bit float interleaved at the input rate."};
+	}
+	std::vector<Processor::Pin_attribute> Velocity_modifier::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input", "Input", true)};
+	}
+	Json::Value Velocity_modifier::serialize() const
+	{
+		Json::Value value;
+		value["velocity"] = velocity;
+		value["keep_pitch"] = keep_pitch;
+		return value;
+	}
+	void Velocity_modifier::deserialize(const Json::Value& value)
+	{
+		if (value.isMember("velocity") && value["velocity"].isDouble()) velocity = value["velocity"].asFloat();
+		if (value.isMember("keep_pitch") && value["keep_pitch"].isBool()) keep_pitch = value["keep_pitch"].asBool();
+	}
+	bool Velocity_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Velocity modifier"); }
+	void Velocity_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
+	{
+		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Velocity modifier");
+	}
+
+	infra::Processor::Info Pitch_modifier::get_processor_info()
+	{
+		return {.identifier = "pitch_modifier", .display_name = "Pitch Modifier", .singleton = false, .generate = std::make_unique<Pitch_modifier>,
+				.description = "Shifts the pitch by a number of semitones at constant duration (SoundTouch). "
+							   "Output: 32-bit float interleaved at the input rate."};
+	}
+	std::vector<Processor::Pin_attribute> Pitch_modifier::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input", "Input", true)};
+	}
+	Json::Value Pitch_modifier::serialize() const
+	{
+		Json::Value value;
+		value["pitch"] = pitch;
+		return value;
+	}
+	void Pitch_modifier::deserialize(const Json::Value& value)
+	{
+		if (value.isMember("pitch") && value["pitch"].isDouble()) pitch = value["pitch"].asFloat();
+	}
+	bool Pitch_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Pitch modifier"); }
+	void Pitch_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
+	{
+		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Pitch modifier");
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// mixers: shared machinery
+	// ---------------------------------------------------------------------------------------------
+	namespace
+	{
+		struct Segment { int input; int64_t out_start, src_start, len; };
+
+		// swr output of one input as two float planes [2][produced]; `contiguous` = it lands at output 0 unbroken
+		struct Resampled
+		{
+			std::shared_ptr<infra::Device_block> block;
+			float* l = nullptr; float* r = nullptr;
+			int64_t len = 0;
+		};
+
+		// resample one whole input (flush: with the reflected tail) to `produced` frames
+		Resampled resample_input(const Audio_buffer& in, int64_t produced, bool flush, const char* node)
+		{
+			Resampled out;
+			out.len = produced;
+			const size_t plane = Arena::padded((size_t)std::max<int64_t>(produced, 1) * sizeof(float));
+			out.block = std::make_shared<infra::Device_block>(2 * plane);
+			out.l = (float*)out.block->ptr;
+			out.r = (float*)((char*)out.block->ptr + plane);
+			if (produced > 0)
+				abi(nodey_resampler_run(resampler_for(in.sample_rate), out.l, out.r, in.plane[0], in.plane[1], in.format, in.channels, in.frames,
+										flush ? 1 : 0, produced, cur_stream()), node);
+			return out;
+		}
+
+		// place an input's resampled frames into zero-initialised planes of `total` frames (gappy inputs)
+		Resampled scatter(const Resampled& src, const std::vector<Segment>& segs, int input, int64_t total, const char* node)
+		{
+			Resampled out;
+			out.len = total;
+			const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+			out.block = std::make_shared<infra::Device_block>(2 * plane);
+			out.l = (float*)out.block->ptr;
+			out.r = (float*)((char*)out.block->ptr + plane);
+			abi(nodey_memset(out.block->ptr, 0, 2 * plane, cur_stream()), node);
+			for (const Segment& s : segs)
+			{
+				if (s.input != input) continue;
+				abi(nodey_memcpy_d2d(out.l + s.out_start, src.l + s.src_start, (size_t)s.len * sizeof(float), cur_stream()), node);
+				abi(nodey_memcpy_d2d(out.r + s.out_start, src.r + s.src_start, (size_t)s.len * sizeof(float), cur_stream()), node);
+			}
+			return out;
+		}
+
+		bool single_front_segment(const std::vector<Segment>& segs, int input, int64_t* len)
+		{
+			int count = 0;
+			*len = 0;
+			for (const Segment& s : segs)
+				if (s.input == input) { count++; if (s.out_start != 0 || s.src_start != 0) return false; *len = s.len; }
+			return count <= 1;
+		}
+
+		int64_t produced_of(const std::vector<Segment>& segs, int input)
+		{
+			int64_t n = 0;
+			for (const Segment& s : segs)
+				if (s.input == input) n = std::max(n, s.src_start + s.len);
+			return n;
+		}
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_amix  (audio-amix.cpp:86-324)
+	// ---------------------------------------------------------------------------------------------
+	Audio_amix::Audio_amix() : volumes(2, 1.0f), locks(2, false) {}     // App. C9: a fresh node mixes at unity
+
+	infra::Processor::Info Audio_amix::get_processor_info()
+	{
+		return {.identifier = "audio_amix", .display_name = "Audio Amix", .singleton = false, .generate = std::make_unique<Audio_amix>,
+				.description = "Mixes 1..16 inputs into one stereo stream: every input is converted to 48 kHz stereo float planar "
+							   "(libswresample defaults), scaled by its volume and summed in input order."};
+	}
+
+	std::vector<Processor::Pin_attribute> Audio_amix::get_pin_attributes() const
+	{
+		std::vector<Processor::Pin_attribute> pins;
+		pins.push_back(Pin_type::audio("output", "Output", false));
+		for (int i = 0; i < input_num; i++) pins.push_back(Pin_type::audio(std::format("input_{}", i + 1), std::format("Input {}", i + 1), true));
+		return pins;
+	}
+
+	Json::Value Audio_amix::serialize() const
+	{
+		Json::Value value;
+		value["input_num"] = input_num;
+		for (int i = 0; i < input_num; i++)
+		{
+			value[std::format("volumes{}", i)] = i < (int)volumes.size() ? volumes[(size_t)i] : 1.0f;
+			value[std::format("locks{}", i)] = i < (int)locks.size() ? (bool)locks[(size_t)i] : false;
+		}
+		return value;
+	}
+
+	void Audio_amix::deserialize(const Json::Value& value)
+	{
+		if (!value.isMember("input_num"))
+			throw Runtime_error("Failed to deserialize JSON file",
+								"Audio_amix failed to serialize the JSON input because of missing or invalid fields.", "Wrong field: input_num");
+		input_num = std::clamp(value["input_num"].asInt(), 1, NODEY_MAX_MIX_INPUTS);       // audio-amix.cpp:342
+		locks.clear();
+		volumes.clear();
+		for (int i = 0; i < input_num; i++)
+		{
+			volumes.push_back(value[std::format("volumes{}", i)].asFloat());
+			locks.push_back(value[std::format("locks{}", i)].asBool());
+		}
+	}
+
+	void Audio_amix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		const int nin = input_num;
+		std::vector<std::shared_ptr<const Audio_buffer>> ins;
+		std::vector<const Frame_runs*> runs;
+		std::vector<int> rates;
+		for (int i = 0; i < nin; i++)
+		{
+			ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer"));
+			check_channels(*ins.back(), "Audio mixer");
+			runs.push_back(&ins.back()->runs);
+			rates.push_back(ins.back()->sample_rate);
+		}
+		std::vector<float> vol(volumes);
+		vol.resize((size_t)nin, 1.0f);
+
+		// frame bookkeeping of the reference loop: total length, placement of every input, own frame sizes
+		const Runs_flat flat(runs);
+		std::vector<int32_t> seg_in(64);
+		std::vector<int64_t> seg_out(64), seg_src(64), seg_len(64), run_len(64), run_cnt(64);
+		int64_t nseg = 0, nrun = 0, total = 0;
+		for (int attempt = 0; attempt < 2; attempt++)
+		{
+			total = nodey_amix_plan(rates.data(), nin, flat.off.data(), flat.len.data(), flat.count.data(), 0, seg_in.data(), seg_out.data(),
+									seg_src.data(), seg_len.data(), (int64_t)seg_in.size(), &nseg, run_len.data(), run_cnt.data(),
+									(int64_t)run_len.size(), &nrun);
+			if (total < 0) abi((int)total, "Audio mixer");
+			if (nseg <= (int64_t)seg_in.size() && nrun <= (int64_t)run_len.size()) break;
+			const size_t a = (size_t)std::max<int64_t>(nseg, 64), b = (size_t)std::max<int64_t>(nrun, 64);
+			seg_in.resize(a); seg_out.resize(a); seg_src.resize(a); seg_len.resize(a); run_len.resize(b); run_cnt.resize(b);
+		}
+		std::vector<Segment> segs;
+		for (int64_t k = 0; k < nseg; k++) segs.push_back({seg_in[(size_t)k], seg_out[(size_t)k], seg_src[(size_t)k], seg_len[(size_t)k]});
+		Frame_runs out_runs;
+		for (int64_t k = 0; k < nrun; k++) out_runs.emplace_back(run_len[(size_t)k], run_cnt[(size_t)k]);
+
+		const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+		auto block = std::make_shared<infra::Device_block>(2 * plane);
+		float* out_l = (float*)block->ptr;
+		float* out_r = (float*)((char*)block->ptr + plane);
+
+		// fused path: same source rate (needs resampling), same channel count, every input lands unbroken at 0
+		bool fused = total > 0;
+		std::vector<int64_t> front_len((size_t)nin, 0);
+		for (int i = 0; i < nin && fused; i++)
+			fused = ins[(size_t)i]->sample_rate == ins[0]->sample_rate && ins[(size_t)i]->sample_rate != 48000
+				 && ins[(size_t)i]->channels == ins[0]->channels && single_front_segment(segs, i, &front_len[(size_t)i]);
+		if (fused)
+		{
+			int info[8];
+			abi(nodey_resampler_info(resampler_for(ins[0]->sample_rate), info), "Audio mixer");
+			fused = info[4] == 0;     // exact-rational plan: the tiled kernel exists
+		}
+		if (total > 0 && fused)
+		{
+			std::vector<const void*> p0, p1;
+			std::vector<int> fmt, ch;
+			std::vector<int64_t> in_frames;
+			for (const auto& in : ins) { p0.push_back(in->plane[0]); p1.push_back(in->plane[1]); fmt.push_back(in->format); ch.push_back(in->channels); in_frames.push_back(in->frames); }
+			const int rc = nodey_resample_mix(resampler_for(ins[0]->sample_rate), out_l, out_r, p0.data(), p1.data(), fmt.data(), ch.data(),
+											  in_frames.data(), front_len.data(), vol.data(), nin, 1, total, cur_stream());
+			if (rc == NODEY_E_RANGE) fused = false; else abi(rc, "Audio mixer");
+		}
+		if (total > 0 && !fused)
+		{
+			std::vector<Resampled> keep;
+			std::vector<const float*> pl, pr;
+			std::vector<int64_t> lens;
+			for (int i = 0; i < nin; i++)
+			{
+				Resampled r = resample_input(*ins[(size_t)i], produced_of(segs, i), true, "Audio mixer");
+				int64_t len = 0;
+				if (!single_front_segment(segs, i, &len)) { r = scatter(r, segs, i, total, "Audio mixer"); len = total; }
+				pl.push_back(r.l); pr.push_back(r.r); lens.push_back(len);
+				keep.push_back(std::move(r));
+			}
+			abi(nodey_mix(out_l, out_r, pl.data(), pr.data(), lens.data(), vol.data(), nin, total, cur_stream()), "Audio mixer");
+		}
+		// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
+		const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;
+		publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), pts));
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_bimix  (audio-bimix.cpp:83-331)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_bimix::get_processor_info()
+	{
+		return {.identifier = "audio_bimix", .display_name = "Audio Bimix", .singleton = false, .generate = std::make_unique<Audio_bimix>,
+				.description = "Builds a stereo stream from a left and a right input: each side is converted to 48 kHz stereo and folded to "
+							   "one channel; 'bias' (-1..1) shifts the balance."};
+	}
+	std::vector<Processor::Pin_attribute> Audio_bimix::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Input L", true), Pin_type::audio("input_r", "Input R", true)};
+	}
+	Json::Value Audio_bimix::serialize() const
+	{
+		Json::Value value;
+		value["bias"] = bias;
+		return value;
+	}
+	void Audio_bimix::deserialize(const Json::Value& value)
+	{
+		if (!value.isMember("bias") || !value["bias"].isDouble())
+			throw Runtime_error("Failed to deserialize JSON file",
+								"Audio_bimix failed to serialize the JSON input because of missing or invalid fields.", "Wrong field: bias");
+		bias = std::clamp<float>((float)value["bias"].asDouble(), -1, 1);
+	}
+
+	namespace
+	{
+		// frame cursor over run-length encoded frame sizes
+		struct Frame_cursor
+		{
+			const Frame_runs* runs; size_t run = 0; int64_t left = 0;
+			explicit Frame_cursor(const Frame_runs& r) : runs(&r) { settle(); }
+			void settle()
+			{
+				while (run < runs->size() && ((*runs)[run].first <= 0 || (*runs)[run].second <= 0)) run++;
+				left = run < runs->size() ? (*runs)[run].second : 0;
+			}
+			bool has() const { return run < runs->size(); }
+			int64_t size() const { return (*runs)[run].first; }
+			void next() { if (--left == 0) { run++; settle(); } }
+		};
+
+		// swr_convert bookkeeping for one input
+		struct Swr_state
+		{
+			const nodey_resampler* plan; int64_t n_in = 0, produced = 0, reflect = 0; bool flushed = false;
+			int64_t feed(int64_t frames, int64_t out_cap)
+			{
+				n_in += frames;
+				return take(out_cap);
+			}
+			int64_t flush(int64_t out_cap)
+			{
+				if (!flushed) { flushed = true; reflect = nodey_resampler_flush_reflect(plan, n_in, produced); }
+				return take(out_cap);
+			}
+			int64_t take(int64_t out_cap)
+			{
+				int64_t got = nodey_resampler_producible(plan, n_in, reflect) - produced;
+				got = std::clamp<int64_t>(got, 0, out_cap);
+				produced += got;
+				return got;
+			}
+		};
+
+		void add_segment(std::vector<Segment>& segs, int input, int64_t out_start, int64_t src_start, int64_t len)
+		{
+			if (len <= 0) return;
+			for (auto it = segs.rbegin(); it != segs.rend(); ++it)
+				if (it->input == input)
+				{
+					if (it->out_start + it->len == out_start && it->src_start + it->len == src_start) { it->len += len; return; }
+					break;
+				}
+			segs.push_back({input, out_start, src_start, len});
+		}
+
+		void add_run(Frame_runs& runs, int64_t len)
+		{
+			if (!runs.empty() && runs.back().first == len) runs.back().second++;
+			else runs.emplace_back(len, 1);
+		}
+	}
+
+	void Audio_bimix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		auto in_l = require_input(input, "input_l", "Audio bimix");
+		auto in_r = require_input(input, "input_r", "Audio bimix");
+		check_channels(*in_l, "Audio bimix");
+		check_channels(*in_r, "Audio bimix");
+
+		// the reference loop, counts only (audio-bimix.cpp:137-329), including its two slips: with both
+		// sides present nb ends up 1152 (:178-183), and the right-hand flush count lands in the left
+		// counter (:294, App. C5)
+		Frame_cursor cl(in_l->runs), cr(in_r->runs);
+		Swr_state sl{resampler_for(in_l->sample_rate)}, sr{resampler_for(in_r->sample_rate)};
+		std::vector<Segment> segs;
+		Frame_runs out_runs;
+		int64_t written = 0, max_frame = 1152;
+		for (const auto& [len, c] : in_l->runs) max_frame = std::max(max_frame, len);
+		for (const auto& [len, c] : in_r->runs) max_frame = std::max(max_frame, len);
+		for (;;)
+		{
+			const bool has_l = cl.has(), has_r = cr.has();
+			int64_t nb = 0;
+			if (has_r && has_l) nb = std::min(cr.size(), cl.size());
+			if (!has_r && has_l) nb = cl.size();
+			else if (has_r && !has_l) nb = cr.size();
+			else nb = 1152;
+			nb = std::min(nb, max_frame);
+			int64_t count_l = 0, count_r = 0;
+			if (has_l) { const int64_t n = cl.size(); cl.next(); const int64_t at = sl.produced; count_l = sl.feed(n, nb); add_segment(segs, 0, written, at, count_l); }
+			else { const int64_t at = sl.produced; count_l = sl.flush(nb); add_segment(segs, 0, written, at, count_l); }
+			if (has_r) { const int64_t n = cr.size(); cr.next(); const int64_t at = sr.produced; count_r = sr.feed(n, nb); add_segment(segs, 1, written, at, count_r); }
+			else { const int64_t at = sr.produced; const int64_t got = sr.flush(nb); add_segment(segs, 1, written, at, got); count_l = got; }
+			add_run(out_runs, nb);
+			written += nb;
+			if (count_r == 0 && count_l == 0) break;
+		}
+		const int64_t total = written;
+		Resampled rl = resample_input(*in_l, sl.produced, sl.flushed, "Audio bimix");
+		Resampled rr = resample_input(*in_r, sr.produced, sr.flushed, "Audio bimix");
+		int64_t len_l = 0, len_r = 0;
+		if (!single_front_segment(segs, 0, &len_l)) { rl = scatter(rl, segs, 0, total, "Audio bimix"); len_l = total; }
+		if (!single_front_segment(segs, 1, &len_r)) { rr = scatter(rr, segs, 1, total, "Audio bimix"); len_r = total; }
+
+		const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+		auto block = std::make_shared<infra::Device_block>(2 * plane);
+		float* out_l = (float*)block->ptr;
+		float* out_r = (float*)((char*)block->ptr + plane);
+		if (total > 0) abi(nodey_bimix(out_l, out_r, rl.l, rl.r, len_l, rr.l, rr.r, len_r, bias, total, cur_stream()), "Audio bimix");
+		const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;     // App. C3: starts at 0, C4: end time
+		publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), pts));
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_bimix_v2  (audio-bimix.cpp:475-877)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_bimix_v2::get_processor_info()
+	{
+		return {.identifier = "audio_bimix_v2", .display_name = "Audio Bimix V2", .singleton = false, .generate = std::make_unique<Audio_bimix_v2>,
+				.description = "Stereo merge with time alignment: both inputs are converted to 48 kHz, folded to mono and placed on the left / "
+							   "right channel according to their timestamps; gaps are filled with silence. Output: float interleaved."};
+	}
+	std::vector<Processor::Pin_attribute> Audio_bimix_v2::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Input L", true), Pin_type::audio("input_r", "Input R", true)};
+	}
+
+	void Audio_bimix_v2::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		std::shared_ptr<const Audio_buffer> in[2] = {require_input(input, "input_l", "Audio bimix v2"), require_input(input, "input_r", "Audio bimix v2")};
+		check_channels(*in[0], "Audio bimix v2");
+		check_channels(*in[1], "Audio bimix v2");
+
+		// per side: list of resampled frames {source offset, length, END time of the block (App. C12)}
+		struct Piece { int64_t src, n; double t; };
+		struct Side { std::vector<Piece> list; size_t head = 0; Frame_cursor cur; Swr_state swr; double time; bool eof = false;
+					  bool empty() const { return head >= list.size(); } Piece& front() { return list[head]; } void pop() { head++; } };
+		Side side[2] = {{{}, 0, Frame_cursor(in[0]->runs), Swr_state{resampler_for(in[0]->sample_rate)}, in[0]->pts_seconds},
+						{{}, 0, Frame_cursor(in[1]->runs), Swr_state{resampler_for(in[1]->sample_rate)}, in[1]->pts_seconds}};
+		struct Out_seg { int64_t out_start, len, l, r; };
+		std::vector<Out_seg> segs;
+		Frame_runs out_runs;
+		int64_t written = 0;
+		bool have_pts = false;
+		double pts0 = 0;
+		const auto emit = [&](int64_t frames, int64_t l_src, int64_t r_src, double t) {
+			if (!have_pts) { have_pts = true; pts0 = t; }
+			if (frames <= 0) { return; }
+			if (!segs.empty())
+			{
+				Out_seg& b = segs.back();
+				const bool l_ok = (b.l < 0 && l_src < 0) || (b.l >= 0 && l_src == b.l + b.len);
+				const bool r_ok = (b.r < 0 && r_src < 0) || (b.r >= 0 && r_src == b.r + b.len);
+				if (l_ok && r_ok) { b.len += frames; written += frames; add_run(out_runs, frames); return; }
+			}
+			segs.push_back({written, frames, l_src, r_src});
+			written += frames;
+			add_run(out_runs, frames);
+		};
+		const auto feed = [&](Side& s) {
+			const int64_t n = s.cur.size();
+			s.cur.next();
+			const int64_t at = s.swr.produced;
+			const int64_t got = s.swr.feed(n, 2 * n);       // swr_convert(out 2n, in n), never flushed
+			s.time += (double)got / 48000;
+			s.list.push_back({at, got, s.time});
+		};
+		const auto drop = [](Piece& p, int64_t count) { p.src += count; p.n -= count; p.t += (double)count / 48000; };
+
+		for (;;)
+		{
+			for (Side& s : side)
+				if (!s.eof) { if (s.cur.has()) feed(s); else s.eof = true; }
+			Side &L = side[0], &R = side[1];
+			if (L.empty() && R.empty() && L.eof && R.eof) break;
+			if (R.empty() && R.eof) { if (L.empty()) continue; const Piece f = L.front(); emit(f.n, f.src, -1, f.t); L.pop(); continue; }
+			if (L.empty() && L.eof) { if (R.empty()) continue; const Piece f = R.front(); emit(f.n, -1, f.src, f.t); R.pop(); continue; }
+			while (!L.empty() && !R.empty())
+			{
+				const bool left_earlier = L.front().t < R.front().t;
+				Side& es = left_earlier ? L : R;
+				Side& ls = left_earlier ? R : L;
+				const double eb = es.front().t, lb = ls.front().t;
+				const double ee = eb + (double)es.front().n / 48000, le = lb + (double)ls.front().n / 48000;
+				const auto lr = [&](int64_t e_src, int64_t l_src, int64_t* l_out, int64_t* r_out) {
+					*l_out = left_earlier ? e_src : l_src; *r_out = left_earlier ? l_src : e_src; };
+				if (ee <= lb)
+				{
+					int64_t a, b; lr(es.front().src, -1, &a, &b);
+					emit(es.front().n, a, b, eb);
+					es.pop();
+					continue;
+				}
+				const double fe = ee < le ? ee : le;
+				const int64_t un = (int64_t)std::round((lb - eb) * 48000);
+				int64_t al = (int64_t)std::round((fe - lb) * 48000);
+				{ const uint64_t room = (uint64_t)es.front().n - (uint64_t)un; if ((uint64_t)al > room) al = (int64_t)room; }
+				if (al > ls.front().n) al = ls.front().n;
+				const int64_t e_src = es.front().src, l_src = ls.front().src;
+				if (ee <= le) { es.pop(); drop(ls.front(), al); }
+				else { ls.pop(); drop(es.front(), un + al); }
+				if (!es.empty() && es.front().n == 0) es.pop();
+				if (!ls.empty() && ls.front().n == 0) ls.pop();
+				// one emitted block of un + al frames: earlier side alone, then both
+				if (!have_pts) { have_pts = true; pts0 = eb; }
+				{
+					int64_t a, b;
+					const size_t before = out_runs.size(); (void)before;
+					lr(e_src, -1, &a, &b);
+					Frame_runs scratch;
+					std::swap(scratch, out_runs);              // both parts belong to ONE reference frame
+					emit(un, a, b, eb);
+					lr(e_src + un, l_src, &a, &b);
+					emit(al, a, b, eb);
+					std::swap(scratch, out_runs);
+					add_run(out_runs, un + al);
+				}
+			}
+		}
+
+		// device work: swr (no flush) + mono fold per side, then one gather into the interleaved output
+		float* mono[2] = {nullptr, nullptr};
+		std::shared_ptr<infra::Device_block> mono_block[2];
+		for (int s = 0; s < 2; s++)
+		{
+			const int64_t n = side[s].swr.produced;
+			Resampled rs = resample_input(*in[s], n, false, "Audio bimix v2");
+			mono_block[s] = std::make_shared<infra::Device_block>((size_t)std::max<int64_t>(n, 1) * sizeof(float));
+			mono[s] = (float*)mono_block[s]->ptr;
+			if (n > 0) abi(nodey_downmix_half(mono[s], rs.l, rs.r, n, cur_stream()), "Audio bimix v2");
+		}
+		auto block = std::make_shared<infra::Device_block>((size_t)std::max<int64_t>(written, 1) * 2 * sizeof(float));
+		if (!segs.empty())
+		{
+			std::vector<int64_t> o, n, l, r;
+			for (const Out_seg& s : segs) { o.push_back(s.out_start); n.push_back(s.len); l.push_back(s.l); r.push_back(s.r); }
+			abi(nodey_merge_segments((float*)block->ptr, mono[0], mono[1], o.data(), n.data(), l.data(), r.data(), (int)segs.size(), cur_stream()),
+				"Audio bimix v2");
+		}
+		publish(output, "output", new_buffer(block, block->ptr, nullptr, FMT_FLT, 48000, 2, written, std::move(out_runs), pts0));
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_channel_split (new)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_channel_split::get_processor_info()
+	{
+		return {.identifier = "audio_channel_split", .display_name = "Channel Split", .singleton = false,
+				.generate = std::make_unique<Audio_channel_split>,
+				.description = "Routes the left and right channel of a stereo stream to two mono streams of the same sample type (bit exact)."};
+	}
+	std::vector<Processor::Pin_attribute> Audio_channel_split::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output_l", "Left", false), Pin_type::audio("output_r", "Right", false), Pin_type::audio("input", "Input", true)};
+	}
+	void Audio_channel_split::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		auto in = require_input(input, "input", "Channel split");
+		check_channels(*in, "Channel split");
+		if (in->channels != 2)
+			throw Runtime_error("Channel split needs a stereo stream", "The input of the channel split node has one channel only.",
+								std::format("channels: {}", in->channels));
+		const size_t bytes = (size_t)in->frames * (size_t)format_bytes(in->format);
+		Arena arena(2 * Arena::padded(bytes));
+		void* l = arena.take(bytes);
+		void* r = arena.take(bytes);
+		if (in->frames > 0) abi(nodey_split(l, r, in->plane[0], in->plane[1], in->format, in->frames, cur_stream()), "Channel split");
+		auto ev = std::make_shared<infra::Device_event>();
+		ev->record(cur_stream());
+		auto bl = new_buffer(arena.block, l, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds);
+		auto br = new_buffer(arena.block, r, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds);
+		bl->ready = ev; br->ready = ev;
+		publish(output, "output_l", bl);
+		publish(output, "output_r", br);
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// audio_spectrum (new)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Audio_spectrum::get_processor_info()
+	{
+		return {.identifier = "audio_spectrum", .display_name = "Spectrum", .singleton = false, .generate = std::make_unique<Audio_spectrum>,
+				.description = "Short-time Fourier transform per channel: 4096-point periodic Hann window, hop 1024, unnormalised forward DFT "
+							   "(FFTW r2c convention), 2049 complex bins per frame."};
+	}
+	std::vector<Processor::Pin_attribute> Audio_spectrum::get_pin_attributes() const
+	{
+		return {Processor::Pin_attribute{.identifier = "output", .display_name = "Spectrum", .type = typeid(Spectrum_stream), .is_input = false,
+										 .generate_func = [] { return std::make_shared<Spectrum_stream>(); }},
+				Pin_type::audio("input", "Input", true)};
+	}
+	Json::Value Audio_spectrum::serialize() const
+	{
+		Json::Value value;
+		value["fft_size"] = fft_size;
+		value["hop"] = hop;
+		value["window"] = window;
+		return value;
+	}
+	void Audio_spectrum::deserialize(const Json::Value& value)
+	{
+		if (value.isMember("fft_size") && value["fft_size"].isInt()) fft_size = value["fft_size"].asInt();
+		if (value.isMember("hop") && value["hop"].isInt()) hop = value["hop"].asInt();
+		if (value.isMember("window") && value["window"].isString()) window = value["window"].asString();
+	}
+	void Audio_spectrum::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		auto in = require_input(input, "input", "Spectrum");
+		check_channels(*in, "Spectrum");
+		if (window != "hann")
+			throw Runtime_error("Unsupported window", "The spectrum node implements the periodic Hann window only.", window);
+		const float* x = (const float*)in->plane[0];
+		int interleaved = in->format == FMT_FLT ? 1 : 0;
+		int64_t plane_stride = in->format == FMT_FLTP && in->channels == 2 ? (const float*)in->plane[1] - (const float*)in->plane[0] : 0;
+		std::unique_ptr<infra::Device_block> converted;
+		if (in->format != FMT_FLT && !(in->format == FMT_FLTP && (in->channels == 1 || plane_stride > 0)))
+		{
+			converted = std::make_unique<infra::Device_block>((size_t)std::max<int64_t>(in->frames, 1) * (size_t)in->channels * sizeof(float));
+			abi(nodey_extract_interleaved((float*)converted->ptr, in->plane[0], in->plane[1], in->format, in->frames, in->channels, cur_stream()), "Spectrum");
+			x = (const float*)converted->ptr;
+			interleaved = 1;
+			plane_stride = 0;
+		}
+		const int64_t m = nodey_stft_frames(in->frames, fft_size, hop);
+		auto spec = std::make_shared<Spectrum_buffer>();
+		spec->channels = in->channels; spec->fft_size = fft_size; spec->hop = hop; spec->sample_rate = in->sample_rate; spec->frames = m;
+		spec->block = std::make_shared<infra::Device_block>((size_t)std::max<int64_t>(m, 1) * (size_t)in->channels * (size_t)(fft_size / 2 + 1) * 2 * sizeof(float));
+		spec->data = (float*)spec->block->ptr;
+		abi(nodey_stft(spec->data, x, in->frames, in->channels, interleaved, plane_stride, fft_size, hop, cur_stream()), "Spectrum");
+		spec->ready = std::make_shared<infra::Device_event>();
+		spec->ready->record(cur_stream());
+		{
+			std::lock_guard lock(result_mutex);
+			result = spec;
+		}
+		if (const auto find = output.find("output"); find != output.end())
+			for (auto& item : find->second) std::dynamic_pointer_cast<Spectrum_stream>(item)->publish(spec);
+	}
+}
+
+namespace infra
+{
+	// reference: src/register.cpp:14-23 (eight nodes) + the two new ones
+	void register_all_processors()
+	{
+		static std::once_flag once;
+		std::call_once(once, [] {
+			Processor::register_processor<processor::Audio_input>();
+			Processor::register_processor<processor::Audio_output>();
+			Processor::register_processor<processor::Audio_vol>();
+			Processor::register_processor<processor::Velocity_modifier>();
+			Processor::register_processor<processor::Pitch_modifier>();
+			Processor::register_processor<processor::Audio_amix>();
+			Processor::register_processor<processor::Audio_bimix>();
+			Processor::register_processor<processor::Audio_bimix_v2>();
+			Processor::register_processor<processor::Audio_channel_split>();
+			Processor::register_processor<processor::Audio_spectrum>();
+		});
+	}
+}

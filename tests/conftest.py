@@ -21,6 +21,14 @@ def orc():
 
 
 @pytest.fixture(scope="session")
+def eng_gpu(nd):
+    """the C++ host layer (Processor API, Graph, Runner) through its C facade"""
+    import engine
+    engine.lib()
+    return engine
+
+
+@pytest.fixture(scope="session")
 def nd():
     """The CUDA library binding; a GPU test without the library or a device is an error, not a skip."""
     import torch

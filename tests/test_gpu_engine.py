@@ -1,0 +1,148 @@
+"""GPU parity through the reference-facing plugin API: project JSON -> Graph::deserialize ->
+Runner::create_and_run -> processor nodes -> C ABI kernels, against the same graphs composed from
+oracle nodes.  Integer/routing and all single-GPU float paths are compared bit for bit."""
+import numpy as np
+import pytest
+
+from helpers import FMT_FLT, FMT_FLTP, FMT_S16, FMT_S16P, assert_bit_equal, make_input
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_gain_amix(eng_gpu, orc):
+    """configs[0] (reference-only nodes): input -> fan-out to two gains -> amix(2) -> output, S16 source"""
+    n = 44100 * 2 + 321
+    x = make_input(orc, FMT_S16, n, 2)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    g0 = p.add("audio_volume_adjust"); g1 = p.add("audio_volume_adjust")
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.5]))
+    out = p.add("audio_output")
+    p.link(src, "output_0", g0, "input"); p.link(src, "output_0", g1, "input")
+    p.link(g0, "output", mix, "input_1"); p.link(g1, "output", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_volume(g0, 0.8); e.set_volume(g1, 0.5)
+    e.bind_source(0, x, FMT_S16, 44100)
+    e.run()
+    a = orc.gain(x, FMT_S16, 0.8); b = orc.gain(x, FMT_S16, 0.5)
+    assert_bit_equal(e.product(g0, "output").numpy(), a, "gain product")
+    rl, rr = orc.amix([orc.make_track(a, FMT_S16, 44100), orc.make_track(b, FMT_S16, 44100)], [0.5, 0.5])
+    got = e.output()
+    assert (got.fmt, got.rate, got.ch) == (FMT_FLTP, 48000, 2)
+    assert_bit_equal(got.numpy(), np.stack([rl, rr]), "amix output")
+
+
+@pytest.mark.parametrize("rates", [(44100, 44100), (48000, 22050), (96000, 44100)])
+def test_amix_mixed_rates_and_gaps(eng_gpu, orc, rates):
+    """per-input resampling incl. an input above 48 kHz, whose frames leave gaps (reference behaviour)"""
+    xs = [make_input(orc, FMT_FLT, 20000 + 777 * i, 2, rate=r, track=i) for i, r in enumerate(rates)]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.7, 0.3]))
+    out = p.add("audio_output")
+    p.link(src, "output_0", mix, "input_1"); p.link(src, "output_1", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    for i, (x, r) in enumerate(zip(xs, rates)):
+        e.bind_source(i, x, FMT_FLT, r)
+    e.run()
+    rl, rr = orc.amix([orc.make_track(x, FMT_FLT, r) for x, r in zip(xs, rates)], [0.7, 0.3])
+    assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), f"amix {rates}")
+
+
+@pytest.mark.parametrize("bias", [0.0, -0.4])
+def test_bimix(eng_gpu, orc, bias):
+    xl = make_input(orc, FMT_FLT, 30000, 2, track=1); xr = make_input(orc, FMT_S16, 26000, 1, track=2)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    bm = p.add("audio_bimix", {"bias": bias})
+    out = p.add("audio_output")
+    p.link(src, "output_0", bm, "input_l"); p.link(src, "output_1", bm, "input_r"); p.link(bm, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.bind_source(0, xl, FMT_FLT, 44100); e.bind_source(1, xr, FMT_S16, 44100)
+    e.run()
+    rl, rr = orc.bimix(orc.make_track(xl, FMT_FLT, 44100), orc.make_track(xr, FMT_S16, 44100), bias)
+    assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "bimix")
+
+
+@pytest.mark.parametrize("pts", [(0.0, 0.0), (0.0, 0.25), (0.1, 0.0)])
+def test_bimix_v2_alignment(eng_gpu, orc, pts):
+    xl = make_input(orc, FMT_FLT, 40000, 2, track=3); xr = make_input(orc, FMT_FLT, 36000, 2, track=4)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    bm = p.add("audio_bimix_v2")
+    out = p.add("audio_output")
+    p.link(src, "output_0", bm, "input_l"); p.link(src, "output_1", bm, "input_r"); p.link(bm, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.bind_source(0, xl, FMT_FLT, 44100, pts=pts[0]); e.bind_source(1, xr, FMT_FLT, 44100, pts=pts[1])
+    e.run()
+    ref, ref_pts = orc.bimix_v2(orc.make_track(xl, FMT_FLT, 44100, pts0=pts[0]), orc.make_track(xr, FMT_FLT, 44100, pts0=pts[1]))
+    got = e.output()
+    assert (got.fmt, got.ch) == (FMT_FLT, 2)
+    assert_bit_equal(got.numpy(), ref, f"bimix_v2 {pts}")
+    assert got.pts == ref_pts
+
+
+def test_split_gain_merge_variant(eng_gpu, orc):
+    """configs[0], new-node variant: channel_split -> per-channel gain -> bimix_v2 merge"""
+    n = 48000
+    x = make_input(orc, FMT_S16, n, 2, rate=48000)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    sp = p.add("audio_channel_split")
+    g0 = p.add("audio_volume_adjust"); g1 = p.add("audio_volume_adjust")
+    bm = p.add("audio_bimix_v2")
+    out = p.add("audio_output")
+    p.link(src, "output_0", sp, "input")
+    p.link(sp, "output_l", g0, "input"); p.link(sp, "output_r", g1, "input")
+    p.link(g0, "output", bm, "input_l"); p.link(g1, "output", bm, "input_r"); p.link(bm, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_volume(g0, 0.8); e.set_volume(g1, 0.5)
+    e.bind_source(0, x, FMT_S16, 48000)
+    e.run()
+    l, r = orc.split(x, FMT_S16)
+    assert_bit_equal(e.product(sp, "output_l").numpy()[:, 0], l, "split L")
+    gl = orc.gain(l.reshape(-1, 1), FMT_S16, 0.8); gr = orc.gain(r.reshape(-1, 1), FMT_S16, 0.5)
+    ref, _ = orc.bimix_v2(orc.make_track(gl, FMT_S16, 48000), orc.make_track(gr, FMT_S16, 48000))
+    assert_bit_equal(e.output().numpy(), ref, "split/gain/merge")
+
+
+def test_config5_graph_through_engine(eng_gpu, orc):
+    """configs[4] at small size, driven by project JSON: 32 tracks, device-resident sources"""
+    from oracle import graph_oracle as G
+    n = 44100 * 2 + 99
+    tracks = [orc.synth_f32(n, 2, 44100, t) for t in range(32)]
+    gains = [G.track_gain(t) for t in range(32)]
+    p, ids = eng_gpu.config5_project(32, gains)
+    e = eng_gpu.Engine(p.json())
+    for t, x in enumerate(tracks):
+        e.bind_source(t, x, FMT_FLT, 44100)
+    e.run()
+    ref_bus, ref_spec = G.render(tracks, threads=8)
+    assert_bit_equal(e.output().numpy(), ref_bus, "master bus")
+    spec = e.product(ids["spectrum"], "output").numpy()
+    peak = np.abs(ref_spec).max(axis=-1, keepdims=True)
+    assert (np.abs(spec - ref_spec) <= 1e-5 * np.maximum(peak, 1e-30)).all()
+    # level-batched runner: 32 pitch nodes -> one batched SoundTouch launch set, not 32
+    assert e.product_runs(ids["master"], "output")[0][0] == 1152
+
+
+def test_node_errors_surface(eng_gpu, orc):
+    p = eng_gpu.Project()
+    g = p.add("audio_volume_adjust")
+    out = p.add("audio_output")
+    p.link(g, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    with pytest.raises(eng_gpu.EngineError) as x:
+        e.run()
+    assert x.value.code == eng_gpu.E_NODE and "has no input" in x.value.message
+    # SoundTouch nodes refuse rates outside 8..48 kHz (audio-velocity.cpp:371)
+    q = eng_gpu.Project()
+    src = q.add("audio_input", {"file_path": [""]})
+    pm = q.add("pitch_modifier", {"pitch": 2.0})
+    o = q.add("audio_output")
+    q.link(src, "output_0", pm, "input"); q.link(pm, "output", o, "input")
+    e2 = eng_gpu.Engine(q.json())
+    e2.bind_source(0, make_input(orc, FMT_FLT, 5000, 2, rate=96000), FMT_FLT, 96000)
+    with pytest.raises(eng_gpu.EngineError) as x:
+        e2.run()
+    assert "Unsupported sample rate" in x.value.message

@@ -1,0 +1,148 @@
+"""CPU: the C++ host layer's graph model and project JSON (reference: src/infra/graph.cpp) through the
+C facade -- registration, pins, (de)serialisation round trip, validation errors, graph levels.
+No kernel is launched (engines are created and inspected, never run)."""
+import json
+
+import pytest
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import engine
+    engine.lib()
+    return engine
+
+
+def simple_project(eng, n_inputs=2):
+    p = eng.Project()
+    src = p.add("audio_input", {"file_path": ["a.wav", "b.wav"]})
+    g0 = p.add("audio_volume_adjust")
+    g1 = p.add("audio_volume_adjust")
+    mix = p.add("audio_amix", eng.amix_info([0.5] * n_inputs))
+    out = p.add("audio_output")
+    p.link(src, "output_0", g0, "input")
+    p.link(src, "output_1", g1, "input")
+    p.link(g0, "output", mix, "input_1")
+    p.link(g1, "output", mix, "input_2")
+    p.link(mix, "output", out, "input")
+    return p
+
+
+def test_project_round_trip(eng):
+    p = simple_project(eng)
+    e = eng.Engine(p.json())
+    text = e.serialize()
+    again = json.loads(text)
+    assert sorted(again["nodes"]) == ["0", "1", "2", "3", "4"]
+    assert again["nodes"]["0"] == {"identifier": "audio_input", "info": {"file_path": ["a.wav", "b.wav"]}, "position": {"x": 0.0, "y": 0.0}}
+    assert again["nodes"]["1"]["info"] is None                   # gain is not serialised (App. C1)
+    assert again["nodes"]["3"]["info"] == {"input_num": 2, "volumes0": 0.5, "locks0": False, "volumes1": 0.5, "locks1": False}
+    assert {json.dumps(l, sort_keys=True) for l in again["links"]} == {json.dumps(l, sort_keys=True) for l in p.json()["links"]}
+    e2 = eng.Engine(text)
+    assert json.loads(e2.serialize()) == again
+    assert text.startswith("{\n  \"links\"")                      # 2-space indent, keys in order
+
+
+def test_nodes_levels_and_identifiers(eng):
+    e = eng.Engine(simple_project(eng).json())
+    e.check()
+    assert e.nodes() == [(0, "audio_input", 0), (1, "audio_volume_adjust", 1), (2, "audio_volume_adjust", 1),
+                         (3, "audio_amix", 2), (4, "audio_output", 3)]
+
+
+@pytest.mark.parametrize("ident", ["audio_input", "audio_output", "audio_volume_adjust", "velocity_modifier", "pitch_modifier",
+                                   "audio_amix", "audio_bimix", "audio_bimix_v2", "audio_channel_split", "audio_spectrum"])
+def test_every_identifier_is_registered(eng, ident):
+    p = eng.Project()
+    info = {"audio_input": {"file_path": [""]}, "audio_amix": eng.amix_info([1.0]), "audio_bimix": {"bias": 0.0}}.get(ident)
+    p.add(ident, info)
+    e = eng.Engine(p.json())
+    assert e.nodes()[0][1] == ident
+
+
+def test_invalid_files(eng):
+    def err(doc):
+        with pytest.raises(eng.EngineError) as x:
+            eng.Engine(doc if isinstance(doc, str) else json.dumps(doc))
+        return x.value
+    assert err("{ not json").code == eng.E_FILE
+    assert err([1, 2]).code == eng.E_FILE
+    assert err({"nodes": [], "links": []}).code == eng.E_FILE
+    assert err({"nodes": {}, "links": {}}).code == eng.E_FILE
+    assert "Unknown processor identifier" in err({"nodes": {"0": {"identifier": "nope", "info": None}}, "links": []}).message
+    assert "Invalid node ID" in err({"nodes": {"1x": {"identifier": "audio_output", "info": None}}, "links": []}).message
+    two = {"nodes": {"0": {"identifier": "audio_output", "info": None}, "1": {"identifier": "audio_output", "info": None}}, "links": []}
+    assert "Duplicating singleton" in err(two).message
+    p = simple_project(eng).json()
+    p["links"].append({"from": {"node": 9, "pin": "output"}, "to": {"node": 4, "pin": "input"}})
+    assert "non-existent node" in err(p).message
+    p = simple_project(eng).json()
+    p["links"][0]["to"]["pin"] = "nope"
+    assert "non-existent pin" in err(p).message
+    assert "Wrong field: input_num" in err({"nodes": {"0": {"identifier": "audio_amix", "info": {}}}, "links": []}).message
+    assert "Wrong field: bias" in err({"nodes": {"0": {"identifier": "audio_bimix", "info": {"bias": "x"}}}, "links": []}).message
+    assert "Wrong field: file_path" in err({"nodes": {"0": {"identifier": "audio_input", "info": {}}}, "links": []}).message
+
+
+def test_multiple_input_and_type_mismatch(eng):
+    p = simple_project(eng).json()
+    p["links"].append({"from": {"node": 2, "pin": "output"}, "to": {"node": 3, "pin": "input_1"}})   # second link into input_1
+    # like the reference, add_link() only refuses a link when the pin ALREADY has two (graph.hpp:173-183
+    # counts the existing links); the doubled input is caught by check_graph()
+    e = eng.Engine(p)
+    with pytest.raises(eng.EngineError) as x:
+        e.check()
+    assert x.value.code == eng.E_GRAPH and "Multiple Inputs" in x.value.message
+    q = eng.Project()
+    s = q.add("audio_spectrum", {"fft_size": 4096, "hop": 1024, "window": "hann"})
+    o = q.add("audio_output")
+    q.link(s, "output", o, "input")        # spectrum product into an audio pin
+    with pytest.raises(eng.EngineError) as x:
+        eng.Engine(q.json())
+    assert x.value.code == eng.E_GRAPH and "Mismatch Pin" in x.value.message
+
+
+def test_loop_detection(eng):
+    p = eng.Project()
+    a = p.add("audio_volume_adjust")
+    b = p.add("audio_volume_adjust")
+    p.link(a, "output", b, "input")
+    p.link(b, "output", a, "input")
+    e = eng.Engine(p.json())
+    with pytest.raises(eng.EngineError) as x:
+        e.check()
+    assert "Loop Detected" in x.value.message
+    # a loop hanging off a valid source
+    q = eng.Project()
+    s = q.add("audio_input", {"file_path": [""]})
+    m = q.add("audio_amix", eng.amix_info([1.0, 1.0]))
+    g = q.add("audio_volume_adjust")
+    q.link(s, "output_0", m, "input_1")
+    q.link(m, "output", g, "input")
+    q.link(g, "output", m, "input_2")
+    with pytest.raises(eng.EngineError):
+        eng.Engine(q.json()).check()
+
+
+def test_amix_pins_follow_input_num(eng):
+    p = eng.Project()
+    m = p.add("audio_amix", eng.amix_info([1.0] * 16))
+    g = p.add("audio_volume_adjust")
+    p.link(g, "output", m, "input_16")
+    eng.Engine(p.json())
+    p2 = eng.Project()
+    m = p2.add("audio_amix", eng.amix_info([1.0] * 3))
+    g = p2.add("audio_volume_adjust")
+    p2.link(g, "output", m, "input_4")
+    with pytest.raises(eng.EngineError):
+        eng.Engine(p2.json())
+
+
+def test_config5_project_shape(eng):
+    p, ids = eng.config5_project(32, [1.0] * 32)
+    e = eng.Engine(p.json())
+    e.check()
+    nodes = e.nodes()
+    assert len(nodes) == 1 + 32 * 4 + 2 + 1 + 1 + 1
+    levels = {nid: lvl for nid, _, lvl in nodes}
+    assert levels[ids["input"]] == 0 and levels[ids["master"]] == 6 and levels[ids["output"]] == 7
