@@ -39,7 +39,6 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=TRACKS, help="total tracks (development only; the contract is 256)")
     ap.add_argument("--seconds", type=int, default=SECONDS, help="track length (development only; the contract is 180)")
-    ap.add_argument("--sub-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -166,46 +165,73 @@ def kernel_algo_bytes(name, r, batch):
 
 
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import nodey
+    import engine
     import pipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    nodey.lib()   # fails loudly when the CUDA library is missing: there is no fallback path
+    L = nodey.lib()        # fails loudly when the CUDA library is missing: there is no fallback path
+    engine.lib()
+    nodey.check(L.nodey_set_device(local))
 
     n_in = IN_RATE * args.seconds
     first, t_local = pipeline.shard_tracks(args.tracks, world, rank)
-    sub = min(args.sub_batch, t_local)
-    r = pipeline.Config5Renderer(n_in, sub_batch=sub, device=dev)
+    plan = pipeline.Config5Renderer(n_in, sub_batch=16, device=dev)      # host-side lengths only (roofline bookkeeping)
+    gains = [pipeline.track_gain(first + t) for t in range(t_local)]
+    # the render is driven through the reference-facing plugin API: project JSON -> Graph -> Runner -> nodes
+    project, ids = engine.config5_project(t_local, gains, spectrum=(world == 1))
+    eng = engine.Engine(project.json())
 
     # synthetic sources, generated on the device by the same generator the oracle uses
     x_dev = torch.empty((t_local, n_in, 2), dtype=torch.float32, device=dev)
     for t in range(t_local):
-        nodey.check(nodey.lib().nodey_synth(nodey._dp(x_dev[t]), None, n_in, 2, IN_RATE, first + t, 0, nodey._stream()))
+        nodey.check(L.nodey_synth(nodey._dp(x_dev[t]), None, n_in, 2, IN_RATE, first + t, 0, None))
     torch.cuda.synchronize()
 
-    total3 = [None]
+    bus_t = [None]
 
-    def reduce_and_spectrum(bus):
+    def finish(want_host=None):
+        """after eng.run(): reduce the partial buses (N > 1), spectrum on rank 0, optional D2H"""
+        out = eng.output()
         if world > 1:
-            dist.reduce(bus, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            return r.spectrum(bus)
-        return None
+            if bus_t[0] is None:
+                bus_t[0] = torch.empty((2, out.frames), dtype=torch.float32, device=dev)
+            nodey.check(L.nodey_memcpy_d2d(nodey._dp(bus_t[0][0]), C.c_void_p(out.p0), out.frames * 4, None))
+            nodey.check(L.nodey_memcpy_d2d(nodey._dp(bus_t[0][1]), C.c_void_p(out.p1), out.frames * 4, None))
+            dist.reduce(bus_t[0], dst=0, op=dist.ReduceOp.SUM)
+            spec_ptr, spec_elems = None, 0
+            if rank == 0:
+                spec = nodey.stft(bus_t[0], False)
+                spec_ptr, spec_elems = spec.data_ptr(), spec.numel()
+                bus_t.append(spec)     # keep alive
+            p0, p1 = bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr()
+        else:
+            sp = eng.product(ids["spectrum"], "output")
+            spec_ptr, spec_elems = sp.p0, sp.ch * sp.frames * sp.bins
+            p0, p1 = out.p0, out.p1
+        if want_host is not None and rank == 0:
+            hb, hs = want_host(out.frames, spec_elems)
+            nodey.check(L.nodey_memcpy_d2h(nodey._dp(hb[0]), C.c_void_p(p0), out.frames * 4, None))
+            nodey.check(L.nodey_memcpy_d2h(nodey._dp(hb[1]), C.c_void_p(p1), out.frames * 4, None))
+            nodey.check(L.nodey_memcpy_d2h(nodey._dp(hs), C.c_void_p(spec_ptr), spec_elems * 8, None))
+        return out.frames, spec_elems
+
+    def bind(sources):
+        for t in range(t_local):
+            eng.bind_source(t, sources[t], nodey.FMT_FLT, IN_RATE)
 
     def step_device():
-        bus = r.render(x_dev, first_track=first)
-        spec = reduce_and_spectrum(bus)
-        return bus, spec
+        eng.run()
+        finish()
 
     def timed(fn, steps):
         if world > 1:
@@ -223,6 +249,7 @@ def run_ours(args):
             dist.barrier()
         return float(ms.item())
 
+    bind(x_dev)
     for _ in range(max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local)
@@ -248,10 +275,10 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        top = max(rep.items(), key=lambda kv: kv[1]["ms"])
-        name, st = top
+        name, st = max(rep.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = st["ms"] / st["launches"]
-        ab = kernel_algo_bytes(name, r, sub)
+        st_batch = min(128, t_local)                     # tracks per SoundTouch launch (host/src/nodes.cpp)
+        ab = kernel_algo_bytes(name, plan, st_batch)
         achieved = (ab / (per_launch_ms * 1e-3) / 1e9) if ab else None
         traffic = None
         try:
@@ -263,9 +290,11 @@ def run_ours(args):
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                     "launch_ms": per_launch_ms, "share_of_step": st["ms"] / step_ms if step_ms else None,
+                    "note": "the dominant kernel is the WSOLA offset search: FP32-issue bound (about 735 rounded FP32 ops per input "
+                            "frame, sequential per track), so its HBM fraction is small by construction; see DESIGN.md 3.1",
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}
 
-    # ---- end to end: pinned host inputs -> H2D -> render -> D2H(bus, spectrum) ----
+    # ---- end to end: pinned host inputs -> H2D (audio_input node) -> render -> D2H(bus, spectrum) ----
     e2e = None
     if not args.no_e2e:
         x_host = torch.empty((t_local, n_in, 2), dtype=torch.float32, pin_memory=True)
@@ -273,50 +302,29 @@ def run_ours(args):
         torch.cuda.synchronize()
         del x_dev
         torch.cuda.empty_cache()
-        stage = [torch.empty((sub, n_in, 2), dtype=torch.float32, device=dev) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-        ev_copied = [torch.cuda.Event() for _ in range(2)]
-        ev_free = [torch.cuda.Event() for _ in range(2)]
-        bus_host = spec_host = None
-        h2d = t_local * n_in * 8
-        d2h = [0]
+        bind(x_host)
+        host_out = {}
+
+        def host_buffers(frames, spec_elems):
+            if "bus" not in host_out:
+                host_out["bus"] = torch.empty((2, frames), dtype=torch.float32, pin_memory=True)
+                host_out["spec"] = torch.empty((spec_elems,), dtype=torch.complex64, pin_memory=True)
+            return host_out["bus"], host_out["spec"]
+
+        sizes = [0, 0]
 
         def step_e2e():
-            nonlocal bus_host, spec_host
-            cur = torch.cuda.current_stream()
-            nsub = t_local // sub
-            buses = []
+            eng.run()
+            f, se = finish(want_host=host_buffers)
+            sizes[0], sizes[1] = f, se
 
-            def issue(s):
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ev_free[s % 2])
-                    stage[s % 2].copy_(x_host[s * sub:(s + 1) * sub], non_blocking=True)
-                    ev_copied[s % 2].record(copy_stream)
-            issue(0)
-            for s in range(nsub):
-                if s + 1 < nsub:
-                    issue(s + 1)
-                cur.wait_event(ev_copied[s % 2])
-                buses += r.render_groups(stage[s % 2], first + s * sub)
-                ev_free[s % 2].record(cur)
-            bus = r.master(buses)
-            spec = reduce_and_spectrum(bus)
-            if rank == 0:
-                if bus_host is None:
-                    bus_host = torch.empty(bus.shape, dtype=bus.dtype, pin_memory=True)
-                    spec_host = torch.empty(spec.shape, dtype=spec.dtype, pin_memory=True)
-                    d2h[0] = bus.numel() * 4 + spec.numel() * 8
-                bus_host.copy_(bus, non_blocking=True)
-                spec_host.copy_(spec, non_blocking=True)
-
-        for e in ev_free:
-            e.record(torch.cuda.current_stream())
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
-        e2e = {"value": audio / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h[0], "ms_per_step": ms_e2e / args.steps,
-               "api": "C ABI (include/nodey_cuda.h) sequenced per reference node, pinned host buffers, H2D overlapped per sub-batch"}
+        e2e = {"value": audio / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": t_local * n_in * 8 * world,
+               "d2h_bytes_per_step": sizes[0] * 8 + sizes[1] * 8, "ms_per_step": ms_e2e / args.steps,
+               "api": "project JSON -> infra::Graph::deserialize -> infra::Runner::create_and_run (libnodey_host.so, "
+                      "include/nodey_engine.h); audio_input uploads the pinned host PCM on its own stream, downstream nodes start per track"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -331,6 +339,7 @@ def run_ours(args):
                "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(out), flush=True)
+    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,8 +49,10 @@ int nodey_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* tota
 
 /* Device runtime behind the ABI (the reference has none: it is a CPU program).  Host layers bind these
  * instead of the CUDA runtime so that the only native dependency is this library.
- * nodey_malloc / nodey_free are stream ordered (cudaMallocAsync / cudaFreeAsync); streams are blocking
- * streams, i.e. ordered against the legacy default stream (NULL). */
+ * nodey_malloc / nodey_free are stream ordered: a block freed on a stream may be handed out again to
+ * that stream at once, to other streams after the free point has been reached (large blocks are
+ * cached by the library, small ones use cudaMallocAsync).  Streams are blocking streams, i.e. ordered
+ * against the legacy default stream (NULL). */
 int nodey_set_device(int ordinal);
 int nodey_get_device(int* ordinal);
 int nodey_device_count(int* count);
@@ -66,6 +68,7 @@ int nodey_event_elapsed_ms(float* ms, nodey_event_t start, nodey_event_t stop);
 int nodey_stream_wait_event(nodey_stream_t s, nodey_event_t e);
 int nodey_malloc(void** out, size_t bytes, nodey_stream_t s);
 int nodey_free(void* p, nodey_stream_t s);
+int nodey_trim_memory(void);   /* return cached blocks to the driver */
 int nodey_memset(void* dst, int value, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_h2d(void* dst, const void* src_host, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_d2h(void* dst_host, const void* src, size_t bytes, nodey_stream_t s);

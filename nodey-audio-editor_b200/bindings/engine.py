@@ -94,8 +94,8 @@ class Engine:
         self._keep = []
 
     def close(self):
-        if getattr(self, "h", None):
-            lib().nodey_engine_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.nodey_engine_destroy(self.h)
             self.h = None
 
     __del__ = close

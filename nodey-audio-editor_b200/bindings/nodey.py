@@ -27,7 +27,7 @@ SYMBOLS = [
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
-    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free",
+    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory",
     "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
 ]
 

@@ -50,6 +50,11 @@ struct LaunchScope {
 // SM count of the current device (cached); grids are sized in multiples of it.
 int sm_count();
 
+// stream-ordered device memory with caching of large blocks (runtime.cu)
+int device_alloc(void** out, size_t bytes, cudaStream_t stream);
+int device_free(void* p, cudaStream_t stream);
+
+
 // grid for a grid-stride streaming kernel: ctas_per_sm resident CTAs on every SM, capped by work
 inline int stream_grid(int64_t work_items, int block, int ctas_per_sm)
 {

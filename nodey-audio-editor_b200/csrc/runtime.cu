@@ -2,6 +2,121 @@
 // reference-side binding) needs nothing but include/nodey_cuda.h: no CUDA headers, no torch.
 #include "nodey_common.cuh"
 
+#include <map>
+#include <mutex>
+#include <vector>
+
+// ---- caching device allocator -----------------------------------------------------------------------
+// A render allocates the same (large) sizes in the same order step after step.  cudaMallocAsync's pool
+// re-maps physical memory when sizes do not line up and stalls the enqueueing thread for hundreds of
+// milliseconds on multi-GB requests, so large blocks are cached here instead: a freed block stays owned
+// by the library, tagged with the stream it was freed on and an event; it is handed out again to the
+// same stream at once (stream order makes that safe) or to another stream once the event has completed.
+// Sizes are rounded up to 2 MiB; blocks are never split.  On out-of-memory every cached block is
+// returned to the driver and the allocation retried.
+namespace nodey {
+
+namespace {
+struct CachedBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; int device; };
+std::mutex g_alloc_mu;
+std::vector<CachedBlock> g_free_blocks;
+std::map<void*, std::pair<size_t, int>> g_live_blocks;     // ptr -> (rounded size, device)
+constexpr size_t kGranule = 2u << 20;
+constexpr size_t kSmall = 1u << 20;                           // below this: cudaMallocAsync (pool handles it well)
+
+void retain_small_pool()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
+void drop_cached_locked(int device)
+{
+    for (size_t i = 0; i < g_free_blocks.size();) {
+        if (g_free_blocks[i].device == device) {
+            cudaEventSynchronize(g_free_blocks[i].event);
+            cudaEventDestroy(g_free_blocks[i].event);
+            cudaFree(g_free_blocks[i].ptr);
+            g_free_blocks[i] = g_free_blocks.back();
+            g_free_blocks.pop_back();
+        } else i++;
+    }
+}
+}  // namespace
+
+int device_alloc(void** out, size_t bytes, cudaStream_t stream)
+{
+    *out = nullptr;
+    if (bytes == 0) return NODEY_OK;
+    if (bytes < kSmall) {
+        retain_small_pool();
+        NODEY_CUDA_OK(cudaMallocAsync(out, bytes, stream));
+        return NODEY_OK;
+    }
+    int dev = 0;
+    NODEY_CUDA_OK(cudaGetDevice(&dev));
+    const size_t want = (bytes + kGranule - 1) / kGranule * kGranule;
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    // best fit among reusable blocks (no more than 12.5 % waste)
+    int best = -1;
+    for (int i = 0; i < (int)g_free_blocks.size(); i++) {
+        const CachedBlock& b = g_free_blocks[(size_t)i];
+        if (b.device != dev || b.bytes < want || b.bytes > want + want / 8) continue;
+        if (b.stream != stream && cudaEventQuery(b.event) != cudaSuccess) continue;
+        if (best < 0 || b.bytes < g_free_blocks[(size_t)best].bytes) best = i;
+    }
+    if (best >= 0) {
+        CachedBlock b = g_free_blocks[(size_t)best];
+        g_free_blocks[(size_t)best] = g_free_blocks.back();
+        g_free_blocks.pop_back();
+        cudaEventDestroy(b.event);
+        g_live_blocks[b.ptr] = {b.bytes, dev};
+        *out = b.ptr;
+        return NODEY_OK;
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        drop_cached_locked(dev);
+        e = cudaMalloc(out, want);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    g_live_blocks[*out] = {want, dev};
+    return NODEY_OK;
+}
+
+int device_free(void* p, cudaStream_t stream)
+{
+    if (!p) return NODEY_OK;
+    {
+        std::lock_guard<std::mutex> lock(g_alloc_mu);
+        const auto it = g_live_blocks.find(p);
+        if (it != g_live_blocks.end()) {
+            CachedBlock b{p, it->second.first, stream, nullptr, it->second.second};
+            g_live_blocks.erase(it);
+            if (cudaEventCreateWithFlags(&b.event, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b.event, stream) != cudaSuccess) {
+                cudaGetLastError();
+                cudaStreamSynchronize(stream);
+                cudaFree(p);
+                return NODEY_OK;
+            }
+            g_free_blocks.push_back(b);
+            return NODEY_OK;
+        }
+    }
+    NODEY_CUDA_OK(cudaFreeAsync(p, stream));
+    return NODEY_OK;
+}
+
+}  // namespace nodey
+
 using namespace nodey;
 
 extern "C" {
@@ -96,15 +211,18 @@ int nodey_stream_wait_event(nodey_stream_t s, nodey_event_t e)
 int nodey_malloc(void** out, size_t bytes, nodey_stream_t s)
 {
     NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_malloc: null argument");
-    *out = nullptr;
-    if (bytes == 0) return NODEY_OK;
-    NODEY_CUDA_OK(cudaMallocAsync(out, bytes, as_stream(s)));
-    return NODEY_OK;
+    return device_alloc(out, bytes, as_stream(s));
 }
 
-int nodey_free(void* p, nodey_stream_t s)
+int nodey_free(void* p, nodey_stream_t s) { return device_free(p, as_stream(s)); }
+
+/* return every cached block of the current device to the driver (synchronises) */
+int nodey_trim_memory(void)
 {
-    if (p) NODEY_CUDA_OK(cudaFreeAsync(p, as_stream(s)));
+    int dev = 0;
+    NODEY_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    drop_cached_locked(dev);
     return NODEY_OK;
 }
 

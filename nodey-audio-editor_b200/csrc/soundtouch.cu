@@ -761,10 +761,13 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     const long long s1 = ((L.l1 * CH + 3) & ~3ll) + 4, s2 = ((L.l2 * CH + 3) & ~3ll) + 4;
     float* ws = nullptr;
     int* ws_offs = nullptr;
-    NODEY_CUDA_OK(cudaMallocAsync((void**)&ws, sizeof(float) * (size_t)((s1 + s2) * ntracks), st));
+    {
+        const int rc = device_alloc((void**)&ws, sizeof(float) * (size_t)((s1 + s2) * ntracks), st);
+        if (rc != NODEY_OK) return rc;
+    }
     if (!offsets) {
-        cudaError_t e = cudaMallocAsync((void**)&ws_offs, sizeof(int) * (size_t)(offs_stride_ws * ntracks), st);
-        if (e != cudaSuccess) { cudaFreeAsync(ws, st); return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__); }
+        const int rc = device_alloc((void**)&ws_offs, sizeof(int) * (size_t)(offs_stride_ws * ntracks), st);
+        if (rc != NODEY_OK) { device_free(ws, st); return rc; }
         d_offs = ws_offs;
     }
     float* b1 = ws;
@@ -852,8 +855,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         View v2{b2, L.l2, 0, s2};
         if (rc == NODEY_OK) rc = run_tds(v2, out, out_stride, out_frames);
     }
-    cudaFreeAsync(ws, st);
-    if (ws_offs) cudaFreeAsync(ws_offs, st);
+    device_free(ws, st);
+    if (ws_offs) device_free(ws_offs, st);
     return rc;
 }
 

@@ -36,6 +36,19 @@ namespace infra
 		void synchronize() const;
 	};
 
+	// The Runner's streams.  A render uses two: a transfer lane (source nodes: host->device uploads) and a
+	// compute lane (every other node), ordered against each other by the events in the products.
+	// Device memory is stream ordered: blocks are allocated on the lane of the node that creates them and
+	// released through free_ordered(), which enqueues the free on the compute lane -- after every kernel
+	// that could still read the block, without stalling anything (a free on the legacy default stream
+	// would act as a barrier across all lanes) and immediately reusable by the next node's allocations.
+	struct Lane_registry
+	{
+		static void add(Stream_handle lane, bool compute);
+		static void remove(Stream_handle lane);
+		static void free_ordered(void* ptr);
+	};
+
 	// owned device allocation (cudaMallocAsync on the current stream; freed stream-ordered)
 	class Device_block
 	{

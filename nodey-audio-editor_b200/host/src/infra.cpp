@@ -6,6 +6,10 @@
 #include "nodey_cuda.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
 #include <typeindex>
 
 namespace infra
@@ -40,11 +44,75 @@ namespace infra
 		abi_check(nodey_malloc(&ptr, n, Exec_context::current().stream), "nodey_malloc");
 	}
 
-	Device_block::~Device_block()
+	Device_block::~Device_block() { Lane_registry::free_ordered(ptr); }
+
+	namespace
 	{
-		// freed on the legacy default stream: ordered after everything already enqueued on the Runner's
-		// (blocking) streams, so consumers that only enqueued work may drop their reference at once
-		nodey_free(ptr, nullptr);
+		struct Lane { Stream_handle stream; Event_handle event; bool compute; };
+		struct Lanes
+		{
+			std::mutex mutex;
+			std::vector<Lane> lanes;
+			Stream_handle reaper = nullptr;
+		};
+		Lanes& lanes_state()
+		{
+			static Lanes s;
+			return s;
+		}
+	}
+
+	void Lane_registry::add(Stream_handle lane, bool compute)
+	{
+		Lanes& s = lanes_state();
+		std::lock_guard lock(s.mutex);
+		Event_handle ev = nullptr;
+		abi_check(nodey_event_create(&ev, 0), "nodey_event_create");
+		s.lanes.push_back({lane, ev, compute});
+	}
+
+	void Lane_registry::remove(Stream_handle lane)
+	{
+		Lanes& s = lanes_state();
+		std::lock_guard lock(s.mutex);
+		for (auto it = s.lanes.begin(); it != s.lanes.end(); ++it)
+			if (it->stream == lane)
+			{
+				nodey_event_destroy(it->event);
+				s.lanes.erase(it);
+				return;
+			}
+	}
+
+	void Lane_registry::free_ordered(void* ptr)
+	{
+		if (!ptr) return;
+		Lanes& s = lanes_state();
+		std::lock_guard lock(s.mutex);
+		Stream_handle compute = nullptr;
+		int n_compute = 0;
+		for (const Lane& l : s.lanes)
+			if (l.compute) { compute = l.stream; n_compute++; }
+		if (s.lanes.empty())
+		{
+			// no render in flight: the legacy default stream orders the free after all earlier work
+			nodey_free(ptr, nullptr);
+			return;
+		}
+		if (n_compute == 1)
+		{
+			// one render in flight: every consumer enqueued on its compute lane, so the free goes there too
+			nodey_free(ptr, compute);
+			return;
+		}
+		// several renders at once: order the free after everything enqueued on every lane
+		if (!s.reaper && nodey_stream_create(&s.reaper) != NODEY_OK) { nodey_free(ptr, nullptr); return; }
+		for (Lane& l : s.lanes)
+		{
+			nodey_event_record(l.event, l.stream);
+			nodey_stream_wait_event(s.reaper, l.event);
+		}
+		nodey_free(ptr, s.reaper);
 	}
 
 	// ---------------------------------------------------------------------------------------------
@@ -373,12 +441,14 @@ namespace infra
 
 	void Runner::launch_threads()
 	{
-		constexpr int kLanes = 4;
-		nodey_stream_t lanes[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+		// lane 0: transfers (nodes without inputs: the sources' uploads); lane 1: compute (everything else)
+		constexpr int kLanes = 2;
+		nodey_stream_t lanes[kLanes] = {nullptr, nullptr};
 		bool failed = false;
 		if (device >= 0 && nodey_set_device(device) != NODEY_OK) failed = true;
-		for (auto& s : lanes)
-			if (nodey_stream_create(&s) != NODEY_OK) failed = true;
+		for (int k = 0; k < kLanes; k++)
+			if (nodey_stream_create(&lanes[k]) != NODEY_OK) failed = true;
+			else Lane_registry::add(lanes[k], k == 1);
 		if (failed)
 		{
 			for (auto& [_, r] : processor_resources)
@@ -392,20 +462,23 @@ namespace infra
 
 		std::any fallback;
 		int level_index = 0;
+		// NODEY_TRACE=1: per-level wall time (host enqueue, then device drain) on stderr; serialises the levels
+		const bool trace = getenv("NODEY_TRACE") != nullptr;
 		for (const auto& level : levels)
 		{
 			if (failed) break;
+			const auto t_begin = std::chrono::steady_clock::now();
 			// group the level's nodes by class: one batch call per class, on its own stream lane
 			std::map<std::type_index, std::vector<Id_t>> groups;
 			for (const Id_t id : level) groups[std::type_index(typeid(*processor_resources.at(id)->processor))].push_back(id);
-			int lane = 0;
 			for (auto& [_, ids] : groups)
 			{
+				// source nodes (level 0 = no inputs) upload on the transfer lane, everything else computes
+				const int lane = level_index == 0 ? 0 : 1;
 				Exec_context& ctx = Exec_context::current();
-				ctx.stream = lanes[lane % kLanes];
+				ctx.stream = lanes[lane];
 				ctx.level = level_index;
-				ctx.lane = lane % kLanes;
-				lane++;
+				ctx.lane = lane;
 
 				std::vector<Processor::Batch_item> items;
 				for (const Id_t id : ids)
@@ -453,11 +526,23 @@ namespace infra
 				}
 				if (failed) break;
 			}
+			if (trace)
+			{
+				const auto t_enq = std::chrono::steady_clock::now();
+				for (auto& s : lanes) nodey_stream_synchronize(s);
+				const auto t_end = std::chrono::steady_clock::now();
+				fprintf(stderr, "[nodey trace] level %d: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", level_index, level.size(),
+						processor_resources.at(level.front())->processor->get_processor_info_non_static().identifier.c_str(),
+						std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+						std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+			}
 			level_index++;
 		}
 		for (auto& s : lanes)
 		{
+			if (!s) continue;
 			nodey_stream_synchronize(s);
+			Lane_registry::remove(s);
 			nodey_stream_destroy(s);
 		}
 		done = true;

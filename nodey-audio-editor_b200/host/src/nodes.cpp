@@ -693,24 +693,50 @@ namespace processor
 		vol.resize((size_t)nin, 1.0f);
 
 		// frame bookkeeping of the reference loop: total length, placement of every input, own frame sizes
+		// (cached: the 256 per-track amix nodes of a batch render share one plan)
 		const Runs_flat flat(runs);
-		std::vector<int32_t> seg_in(64);
-		std::vector<int64_t> seg_out(64), seg_src(64), seg_len(64), run_len(64), run_cnt(64);
-		int64_t nseg = 0, nrun = 0, total = 0;
-		for (int attempt = 0; attempt < 2; attempt++)
+		struct Plan { int64_t total = 0; std::vector<Segment> segs; Frame_runs out_runs; };
+		static std::map<std::vector<int64_t>, std::shared_ptr<const Plan>> plan_cache;
+		std::vector<int64_t> key;
+		for (const int r : rates) key.push_back(r);
+		key.push_back(-1);
+		key.insert(key.end(), flat.off.begin(), flat.off.end());
+		key.push_back(-1);
+		key.insert(key.end(), flat.len.begin(), flat.len.end());
+		key.push_back(-1);
+		key.insert(key.end(), flat.count.begin(), flat.count.end());
+		std::shared_ptr<const Plan> plan;
 		{
-			total = nodey_amix_plan(rates.data(), nin, flat.off.data(), flat.len.data(), flat.count.data(), 0, seg_in.data(), seg_out.data(),
-									seg_src.data(), seg_len.data(), (int64_t)seg_in.size(), &nseg, run_len.data(), run_cnt.data(),
-									(int64_t)run_len.size(), &nrun);
-			if (total < 0) abi((int)total, "Audio mixer");
-			if (nseg <= (int64_t)seg_in.size() && nrun <= (int64_t)run_len.size()) break;
-			const size_t a = (size_t)std::max<int64_t>(nseg, 64), b = (size_t)std::max<int64_t>(nrun, 64);
-			seg_in.resize(a); seg_out.resize(a); seg_src.resize(a); seg_len.resize(a); run_len.resize(b); run_cnt.resize(b);
+			std::lock_guard lock(plan_mutex);
+			const auto it = plan_cache.find(key);
+			if (it != plan_cache.end()) plan = it->second;
 		}
-		std::vector<Segment> segs;
-		for (int64_t k = 0; k < nseg; k++) segs.push_back({seg_in[(size_t)k], seg_out[(size_t)k], seg_src[(size_t)k], seg_len[(size_t)k]});
-		Frame_runs out_runs;
-		for (int64_t k = 0; k < nrun; k++) out_runs.emplace_back(run_len[(size_t)k], run_cnt[(size_t)k]);
+		if (!plan)
+		{
+			auto fresh = std::make_shared<Plan>();
+			std::vector<int32_t> seg_in(64);
+			std::vector<int64_t> seg_out(64), seg_src(64), seg_len(64), run_len(64), run_cnt(64);
+			int64_t nseg = 0, nrun = 0;
+			for (int attempt = 0; attempt < 2; attempt++)
+			{
+				fresh->total = nodey_amix_plan(rates.data(), nin, flat.off.data(), flat.len.data(), flat.count.data(), 0, seg_in.data(),
+											   seg_out.data(), seg_src.data(), seg_len.data(), (int64_t)seg_in.size(), &nseg, run_len.data(),
+											   run_cnt.data(), (int64_t)run_len.size(), &nrun);
+				if (fresh->total < 0) abi((int)fresh->total, "Audio mixer");
+				if (nseg <= (int64_t)seg_in.size() && nrun <= (int64_t)run_len.size()) break;
+				const size_t a = (size_t)std::max<int64_t>(nseg, 64), b = (size_t)std::max<int64_t>(nrun, 64);
+				seg_in.resize(a); seg_out.resize(a); seg_src.resize(a); seg_len.resize(a); run_len.resize(b); run_cnt.resize(b);
+			}
+			for (int64_t k = 0; k < nseg; k++) fresh->segs.push_back({seg_in[(size_t)k], seg_out[(size_t)k], seg_src[(size_t)k], seg_len[(size_t)k]});
+			for (int64_t k = 0; k < nrun; k++) fresh->out_runs.emplace_back(run_len[(size_t)k], run_cnt[(size_t)k]);
+			std::lock_guard lock(plan_mutex);
+			if (plan_cache.size() > 256) plan_cache.clear();
+			plan_cache[key] = fresh;
+			plan = fresh;
+		}
+		const int64_t total = plan->total;
+		const std::vector<Segment>& segs = plan->segs;
+		Frame_runs out_runs = plan->out_runs;
 
 		const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
 		auto block = std::make_shared<infra::Device_block>(2 * plane);
