@@ -42,7 +42,7 @@
 namespace nodey {
 
 constexpr int kAaLen = 64;
-constexpr int kTdsThreads = 512;
+constexpr int kTdsThreads = 256;      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
 
 // frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
 // (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks)
@@ -85,6 +85,11 @@ struct TdsArgs {
     int sk;                    // floats per sub-plane
     int ncand_pad;             // padded candidates per CTA (partial-sum arrays)
 };
+
+// partial-sum slot of candidate cc: one word of padding per K*KT candidates makes both the strided
+// stores of the lane-sum phase (stride K*KT) and the unit-stride loads of the combine phase conflict free
+template <int S>
+__device__ __forceinline__ int ps_slot(int cc) { return cc + cc / S; }
 
 struct ArgMax { double v; int i; };
 
@@ -160,7 +165,7 @@ __device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int 
 // candidates (blocks of KT per class) and exchange their local arg-max through distributed
 // shared memory, one cluster barrier per sequence.
 template <int CH, int KT>
-__global__ void __launch_bounds__(kTdsThreads, 1) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+__global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kTdsThreads, 1) tds_offsets_kernel(const __gri
 #pragma unroll
                 for (int k = 0; k < KT; k++) {
                     const int cc = kappa + K * (KT * tb + k);
-                    if (cc < ncand) { PS[l * a.ncand_pad + cc] = acc[k]; PN[l * a.ncand_pad + cc] = nrm[k]; }
+                    if (cc < ncand) { PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k]; PN[l * a.ncand_pad + ps_slot<K * KT>(cc)] = nrm[k]; }
                 }
             }
         }
@@ -260,9 +265,9 @@ __global__ void __launch_bounds__(kTdsThreads, 1) tds_offsets_kernel(const __gri
         // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max ----
         ArgMax best; best.v = -1e300; best.i = 0x7fffffff;
         for (int cc = tid; cc < ncand; cc += blockDim.x) {
-            const int c = c_base + cc, np = a.ncand_pad;
-            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[cc], PS[np + cc]), PS[2 * np + cc]), PS[3 * np + cc]);
-            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[cc], PN[np + cc]), PN[2 * np + cc]), PN[3 * np + cc]);
+            const int c = c_base + cc, np = a.ncand_pad, sl = ps_slot<K * KT>(cc);
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[sl], PS[np + sl]), PS[2 * np + sl]), PS[3 * np + sl]);
+            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[sl], PN[np + sl]), PN[2 * np + sl]), PN[3 * np + sl]);
             const double dn = (double)nr;
             double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
             const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
@@ -372,14 +377,14 @@ struct FirArgs {
     float h[kAaLen];            // coefficients ride in the kernel parameters (constant bank, uniform reads)
 };
 
-constexpr int kFirR = 4;                  // outputs per thread
+constexpr int kFirR = 4;                  // outputs per thread (mono path)
 constexpr int kFirThreads = 256;
-constexpr int kFirTile = kFirR * kFirThreads;   // 1024 outputs per CTA
+constexpr int kFirTile = kFirR * kFirThreads;   // 1024 outputs per CTA (mono path)
 
-template <int CH>
-__global__ void __launch_bounds__(kFirThreads) aa_fir_kernel(const __grid_constant__ FirArgs a)
+// mono: FIRFilter::evaluateFilterMono, double accumulator
+__global__ void __launch_bounds__(kFirThreads) aa_fir_mono_kernel(const __grid_constant__ FirArgs a)
 {
-    __shared__ __align__(16) float tile[(kFirTile + kAaLen) * CH];
+    __shared__ __align__(16) float tile[kFirTile + kAaLen];
     const long long track = blockIdx.y;
     const float* base = a.in.p + track * a.in.stride;
     float* out = a.out + track * a.out_stride;
@@ -388,49 +393,82 @@ __global__ void __launch_bounds__(kFirThreads) aa_fir_kernel(const __grid_consta
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const long long n0 = t * kFirTile;
         __syncthreads();
-        for (int f = threadIdx.x; f < kFirTile + kAaLen; f += blockDim.x) {
-            if (CH == 2) reinterpret_cast<float2*>(tile)[f] = view_frame2<2>(a.in, base, n0 + f);
-            else tile[f] = view_sample<1>(a.in, base, n0 + f, 0);
+        for (int f = threadIdx.x; f < kFirTile + kAaLen; f += blockDim.x) tile[f] = view_sample<1>(a.in, base, n0 + f, 0);
+        __syncthreads();
+        double s[kFirR];
+#pragma unroll
+        for (int r = 0; r < kFirR; r++) s[r] = 0.0;
+        const float* tp = tile + threadIdx.x;
+        for (int i = 0; i < kAaLen; i++) {
+            const float hi = h[i];
+#pragma unroll
+            for (int r = 0; r < kFirR; r++) s[r] = __dadd_rn(s[r], (double)__fmul_rn(tp[r * kFirThreads + i], hi));
+        }
+#pragma unroll
+        for (int r = 0; r < kFirR; r++) {
+            const long long n = n0 + threadIdx.x + r * kFirThreads;
+            if (n < a.count) out[n] = (float)s[r];
+        }
+    }
+}
+
+// stereo: FIRFilterSSE::evaluateFilterStereo.  A thread owns 8 CONSECUTIVE output frames and slides one
+// register window of 10 input frames over the 32 tap pairs: one 128-bit shared load (two new frames)
+// feeds 64 rounded multiply/adds.  The tile is stored in 16-byte chunks (two frames) whose column is
+// XOR-swizzled with the 128-byte row, so the threads' strided 128-bit loads are conflict free.
+constexpr int kFirS = 8;                              // outputs per thread
+constexpr int kFirTileS = kFirS * kFirThreads;        // 2048 outputs per CTA
+constexpr int kFirChunks = (kFirTileS + kAaLen + 8) / 2;
+
+__device__ __forceinline__ int fir_chunk(int chunk) { return (chunk & ~7) | ((chunk ^ (chunk >> 3)) & 7); }
+
+__global__ void __launch_bounds__(kFirThreads) aa_fir_stereo_kernel(const __grid_constant__ FirArgs a)
+{
+    __shared__ __align__(16) float4 tile[kFirChunks];
+    const long long track = blockIdx.y;
+    const float* base = a.in.p + track * a.in.stride;
+    float* out = a.out + track * a.out_stride;
+    const float* h = a.h;
+    const long long ntiles = (a.count + kFirTileS - 1) / kFirTileS;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long long n0 = t * kFirTileS;
+        __syncthreads();
+        for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
+            const float2 f0 = view_frame2<2>(a.in, base, n0 + 2 * c), f1 = view_frame2<2>(a.in, base, n0 + 2 * c + 1);
+            tile[fir_chunk(c)] = make_float4(f0.x, f0.y, f1.x, f1.y);
         }
         __syncthreads();
-        // thread owns outputs j = threadIdx.x + r * kFirThreads (conflict-free shared reads)
-        if (CH == 2) {
-            float e0[kFirR], e1[kFirR], o0[kFirR], o1[kFirR];
+        float e0[kFirS], e1[kFirS], o0[kFirS], o1[kFirS];
 #pragma unroll
-            for (int r = 0; r < kFirR; r++) { e0[r] = e1[r] = o0[r] = o1[r] = 0.f; }
-            const float2* tp = reinterpret_cast<const float2*>(tile) + threadIdx.x;
-#pragma unroll 8
-            for (int i = 0; i < kAaLen; i += 2) {
-                const float h0 = h[i], h1 = h[i + 1];
+        for (int r = 0; r < kFirS; r++) { e0[r] = e1[r] = o0[r] = o1[r] = 0.f; }
+        // window: frames 8*tid + 2*step .. + 9, kept as 5 chunks in a rotating register file
+        float4 w[5];
+        const int c0 = threadIdx.x * (kFirS / 2);
 #pragma unroll
-                for (int r = 0; r < kFirR; r++) {
-                    const float2 x0 = tp[r * kFirThreads + i], x1 = tp[r * kFirThreads + i + 1];
-                    e0[r] = __fadd_rn(e0[r], __fmul_rn(x0.x, h0));
-                    e1[r] = __fadd_rn(e1[r], __fmul_rn(x0.y, h0));
-                    o0[r] = __fadd_rn(o0[r], __fmul_rn(x1.x, h1));
-                    o1[r] = __fadd_rn(o1[r], __fmul_rn(x1.y, h1));
-                }
+        for (int k = 0; k < 5; k++) w[k] = tile[fir_chunk(c0 + k)];
+#pragma unroll
+        for (int step = 0; step < kAaLen / 2; step++) {
+            const float h0 = h[2 * step], h1 = h[2 * step + 1];
+#pragma unroll
+            for (int r = 0; r < kFirS; r++) {
+                // even tap: frame r of the window; odd tap: frame r + 1
+                const float4 ce = w[(step + r / 2) % 5], co = w[(step + (r + 1) / 2) % 5];
+                const float xe0 = (r & 1) ? ce.z : ce.x, xe1 = (r & 1) ? ce.w : ce.y;
+                const float xo0 = ((r + 1) & 1) ? co.z : co.x, xo1 = ((r + 1) & 1) ? co.w : co.y;
+                e0[r] = __fadd_rn(e0[r], __fmul_rn(xe0, h0));
+                e1[r] = __fadd_rn(e1[r], __fmul_rn(xe1, h0));
+                o0[r] = __fadd_rn(o0[r], __fmul_rn(xo0, h1));
+                o1[r] = __fadd_rn(o1[r], __fmul_rn(xo1, h1));
             }
+            if (step + 1 < kAaLen / 2) w[step % 5] = tile[fir_chunk(c0 + step + 5)];    // the chunk that just left the window
+        }
+        const long long n = n0 + (long long)threadIdx.x * kFirS;
+        float4* o4 = reinterpret_cast<float4*>(out + 2 * n);       // track strides and n are multiples of 2 frames: 16-byte aligned
 #pragma unroll
-            for (int r = 0; r < kFirR; r++) {
-                const long long n = n0 + threadIdx.x + r * kFirThreads;
-                if (n < a.count) reinterpret_cast<float2*>(out)[n] = make_float2(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]));
-            }
-        } else {
-            double s[kFirR];
-#pragma unroll
-            for (int r = 0; r < kFirR; r++) s[r] = 0.0;
-            const float* tp = tile + threadIdx.x;
-            for (int i = 0; i < kAaLen; i++) {
-                const float hi = h[i];
-#pragma unroll
-                for (int r = 0; r < kFirR; r++) s[r] = __dadd_rn(s[r], (double)__fmul_rn(tp[r * kFirThreads + i], hi));
-            }
-#pragma unroll
-            for (int r = 0; r < kFirR; r++) {
-                const long long n = n0 + threadIdx.x + r * kFirThreads;
-                if (n < a.count) out[n] = (float)s[r];
-            }
+        for (int r = 0; r < kFirS; r += 2) {
+            const float4 v = make_float4(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]), __fadd_rn(o0[r + 1], e0[r + 1]), __fadd_rn(o1[r + 1], e1[r + 1]));
+            if (n + r + 1 < a.count) o4[r / 2] = v;
+            else if (n + r < a.count) { out[2 * (n + r)] = v.x; out[2 * (n + r) + 1] = v.y; }
         }
     }
 }
@@ -780,8 +818,9 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         ta.Q = 4 * (CH * s->overlap / 16);
         if (nseq > 1) {
             // cluster size: spread one track over CL SMs while the batch leaves SMs idle
+            // two CTAs fit per SM: grow the cluster while every CTA of the batch can still be resident
             int CL = 1;
-            while (CL < 4 && (long long)ntracks * CL * 2 <= sm_count()) CL *= 2;
+            while (CL < 4 && (long long)ntracks * CL * 2 <= 2ll * sm_count()) CL *= 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
             const int KT = CL >= 4 ? 4 : 8;
             const int K = 4 / CH;
@@ -790,7 +829,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             int sk = ta.tb_per + ta.Q / KT + 4;
             while ((sk & 7) != 4) sk++;
             ta.sk = sk;
-            ta.ncand_pad = (K * KT * ta.tb_per + 3) & ~3;
+            ta.ncand_pad = (K * KT * ta.tb_per + ta.tb_per + 4 + 3) & ~3;      // + one pad word per K*KT candidates
             const size_t smem = sizeof(float) * ((size_t)4 * KT * sk + (size_t)4 * ta.Q + (size_t)8 * ta.ncand_pad);
             void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
                                             : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);
@@ -821,10 +860,13 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     auto run_fir = [&](View vin, float* dst, long long dst_stride, long long count) -> int {
         if (count <= 0) return NODEY_OK;
         FirArgs fa; fa.in = vin; fa.out = dst; fa.out_stride = dst_stride; fa.count = count; memcpy(fa.h, s->aa, sizeof(fa.h));
-        long long tiles = (count + kFirTile - 1) / kFirTile;
+        const int tile = CH == 2 ? kFirTileS : kFirTile;
+        long long tiles = (count + tile - 1) / tile;
         long long gx = tiles < 65535 ? tiles : 65535;
         dim3 grid((unsigned)gx, (unsigned)ntracks);
-        if (CH == 2) NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_kernel<2><<<grid, kFirThreads, 0, st>>>(fa)); else NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_kernel<1><<<grid, kFirThreads, 0, st>>>(fa));
+        const bool aligned = (((uintptr_t)dst) & 15) == 0 && (dst_stride % 4) == 0;
+        NODEY_REQUIRE(CH == 1 || aligned, NODEY_E_INVALID, "aa_fir: stereo output must be 16-byte aligned");
+        if (CH == 2) NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_stereo_kernel<<<grid, kFirThreads, 0, st>>>(fa)); else NODEY_LAUNCH("aa_fir_kernel", st, aa_fir_mono_kernel<<<grid, kFirThreads, 0, st>>>(fa));
         NODEY_LAUNCH_OK();
         return NODEY_OK;
     };

@@ -113,6 +113,10 @@ namespace infra
 		// to let the Runner fall back to one process_payload() call per node.
 		virtual bool process_batch(const std::vector<Batch_item>& /*items*/) { return false; }
 
+		// Optional: bytes this node will copy host -> device when it runs with `user_data` (source nodes).
+		// The Runner pipelines the graph in waves over the source pins only when there is an upload to hide.
+		virtual size_t upload_bytes(const std::any& /*user_data*/) const { return 0; }
+
 		template <typename T>
 			requires(std::is_base_of_v<Processor, T> && Has_static_processor_info_func<T, Processor::Info>)
 		static void register_processor()

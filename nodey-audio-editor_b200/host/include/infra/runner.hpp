@@ -43,6 +43,7 @@ namespace infra
 		std::map<Id_t, std::shared_ptr<Processor::Product>> link_products;
 		std::map<Id_t, std::shared_ptr<std::any>> node_data;
 		std::vector<std::vector<Id_t>> levels;
+		std::map<Id_t, int> node_wave;          // which block of source pins feeds the node (see launch_threads)
 		std::thread worker;
 		std::atomic<bool> done = false;
 		int device = -1;     // CUDA device of the creating thread; the worker thread binds to it

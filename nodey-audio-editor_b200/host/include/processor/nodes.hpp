@@ -67,6 +67,7 @@ namespace processor
 		virtual Json::Value serialize() const;
 		virtual void deserialize(const Json::Value& value);
 		void set_file_count(size_t n);          // programmatic equivalent of the UI's add/remove file buttons
+		virtual size_t upload_bytes(const std::any& user_data) const;
 	};
 
 	// ---- sink --------------------------------------------------------------------------------------

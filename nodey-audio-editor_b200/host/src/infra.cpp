@@ -392,6 +392,46 @@ namespace infra
 			processor_resources.at(to_pin.parent)->input_payloads.emplace(to_pin.attribute.identifier, product);
 			link_products.emplace(idx, product);
 		}
+
+		// waves: links leaving a source node (level 0) belong to wave (position of the pin among the node's
+		// output pins) / wave_size; every other node runs in the latest wave among its inputs
+		// Waves only pay off when there is a host -> device upload to hide behind compute (smaller batches
+		// cost some kernel efficiency): one wave when the sources are already in HBM.
+		size_t upload = 0;
+		std::any no_data;
+		if (!levels.empty())
+			for (const Id_t id : levels.front())
+			{
+				const auto data = node_data.find(id);
+				upload += graph.nodes.at(id).processor->upload_bytes(data == node_data.end() ? no_data : *data->second);
+			}
+		int wave_size = upload >= (1u << 30) ? 64 : 1 << 30;
+		if (const char* env = getenv("NODEY_WAVE")) wave_size = std::max(1, atoi(env));
+		std::map<Id_t, int> pin_position;     // output pin -> index in its node's attribute order
+		for (const auto& [id, node] : graph.nodes)
+		{
+			int k = 0;
+			for (const auto& attribute : node.processor->get_pin_attributes())
+				if (!attribute.is_input) pin_position[node.pin_name_map.at(attribute.identifier)] = k++;
+		}
+		std::set<Id_t> sources(levels.empty() ? std::vector<Id_t>{}.begin() : levels.front().begin(),
+							   levels.empty() ? std::vector<Id_t>{}.end() : levels.front().end());
+		for (const auto& [id, _] : graph.nodes) node_wave[id] = 0;
+		std::map<Id_t, std::vector<Id_t>> incoming;     // node -> producer pins
+		for (const auto& [_, link] : graph.links) incoming[graph.pins.at(link.to).parent].push_back(link.from);
+		for (size_t l = 1; l < levels.size(); l++)
+			for (const Id_t id : levels[l])
+			{
+				int wave = 0;
+				const auto in = incoming.find(id);
+				if (in != incoming.end())
+					for (const Id_t from_pin : in->second)
+					{
+						const Id_t producer = graph.pins.at(from_pin).parent;
+						wave = std::max(wave, sources.contains(producer) ? pin_position.at(from_pin) / wave_size : node_wave.at(producer));
+					}
+				node_wave[id] = wave;
+			}
 	}
 
 	Runner::~Runner()
@@ -461,20 +501,16 @@ namespace infra
 		}
 
 		std::any fallback;
-		int level_index = 0;
-		// NODEY_TRACE=1: per-level wall time (host enqueue, then device drain) on stderr; serialises the levels
+		// NODEY_TRACE=1: per-step wall time (host enqueue, then device drain) on stderr; serialises the steps
 		const bool trace = getenv("NODEY_TRACE") != nullptr;
-		for (const auto& level : levels)
-		{
-			if (failed) break;
-			const auto t_begin = std::chrono::steady_clock::now();
-			// group the level's nodes by class: one batch call per class, on its own stream lane
+
+		// run one batch per node class of `ids` on lane `lane`
+		const auto run_group = [&](const std::vector<Id_t>& all_ids, int lane, int level_index) {
 			std::map<std::type_index, std::vector<Id_t>> groups;
-			for (const Id_t id : level) groups[std::type_index(typeid(*processor_resources.at(id)->processor))].push_back(id);
+			for (const Id_t id : all_ids) groups[std::type_index(typeid(*processor_resources.at(id)->processor))].push_back(id);
 			for (auto& [_, ids] : groups)
 			{
-				// source nodes (level 0 = no inputs) upload on the transfer lane, everything else computes
-				const int lane = level_index == 0 ? 0 : 1;
+				if (failed) return;
 				Exec_context& ctx = Exec_context::current();
 				ctx.stream = lanes[lane];
 				ctx.level = level_index;
@@ -507,7 +543,7 @@ namespace infra
 							if (&r != &first) { r.exception = first.exception; r.state = State::Error; }
 						}
 						failed = true;
-						break;
+						return;
 					}
 				}
 				if (batched)
@@ -524,20 +560,34 @@ namespace infra
 					else
 						failed = true;
 				}
-				if (failed) break;
 			}
-			if (trace)
+		};
+
+		// Schedule: sources first (their uploads are enqueued on the transfer lane in pin order), then wave
+		// by wave, each wave level by level on the compute lane.  A wave is the part of the graph fed by a
+		// contiguous block of source pins, so wave k computes while the uploads of wave k+1 are in flight.
+		int max_wave = 0;
+		for (const auto& [_, w] : node_wave) max_wave = std::max(max_wave, w);
+		for (int wave = 0; wave <= max_wave && !failed; wave++)
+			for (size_t level_index = wave == 0 ? 0 : 1; level_index < levels.size() && !failed; level_index++)
 			{
-				const auto t_enq = std::chrono::steady_clock::now();
-				for (auto& s : lanes) nodey_stream_synchronize(s);
-				const auto t_end = std::chrono::steady_clock::now();
-				fprintf(stderr, "[nodey trace] level %d: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", level_index, level.size(),
-						processor_resources.at(level.front())->processor->get_processor_info_non_static().identifier.c_str(),
-						std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
-						std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+				std::vector<Id_t> ids;
+				for (const Id_t id : levels[level_index])
+					if (node_wave.at(id) == wave) ids.push_back(id);
+				if (ids.empty()) continue;
+				const auto t_begin = std::chrono::steady_clock::now();
+				run_group(ids, level_index == 0 ? 0 : 1, (int)level_index);
+				if (trace)
+				{
+					const auto t_enq = std::chrono::steady_clock::now();
+					for (auto& s : lanes) nodey_stream_synchronize(s);
+					const auto t_end = std::chrono::steady_clock::now();
+					fprintf(stderr, "[nodey trace] wave %d level %zu: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", wave, level_index,
+							ids.size(), processor_resources.at(ids.front())->processor->get_processor_info_non_static().identifier.c_str(),
+							std::chrono::duration<double, std::milli>(t_enq - t_begin).count(),
+							std::chrono::duration<double, std::milli>(t_end - t_begin).count());
+				}
 			}
-			level_index++;
-		}
 		for (auto& s : lanes)
 		{
 			if (!s) continue;

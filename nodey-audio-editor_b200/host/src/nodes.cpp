@@ -273,6 +273,24 @@ namespace processor
 		}
 	}
 
+	size_t Audio_input::upload_bytes(const std::any& user_data) const
+	{
+		const Pcm_source_list* bound = std::any_cast<Pcm_source_list>(&user_data);
+		if (!bound)
+			if (const auto* sp = std::any_cast<std::shared_ptr<Pcm_source_list>>(&user_data)) bound = sp->get();
+		size_t bytes = 0;
+		for (size_t i = 0; i < file_count; i++)
+		{
+			if (bound && i < bound->sources.size() && bound->sources[i].data)
+			{
+				const Pcm_source& s = bound->sources[i];
+				if (!s.on_device) bytes += (size_t)s.frames * (size_t)format_bytes(s.format) * (size_t)s.channels;
+			}
+			else if (!file_paths[i].empty()) bytes += 64u << 20;     // a file: size unknown until it is read
+		}
+		return bytes;
+	}
+
 	void Audio_input::process_payload(const Input_map&, const Output_map& output, const std::atomic<bool>&, std::any& user_data)
 	{
 		const Pcm_source_list* bound = std::any_cast<Pcm_source_list>(&user_data);
@@ -454,7 +472,7 @@ namespace processor
 	namespace
 	{
 		constexpr int kSoundtouchFrame = 1152;     // canonical putSamples / output chunk
-		constexpr size_t kMaxTracksPerLaunch = 128;
+		constexpr size_t kMaxTracksPerLaunch = 256;
 
 		bool soundtouch_batch(const std::vector<Processor::Batch_item>& items, const char* title)
 		{
