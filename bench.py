@@ -277,7 +277,7 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         name, st = max(rep.items(), key=lambda kv: kv[1]["ms"])
         per_launch_ms = st["ms"] / st["launches"]
-        st_batch = min(128, t_local)                     # tracks per SoundTouch launch (host/src/nodes.cpp)
+        st_batch = min(256, t_local)                     # tracks per SoundTouch launch when the sources are resident (host/src/nodes.cpp)
         ab = kernel_algo_bytes(name, plan, st_batch)
         achieved = (ab / (per_launch_ms * 1e-3) / 1e9) if ab else None
         traffic = None

@@ -19,7 +19,7 @@ namespace nodey {
 namespace {
 struct CachedBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; int device; };
 std::mutex g_alloc_mu;
-std::vector<CachedBlock> g_free_blocks;
+std::multimap<size_t, CachedBlock> g_free_blocks;           // by (rounded) size
 std::map<void*, std::pair<size_t, int>> g_live_blocks;     // ptr -> (rounded size, device)
 constexpr size_t kGranule = 2u << 20;
 constexpr size_t kSmall = 1u << 20;                           // below this: cudaMallocAsync (pool handles it well)
@@ -39,14 +39,13 @@ void retain_small_pool()
 
 void drop_cached_locked(int device)
 {
-    for (size_t i = 0; i < g_free_blocks.size();) {
-        if (g_free_blocks[i].device == device) {
-            cudaEventSynchronize(g_free_blocks[i].event);
-            cudaEventDestroy(g_free_blocks[i].event);
-            cudaFree(g_free_blocks[i].ptr);
-            g_free_blocks[i] = g_free_blocks.back();
-            g_free_blocks.pop_back();
-        } else i++;
+    for (auto it = g_free_blocks.begin(); it != g_free_blocks.end();) {
+        if (it->second.device == device) {
+            cudaEventSynchronize(it->second.event);
+            cudaEventDestroy(it->second.event);
+            cudaFree(it->second.ptr);
+            it = g_free_blocks.erase(it);
+        } else ++it;
     }
 }
 }  // namespace
@@ -64,18 +63,18 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
     NODEY_CUDA_OK(cudaGetDevice(&dev));
     const size_t want = (bytes + kGranule - 1) / kGranule * kGranule;
     std::lock_guard<std::mutex> lock(g_alloc_mu);
-    // best fit among reusable blocks (no more than 12.5 % waste)
-    int best = -1;
-    for (int i = 0; i < (int)g_free_blocks.size(); i++) {
-        const CachedBlock& b = g_free_blocks[(size_t)i];
-        if (b.device != dev || b.bytes < want || b.bytes > want + want / 8) continue;
-        if (b.stream != stream && cudaEventQuery(b.event) != cudaSuccess) continue;
-        if (best < 0 || b.bytes < g_free_blocks[(size_t)best].bytes) best = i;
+    // smallest reusable block that fits with no more than 12.5 % waste; blocks freed on this very stream
+    // are preferred (no event query needed: stream order already protects them)
+    auto pick = g_free_blocks.end();
+    for (auto it = g_free_blocks.lower_bound(want); it != g_free_blocks.end() && it->first <= want + want / 8; ++it) {
+        const CachedBlock& b = it->second;
+        if (b.device != dev) continue;
+        if (b.stream == stream) { pick = it; break; }
+        if (pick == g_free_blocks.end() && cudaEventQuery(b.event) == cudaSuccess) pick = it;
     }
-    if (best >= 0) {
-        CachedBlock b = g_free_blocks[(size_t)best];
-        g_free_blocks[(size_t)best] = g_free_blocks.back();
-        g_free_blocks.pop_back();
+    if (pick != g_free_blocks.end()) {
+        const CachedBlock b = pick->second;
+        g_free_blocks.erase(pick);
         cudaEventDestroy(b.event);
         g_live_blocks[b.ptr] = {b.bytes, dev};
         *out = b.ptr;
@@ -107,7 +106,7 @@ int device_free(void* p, cudaStream_t stream)
                 cudaFree(p);
                 return NODEY_OK;
             }
-            g_free_blocks.push_back(b);
+            g_free_blocks.emplace(b.bytes, b);
             return NODEY_OK;
         }
     }

@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     extern __shared__ __align__(16) float smem[];
     constexpr int K = 4 / CH;                       // candidate classes per lane
     const int plane_len = KT * a.sk;
-    float* X = smem;                                // [4 planes][KT sub-planes][sk]
-    float* Y = X + 4 * plane_len;                   // [4][Q]
+    float* X0 = smem;                               // 2 x [4 planes][KT sub-planes][sk] (double buffered)
+    float* Y = X0 + 8 * plane_len;                  // [4][Q]
     float* PS = Y + 4 * a.Q;                        // [4][ncand_pad] correlation lane sums
     float* PN = PS + 4 * a.ncand_pad;               // [4][ncand_pad] norm lane sums
     __shared__ double red_v[kTdsThreads / 32];
@@ -205,40 +205,63 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
 
     long long mid_pos = a.pos[0] + temp;             // first sequence: offset 0, no search
 
+    // The search window of sequence i+1 does not depend on offset i: it is fetched into registers while
+    // sequence i is searched and written to the other half of the double-buffered planes afterwards, so
+    // only the mid buffer (which does depend on the offset) is loaded on the critical path.
+    constexpr int NR = 2048 / kTdsThreads;           // frames (stereo) / samples (mono) per thread, nfr <= 2048
+    float2 pre[NR];
+    const auto window_fetch = [&](int seq) {
+        const long long p0 = a.pos[seq];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const int fr = tid + r * kTdsThreads;
+            const int f = f_lo + fr;
+            pre[r] = make_float2(0.f, 0.f);
+            if (fr < nfr && f < region) {
+                if (CH == 2) pre[r] = view_frame2<2>(a.in, base, p0 + f);
+                else pre[r].x = view_sample<1>(a.in, base, p0 + f, 0);
+            }
+        }
+    };
+    const auto window_store = [&](float* Xb) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const int fr = tid + r * kTdsThreads;
+            if (fr >= nfr) continue;
+            if (CH == 2) {
+                const int m = fr >> 1, pl = (fr & 1) * 2;
+                const int ph = (m % KT) * a.sk + m / KT;
+                Xb[pl * plane_len + ph] = pre[r].x;
+                Xb[(pl + 1) * plane_len + ph] = pre[r].y;
+            } else {
+                const int m = fr >> 2;
+                Xb[(fr & 3) * plane_len + (m % KT) * a.sk + m / KT] = pre[r].x;
+            }
+        }
+    };
+    const auto l2_prefetch = [&](int seq) {
+        if (seq >= a.nseq) return;
+        const long long q0 = a.pos[seq] + f_lo - a.in.prefix;
+        const int lines = (nfr * CH * 4 + 127) / 128 + 1;
+        for (int t = tid; t < lines; t += blockDim.x) {
+            const long long f = q0 + (long long)t * (32 / CH);
+            if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
+        }
+    };
+
+    if (a.nseq > 1) { window_fetch(1); window_store(X0); }
+    int cur = 0;
+
     for (int i = 1; i < a.nseq; i++) {
         const long long p0 = a.pos[i];
-        // L2 prefetch of the next sequence's window (its position does not depend on this search)
-        if (i + 1 < a.nseq) {
-            const long long q0 = a.pos[i + 1] + f_lo - a.in.prefix;
-            const int lines = (nfr * CH * 4 + 127) / 128 + 1;
-            for (int t = tid; t < lines; t += blockDim.x) {
-                const long long f = q0 + (long long)t * (32 / CH);
-                if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
-            }
-        }
-        // ---- stage this CTA's slice of the search window: plane = float index mod 4, sub-plane = m mod KT ----
-        if (CH == 2) {
-            for (int fr = tid; fr < nfr; fr += blockDim.x) {
-                const int f = f_lo + fr;
-                const float2 v = f < region ? view_frame2<2>(a.in, base, p0 + f) : make_float2(0.f, 0.f);
-                const int m = fr >> 1, r = (fr & 1) * 2;
-                const int ph = (m % KT) * a.sk + m / KT;
-                X[r * plane_len + ph] = v.x;
-                X[(r + 1) * plane_len + ph] = v.y;
-            }
-        } else {
-            for (int fr = tid; fr < nfr; fr += blockDim.x) {
-                const int f = f_lo + fr;
-                const float v = f < region ? view_sample<1>(a.in, base, p0 + f, 0) : 0.f;
-                const int m = fr >> 2;
-                X[(fr & 3) * plane_len + (m % KT) * a.sk + m / KT] = v;
-            }
-        }
+        float* X = X0 + cur * 4 * plane_len;
+        l2_prefetch(i + 2);
         // ---- mid buffer (depends on the previous offset), de-interleaved by lane ----
         for (int j = tid; j < 4 * Q; j += blockDim.x) {
             const long long fr = mid_pos + j / CH;
             Y[(j & 3) * Q + (j >> 2)] = view_sample<CH>(a.in, base, fr, j % CH);
         }
+        if (i + 1 < a.nseq) window_fetch(i + 1);     // in flight during the search below
         __syncthreads();
 
         // ---- lane sums: thread = (lane l, class kappa, KT consecutive candidates of the class) ----
@@ -261,6 +284,8 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             }
         }
         __syncthreads();
+        if (i + 1 < a.nseq) window_store(X0 + (cur ^ 1) * 4 * plane_len);
+        cur ^= 1;
 
         // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max ----
         ArgMax best; best.v = -1e300; best.i = 0x7fffffff;
@@ -830,7 +855,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             while ((sk & 7) != 4) sk++;
             ta.sk = sk;
             ta.ncand_pad = (K * KT * ta.tb_per + ta.tb_per + 4 + 3) & ~3;      // + one pad word per K*KT candidates
-            const size_t smem = sizeof(float) * ((size_t)4 * KT * sk + (size_t)4 * ta.Q + (size_t)8 * ta.ncand_pad);
+            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.Q + (size_t)8 * ta.ncand_pad);
+            NODEY_REQUIRE(KT * sk * 4 / CH <= 2048, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
             void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
                                             : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);
             NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -405,8 +405,20 @@ namespace infra
 				const auto data = node_data.find(id);
 				upload += graph.nodes.at(id).processor->upload_bytes(data == node_data.end() ? no_data : *data->second);
 			}
-		int wave_size = upload >= (1u << 30) ? 64 : 1 << 30;
-		if (const char* env = getenv("NODEY_WAVE")) wave_size = std::max(1, atoi(env));
+		// Uploads are faster than compute per track, so only the FIRST wave's upload is exposed: keep it
+		// small (32 source pins), then grow (96, 128, then 256 each) so that the batched kernels of the later
+		// waves run at full efficiency.  NODEY_WAVE=n forces uniform waves of n pins.
+		const bool pipelined = upload >= (1u << 30);
+		int uniform = 0;
+		if (const char* env = getenv("NODEY_WAVE")) uniform = std::max(1, atoi(env));
+		const auto wave_of_pin = [&](int position) {
+			if (uniform > 0) return position / uniform;
+			if (!pipelined) return 0;
+			if (position < 32) return 0;
+			if (position < 128) return 1;
+			if (position < 256) return 2;
+			return 3 + (position - 256) / 256;
+		};
 		std::map<Id_t, int> pin_position;     // output pin -> index in its node's attribute order
 		for (const auto& [id, node] : graph.nodes)
 		{
@@ -428,7 +440,7 @@ namespace infra
 					for (const Id_t from_pin : in->second)
 					{
 						const Id_t producer = graph.pins.at(from_pin).parent;
-						wave = std::max(wave, sources.contains(producer) ? pin_position.at(from_pin) / wave_size : node_wave.at(producer));
+						wave = std::max(wave, sources.contains(producer) ? wave_of_pin(pin_position.at(from_pin)) : node_wave.at(producer));
 					}
 				node_wave[id] = wave;
 			}
