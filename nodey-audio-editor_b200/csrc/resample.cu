@@ -179,6 +179,12 @@ struct TileArgs {
     long long n_tiles;
 };
 
+// fast staging test: the whole tile lies inside the real input (no mirror / reflection / zero fill)
+__device__ __forceinline__ bool tile_interior(const SrcDesc& s, long long in0, int frames)
+{
+    return in0 >= 0 && in0 + frames <= s.n;
+}
+
 template <int CH>
 __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
                                                             const __grid_constant__ TileArgs a)
@@ -203,11 +209,17 @@ __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ 
 
         for (int inp = 0; inp < a.nin; inp++) {
             __syncthreads();   // previous use of s_in (and of the staging rows on a new tile) is over
-            const SrcDesc s = a.src[inp];
+            const SrcDesc& s = a.src[inp];
             if (k0 < a.out_len[inp]) {
                 if (CH == 2) {
                     float2* dst = reinterpret_cast<float2*>(s_in);
-                    for (int f = tid; f < a.in_tile; f += nthr) dst[f] = src_frame(s, in0 + f);
+                    if (s.fmt == NODEY_FMT_FLT && tile_interior(s, in0, a.in_tile)) {
+                        // interior tile of a packed float source: plain coalesced copy, no per-frame edge logic
+                        const float2* src = reinterpret_cast<const float2*>(s.p0) + in0;
+                        for (int f = tid; f < a.in_tile; f += nthr) dst[f] = __ldg(src + f);
+                    } else {
+                        for (int f = tid; f < a.in_tile; f += nthr) dst[f] = src_frame(s, in0 + f);
+                    }
                 } else {
                     for (int f = tid; f < a.in_tile; f += nthr) s_in[f] = src_frame(s, in0 + f).x;
                 }
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ 
                     const int base = lane * a.D + s_gs[q];
                     if (CH == 2) {
                         const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
+#pragma unroll 4
                         for (int m = 0; m < a.wmax; m++) {
                             const float2 x = x2[m];
                             const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
@@ -241,6 +254,7 @@ __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ 
                         }
                     } else {
                         const float* x1 = s_in + base;
+#pragma unroll 4
                         for (int m = 0; m < a.wmax; m++) {
                             const float x = x1[m];
                             const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
