@@ -208,6 +208,9 @@ int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int 
 /* Test hook: cluster size of the WSOLA offsets kernel (thread-block cluster of 1, 2 or 4 CTAs per track;
  * 0 = automatic: the largest that keeps tracks * cluster * 2 <= SM count). */
 int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster);
+/* Test hook: 1 = run cross-fade, AA FIR and cubic transposer as separate kernels even where the fused
+ * tail kernel applies (stereo, TDStretch-first order). */
+int nodey_soundtouch_set_unfused(nodey_soundtouch* s, int unfused);
 int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                          int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                          int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);

@@ -544,6 +544,121 @@ __global__ void __launch_bounds__(256) cubic_kernel(const __grid_constant__ Cubi
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused tail of the TDStretch-first order (rate > 1, stereo): cross-fade + sequence copy -> AA FIR ->
+// cubic transposer in one kernel.  A CTA owns 2040 FIR outputs (computes 2048: the cubic kernel needs
+// three frames beyond its last read position): it assembles the TDStretch output it needs straight
+// from the node's input and the offset trace into the swizzled shared tile, runs the sliding-window
+// FIR, parks the filtered frames in shared memory and interpolates every output whose read position
+// falls into the tile.  Same rounding sequence as the three separate kernels; their two intermediate
+// streams (2 x 8 B per frame, written and read) never touch HBM.
+// ---------------------------------------------------------------------------------------------
+struct PostArgs {
+    View in;
+    const long long* pos; const int* offs; long long offs_stride;
+    const float* fade;
+    int nseq, overlap, seek_window, prefill;
+    long long l1;               // TDStretch output frames
+    float h[kAaLen];
+    unsigned long long R; int e;
+    float* out; long long out_stride; long long count;     // final frames to write
+};
+
+constexpr int kPostStride = kFirTileS - 8;        // FIR outputs a tile contributes to the cubic stage
+
+__global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_constant__ PostArgs a)
+{
+    __shared__ __align__(16) float4 tile[kFirChunks];
+    __shared__ float2 filt[kFirTileS + kFirTileS / 8];     // one pad slot per 8 frames: thread-strided stores stay 2-way
+    const long long track = blockIdx.y;
+    const float* base = a.in.p + track * a.in.stride;
+    const int* offs = a.offs + track * a.offs_stride;
+    float* out = a.out + track * a.out_stride;
+    const int ovl = a.overlap, temp = a.seek_window - 2 * ovl, hop = a.seek_window - ovl;
+
+    // TDStretch output frame o (0 <= o < l1), assembled on the fly (tds_assemble_kernel's arithmetic)
+    const auto tds_frame = [&](long long o) -> float2 {
+        if (o < 0 || o >= a.l1) return make_float2(0.f, 0.f);
+        if (o < temp) return view_frame2<2>(a.in, base, a.pos[0] + o);
+        const long long o2 = o - temp;
+        const int i = 1 + (int)(o2 / hop);
+        const int k = (int)(o2 - (long long)(i - 1) * hop);
+        const long long src = a.pos[i] + offs[i - 1];
+        const float2 x = view_frame2<2>(a.in, base, src + k);
+        if (k >= ovl) return x;
+        const long long mid = (i == 1) ? a.pos[0] + temp : a.pos[i - 1] + offs[i - 2] + ovl + temp;
+        const float2 m = view_frame2<2>(a.in, base, mid + k);
+        const float f1 = a.fade[k], f2 = a.fade[ovl + k];
+        return make_float2(__fadd_rn(__fmul_rn(x.x, f1), __fmul_rn(m.x, f2)), __fadd_rn(__fmul_rn(x.y, f1), __fmul_rn(m.y, f2)));
+    };
+
+    // tiles until the last cubic read position is covered
+    for (long long t = blockIdx.x;; t += gridDim.x) {
+        const long long n0 = t * kPostStride;
+        // cubic outputs whose read position lies in [n0, n0 + kPostStride): i in [i_lo, i_hi)
+        long long i_lo = (long long)((((unsigned __int128)n0 << a.e) + a.R - 1) / a.R);
+        long long i_hi = (long long)((((unsigned __int128)(n0 + kPostStride) << a.e) + a.R - 1) / a.R);
+        if (i_lo >= a.count) break;
+        if (i_hi > a.count) i_hi = a.count;
+        __syncthreads();
+        for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
+            const float2 f0 = tds_frame(n0 + 2 * c - a.prefill), f1 = tds_frame(n0 + 2 * c + 1 - a.prefill);
+            tile[fir_chunk(c)] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        }
+        __syncthreads();
+        {
+            float e0[kFirS], e1[kFirS], o0[kFirS], o1[kFirS];
+#pragma unroll
+            for (int r = 0; r < kFirS; r++) { e0[r] = e1[r] = o0[r] = o1[r] = 0.f; }
+            float4 w[5];
+            const int c0 = threadIdx.x * (kFirS / 2);
+#pragma unroll
+            for (int k = 0; k < 5; k++) w[k] = tile[fir_chunk(c0 + k)];
+#pragma unroll
+            for (int step = 0; step < kAaLen / 2; step++) {
+                const float h0 = a.h[2 * step], h1 = a.h[2 * step + 1];
+#pragma unroll
+                for (int r = 0; r < kFirS; r++) {
+                    const float4 ce = w[(step + r / 2) % 5], co = w[(step + (r + 1) / 2) % 5];
+                    const float xe0 = (r & 1) ? ce.z : ce.x, xe1 = (r & 1) ? ce.w : ce.y;
+                    const float xo0 = ((r + 1) & 1) ? co.z : co.x, xo1 = ((r + 1) & 1) ? co.w : co.y;
+                    e0[r] = __fadd_rn(e0[r], __fmul_rn(xe0, h0));
+                    e1[r] = __fadd_rn(e1[r], __fmul_rn(xe1, h0));
+                    o0[r] = __fadd_rn(o0[r], __fmul_rn(xo0, h1));
+                    o1[r] = __fadd_rn(o1[r], __fmul_rn(xo1, h1));
+                }
+                if (step + 1 < kAaLen / 2) w[step % 5] = tile[fir_chunk(c0 + step + 5)];
+            }
+            // park the filtered frames (frame q of the tile lives at q + q/8)
+#pragma unroll
+            for (int r = 0; r < kFirS; r++)
+                filt[threadIdx.x * (kFirS + 1) + r] = make_float2(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]));
+        }
+        __syncthreads();
+        // cubic transposer over the tile (InterpolateCubic::transposeStereo)
+        const double inv = 1.0 / (double)(1ull << a.e);
+        for (long long i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const unsigned long long lo = (unsigned long long)i * a.R, hi = __umul64hi((unsigned long long)i, a.R);
+            const long long P = (long long)((lo >> a.e) | (a.e ? (hi << (64 - a.e)) : 0ull));
+            const unsigned long long fb = lo & ((1ull << a.e) - 1ull);
+            const float x2 = (float)((double)fb * inv);
+            const float x1 = __fmul_rn(x2, x2);
+            const float x0 = __fmul_rn(x1, x2);
+            const float y0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), __fmul_rn(1.0f, x1)), __fmul_rn(-0.5f, x2)), __fmul_rn(0.0f, 1.0f));
+            const float y1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(1.0f, 1.0f));
+            const float y2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2)), __fmul_rn(0.0f, 1.0f));
+            const float y3 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(0.0f, 1.0f));
+            const int q = (int)(P - n0);
+            const auto at = [&](int f) { return filt[f + (f >> 3)]; };
+            const float2 p0 = at(q), p1 = at(q + 1), p2 = at(q + 2), p3 = at(q + 3);
+            float2 o;
+            o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.x), __fmul_rn(y1, p1.x)), __fmul_rn(y2, p2.x)), __fmul_rn(y3, p3.x));
+            o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.y), __fmul_rn(y1, p1.y)), __fmul_rn(y2, p2.y)), __fmul_rn(y3, p3.y));
+            reinterpret_cast<float2*>(out)[i] = o;
+        }
+    }
+}
+
 }  // namespace nodey
 
 using namespace nodey;
@@ -560,6 +675,7 @@ struct nodey_soundtouch {
     unsigned long long R = 0; int e = 0;       // rate = R * 2^-e exactly
     int prefill = 0;                           // silent frames in front of the RateTransposer input
     int force_cluster = 0;                     // test hook: 0 = automatic cluster size for the offsets kernel
+    int force_unfused = 0;                     // test hook: separate assemble / FIR / cubic kernels
     float aa[kAaLen];
     float* d_fade = nullptr;
     // sequence start positions (prefix-stable in the input length): grown on demand
@@ -746,6 +862,14 @@ int nodey_soundtouch_create(nodey_soundtouch** out, int sample_rate, int channel
     return NODEY_OK;
 }
 
+/* test hook: 1 = run cross-fade, FIR and cubic stage as separate kernels even where the fused one applies */
+int nodey_soundtouch_set_unfused(nodey_soundtouch* s, int unfused)
+{
+    NODEY_REQUIRE(s, NODEY_E_INVALID, "nodey_soundtouch_set_unfused: null handle");
+    s->force_unfused = unfused ? 1 : 0;
+    return NODEY_OK;
+}
+
 /* test hook: force the cluster size (1, 2 or 4; 0 = automatic) of the offsets kernel */
 int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster)
 {
@@ -836,7 +960,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     float* b1 = ws;
     float* b2 = ws + s1 * ntracks;
 
-    auto run_tds = [&](View vin, float* dst, long long dst_stride, long long dst_cap) -> int {
+    auto run_offsets = [&](View vin) -> int {
         TdsArgs ta;
         ta.in = vin; ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
@@ -874,6 +998,11 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             }
             NODEY_LAUNCH_OK();
         }
+        return NODEY_OK;
+    };
+    auto run_tds = [&](View vin, float* dst, long long dst_stride, long long dst_cap) -> int {
+        const int rc0 = run_offsets(vin);
+        if (rc0 != NODEY_OK) return rc0;
         AsmArgs aa;
         aa.in = vin; aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = s->d_pos;
         aa.offs = d_offs; aa.offs_stride = offs_stride; aa.fade = s->d_fade; aa.nseq = (int)nseq;
@@ -908,7 +1037,23 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     };
 
     int rc = NODEY_OK;
-    if (s->td_first) {
+    if (s->td_first && CH == 2 && !s->force_unfused) {
+        // offsets, then the fused assemble + FIR + cubic tail
+        View v0{in, in_frames, 0, in_stride};
+        rc = run_offsets(v0);
+        if (rc == NODEY_OK) {
+            PostArgs pa;
+            pa.in = v0; pa.pos = s->d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
+            pa.nseq = (int)nseq; pa.overlap = s->overlap; pa.seek_window = s->seek_window; pa.prefill = s->prefill; pa.l1 = L.l1;
+            memcpy(pa.h, s->aa, sizeof(pa.h));
+            pa.R = s->R; pa.e = s->e; pa.out = out; pa.out_stride = out_stride; pa.count = out_frames;
+            const long long tiles = (L.l2 + kPostStride - 1) / kPostStride + 1;
+            const long long cap = (long long)sm_count() * 4;
+            dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)ntracks);
+            NODEY_LAUNCH("st_post_kernel", st, st_post_kernel<<<grid, kFirThreads, 0, st>>>(pa));
+            NODEY_LAUNCH_OK();
+        }
+    } else if (s->td_first) {
         View v0{in, in_frames, 0, in_stride};
         rc = run_tds(v0, b1, s1, L.l1);
         View v1{b1, L.l1, s->prefill, s1};

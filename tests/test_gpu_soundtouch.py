@@ -70,6 +70,23 @@ def test_soundtouch_cluster_sizes(nd, orc, cluster, cfg):
         assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t}")
 
 
+@pytest.mark.parametrize("cfg", [(48000, 1.0, 3.0, None), (48000, 1.25, None, True), (44100, 1.7, None, False), (8000, 1.0, 11.0, None)])
+def test_soundtouch_fused_and_unfused_tails_agree(nd, orc, cfg):
+    """stereo, TDStretch-first: the fused cross-fade + FIR + cubic kernel and the three separate kernels"""
+    sr, rate, st_, keep = cfg
+    pitch = orc.pitch_node_factor(st_) if st_ is not None else orc.velocity_node_pitch(rate, keep)
+    n = sr * 3 + 5
+    x = orc.synth_f32(n, 2, sr, 8)
+    ref, _, info = orc.soundtouch(x, sr, rate, pitch, 1152)
+    assert info.tdstretch_first == 1
+    st = nd.SoundTouch(sr, 2, rate, pitch)
+    fused = st.run(to_dev(x)).cpu().numpy()
+    st.set_unfused(True)
+    unfused = st.run(to_dev(x)).cpu().numpy()
+    assert_bit_equal(fused, ref, "fused tail")
+    assert_bit_equal(unfused, ref, "unfused tail")
+
+
 def test_soundtouch_batch_and_chunking(nd, orc):
     sr, n = 48000, 48000 * 2
     xs = np.stack([orc.synth_f32(n, 2, sr, t) for t in range(5)])
