@@ -566,6 +566,25 @@ struct PostArgs {
 
 constexpr int kPostStride = kFirTileS - 8;        // FIR outputs a tile contributes to the cubic stage
 
+// read position of cubic output i: floor(i * R / 2^e)
+__device__ __forceinline__ long long cubic_pos(unsigned long long i, unsigned long long R, int e)
+{
+    const unsigned long long lo = i * R, hi = __umul64hi(i, R);
+    return (long long)((lo >> e) | (e ? (hi << (64 - e)) : 0ull));
+}
+
+// smallest i with cubic_pos(i) >= n, i.e. ceil(n * 2^e / R): double estimate, exact correction (a 128-bit
+// division would be a several-hundred-instruction software loop)
+__device__ __forceinline__ long long cubic_first_at(long long n, unsigned long long R, int e, double inv_rate)
+{
+    if (n <= 0) return 0;
+    long long i = (long long)((double)n * inv_rate);
+    if (i < 0) i = 0;
+    while (cubic_pos((unsigned long long)i, R, e) < n) i++;
+    while (i > 0 && cubic_pos((unsigned long long)(i - 1), R, e) >= n) i--;
+    return i;
+}
+
 __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_constant__ PostArgs a)
 {
     __shared__ __align__(16) float4 tile[kFirChunks];
@@ -576,34 +595,95 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
     float* out = a.out + track * a.out_stride;
     const int ovl = a.overlap, temp = a.seek_window - 2 * ovl, hop = a.seek_window - ovl;
 
-    // TDStretch output frame o (0 <= o < l1), assembled on the fly (tds_assemble_kernel's arithmetic)
-    const auto tds_frame = [&](long long o) -> float2 {
+    // TDStretch output frame o (0 <= o < l1): position k of a sequence whose input source (src) and
+    // cross-fade partner (mid) positions are given; seq0 = first sequence (plain copy from src)
+    const auto tds_frame = [&](long long o, bool seq0, long long src, long long mid, int k) -> float2 {
         if (o < 0 || o >= a.l1) return make_float2(0.f, 0.f);
-        if (o < temp) return view_frame2<2>(a.in, base, a.pos[0] + o);
-        const long long o2 = o - temp;
-        const int i = 1 + (int)(o2 / hop);
-        const int k = (int)(o2 - (long long)(i - 1) * hop);
-        const long long src = a.pos[i] + offs[i - 1];
         const float2 x = view_frame2<2>(a.in, base, src + k);
-        if (k >= ovl) return x;
-        const long long mid = (i == 1) ? a.pos[0] + temp : a.pos[i - 1] + offs[i - 2] + ovl + temp;
+        if (seq0 || k >= ovl) return x;
         const float2 m = view_frame2<2>(a.in, base, mid + k);
         const float f1 = a.fade[k], f2 = a.fade[ovl + k];
         return make_float2(__fadd_rn(__fmul_rn(x.x, f1), __fmul_rn(m.x, f2)), __fadd_rn(__fmul_rn(x.y, f1), __fmul_rn(m.y, f2)));
     };
+    // source / partner positions of sequence i (i >= 1); sequence 0 copies from pos[0]
+    const auto seq_src = [&](int i) { return i < a.nseq ? a.pos[i] + offs[i - 1] : 0ll; };
+    const auto seq_mid = [&](int i) { return i >= a.nseq ? 0ll : (i == 1 ? a.pos[0] + temp : a.pos[i - 1] + offs[i - 2] + ovl + temp); };
 
+    const double inv_rate = (double)(1ull << a.e) / (double)a.R;
     // tiles until the last cubic read position is covered
     for (long long t = blockIdx.x;; t += gridDim.x) {
         const long long n0 = t * kPostStride;
         // cubic outputs whose read position lies in [n0, n0 + kPostStride): i in [i_lo, i_hi)
-        long long i_lo = (long long)((((unsigned __int128)n0 << a.e) + a.R - 1) / a.R);
-        long long i_hi = (long long)((((unsigned __int128)(n0 + kPostStride) << a.e) + a.R - 1) / a.R);
+        long long i_lo = cubic_first_at(n0, a.R, a.e, inv_rate);
+        long long i_hi = cubic_first_at(n0 + kPostStride, a.R, a.e, inv_rate);
         if (i_lo >= a.count) break;
         if (i_hi > a.count) i_hi = a.count;
         __syncthreads();
-        for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
-            const float2 f0 = tds_frame(n0 + 2 * c - a.prefill), f1 = tds_frame(n0 + 2 * c + 1 - a.prefill);
-            tile[fir_chunk(c)] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        {
+            // sequence / position of the tile's first frame: one division per tile; the tile spans at most
+            // kMaxSeq sequences whose source positions are fetched once (generic stepping beyond that)
+            constexpr int kMaxSeq = 3;
+            const long long o_first = n0 - a.prefill;
+            int i_first = 0; long long k_first = o_first;                   // inside sequence 0 (or before the stream)
+            if (o_first >= temp) { const long long o2 = o_first - temp; i_first = 1 + (int)(o2 / hop); k_first = o2 - (long long)(i_first - 1) * hop; }
+            long long src_j[kMaxSeq], mid_j[kMaxSeq];
+            const int i_base = i_first > 0 ? i_first : 1;
+#pragma unroll
+            for (int j = 0; j < kMaxSeq; j++) { src_j[j] = seq_src(i_base + j); mid_j[j] = seq_mid(i_base + j); }
+            const long long pos0 = a.pos[0];
+            // interior tile: every frame it can touch lies inside the real input and inside sequences >= 1 that
+            // were fetched above -> no bounds checks, 32-bit stepping
+            const long long o_last = o_first + 2 * kFirChunks - 1;
+            const long long reach = (long long)hop + 2 * kFirChunks + ovl;
+            bool interior = i_first >= 1 && o_last < a.l1 && i_first + kMaxSeq - 1 < a.nseq && 2 * kFirChunks + k_first < (long long)kMaxSeq * hop;
+#pragma unroll
+            for (int j = 0; j < kMaxSeq; j++)
+                interior = interior && src_j[j] - a.in.prefix >= 0 && src_j[j] - a.in.prefix + reach <= a.in.n
+                                    && mid_j[j] - a.in.prefix >= 0 && mid_j[j] - a.in.prefix + ovl <= a.in.n;
+            if (interior) {
+                const float2* b2 = reinterpret_cast<const float2*>(base) - a.in.prefix;
+                const int kf = (int)k_first;
+                for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
+                    float2 f[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        int k = kf + 2 * c + u, j = 0;
+                        if (k >= hop) { k -= hop; j = 1; }
+                        if (k >= hop) { k -= hop; j = 2; }
+                        const long long src = j == 0 ? src_j[0] : (j == 1 ? src_j[1] : src_j[2]);
+                        float2 x = __ldg(b2 + src + k);
+                        if (k < ovl) {
+                            const long long mid = j == 0 ? mid_j[0] : (j == 1 ? mid_j[1] : mid_j[2]);
+                            const float2 m = __ldg(b2 + mid + k);
+                            const float f1 = a.fade[k], f2 = a.fade[ovl + k];
+                            x = make_float2(__fadd_rn(__fmul_rn(x.x, f1), __fmul_rn(m.x, f2)), __fadd_rn(__fmul_rn(x.y, f1), __fmul_rn(m.y, f2)));
+                        }
+                        f[u] = x;
+                    }
+                    tile[fir_chunk(c)] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+                }
+            } else
+            for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
+                float2 f[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const long long o = o_first + 2 * c + u;
+                    int i = i_first; long long k = k_first + 2 * c + u;
+                    if (i == 0 && o >= temp) { i = 1; k = o - temp; }
+                    while (i > 0 && k >= hop) { k -= hop; i++; }
+                    if (i == 0) f[u] = tds_frame(o, true, pos0, 0, (int)(o < 0 ? 0 : o));
+                    else {
+                        const int j = i - i_base;
+                        long long src, mid;
+                        if (j == 0) { src = src_j[0]; mid = mid_j[0]; }
+                        else if (j == 1) { src = src_j[1]; mid = mid_j[1]; }
+                        else if (j == 2) { src = src_j[2]; mid = mid_j[2]; }
+                        else { src = seq_src(i); mid = seq_mid(i); }
+                        f[u] = tds_frame(o, false, src, mid, (int)k);
+                    }
+                }
+                tile[fir_chunk(c)] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+            }
         }
         __syncthreads();
         {
@@ -638,8 +718,8 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
         // cubic transposer over the tile (InterpolateCubic::transposeStereo)
         const double inv = 1.0 / (double)(1ull << a.e);
         for (long long i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-            const unsigned long long lo = (unsigned long long)i * a.R, hi = __umul64hi((unsigned long long)i, a.R);
-            const long long P = (long long)((lo >> a.e) | (a.e ? (hi << (64 - a.e)) : 0ull));
+            const unsigned long long lo = (unsigned long long)i * a.R;
+            const long long P = cubic_pos((unsigned long long)i, a.R, a.e);
             const unsigned long long fb = lo & ((1ull << a.e) - 1ull);
             const float x2 = (float)((double)fb * inv);
             const float x1 = __fmul_rn(x2, x2);
