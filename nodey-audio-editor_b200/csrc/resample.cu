@@ -524,9 +524,11 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
     if (grid < 1) grid = 1;
     if (ch == 2) {
         NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         NODEY_LAUNCH("resample_tile_kernel", st, resample_tile_kernel<2><<<grid, threads, smem, st>>>(out_l, out_r, a));
     } else {
         NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NODEY_CUDA_OK(cudaFuncSetAttribute(resample_tile_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         NODEY_LAUNCH("resample_tile_kernel", st, resample_tile_kernel<1><<<grid, threads, smem, st>>>(out_l, out_r, a));
     }
     NODEY_LAUNCH_OK();
