@@ -146,9 +146,7 @@ def kernel_algo_bytes(name, r, batch):
         "resample_tile_kernel": r.n_in * f8 + r.total1 * f8,                     # one track: in + out planes
         "extract_planar_kernel": r.total1 * f8 * 2,
         "tds_offsets_kernel": None,                                               # filled per node below
-        "tds_assemble_kernel": None,
-        "aa_fir_kernel": None,
-        "cubic_kernel": None,
+        "st_post_kernel": None,
         "gain_f32_kernel": r.m2 * f8 * 2,
         "to_fltp_kernel": r.m2 * f8 * 2,
         "mix_kernel": 16 * r.m2 * f8 + r.total2 * f8,
@@ -157,10 +155,15 @@ def kernel_algo_bytes(name, r, batch):
     # SoundTouch kernels run once per node per sub-batch; both nodes read ~their input and write ~their output
     st_in = (r.total1 + r.m1) / 2.0
     st_out = (r.m1 + r.m2) / 2.0
-    table["tds_offsets_kernel"] = batch * st_in * f8                              # reads every input frame once; output is the trace
-    table["tds_assemble_kernel"] = batch * (st_in + st_out) * f8 / 1.0
-    table["aa_fir_kernel"] = batch * 2 * st_out * f8
-    table["cubic_kernel"] = batch * 2 * st_out * f8
+    # the search reads, per sequence, the window (seek_length + overlap frames) and the mid buffer (overlap frames);
+    # the frames between windows are never touched by this kernel.  Mean over the pitch and the tempo node.
+    per_track = 0.0
+    for st, n_in in ((r.st_pitch, r.total1), (r.st_tempo, r.m1)):
+        info = st.info()
+        _, nseq = st.out_frames(n_in, r.frame_size)
+        per_track += 0.5 * max(nseq - 1, 0) * (info["seek_length"] + 2 * info["overlap"]) * f8
+    table["tds_offsets_kernel"] = batch * per_track
+    table["st_post_kernel"] = batch * (st_in + st_out) * f8                       # fused cross-fade + FIR + cubic: in once, out once
     return table.get(name)
 
 

@@ -1047,9 +1047,11 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         ta.Q = 4 * (CH * s->overlap / 16);
         if (nseq > 1) {
             // cluster size: spread one track over CL SMs while the batch leaves SMs idle
-            // two CTAs fit per SM: grow the cluster while every CTA of the batch can still be resident
+            // cluster size from the measured batch sweep (tools/st_sweep.py, 256-thread CTAs, two per SM):
+            // 4 CTAs per track while they all fit at two per SM, 2 up to about 200 tracks, 1 beyond
             int CL = 1;
-            while (CL < 4 && (long long)ntracks * CL * 2 <= 2ll * sm_count()) CL *= 2;
+            if ((long long)ntracks * 4 <= 2ll * sm_count()) CL = 4;
+            else if ((long long)ntracks * 2 <= 400ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
             const int KT = CL >= 4 ? 4 : 8;
             const int K = 4 / CH;
