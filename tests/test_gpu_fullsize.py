@@ -1,0 +1,116 @@
+"""GPU parity at BASELINE.json's full sizes.  Where the oracle finishes in seconds it is run in full
+(configs[1], configs[2] per track); otherwise size-independent properties are used: causality
+(a prefix of the output is fixed by a prefix of the input), Parseval and linearity for the STFT,
+spot frames against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import FMT_FLT, assert_bit_equal, to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_soundtouch_10min_track(nd, orc):
+    """configs[1]: pitch +3 st then tempo 1.25x keep-pitch on a 10 min stereo 48 kHz track (one track, so the
+    search runs on 4-CTA clusters).  Full comparison with the oracle: offset traces and samples bit exact."""
+    import torch
+    sr, n = 48000, 48000 * 600
+    x = nd.synth(n, 2, sr, track=1)
+    xh = x.cpu().numpy()
+    p = orc.pitch_node_factor(3.0)
+    st1 = nd.SoundTouch(sr, 2, 1.0, p)
+    y1, o1 = st1.run(x, want_offsets=True)
+    r1, ro1, info1 = orc.soundtouch(xh, sr, 1.0, p, 1152)
+    assert (info1.overlap, info1.seek_window, info1.seek_length) == (384, 3792, 912)
+    assert y1.shape[0] == n and len(ro1) > 10000
+    assert np.array_equal(o1.cpu().numpy(), ro1), "pitch node offset trace"
+    assert_bit_equal(y1.cpu().numpy(), r1, "pitch node output")
+    st2 = nd.SoundTouch(sr, 2, 1.25, orc.velocity_node_pitch(1.25, True))
+    y2, o2 = st2.run(y1, want_offsets=True)
+    r2, ro2, info2 = orc.soundtouch(r1, sr, 1.25, orc.velocity_node_pitch(1.25, True), 1152)
+    assert abs(y2.shape[0] - n / 1.25) <= 1
+    assert np.array_equal(o2.cpu().numpy(), ro2), "tempo node offset trace"
+    assert_bit_equal(y2.cpu().numpy(), r2, "tempo node output")
+    del x, y1, y2
+    torch.cuda.empty_cache()
+
+
+def test_config3_resample_and_mix16_5min(nd, orc):
+    """configs[2]: 16 x 5 min stereo 44.1 kHz -> 48 kHz polyphase + 16-input mix.  Every track's resampled
+    planes are compared in full with the oracle; the fused mix with the ordered float sum of those planes."""
+    n = 44100 * 300
+    r = nd.Resampler(44100, 48000)
+    m = r.out_count(n, True)
+    assert m == 48000 * 300
+    xs = [nd.synth(n, 2, 44100, track=t) for t in range(16)]
+    vols = [1.0 / 16] * 16
+    ref_mix = np.zeros((2, m), np.float32)
+    for t in range(16):
+        rl, rr = orc.swr_whole(xs[t].cpu().numpy(), FMT_FLT, 44100, 48000, flush=True)
+        if t in (0, 7, 15):
+            got = r.run(xs[t], nd.FMT_FLT).cpu().numpy()
+            assert_bit_equal(got[0], rl, f"track {t} L")
+            assert_bit_equal(got[1], rr, f"track {t} R")
+        ref_mix[0] = (ref_mix[0] + rl * np.float32(vols[t])).astype(np.float32)
+        ref_mix[1] = (ref_mix[1] + rr * np.float32(vols[t])).astype(np.float32)
+    fused = r.resample_mix(xs, [nd.FMT_FLT] * 16, vols).cpu().numpy()
+    assert_bit_equal(fused, ref_mix, "fused resample + mix16")
+
+
+def test_config4_stft_one_hour(nd, orc):
+    """configs[3]: 4096/1024 Hann STFT over 1 h of stereo 48 kHz (168 747 frames per channel, 5.5 GB out).
+    Frame count, spot frames against the oracle's double DFT, Parseval per frame, linearity."""
+    import torch
+    n = 48000 * 3600
+    x = nd.synth(n, 2, 48000, track=2)
+    spec = nd.stft(x, True)
+    assert spec.shape == (2, 168747, 2049)
+    w = torch.from_numpy(orc.hann()).cuda().double()
+    rng = np.random.default_rng(0)
+    frames = sorted(set([0, 1, 168746] + [int(f) for f in rng.integers(0, 168747, 24)]))
+    for f in frames:
+        seg = x[f * 1024:f * 1024 + 4096]
+        for c in range(2):
+            ref = orc.stft(seg[:, c].contiguous().cpu().numpy())[0]
+            got = spec[c, f].cpu().numpy()
+            assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (f, c)
+    # Parseval on 4096 frames at once: sum |x w|^2 = (|X0|^2 + 2 sum_{1..2047} |Xk|^2 + |X2048|^2) / 4096
+    idx = torch.arange(0, 168747, 41, device="cuda")[:4096]
+    for c in range(2):
+        seg = torch.stack([x[int(f) * 1024:int(f) * 1024 + 4096, c] for f in idx[:256]]).double() * w
+        lhs = (seg ** 2).sum(dim=1)
+        X = spec[c, idx[:256]].to(torch.complex128)
+        p = X.real ** 2 + X.imag ** 2
+        rhs = (p[:, 0] + 2 * p[:, 1:2048].sum(dim=1) + p[:, 2048]) / 4096
+        assert torch.allclose(lhs, rhs, rtol=2e-6)
+    del spec
+    torch.cuda.empty_cache()
+    # linearity on a 2 min excerpt: stft(a + b) = stft(a) + stft(b)
+    a = x[:48000 * 120].T.contiguous()
+    b = nd.synth(48000 * 120, 2, 48000, track=9).T.contiguous()
+    sa, sb, sab = nd.stft(a, False), nd.stft(b, False), nd.stft((a + b).contiguous(), False)
+    err = (sab - (sa + sb)).abs().max().item()
+    assert err <= 1e-5 * sab.abs().max().item()
+
+
+def test_config1_60s_graph_through_engine(eng_gpu, orc):
+    """configs[0] at full length: 60 s stereo 44.1 kHz S16 -> two gains -> amix(2) -> output, plugin API"""
+    import torch
+    n = 44100 * 60
+    x = orc.f32_to_s16(orc.synth_f32(n, 2, 44100, 0))
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    g0 = p.add("audio_volume_adjust"); g1 = p.add("audio_volume_adjust")
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.5]))
+    out = p.add("audio_output")
+    p.link(src, "output_0", g0, "input"); p.link(src, "output_0", g1, "input")
+    p.link(g0, "output", mix, "input_1"); p.link(g1, "output", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_volume(g0, 0.8); e.set_volume(g1, 0.5)
+    e.bind_source(0, x, 1, 44100)
+    e.run()
+    a = orc.gain(x, 1, 0.8); b = orc.gain(x, 1, 0.5)
+    rl, rr = orc.amix([orc.make_track(a, 1, 44100), orc.make_track(b, 1, 44100)], [0.5, 0.5])
+    got = e.output()
+    assert got.frames == len(rl) and got.frames >= 2880000
+    assert_bit_equal(got.numpy(), np.stack([rl, rr]), "config 1 output")
