@@ -83,7 +83,8 @@ struct TdsArgs {
     int Q;                     // lane steps = 4 * (CH*overlap/16)
     int tb_per;                // candidate blocks per CTA of the cluster
     int sk;                    // floats per sub-plane
-    int ncand_pad;             // padded candidates per CTA (partial-sum arrays)
+    int ncand_pad;             // padded candidates per CTA (correlation lane sums)
+    int npm;                   // padded start positions per CTA (norm sums)
 };
 
 // partial-sum slot of candidate cc: one word of padding per K*KT candidates makes both the strided
@@ -104,22 +105,27 @@ __device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b)
 // Window = two blocks of KT samples (w[CUR] current, w[CUR^1] next); sample idx = s + k of the
 // window feeds candidate k at step s.  Block b of a thread's stream lives at
 // plane[((OFF + k) % KT) * sk + (OFF + k) / KT + b]: consecutive threads -> consecutive words.
-template <int KT, int OFF, int CUR, int NS>
-__device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&sq)[2][KT], float (&acc)[KT], float (&nrm)[KT],
-                                          const float* __restrict__ xnext, int sk, const float* __restrict__ yq)
+// MODE 0: correlation lane sums only (acc[k] += x * y); MODE 1: norm sums only (acc[k] += x * x).
+// The norm of a candidate does not involve the mid buffer, and candidates of different (lane, class)
+// pairs walk the same squared samples: it is computed once per sample stream (plane) and start
+// position instead of once per (lane, class) -- see tds_offsets_kernel.
+template <int KT, int OFF, int CUR, int NS, int MODE>
+__device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&acc)[KT], const float* __restrict__ xnext, int sk,
+                                          const float* __restrict__ yq)
 {
     constexpr int NXT = CUR ^ 1;
 #pragma unroll
     for (int k = 0; k < KT; k++) {
         const float v = xnext[((OFF + k) % KT) * sk + (OFF + k) / KT];
-        w[NXT][k] = v;
-        sq[NXT][k] = __fmul_rn(v, v);
+        w[NXT][k] = MODE == 0 ? v : __fmul_rn(v, v);
     }
     float y[NS];
+    if (MODE == 0) {
 #pragma unroll
-    for (int s = 0; s < NS; s += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(yq + s);
-        y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
+        for (int s = 0; s < NS; s += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(yq + s);
+            y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
+        }
     }
 #pragma unroll
     for (int s = 0; s < NS; s++) {
@@ -127,37 +133,35 @@ __device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&sq)[2][KT],
         for (int k = 0; k < KT; k++) {
             const int idx = s + k;
             const float x = idx < KT ? w[CUR][idx] : w[NXT][idx - KT];
-            const float x2 = idx < KT ? sq[CUR][idx] : sq[NXT][idx - KT];
-            acc[k] = __fadd_rn(acc[k], __fmul_rn(x, y[s]));
-            nrm[k] = __fadd_rn(nrm[k], x2);
+            acc[k] = __fadd_rn(acc[k], MODE == 0 ? __fmul_rn(x, y[s]) : x);
         }
     }
 }
 
-template <int KT, int OFF>
+template <int KT, int OFF, int MODE>
 __device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int sk, const float* __restrict__ yp, int Q,
-                                              float (&acc)[KT], float (&nrm)[KT])
+                                              float (&acc)[KT])
 {
-    float w[2][KT], sq[2][KT];
+    float w[2][KT];
 #pragma unroll
-    for (int k = 0; k < KT; k++) { acc[k] = 0.f; nrm[k] = 0.f; }
+    for (int k = 0; k < KT; k++) acc[k] = 0.f;
 #pragma unroll
     for (int k = 0; k < KT; k++) {
         const float v = xb[((OFF + k) % KT) * sk + (OFF + k) / KT];
-        w[0][k] = v; sq[0][k] = __fmul_rn(v, v);
+        w[0][k] = MODE == 0 ? v : __fmul_rn(v, v);
     }
     const int NG = Q / KT, tail = Q - NG * KT;      // tail is 0 or 4 (Q is a multiple of 4)
     int G = 0;
     for (; G + 2 <= NG; G += 2) {
-        tds_group<KT, OFF, 0, KT>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
-        tds_group<KT, OFF, 1, KT>(w, sq, acc, nrm, xb + G + 2, sk, yp + (G + 1) * KT);
+        tds_group<KT, OFF, 0, KT, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
+        tds_group<KT, OFF, 1, KT, MODE>(w, acc, xb + G + 2, sk, yp + (G + 1) * KT);
     }
     if (G < NG) {
-        tds_group<KT, OFF, 0, KT>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+        tds_group<KT, OFF, 0, KT, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
         G++;
-        if (tail) tds_group<KT, OFF, 1, 4>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+        if (tail) tds_group<KT, OFF, 1, 4, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
     } else if (tail) {
-        tds_group<KT, OFF, 0, 4>(w, sq, acc, nrm, xb + G + 1, sk, yp + G * KT);
+        tds_group<KT, OFF, 0, 4, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
     }
 }
 
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     float* X0 = smem;                               // 2 x [4 planes][KT sub-planes][sk] (double buffered)
     float* Y = X0 + 8 * plane_len;                  // [4][Q]
     float* PS = Y + 4 * a.Q;                        // [4][ncand_pad] correlation lane sums
-    float* PN = PS + 4 * a.ncand_pad;               // [4][ncand_pad] norm lane sums
+    float* PN = PS + 4 * a.ncand_pad;               // [4 planes][npm] norm sums by start position
     __shared__ double red_v[kTdsThreads / 32];
     __shared__ int red_i[kTdsThreads / 32];
     __shared__ double xch_v[2][8];
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     int ntb = tblocks - tb_lo; if (ntb > a.tb_per) ntb = a.tb_per; if (ntb < 0) ntb = 0;
     const int wpc = (ntb + 31) / 32;                 // warps per (lane, class) combo
     const int nunits = 4 * K * wpc;
+    const int wpn = (ntb + 1 + 31) / 32;             // warps per plane for the norm sums (ntb + 1 position blocks)
+    const int nnorm = 4 * wpn;
     const int m_lo = KT * tb_lo;                     // first plane element this CTA stages
     const int f_lo = 4 * m_lo / CH;                  // ... and the first frame
     const int nfr = plane_len * 4 / CH;              // frames covered by the staged planes
@@ -264,22 +270,36 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         if (i + 1 < a.nseq) window_fetch(i + 1);     // in flight during the search below
         __syncthreads();
 
-        // ---- lane sums: thread = (lane l, class kappa, KT consecutive candidates of the class) ----
-        for (int unit = warp; unit < nunits; unit += nwarps) {
-            const int combo = unit / wpc, wsub = unit - combo * wpc;
-            const int l = combo & 3, kappa = combo >> 2;
-            const int tb = wsub * 32 + lane;
-            if (tb < ntb) {
-                const int u0 = CH * kappa + l;
-                const float* xb = X + (u0 & 3) * plane_len + tb;
-                const float* yp = Y + l * Q;
-                float acc[KT], nrm[KT];
-                if (u0 >> 2) tds_lane_sums<KT, 1>(xb, a.sk, yp, Q, acc, nrm);
-                else tds_lane_sums<KT, 0>(xb, a.sk, yp, Q, acc, nrm);
+        // ---- lane sums.  Correlation units: thread = (lane l, class kappa, KT consecutive candidates of the class).
+        //      Norm units: thread = (plane rho, KT consecutive start positions): N[rho][m] = sum_q X_rho[m + q]^2,
+        //      which is the norm lane sum of every (l, kappa, t) with plane (CH*kappa + l) & 3 and
+        //      t + ((CH*kappa + l) >> 2) == m -- same samples, same order, computed once. ----
+        for (int unit = warp; unit < nunits + nnorm; unit += nwarps) {
+            if (unit < nunits) {
+                const int combo = unit / wpc, wsub = unit - combo * wpc;
+                const int l = combo & 3, kappa = combo >> 2;
+                const int tb = wsub * 32 + lane;
+                if (tb < ntb) {
+                    const int u0 = CH * kappa + l;
+                    const float* xb = X + (u0 & 3) * plane_len + tb;
+                    const float* yp = Y + l * Q;
+                    float acc[KT];
+                    if (u0 >> 2) tds_lane_sums<KT, 1, 0>(xb, a.sk, yp, Q, acc);
+                    else tds_lane_sums<KT, 0, 0>(xb, a.sk, yp, Q, acc);
 #pragma unroll
-                for (int k = 0; k < KT; k++) {
-                    const int cc = kappa + K * (KT * tb + k);
-                    if (cc < ncand) { PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k]; PN[l * a.ncand_pad + ps_slot<K * KT>(cc)] = nrm[k]; }
+                    for (int k = 0; k < KT; k++) {
+                        const int cc = kappa + K * (KT * tb + k);
+                        if (cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
+                    }
+                }
+            } else {
+                const int v = unit - nunits;
+                const int rho = v / wpn, mb = (v - rho * wpn) * 32 + lane;
+                if (mb <= ntb) {
+                    float nr[KT];
+                    tds_lane_sums<KT, 0, 1>(X + rho * plane_len + mb, a.sk, nullptr, Q, nr);
+#pragma unroll
+                    for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
                 }
             }
         }
@@ -292,7 +312,14 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         for (int cc = tid; cc < ncand; cc += blockDim.x) {
             const int c = c_base + cc, np = a.ncand_pad, sl = ps_slot<K * KT>(cc);
             const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[sl], PS[np + sl]), PS[2 * np + sl]), PS[3 * np + sl]);
-            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(PN[sl], PN[np + sl]), PN[2 * np + sl]), PN[3 * np + sl]);
+            const int kap = cc % K, trel = cc / K;
+            float nl[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                const int u0 = CH * kap + l;
+                nl[l] = PN[(u0 & 3) * a.npm + ps_slot<KT>(trel + (u0 >> 2))];
+            }
+            const float nr = __fadd_rn(__fadd_rn(__fadd_rn(nl[0], nl[1]), nl[2]), nl[3]);
             const double dn = (double)nr;
             double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
             const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
@@ -1061,7 +1088,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             while ((sk & 7) != 4) sk++;
             ta.sk = sk;
             ta.ncand_pad = (K * KT * ta.tb_per + ta.tb_per + 4 + 3) & ~3;      // + one pad word per K*KT candidates
-            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.Q + (size_t)8 * ta.ncand_pad);
+            ta.npm = (KT * (ta.tb_per + 1) + ta.tb_per + 1 + 4 + 3) & ~3;
+            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.Q + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm);
             NODEY_REQUIRE(KT * sk * 4 / CH <= 2048, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
             void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
                                             : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);
