@@ -316,14 +316,24 @@ def run_ours(args):
 
         sizes = [0, 0]
 
+        split = [0.0, 0.0]
+
         def step_e2e():
+            t0 = time.perf_counter()
             eng.run()
+            t1 = time.perf_counter()
             f, se = finish(want_host=host_buffers)
+            torch.cuda.synchronize()
+            split[0] += t1 - t0; split[1] += time.perf_counter() - t1
             sizes[0], sizes[1] = f, se
 
         for _ in range(2):
             step_e2e()
+        split[0] = split[1] = 0.0
         ms_e2e = timed(step_e2e, args.steps)
+        if rank == 0:
+            print(f"[bench] e2e split per step: engine run {split[0] / args.steps * 1e3:.1f} ms, bus reduce / D2H {split[1] / args.steps * 1e3:.1f} ms",
+                  file=sys.stderr, flush=True)
         e2e = {"value": audio / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": t_local * n_in * 8 * world,
                "d2h_bytes_per_step": sizes[0] * 8 + sizes[1] * 8, "ms_per_step": ms_e2e / args.steps,
                "api": "project JSON -> infra::Graph::deserialize -> infra::Runner::create_and_run (libnodey_host.so, "

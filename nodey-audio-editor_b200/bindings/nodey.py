@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnodey_cuda.so")
+# NODEY_CUDA_LIB: development override (instrumented builds under tools/micro); the default is the in-tree library
+LIB_PATH = os.environ.get("NODEY_CUDA_LIB") or os.path.join(os.path.dirname(_HERE), "libnodey_cuda.so")
 
 FMT_U8, FMT_S16, FMT_S32, FMT_FLT, FMT_DBL, FMT_U8P, FMT_S16P, FMT_S32P, FMT_FLTP, FMT_DBLP = range(10)
 MAX_MIX_INPUTS = 16

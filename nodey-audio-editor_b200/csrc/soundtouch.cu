@@ -85,6 +85,7 @@ struct TdsArgs {
     int sk;                    // floats per sub-plane
     int ncand_pad;             // padded candidates per CTA (correlation lane sums)
     int npm;                   // padded start positions per CTA (norm sums)
+    int vec8;                  // stereo frames are 8-byte aligned in global memory
 };
 
 // partial-sum slot of candidate cc: one word of padding per K*KT candidates makes both the strided
@@ -92,14 +93,13 @@ struct TdsArgs {
 template <int S>
 __device__ __forceinline__ int ps_slot(int cc) { return cc + cc / S; }
 
-struct ArgMax { double v; int i; };
-
-__device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b)
-{
-    // scalar loop semantics: ascending index, replace only on strictly greater -> ties keep lowest index
-    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-    return a;
-}
+#ifdef NODEY_TDS_TIMING
+// development build only (tools/micro/Makefile): clock64 deltas of the phases of one sequence, thread 0 of CTA 0
+__device__ unsigned long long g_tds_phase[8];
+#define TDS_T(k) do { if (timing_on) { const long long now_ = clock64(); tacc[k] += now_ - tprev; tprev = now_; } } while (0)
+#else
+#define TDS_T(k) do { } while (0)
+#endif
 
 // One group of NS lane steps for KT consecutive candidates of one (lane, class) stream.
 // Window = two blocks of KT samples (w[CUR] current, w[CUR^1] next); sample idx = s + k of the
@@ -165,9 +165,43 @@ __device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int 
     }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no registers held while the data is in flight ----
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 4 : 0;                 // src-size 0: nothing is read, the word is zero filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(float* dst_smem, const float* src, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// order-preserving map double -> u64 for the arg-max: NaN lowest (the scalar loop's `>` never picks it), -0 == +0
+__device__ __forceinline__ unsigned long long argmax_key(double v)
+{
+    if (!(v == v)) return 0ull;
+    if (v == 0.0) v = 0.0;
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+
 // grid = ntracks * CL CTAs, launched as clusters of CL: the CTAs of a cluster split one track's
 // candidates (blocks of KT per class) and exchange their local arg-max through distributed
 // shared memory, one cluster barrier per sequence.
+//
+// What is on the per-sequence critical path and what is not (measured with the clock64 phase timers of the
+// NODEY_TDS_TIMING build, tools/tds_phases.py): only the correlation lane sums need the mid buffer, i.e.
+// the previous offset.  Everything else is moved off the chain:
+//   * the search window of sequence i+1 and the REGION the next mid buffer can come from (it starts at
+//     pos_i + overlap + temp + offset_i, offset_i < seek_length) are copied global -> shared with cp.async
+//     while sequence i is searched; the mid buffer is then a shared -> shared gather;
+//   * the norm sums of sequence i+1 (no mid buffer involved) are computed between the arrive and the wait
+//     of the cluster barrier that publishes offset i;
+//   * the position weights 1 - 0.25 t^2 are tabulated once.
 template <int CH, int KT>
 __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
 {
@@ -177,14 +211,19 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
 
     extern __shared__ __align__(16) float smem[];
     constexpr int K = 4 / CH;                       // candidate classes per lane
+    const int L = a.seek_length, ovl = a.overlap, Q = a.Q;
+    const int QP = Q + 8;                           // padded lane row: the de-interleaving stores hit 32 banks
     const int plane_len = KT * a.sk;
+    const int mreg = L + ovl;                       // frames the next mid buffer can come from
     float* X0 = smem;                               // 2 x [4 planes][KT sub-planes][sk] (double buffered)
-    float* Y = X0 + 8 * plane_len;                  // [4][Q]
-    float* PS = Y + 4 * a.Q;                        // [4][ncand_pad] correlation lane sums
+    float* Y = X0 + 8 * plane_len;                  // [4][QP]
+    float* PS = Y + 4 * QP;                         // [4][ncand_pad] correlation lane sums
     float* PN = PS + 4 * a.ncand_pad;               // [4 planes][npm] norm sums by start position
-    __shared__ double red_v[kTdsThreads / 32];
+    float* MR = PN + 4 * a.npm;                     // [mreg * CH] interleaved frames: mid-buffer region
+    double* PW = reinterpret_cast<double*>(MR + ((mreg * CH + 3) & ~3));   // [ncand] position weights
+    __shared__ unsigned long long red_k[kTdsThreads / 32];
     __shared__ int red_i[kTdsThreads / 32];
-    __shared__ double xch_v[2][8];
+    __shared__ unsigned long long xch_k[2][8];
     __shared__ int xch_i[2][8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -192,7 +231,6 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     const float* base = a.in.p + track * a.in.stride;
     int* offs = a.offs + track * a.offs_stride;
 
-    const int L = a.seek_length, ovl = a.overlap, Q = a.Q;
     const int region = L + ovl;                      // frames of the search window
     const int temp = a.seek_window - 2 * ovl;
     const int tcount = (L + K - 1) / K;
@@ -209,40 +247,35 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     const int c_base = K * KT * tb_lo;               // first candidate of this CTA
     int ncand = K * KT * ntb; if (c_base + ncand > L) ncand = L - c_base; if (ncand < 0) ncand = 0;
 
-    long long mid_pos = a.pos[0] + temp;             // first sequence: offset 0, no search
-
-    // The search window of sequence i+1 does not depend on offset i: it is fetched into registers while
-    // sequence i is searched and written to the other half of the double-buffered planes afterwards, so
-    // only the mid buffer (which does depend on the offset) is loaded on the critical path.
-    constexpr int NR = 2048 / kTdsThreads;           // frames (stereo) / samples (mono) per thread, nfr <= 2048
-    float2 pre[NR];
-    const auto window_fetch = [&](int seq) {
-        const long long p0 = a.pos[seq];
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-            const int fr = tid + r * kTdsThreads;
+    // ---- staging (all asynchronous) ----
+    const auto window_copy = [&](int seq, float* Xb) {
+        const long long p0 = a.pos[seq] - a.in.prefix;
+        for (int fr = tid; fr < nfr; fr += kTdsThreads) {
             const int f = f_lo + fr;
-            pre[r] = make_float2(0.f, 0.f);
-            if (fr < nfr && f < region) {
-                if (CH == 2) pre[r] = view_frame2<2>(a.in, base, p0 + f);
-                else pre[r].x = view_sample<1>(a.in, base, p0 + f, 0);
+            const long long g = p0 + f;
+            const bool ok = f < region && g >= 0 && g < a.in.n;
+            const float* src = ok ? base + g * CH : base;
+            if (CH == 2) {
+                const int m = fr >> 1, pl = (fr & 1) * 2;
+                float* d = Xb + pl * plane_len + (m % KT) * a.sk + m / KT;
+                cp_async4(d, src, ok);
+                cp_async4(d + plane_len, src + (ok ? 1 : 0), ok);
+            } else {
+                const int m = fr >> 2;
+                cp_async4(Xb + (fr & 3) * plane_len + (m % KT) * a.sk + m / KT, src, ok);
             }
         }
     };
-    const auto window_store = [&](float* Xb) {
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-            const int fr = tid + r * kTdsThreads;
-            if (fr >= nfr) continue;
+    const auto mid_region_copy = [&](long long first_frame) {
+        const long long p0 = first_frame - a.in.prefix;
+        for (int fr = tid; fr < mreg; fr += kTdsThreads) {
+            const long long g = p0 + fr;
+            const bool ok = g >= 0 && g < a.in.n;
+            const float* src = ok ? base + g * CH : base;
             if (CH == 2) {
-                const int m = fr >> 1, pl = (fr & 1) * 2;
-                const int ph = (m % KT) * a.sk + m / KT;
-                Xb[pl * plane_len + ph] = pre[r].x;
-                Xb[(pl + 1) * plane_len + ph] = pre[r].y;
-            } else {
-                const int m = fr >> 2;
-                Xb[(fr & 3) * plane_len + (m % KT) * a.sk + m / KT] = pre[r].x;
-            }
+                if (a.vec8) cp_async8(MR + 2 * fr, src, ok);
+                else { cp_async4(MR + 2 * fr, src, ok); cp_async4(MR + 2 * fr + 1, src + (ok ? 1 : 0), ok); }
+            } else cp_async4(MR + fr, src, ok);
         }
     };
     const auto l2_prefetch = [&](int seq) {
@@ -254,63 +287,81 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
         }
     };
+    // norm units: thread = (plane rho, KT consecutive start positions): N[rho][m] = sum_q X_rho[m + q]^2, which is
+    // the norm lane sum of every (l, kappa, t) with plane (CH*kappa + l) & 3 and t + ((CH*kappa + l) >> 2) == m --
+    // same samples, same order, computed once.
+    const auto norm_units = [&](const float* X) {
+        for (int v = warp; v < nnorm; v += nwarps) {
+            const int rho = v / wpn, mb = (v - rho * wpn) * 32 + lane;
+            if (mb <= ntb) {
+                float nr[KT];
+                tds_lane_sums<KT, 0, 1>(X + rho * plane_len + mb, a.sk, nullptr, Q, nr);
+#pragma unroll
+                for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
+            }
+        }
+    };
 
-    if (a.nseq > 1) { window_fetch(1); window_store(X0); }
+    if (a.nseq <= 1) return;                         // uniform over the cluster: nobody touches a peer
+
+    // position weights (sequence independent): 1 - 0.25 t^2, t = (2c - L) / L
+    for (int cc = tid; cc < ncand; cc += blockDim.x) {
+        const int c = c_base + cc;
+        const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
+        PW[cc] = __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp));
+    }
+    window_copy(1, X0);
+    mid_region_copy(a.pos[0] + temp);                // first sequence: offset 0, no search
+    cp_async_wait_all();
+    __syncthreads();
+    norm_units(X0);
     int cur = 0;
+    int moff = 0;                                    // offset of the mid buffer inside the staged region
+#ifdef NODEY_TDS_TIMING
+    const bool timing_on = blockIdx.x == 0 && tid == 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#endif
 
     for (int i = 1; i < a.nseq; i++) {
         const long long p0 = a.pos[i];
-        float* X = X0 + cur * 4 * plane_len;
+        const float* X = X0 + cur * 4 * plane_len;
+        // ---- mid buffer: gathered from the staged region, de-interleaved by lane ----
+        for (int j = tid; j < 4 * Q; j += blockDim.x) Y[(j & 3) * QP + (j >> 2)] = MR[moff * CH + j];
+        if (i + 1 < a.nseq) window_copy(i + 1, X0 + (cur ^ 1) * 4 * plane_len);
         l2_prefetch(i + 2);
-        // ---- mid buffer (depends on the previous offset), de-interleaved by lane ----
-        for (int j = tid; j < 4 * Q; j += blockDim.x) {
-            const long long fr = mid_pos + j / CH;
-            Y[(j & 3) * Q + (j >> 2)] = view_sample<CH>(a.in, base, fr, j % CH);
-        }
-        if (i + 1 < a.nseq) window_fetch(i + 1);     // in flight during the search below
+        TDS_T(0);
         __syncthreads();
+        TDS_T(1);
+        if (i + 1 < a.nseq) mid_region_copy(p0 + ovl + temp);     // the region is free again: everybody has gathered
 
-        // ---- lane sums.  Correlation units: thread = (lane l, class kappa, KT consecutive candidates of the class).
-        //      Norm units: thread = (plane rho, KT consecutive start positions): N[rho][m] = sum_q X_rho[m + q]^2,
-        //      which is the norm lane sum of every (l, kappa, t) with plane (CH*kappa + l) & 3 and
-        //      t + ((CH*kappa + l) >> 2) == m -- same samples, same order, computed once. ----
-        for (int unit = warp; unit < nunits + nnorm; unit += nwarps) {
-            if (unit < nunits) {
-                const int combo = unit / wpc, wsub = unit - combo * wpc;
-                const int l = combo & 3, kappa = combo >> 2;
-                const int tb = wsub * 32 + lane;
-                if (tb < ntb) {
-                    const int u0 = CH * kappa + l;
-                    const float* xb = X + (u0 & 3) * plane_len + tb;
-                    const float* yp = Y + l * Q;
-                    float acc[KT];
-                    if (u0 >> 2) tds_lane_sums<KT, 1, 0>(xb, a.sk, yp, Q, acc);
-                    else tds_lane_sums<KT, 0, 0>(xb, a.sk, yp, Q, acc);
+        // ---- correlation lane sums: thread = (lane l, class kappa, KT consecutive candidates of the class) ----
+        for (int unit = warp; unit < nunits; unit += nwarps) {
+            const int combo = unit / wpc, wsub = unit - combo * wpc;
+            const int l = combo & 3, kappa = combo >> 2;
+            const int tb = wsub * 32 + lane;
+            if (tb < ntb) {
+                const int u0 = CH * kappa + l;
+                const float* xb = X + (u0 & 3) * plane_len + tb;
+                const float* yp = Y + l * QP;
+                float acc[KT];
+                if (u0 >> 2) tds_lane_sums<KT, 1, 0>(xb, a.sk, yp, Q, acc);
+                else tds_lane_sums<KT, 0, 0>(xb, a.sk, yp, Q, acc);
 #pragma unroll
-                    for (int k = 0; k < KT; k++) {
-                        const int cc = kappa + K * (KT * tb + k);
-                        if (cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
-                    }
-                }
-            } else {
-                const int v = unit - nunits;
-                const int rho = v / wpn, mb = (v - rho * wpn) * 32 + lane;
-                if (mb <= ntb) {
-                    float nr[KT];
-                    tds_lane_sums<KT, 0, 1>(X + rho * plane_len + mb, a.sk, nullptr, Q, nr);
-#pragma unroll
-                    for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
+                for (int k = 0; k < KT; k++) {
+                    const int cc = kappa + K * (KT * tb + k);
+                    if (cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
                 }
             }
         }
+        TDS_T(2);
         __syncthreads();
-        if (i + 1 < a.nseq) window_store(X0 + (cur ^ 1) * 4 * plane_len);
-        cur ^= 1;
+        TDS_T(3);
 
-        // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max ----
-        ArgMax best; best.v = -1e300; best.i = 0x7fffffff;
+        // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max (first wins) ----
+        unsigned long long bk = 0ull; int bi = 0x7fffffff;
         for (int cc = tid; cc < ncand; cc += blockDim.x) {
-            const int c = c_base + cc, np = a.ncand_pad, sl = ps_slot<K * KT>(cc);
+            const int np = a.ncand_pad, sl = ps_slot<K * KT>(cc);
             const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[sl], PS[np + sl]), PS[2 * np + sl]), PS[3 * np + sl]);
             const int kap = cc % K, trel = cc / K;
             float nl[4];
@@ -322,46 +373,61 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             const float nr = __fadd_rn(__fadd_rn(__fadd_rn(nl[0], nl[1]), nl[2]), nl[3]);
             const double dn = (double)nr;
             double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
-            const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
-            corr = __dmul_rn(__dadd_rn(corr, 0.1), __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp)));
-            ArgMax cand; cand.v = corr; cand.i = c;
-            best = argmax_better(best, cand);
+            corr = __dmul_rn(__dadd_rn(corr, 0.1), PW[cc]);
+            const unsigned long long k = argmax_key(corr);
+            if (k > bk || bi == 0x7fffffff) { bk = k; bi = c_base + cc; }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            ArgMax o;
-            o.v = __shfl_xor_sync(0xffffffffu, best.v, d);
-            o.i = __shfl_xor_sync(0xffffffffu, best.i, d);
-            best = argmax_better(best, o);
+        {
+            // warp arg-max with three integer reductions: high word, low word among the leaders, lowest index
+            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            const int mi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? bi : 0x7fffffff);
+            if (lane == 0) { red_k[warp] = ((unsigned long long)mh << 32) | ml; red_i[warp] = mi; }
         }
-        if (lane == 0) { red_v[warp] = best.v; red_i[warp] = best.i; }
+        TDS_T(4);
         __syncthreads();
+        TDS_T(5);
+        unsigned long long fk = red_k[0]; int fi = red_i[0];
+        for (int w = 1; w < nwarps; w++) {
+            const unsigned long long k = red_k[w]; const int ix = red_i[w];
+            if (k > fk || (k == fk && ix < fi)) { fk = k; fi = ix; }
+        }
         const int par = i & 1;
-        if (warp == 0) {
-            ArgMax b2; b2.v = lane < nwarps ? red_v[lane] : -1e300; b2.i = lane < nwarps ? red_i[lane] : 0x7fffffff;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                ArgMax o;
-                o.v = __shfl_xor_sync(0xffffffffu, b2.v, d);
-                o.i = __shfl_xor_sync(0xffffffffu, b2.i, d);
-                b2 = argmax_better(b2, o);
+        if (CL > 1) {
+            // publish this CTA's best to every CTA of the cluster (own slot included), then arrive
+            if (tid < (int)CL) {
+                *cluster.map_shared_rank(&xch_k[par][crank], tid) = fk;
+                *cluster.map_shared_rank(&xch_i[par][crank], tid) = fi;
             }
-            // publish this CTA's best to every CTA of the cluster (own slot included)
-            if (lane < CL) {
-                double* pv = cluster.map_shared_rank(&xch_v[par][crank], lane);
-                int* pi = cluster.map_shared_rank(&xch_i[par][crank], lane);
-                *pv = b2.v; *pi = b2.i;
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        }
+        TDS_T(6);
+        // ---- in the shadow of the exchange: next window landed -> its norm sums ----
+        cp_async_wait_all();
+        __syncthreads();
+        cur ^= 1;
+        if (i + 1 < a.nseq) norm_units(X0 + cur * 4 * plane_len);
+        if (CL > 1) {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            fk = xch_k[par][0]; fi = xch_i[par][0];
+            for (unsigned r = 1; r < CL; r++) {
+                const unsigned long long k = xch_k[par][r]; const int ix = xch_i[par][r];
+                if (k > fk || (k == fk && ix < fi)) { fk = k; fi = ix; }
             }
         }
-        if (CL > 1) cluster.sync(); else __syncthreads();
-        ArgMax fin; fin.v = xch_v[par][0]; fin.i = xch_i[par][0];
-        for (unsigned r = 1; r < CL; r++) { ArgMax o; o.v = xch_v[par][r]; o.i = xch_i[par][r]; fin = argmax_better(fin, o); }
-        if (crank == 0 && tid == 0) offs[i - 1] = fin.i;
-        mid_pos = p0 + fin.i + ovl + temp;
+        TDS_T(7);
+        if (fi == 0x7fffffff) fi = 0;
+        if (crank == 0 && tid == 0) offs[i - 1] = fi;
+        moff = fi;
         // the slots of parity `par` are rewritten two sequences later, after another cluster barrier;
-        // X/Y/PS are rewritten only after the next __syncthreads of this CTA
+        // Y/PS/MR are rewritten only after the next __syncthreads of this CTA, PN after the one above
     }
     if (CL > 1) cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
+#ifdef NODEY_TDS_TIMING
+    if (timing_on)
+        for (int k = 0; k < 8; k++) g_tds_phase[k] = (unsigned long long)tacc[k];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -977,6 +1043,16 @@ int nodey_soundtouch_set_unfused(nodey_soundtouch* s, int unfused)
     return NODEY_OK;
 }
 
+#ifdef NODEY_TDS_TIMING
+/* development build only: phase clocks of the last tds_offsets launch (thread 0 of CTA 0) */
+int nodey_debug_tds_phases(unsigned long long out[8])
+{
+    NODEY_CUDA_OK(cudaDeviceSynchronize());
+    NODEY_CUDA_OK(cudaMemcpyFromSymbol(out, nodey::g_tds_phase, sizeof(unsigned long long) * 8));
+    return NODEY_OK;
+}
+#endif
+
 /* test hook: force the cluster size (1, 2 or 4; 0 = automatic) of the offsets kernel */
 int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster)
 {
@@ -1073,11 +1149,11 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
         ta.Q = 4 * (CH * s->overlap / 16);
         if (nseq > 1) {
-            // cluster size: spread one track over CL SMs while the batch leaves SMs idle
-            // cluster size from the measured batch sweep (tools/st_sweep.py, 256-thread CTAs, two per SM):
-            // 4 CTAs per track while they all fit at two per SM, 2 up to about 200 tracks, 1 beyond
+            // cluster size: spread one track over CL SMs while the batch leaves SMs idle.  From the measured batch
+            // sweep (tools/st_sweep.py, 256-thread CTAs, two per SM): 4 CTAs per track up to about 40 tracks (one CTA
+            // per SM), 2 up to about 200 tracks, 1 beyond
             int CL = 1;
-            if ((long long)ntracks * 4 <= 2ll * sm_count()) CL = 4;
+            if ((long long)ntracks * 4 <= 160ll * sm_count() / 148) CL = 4;
             else if ((long long)ntracks * 2 <= 400ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
             const int KT = CL >= 4 ? 4 : 8;
@@ -1089,7 +1165,11 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             ta.sk = sk;
             ta.ncand_pad = (K * KT * ta.tb_per + ta.tb_per + 4 + 3) & ~3;      // + one pad word per K*KT candidates
             ta.npm = (KT * (ta.tb_per + 1) + ta.tb_per + 1 + 4 + 3) & ~3;
-            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.Q + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm);
+            const int mreg = s->seek_length + s->overlap;
+            ta.vec8 = (CH == 2 && (((uintptr_t)vin.p) & 7) == 0 && (vin.stride % 2) == 0) ? 1 : 0;
+            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * (ta.Q + 8) + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
+                                                 (size_t)((mreg * CH + 3) & ~3)) + sizeof(double) * (size_t)(K * KT * ta.tb_per);
+            NODEY_REQUIRE(smem <= 110 * 1024, NODEY_E_RANGE, "tds_offsets: %zu bytes of shared memory per CTA exceed the two-per-SM budget", smem);
             NODEY_REQUIRE(KT * sk * 4 / CH <= 2048, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
             void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
                                             : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);

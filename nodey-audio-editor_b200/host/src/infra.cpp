@@ -405,19 +405,33 @@ namespace infra
 				const auto data = node_data.find(id);
 				upload += graph.nodes.at(id).processor->upload_bytes(data == node_data.end() ? no_data : *data->second);
 			}
-		// Uploads are faster than compute per track, so only the FIRST wave's upload is exposed: keep it
-		// small (32 source pins), then grow (96, 128, then 256 each) so that the batched kernels of the later
-		// waves run at full efficiency.  NODEY_WAVE=n forces uniform waves of n pins.
+		// Uploads are only a little slower than compute per track, so (1) only the FIRST wave's upload is
+		// exposed: keep it small (32 source pins); (2) the LAST wave's compute is exposed: keep it small too --
+		// a SoundTouch chain costs the same 50 ms for 8 or 40 tracks (sequential per track), so 32 is the
+		// cheapest tail; (3) in between, waves of 64 pins keep the batched kernels efficient, and consecutive
+		// waves run on alternating compute lanes so that a small wave does not leave the SMs idle while its
+		// sequential chains run.  NODEY_WAVE=n forces uniform waves of n pins.
 		const bool pipelined = upload >= (1u << 30);
 		int uniform = 0;
 		if (const char* env = getenv("NODEY_WAVE")) uniform = std::max(1, atoi(env));
+		int source_pins = 0;
+		if (!levels.empty())
+			for (const Id_t id : levels.front())
+				for (const auto& attribute : graph.nodes.at(id).processor->get_pin_attributes())
+					if (!attribute.is_input) source_pins++;
+		std::vector<int> wave_begin{0};      // first pin position of every wave
+		if (uniform > 0)
+			for (int p = uniform; p < source_pins; p += uniform) wave_begin.push_back(p);
+		else if (pipelined && source_pins > 32)
+		{
+			constexpr int kEdge = 32, kBody = 64;
+			int p = kEdge;
+			while (source_pins - p > kBody + kEdge) { wave_begin.push_back(p); p += kBody; }
+			wave_begin.push_back(p);
+			if (source_pins - p > kBody) wave_begin.push_back(source_pins - kEdge);
+		}
 		const auto wave_of_pin = [&](int position) {
-			if (uniform > 0) return position / uniform;
-			if (!pipelined) return 0;
-			if (position < 32) return 0;
-			if (position < 128) return 1;
-			if (position < 256) return 2;
-			return 3 + (position - 256) / 256;
+			return (int)(std::upper_bound(wave_begin.begin(), wave_begin.end(), position) - wave_begin.begin()) - 1;
 		};
 		std::map<Id_t, int> pin_position;     // output pin -> index in its node's attribute order
 		for (const auto& [id, node] : graph.nodes)
@@ -493,14 +507,20 @@ namespace infra
 
 	void Runner::launch_threads()
 	{
-		// lane 0: transfers (nodes without inputs: the sources' uploads); lane 1: compute (everything else)
-		constexpr int kLanes = 2;
-		nodey_stream_t lanes[kLanes] = {nullptr, nullptr};
+		// lane 0: transfers (nodes without inputs: the sources' uploads); lanes 1..: compute (everything else).
+		// One compute lane when the render is a single wave; waves alternate between two otherwise.
+		int max_wave = 0;
+		for (const auto& [_, w] : node_wave) max_wave = std::max(max_wave, w);
+		int compute_lanes = max_wave > 0 ? 2 : 1;
+		if (const char* env = getenv("NODEY_COMPUTE_LANES")) compute_lanes = std::clamp(atoi(env), 1, 4);
+		constexpr int kMaxLanes = 5;
+		const int kLanes = 1 + compute_lanes;
+		nodey_stream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 		bool failed = false;
 		if (device >= 0 && nodey_set_device(device) != NODEY_OK) failed = true;
 		for (int k = 0; k < kLanes; k++)
 			if (nodey_stream_create(&lanes[k]) != NODEY_OK) failed = true;
-			else Lane_registry::add(lanes[k], k == 1);
+			else Lane_registry::add(lanes[k], k >= 1);
 		if (failed)
 		{
 			for (auto& [_, r] : processor_resources)
@@ -578,8 +598,6 @@ namespace infra
 		// Schedule: sources first (their uploads are enqueued on the transfer lane in pin order), then wave
 		// by wave, each wave level by level on the compute lane.  A wave is the part of the graph fed by a
 		// contiguous block of source pins, so wave k computes while the uploads of wave k+1 are in flight.
-		int max_wave = 0;
-		for (const auto& [_, w] : node_wave) max_wave = std::max(max_wave, w);
 		for (int wave = 0; wave <= max_wave && !failed; wave++)
 			for (size_t level_index = wave == 0 ? 0 : 1; level_index < levels.size() && !failed; level_index++)
 			{
@@ -588,11 +606,11 @@ namespace infra
 					if (node_wave.at(id) == wave) ids.push_back(id);
 				if (ids.empty()) continue;
 				const auto t_begin = std::chrono::steady_clock::now();
-				run_group(ids, level_index == 0 ? 0 : 1, (int)level_index);
+				run_group(ids, level_index == 0 ? 0 : 1 + wave % compute_lanes, (int)level_index);
 				if (trace)
 				{
 					const auto t_enq = std::chrono::steady_clock::now();
-					for (auto& s : lanes) nodey_stream_synchronize(s);
+					for (auto& s : lanes) if (s) nodey_stream_synchronize(s);
 					const auto t_end = std::chrono::steady_clock::now();
 					fprintf(stderr, "[nodey trace] wave %d level %zu: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", wave, level_index,
 							ids.size(), processor_resources.at(ids.front())->processor->get_processor_info_non_static().identifier.c_str(),

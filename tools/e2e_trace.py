@@ -1,4 +1,5 @@
-"""Development: trace the engine on the config-5 project with pinned host sources."""
+"""Development: end-to-end engine time on the config-5 project with pinned host sources, for several
+wave / compute-lane settings (NODEY_WAVE, NODEY_COMPUTE_LANES), then one traced run."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
@@ -12,7 +13,20 @@ p, ids = engine.config5_project(T, [pipeline.track_gain(t) for t in range(T)])
 e = engine.Engine(p.json())
 for t in range(T):
     e.bind_source(t, x[t], 3, 44100)
-for it in range(3):
-    t0 = time.perf_counter(); e.run(); torch.cuda.synchronize(); print(f"run {it}: {(time.perf_counter()-t0)*1e3:.1f} ms", flush=True)
-os.environ["NODEY_TRACE"] = "1"
-t0 = time.perf_counter(); e.run(); torch.cuda.synchronize(); print(f"traced run: {(time.perf_counter()-t0)*1e3:.1f} ms", flush=True)
+def timed(label, reps=3):
+    ts = []
+    for it in range(reps):
+        t0 = time.perf_counter(); e.run(); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+    print(f"{label}: " + " ".join(f"{t:.1f}" for t in ts) + " ms", flush=True)
+timed("default (warm-up)")
+for lanes in ("1", "2", "3"):
+    os.environ["NODEY_COMPUTE_LANES"] = lanes
+    timed(f"default waves, lanes={lanes}")
+    for w in ("32", "64"):
+        os.environ["NODEY_WAVE"] = w
+        timed(f"uniform waves of {w}, lanes={lanes}")
+    del os.environ["NODEY_WAVE"]
+del os.environ["NODEY_COMPUTE_LANES"]
+if os.environ.get("TRACE"):
+    os.environ["NODEY_TRACE"] = "1"
+    timed("traced", 1)
