@@ -105,7 +105,8 @@ int nodey_to_fltp_stereo(float* dst_l, float* dst_r, const void* plane0, const v
 /* A4  audio_amix mix loop, src/processor/audio-amix.cpp:293-307.
  * out[j] = ((0 + in0[j]*v0) + in1[j]*v1) + ... in input order; input i contributes zeros for
  * j >= in_len[i] (the reference's zero-filled temp buffers).  in_l / in_r / in_len / volumes are
- * HOST arrays of nin entries (device pointers inside). */
+ * HOST arrays of nin entries (device pointers inside).  in_r[i] == NULL: in_l[i] holds interleaved
+ * stereo float frames (swr's FLT -> FLTP conversion is a pure de-interleave, done in registers). */
 int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r,
               const int64_t* in_len, const float* volumes, int nin, int64_t nframes,
               nodey_stream_t stream);
@@ -214,6 +215,13 @@ int nodey_soundtouch_set_unfused(nodey_soundtouch* s, int unfused);
 int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                          int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                          int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);
+/* Same, with the tracks read in place through per-track pointers (HOST arrays of device pointers, at most
+ * 256 tracks per call): in_a[t] = interleaved float frames, or -- for stereo with in_b != NULL -- the left
+ * plane with in_b[t] the right plane.  extract_samples_interleaved (audio-velocity.cpp:150-232) is the
+ * identity on float samples, so FLT / FLTP streams need no staging copy. */
+int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
+                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                                int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);
 
 /* N2  audio_spectrum (new node; FFTW r2c convention, unnormalised):
  * per channel, frame m = x[m*hop .. m*hop+nfft) * periodic Hann; out[ch][m][0..nfft/2] complex64

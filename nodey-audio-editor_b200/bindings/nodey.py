@@ -24,7 +24,7 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
@@ -88,6 +88,7 @@ def lib():
     L.nodey_soundtouch_set_cluster.argtypes = [vp, i32]
     L.nodey_soundtouch_set_unfused.argtypes = [vp, i32]
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
+    L.nodey_soundtouch_run_tracks.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, vp]
     L.nodey_amix_plan.argtypes = [C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32,
                                   C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64),
                                   C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64)]
@@ -396,6 +397,24 @@ class SoundTouch:
                 "sample_rate"]
         out = dict(zip(keys, list(a)))
         out.update(rate=d[0], tempo=d[1], nominal_skip=d[2])
+        return out
+
+    def run_tracks(self, tracks, frame_size=1152, want_offsets=False):
+        """tracks: list of [frames, ch] interleaved tensors or (left, right) plane pairs, read in place (no staging copy)."""
+        t = _torch()
+        ntr = len(tracks)
+        planar = isinstance(tracks[0], (tuple, list))
+        first = tracks[0][0] if planar else tracks[0]
+        n = first.shape[0]
+        m, nseq = self.out_frames(n, frame_size)
+        out = t.empty((ntr, m, self.ch), dtype=t.float32, device=first.device)
+        offs = t.zeros((ntr, max(nseq - 1, 1)), dtype=t.int32, device=first.device) if want_offsets else None
+        pa = (C.c_void_p * ntr)(*[(tr[0] if planar else tr).data_ptr() for tr in tracks])
+        pb = (C.c_void_p * ntr)(*[tr[1].data_ptr() for tr in tracks]) if planar else None
+        check(lib().nodey_soundtouch_run_tracks(self.h, _dp(out), out.stride(0), pa, pb, ntr, n, frame_size, m,
+                                                _dp(offs), offs.stride(0) if offs is not None else 0, _stream()))
+        if want_offsets:
+            return out, offs[:, :max(nseq - 1, 0)]
         return out
 
     def out_frames(self, in_frames, frame_size=1152):

@@ -45,36 +45,58 @@ constexpr int kAaLen = 64;
 constexpr int kTdsThreads = 256;      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
 
 // frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
-// (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks)
+// (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks).
+// Two addressings: one contiguous batch of interleaved tracks `stride` floats apart (the intermediates), or a
+// per-track pointer table (the node's input read in place: interleaved FLT, or the two planes of stereo FLTP --
+// extract_samples_interleaved, audio-velocity.cpp:150-232, is the identity on float samples, so no copy is made).
 struct View {
     const float* p;
     long long n;        // real frames
     long long prefix;   // silent frames in front
     long long stride;   // floats between tracks
+    int use_tab;        // 1: tracks are addressed through the kernel's TrackTab instead of p + track * stride
 };
 
+// per-track source pointers, passed by value in the kernel parameters (no upload, no lifetime to manage):
+// p[2t] = interleaved frames or left plane, p[2t + 1] = right plane or null
+constexpr int kMaxTabTracks = 256;
+struct TrackTab { const float* p[2 * kMaxTabTracks]; };
+
+struct Src { const float* a; const float* b; };     // b != nullptr: stereo planes (a = left, b = right)
+
+__device__ __forceinline__ Src view_src(const View& v, const TrackTab& tt, long long track)
+{
+    if (v.use_tab) return Src{tt.p[2 * track], tt.p[2 * track + 1]};
+    return Src{v.p + track * v.stride, nullptr};
+}
+__device__ __forceinline__ Src view_src(const View& v, long long track) { return Src{v.p + track * v.stride, nullptr}; }
+
 template <int CH>
-__device__ __forceinline__ float view_sample(const View& v, const float* base, long long frame, int c)
+__device__ __forceinline__ float view_sample(const View& v, const Src& base, long long frame, int c)
 {
     const long long f = frame - v.prefix;
     if (f < 0 || f >= v.n) return 0.f;
-    return base[f * CH + c];
+    if (CH == 2 && base.b) return (c ? base.b : base.a)[f];
+    return base.a[f * CH + c];
 }
 
 template <int CH>
-__device__ __forceinline__ float2 view_frame2(const View& v, const float* base, long long frame)
+__device__ __forceinline__ float2 view_frame2(const View& v, const Src& base, long long frame)
 {
     const long long f = frame - v.prefix;
     if (f < 0 || f >= v.n) return make_float2(0.f, 0.f);
-    if (CH == 2) return *reinterpret_cast<const float2*>(base + f * 2);
-    return make_float2(base[f], 0.f);
+    if (CH == 2) {
+        if (base.b) return make_float2(base.a[f], base.b[f]);
+        return *reinterpret_cast<const float2*>(base.a + f * 2);
+    }
+    return make_float2(base.a[f], 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
 // TDStretch offsets
 // ---------------------------------------------------------------------------------------------
 struct TdsArgs {
-    View in;
+    View in; TrackTab tt;
     const long long* pos;      // [nseq] input frame where sequence i starts
     int* offs;                 // [ntracks][offs_stride] offsets of sequences 1..nseq-1 at index i-1
     long long offs_stride;
@@ -228,7 +250,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const long long track = blockIdx.x / CL;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, a.tt, track);
     int* offs = a.offs + track * a.offs_stride;
 
     const int region = L + ovl;                      // frames of the search window
@@ -254,13 +276,14 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             const int f = f_lo + fr;
             const long long g = p0 + f;
             const bool ok = f < region && g >= 0 && g < a.in.n;
-            const float* src = ok ? base + g * CH : base;
+            const long long go = ok ? g : 0;
             if (CH == 2) {
                 const int m = fr >> 1, pl = (fr & 1) * 2;
                 float* d = Xb + pl * plane_len + (m % KT) * a.sk + m / KT;
-                cp_async4(d, src, ok);
-                cp_async4(d + plane_len, src + (ok ? 1 : 0), ok);
+                cp_async4(d, base.b ? base.a + go : base.a + 2 * go, ok);
+                cp_async4(d + plane_len, base.b ? base.b + go : base.a + 2 * go + 1, ok);
             } else {
+                const float* src = base.a + go;
                 const int m = fr >> 2;
                 cp_async4(Xb + (fr & 3) * plane_len + (m % KT) * a.sk + m / KT, src, ok);
             }
@@ -271,11 +294,12 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         for (int fr = tid; fr < mreg; fr += kTdsThreads) {
             const long long g = p0 + fr;
             const bool ok = g >= 0 && g < a.in.n;
-            const float* src = ok ? base + g * CH : base;
+            const long long go = ok ? g : 0;
             if (CH == 2) {
-                if (a.vec8) cp_async8(MR + 2 * fr, src, ok);
-                else { cp_async4(MR + 2 * fr, src, ok); cp_async4(MR + 2 * fr + 1, src + (ok ? 1 : 0), ok); }
-            } else cp_async4(MR + fr, src, ok);
+                if (base.b) { cp_async4(MR + 2 * fr, base.a + go, ok); cp_async4(MR + 2 * fr + 1, base.b + go, ok); }
+                else if (a.vec8) cp_async8(MR + 2 * fr, base.a + 2 * go, ok);
+                else { cp_async4(MR + 2 * fr, base.a + 2 * go, ok); cp_async4(MR + 2 * fr + 1, base.a + 2 * go + 1, ok); }
+            } else cp_async4(MR + fr, base.a + go, ok);
         }
     };
     const auto l2_prefetch = [&](int seq) {
@@ -284,7 +308,12 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         const int lines = (nfr * CH * 4 + 127) / 128 + 1;
         for (int t = tid; t < lines; t += blockDim.x) {
             const long long f = q0 + (long long)t * (32 / CH);
-            if (f >= 0 && f < a.in.n) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + f * CH));
+            if (f >= 0 && f < a.in.n) {
+                if (CH == 2 && base.b) {
+                    // planes: a 128-byte line holds 32 frames of one plane; t walks 16-frame steps, so alternate the planes
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"((t & 1 ? base.b : base.a) + f));
+                } else asm volatile("prefetch.global.L2 [%0];" :: "l"(base.a + f * CH));
+            }
         }
     };
     // norm units: thread = (plane rho, KT consecutive start positions): N[rho][m] = sum_q X_rho[m + q]^2, which is
@@ -434,7 +463,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
 // TDStretch assemble: overlap (cross-fade) + copy of every sequence, one CTA per (sequence, track)
 // ---------------------------------------------------------------------------------------------
 struct AsmArgs {
-    View in;
+    View in; TrackTab tt;
     float* out; long long out_stride; long long out_cap;   // frames to write at most (trim)
     const long long* pos;
     const int* offs; long long offs_stride;
@@ -447,7 +476,7 @@ __global__ void __launch_bounds__(256) tds_assemble_kernel(const __grid_constant
 {
     const int i = blockIdx.x;
     const long long track = blockIdx.y;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, a.tt, track);
     float* out = a.out + track * a.out_stride;
     const int* offs = a.offs + track * a.offs_stride;
     const int ovl = a.overlap, temp = a.seek_window - 2 * ovl;
@@ -504,7 +533,7 @@ __global__ void __launch_bounds__(kFirThreads) aa_fir_mono_kernel(const __grid_c
 {
     __shared__ __align__(16) float tile[kFirTile + kAaLen];
     const long long track = blockIdx.y;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, track);
     float* out = a.out + track * a.out_stride;
     const float* h = a.h;
     const long long ntiles = (a.count + kFirTile - 1) / kFirTile;
@@ -544,7 +573,7 @@ __global__ void __launch_bounds__(kFirThreads) aa_fir_stereo_kernel(const __grid
 {
     __shared__ __align__(16) float4 tile[kFirChunks];
     const long long track = blockIdx.y;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, track);
     float* out = a.out + track * a.out_stride;
     const float* h = a.h;
     const long long ntiles = (a.count + kFirTileS - 1) / kFirTileS;
@@ -595,7 +624,7 @@ __global__ void __launch_bounds__(kFirThreads) aa_fir_stereo_kernel(const __grid
 // cubic transposer: output i reads 4 frames at floor(i*rate), fraction (float)frac(i*rate)
 // ---------------------------------------------------------------------------------------------
 struct CubicArgs {
-    View in;
+    View in; TrackTab tt;
     float* out; long long out_stride;
     long long count;
     unsigned long long R;   // rate = R * 2^-e
@@ -606,7 +635,7 @@ template <int CH>
 __global__ void __launch_bounds__(256) cubic_kernel(const __grid_constant__ CubicArgs a)
 {
     const long long track = blockIdx.y;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, a.tt, track);
     float* out = a.out + track * a.out_stride;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const double inv = 1.0 / (double)(1ull << a.e);     // exact power of two (e <= 62)
@@ -647,7 +676,7 @@ __global__ void __launch_bounds__(256) cubic_kernel(const __grid_constant__ Cubi
 // streams (2 x 8 B per frame, written and read) never touch HBM.
 // ---------------------------------------------------------------------------------------------
 struct PostArgs {
-    View in;
+    View in; TrackTab tt;
     const long long* pos; const int* offs; long long offs_stride;
     const float* fade;
     int nseq, overlap, seek_window, prefill;
@@ -683,7 +712,7 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
     __shared__ __align__(16) float4 tile[kFirChunks];
     __shared__ float2 filt[kFirTileS + kFirTileS / 8];     // one pad slot per 8 frames: thread-strided stores stay 2-way
     const long long track = blockIdx.y;
-    const float* base = a.in.p + track * a.in.stride;
+    const Src base = view_src(a.in, a.tt, track);
     const int* offs = a.offs + track * a.offs_stride;
     float* out = a.out + track * a.out_stride;
     const int ovl = a.overlap, temp = a.seek_window - 2 * ovl, hop = a.seek_window - ovl;
@@ -734,7 +763,10 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                 interior = interior && src_j[j] - a.in.prefix >= 0 && src_j[j] - a.in.prefix + reach <= a.in.n
                                     && mid_j[j] - a.in.prefix >= 0 && mid_j[j] - a.in.prefix + ovl <= a.in.n;
             if (interior) {
-                const float2* b2 = reinterpret_cast<const float2*>(base) - a.in.prefix;
+                const float2* b2 = reinterpret_cast<const float2*>(base.a) - a.in.prefix;
+                const float* pl = base.a - a.in.prefix;
+                const float* pr = base.b - a.in.prefix;
+                const bool planar = base.b != nullptr;
                 const int kf = (int)k_first;
                 for (int c = threadIdx.x; c < kFirChunks; c += blockDim.x) {
                     float2 f[2];
@@ -744,10 +776,10 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                         if (k >= hop) { k -= hop; j = 1; }
                         if (k >= hop) { k -= hop; j = 2; }
                         const long long src = j == 0 ? src_j[0] : (j == 1 ? src_j[1] : src_j[2]);
-                        float2 x = __ldg(b2 + src + k);
+                        float2 x = planar ? make_float2(__ldg(pl + src + k), __ldg(pr + src + k)) : __ldg(b2 + src + k);
                         if (k < ovl) {
                             const long long mid = j == 0 ? mid_j[0] : (j == 1 ? mid_j[1] : mid_j[2]);
-                            const float2 m = __ldg(b2 + mid + k);
+                            const float2 m = planar ? make_float2(__ldg(pl + mid + k), __ldg(pr + mid + k)) : __ldg(b2 + mid + k);
                             const float f1 = a.fade[k], f2 = a.fade[ovl + k];
                             x = make_float2(__fadd_rn(__fmul_rn(x.x, f1), __fmul_rn(m.x, f2)), __fadd_rn(__fmul_rn(x.y, f1), __fmul_rn(m.y, f2)));
                         }
@@ -1093,11 +1125,11 @@ int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int 
     return total;
 }
 
-int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
-                         int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                         int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
+static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride, const TrackTab* tab,
+                               int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                               int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
 {
-    NODEY_REQUIRE(s && out && in, NODEY_E_INVALID, "nodey_soundtouch_run: null argument");
+    NODEY_REQUIRE(s && out && (in || tab), NODEY_E_INVALID, "nodey_soundtouch_run: null argument");
     NODEY_REQUIRE(ntracks >= 1 && in_frames >= 0 && frame_size > 0, NODEY_E_INVALID, "nodey_soundtouch_run: bad size");
     std::lock_guard<std::mutex> lock(s->mu);
     cudaStream_t st = as_stream(stream);
@@ -1145,7 +1177,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
 
     auto run_offsets = [&](View vin) -> int {
         TdsArgs ta;
-        ta.in = vin; ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
+        ta.in = vin; if (vin.use_tab) ta.tt = *tab;
+        ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
         ta.Q = 4 * (CH * s->overlap / 16);
         if (nseq > 1) {
@@ -1167,6 +1200,10 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             ta.npm = (KT * (ta.tb_per + 1) + ta.tb_per + 1 + 4 + 3) & ~3;
             const int mreg = s->seek_length + s->overlap;
             ta.vec8 = (CH == 2 && (((uintptr_t)vin.p) & 7) == 0 && (vin.stride % 2) == 0) ? 1 : 0;
+            if (vin.use_tab) {
+                ta.vec8 = CH == 2 ? 1 : 0;
+                for (int t = 0; t < ntracks; t++) if (((uintptr_t)tab->p[2 * t]) & 7) ta.vec8 = 0;
+            }
             const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * (ta.Q + 8) + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
                                                  (size_t)((mreg * CH + 3) & ~3)) + sizeof(double) * (size_t)(K * KT * ta.tb_per);
             NODEY_REQUIRE(smem <= 110 * 1024, NODEY_E_RANGE, "tds_offsets: %zu bytes of shared memory per CTA exceed the two-per-SM budget", smem);
@@ -1195,7 +1232,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
         const int rc0 = run_offsets(vin);
         if (rc0 != NODEY_OK) return rc0;
         AsmArgs aa;
-        aa.in = vin; aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = s->d_pos;
+        aa.in = vin; if (vin.use_tab) aa.tt = *tab;
+        aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = s->d_pos;
         aa.offs = d_offs; aa.offs_stride = offs_stride; aa.fade = s->d_fade; aa.nseq = (int)nseq;
         aa.overlap = s->overlap; aa.seek_window = s->seek_window;
         dim3 grid((unsigned)nseq, (unsigned)ntracks);
@@ -1218,7 +1256,8 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     };
     auto run_cubic = [&](View vin, float* dst, long long dst_stride, long long count) -> int {
         if (count <= 0) return NODEY_OK;
-        CubicArgs ca; ca.in = vin; ca.out = dst; ca.out_stride = dst_stride; ca.count = count; ca.R = s->R; ca.e = s->e;
+        CubicArgs ca; ca.in = vin; if (vin.use_tab) ca.tt = *tab;
+        ca.out = dst; ca.out_stride = dst_stride; ca.count = count; ca.R = s->R; ca.e = s->e;
         long long blocks = (count + 255) / 256;
         const long long cap = (long long)sm_count() * 8;
         dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)ntracks);
@@ -1230,11 +1269,12 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
     int rc = NODEY_OK;
     if (s->td_first && CH == 2 && !s->force_unfused) {
         // offsets, then the fused assemble + FIR + cubic tail
-        View v0{in, in_frames, 0, in_stride};
+        View v0{in, in_frames, 0, in_stride, tab ? 1 : 0};
         rc = run_offsets(v0);
         if (rc == NODEY_OK) {
             PostArgs pa;
-            pa.in = v0; pa.pos = s->d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
+            pa.in = v0; if (v0.use_tab) pa.tt = *tab;
+            pa.pos = s->d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
             pa.nseq = (int)nseq; pa.overlap = s->overlap; pa.seek_window = s->seek_window; pa.prefill = s->prefill; pa.l1 = L.l1;
             memcpy(pa.h, s->aa, sizeof(pa.h));
             pa.R = s->R; pa.e = s->e; pa.out = out; pa.out_stride = out_stride; pa.count = out_frames;
@@ -1245,23 +1285,46 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
             NODEY_LAUNCH_OK();
         }
     } else if (s->td_first) {
-        View v0{in, in_frames, 0, in_stride};
+        View v0{in, in_frames, 0, in_stride, tab ? 1 : 0};
         rc = run_tds(v0, b1, s1, L.l1);
-        View v1{b1, L.l1, s->prefill, s1};
+        View v1{b1, L.l1, s->prefill, s1, 0};
         if (rc == NODEY_OK) rc = run_fir(v1, b2, s2, L.l2);
-        View v2{b2, L.l2, 0, s2};
+        View v2{b2, L.l2, 0, s2, 0};
         if (rc == NODEY_OK) rc = run_cubic(v2, out, out_stride, out_frames);
     } else {
-        View v0{in, in_frames, s->prefill, in_stride};
+        View v0{in, in_frames, s->prefill, in_stride, tab ? 1 : 0};
         rc = run_cubic(v0, b1, s1, L.l1);
-        View v1{b1, L.l1, 0, s1};
+        View v1{b1, L.l1, 0, s1, 0};
         if (rc == NODEY_OK) rc = run_fir(v1, b2, s2, L.l2);
-        View v2{b2, L.l2, 0, s2};
+        View v2{b2, L.l2, 0, s2, 0};
         if (rc == NODEY_OK) rc = run_tds(v2, out, out_stride, out_frames);
     }
     device_free(ws, st);
     if (ws_offs) device_free(ws_offs, st);
     return rc;
+}
+
+int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
+                         int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                         int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
+{
+    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, stream);
+}
+
+int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
+                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                                int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(s && in_a, NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null argument");
+    NODEY_REQUIRE(ntracks >= 1 && ntracks <= kMaxTabTracks, NODEY_E_RANGE, "nodey_soundtouch_run_tracks: 1..%d tracks per call", kMaxTabTracks);
+    TrackTab tab;
+    memset(&tab, 0, sizeof(tab));
+    for (int t = 0; t < ntracks; t++) {
+        NODEY_REQUIRE(in_a[t], NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null track pointer");
+        tab.p[2 * t] = in_a[t];
+        tab.p[2 * t + 1] = (in_b && s->ch == 2) ? in_b[t] : nullptr;
+    }
+    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, stream);
 }
 
 }  // extern "C"

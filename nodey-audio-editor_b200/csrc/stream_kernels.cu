@@ -278,8 +278,17 @@ __global__ void __launch_bounds__(kBlock) mix_kernel(float* __restrict__ out_l, 
         const int64_t j = pk * 4;
         float4 tl = make_float4(0.f, 0.f, 0.f, 0.f), tr = tl;
         for (int i = 0; i < a.nin; i++) {
-            const float4 xl = load4_zero_tail(a.l[i], j, a.len[i], a.vec);
-            const float4 xr = load4_zero_tail(a.r[i], j, a.len[i], a.vec);
+            float4 xl, xr;
+            if (a.r[i]) {
+                xl = load4_zero_tail(a.l[i], j, a.len[i], a.vec);
+                xr = load4_zero_tail(a.r[i], j, a.len[i], a.vec);
+            } else {
+                // interleaved stereo input: frames j .. j+3 are 8 consecutive floats (de-interleaved in registers)
+                const float4 f0 = load4_zero_tail(a.l[i], 2 * j, 2 * a.len[i], a.vec);
+                const float4 f1 = load4_zero_tail(a.l[i], 2 * j + 4, 2 * a.len[i], a.vec);
+                xl = make_float4(f0.x, f0.z, f1.x, f1.z);
+                xr = make_float4(f0.y, f0.w, f1.y, f1.w);
+            }
             tl = mac4(tl, xl, a.vol[i]);
             tr = mac4(tr, xr, a.vol[i]);
         }
@@ -586,7 +595,7 @@ int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float*
     a.vec = aligned16(out_l) && aligned16(out_r);
     for (int i = 0; i < nin; i++) {
         a.l[i] = in_l[i]; a.r[i] = in_r[i]; a.len[i] = in_len[i]; a.vol[i] = volumes[i];
-        a.vec = a.vec && aligned16(in_l[i]) && aligned16(in_r[i]);
+        a.vec = a.vec && aligned16(in_l[i]) && (in_r[i] == nullptr || aligned16(in_r[i]));
     }
     NODEY_LAUNCH("mix_kernel", as_stream(stream), mix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(out_l, out_r, a, n));
     NODEY_LAUNCH_OK();

@@ -500,18 +500,41 @@ namespace processor
 					const size_t cnt = std::min(kMaxTracksPerLaunch, all.size() - first);
 					const size_t in_stride = Arena::padded((size_t)n * ch * sizeof(float)) / sizeof(float);
 					const size_t out_stride = Arena::padded((size_t)std::max<int64_t>(m, 1) * ch * sizeof(float)) / sizeof(float);
-					// A8: extract_samples_interleaved into one contiguous batch, then the whole-track SoundTouch
-					infra::Device_block staging(in_stride * sizeof(float) * cnt);
+					// A8: extract_samples_interleaved is the identity on float samples: FLT / FLTP streams are read in
+					// place through per-track pointers; integer formats are converted into one contiguous batch first
 					Arena arena(out_stride * sizeof(float) * cnt);
 					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
+					bool in_place = true;
 					for (size_t k = 0; k < cnt; k++)
 					{
-						const Audio_buffer& in = *all[first + k].in;
-						abi(nodey_extract_interleaved((float*)staging.ptr + k * in_stride, in.plane[0], in.plane[1], in.format, n, ch, cur_stream()), title);
+						const int f = all[first + k].in->format;
+						in_place = in_place && (f == FMT_FLT || f == FMT_FLTP) && f == all[first].in->format;
 					}
-					if (m > 0)
-						abi(nodey_soundtouch_run(st, out_base, (int64_t)out_stride, (const float*)staging.ptr, (int64_t)in_stride, (int)cnt, n,
-												 kSoundtouchFrame, m, nullptr, 0, cur_stream()), title);
+					if (in_place)
+					{
+						const bool planes = all[first].in->format == FMT_FLTP && ch == 2;
+						std::vector<const float*> pa(cnt), pb(cnt, nullptr);
+						for (size_t k = 0; k < cnt; k++)
+						{
+							pa[k] = (const float*)all[first + k].in->plane[0];
+							if (planes) pb[k] = (const float*)all[first + k].in->plane[1];
+						}
+						if (m > 0)
+							abi(nodey_soundtouch_run_tracks(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
+															kSoundtouchFrame, m, nullptr, 0, cur_stream()), title);
+					}
+					else
+					{
+						infra::Device_block staging(in_stride * sizeof(float) * cnt);
+						for (size_t k = 0; k < cnt; k++)
+						{
+							const Audio_buffer& in = *all[first + k].in;
+							abi(nodey_extract_interleaved((float*)staging.ptr + k * in_stride, in.plane[0], in.plane[1], in.format, n, ch, cur_stream()), title);
+						}
+						if (m > 0)
+							abi(nodey_soundtouch_run(st, out_base, (int64_t)out_stride, (const float*)staging.ptr, (int64_t)in_stride, (int)cnt, n,
+													 kSoundtouchFrame, m, nullptr, 0, cur_stream()), title);
+					}
 					for (size_t k = 0; k < cnt; k++)
 					{
 						const Entry& e = all[first + k];
@@ -790,8 +813,19 @@ namespace processor
 			std::vector<int64_t> lens;
 			for (int i = 0; i < nin; i++)
 			{
-				Resampled r = resample_input(*ins[(size_t)i], produced_of(segs, i), true, "Audio mixer");
 				int64_t len = 0;
+				const Audio_buffer& in = *ins[(size_t)i];
+				// 48 kHz stereo float that lands unbroken at 0: swr would only copy (FLTP) or de-interleave (FLT) it;
+				// the mix kernel reads it in place
+				if (in.sample_rate == 48000 && in.channels == 2 && (in.format == FMT_FLT || in.format == FMT_FLTP)
+					&& single_front_segment(segs, i, &len) && len <= in.frames)
+				{
+					pl.push_back((const float*)in.plane[0]);
+					pr.push_back(in.format == FMT_FLTP ? (const float*)in.plane[1] : nullptr);
+					lens.push_back(len);
+					continue;
+				}
+				Resampled r = resample_input(in, produced_of(segs, i), true, "Audio mixer");
 				if (!single_front_segment(segs, i, &len)) { r = scatter(r, segs, i, total, "Audio mixer"); len = total; }
 				pl.push_back(r.l); pr.push_back(r.r); lens.push_back(len);
 				keep.push_back(std::move(r));

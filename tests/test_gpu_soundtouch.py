@@ -118,3 +118,36 @@ def test_soundtouch_short_and_errors(nd, orc):
     assert e.value.code == -5
     with pytest.raises(nd.NodeyError):
         nd.SoundTouch(48000, 3, 1.0, 1.0)
+
+
+IN_PLACE = [
+    # (sample_rate, ch, rate, semitones-or-None, planar)
+    (48000, 2, 1.0, 3.0, True),        # TDStretch first: offsets + fused tail read the planes
+    (48000, 2, 1.0, 3.0, False),
+    (48000, 2, 0.8, None, True),       # rate <= 1: the cubic transposer reads the planes first
+    (44100, 2, 1.25, None, True),      # odd length: plane pointers not 8-byte aligned relative to each other
+    (48000, 1, 1.0, -2.0, False),      # mono
+]
+
+
+@pytest.mark.parametrize("unfused", [0, 1])
+@pytest.mark.parametrize("cfg", IN_PLACE, ids=[f"{c[0]}-{c[1]}ch-r{c[2]}-st{c[3]}-{'planar' if c[4] else 'packed'}" for c in IN_PLACE])
+def test_soundtouch_reads_tracks_in_place(nd, orc, cfg, unfused):
+    """nodey_soundtouch_run_tracks (per-track pointers, FLT or FLTP read in place) == the staged batch == the oracle"""
+    import torch
+    sr, ch, rate, st_, planar = cfg
+    pitch = orc.pitch_node_factor(st_) if st_ is not None else 1.0
+    n = int(sr * 2.5) + 7
+    xs = [orc.synth_f32(n, ch, sr, 20 + t) for t in range(3)]
+    st = nd.SoundTouch(sr, ch, rate, pitch)
+    st.set_unfused(unfused)
+    if planar:
+        devs = [(to_dev(np.ascontiguousarray(x[:, 0])), to_dev(np.ascontiguousarray(x[:, 1]))) for x in xs]
+    else:
+        devs = [to_dev(x) for x in xs]
+    got, offs = st.run_tracks(devs, 1152, want_offsets=True)
+    torch.cuda.synchronize()
+    for t, x in enumerate(xs):
+        ref, ref_offs, _ = orc.soundtouch(x, sr, rate, pitch, 1152)
+        assert np.array_equal(offs[t].cpu().numpy()[:len(ref_offs)], ref_offs), f"track {t}: WSOLA offset trace differs"
+        assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t} samples")
