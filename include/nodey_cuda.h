@@ -161,6 +161,15 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r,
                        const int* nch, const int64_t* in_frames, const int64_t* out_len,
                        const float* volumes, int nin, int flush, int64_t out_frames,
                        nodey_stream_t stream);
+/* The same for a BATCH of independent single-input mixers (the per-track audio_amix(1) resamplers of a render) in
+ * one launch: track t reads plane0[t] / plane1[t] (HOST arrays of device pointers; all tracks share format,
+ * channel count and length), is scaled by volumes[t] (temp = 0 + data*volume, audio-amix.cpp:296-304) and
+ * written to out_l/out_r + t*out_track_stride.  At most 256 tracks per call; exact-rational plans with at most
+ * 160 phases (NODEY_E_RANGE otherwise: fall back to nodey_resample_mix per track). */
+int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, int64_t out_track_stride,
+                          const void* const* plane0, const void* const* plane1, int fmt, int nch, int64_t in_frames,
+                          const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
+                          nodey_stream_t stream);
 
 /* A4  audio_amix frame bookkeeping (host only, no device work), audio-amix.cpp:149-322.  The node pulls
  * one frame per input and iteration, asks swr for nb = min(frame sizes) frames (1152 once the inputs

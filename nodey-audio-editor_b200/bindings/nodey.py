@@ -22,7 +22,7 @@ SYMBOLS = [
     "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
     "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
-    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
+    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
     "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
@@ -74,6 +74,7 @@ def lib():
     L.nodey_resampler_out_count.restype = i64
     L.nodey_resampler_run.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, vp]
     L.nodey_resampler_run_mode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, i32, vp]
+    L.nodey_resample_tracks.argtypes = [vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i64, C.POINTER(C.c_float), i32, i32, i64, i64, vp]
     L.nodey_resample_mix.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
                                      C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float), i32, i32, i64, vp]
     L.nodey_stft_frames.argtypes = [i64, i32, i32]
@@ -287,6 +288,27 @@ class Resampler:
         check(lib().nodey_resample_mix(self.h, _dp(out[0]), _dp(out[1]), p0, p1, fm, ch, inf, ol, vol, nin,
                                        1 if flush else 0, m, _stream()))
         return out
+
+
+def _resample_tracks(self, inputs, fmt, volumes, flush=True, out_len=None, out_frames=None):
+    """batch of independent single-input mixers (audio_amix(1) per track) in one launch -> [ntracks, 2, out_frames]"""
+    t = _torch()
+    ntr = len(inputs)
+    pls = [planes_of(x, fmt) for x in inputs]
+    n, nch = pls[0][2], pls[0][3]
+    ol = self.out_count(n, flush) if out_len is None else out_len
+    m = ol if out_frames is None else out_frames
+    stride = (m + 63) & ~63
+    out = t.empty((ntr, 2, stride), dtype=t.float32, device=inputs[0].device)
+    p0 = (C.c_void_p * ntr)(*[p[0].data_ptr() for p in pls])
+    p1 = (C.c_void_p * ntr)(*[(p[1].data_ptr() if p[1] is not None else 0) for p in pls])
+    vol = (C.c_float * ntr)(*[float(v) for v in volumes])
+    check(lib().nodey_resample_tracks(self.h, _dp(out[0, 0]), _dp(out[0, 1]), out.stride(0), p0, p1, fmt, nch, n, vol, ntr,
+                                      1 if flush else 0, ol, m, _stream()))
+    return out[:, :, :m]
+
+
+Resampler.resample_tracks = _resample_tracks
 
 
 def stft_frames(n, nfft=4096, hop=1024):

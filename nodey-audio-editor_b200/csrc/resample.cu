@@ -177,6 +177,9 @@ struct TileArgs {
     int out_stride;          // padded staging row stride (odd)
     long long out_frames;
     long long n_tiles;
+    int vec_out;             // 128-bit stores allowed: planes 16-byte aligned and P a multiple of 4
+    int ntracks;             // pipelined kernel: tracks of the batch (per-track planes in TrackPlanes), 1 otherwise
+    long long out_track_stride;   // floats between the output planes of consecutive tracks
 };
 
 // fast staging test: the whole tile lies inside the real input (no mirror / reflection / zero fill)
@@ -186,7 +189,7 @@ __device__ __forceinline__ bool tile_interior(const SrcDesc& s, long long in0, i
 }
 
 template <int CH>
-__global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+__global__ void __launch_bounds__(640, 2) resample_tile_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
                                                             const __grid_constant__ TileArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -206,6 +209,9 @@ __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ 
     for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const long long k0 = tile * (long long)kNB * a.P;               // first output frame of the tile
         const long long in0 = tile * (long long)kNB * a.D + a.s0 - a.center;  // first staged input frame
+        // direct mode (a single input, one group per warp -- e.g. the per-track 44.1 -> 48 kHz audio_amix(1): 20 groups
+        // on 20 warps): a thread's 8 outputs leave its registers as 128-bit stores; no staging rows, no copy-out pass
+        const bool direct = a.nin == 1 && nwarps >= a.n_groups;
 
         for (int inp = 0; inp < a.nin; inp++) {
             __syncthreads();   // previous use of s_in (and of the staging rows on a new tile) is over
@@ -266,34 +272,248 @@ __global__ void __launch_bounds__(640) resample_tile_kernel(float* __restrict__ 
                         }
                     }
                 }
-                // accumulate into the staging rows in input order: temp += data * volume (audio-amix.cpp:300-304)
+                // accumulate in input order: temp += data * volume (audio-amix.cpp:300-304)
+                if (direct) {
+                    const int ng = a.P - q * kG < kG ? a.P - q * kG : kG;             // phases of the last group may run short
+                    float o[kG][2];
+#pragma unroll
+                    for (int g = 0; g < kG; g++) {
+                        const bool live = (kq + g) < a.out_len[inp];
+                        float vl = live ? acc[g][0] : 0.f;
+                        float vr = live ? acc[g][CH - 1] : 0.f;
+                        if (a.mix) {
+                            vl = __fadd_rn(0.f, __fmul_rn(vl, vol));      // 0.0f: the reference's zeroed temp buffer
+                            vr = __fadd_rn(0.f, __fmul_rn(vr, vol));
+                        }
+                        o[g][0] = vl; o[g][1] = vr;
+                    }
+                    if (a.vec_out && ng == kG && kq + kG <= a.out_frames) {
+                        float4* gl = reinterpret_cast<float4*>(out_l + kq);
+                        float4* gr = reinterpret_cast<float4*>(out_r + kq);
+                        gl[0] = make_float4(o[0][0], o[1][0], o[2][0], o[3][0]);
+                        gl[1] = make_float4(o[4][0], o[5][0], o[6][0], o[7][0]);
+                        gr[0] = make_float4(o[0][1], o[1][1], o[2][1], o[3][1]);
+                        gr[1] = make_float4(o[4][1], o[5][1], o[6][1], o[7][1]);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < kG; g++)
+                            if (g < ng && kq + g < a.out_frames) { out_l[kq + g] = o[g][0]; out_r[kq + g] = o[g][1]; }
+                    }
+                    continue;
+                }
                 float* rl = s_out_l + lane * a.out_stride + q * kG;
                 float* rr = s_out_r + lane * a.out_stride + q * kG;
+                if (q * kG + kG <= a.P && kq + kG <= a.out_len[inp]) {
+                    // whole group live: no per-output tests
 #pragma unroll
-                for (int g = 0; g < kG; g++) {
-                    if (q * kG + g >= a.P) break;
-                    const bool live = (kq + g) < a.out_len[inp];
-                    float vl = live ? acc[g][0] : 0.f;
-                    float vr = live ? acc[g][CH - 1] : 0.f;
-                    if (a.mix) {
-                        const float pl = inp ? rl[g] : 0.f, pr = inp ? rr[g] : 0.f;
-                        vl = __fadd_rn(pl, __fmul_rn(vl, vol));
-                        vr = __fadd_rn(pr, __fmul_rn(vr, vol));
+                    for (int g = 0; g < kG; g++) {
+                        float vl = acc[g][0], vr = acc[g][CH - 1];
+                        if (a.mix) {
+                            const float pl = inp ? rl[g] : 0.f, pr = inp ? rr[g] : 0.f;
+                            vl = __fadd_rn(pl, __fmul_rn(vl, vol));
+                            vr = __fadd_rn(pr, __fmul_rn(vr, vol));
+                        }
+                        rl[g] = vl;
+                        rr[g] = vr;
                     }
-                    rl[g] = vl;
-                    rr[g] = vr;
+                } else {
+#pragma unroll
+                    for (int g = 0; g < kG; g++) {
+                        if (q * kG + g >= a.P) break;
+                        const bool live = (kq + g) < a.out_len[inp];
+                        float vl = live ? acc[g][0] : 0.f;
+                        float vr = live ? acc[g][CH - 1] : 0.f;
+                        if (a.mix) {
+                            const float pl = inp ? rl[g] : 0.f, pr = inp ? rr[g] : 0.f;
+                            vl = __fadd_rn(pl, __fmul_rn(vl, vol));
+                            vr = __fadd_rn(pr, __fmul_rn(vr, vol));
+                        }
+                        rl[g] = vl;
+                        rr[g] = vr;
+                    }
                 }
             }
         }
+        if (direct) continue;
         __syncthreads();
-        // coalesced copy-out of the tile (rows are NB periods of P frames)
+        // coalesced copy-out of the tile: warp w takes rows (periods) w, w + nwarps, ...; a row is P consecutive
+        // output frames, so the lanes walk it in 128-byte steps -- no division, no per-element index arithmetic
         const long long remain = a.out_frames - k0;
         const int n_out = (int)(remain < (long long)kNB * a.P ? remain : (long long)kNB * a.P);
-        for (int i = tid; i < n_out; i += nthr) {
-            const int b = i / a.P, t = i - b * a.P;
-            out_l[k0 + i] = s_out_l[b * a.out_stride + t];
-            out_r[k0 + i] = s_out_r[b * a.out_stride + t];
+        for (int b = warp; b < kNB; b += nwarps) {
+            const int row0 = b * a.P;
+            if (row0 >= n_out) break;
+            const int len = n_out - row0 < a.P ? n_out - row0 : a.P;
+            const float* sl = s_out_l + b * a.out_stride;
+            const float* sr = s_out_r + b * a.out_stride;
+            float* gl = out_l + k0 + row0;
+            float* gr = out_r + k0 + row0;
+            for (int t = lane; t < len; t += 32) { gl[t] = sl[t]; gr[t] = sr[t]; }
         }
+    }
+}
+
+// ---- tile kernel, pipelined ------------------------------------------------------------------------------
+// Same arithmetic as resample_tile_kernel for plans with one phase group per warp (P <= 160, e.g. 44.1 -> 48 kHz),
+// restructured after the ncu source view showed 39 % of the stall samples on the input staging loop:
+//  * the input tile is DOUBLE BUFFERED and filled with cp.async (LDGSTS): the tile of the next (track, tile, input)
+//    stage is in flight while the current one is filtered; one barrier per stage;
+//  * a thread keeps its 8 outputs in registers across the inputs of a mix (MIX) and writes them with 128-bit
+//    stores: no shared staging rows, no copy-out pass;
+//  * a launch covers a BATCH of tracks (per-track source planes and volume ride in the kernel parameters), so the
+//    256 per-track audio_amix(1) resamplers of a render are one persistent grid instead of 256 launches.
+constexpr int kMaxResampleBatch = 256;
+struct TrackPlanes {
+    const void* p0[kMaxResampleBatch];
+    const void* p1[kMaxResampleBatch];
+    float vol[kMaxResampleBatch];
+};
+
+__device__ __forceinline__ void rs_cp_async4(float* dst_smem, const float* src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async8(float* dst_smem, const float* src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
+}
+
+template <int CH, bool MIX>
+__global__ void __launch_bounds__(640, MIX ? 1 : 2) resample_tile2_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                                          const __grid_constant__ TileArgs a,
+                                                                          const __grid_constant__ TrackPlanes tp)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [hq: n_groups*wmax*G floats][group_start: n_groups ints][input tile 0][input tile 1]
+    float* s_hq = reinterpret_cast<float*>(smem_raw);
+    int* s_gs = reinterpret_cast<int*>(s_hq + a.n_groups * a.wmax * kG);
+    float* s_in0 = reinterpret_cast<float*>(s_gs + ((a.n_groups + 3) & ~3));
+    const int buf_floats = (a.in_tile * CH + 3) & ~3;
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int q = tid >> 5, lane = tid & 31;           // one phase group per warp
+
+    for (int i = tid; i < a.n_groups * a.wmax * kG; i += nthr) s_hq[i] = a.hq[i];
+    for (int i = tid; i < a.n_groups; i += nthr) s_gs[i] = a.group_start[i];
+
+    const long long total = a.n_tiles * (long long)a.ntracks;
+    const int nin = MIX ? a.nin : 1;                  // compile-time 1 without MIX: the accumulators die with the stage
+
+    // stage (item, inp): fill `dst` with the input tile -- asynchronously when the tile is an interior run of float frames
+    const auto stage = [&](long long item, int inp, float* dst) {
+        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
+        const long long k0 = tile * (long long)kNB * a.P;
+        if (k0 >= a.out_len[inp]) return;                       // contributes zeros: nothing is read
+        const long long in0 = tile * (long long)kNB * a.D + a.s0 - a.center;
+        SrcDesc s = a.src[inp];
+        if (!MIX) { s.p0 = tp.p0[track]; s.p1 = tp.p1[track]; }
+        const bool interior = tile_interior(s, in0, a.in_tile);
+        if (CH == 2 && interior && s.fmt == NODEY_FMT_FLT && (((uintptr_t)s.p0) & 7) == 0) {
+            const float* src = reinterpret_cast<const float*>(s.p0) + 2 * in0;
+            for (int f = tid; f < a.in_tile; f += nthr) rs_cp_async8(dst + 2 * f, src + 2 * f);
+        } else if (CH == 2 && interior && s.fmt == NODEY_FMT_FLTP) {
+            const float* sl = reinterpret_cast<const float*>(s.p0) + in0;
+            const float* sr = reinterpret_cast<const float*>(s.p1) + in0;
+            for (int f = tid; f < a.in_tile; f += nthr) { rs_cp_async4(dst + 2 * f, sl + f); rs_cp_async4(dst + 2 * f + 1, sr + f); }
+        } else if (CH == 2) {
+            float2* d2 = reinterpret_cast<float2*>(dst);
+            for (int f = tid; f < a.in_tile; f += nthr) d2[f] = src_frame(s, in0 + f);
+        } else {
+            for (int f = tid; f < a.in_tile; f += nthr) dst[f] = src_frame(s, in0 + f).x;
+        }
+    };
+
+    long long item = blockIdx.x;
+    int inp = 0, cur = 0;
+    if (item < total) stage(item, 0, s_in0);
+    float macc[kG][2];
+#pragma unroll
+    for (int g = 0; g < kG; g++) macc[g][0] = macc[g][1] = 0.f;
+
+    while (item < total) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();          // this stage's tile has landed; everybody is done reading the other buffer
+        long long nitem = item; int ninp = inp + 1;
+        if (ninp >= nin) { ninp = 0; nitem += gridDim.x; }
+        if (nitem < total) stage(nitem, ninp, s_in0 + (cur ^ 1) * buf_floats);
+
+        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
+        const long long k0 = tile * (long long)kNB * a.P;
+        const float* s_in = s_in0 + cur * buf_floats;
+        const float vol = MIX ? a.vol[inp] : tp.vol[track];
+        if (q < a.n_groups) {
+            float acc[kG][CH];
+#pragma unroll
+            for (int g = 0; g < kG; g++)
+#pragma unroll
+                for (int c = 0; c < CH; c++) acc[g][c] = 0.f;
+            const long long kq = k0 + (long long)lane * a.P + (long long)q * kG;   // first output of this thread
+            if (k0 < a.out_len[inp] && kq < a.out_frames) {
+                const float* hq = s_hq + q * a.wmax * kG;
+                const int base = lane * a.D + s_gs[q];
+                if (CH == 2) {
+                    const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
+#pragma unroll 4
+                    for (int m = 0; m < a.wmax; m++) {
+                        const float2 x = x2[m];
+                        const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
+                        const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
+                        acc[0][0] = __fmaf_rn(x.x, h0.x, acc[0][0]); acc[0][CH - 1] = __fmaf_rn(x.y, h0.x, acc[0][CH - 1]);
+                        acc[1][0] = __fmaf_rn(x.x, h0.y, acc[1][0]); acc[1][CH - 1] = __fmaf_rn(x.y, h0.y, acc[1][CH - 1]);
+                        acc[2][0] = __fmaf_rn(x.x, h0.z, acc[2][0]); acc[2][CH - 1] = __fmaf_rn(x.y, h0.z, acc[2][CH - 1]);
+                        acc[3][0] = __fmaf_rn(x.x, h0.w, acc[3][0]); acc[3][CH - 1] = __fmaf_rn(x.y, h0.w, acc[3][CH - 1]);
+                        acc[4][0] = __fmaf_rn(x.x, h1.x, acc[4][0]); acc[4][CH - 1] = __fmaf_rn(x.y, h1.x, acc[4][CH - 1]);
+                        acc[5][0] = __fmaf_rn(x.x, h1.y, acc[5][0]); acc[5][CH - 1] = __fmaf_rn(x.y, h1.y, acc[5][CH - 1]);
+                        acc[6][0] = __fmaf_rn(x.x, h1.z, acc[6][0]); acc[6][CH - 1] = __fmaf_rn(x.y, h1.z, acc[6][CH - 1]);
+                        acc[7][0] = __fmaf_rn(x.x, h1.w, acc[7][0]); acc[7][CH - 1] = __fmaf_rn(x.y, h1.w, acc[7][CH - 1]);
+                    }
+                } else {
+                    const float* x1 = s_in + base;
+#pragma unroll 4
+                    for (int m = 0; m < a.wmax; m++) {
+                        const float x = x1[m];
+                        const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
+                        const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
+                        acc[0][0] = __fmaf_rn(x, h0.x, acc[0][0]); acc[1][0] = __fmaf_rn(x, h0.y, acc[1][0]);
+                        acc[2][0] = __fmaf_rn(x, h0.z, acc[2][0]); acc[3][0] = __fmaf_rn(x, h0.w, acc[3][0]);
+                        acc[4][0] = __fmaf_rn(x, h1.x, acc[4][0]); acc[5][0] = __fmaf_rn(x, h1.y, acc[5][0]);
+                        acc[6][0] = __fmaf_rn(x, h1.z, acc[6][0]); acc[7][0] = __fmaf_rn(x, h1.w, acc[7][0]);
+                    }
+                }
+            }
+            // accumulate in input order: temp += data * volume, temp zeroed first (audio-amix.cpp:296-304)
+#pragma unroll
+            for (int g = 0; g < kG; g++) {
+                const bool live = (kq + g) < a.out_len[inp];
+                float vl = live ? acc[g][0] : 0.f;
+                float vr = live ? acc[g][CH - 1] : 0.f;
+                if (a.mix) {
+                    vl = __fadd_rn((MIX && inp) ? macc[g][0] : 0.f, __fmul_rn(vl, vol));
+                    vr = __fadd_rn((MIX && inp) ? macc[g][1] : 0.f, __fmul_rn(vr, vol));
+                }
+                macc[g][0] = vl; macc[g][1] = vr;
+            }
+            if (inp == nin - 1) {
+                float* gl0 = out_l + track * a.out_track_stride;
+                float* gr0 = out_r + track * a.out_track_stride;
+                const int ng = a.P - q * kG < kG ? a.P - q * kG : kG;             // phases of the last group may run short
+                if (a.vec_out && ng == kG && kq + kG <= a.out_frames) {
+                    float4* gl = reinterpret_cast<float4*>(gl0 + kq);
+                    float4* gr = reinterpret_cast<float4*>(gr0 + kq);
+                    gl[0] = make_float4(macc[0][0], macc[1][0], macc[2][0], macc[3][0]);
+                    gl[1] = make_float4(macc[4][0], macc[5][0], macc[6][0], macc[7][0]);
+                    gr[0] = make_float4(macc[0][1], macc[1][1], macc[2][1], macc[3][1]);
+                    gr[1] = make_float4(macc[4][1], macc[5][1], macc[6][1], macc[7][1]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < kG; g++)
+                        if (g < ng && kq + g < a.out_frames) { gl0[kq + g] = macc[g][0]; gr0[kq + g] = macc[g][1]; }
+                }
+            }
+        }
+        item = nitem; inp = ninp; cur ^= 1;
     }
 }
 
@@ -517,6 +737,7 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
     a.hq = r->d_hq; a.group_start = r->d_group_start;
     const size_t smem = tile_geometry(r, a, ch);
     a.n_tiles = (a.out_frames + (int64_t)kNB * a.P - 1) / ((int64_t)kNB * a.P);
+    a.vec_out = (((uintptr_t)out_l | (uintptr_t)out_r) & 15) == 0 && a.P % 4 == 0;
     NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
     int threads = 32 * (a.n_groups < 20 ? a.n_groups : 20);
     const int ctas_per_sm = smem > 113 * 1024 ? 1 : 2;
@@ -535,7 +756,37 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
     return NODEY_OK;
 }
 
-// mode: 0 auto, 1 force generic, 2 force tile (testing hook, not in the public header)
+// pipelined tile kernel: plans with one phase group per warp
+static bool tile2_ok(const nodey_resampler* r) { return r->tile_ok && r->n_groups <= 20; }
+
+static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, const TrackPlanes& tp, int ch, cudaStream_t st)
+{
+    a.hq = r->d_hq; a.group_start = r->d_group_start;
+    tile_geometry(r, a, ch);
+    const size_t buf_floats = ((size_t)a.in_tile * ch + 3) & ~(size_t)3;
+    const size_t smem = sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) + 2 * buf_floats);
+    NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
+    a.n_tiles = (a.out_frames + (int64_t)kNB * a.P - 1) / ((int64_t)kNB * a.P);
+    if (a.ntracks < 1) a.ntracks = 1;
+    a.vec_out = (((uintptr_t)out_l | (uintptr_t)out_r) & 15) == 0 && a.P % 4 == 0 && a.out_track_stride % 4 == 0;
+    const bool mix = a.nin > 1;
+    const int threads = 32 * a.n_groups;
+    const int ctas_per_sm = (mix || smem > 113 * 1024) ? 1 : 2;
+    const int64_t total = a.n_tiles * a.ntracks;
+    int grid = (int)(total < (int64_t)sm_count() * ctas_per_sm ? total : (int64_t)sm_count() * ctas_per_sm);
+    if (grid < 1) grid = 1;
+    void (*kern)(float*, float*, TileArgs, TrackPlanes) =
+        ch == 2 ? (mix ? resample_tile2_kernel<2, true> : resample_tile2_kernel<2, false>)
+                : (mix ? resample_tile2_kernel<1, true> : resample_tile2_kernel<1, false>);
+    NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    NODEY_LAUNCH("resample_tile_kernel", st, kern<<<grid, threads, smem, st>>>(out_l, out_r, a, tp));
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+// mode: 0 auto, 1 force generic, 2 force the staging-row tile kernel, 3 force the pipelined tile kernel
+// (testing hook, not in the public header)
 int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_r, const void* p0, const void* p1,
                              int fmt, int nch, int64_t in_frames, int flush, int64_t out_frames, int mode,
                              nodey_stream_t stream)
@@ -550,13 +801,20 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
     NODEY_REQUIRE(out_frames >= 0 && out_frames <= avail, NODEY_E_RANGE,
                   "nodey_resampler_run: out_frames %lld exceeds what swr would produce (%lld)", (long long)out_frames, (long long)avail);
     if (out_frames == 0) return NODEY_OK;
-    if ((mode == 0 && r->tile_ok) || mode == 2) {
+    if ((mode == 0 && r->tile_ok) || mode == 2 || mode == 3) {
         NODEY_REQUIRE(r->tile_ok, NODEY_E_RANGE, "tile kernel unavailable for this plan");
+        NODEY_REQUIRE(mode != 3 || tile2_ok(r), NODEY_E_RANGE, "pipelined tile kernel unavailable for this plan");
         TileArgs a;
         memset(&a, 0, sizeof(a));
         int rc = fill_src(&a.src[0], r, p0, p1, fmt, nch, in_frames, flush);
         if (rc != NODEY_OK) return rc;
         a.out_len[0] = out_frames; a.vol[0] = 1.f; a.nin = 1; a.mix = 0; a.out_frames = out_frames;
+        if (mode == 3 || (mode == 0 && tile2_ok(r))) {
+            static thread_local TrackPlanes tp;
+            tp.p0[0] = p0; tp.p1[0] = p1; tp.vol[0] = 1.f;
+            a.ntracks = 1; a.out_track_stride = 0;
+            return launch_tile2(r, out_l, out_r, a, tp, nch, st);
+        }
         return launch_tile(r, out_l, out_r, a, nch, st);
     }
     SrcDesc s;
@@ -597,7 +855,40 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r, con
         a.vol[i] = volumes[i];
     }
     a.nin = nin; a.mix = 1; a.out_frames = out_frames;
+    if (tile2_ok(r)) {
+        static thread_local TrackPlanes tp;
+        tp.p0[0] = plane0[0]; tp.p1[0] = plane1 ? plane1[0] : nullptr; tp.vol[0] = volumes[0];
+        a.ntracks = 1; a.out_track_stride = 0;
+        return launch_tile2(r, out_l, out_r, a, tp, ch, as_stream(stream));
+    }
     return launch_tile(r, out_l, out_r, a, ch, as_stream(stream));
+}
+
+int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, int64_t out_track_stride,
+                          const void* const* plane0, const void* const* plane1, int fmt, int nch, int64_t in_frames,
+                          const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
+                          nodey_stream_t stream)
+{
+    NODEY_REQUIRE(r && out_l && out_r && plane0 && volumes, NODEY_E_INVALID, "nodey_resample_tracks: null argument");
+    NODEY_REQUIRE(ntracks >= 1 && ntracks <= kMaxResampleBatch, NODEY_E_RANGE, "nodey_resample_tracks: 1..%d tracks per call", kMaxResampleBatch);
+    NODEY_REQUIRE(r->resample && tile2_ok(r), NODEY_E_RANGE, "nodey_resample_tracks: plan has no pipelined tile kernel (use nodey_resample_mix per track)");
+    NODEY_REQUIRE(out_track_stride >= out_frames, NODEY_E_INVALID, "nodey_resample_tracks: out_track_stride smaller than out_frames");
+    if (out_frames <= 0) return out_frames == 0 ? NODEY_OK : NODEY_E_INVALID;
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_src(&a.src[0], r, plane0[0], plane1 ? plane1[0] : nullptr, fmt, nch, in_frames, flush);
+    if (rc != NODEY_OK) return rc;
+    const int64_t avail = nodey_resampler_out_count(r, in_frames, flush);
+    NODEY_REQUIRE(out_len >= 0 && out_len <= avail, NODEY_E_RANGE,
+                  "nodey_resample_tracks: out_len %lld exceeds what swr would produce (%lld)", (long long)out_len, (long long)avail);
+    a.out_len[0] = out_len; a.vol[0] = volumes[0]; a.nin = 1; a.mix = 1; a.out_frames = out_frames;
+    a.ntracks = ntracks; a.out_track_stride = out_track_stride;
+    static thread_local TrackPlanes tp;
+    for (int t = 0; t < ntracks; t++) {
+        NODEY_REQUIRE(plane0[t], NODEY_E_INVALID, "nodey_resample_tracks: null plane");
+        tp.p0[t] = plane0[t]; tp.p1[t] = plane1 ? plane1[t] : nullptr; tp.vol[t] = volumes[t];
+    }
+    return launch_tile2(r, out_l, out_r, a, tp, nch, as_stream(stream));
 }
 
 /* audio_amix frame bookkeeping, audio-amix.cpp:149-322 (see nodey_cuda.h) */

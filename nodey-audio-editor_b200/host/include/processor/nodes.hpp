@@ -151,6 +151,7 @@ namespace processor
 		NODEY_NODE_COMMON(Audio_amix)
 		virtual Json::Value serialize() const;
 		virtual void deserialize(const Json::Value& value);
+		virtual bool process_batch(const std::vector<Batch_item>& items);
 	};
 
 	class Audio_bimix : public infra::Processor

@@ -717,124 +717,212 @@ namespace processor
 		}
 	}
 
-	void Audio_amix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	namespace
 	{
-		const int nin = input_num;
-		std::vector<std::shared_ptr<const Audio_buffer>> ins;
-		std::vector<const Frame_runs*> runs;
-		std::vector<int> rates;
-		for (int i = 0; i < nin; i++)
-		{
-			ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer"));
-			check_channels(*ins.back(), "Audio mixer");
-			runs.push_back(&ins.back()->runs);
-			rates.push_back(ins.back()->sample_rate);
-		}
-		std::vector<float> vol(volumes);
-		vol.resize((size_t)nin, 1.0f);
-
 		// frame bookkeeping of the reference loop: total length, placement of every input, own frame sizes
-		// (cached: the 256 per-track amix nodes of a batch render share one plan)
-		const Runs_flat flat(runs);
-		struct Plan { int64_t total = 0; std::vector<Segment> segs; Frame_runs out_runs; };
-		static std::map<std::vector<int64_t>, std::shared_ptr<const Plan>> plan_cache;
-		std::vector<int64_t> key;
-		for (const int r : rates) key.push_back(r);
-		key.push_back(-1);
-		key.insert(key.end(), flat.off.begin(), flat.off.end());
-		key.push_back(-1);
-		key.insert(key.end(), flat.len.begin(), flat.len.end());
-		key.push_back(-1);
-		key.insert(key.end(), flat.count.begin(), flat.count.end());
-		std::shared_ptr<const Plan> plan;
-		{
-			std::lock_guard lock(plan_mutex);
-			const auto it = plan_cache.find(key);
-			if (it != plan_cache.end()) plan = it->second;
-		}
-		if (!plan)
-		{
-			auto fresh = std::make_shared<Plan>();
-			std::vector<int32_t> seg_in(64);
-			std::vector<int64_t> seg_out(64), seg_src(64), seg_len(64), run_len(64), run_cnt(64);
-			int64_t nseg = 0, nrun = 0;
-			for (int attempt = 0; attempt < 2; attempt++)
-			{
-				fresh->total = nodey_amix_plan(rates.data(), nin, flat.off.data(), flat.len.data(), flat.count.data(), 0, seg_in.data(),
-											   seg_out.data(), seg_src.data(), seg_len.data(), (int64_t)seg_in.size(), &nseg, run_len.data(),
-											   run_cnt.data(), (int64_t)run_len.size(), &nrun);
-				if (fresh->total < 0) abi((int)fresh->total, "Audio mixer");
-				if (nseg <= (int64_t)seg_in.size() && nrun <= (int64_t)run_len.size()) break;
-				const size_t a = (size_t)std::max<int64_t>(nseg, 64), b = (size_t)std::max<int64_t>(nrun, 64);
-				seg_in.resize(a); seg_out.resize(a); seg_src.resize(a); seg_len.resize(a); run_len.resize(b); run_cnt.resize(b);
-			}
-			for (int64_t k = 0; k < nseg; k++) fresh->segs.push_back({seg_in[(size_t)k], seg_out[(size_t)k], seg_src[(size_t)k], seg_len[(size_t)k]});
-			for (int64_t k = 0; k < nrun; k++) fresh->out_runs.emplace_back(run_len[(size_t)k], run_cnt[(size_t)k]);
-			std::lock_guard lock(plan_mutex);
-			if (plan_cache.size() > 256) plan_cache.clear();
-			plan_cache[key] = fresh;
-			plan = fresh;
-		}
-		const int64_t total = plan->total;
-		const std::vector<Segment>& segs = plan->segs;
-		Frame_runs out_runs = plan->out_runs;
+		struct Amix_plan { int64_t total = 0; std::vector<Segment> segs; Frame_runs out_runs; };
 
-		const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
-		auto block = std::make_shared<infra::Device_block>(2 * plane);
-		float* out_l = (float*)block->ptr;
-		float* out_r = (float*)((char*)block->ptr + plane);
+		// everything process_payload decides before it touches the device
+		struct Amix_job
+		{
+			std::vector<std::shared_ptr<const Audio_buffer>> ins;
+			std::vector<float> vol;
+			std::shared_ptr<const Amix_plan> plan;
+			bool fused = false;     // same-rate inputs that need resampling, each landing unbroken at 0, exact-rational plan
+			std::vector<int64_t> front_len;
+		};
 
-		// fused path: same source rate (needs resampling), same channel count, every input lands unbroken at 0
-		bool fused = total > 0;
-		std::vector<int64_t> front_len((size_t)nin, 0);
-		for (int i = 0; i < nin && fused; i++)
-			fused = ins[(size_t)i]->sample_rate == ins[0]->sample_rate && ins[(size_t)i]->sample_rate != 48000
-				 && ins[(size_t)i]->channels == ins[0]->channels && single_front_segment(segs, i, &front_len[(size_t)i]);
-		if (fused)
+		Amix_job amix_prepare(int nin, const std::vector<float>& volumes, const Processor::Input_map& input)
 		{
-			int info[8];
-			abi(nodey_resampler_info(resampler_for(ins[0]->sample_rate), info), "Audio mixer");
-			fused = info[4] == 0;     // exact-rational plan: the tiled kernel exists
-		}
-		if (total > 0 && fused)
-		{
-			std::vector<const void*> p0, p1;
-			std::vector<int> fmt, ch;
-			std::vector<int64_t> in_frames;
-			for (const auto& in : ins) { p0.push_back(in->plane[0]); p1.push_back(in->plane[1]); fmt.push_back(in->format); ch.push_back(in->channels); in_frames.push_back(in->frames); }
-			const int rc = nodey_resample_mix(resampler_for(ins[0]->sample_rate), out_l, out_r, p0.data(), p1.data(), fmt.data(), ch.data(),
-											  in_frames.data(), front_len.data(), vol.data(), nin, 1, total, cur_stream());
-			if (rc == NODEY_E_RANGE) fused = false; else abi(rc, "Audio mixer");
-		}
-		if (total > 0 && !fused)
-		{
-			std::vector<Resampled> keep;
-			std::vector<const float*> pl, pr;
-			std::vector<int64_t> lens;
+			Amix_job job;
+			std::vector<const Frame_runs*> runs;
+			std::vector<int> rates;
 			for (int i = 0; i < nin; i++)
 			{
-				int64_t len = 0;
-				const Audio_buffer& in = *ins[(size_t)i];
-				// 48 kHz stereo float that lands unbroken at 0: swr would only copy (FLTP) or de-interleave (FLT) it;
-				// the mix kernel reads it in place
-				if (in.sample_rate == 48000 && in.channels == 2 && (in.format == FMT_FLT || in.format == FMT_FLTP)
-					&& single_front_segment(segs, i, &len) && len <= in.frames)
-				{
-					pl.push_back((const float*)in.plane[0]);
-					pr.push_back(in.format == FMT_FLTP ? (const float*)in.plane[1] : nullptr);
-					lens.push_back(len);
-					continue;
-				}
-				Resampled r = resample_input(in, produced_of(segs, i), true, "Audio mixer");
-				if (!single_front_segment(segs, i, &len)) { r = scatter(r, segs, i, total, "Audio mixer"); len = total; }
-				pl.push_back(r.l); pr.push_back(r.r); lens.push_back(len);
-				keep.push_back(std::move(r));
+				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer"));
+				check_channels(*job.ins.back(), "Audio mixer");
+				runs.push_back(&job.ins.back()->runs);
+				rates.push_back(job.ins.back()->sample_rate);
 			}
-			abi(nodey_mix(out_l, out_r, pl.data(), pr.data(), lens.data(), vol.data(), nin, total, cur_stream()), "Audio mixer");
+			job.vol = volumes;
+			job.vol.resize((size_t)nin, 1.0f);
+
+			// (cached: the 256 per-track amix nodes of a batch render share one plan)
+			const Runs_flat flat(runs);
+			static std::map<std::vector<int64_t>, std::shared_ptr<const Amix_plan>> plan_cache;
+			std::vector<int64_t> key;
+			for (const int r : rates) key.push_back(r);
+			key.push_back(-1);
+			key.insert(key.end(), flat.off.begin(), flat.off.end());
+			key.push_back(-1);
+			key.insert(key.end(), flat.len.begin(), flat.len.end());
+			key.push_back(-1);
+			key.insert(key.end(), flat.count.begin(), flat.count.end());
+			{
+				std::lock_guard lock(plan_mutex);
+				const auto it = plan_cache.find(key);
+				if (it != plan_cache.end()) job.plan = it->second;
+			}
+			if (!job.plan)
+			{
+				auto fresh = std::make_shared<Amix_plan>();
+				std::vector<int32_t> seg_in(64);
+				std::vector<int64_t> seg_out(64), seg_src(64), seg_len(64), run_len(64), run_cnt(64);
+				int64_t nseg = 0, nrun = 0;
+				for (int attempt = 0; attempt < 2; attempt++)
+				{
+					fresh->total = nodey_amix_plan(rates.data(), nin, flat.off.data(), flat.len.data(), flat.count.data(), 0, seg_in.data(),
+												   seg_out.data(), seg_src.data(), seg_len.data(), (int64_t)seg_in.size(), &nseg, run_len.data(),
+												   run_cnt.data(), (int64_t)run_len.size(), &nrun);
+					if (fresh->total < 0) abi((int)fresh->total, "Audio mixer");
+					if (nseg <= (int64_t)seg_in.size() && nrun <= (int64_t)run_len.size()) break;
+					const size_t a = (size_t)std::max<int64_t>(nseg, 64), b = (size_t)std::max<int64_t>(nrun, 64);
+					seg_in.resize(a); seg_out.resize(a); seg_src.resize(a); seg_len.resize(a); run_len.resize(b); run_cnt.resize(b);
+				}
+				for (int64_t k = 0; k < nseg; k++) fresh->segs.push_back({seg_in[(size_t)k], seg_out[(size_t)k], seg_src[(size_t)k], seg_len[(size_t)k]});
+				for (int64_t k = 0; k < nrun; k++) fresh->out_runs.emplace_back(run_len[(size_t)k], run_cnt[(size_t)k]);
+				std::lock_guard lock(plan_mutex);
+				if (plan_cache.size() > 256) plan_cache.clear();
+				plan_cache[key] = fresh;
+				job.plan = fresh;
+			}
+
+			// fused path: same source rate (needs resampling), same channel count, every input lands unbroken at 0
+			job.fused = job.plan->total > 0;
+			job.front_len.assign((size_t)nin, 0);
+			for (int i = 0; i < nin && job.fused; i++)
+				job.fused = job.ins[(size_t)i]->sample_rate == job.ins[0]->sample_rate && job.ins[(size_t)i]->sample_rate != 48000
+						 && job.ins[(size_t)i]->channels == job.ins[0]->channels && single_front_segment(job.plan->segs, i, &job.front_len[(size_t)i]);
+			if (job.fused)
+			{
+				int info[8];
+				abi(nodey_resampler_info(resampler_for(job.ins[0]->sample_rate), info), "Audio mixer");
+				job.fused = info[4] == 0;     // exact-rational plan: the tiled kernel exists
+			}
+			return job;
 		}
-		// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
-		const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;
-		publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), pts));
+
+		void amix_publish(const Amix_job& job, const Processor::Output_map& output, const std::shared_ptr<infra::Device_block>& block,
+						  float* out_l, float* out_r)
+		{
+			// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
+			Frame_runs out_runs = job.plan->out_runs;
+			const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;
+			publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), pts));
+		}
+
+		void amix_execute(Amix_job& job, const Processor::Output_map& output)
+		{
+			const int nin = (int)job.ins.size();
+			const auto& ins = job.ins;
+			const int64_t total = job.plan->total;
+			const std::vector<Segment>& segs = job.plan->segs;
+			bool fused = job.fused;
+
+			const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+			auto block = std::make_shared<infra::Device_block>(2 * plane);
+			float* out_l = (float*)block->ptr;
+			float* out_r = (float*)((char*)block->ptr + plane);
+
+			if (total > 0 && fused)
+			{
+				std::vector<const void*> p0, p1;
+				std::vector<int> fmt, ch;
+				std::vector<int64_t> in_frames;
+				for (const auto& in : ins) { p0.push_back(in->plane[0]); p1.push_back(in->plane[1]); fmt.push_back(in->format); ch.push_back(in->channels); in_frames.push_back(in->frames); }
+				const int rc = nodey_resample_mix(resampler_for(ins[0]->sample_rate), out_l, out_r, p0.data(), p1.data(), fmt.data(), ch.data(),
+												  in_frames.data(), job.front_len.data(), job.vol.data(), nin, 1, total, cur_stream());
+				if (rc == NODEY_E_RANGE) fused = false; else abi(rc, "Audio mixer");
+			}
+			if (total > 0 && !fused)
+			{
+				std::vector<Resampled> keep;
+				std::vector<const float*> pl, pr;
+				std::vector<int64_t> lens;
+				for (int i = 0; i < nin; i++)
+				{
+					int64_t len = 0;
+					const Audio_buffer& in = *ins[(size_t)i];
+					// 48 kHz stereo float that lands unbroken at 0: swr would only copy (FLTP) or de-interleave (FLT) it;
+					// the mix kernel reads it in place
+					if (in.sample_rate == 48000 && in.channels == 2 && (in.format == FMT_FLT || in.format == FMT_FLTP)
+						&& single_front_segment(segs, i, &len) && len <= in.frames)
+					{
+						pl.push_back((const float*)in.plane[0]);
+						pr.push_back(in.format == FMT_FLTP ? (const float*)in.plane[1] : nullptr);
+						lens.push_back(len);
+						continue;
+					}
+					Resampled r = resample_input(in, produced_of(segs, i), true, "Audio mixer");
+					if (!single_front_segment(segs, i, &len)) { r = scatter(r, segs, i, total, "Audio mixer"); len = total; }
+					pl.push_back(r.l); pr.push_back(r.r); lens.push_back(len);
+					keep.push_back(std::move(r));
+				}
+				abi(nodey_mix(out_l, out_r, pl.data(), pr.data(), lens.data(), job.vol.data(), nin, total, cur_stream()), "Audio mixer");
+			}
+			amix_publish(job, output, block, out_l, out_r);
+		}
+	}
+
+	void Audio_amix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
+	{
+		Amix_job job = amix_prepare(input_num, volumes, input);
+		amix_execute(job, output);
+	}
+
+	// Batch: the single-input mixers of one level that resample the same kind of stream (the per-track audio_amix(1)
+	// nodes of a multitrack render) become ONE launch over all their tracks; every other node runs as it would alone.
+	bool Audio_amix::process_batch(const std::vector<Batch_item>& items)
+	{
+		constexpr size_t kMaxTracks = 256;
+		std::vector<Amix_job> jobs;
+		std::map<std::tuple<int, int, int, int64_t, int64_t, int64_t>, std::vector<size_t>> groups;
+		for (size_t k = 0; k < items.size(); k++)
+		{
+			const auto* node = static_cast<const Audio_amix*>(items[k].processor);
+			jobs.push_back(amix_prepare(node->input_num, node->volumes, *items[k].input));
+			const Amix_job& job = jobs.back();
+			if (job.ins.size() == 1 && job.fused)
+			{
+				const Audio_buffer& in = *job.ins[0];
+				groups[{in.sample_rate, in.format, in.channels, in.frames, job.plan->total, job.front_len[0]}].push_back(k);
+			}
+		}
+		std::vector<bool> done(items.size(), false);
+		for (const auto& [key, members] : groups)
+		{
+			if (members.size() < 2) continue;
+			const auto [rate, fmt, ch, frames, total, front] = key;
+			for (size_t first = 0; first < members.size(); first += kMaxTracks)
+			{
+				const size_t cnt = std::min(kMaxTracks, members.size() - first);
+				const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+				auto block = std::make_shared<infra::Device_block>(2 * plane * cnt);
+				float* base = (float*)block->ptr;
+				std::vector<const void*> p0(cnt), p1(cnt);
+				std::vector<float> vol(cnt);
+				for (size_t t = 0; t < cnt; t++)
+				{
+					const Amix_job& job = jobs[members[first + t]];
+					p0[t] = job.ins[0]->plane[0]; p1[t] = job.ins[0]->plane[1]; vol[t] = job.vol[0];
+				}
+				// track t: left plane at base + 2t * plane, right plane one plane further
+				const int rc = nodey_resample_tracks(resampler_for(rate), base, base + plane / sizeof(float), (int64_t)(2 * plane / sizeof(float)),
+													 p0.data(), p1.data(), fmt, ch, frames, vol.data(), (int)cnt, 1, front, total, cur_stream());
+				if (rc == NODEY_E_RANGE) break;      // no pipelined kernel for this plan: the members run one by one below
+				abi(rc, "Audio mixer");
+				for (size_t t = 0; t < cnt; t++)
+				{
+					const size_t k = members[first + t];
+					float* out_l = base + 2 * t * (plane / sizeof(float));
+					amix_publish(jobs[k], *items[k].output, block, out_l, out_l + plane / sizeof(float));
+					done[k] = true;
+				}
+			}
+		}
+		for (size_t k = 0; k < items.size(); k++)
+			if (!done[k]) amix_execute(jobs[k], *items[k].output);
+		return true;
 	}
 
 	// ---------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ def test_plan_matches_oracle(nd, orc):
             r.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("fmt", ALL_FMTS)
 @pytest.mark.parametrize("nch", [1, 2])
 def test_resample_441_to_48_bit_exact(nd, orc, mode, fmt, nch):
@@ -58,7 +58,7 @@ def test_resample_short_inputs(nd, orc, n):
     r = nd.Resampler(44100, 48000)
     assert r.out_count(n, True) == len(rl)
     if len(rl):
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             got = r.run(to_dev(x), FMT_FLT, flush=True, mode=mode).cpu().numpy()
             assert_bit_equal(got[0], rl, f"short L mode {mode}")
             assert_bit_equal(got[1], rr, f"short R mode {mode}")
@@ -116,3 +116,30 @@ def test_amix_mixed_formats_unfused(nd, orc):
     assert_bit_equal(got[0], rl[:m], "amix mixed L")
     assert_bit_equal(got[1], rr[:m], "amix mixed R")
     assert not rl[m:].any()
+
+
+@pytest.mark.parametrize("fmt", [FMT_FLT, FMT_FLTP, FMT_S16])
+@pytest.mark.parametrize("nch", [1, 2])
+def test_resample_tracks_batch_matches_single_mixers(nd, orc, fmt, nch):
+    """nodey_resample_tracks: a batch of audio_amix(1) resamplers in one launch == the oracle's amix per track"""
+    n = 61013                      # several tiles per track, ragged last tile
+    ntr = 5
+    vols = np.array([1.0, 0.5, 0.25, 0.9, 0.1], np.float32)
+    xs = [make_input(orc, fmt, n, nch, track=i) for i in range(ntr)]
+    r = nd.Resampler(44100, 48000)
+    got = r.resample_tracks([to_dev(x) for x in xs], fmt, vols, flush=True).cpu().numpy()
+    for t in range(ntr):
+        rl, rr = orc.amix([orc.make_track(xs[t], fmt, 44100)], vols[t:t + 1], quirk=0)
+        m = got.shape[2]
+        assert m <= len(rl)
+        assert_bit_equal(got[t, 0], rl[:m], f"track {t} L")
+        assert_bit_equal(got[t, 1], rr[:m], f"track {t} R")
+        assert not rl[m:].any() and not rr[m:].any()
+
+
+def test_resample_tracks_rejects_plans_without_pipelined_kernel(nd, orc):
+    x = to_dev(make_input(orc, FMT_FLT, 5000, 2, rate=22050))
+    r = nd.Resampler(22050, 48000)            # 320 phases: two groups per warp -> staging-row kernel only
+    with pytest.raises(nd.NodeyError) as e:
+        r.resample_tracks([x], FMT_FLT, [1.0])
+    assert e.value.code == -5
