@@ -171,6 +171,17 @@ int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, 
                           const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
                           nodey_stream_t stream);
 
+/* Time-segment sharding of one long stream across GPUs: outputs [k0, k1) of the flushed
+ * conversion of n_in frames depend only on the input slice [*in0, *in1).  Run the resampler on that slice with
+ * flush = *flush and out_frames = *skip + (k1 - k0), drop the first *skip outputs: the rest is bit identical
+ * to the whole-stream result (one period of phase_count outputs consumes exactly dst_incr_div input frames, so
+ * a conversion started whole periods early reproduces every phase; the lead-in spans at least (taps-1)/2 input
+ * frames, so only dropped outputs see the mirrored left edge).  k0 must be a multiple of phase_count; exact-rational plans only (NODEY_E_RANGE otherwise).
+ * Streaming nodes (gain, split, merge, mix) cut anywhere without halo; the spectrum node needs
+ * [m0*hop, (m1-1)*hop + nfft) for frames [m0, m1); SoundTouch state is sequential and cannot be cut. */
+int nodey_resampler_segment(const nodey_resampler* r, int64_t n_in, int64_t k0, int64_t k1,
+                            int64_t* in0, int64_t* in1, int64_t* skip, int* flush);
+
 /* A4  audio_amix frame bookkeeping (host only, no device work), audio-amix.cpp:149-322.  The node pulls
  * one frame per input and iteration, asks swr for nb = min(frame sizes) frames (1152 once the inputs
  * ran dry) and zero fills what swr did not deliver, until every input is flushed.  Inputs are

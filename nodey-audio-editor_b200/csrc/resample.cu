@@ -891,6 +891,37 @@ int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, 
     return launch_tile2(r, out_l, out_r, a, tp, nch, as_stream(stream));
 }
 
+/* time-segment sharding of one long stream: see nodey_cuda.h */
+int nodey_resampler_segment(const nodey_resampler* r, int64_t n_in, int64_t k0, int64_t k1,
+                            int64_t* in0, int64_t* in1, int64_t* skip, int* flush)
+{
+    NODEY_REQUIRE(r && in0 && in1 && skip && flush, NODEY_E_INVALID, "nodey_resampler_segment: null argument");
+    NODEY_REQUIRE(n_in >= 0 && k0 >= 0 && k1 >= k0, NODEY_E_INVALID, "nodey_resampler_segment: bad range");
+    if (!r->resample) { *in0 = k0; *in1 = k1 < n_in ? k1 : n_in; *skip = 0; *flush = 0; return NODEY_OK; }
+    NODEY_REQUIRE(r->dst_incr_mod == 0, NODEY_E_RANGE, "nodey_resampler_segment: only exact-rational plans can be cut into segments");
+    const int64_t P = r->phase_count, D = r->dst_incr_div, L = r->filter_length, center = (L - 1) / 2;
+    const int64_t total = nodey_resampler_out_count(r, n_in, 1);
+    NODEY_REQUIRE(k1 <= total, NODEY_E_RANGE, "nodey_resampler_segment: k1 %lld beyond the %lld outputs of the stream", (long long)k1, (long long)total);
+    NODEY_REQUIRE(k0 % P == 0, NODEY_E_INVALID, "nodey_resampler_segment: k0 must be a multiple of the phase count %lld", (long long)P);
+    // one period of P outputs consumes exactly D input frames, so a conversion started a whole number of periods
+    // before the segment reproduces the phases; the lead-in covers at least `center` input frames, so only
+    // outputs that are dropped see the mirrored left edge
+    int64_t lead = (center + D - 1) / D;
+    if (lead < 1) lead = 1;
+    const int64_t periods = k0 / P;
+    *in0 = periods <= lead ? 0 : (periods - lead) * D;
+    *skip = periods <= lead ? k0 : lead * P;
+    *in1 = n_in; *flush = 1;
+    if (k1 < total && k1 > k0) {
+        // last output needs input frames up to s - center + L - 1 of the slice
+        const int64_t s_last = plan_pos_index(r, *skip + (k1 - k0) - 1) / P;
+        int64_t need = s_last - center + L;
+        if (need < L + 1) need = L + 1;
+        if (*in0 + need <= n_in) { *in1 = *in0 + need; *flush = 0; }
+    }
+    return NODEY_OK;
+}
+
 /* audio_amix frame bookkeeping, audio-amix.cpp:149-322 (see nodey_cuda.h) */
 int64_t nodey_amix_plan(const int* in_rate, int nin, const int64_t* run_off, const int64_t* run_len,
                         const int64_t* run_count, int index_mask_quirk,

@@ -42,7 +42,12 @@
 namespace nodey {
 
 constexpr int kAaLen = 64;
-constexpr int kTdsThreads = 256;      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
+// 256 threads, two CTAs per SM, measured best: 384 / 512-thread CTAs (tools/micro: libnodey_cuda_t384/512.so + tools/st_sweep.py)
+// were 3-5 % slower at 256 tracks and no faster at 32; a three-block register ring for the sample window changed nothing
+#ifndef NODEY_TDS_THREADS
+#define NODEY_TDS_THREADS 256
+#endif
+constexpr int kTdsThreads = NODEY_TDS_THREADS;      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
 
 // frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
 // (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks).
