@@ -131,6 +131,8 @@ __device__ __forceinline__ void untangle_pair(float2 zk, float2 zmc, float2 w, f
     xm = make_float2(0.5f * (e.x - t.y), -0.5f * (e.y + t.x));
 }
 
+// VEC: channel samples are contiguous and 8-byte aligned (planar input): one 64-bit load per complex point
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_constant__ StftArgs a)
 {
     extern __shared__ __align__(16) float2 stft_smem[];      // 51 KB: above the static limit
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_cons
         for (int r = 0; r < 16; r++) {
             const int n = 2 * (j + 128 * r);
             float2 s;
-            if (a.vec_ok) s = __ldg(reinterpret_cast<const float2*>(p + n));
-            else { s.x = __ldg(p + (long long)n * a.x_stride); s.y = __ldg(p + (long long)(n + 1) * a.x_stride); }
+            if (VEC) s = __ldg(reinterpret_cast<const float2*>(p + n));
+            else { s.x = __ldg(p + n * a.x_stride); s.y = __ldg(p + (n + 1) * a.x_stride); }
             const float2 w = __ldg(reinterpret_cast<const float2*>(a.win + n));
             v[r] = make_float2(__fmul_rn(s.x, w.x), __fmul_rn(s.y, w.y));
         }
@@ -304,9 +306,10 @@ int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int
     const int64_t cap = (int64_t)sm_count() * 4;
     const int grid = (int)(items < cap ? items : cap);
     constexpr size_t smem = sizeof(float2) * (2 * kBufLen + 15 * 16 + 7 * 256);
-    NODEY_CUDA_OK(cudaFuncSetAttribute(stft4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NODEY_CUDA_OK(cudaFuncSetAttribute(stft4096_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    NODEY_LAUNCH("stft4096_kernel", as_stream(stream), stft4096_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(a));
+    void (*kern)(StftArgs) = a.vec_ok ? stft4096_kernel<true> : stft4096_kernel<false>;
+    NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    NODEY_LAUNCH("stft4096_kernel", as_stream(stream), kern<<<grid, kThreads, smem, as_stream(stream)>>>(a));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }
