@@ -380,17 +380,22 @@ __device__ __forceinline__ void rs_cp_async8(float* dst_smem, const float* src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(src) : "memory");
 }
 
-template <int CH, bool MIX>
-__global__ void __launch_bounds__(640, MIX ? 1 : 2) resample_tile2_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
-                                                                          const __grid_constant__ TileArgs a,
-                                                                          const __grid_constant__ TrackPlanes tp)
+// PT = periods per thread (tile = 32 * PT periods): the warp-uniform 128-bit tap loads cost about three shared-memory
+// wavefronts each (ncu: 7.7 wavefronts per window position and warp, 2 of them the samples), so with one period per
+// thread the LSU pipe, not the FMA pipe, set the pace; two periods per thread halve the tap traffic per FMA.
+template <int CH, bool MIX, int PT>
+__global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
+                                                                                      const __grid_constant__ TileArgs a,
+                                                                                      const __grid_constant__ TrackPlanes tp)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [hq: n_groups*wmax*G floats][group_start: n_groups ints][input tile 0][input tile 1]
     float* s_hq = reinterpret_cast<float*>(smem_raw);
     int* s_gs = reinterpret_cast<int*>(s_hq + a.n_groups * a.wmax * kG);
     float* s_in0 = reinterpret_cast<float*>(s_gs + ((a.n_groups + 3) & ~3));
-    const int buf_floats = (a.in_tile * CH + 3) & ~3;
+    constexpr int NBT = kNB * PT;                       // periods per tile
+    const int in_tile = (NBT - 1) * a.D + a.span + a.wmax + 1;
+    const int buf_floats = (in_tile * CH + 3) & ~3;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int q = tid >> 5, lane = tid & 31;           // one phase group per warp
@@ -404,33 +409,35 @@ __global__ void __launch_bounds__(640, MIX ? 1 : 2) resample_tile2_kernel(float*
     // stage (item, inp): fill `dst` with the input tile -- asynchronously when the tile is an interior run of float frames
     const auto stage = [&](long long item, int inp, float* dst) {
         const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
-        const long long k0 = tile * (long long)kNB * a.P;
+        const long long k0 = tile * (long long)NBT * a.P;
         if (k0 >= a.out_len[inp]) return;                       // contributes zeros: nothing is read
-        const long long in0 = tile * (long long)kNB * a.D + a.s0 - a.center;
+        const long long in0 = tile * (long long)NBT * a.D + a.s0 - a.center;
         SrcDesc s = a.src[inp];
         if (!MIX) { s.p0 = tp.p0[track]; s.p1 = tp.p1[track]; }
-        const bool interior = tile_interior(s, in0, a.in_tile);
+        const bool interior = tile_interior(s, in0, in_tile);
         if (CH == 2 && interior && s.fmt == NODEY_FMT_FLT && (((uintptr_t)s.p0) & 7) == 0) {
             const float* src = reinterpret_cast<const float*>(s.p0) + 2 * in0;
-            for (int f = tid; f < a.in_tile; f += nthr) rs_cp_async8(dst + 2 * f, src + 2 * f);
+            for (int f = tid; f < in_tile; f += nthr) rs_cp_async8(dst + 2 * f, src + 2 * f);
         } else if (CH == 2 && interior && s.fmt == NODEY_FMT_FLTP) {
             const float* sl = reinterpret_cast<const float*>(s.p0) + in0;
             const float* sr = reinterpret_cast<const float*>(s.p1) + in0;
-            for (int f = tid; f < a.in_tile; f += nthr) { rs_cp_async4(dst + 2 * f, sl + f); rs_cp_async4(dst + 2 * f + 1, sr + f); }
+            for (int f = tid; f < in_tile; f += nthr) { rs_cp_async4(dst + 2 * f, sl + f); rs_cp_async4(dst + 2 * f + 1, sr + f); }
         } else if (CH == 2) {
             float2* d2 = reinterpret_cast<float2*>(dst);
-            for (int f = tid; f < a.in_tile; f += nthr) d2[f] = src_frame(s, in0 + f);
+            for (int f = tid; f < in_tile; f += nthr) d2[f] = src_frame(s, in0 + f);
         } else {
-            for (int f = tid; f < a.in_tile; f += nthr) dst[f] = src_frame(s, in0 + f).x;
+            for (int f = tid; f < in_tile; f += nthr) dst[f] = src_frame(s, in0 + f).x;
         }
     };
 
     long long item = blockIdx.x;
     int inp = 0, cur = 0;
     if (item < total) stage(item, 0, s_in0);
-    float macc[kG][2];
+    float macc[PT][kG][2];
 #pragma unroll
-    for (int g = 0; g < kG; g++) macc[g][0] = macc[g][1] = 0.f;
+    for (int p = 0; p < PT; p++)
+#pragma unroll
+        for (int g = 0; g < kG; g++) macc[p][g][0] = macc[p][g][1] = 0.f;
 
     while (item < total) {
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -440,76 +447,90 @@ __global__ void __launch_bounds__(640, MIX ? 1 : 2) resample_tile2_kernel(float*
         if (nitem < total) stage(nitem, ninp, s_in0 + (cur ^ 1) * buf_floats);
 
         const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
-        const long long k0 = tile * (long long)kNB * a.P;
+        const long long k0 = tile * (long long)NBT * a.P;
         const float* s_in = s_in0 + cur * buf_floats;
         const float vol = MIX ? a.vol[inp] : tp.vol[track];
         if (q < a.n_groups) {
-            float acc[kG][CH];
+            float acc[PT][kG][CH];
 #pragma unroll
-            for (int g = 0; g < kG; g++)
+            for (int p = 0; p < PT; p++)
 #pragma unroll
-                for (int c = 0; c < CH; c++) acc[g][c] = 0.f;
-            const long long kq = k0 + (long long)lane * a.P + (long long)q * kG;   // first output of this thread
+                for (int g = 0; g < kG; g++)
+#pragma unroll
+                    for (int c = 0; c < CH; c++) acc[p][g][c] = 0.f;
+            // thread = periods lane, lane + 32, ... of the tile; first output of period p: kq + p * 32 * P
+            const long long kq = k0 + (long long)lane * a.P + (long long)q * kG;
             if (k0 < a.out_len[inp] && kq < a.out_frames) {
                 const float* hq = s_hq + q * a.wmax * kG;
                 const int base = lane * a.D + s_gs[q];
+                const int pstep = kNB * a.D;                       // input frames between a thread's periods
                 if (CH == 2) {
                     const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
-#pragma unroll 4
+#pragma unroll 2
                     for (int m = 0; m < a.wmax; m++) {
-                        const float2 x = x2[m];
                         const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
                         const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
-                        acc[0][0] = __fmaf_rn(x.x, h0.x, acc[0][0]); acc[0][CH - 1] = __fmaf_rn(x.y, h0.x, acc[0][CH - 1]);
-                        acc[1][0] = __fmaf_rn(x.x, h0.y, acc[1][0]); acc[1][CH - 1] = __fmaf_rn(x.y, h0.y, acc[1][CH - 1]);
-                        acc[2][0] = __fmaf_rn(x.x, h0.z, acc[2][0]); acc[2][CH - 1] = __fmaf_rn(x.y, h0.z, acc[2][CH - 1]);
-                        acc[3][0] = __fmaf_rn(x.x, h0.w, acc[3][0]); acc[3][CH - 1] = __fmaf_rn(x.y, h0.w, acc[3][CH - 1]);
-                        acc[4][0] = __fmaf_rn(x.x, h1.x, acc[4][0]); acc[4][CH - 1] = __fmaf_rn(x.y, h1.x, acc[4][CH - 1]);
-                        acc[5][0] = __fmaf_rn(x.x, h1.y, acc[5][0]); acc[5][CH - 1] = __fmaf_rn(x.y, h1.y, acc[5][CH - 1]);
-                        acc[6][0] = __fmaf_rn(x.x, h1.z, acc[6][0]); acc[6][CH - 1] = __fmaf_rn(x.y, h1.z, acc[6][CH - 1]);
-                        acc[7][0] = __fmaf_rn(x.x, h1.w, acc[7][0]); acc[7][CH - 1] = __fmaf_rn(x.y, h1.w, acc[7][CH - 1]);
+#pragma unroll
+                        for (int p = 0; p < PT; p++) {
+                            const float2 x = x2[m + p * pstep];
+                            acc[p][0][0] = __fmaf_rn(x.x, h0.x, acc[p][0][0]); acc[p][0][CH - 1] = __fmaf_rn(x.y, h0.x, acc[p][0][CH - 1]);
+                            acc[p][1][0] = __fmaf_rn(x.x, h0.y, acc[p][1][0]); acc[p][1][CH - 1] = __fmaf_rn(x.y, h0.y, acc[p][1][CH - 1]);
+                            acc[p][2][0] = __fmaf_rn(x.x, h0.z, acc[p][2][0]); acc[p][2][CH - 1] = __fmaf_rn(x.y, h0.z, acc[p][2][CH - 1]);
+                            acc[p][3][0] = __fmaf_rn(x.x, h0.w, acc[p][3][0]); acc[p][3][CH - 1] = __fmaf_rn(x.y, h0.w, acc[p][3][CH - 1]);
+                            acc[p][4][0] = __fmaf_rn(x.x, h1.x, acc[p][4][0]); acc[p][4][CH - 1] = __fmaf_rn(x.y, h1.x, acc[p][4][CH - 1]);
+                            acc[p][5][0] = __fmaf_rn(x.x, h1.y, acc[p][5][0]); acc[p][5][CH - 1] = __fmaf_rn(x.y, h1.y, acc[p][5][CH - 1]);
+                            acc[p][6][0] = __fmaf_rn(x.x, h1.z, acc[p][6][0]); acc[p][6][CH - 1] = __fmaf_rn(x.y, h1.z, acc[p][6][CH - 1]);
+                            acc[p][7][0] = __fmaf_rn(x.x, h1.w, acc[p][7][0]); acc[p][7][CH - 1] = __fmaf_rn(x.y, h1.w, acc[p][7][CH - 1]);
+                        }
                     }
                 } else {
                     const float* x1 = s_in + base;
-#pragma unroll 4
+#pragma unroll 2
                     for (int m = 0; m < a.wmax; m++) {
-                        const float x = x1[m];
                         const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
                         const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
-                        acc[0][0] = __fmaf_rn(x, h0.x, acc[0][0]); acc[1][0] = __fmaf_rn(x, h0.y, acc[1][0]);
-                        acc[2][0] = __fmaf_rn(x, h0.z, acc[2][0]); acc[3][0] = __fmaf_rn(x, h0.w, acc[3][0]);
-                        acc[4][0] = __fmaf_rn(x, h1.x, acc[4][0]); acc[5][0] = __fmaf_rn(x, h1.y, acc[5][0]);
-                        acc[6][0] = __fmaf_rn(x, h1.z, acc[6][0]); acc[7][0] = __fmaf_rn(x, h1.w, acc[7][0]);
+#pragma unroll
+                        for (int p = 0; p < PT; p++) {
+                            const float x = x1[m + p * pstep];
+                            acc[p][0][0] = __fmaf_rn(x, h0.x, acc[p][0][0]); acc[p][1][0] = __fmaf_rn(x, h0.y, acc[p][1][0]);
+                            acc[p][2][0] = __fmaf_rn(x, h0.z, acc[p][2][0]); acc[p][3][0] = __fmaf_rn(x, h0.w, acc[p][3][0]);
+                            acc[p][4][0] = __fmaf_rn(x, h1.x, acc[p][4][0]); acc[p][5][0] = __fmaf_rn(x, h1.y, acc[p][5][0]);
+                            acc[p][6][0] = __fmaf_rn(x, h1.z, acc[p][6][0]); acc[p][7][0] = __fmaf_rn(x, h1.w, acc[p][7][0]);
+                        }
                     }
                 }
             }
-            // accumulate in input order: temp += data * volume, temp zeroed first (audio-amix.cpp:296-304)
+            float* gl0 = out_l + track * a.out_track_stride;
+            float* gr0 = out_r + track * a.out_track_stride;
+            const int ng = a.P - q * kG < kG ? a.P - q * kG : kG;             // phases of the last group may run short
 #pragma unroll
-            for (int g = 0; g < kG; g++) {
-                const bool live = (kq + g) < a.out_len[inp];
-                float vl = live ? acc[g][0] : 0.f;
-                float vr = live ? acc[g][CH - 1] : 0.f;
-                if (a.mix) {
-                    vl = __fadd_rn((MIX && inp) ? macc[g][0] : 0.f, __fmul_rn(vl, vol));
-                    vr = __fadd_rn((MIX && inp) ? macc[g][1] : 0.f, __fmul_rn(vr, vol));
+            for (int p = 0; p < PT; p++) {
+                const long long kp = kq + (long long)p * kNB * a.P;
+                // accumulate in input order: temp += data * volume, temp zeroed first (audio-amix.cpp:296-304)
+#pragma unroll
+                for (int g = 0; g < kG; g++) {
+                    const bool live = (kp + g) < a.out_len[inp];
+                    float vl = live ? acc[p][g][0] : 0.f;
+                    float vr = live ? acc[p][g][CH - 1] : 0.f;
+                    if (a.mix) {
+                        vl = __fadd_rn((MIX && inp) ? macc[p][g][0] : 0.f, __fmul_rn(vl, vol));
+                        vr = __fadd_rn((MIX && inp) ? macc[p][g][1] : 0.f, __fmul_rn(vr, vol));
+                    }
+                    macc[p][g][0] = vl; macc[p][g][1] = vr;
                 }
-                macc[g][0] = vl; macc[g][1] = vr;
-            }
-            if (inp == nin - 1) {
-                float* gl0 = out_l + track * a.out_track_stride;
-                float* gr0 = out_r + track * a.out_track_stride;
-                const int ng = a.P - q * kG < kG ? a.P - q * kG : kG;             // phases of the last group may run short
-                if (a.vec_out && ng == kG && kq + kG <= a.out_frames) {
-                    float4* gl = reinterpret_cast<float4*>(gl0 + kq);
-                    float4* gr = reinterpret_cast<float4*>(gr0 + kq);
-                    gl[0] = make_float4(macc[0][0], macc[1][0], macc[2][0], macc[3][0]);
-                    gl[1] = make_float4(macc[4][0], macc[5][0], macc[6][0], macc[7][0]);
-                    gr[0] = make_float4(macc[0][1], macc[1][1], macc[2][1], macc[3][1]);
-                    gr[1] = make_float4(macc[4][1], macc[5][1], macc[6][1], macc[7][1]);
-                } else {
+                if (inp == nin - 1) {
+                    if (a.vec_out && ng == kG && kp + kG <= a.out_frames) {
+                        float4* gl = reinterpret_cast<float4*>(gl0 + kp);
+                        float4* gr = reinterpret_cast<float4*>(gr0 + kp);
+                        gl[0] = make_float4(macc[p][0][0], macc[p][1][0], macc[p][2][0], macc[p][3][0]);
+                        gl[1] = make_float4(macc[p][4][0], macc[p][5][0], macc[p][6][0], macc[p][7][0]);
+                        gr[0] = make_float4(macc[p][0][1], macc[p][1][1], macc[p][2][1], macc[p][3][1]);
+                        gr[1] = make_float4(macc[p][4][1], macc[p][5][1], macc[p][6][1], macc[p][7][1]);
+                    } else {
 #pragma unroll
-                    for (int g = 0; g < kG; g++)
-                        if (g < ng && kq + g < a.out_frames) { gl0[kq + g] = macc[g][0]; gr0[kq + g] = macc[g][1]; }
+                        for (int g = 0; g < kG; g++)
+                            if (g < ng && kp + g < a.out_frames) { gl0[kp + g] = macc[p][g][0]; gr0[kp + g] = macc[p][g][1]; }
+                    }
                 }
             }
         }
@@ -759,25 +780,37 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
 // pipelined tile kernel: plans with one phase group per warp
 static bool tile2_ok(const nodey_resampler* r) { return r->tile_ok && r->n_groups <= 20; }
 
-static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, const TrackPlanes& tp, int ch, cudaStream_t st)
+static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, const TrackPlanes& tp, int ch, cudaStream_t st, int force_pt = 0)
 {
     a.hq = r->d_hq; a.group_start = r->d_group_start;
     tile_geometry(r, a, ch);
-    const size_t buf_floats = ((size_t)a.in_tile * ch + 3) & ~(size_t)3;
-    const size_t smem = sizeof(float) * ((size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3) + 2 * buf_floats);
+    const size_t table = (size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3);
+    const auto smem_for = [&](int pt) {
+        const size_t in_tile = (size_t)(kNB * pt - 1) * a.D + a.span + a.wmax + 1;
+        return sizeof(float) * (table + 2 * ((in_tile * ch + 3) & ~(size_t)3));
+    };
+    // two periods per thread when the double-buffered 64-period tile fits one SM
+    int pt = smem_for(2) <= 227 * 1024 ? 2 : 1;
+    if (force_pt) pt = force_pt;
+    const size_t smem = smem_for(pt);
     NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
-    a.n_tiles = (a.out_frames + (int64_t)kNB * a.P - 1) / ((int64_t)kNB * a.P);
+    const int64_t per_tile = (int64_t)kNB * pt * a.P;
+    a.n_tiles = (a.out_frames + per_tile - 1) / per_tile;
     if (a.ntracks < 1) a.ntracks = 1;
     a.vec_out = (((uintptr_t)out_l | (uintptr_t)out_r) & 15) == 0 && a.P % 4 == 0 && a.out_track_stride % 4 == 0;
     const bool mix = a.nin > 1;
     const int threads = 32 * a.n_groups;
-    const int ctas_per_sm = (mix || smem > 113 * 1024) ? 1 : 2;
+    const int ctas_per_sm = (mix || pt > 1 || smem > 113 * 1024) ? 1 : 2;
     const int64_t total = a.n_tiles * a.ntracks;
     int grid = (int)(total < (int64_t)sm_count() * ctas_per_sm ? total : (int64_t)sm_count() * ctas_per_sm);
     if (grid < 1) grid = 1;
-    void (*kern)(float*, float*, TileArgs, TrackPlanes) =
-        ch == 2 ? (mix ? resample_tile2_kernel<2, true> : resample_tile2_kernel<2, false>)
-                : (mix ? resample_tile2_kernel<1, true> : resample_tile2_kernel<1, false>);
+    void (*kern)(float*, float*, TileArgs, TrackPlanes);
+    if (pt == 2)
+        kern = ch == 2 ? (mix ? resample_tile2_kernel<2, true, 2> : resample_tile2_kernel<2, false, 2>)
+                       : (mix ? resample_tile2_kernel<1, true, 2> : resample_tile2_kernel<1, false, 2>);
+    else
+        kern = ch == 2 ? (mix ? resample_tile2_kernel<2, true, 1> : resample_tile2_kernel<2, false, 1>)
+                       : (mix ? resample_tile2_kernel<1, true, 1> : resample_tile2_kernel<1, false, 1>);
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     NODEY_LAUNCH("resample_tile_kernel", st, kern<<<grid, threads, smem, st>>>(out_l, out_r, a, tp));
@@ -785,7 +818,8 @@ static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, Ti
     return NODEY_OK;
 }
 
-// mode: 0 auto, 1 force generic, 2 force the staging-row tile kernel, 3 force the pipelined tile kernel
+// mode: 0 auto, 1 force generic, 2 force the staging-row tile kernel, 3 force the pipelined tile kernel,
+// 4 the pipelined kernel with one period per thread
 // (testing hook, not in the public header)
 int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_r, const void* p0, const void* p1,
                              int fmt, int nch, int64_t in_frames, int flush, int64_t out_frames, int mode,
@@ -801,19 +835,19 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
     NODEY_REQUIRE(out_frames >= 0 && out_frames <= avail, NODEY_E_RANGE,
                   "nodey_resampler_run: out_frames %lld exceeds what swr would produce (%lld)", (long long)out_frames, (long long)avail);
     if (out_frames == 0) return NODEY_OK;
-    if ((mode == 0 && r->tile_ok) || mode == 2 || mode == 3) {
+    if ((mode == 0 && r->tile_ok) || mode == 2 || mode == 3 || mode == 4) {
         NODEY_REQUIRE(r->tile_ok, NODEY_E_RANGE, "tile kernel unavailable for this plan");
-        NODEY_REQUIRE(mode != 3 || tile2_ok(r), NODEY_E_RANGE, "pipelined tile kernel unavailable for this plan");
+        NODEY_REQUIRE(mode < 3 || tile2_ok(r), NODEY_E_RANGE, "pipelined tile kernel unavailable for this plan");
         TileArgs a;
         memset(&a, 0, sizeof(a));
         int rc = fill_src(&a.src[0], r, p0, p1, fmt, nch, in_frames, flush);
         if (rc != NODEY_OK) return rc;
         a.out_len[0] = out_frames; a.vol[0] = 1.f; a.nin = 1; a.mix = 0; a.out_frames = out_frames;
-        if (mode == 3 || (mode == 0 && tile2_ok(r))) {
+        if (mode >= 3 || (mode == 0 && tile2_ok(r))) {
             static thread_local TrackPlanes tp;
             tp.p0[0] = p0; tp.p1[0] = p1; tp.vol[0] = 1.f;
             a.ntracks = 1; a.out_track_stride = 0;
-            return launch_tile2(r, out_l, out_r, a, tp, nch, st);
+            return launch_tile2(r, out_l, out_r, a, tp, nch, st, mode == 4 ? 1 : 0);
         }
         return launch_tile(r, out_l, out_r, a, nch, st);
     }

@@ -21,7 +21,7 @@ def test_plan_matches_oracle(nd, orc):
             r.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("fmt", ALL_FMTS)
 @pytest.mark.parametrize("nch", [1, 2])
 def test_resample_441_to_48_bit_exact(nd, orc, mode, fmt, nch):
@@ -58,7 +58,7 @@ def test_resample_short_inputs(nd, orc, n):
     r = nd.Resampler(44100, 48000)
     assert r.out_count(n, True) == len(rl)
     if len(rl):
-        for mode in (1, 2, 3):
+        for mode in (1, 2, 3, 4):
             got = r.run(to_dev(x), FMT_FLT, flush=True, mode=mode).cpu().numpy()
             assert_bit_equal(got[0], rl, f"short L mode {mode}")
             assert_bit_equal(got[1], rr, f"short R mode {mode}")
