@@ -143,7 +143,7 @@ def kernel_algo_bytes(name, r, batch):
     the bytes a perfect implementation must read plus the bytes it must write, per launch."""
     f8 = 8  # stereo float frame
     table = {
-        "resample_tile_kernel": r.n_in * f8 + r.total1 * f8,                     # one track: in + out planes
+        "resample_tile_kernel": batch * (r.n_in * f8 + r.total1 * f8),           # one launch per batch of audio_amix(1): in + out planes
         "extract_planar_kernel": r.total1 * f8 * 2,
         "tds_offsets_kernel": None,                                               # filled per node below
         "st_post_kernel": None,
@@ -165,6 +165,18 @@ def kernel_algo_bytes(name, r, batch):
     table["tds_offsets_kernel"] = batch * per_track
     table["st_post_kernel"] = batch * (st_in + st_out) * f8                       # fused cross-fade + FIR + cubic: in once, out once
     return table.get(name)
+
+
+def tds_fp32_ops(r, batch):
+    """separately rounded FP32 operations one WSOLA offsets launch must issue (mean of the pitch and the tempo node):
+    per sequence, seek_length candidates x (channels * overlap) samples x (multiply + add) for the correlation, plus
+    half an add per (candidate, sample) for the norm sums shared between candidate classes."""
+    ops = 0.0
+    for st, n_in in ((r.st_pitch, r.total1), (r.st_tempo, r.m1)):
+        info = st.info()
+        _, nseq = st.out_frames(n_in, r.frame_size)
+        ops += 0.5 * max(nseq - 1, 0) * info["seek_length"] * 2 * info["overlap"] * 2.5
+    return batch * ops
 
 
 def run_ours(args):
@@ -293,9 +305,16 @@ def run_ours(args):
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                     "launch_ms": per_launch_ms, "share_of_step": st["ms"] / step_ms if step_ms else None,
-                    "note": "the dominant kernel is the WSOLA offset search: FP32-issue bound (about 735 rounded FP32 ops per input "
-                            "frame, sequential per track), so its HBM fraction is small by construction; see DESIGN.md 3.1",
+                    "note": "the dominant kernel is the WSOLA offset search: FP32-issue bound (about 610 separately rounded FP32 "
+                            "operations per input frame, sequential per track), so its HBM fraction is small by construction; "
+                            "`fp32` gives its fraction of the FP32 issue peak; see DESIGN.md 3.1",
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}
+        if name == "tds_offsets_kernel":
+            sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+            fp_peak = nodey.device_info()["sm_count"] * 128 * sm_mhz * 1e6          # one FP32 operation per lane and clock (no FMA: -fmad=false)
+            fp_ach = tds_fp32_ops(plan, st_batch) / (per_launch_ms * 1e-3)
+            roofline["fp32"] = {"achieved": fp_ach / 1e12, "peak": fp_peak / 1e12, "unit": "Tops/s (separately rounded mul/add)",
+                                "frac": fp_ach / fp_peak, "peak_source": f"SMs x 128 lanes x {sm_mhz:.0f} MHz"}
 
     # ---- end to end: pinned host inputs -> H2D (audio_input node) -> render -> D2H(bus, spectrum) ----
     e2e = None
