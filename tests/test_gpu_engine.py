@@ -146,3 +146,65 @@ def test_node_errors_surface(eng_gpu, orc):
     with pytest.raises(eng_gpu.EngineError) as x:
         e2.run()
     assert "Unsupported sample rate" in x.value.message
+
+
+def test_amix_batch_of_mixed_nodes(eng_gpu, orc):
+    """One graph level holding every kind of audio_amix the batch path must tell apart: three single-input
+    resamplers of equal streams with different volumes (one launch), one of another length, one S16, one at
+    22.05 kHz (320 phases: no pipelined kernel), one at 48 kHz (no resampling) and a two-input mixer -- each
+    product must equal the oracle's amix of that node alone."""
+    specs = [  # (format, rate, frames, volumes)
+        (FMT_FLT, 44100, 30000, [1.0]), (FMT_FLT, 44100, 30000, [0.5]), (FMT_FLT, 44100, 30000, [0.25]),
+        (FMT_FLT, 44100, 21111, [0.8]), (FMT_S16, 44100, 30000, [0.9]), (FMT_FLT, 22050, 15000, [0.7]),
+        (FMT_FLT, 48000, 20000, [0.6]),
+    ]
+    xs = [make_input(orc, f, n, 2, rate=r, track=i) for i, (f, r, n, _) in enumerate(specs)]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""] * len(specs)})
+    nodes = []
+    for i, (_, _, _, vol) in enumerate(specs):
+        m = p.add("audio_amix", eng_gpu.amix_info(vol))
+        p.link(src, f"output_{i}", m, "input_1")
+        p.link(m, "output", p.add("audio_volume_adjust"), "input")      # a product exists per link: give every node a consumer
+        nodes.append(m)
+    two = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.5]))
+    p.link(src, "output_0", two, "input_1"); p.link(src, "output_3", two, "input_2")
+    out = p.add("audio_output")
+    p.link(two, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    for i, (x, (f, r, _, _)) in enumerate(zip(xs, specs)):
+        e.bind_source(i, x, f, r)
+    e.run()
+    for i, (m, (f, r, _, vol)) in enumerate(zip(nodes, specs)):
+        rl, rr = orc.amix([orc.make_track(xs[i], f, r)], vol)
+        got = e.product(m, "output")
+        assert (got.fmt, got.rate, got.ch) == (FMT_FLTP, 48000, 2)
+        assert_bit_equal(got.numpy(), np.stack([rl, rr]), f"amix node {i}")
+    rl, rr = orc.amix([orc.make_track(xs[0], FMT_FLT, 44100), orc.make_track(xs[3], FMT_FLT, 44100)], [0.5, 0.5])
+    assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "two-input amix in the same level")
+
+
+def test_soundtouch_batch_of_mixed_formats(eng_gpu, orc):
+    """pitch nodes of one level fed by FLT, FLTP (read in place) and S16 (converted) streams of equal length"""
+    n = 48000 + 123
+    fmts = [FMT_FLT, FMT_FLTP, FMT_S16, FMT_FLTP]
+    xs = [make_input(orc, f, n, 2, rate=48000, track=10 + i) for i, f in enumerate(fmts)]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""] * len(fmts)})
+    nodes = []
+    for i in range(len(fmts)):
+        pm = p.add("pitch_modifier", {"pitch": 3.0})
+        p.link(src, f"output_{i}", pm, "input")
+        p.link(pm, "output", p.add("audio_volume_adjust"), "input")
+        nodes.append(pm)
+    out = p.add("audio_output")
+    p.link(nodes[0], "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    for i, (x, f) in enumerate(zip(xs, fmts)):
+        e.bind_source(i, x, f, 48000)
+    e.run()
+    pitch = orc.pitch_node_factor(3.0)
+    for i, (x, f) in enumerate(zip(xs, fmts)):
+        xi = orc.extract_interleaved(x, f)
+        ref, _, _ = orc.soundtouch(xi, 48000, 1.0, pitch, 1152)
+        assert_bit_equal(e.product(nodes[i], "output").numpy(), ref, f"pitch node {i} (format {f})")
