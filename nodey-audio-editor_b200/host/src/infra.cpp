@@ -405,12 +405,13 @@ namespace infra
 				const auto data = node_data.find(id);
 				upload += graph.nodes.at(id).processor->upload_bytes(data == node_data.end() ? no_data : *data->second);
 			}
-		// Uploads are only a little slower than compute per track, so (1) only the FIRST wave's upload is
-		// exposed: keep it small (32 source pins); (2) the LAST wave's compute is exposed: keep it small too --
-		// a SoundTouch chain costs the same 50 ms for 8 or 40 tracks (sequential per track), so 32 is the
-		// cheapest tail; (3) in between, waves of 64 pins keep the batched kernels efficient, and consecutive
-		// waves run on alternating compute lanes so that a small wave does not leave the SMs idle while its
-		// sequential chains run.  NODEY_WAVE=n forces uniform waves of n pins.
+		// Uploads are only a little slower than compute per track (1.15 vs 0.94 ms), so the first wave's upload and the
+		// last wave's compute are exposed: both want SMALL waves.  A SoundTouch chain costs the same 40 ms for 8 or 40
+		// tracks (sequential per track), so waves of 32 source pins are the smallest that still pay; consecutive waves
+		// run on three rotating compute lanes so that a wave's sequential chains do not leave the SMs idle.  Measured on
+		// the 256-track render (tools/e2e_trace.py): 364 ms for 32-pin waves on three lanes, 379 ms for 32/64/64/64/32 on
+		// two, 437 ms for 32/96/128 on one; the 16.26 GB upload alone takes 294 ms.  NODEY_WAVE=n forces waves of n pins,
+		// NODEY_WAVES="a,b,c" an explicit pattern.
 		const bool pipelined = upload >= (1u << 30);
 		int uniform = 0;
 		if (const char* env = getenv("NODEY_WAVE")) uniform = std::max(1, atoi(env));
@@ -420,11 +421,24 @@ namespace infra
 				for (const auto& attribute : graph.nodes.at(id).processor->get_pin_attributes())
 					if (!attribute.is_input) source_pins++;
 		std::vector<int> wave_begin{0};      // first pin position of every wave
-		if (uniform > 0)
+		if (const char* env = getenv("NODEY_WAVES"))
+		{
+			// development: explicit wave sizes "32,64,48" (the last one repeats)
+			int p = 0, size = 0;
+			const char* c = env;
+			while (p < source_pins)
+			{
+				if (*c) { size = std::max(1, atoi(c)); while (*c && *c != ',') c++; if (*c == ',') c++; }
+				if (size <= 0) break;
+				p += size;
+				if (p < source_pins) wave_begin.push_back(p);
+			}
+		}
+		else if (uniform > 0)
 			for (int p = uniform; p < source_pins; p += uniform) wave_begin.push_back(p);
 		else if (pipelined && source_pins > 32)
 		{
-			constexpr int kEdge = 32, kBody = 64;
+			constexpr int kEdge = 32, kBody = 32;
 			int p = kEdge;
 			while (source_pins - p > kBody + kEdge) { wave_begin.push_back(p); p += kBody; }
 			wave_begin.push_back(p);
@@ -508,10 +522,10 @@ namespace infra
 	void Runner::launch_threads()
 	{
 		// lane 0: transfers (nodes without inputs: the sources' uploads); lanes 1..: compute (everything else).
-		// One compute lane when the render is a single wave; waves alternate between two otherwise.
+		// One compute lane when the render is a single wave; waves rotate over up to three otherwise.
 		int max_wave = 0;
 		for (const auto& [_, w] : node_wave) max_wave = std::max(max_wave, w);
-		int compute_lanes = max_wave > 0 ? 2 : 1;
+		int compute_lanes = max_wave > 1 ? 3 : (max_wave > 0 ? 2 : 1);
 		if (const char* env = getenv("NODEY_COMPUTE_LANES")) compute_lanes = std::clamp(atoi(env), 1, 4);
 		constexpr int kMaxLanes = 5;
 		const int kLanes = 1 + compute_lanes;

@@ -1,5 +1,5 @@
 """Development: end-to-end engine time on the config-5 project with pinned host sources, for several
-wave / compute-lane settings (NODEY_WAVE, NODEY_COMPUTE_LANES), then one traced run."""
+wave patterns / compute-lane counts (NODEY_WAVES, NODEY_WAVE, NODEY_COMPUTE_LANES)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
@@ -19,14 +19,10 @@ def timed(label, reps=3):
         t0 = time.perf_counter(); e.run(); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
     print(f"{label}: " + " ".join(f"{t:.1f}" for t in ts) + " ms", flush=True)
 timed("default (warm-up)")
-for lanes in ("1", "2", "3"):
+timed("default")
+patterns = sys.argv[1:] or ["32,64,64,64,32", "32", "16,32,48,64,48,32,16", "32,48,48,48,48,32", "48,64,64,48,32", "32,64,64,48,32,16", "24,40,64,64,40,24"]
+for lanes in ("2", "3"):
     os.environ["NODEY_COMPUTE_LANES"] = lanes
-    timed(f"default waves, lanes={lanes}")
-    for w in ("32", "64"):
-        os.environ["NODEY_WAVE"] = w
-        timed(f"uniform waves of {w}, lanes={lanes}")
-    del os.environ["NODEY_WAVE"]
-del os.environ["NODEY_COMPUTE_LANES"]
-if os.environ.get("TRACE"):
-    os.environ["NODEY_TRACE"] = "1"
-    timed("traced", 1)
+    for pat in patterns:
+        os.environ["NODEY_WAVES"] = pat
+        timed(f"waves {pat}, lanes={lanes}")
