@@ -145,27 +145,74 @@ __device__ __forceinline__ float extract_one(const void* p, int64_t i)
     return ((const float*)p)[i];
 }
 
+// scalar reference form of the four scales (audio-velocity.cpp:186-218)
 template <int FMT>
-__global__ void __launch_bounds__(kBlock) extract_packed_kernel(float* __restrict__ dst, const void* __restrict__ src, int64_t n)
+__device__ __forceinline__ float extract_scale(int v)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = extract_one<FMT>(src, i);
+    // dividing by a power of two is exact, so the S16 / S32 scales are multiplications; 32767 and 2147483647 need
+    // the correctly rounded division
+    if (FMT == NODEY_FMT_S16) return __fmul_rn((float)v, 3.0517578125e-05f);                 // / 32768.0f
+    if (FMT == NODEY_FMT_S16P) return __fdiv_rn((float)v, 32767.0f);
+    if (FMT == NODEY_FMT_S32) return __fmul_rn((float)v, 4.656612873077393e-10f);            // / 2147483648.0f
+    if (FMT == NODEY_FMT_S32P) return __double2float_rn(__ddiv_rn((double)v, 2147483647.0));
+    return __int_as_float(v);
 }
 
+// K samples of one 128-bit load -> floats
 template <int FMT>
-__global__ void __launch_bounds__(kBlock) extract_planar_kernel(float* __restrict__ dst, const void* __restrict__ p0,
-                                                                const void* __restrict__ p1, int64_t nframes, int nch)
+__device__ __forceinline__ void extract_vec(const int4 raw, float (&o)[8])
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nframes; i += stride) {
-        if (nch == 2) {
-            float2 v;
-            v.x = extract_one<FMT>(p0, i);
-            v.y = extract_one<FMT>(p1, i);
-            reinterpret_cast<float2*>(dst)[i] = v;
-        } else {
-            dst[i] = extract_one<FMT>(p0, i);
+    if (FMT == NODEY_FMT_S16 || FMT == NODEY_FMT_S16P) {
+        const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            o[2 * k] = extract_scale<FMT>((int)(short)(w[k] & 0xffff));
+            o[2 * k + 1] = extract_scale<FMT>(w[k] >> 16);
         }
+    } else {
+        o[0] = extract_scale<FMT>(raw.x); o[1] = extract_scale<FMT>(raw.y);
+        o[2] = extract_scale<FMT>(raw.z); o[3] = extract_scale<FMT>(raw.w);
+    }
+}
+
+// packed (or mono planar) source: 128-bit loads and stores, grid-stride; VEC = 0: any alignment, one sample per thread
+template <int FMT, int VEC>
+__global__ void __launch_bounds__(kBlock) extract_packed_kernel(float* __restrict__ dst, const void* __restrict__ src, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int K = (FMT == NODEY_FMT_S16 || FMT == NODEY_FMT_S16P) ? 8 : 4;     // samples per 128-bit load
+    const int64_t nvec = VEC ? n / K : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        float o[8];
+        extract_vec<FMT>(ld_stream4i(reinterpret_cast<const int4*>(src) + i), o);
+        float4* d = reinterpret_cast<float4*>(dst) + i * (K / 4);
+        st_stream4(d, make_float4(o[0], o[1], o[2], o[3]));
+        if (K == 8) st_stream4(d + 1, make_float4(o[4], o[5], o[6], o[7]));
+    }
+    for (int64_t i = nvec * K + tid; i < n; i += stride) dst[i] = extract_one<FMT>(src, i);
+}
+
+// planar stereo source -> interleaved: one 128-bit load per plane, 2 or 4 128-bit stores
+template <int FMT, int VEC>
+__global__ void __launch_bounds__(kBlock) extract_planar_kernel(float* __restrict__ dst, const void* __restrict__ p0,
+                                                                const void* __restrict__ p1, int64_t nframes)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int K = FMT == NODEY_FMT_S16P ? 8 : 4;                                 // frames per 128-bit load
+    const int64_t nvec = VEC ? nframes / K : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        float l[8], r[8];
+        extract_vec<FMT>(ld_stream4i(reinterpret_cast<const int4*>(p0) + i), l);
+        extract_vec<FMT>(ld_stream4i(reinterpret_cast<const int4*>(p1) + i), r);
+        float4* d = reinterpret_cast<float4*>(dst) + i * (K / 2);
+#pragma unroll
+        for (int k = 0; k < K / 2; k++) st_stream4(d + k, make_float4(l[2 * k], r[2 * k], l[2 * k + 1], r[2 * k + 1]));
+    }
+    for (int64_t i = nvec * K + tid; i < nframes; i += stride) {
+        float2 v;
+        v.x = extract_one<FMT>(p0, i);
+        v.y = extract_one<FMT>(p1, i);
+        reinterpret_cast<float2*>(dst)[i] = v;
     }
 }
 
@@ -525,16 +572,22 @@ int nodey_extract_interleaved(float* dst, const void* p0, const void* p1, int fm
     if (nframes == 0) return NODEY_OK;
     cudaStream_t st = as_stream(stream);
     const int64_t n = nframes * nch;
-    const int g = stream_grid(n, kBlock, kCtasPerSm), gp = stream_grid(nframes, kBlock, kCtasPerSm);
+    const bool vec = aligned16(dst) && aligned16(p0) && (nch == 1 || fmt < NODEY_FMT_U8P || aligned16(p1));
+    const int g = stream_grid((n + 7) / 8, kBlock, kCtasPerSm);
+#define NODEY_EXTRACT_PACKED(F) do { if (vec) NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<F, 1><<<g, kBlock, 0, st>>>(dst, p0, n)); \
+                                     else NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<F, 0><<<stream_grid(n, kBlock, kCtasPerSm), kBlock, 0, st>>>(dst, p0, n)); } while (0)
+#define NODEY_EXTRACT_PLANAR(F) do { if (nch == 1) NODEY_EXTRACT_PACKED(F); \
+                                     else if (vec) NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<F, 1><<<g, kBlock, 0, st>>>(dst, p0, p1, nframes)); \
+                                     else NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<F, 0><<<stream_grid(nframes, kBlock, kCtasPerSm), kBlock, 0, st>>>(dst, p0, p1, nframes)); } while (0)
     switch (fmt) {
     case NODEY_FMT_FLT:
         NODEY_CUDA_OK(cudaMemcpyAsync(dst, p0, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, st));
         return NODEY_OK;
-    case NODEY_FMT_S16: NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<NODEY_FMT_S16><<<g, kBlock, 0, st>>>(dst, p0, n)); break;
-    case NODEY_FMT_S32: NODEY_LAUNCH("extract_packed_kernel", st, extract_packed_kernel<NODEY_FMT_S32><<<g, kBlock, 0, st>>>(dst, p0, n)); break;
-    case NODEY_FMT_FLTP: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_FLTP><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
-    case NODEY_FMT_S16P: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_S16P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
-    case NODEY_FMT_S32P: NODEY_LAUNCH("extract_planar_kernel", st, extract_planar_kernel<NODEY_FMT_S32P><<<gp, kBlock, 0, st>>>(dst, p0, p1, nframes, nch)); break;
+    case NODEY_FMT_S16: NODEY_EXTRACT_PACKED(NODEY_FMT_S16); break;
+    case NODEY_FMT_S32: NODEY_EXTRACT_PACKED(NODEY_FMT_S32); break;
+    case NODEY_FMT_FLTP: NODEY_EXTRACT_PLANAR(NODEY_FMT_FLTP); break;
+    case NODEY_FMT_S16P: NODEY_EXTRACT_PLANAR(NODEY_FMT_S16P); break;
+    case NODEY_FMT_S32P: NODEY_EXTRACT_PLANAR(NODEY_FMT_S32P); break;
     default:
         set_error("Unsupported sample format: %d", fmt);
         return NODEY_E_FORMAT;
