@@ -24,6 +24,11 @@ const char* nodey_engine_last_error(void);
 /* infra::register_all_processors() + Graph::deserialize(Json).  NODEY_ENGINE_E_FILE for Invalid_file_error. */
 int nodey_engine_create(nodey_engine** out, const char* project_json);
 void nodey_engine_destroy(nodey_engine* e);
+/* Registers the example processors that are not part of the reference's set (src/register.cpp:14-23):
+ * "frame_gain_example", a node written against the reference's FRAME interface (Audio_stream::try_pop /
+ * try_push / set_eof, src/processor/audio-stream.cpp:60-80) -- the frame-streaming compatibility mode that lets
+ * processors which were never ported to device buffers run inside this engine.  Call before nodey_engine_create. */
+int nodey_engine_register_examples(void);
 
 /* Graph::serialize() with a 2-space indent (src/frontend/app.cpp:837-839).  Returns the length needed. */
 int nodey_engine_serialize(nodey_engine* e, char* buf, int cap);

@@ -51,6 +51,11 @@ def lib():
     return L
 
 
+def register_examples():
+    """registers the example processors outside the reference's set ("frame_gain_example": frame-interface node)"""
+    _check(lib().nodey_engine_register_examples())
+
+
 def _check(rc):
     if rc < 0:
         raise EngineError(rc, lib().nodey_engine_last_error().decode("utf-8", "replace"))

@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <mutex>
+#include <optional>
 #include <utility>
 #include <vector>
 
@@ -55,11 +56,34 @@ namespace processor
 		size_t plane_bytes() const { return (size_t)frames * (size_t)format_bytes(format) * (format_is_planar(format) ? 1u : (size_t)channels); }
 	};
 
+	// Host-side frame of the frame-streaming compatibility mode: the AVFrame subset the reference's nodes touch
+	// (include/processor/audio-stream.hpp:22-42: format, sample_rate, channel count, nb_samples, pts, data planes).
+	struct Audio_frame
+	{
+		int format = FMT_FLT;
+		int sample_rate = 48000;
+		int channels = 2;
+		int64_t nb_samples = 0;                        // samples per channel
+		double pts_seconds = 0.0;
+		std::vector<uint8_t> data[2];                  // packed: data[0]; planar: one plane per channel
+
+		uint8_t* plane(int c) { return data[format_is_planar(format) ? c : 0].data(); }
+		const uint8_t* plane(int c) const { return data[format_is_planar(format) ? c : 0].data(); }
+	};
+
 	class Audio_stream : public infra::Processor::Product
 	{
 		mutable std::mutex mutex;
 		std::shared_ptr<const Audio_buffer> buffer;
 		std::atomic<bool> end_of_stream = false;
+
+		// frame-streaming compatibility mode: a consumer written against the reference's
+		// try_pop() sees the published device buffer cut into its frames (downloaded once, on first use); a
+		// producer written against try_push() has its frames collected and uploaded as one buffer at set_eof()
+		struct Frame_cursor { std::vector<uint8_t> host[2]; size_t run = 0; int64_t left = 0, done = 0; bool loaded = false; };
+		std::unique_ptr<Frame_cursor> cursor;
+		std::vector<std::shared_ptr<const Audio_frame>> pushed;
+		void upload_pushed();
 
 	  public:
 
@@ -85,8 +109,21 @@ namespace processor
 		}
 
 		bool eof() const { return end_of_stream.load(); }
-		void set_eof() { end_of_stream.store(true); }
+		// closes the stream; frames collected by try_push() are uploaded and published first
+		void set_eof()
+		{
+			if (!pushed.empty()) upload_pushed();
+			end_of_stream.store(true);
+		}
 		size_t buffered_count() const { return get() ? 1 : 0; }
+
+		// ---- the reference's frame interface (src/processor/audio-stream.cpp:60-80) ----
+		// try_push: always accepts (no 16-frame bound: nothing drains the stream concurrently); all frames of a
+		// stream must share format, rate and channel count
+		bool try_push(std::shared_ptr<const Audio_frame> frame);
+		// try_pop: next frame of the rendered stream, in the frame sizes the producing node recorded; nullopt when
+		// the stream is drained (check eof()) or nothing was published
+		std::optional<std::shared_ptr<const Audio_frame>> try_pop();
 	};
 
 	// product of audio_spectrum: complex64 bins, [channels][frames][fft_size/2+1], device resident

@@ -187,6 +187,24 @@ namespace processor
 		virtual void deserialize(const Json::Value&) {}
 	};
 
+	// ---- example of a processor written against the reference's FRAME interface --------------------------
+	// (frame-streaming compatibility mode): pops host frames, scales them on the CPU the way the
+	// reference's change_volume<T> does (audio-vol.cpp:75-100) and pushes them on, like a third-party node that
+	// was never ported to device buffers.  Not part of register_all_processors(): the host registers it
+	// explicitly (processor::register_example_processors / nodey_engine_register_examples).
+	class Frame_gain_example : public infra::Processor
+	{
+		float volume = 1.0f;
+
+	  public:
+		Frame_gain_example() = default;
+		virtual ~Frame_gain_example() = default;
+		NODEY_NODE_COMMON(Frame_gain_example)
+		virtual Json::Value serialize() const;
+		virtual void deserialize(const Json::Value& value);
+	};
+	void register_example_processors();
+
 	class Audio_spectrum : public infra::Processor
 	{
 		int fft_size = 4096, hop = 1024;

@@ -75,6 +75,17 @@ int nodey_engine_create(nodey_engine** out, const char* project_json)
 
 void nodey_engine_destroy(nodey_engine* e) { delete e; }
 
+int nodey_engine_register_examples(void)
+{
+	try
+	{
+		register_all_processors();
+		processor::register_example_processors();
+		return 0;
+	}
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_INVALID, err.what()); }
+}
+
 int nodey_engine_serialize(nodey_engine* e, char* buf, int cap)
 {
 	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");

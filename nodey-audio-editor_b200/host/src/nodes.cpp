@@ -174,6 +174,178 @@ namespace processor
 	}
 
 	// ---------------------------------------------------------------------------------------------
+	// frame-streaming compatibility mode of Audio_stream (reference: src/processor/audio-stream.cpp:60-80)
+	// ---------------------------------------------------------------------------------------------
+	bool Audio_stream::try_push(std::shared_ptr<const Audio_frame> frame)
+	{
+		if (!frame || end_of_stream.load()) return false;
+		if (format_bytes(frame->format) == 0 || (frame->channels != 1 && frame->channels != 2) || frame->nb_samples < 0)
+			throw Runtime_error("Invalid audio frame", "A processor pushed a frame this engine cannot carry.",
+								std::format("format {}, channels {}, samples {}", frame->format, frame->channels, frame->nb_samples));
+		if (!pushed.empty())
+		{
+			const Audio_frame& first = *pushed.front();
+			if (first.format != frame->format || first.sample_rate != frame->sample_rate || first.channels != frame->channels)
+				throw Runtime_error("Inconsistent audio frames", "All frames of one stream must share format, sample rate and channel count.",
+									std::format("format {} vs {}, rate {} vs {}", first.format, frame->format, first.sample_rate, frame->sample_rate));
+		}
+		pushed.push_back(std::move(frame));
+		return true;
+	}
+
+	// the collected frames become one device-resident buffer, with their sizes as the stream's frame runs
+	void Audio_stream::upload_pushed()
+	{
+		const Audio_frame& first = *pushed.front();
+		const bool planar2 = format_is_planar(first.format) && first.channels == 2;
+		const size_t sample = (size_t)format_bytes(first.format) * (format_is_planar(first.format) ? 1u : (size_t)first.channels);
+		int64_t total = 0;
+		Frame_runs runs;
+		for (const auto& f : pushed)
+		{
+			if (f->nb_samples == 0) continue;
+			total += f->nb_samples;
+			if (!runs.empty() && runs.back().first == f->nb_samples) runs.back().second++;
+			else runs.emplace_back(f->nb_samples, 1);
+		}
+		const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sample);
+		auto block = std::make_shared<infra::Device_block>(plane * (planar2 ? 2 : 1));
+		// one contiguous host image per plane (kept alive by the buffer's deleter until the copy has landed: the
+		// stream is synchronised here, uploads of this mode are not performance paths)
+		for (int c = 0; c < (planar2 ? 2 : 1); c++)
+		{
+			std::vector<uint8_t> host((size_t)total * sample);
+			size_t at = 0;
+			for (const auto& f : pushed)
+			{
+				const size_t bytes = (size_t)f->nb_samples * sample;
+				if (f->data[c].size() < bytes)
+					throw Runtime_error("Invalid audio frame", "A pushed frame holds fewer samples than it declares.", std::format("{} < {}", f->data[c].size(), bytes));
+				memcpy(host.data() + at, f->data[c].data(), bytes);
+				at += bytes;
+			}
+			if (total > 0)
+			{
+				abi(nodey_memcpy_h2d((char*)block->ptr + c * plane, host.data(), host.size(), cur_stream()), "frame upload");
+				abi(nodey_stream_synchronize(cur_stream()), "frame upload");
+			}
+		}
+		auto b = new_buffer(block, block->ptr, planar2 ? (char*)block->ptr + plane : nullptr, first.format, first.sample_rate, first.channels,
+							total, std::move(runs), first.pts_seconds);
+		auto ev = std::make_shared<infra::Device_event>();
+		ev->record(cur_stream());
+		b->ready = std::move(ev);
+		pushed.clear();
+		{
+			std::lock_guard lock(mutex);
+			buffer = std::move(b);
+		}
+	}
+
+	std::optional<std::shared_ptr<const Audio_frame>> Audio_stream::try_pop()
+	{
+		const auto b = get();
+		if (!b) return std::nullopt;
+		if (!cursor) cursor = std::make_unique<Frame_cursor>();
+		Frame_cursor& cur = *cursor;
+		const bool planar2 = format_is_planar(b->format) && b->channels == 2;
+		const size_t sample = (size_t)format_bytes(b->format) * (format_is_planar(b->format) ? 1u : (size_t)b->channels);
+		if (!cur.loaded)
+		{
+			// download once; the frames below are cut from this image
+			if (b->ready) b->ready->wait_on(cur_stream());
+			for (int c = 0; c < (planar2 ? 2 : 1); c++)
+			{
+				cur.host[c].resize((size_t)b->frames * sample);
+				if (b->frames > 0) abi(nodey_memcpy_d2h(cur.host[c].data(), b->plane[c], cur.host[c].size(), cur_stream()), "frame download");
+			}
+			abi(nodey_stream_synchronize(cur_stream()), "frame download");
+			cur.loaded = true;
+			cur.run = 0;
+			cur.left = b->runs.empty() ? 0 : b->runs[0].second;
+		}
+		while (cur.run < b->runs.size() && (cur.left <= 0 || b->runs[cur.run].first <= 0))
+		{
+			cur.run++;
+			cur.left = cur.run < b->runs.size() ? b->runs[cur.run].second : 0;
+		}
+		if (cur.run >= b->runs.size() || cur.done >= b->frames) return std::nullopt;
+		const int64_t n = std::min<int64_t>(b->runs[cur.run].first, b->frames - cur.done);
+		auto f = std::make_shared<Audio_frame>();
+		f->format = b->format; f->sample_rate = b->sample_rate; f->channels = b->channels; f->nb_samples = n;
+		f->pts_seconds = b->pts_seconds + (double)cur.done / (double)b->sample_rate;
+		for (int c = 0; c < (planar2 ? 2 : 1); c++)
+			f->data[c].assign(cur.host[c].begin() + (size_t)cur.done * sample, cur.host[c].begin() + (size_t)(cur.done + n) * sample);
+		cur.done += n;
+		cur.left--;
+		return std::shared_ptr<const Audio_frame>(std::move(f));
+	}
+
+	// ---------------------------------------------------------------------------------------------
+	// frame_gain_example: a node in the reference's own style (pop a frame, work on the host, push it on)
+	// ---------------------------------------------------------------------------------------------
+	infra::Processor::Info Frame_gain_example::get_processor_info()
+	{
+		return {.identifier = "frame_gain_example", .display_name = "Frame Gain (example)", .singleton = false,
+				.generate = std::make_unique<Frame_gain_example>,
+				.description = "Example of a processor written against the frame interface (try_pop / try_push): scales every frame on the host."};
+	}
+	std::vector<Processor::Pin_attribute> Frame_gain_example::get_pin_attributes() const
+	{
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input", "Input", true)};
+	}
+	Json::Value Frame_gain_example::serialize() const
+	{
+		Json::Value value;
+		value["volume"] = volume;
+		return value;
+	}
+	void Frame_gain_example::deserialize(const Json::Value& value)
+	{
+		if (value.isObject() && value.isMember("volume") && value["volume"].isDouble()) volume = value["volume"].asFloat();
+	}
+	void Frame_gain_example::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop_token, std::any&)
+	{
+		const auto in = infra::get_input_item<Audio_stream>(input, "input");
+		if (!in.has_value())
+			throw Runtime_error("Frame gain has no input", "The example node requires an audio stream on pin 'input'.", "Input item 'input' not found");
+		Audio_stream& stream = in->get();
+		const auto outs = infra::get_output_item<Audio_stream>(output, "output");
+		// the loop shape of the reference's nodes (audio-vol.cpp:102-250): pop, process, push to every link, until EOF
+		while (!stop_token)
+		{
+			const auto popped = stream.try_pop();
+			if (!popped.has_value())
+			{
+				if (stream.eof()) break;
+				continue;       // the reference yields its fiber here; in this engine an unpublished input means an upstream error
+			}
+			const Audio_frame& src = **popped;
+			auto dst = std::make_shared<Audio_frame>(src);
+			const size_t count = (size_t)src.nb_samples * (format_is_planar(src.format) ? 1u : (size_t)src.channels);
+			for (int c = 0; c < (format_is_planar(src.format) ? src.channels : 1); c++)
+			{
+				// change_volume<T>: dst[i] = T(src[i] * volume), float multiply, C++ truncating conversion (audio-vol.cpp:75-100)
+				switch (src.format)
+				{
+				case FMT_FLT: case FMT_FLTP: { auto* p = (float*)dst->data[c].data(); for (size_t i = 0; i < count; i++) p[i] = p[i] * volume; break; }
+				case FMT_S16: case FMT_S16P: { auto* p = (int16_t*)dst->data[c].data(); for (size_t i = 0; i < count; i++) p[i] = (int16_t)(int32_t)((float)p[i] * volume); break; }
+				case FMT_S32: case FMT_S32P: { auto* p = (int32_t*)dst->data[c].data(); for (size_t i = 0; i < count; i++) { const float v = (float)p[i] * volume; p[i] = (v >= -2147483648.0f && v < 2147483648.0f) ? (int32_t)v : INT32_MIN; } break; }
+				default: throw Runtime_error("Audio format is not support (Include FLT, S16, S32)", "Frame gain cannot process this sample format.", std::format("AVSampleFormat {}", src.format));
+				}
+			}
+			for (auto& o : outs) o->try_push(dst);
+		}
+		for (auto& o : outs) o->set_eof();
+	}
+
+	void register_example_processors()
+	{
+		static std::once_flag once;
+		std::call_once(once, [] { Processor::register_processor<Frame_gain_example>(); });
+	}
+
+	// ---------------------------------------------------------------------------------------------
 	// audio_input
 	// ---------------------------------------------------------------------------------------------
 	infra::Processor::Info Audio_input::get_processor_info()

@@ -146,3 +146,21 @@ def test_config5_project_shape(eng):
     assert len(nodes) == 1 + 32 * 4 + 2 + 1 + 1 + 1
     levels = {nid: lvl for nid, _, lvl in nodes}
     assert levels[ids["input"]] == 0 and levels[ids["master"]] == 6 and levels[ids["output"]] == 7
+
+
+def test_example_frame_processor_registers_and_round_trips():
+    """frame-streaming compatibility mode: the frame-interface example node is outside the reference's set until the
+    host registers it; afterwards it loads from project JSON like any other processor"""
+    import engine
+    engine.register_examples()
+    engine.register_examples()          # idempotent
+    p = engine.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    fg = p.add("frame_gain_example", {"volume": 0.25})
+    out = p.add("audio_output")
+    p.link(src, "output_0", fg, "input"); p.link(fg, "output", out, "input")
+    e = engine.Engine(p.json())
+    e.check()
+    again = json.loads(e.serialize())
+    assert again["nodes"][str(fg)]["identifier"] == "frame_gain_example"
+    assert again["nodes"][str(fg)]["info"] == {"volume": 0.25}
