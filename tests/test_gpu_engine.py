@@ -208,3 +208,43 @@ def test_soundtouch_batch_of_mixed_formats(eng_gpu, orc):
         xi = orc.extract_interleaved(x, f)
         ref, _, _ = orc.soundtouch(xi, 48000, 1.0, pitch, 1152)
         assert_bit_equal(e.product(nodes[i], "output").numpy(), ref, f"pitch node {i} (format {f})")
+
+
+def test_tiny_and_ragged_streams_through_the_graph(eng_gpu, orc):
+    """a 300-frame and a 5000-frame source (shorter than a WSOLA sequence, shorter than a resampler tile) through
+    resample -> pitch -> gain -> two-input mix: every length and sample as the oracle's nodes"""
+    xs = [make_input(orc, FMT_FLT, 300, 2, track=1), make_input(orc, FMT_S16, 5000, 2, track=2)]
+    fmts = [FMT_FLT, FMT_S16]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    chain = []
+    for i in range(2):
+        rs = p.add("audio_amix", eng_gpu.amix_info([1.0]))
+        pm = p.add("pitch_modifier", {"pitch": 3.0})
+        g = p.add("audio_volume_adjust")
+        p.link(src, f"output_{i}", rs, "input_1"); p.link(rs, "output", pm, "input"); p.link(pm, "output", g, "input")
+        chain.append((rs, pm, g))
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.5]))
+    out = p.add("audio_output")
+    p.link(chain[0][2], "output", mix, "input_1"); p.link(chain[1][2], "output", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    for i in range(2):
+        e.set_volume(chain[i][2], 0.7)
+        e.bind_source(i, xs[i], fmts[i], 44100)
+    e.run()
+    pitch = orc.pitch_node_factor(3.0)
+    tracks = []
+    for i in range(2):
+        rl, rr = orc.amix([orc.make_track(xs[i], fmts[i], 44100)], [1.0])
+        got = e.product(chain[i][0], "output")
+        assert_bit_equal(got.numpy(), np.stack([rl, rr]), f"resampler node {i}")
+        xi = orc.extract_interleaved(np.stack([rl, rr]), FMT_FLTP)
+        y, _, _ = orc.soundtouch(xi, 48000, 1.0, pitch, 1152)
+        got = e.product(chain[i][1], "output")
+        assert got.frames == y.shape[0]
+        if y.shape[0]:
+            assert_bit_equal(got.numpy(), y, f"pitch node {i}")
+        tracks.append(orc.make_track(orc.gain(y, FMT_FLT, 0.7), FMT_FLT, 48000) if y.shape[0] else None)
+    if all(t is not None for t in tracks):
+        rl, rr = orc.amix(tracks, [0.5, 0.5])
+        assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "mix of the short streams")

@@ -151,3 +151,24 @@ def test_soundtouch_reads_tracks_in_place(nd, orc, cfg, unfused):
         ref, ref_offs, _ = orc.soundtouch(x, sr, rate, pitch, 1152)
         assert np.array_equal(offs[t].cpu().numpy()[:len(ref_offs)], ref_offs), f"track {t}: WSOLA offset trace differs"
         assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t} samples")
+
+
+@pytest.mark.parametrize("n", [0, 1, 100, 1152, 4000, 5615, 5616, 5617, 9000])
+@pytest.mark.parametrize("cfg", [(48000, 2, 1.0, 3.0), (48000, 2, 1.25, None), (44100, 1, 0.8, None)])
+def test_soundtouch_short_inputs(nd, orc, n, cfg):
+    """inputs shorter than one WSOLA sequence, around the first sequence boundary and just above: flush() pads
+    with silence until the expected amount exists (or nothing at all comes out) -- lengths and samples as the oracle"""
+    sr, ch, rate, st_ = cfg
+    pitch = orc.pitch_node_factor(st_) if st_ is not None else orc.velocity_node_pitch(rate, True)
+    x = orc.synth_f32(max(n, 1), ch, sr, 31)[:n]
+    ref, ref_offs, info = orc.soundtouch(x, sr, rate, pitch, 1152)
+    st = nd.SoundTouch(sr, ch, rate, pitch)
+    m, nseq = st.out_frames(n, 1152)
+    assert m == ref.shape[0] and nseq == info.n_sequences
+    if n == 0:
+        return
+    got, offs = st.run(to_dev(x), 1152, want_offsets=True)
+    assert got.shape[0] == m
+    if m:
+        assert np.array_equal(offs.cpu().numpy()[:len(ref_offs)], ref_offs)
+        assert_bit_equal(got.cpu().numpy(), ref, f"short input n={n}")
