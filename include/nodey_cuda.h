@@ -117,6 +117,11 @@ int nodey_bimix(float* out_l, float* out_r, const float* ll, const float* lr, in
                 const float* rl, const float* rr, int64_t len_r, float bias, int64_t nframes,
                 nodey_stream_t stream);
 
+/* Preview sink, src/processor/audio-io.cpp:478-638 (do_preview): after swr has brought the stream to 48 kHz
+ * stereo float, every sample is clamped to [-1, 1] (std::clamp, :598-599) and queued as packed frames.
+ * dst[2j] = clamp(l[j]), dst[2j+1] = clamp(r[j]). */
+int nodey_preview_pack(float* dst, const float* l, const float* r, int64_t nframes, nodey_stream_t stream);
+
 /* A6  audio_bimix_v2 pieces, src/processor/audio-bimix.cpp:625-627 and :777-872.
  * downmix: dst = (l + r) * 0.5.  merge: interleaved stereo out; for frame j of segment s
  * (seg_out_start[s] <= j < seg_out_start[s] + seg_len[s]) L = left[seg_l[s] + d] or 0 when

@@ -59,6 +59,13 @@ int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kin
 /* what arrived at the audio_output sink (same fields) */
 int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames,
                         double* pts_seconds, void** plane0, void** plane1);
+/* Preview instead of export (the reference's Preview state, src/frontend/app.cpp:2001-2040 -> Audio_output::do_preview,
+ * src/processor/audio-io.cpp:478-638): the sink brings the stream to 48 kHz stereo float frame by frame without a
+ * final flush, clamps to [-1, 1] and queues packed frames.  nodey_engine_preview returns that queue content (device
+ * pointer, packed stereo float) and the chunk sizes the sink callback received (one per input frame); the return
+ * value is the number of chunks. */
+int nodey_engine_set_preview(nodey_engine* e, int preview);
+int nodey_engine_preview(nodey_engine* e, int64_t* frames, void** packed, int64_t* chunk_len, int chunk_cap);
 /* frame sizes (run-length encoded) of an audio product: fills up to cap pairs, returns the count */
 int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap);
 

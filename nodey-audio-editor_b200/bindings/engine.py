@@ -47,6 +47,8 @@ def lib():
     L.nodey_engine_product_runs.argtypes = [vp, i32, cp, C.POINTER(i64), C.POINTER(i64), i32]
     L.nodey_engine_output.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(C.c_double),
                                       C.POINTER(vp), C.POINTER(vp)]
+    L.nodey_engine_set_preview.argtypes = [vp, i32]
+    L.nodey_engine_preview.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), i32]
     _lib = L
     return L
 
@@ -150,6 +152,22 @@ class Engine:
 
     def run(self):
         _check(lib().nodey_engine_run(self.h))
+
+    def set_preview(self, on=True):
+        """the next runs take the sink's preview path (swr without flush -> clamp -> packed 48 kHz stereo float)"""
+        _check(lib().nodey_engine_set_preview(self.h, 1 if on else 0))
+
+    def preview(self):
+        """(packed [frames, 2] float32 numpy array, chunk sizes) of the last preview run"""
+        frames, ptr = C.c_int64(), C.c_void_p()
+        cap = 1 << 16
+        chunks = (C.c_int64 * cap)()
+        n = _check(lib().nodey_engine_preview(self.h, C.byref(frames), C.byref(ptr), chunks, cap))
+        out = np.empty((frames.value, 2), np.float32)
+        if frames.value:
+            nodey.check(nodey.lib().nodey_memcpy_d2h(out.ctypes.data_as(C.c_void_p), ptr, out.nbytes, None))
+            nodey.check(nodey.lib().nodey_stream_synchronize(None))
+        return out, [chunks[k] for k in range(min(n, cap))]
 
     def product(self, node_id, pin):
         kind, fmt, rate, ch, extra = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

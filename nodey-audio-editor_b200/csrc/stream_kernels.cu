@@ -391,6 +391,25 @@ __global__ void __launch_bounds__(kBlock) downmix_half_kernel(float* __restrict_
     }
 }
 
+// preview sink (audio-io.cpp:598-599): 48 kHz stereo planes -> packed frames, every sample clamped to [-1, 1]
+// with std::clamp's comparisons (a NaN passes through)
+__device__ __forceinline__ float clamp_unit(float v) { return v < -1.0f ? -1.0f : (1.0f < v ? 1.0f : v); }
+
+__global__ void __launch_bounds__(kBlock) pack_clamp_kernel(float* __restrict__ dst, const float* __restrict__ l,
+                                                            const float* __restrict__ r, int64_t n, int vec)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t npack = (n + 3) / 4;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npack; pk += stride) {
+        const int64_t j = pk * 4;
+        const float4 a = load4_zero_tail(l, j, n, vec), b = load4_zero_tail(r, j, n, vec);
+        const float4 o0 = make_float4(clamp_unit(a.x), clamp_unit(b.x), clamp_unit(a.y), clamp_unit(b.y));
+        const float4 o1 = make_float4(clamp_unit(a.z), clamp_unit(b.z), clamp_unit(a.w), clamp_unit(b.w));
+        store4_tail(dst, 2 * j, 2 * n, o0, vec);
+        store4_tail(dst, 2 * j + 4, 2 * n, o1, vec);
+    }
+}
+
 struct MergeSeg { long long out_start, len, l, r; };
 
 __global__ void __launch_bounds__(kBlock) merge_segments_kernel(float2* __restrict__ out, const float* __restrict__ left,
@@ -672,6 +691,16 @@ int nodey_downmix_half(float* dst, const float* l, const float* r, int64_t n, no
     if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
     const int vec = aligned16(dst) && aligned16(l) && aligned16(r);
     NODEY_LAUNCH("downmix_half_kernel", as_stream(stream), downmix_half_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dst, l, r, n, vec));
+    NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_preview_pack(float* dst, const float* l, const float* r, int64_t n, nodey_stream_t stream)
+{
+    if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
+    NODEY_REQUIRE(dst && l && r, NODEY_E_INVALID, "nodey_preview_pack: null buffer");
+    const int vec = aligned16(dst) && aligned16(l) && aligned16(r);
+    NODEY_LAUNCH("pack_clamp_kernel", as_stream(stream), pack_clamp_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(dst, l, r, n, vec));
     NODEY_LAUNCH_OK();
     return NODEY_OK;
 }

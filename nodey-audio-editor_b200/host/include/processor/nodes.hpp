@@ -16,6 +16,8 @@
 #include "infra/processor.hpp"
 #include "processor/audio-stream.hpp"
 
+#include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -83,6 +85,13 @@ namespace processor
 			size_t kbps = 0;
 			std::shared_ptr<std::atomic<double>> time = std::make_shared<std::atomic<double>>(0.0);
 			std::shared_ptr<const Audio_buffer> rendered;    // OUT: what arrived at the sink (device resident)
+			// do_export == false selects the reference's preview path (audio-io.cpp:478-638): the stream is brought to
+			// 48 kHz stereo float by swr frame by frame WITHOUT a final flush, clamped to [-1, 1] and queued as packed
+			// frames.  OUT: that queue content as one packed buffer whose frame runs are the per-frame chunk sizes.
+			// preview_sink (optional) plays the role of SDL_QueueAudio: it receives the chunks in order (host memory,
+			// packed stereo float) and returns false to stop the preview, like the stop token.
+			std::shared_ptr<const Audio_buffer> preview;
+			std::function<bool(const float* packed_frames, int64_t frames)> preview_sink;
 		};
 
 		Audio_output() = default;

@@ -16,6 +16,8 @@ struct nodey_engine
 	Pcm_source_list sources;
 	std::unique_ptr<Runner> runner;
 	std::shared_ptr<std::any> sink_data;
+	bool preview = false;
+	std::vector<int64_t> preview_chunks;     // chunk sizes the preview sink callback received, in order
 };
 
 namespace
@@ -159,7 +161,10 @@ int nodey_engine_run(nodey_engine* e)
 		if (const auto out = e->graph.singleton_node_map.find("audio_output"); out != e->graph.singleton_node_map.end())
 		{
 			Audio_output::Process_context ctx;
-			ctx.do_export = true;
+			ctx.do_export = !e->preview;
+			e->preview_chunks.clear();
+			if (e->preview)
+				ctx.preview_sink = [e](const float*, int64_t frames) { e->preview_chunks.push_back(frames); return true; };
 			e->sink_data = std::make_shared<std::any>(ctx);
 			node_data[out->second] = e->sink_data;
 		}
@@ -253,6 +258,25 @@ int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channe
 	if (plane0) *plane0 = b->plane[0];
 	if (plane1) *plane1 = b->plane[1];
 	return 0;
+}
+
+int nodey_engine_set_preview(nodey_engine* e, int preview)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	e->preview = preview != 0;
+	return 0;
+}
+
+int nodey_engine_preview(nodey_engine* e, int64_t* frames, void** packed, int64_t* chunk_len, int chunk_cap)
+{
+	if (!e || !e->sink_data) return fail(NODEY_ENGINE_E_INVALID, "the graph has no audio_output node or has not run");
+	const auto* ctx = std::any_cast<Audio_output::Process_context>(e->sink_data.get());
+	if (!ctx || !ctx->preview) return fail(NODEY_ENGINE_E_NODE, "no preview was rendered (nodey_engine_set_preview before the run)");
+	if (frames) *frames = ctx->preview->frames;
+	if (packed) *packed = ctx->preview->plane[0];
+	const int n = (int)e->preview_chunks.size();
+	for (int k = 0; k < n && k < chunk_cap && chunk_len; k++) chunk_len[k] = e->preview_chunks[(size_t)k];
+	return n;
 }
 
 }  // extern "C"

@@ -541,6 +541,66 @@ namespace processor
 		Process_context* ctx = std::any_cast<Process_context>(&user_data);
 		if (!ctx) throw std::bad_any_cast();
 		ctx->rendered = buffer;
+		ctx->preview.reset();
+		if (!ctx->do_export)
+		{
+			// ---- preview (audio-io.cpp:478-638): per input frame swr_convert -> clamp -> queue; never flushed ----
+			check_channels(*buffer, "Audio output");
+			const nodey_resampler* plan = resampler_for(buffer->sample_rate);
+			const int64_t total = nodey_resampler_producible(plan, buffer->frames, 0);
+			if (total < 0) abi((int)total, "Audio output");
+			// chunk sizes: what each swr_convert call returns for the stream's frames
+			Frame_runs chunks;
+			{
+				int64_t fed = 0, made = 0;
+				for (const auto& [len, count] : buffer->runs)
+					for (int64_t k = 0; k < count; k++)
+					{
+						fed += len;
+						const int64_t now = nodey_resampler_producible(plan, std::min(fed, buffer->frames), 0);
+						const int64_t got = now - made;
+						made = now;
+						if (!chunks.empty() && chunks.back().first == got) chunks.back().second++;
+						else chunks.emplace_back(got, 1);
+					}
+			}
+			const size_t bytes = Arena::padded((size_t)std::max<int64_t>(total, 1) * 2 * sizeof(float));
+			auto block = std::make_shared<infra::Device_block>(bytes);
+			if (total > 0)
+			{
+				const size_t plane = Arena::padded((size_t)total * sizeof(float));
+				infra::Device_block planes(2 * plane);
+				float* pl = (float*)planes.ptr;
+				float* pr = (float*)((char*)planes.ptr + plane);
+				abi(nodey_resampler_run(plan, pl, pr, buffer->plane[0], buffer->plane[1], buffer->format, buffer->channels, buffer->frames,
+										0, total, cur_stream()), "Audio output");
+				abi(nodey_preview_pack((float*)block->ptr, pl, pr, total, cur_stream()), "Audio output");
+			}
+			auto pv = new_buffer(block, block->ptr, nullptr, FMT_FLT, 48000, 2, total, std::move(chunks), buffer->pts_seconds);
+			auto ev = std::make_shared<infra::Device_event>();
+			ev->record(cur_stream());
+			pv->ready = std::move(ev);
+			ctx->preview = pv;
+			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
+			if (ctx->preview_sink && total > 0)
+			{
+				// the "audio device": chunks in order from one host image; a false return stops the preview
+				std::vector<float> host((size_t)total * 2);
+				abi(nodey_memcpy_d2h(host.data(), block->ptr, host.size() * sizeof(float), cur_stream()), "audio_output");
+				abi(nodey_stream_synchronize(cur_stream()), "audio_output");
+				int64_t at = 0;
+				bool go = true;
+				for (const auto& [len, count] : pv->runs)
+					for (int64_t k = 0; k < count && go; k++)
+					{
+						if (len > 0) go = ctx->preview_sink(host.data() + 2 * at, len);
+						at += len;
+						if (ctx->time) ctx->time->store((double)at / 48000.0);
+					}
+			}
+			if (ctx->time && !ctx->preview_sink) ctx->time->store((double)total / 48000.0);
+			return;
+		}
 		abi(nodey_stream_synchronize(cur_stream()), "audio_output");     // the sink is where the host waits for the device
 		if (!ctx->export_path.empty())
 		{
