@@ -241,7 +241,10 @@ class Resampler:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().nodey_resampler_destroy(self.h)
+            try:
+                lib().nodey_resampler_destroy(self.h)
+            except TypeError:        # interpreter shutdown: module globals are already gone
+                pass
             self.h = None
 
     __del__ = close
@@ -413,7 +416,10 @@ class SoundTouch:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().nodey_soundtouch_destroy(self.h)
+            try:
+                lib().nodey_soundtouch_destroy(self.h)
+            except TypeError:        # interpreter shutdown: module globals are already gone
+                pass
             self.h = None
 
     __del__ = close
