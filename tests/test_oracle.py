@@ -166,3 +166,61 @@ def test_graph_oracle_linearity_of_mix(orc):
     assert bus.shape[0] == 2 and spec.shape[2] == 2049
     assert bus.shape[1] % 1152 == 0 or True
     assert np.isfinite(bus).all() and np.abs(bus).max() < 2.0
+
+
+def _dominant_hz(y, sr):
+    """frequency of the strongest spectral line of the middle of a signal (parabolic peak interpolation)"""
+    n = len(y)
+    seg = y[n // 4: n // 4 + (1 << int(np.log2(n // 2)))].astype(np.float64)
+    w = np.hanning(len(seg))
+    s = np.abs(np.fft.rfft(seg * w))
+    k = int(np.argmax(s[1:-1])) + 1
+    a, b, c = np.log(s[k - 1] + 1e-30), np.log(s[k] + 1e-30), np.log(s[k + 1] + 1e-30)
+    return (k + 0.5 * (a - c) / (a - 2 * b + c)) * sr / len(seg)
+
+
+@pytest.mark.parametrize("semitones", [3.0, -5.0, 12.0])
+def test_pitch_node_shifts_a_sine_by_the_musical_interval(orc, semitones):
+    """Behavioural pin of the SoundTouch restatement, independent of its rounding: a 440 Hz sine through
+    pitch_modifier comes out at 440 * 2^(st/12) Hz, with the same duration and about the same level
+    (what SoundTouch 2.3.2 documents for setPitch, audio-velocity.cpp:473-474)."""
+    sr, f0, n = 48000, 440.0, 48000 * 3
+    t = np.arange(n) / sr
+    x = np.stack([0.5 * np.sin(2 * np.pi * f0 * t)] * 2, axis=1).astype(np.float32)
+    y, offs, info = orc.soundtouch(x, sr, 1.0, orc.pitch_node_factor(semitones))
+    assert abs(y.shape[0] - n) <= 1
+    want = f0 * 2.0 ** (semitones / 12.0)
+    got = _dominant_hz(y[:, 0], sr)
+    assert abs(got - want) / want < 2e-3, (got, want)
+    rms = float(np.sqrt(np.mean(y[n // 4: 3 * n // 4, 0].astype(np.float64) ** 2)))
+    assert 0.30 < rms < 0.40                                  # 0.5 / sqrt(2) = 0.354 for the input
+    assert offs.min() >= 0 and offs.max() < info.seek_length
+
+
+@pytest.mark.parametrize("velocity,keep", [(1.25, True), (1.25, False), (0.8, True), (2.0, False)])
+def test_velocity_node_changes_duration_and_keeps_or_scales_pitch(orc, velocity, keep):
+    """velocity_modifier (audio-velocity.cpp:445-460): duration / velocity; with keep_pitch the tone stays, without it
+    scales by the velocity like a tape"""
+    sr, f0, n = 44100, 330.0, 44100 * 3
+    t = np.arange(n) / sr
+    x = np.stack([0.4 * np.sin(2 * np.pi * f0 * t), 0.4 * np.cos(2 * np.pi * f0 * t)], axis=1).astype(np.float32)
+    y, _, _ = orc.soundtouch(x, sr, velocity, orc.velocity_node_pitch(velocity, keep))
+    assert abs(y.shape[0] - n / velocity) <= 2
+    want = f0 if keep else f0 * velocity
+    got = _dominant_hz(y[:, 1], sr)
+    assert abs(got - want) / want < 3e-3, (got, want)
+
+
+def test_resampler_matches_an_independent_polyphase_design(orc):
+    """libswresample restatement vs scipy's polyphase resampler (a different Kaiser design of the same conversion):
+    for band-limited content both must agree to well below the level of either filter's stop band"""
+    from scipy import signal
+    sr, n = 44100, 44100
+    t = np.arange(n) / sr
+    x = (0.4 * np.sin(2 * np.pi * 997.0 * t) + 0.2 * np.sin(2 * np.pi * 5003.0 * t + 0.3)).astype(np.float32)
+    l, _ = orc.swr_whole(np.stack([x, x], axis=1), 3, 44100, 48000, flush=True)
+    ref = signal.resample_poly(x.astype(np.float64), 160, 147, window=("kaiser", 9.0))
+    m = min(len(l), len(ref))
+    mid = slice(2000, m - 2000)                                   # away from the two designs' different edge handling
+    err = np.abs(l[:m][mid] - ref[:m][mid]).max()
+    assert err < 2e-4, err
