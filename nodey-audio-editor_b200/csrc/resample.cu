@@ -383,6 +383,32 @@ __device__ __forceinline__ void rs_cp_async8(float* dst_smem, const float* src)
 // PT = periods per thread (tile = 32 * PT periods): the warp-uniform 128-bit tap loads cost about three shared-memory
 // wavefronts each (ncu: 7.7 wavefronts per window position and warp, 2 of them the samples), so with one period per
 // thread the LSU pipe, not the FMA pipe, set the pace; two periods per thread halve the tap traffic per FMA.
+// ---- TMA (bulk async copy engine) staging: one elected thread issues the copy, an mbarrier counts the bytes ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* m, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(m)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* m, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(m)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* m)
+{
+    // 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completion signalled on the mbarrier
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(m)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* m, unsigned parity)
+{
+    unsigned done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(m)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 22)) __trap();      // a byte-count mismatch must not hang the device
+    }
+}
+
 template <int CH, bool MIX, int PT>
 __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_kernel(float* __restrict__ out_l, float* __restrict__ out_r,
                                                                                       const __grid_constant__ TileArgs a,
@@ -395,26 +421,58 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
     float* s_in0 = reinterpret_cast<float*>(s_gs + ((a.n_groups + 3) & ~3));
     constexpr int NBT = kNB * PT;                       // periods per tile
     const int in_tile = (NBT - 1) * a.D + a.span + a.wmax + 1;
-    const int buf_floats = (in_tile * CH + 3) & ~3;
+    const int buf_floats = ((in_tile + 2) * CH + 3) & ~3;      // + 2 frames: a TMA-staged tile starts on an even frame
+    __shared__ __align__(8) unsigned long long mbar[3];        // tile buffer 0, tile buffer 1, tap table
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int q = tid >> 5, lane = tid & 31;           // one phase group per warp
 
-    for (int i = tid; i < a.n_groups * a.wmax * kG; i += nthr) s_hq[i] = a.hq[i];
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init(&mbar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the dense tap table (25 KB for 44.1 -> 48 kHz) is staged by the TMA engine: one bulk copy, one elected thread
+    const unsigned hq_bytes = (unsigned)(a.n_groups * a.wmax * kG * sizeof(float));
+    const bool hq_tma = (hq_bytes & 15u) == 0 && (((uintptr_t)a.hq) & 15) == 0;
+    if (hq_tma) {
+        if (tid == 0) { mbar_expect_tx(&mbar[2], hq_bytes); tma_bulk_g2s(s_hq, a.hq, hq_bytes, &mbar[2]); }
+    } else {
+        for (int i = tid; i < a.n_groups * a.wmax * kG; i += nthr) s_hq[i] = a.hq[i];
+    }
     for (int i = tid; i < a.n_groups; i += nthr) s_gs[i] = a.group_start[i];
 
     const long long total = a.n_tiles * (long long)a.ntracks;
     const int nin = MIX ? a.nin : 1;                  // compile-time 1 without MIX: the accumulators die with the stage
 
-    // stage (item, inp): fill `dst` with the input tile -- asynchronously when the tile is an interior run of float frames
-    const auto stage = [&](long long item, int inp, float* dst) {
+    // stage (item, inp): fill buffer `b` with the input tile -- asynchronously when the tile is an interior run of float
+    // frames.  Returns -1 when the tile was handed to the TMA engine (wait on mbar[b]), else 0; *lead = frames in front of
+    // the tile's first frame inside the buffer.
+    const auto stage = [&](long long item, int inp, int b, int* lead) -> int {
+        float* dst = s_in0 + b * buf_floats;
+        *lead = 0;
         const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
         const long long k0 = tile * (long long)NBT * a.P;
-        if (k0 >= a.out_len[inp]) return;                       // contributes zeros: nothing is read
+        if (k0 >= a.out_len[inp]) return 0;                     // contributes zeros: nothing is read
         const long long in0 = tile * (long long)NBT * a.D + a.s0 - a.center;
         SrcDesc s = a.src[inp];
         if (!MIX) { s.p0 = tp.p0[track]; s.p1 = tp.p1[track]; }
         const bool interior = tile_interior(s, in0, in_tile);
+        if (CH == 2 && interior && s.fmt == NODEY_FMT_FLT && (((uintptr_t)s.p0) & 15) == 0) {
+            // packed float frames: ONE bulk copy by the TMA engine.  It wants 16-byte alignment and size: start on the
+            // even frame at or before in0 and take an even number of frames (the buffer has two spare frames).
+            const long long in0e = in0 & ~1ll;
+            const int ld = (int)(in0 - in0e);
+            const int nfr = (in_tile + ld + 1) & ~1;
+            if (in0e + nfr <= s.n) {
+                if (tid == 0) {
+                    mbar_expect_tx(&mbar[b], (unsigned)nfr * 8u);
+                    tma_bulk_g2s(dst, reinterpret_cast<const float*>(s.p0) + 2 * in0e, (unsigned)nfr * 8u, &mbar[b]);
+                }
+                *lead = ld;
+                return -1;
+            }
+        }
         if (CH == 2 && interior && s.fmt == NODEY_FMT_FLT && (((uintptr_t)s.p0) & 7) == 0) {
             const float* src = reinterpret_cast<const float*>(s.p0) + 2 * in0;
             for (int f = tid; f < in_tile; f += nthr) rs_cp_async8(dst + 2 * f, src + 2 * f);
@@ -428,11 +486,15 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
         } else {
             for (int f = tid; f < in_tile; f += nthr) dst[f] = src_frame(s, in0 + f).x;
         }
+        return 0;
     };
 
     long long item = blockIdx.x;
     int inp = 0, cur = 0;
-    if (item < total) stage(item, 0, s_in0);
+    int lead_cur = 0, lead_nxt = 0, tma_cur = 0, tma_nxt = 0;     // per buffer: frames of lead-in, staged by TMA?
+    unsigned phase = 0;                                            // bit b: parity the next wait on mbar[b] uses
+    if (item < total) tma_cur = stage(item, 0, 0, &lead_cur);
+    if (hq_tma) mbar_wait(&mbar[2], 0);
     float macc[PT][kG][2];
 #pragma unroll
     for (int p = 0; p < PT; p++)
@@ -440,15 +502,18 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
         for (int g = 0; g < kG; g++) macc[p][g][0] = macc[p][g][1] = 0.f;
 
     while (item < total) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        if (tma_cur) { mbar_wait(&mbar[cur], (phase >> cur) & 1u); phase ^= 1u << cur; }
+        else asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic accesses of the other buffer before the TMA rewrites it
         __syncthreads();          // this stage's tile has landed; everybody is done reading the other buffer
         long long nitem = item; int ninp = inp + 1;
         if (ninp >= nin) { ninp = 0; nitem += gridDim.x; }
-        if (nitem < total) stage(nitem, ninp, s_in0 + (cur ^ 1) * buf_floats);
+        tma_nxt = 0; lead_nxt = 0;
+        if (nitem < total) tma_nxt = stage(nitem, ninp, cur ^ 1, &lead_nxt);
 
         const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
         const long long k0 = tile * (long long)NBT * a.P;
-        const float* s_in = s_in0 + cur * buf_floats;
+        const float* s_in = s_in0 + cur * buf_floats + lead_cur * CH;
         const float vol = MIX ? a.vol[inp] : tp.vol[track];
         if (q < a.n_groups) {
             float acc[PT][kG][CH];
@@ -535,6 +600,7 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
             }
         }
         item = nitem; inp = ninp; cur ^= 1;
+        lead_cur = lead_nxt; tma_cur = tma_nxt;
     }
 }
 
@@ -787,7 +853,7 @@ static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, Ti
     const size_t table = (size_t)a.n_groups * a.wmax * kG + (size_t)((a.n_groups + 3) & ~3);
     const auto smem_for = [&](int pt) {
         const size_t in_tile = (size_t)(kNB * pt - 1) * a.D + a.span + a.wmax + 1;
-        return sizeof(float) * (table + 2 * ((in_tile * ch + 3) & ~(size_t)3));
+        return sizeof(float) * (table + 2 * (((in_tile + 2) * ch + 3) & ~(size_t)3));
     };
     // two periods per thread when the double-buffered 64-period tile fits one SM
     int pt = smem_for(2) <= 227 * 1024 ? 2 : 1;
