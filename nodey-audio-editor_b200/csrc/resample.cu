@@ -6,20 +6,22 @@
 // x mirrored about sample 0 on the left and reflected at the end after a flush.  The accumulation
 // order is the oracle's: one accumulator, ascending taps, fused multiply-add.
 //
-// Two kernels:
+// Three kernels:
 //  * resample_generic_kernel: one thread per output frame, any plan (incl. the interpolating
 //    path when the ratio is not exact), taps and samples straight from global/L1.  Correctness
 //    baseline and fallback.
-//  * resample_tile_kernel: the production path for exact-rational plans.  A CTA owns a tile of
-//    32 periods (period = P outputs <-> D input frames).  The input tile is converted to float
-//    once into shared memory; warp w owns a group of G=8 consecutive phases, lane b owns period b.
-//    A thread keeps G x channels accumulators in registers and walks the union window of its
-//    group once: one shared-memory sample feeds G FMAs, and the G taps of a window position are
-//    a warp-uniform broadcast read (dense per-group tap matrix, zero where a phase's window does
-//    not reach).  That takes shared-memory traffic from ~4 B/FMA to ~0.6 B/FMA, which is what
-//    lets an FP32-co-limited FIR approach the HBM roofline.  Results are staged in
-//    shared memory and leave as coalesced 128-bit stores.  Up to 16 inputs can be accumulated in
-//    input order before the store (audio_amix fused; config 3).
+//  * resample_tile2_kernel: the production path for exact-rational plans with at most 160 phases
+//    (one phase group per warp; 44.1 -> 48 kHz: 160 phases, 20 groups).  A CTA owns a tile of 32 or 64
+//    periods (period = P outputs <-> D input frames).  Tap table and packed-float input tiles are
+//    staged by the TMA engine (cp.async.bulk + mbarrier), the tiles double buffered; warp w owns a
+//    group of G=8 consecutive phases, lane b owns period b (and b + 32).  A thread keeps G x channels
+//    (x periods) accumulators in registers and walks the union window of its group once: one
+//    shared-memory sample feeds G FMAs, and the G taps of a window position are a warp-uniform
+//    broadcast read (dense per-group tap matrix, zero where a phase's window does not reach).  The
+//    accumulators survive across the <= 16 inputs of a mix (audio_amix fused; config 3) and leave as
+//    128-bit stores; one launch covers a batch of tracks.
+//  * resample_tile_kernel: the same arithmetic with shared staging rows and a copy-out pass, for
+//    plans with more phase groups than warps (e.g. 22.05 -> 48 kHz: 320 phases).
 #include "nodey_common.cuh"
 
 #include <math.h>
