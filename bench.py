@@ -279,10 +279,16 @@ def run_ours(args):
 
     # ---- per-kernel device time of one step (events around every launch; not part of the timed runs) ----
     roofline = None
+    # The render runs as two half-size waves on two compute lanes; kernels of the two lanes overlap, so events around
+    # a launch would time its share of the machine, not the kernel.  The profiled step therefore runs the same graph
+    # as ONE wave on one lane (NODEY_WAVE larger than the pin count): every launch alone on the device, full batch.
+    os.environ["NODEY_WAVE"] = "1000000"
+    step_device()
     nodey.profile_enable(True)
     step_device()
     rep = nodey.profile_report()
     nodey.profile_enable(False)
+    del os.environ["NODEY_WAVE"]
     if rank == 0 and rep:
         peaks = {}
         try:
@@ -309,6 +315,15 @@ def run_ours(args):
                             "operations per input frame, sequential per track), so its HBM fraction is small by construction; "
                             "`fp32` gives its fraction of the FP32 issue peak; see DESIGN.md 3.1",
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}
+        # every kernel of the step against the same HBM peak: algorithmic bytes of its launches / its device time
+        per_kernel = {}
+        batches = {"resample_tile_kernel": st_batch, "tds_offsets_kernel": st_batch, "st_post_kernel": st_batch}
+        for k, v in rep.items():
+            kb = kernel_algo_bytes(k, plan, batches.get(k, 1))
+            if kb and v["ms"] > 0:
+                gbs = kb * v["launches"] / (v["ms"] * 1e-3) / 1e9
+                per_kernel[k] = {"launches": v["launches"], "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        roofline["kernels_hbm"] = per_kernel
         if name == "tds_offsets_kernel":
             sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
             fp_peak = nodey.device_info()["sm_count"] * 128 * sm_mhz * 1e6          # one FP32 operation per lane and clock (no FMA: -fmad=false)

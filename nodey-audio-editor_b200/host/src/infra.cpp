@@ -395,8 +395,8 @@ namespace infra
 
 		// waves: links leaving a source node (level 0) belong to wave (position of the pin among the node's
 		// output pins) / wave_size; every other node runs in the latest wave among its inputs
-		// Waves only pay off when there is a host -> device upload to hide behind compute (smaller batches
-		// cost some kernel efficiency): one wave when the sources are already in HBM.
+		// Waves hide the host -> device upload behind compute; smaller batches cost some kernel efficiency, so a render
+		// whose sources are already in HBM runs as one wave, or as two halves from 128 source pins on (see below).
 		size_t upload = 0;
 		std::any no_data;
 		if (!levels.empty())
@@ -436,6 +436,14 @@ namespace infra
 		}
 		else if (uniform > 0)
 			for (int p = uniform; p < source_pins; p += uniform) wave_begin.push_back(p);
+		else if (!pipelined && source_pins >= 128)
+		{
+			// sources already in HBM: two half-size waves on two lanes.  The batched kernels lose nothing at 64+ tracks,
+			// and the second lane fills what a single stream leaves idle -- the SMs that hold one WSOLA CTA instead of
+			// two, the tail of every kernel (256 tracks: 241 -> 233 ms, 128 tracks: 129 -> 126 ms; 64 tracks lose 3 %,
+			// tools/value_waves.py)
+			wave_begin.push_back(((source_pins / 2 + 15) / 16) * 16);
+		}
 		else if (pipelined && source_pins > 32)
 		{
 			constexpr int kEdge = 32, kBody = 32;
