@@ -31,6 +31,7 @@
 
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -1194,6 +1195,7 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             if ((long long)ntracks * 4 <= 160ll * sm_count() / 148) CL = 4;
             else if ((long long)ntracks * 2 <= 400ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
+            if (const char* env = getenv("NODEY_TDS_CLUSTER")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) CL = v; }   // development override
             const int KT = CL >= 4 ? 4 : 8;
             const int K = 4 / CH;
             const int tcount = (s->seek_length + K - 1) / K, tblocks = (tcount + KT - 1) / KT;
