@@ -244,9 +244,16 @@ def run_ours(args):
         for t in range(t_local):
             eng.bind_source(t, sources[t], nodey.FMT_FLT, IN_RATE)
 
+    dev_split = [0.0, 0.0]
+
     def step_device():
+        t0 = time.perf_counter()
         eng.run()
+        t1 = time.perf_counter()
         finish()
+        if world > 1:
+            torch.cuda.synchronize()
+        dev_split[0] += t1 - t0; dev_split[1] += time.perf_counter() - t1
 
     def timed(fn, steps):
         if world > 1:
@@ -271,7 +278,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = nodey.profile_launches()
+    dev_split[0] = dev_split[1] = 0.0
     ms_total = timed(step_device, args.steps)
+    print(f"[bench] rank {rank} device-resident split per step: engine run {dev_split[0] / args.steps * 1e3:.1f} ms, "
+          f"bus reduce / spectrum {dev_split[1] / args.steps * 1e3:.1f} ms", file=sys.stderr, flush=True)
     launches = nodey.profile_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     audio = args.tracks * args.seconds * args.steps
