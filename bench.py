@@ -225,9 +225,10 @@ def run_ours(args):
             dist.reduce(bus_t[0], dst=0, op=dist.ReduceOp.SUM)
             spec_ptr, spec_elems = None, 0
             if rank == 0:
-                spec = nodey.stft(bus_t[0], False)
+                if len(bus_t) < 2:     # the spectrum buffer is allocated once: a fresh 221 MB cudaMalloc per step stalled rank 0 for up to 50 ms
+                    bus_t.append(torch.empty((2, nodey.stft_frames(out.frames), 2049), dtype=torch.complex64, device=dev))
+                spec = nodey.stft(bus_t[0], False, out=bus_t[1])
                 spec_ptr, spec_elems = spec.data_ptr(), spec.numel()
-                bus_t.append(spec)     # keep alive
             p0, p1 = bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr()
         else:
             sp = eng.product(ids["spectrum"], "output")
