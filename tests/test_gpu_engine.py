@@ -248,3 +248,57 @@ def test_tiny_and_ragged_streams_through_the_graph(eng_gpu, orc):
     if all(t is not None for t in tracks):
         rl, rr = orc.amix(tracks, [0.5, 0.5])
         assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "mix of the short streams")
+
+
+@pytest.mark.parametrize("env", [{"NODEY_WAVE": "16"}, {"NODEY_WAVES": "16,8,8", "NODEY_COMPUTE_LANES": "3"},
+                                 {"NODEY_WAVE": "16", "NODEY_COMPUTE_LANES": "1"}, {"NODEY_WAVES": "8,24"}],
+                         ids=["two-waves-two-lanes", "three-waves-three-lanes", "two-waves-one-lane", "uneven-waves"])
+def test_config5_graph_in_waves_on_several_lanes(eng_gpu, orc, env, monkeypatch):
+    """The Runner's wave schedule (what a large render uses: blocks of source pins on rotating compute lanes, nodes that
+    join several waves -- the level-1 mixes of a group cut by a wave boundary, the master mix -- waiting on the other
+    lanes' events) must not change a single bit of the result.  Forced here at small size through the development
+    overrides; host-bound sources so that the uploads run on the transfer lane as well."""
+    from oracle import graph_oracle as G
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 44100 + 333
+    tracks = [orc.synth_f32(n, 2, 44100, t) for t in range(32)]
+    gains = [G.track_gain(t) for t in range(32)]
+    p, ids = eng_gpu.config5_project(32, gains)
+    e = eng_gpu.Engine(p.json())
+    for t, x in enumerate(tracks):
+        e.bind_source(t, x, FMT_FLT, 44100)          # numpy arrays: uploaded by audio_input
+    ref_bus, ref_spec = G.render(tracks, threads=8)
+    for _ in range(2):                                # twice: the second run reuses cached device blocks across lanes
+        e.run()
+        assert_bit_equal(e.output().numpy(), ref_bus, f"master bus with {env}")
+    spec = e.product(ids["spectrum"], "output").numpy()
+    peak = np.abs(ref_spec).max(axis=-1, keepdims=True)
+    assert (np.abs(spec - ref_spec) <= 1e-5 * np.maximum(peak, 1e-30)).all()
+
+
+def test_device_resident_render_of_128_tracks_takes_two_waves_and_matches(eng_gpu, orc, nd):
+    """from 128 source pins on, a render whose sources are already in HBM runs as two half-size waves on two lanes (the
+    default the bench uses at 256 tracks): same bits as the oracle graph and as the single-wave schedule"""
+    import torch
+    from oracle import graph_oracle as G
+    n = 44100 + 17
+    T = 128
+    tracks = [orc.synth_f32(n, 2, 44100, t) for t in range(T)]
+    gains = [G.track_gain(t) for t in range(T)]
+    p, ids = eng_gpu.config5_project(T, gains)
+    e = eng_gpu.Engine(p.json())
+    dev = [torch.from_numpy(x).cuda() for x in tracks]
+    for t in range(T):
+        e.bind_source(t, dev[t], FMT_FLT, 44100)
+    e.run()
+    two = e.output().numpy().copy()
+    ref_bus, _ = G.render(tracks, threads=8, spectrum=False)
+    assert_bit_equal(two, ref_bus, "two-wave master bus vs oracle")
+    import os
+    os.environ["NODEY_WAVE"] = "1000000"
+    try:
+        e.run()
+        assert_bit_equal(e.output().numpy(), two, "single-wave schedule")
+    finally:
+        del os.environ["NODEY_WAVE"]
