@@ -59,6 +59,11 @@ int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kin
 /* what arrived at the audio_output sink (same fields) */
 int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames,
                         double* pts_seconds, void** plane0, void** plane1);
+/* Process_context::export_path of the sink (src/frontend/app.cpp:2067-2073): "" keeps the result in memory only, a
+ * path makes the export also write an interleaved 32-bit float WAV (the reference encodes MP3 with LAME, which this
+ * image does not have), with do_export's pts rule: (int)(first pts * sample_rate) frames of silence in front
+ * (src/processor/audio-io.cpp:833-839). */
+int nodey_engine_set_export_path(nodey_engine* e, const char* path);
 /* Preview instead of export (the reference's Preview state, src/frontend/app.cpp:2001-2040 -> Audio_output::do_preview,
  * src/processor/audio-io.cpp:478-638): the sink brings the stream to 48 kHz stereo float frame by frame without a
  * final flush, clamps to [-1, 1] and queues packed frames.  nodey_engine_preview returns that queue content (device

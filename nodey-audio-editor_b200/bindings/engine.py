@@ -47,6 +47,7 @@ def lib():
     L.nodey_engine_product_runs.argtypes = [vp, i32, cp, C.POINTER(i64), C.POINTER(i64), i32]
     L.nodey_engine_output.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(C.c_double),
                                       C.POINTER(vp), C.POINTER(vp)]
+    L.nodey_engine_set_export_path.argtypes = [vp, cp]
     L.nodey_engine_set_preview.argtypes = [vp, i32]
     L.nodey_engine_preview.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), i32]
     _lib = L
@@ -152,6 +153,10 @@ class Engine:
 
     def run(self):
         _check(lib().nodey_engine_run(self.h))
+
+    def set_export_path(self, path):
+        """the sink also writes the exported stream as a 32-bit float WAV ("" = memory only)"""
+        _check(lib().nodey_engine_set_export_path(self.h, (path or "").encode()))
 
     def set_preview(self, on=True):
         """the next runs take the sink's preview path (swr without flush -> clamp -> packed 48 kHz stereo float)"""

@@ -17,6 +17,7 @@ struct nodey_engine
 	std::unique_ptr<Runner> runner;
 	std::shared_ptr<std::any> sink_data;
 	bool preview = false;
+	std::string export_path;
 	std::vector<int64_t> preview_chunks;     // chunk sizes the preview sink callback received, in order
 };
 
@@ -162,6 +163,7 @@ int nodey_engine_run(nodey_engine* e)
 		{
 			Audio_output::Process_context ctx;
 			ctx.do_export = !e->preview;
+			ctx.export_path = e->export_path;
 			e->preview_chunks.clear();
 			if (e->preview)
 				ctx.preview_sink = [e](const float*, int64_t frames) { e->preview_chunks.push_back(frames); return true; };
@@ -257,6 +259,13 @@ int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channe
 	if (pts_seconds) *pts_seconds = b->pts_seconds;
 	if (plane0) *plane0 = b->plane[0];
 	if (plane1) *plane1 = b->plane[1];
+	return 0;
+}
+
+int nodey_engine_set_export_path(nodey_engine* e, const char* path)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	e->export_path = path ? path : "";
 	return 0;
 }
 

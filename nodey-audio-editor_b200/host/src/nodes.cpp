@@ -614,15 +614,23 @@ namespace processor
 			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
 			std::ofstream f(ctx->export_path, std::ios::binary);
 			if (!f) throw Runtime_error("Cannot write output file", "The export path could not be opened for writing.", ctx->export_path);
-			const uint32_t data_bytes = (uint32_t)(host.size() * sizeof(float));
+			// do_export's pts rule (audio-io.cpp:833-839): before a frame, (int)((frame_begin - time) * sample_rate) samples of
+			// silence are encoded; `time` starts at 0 and then follows the frame ends, so what matters is the stream's
+			// first pts -- including the end-time stamps of amix / bimix (App. C4), which make the reference prepend one
+			// frame of silence to their exports
+			const int lead = std::max(0, (int)(buffer->pts_seconds * (double)buffer->sample_rate));
+			const std::vector<float> silence((size_t)lead * (size_t)buffer->channels, 0.0f);
+			const uint32_t data_bytes = (uint32_t)((host.size() + silence.size()) * sizeof(float));
 			const uint16_t tag = 3, ch = (uint16_t)buffer->channels, bits = 32, align = (uint16_t)(4 * buffer->channels);
 			const uint32_t rate = (uint32_t)buffer->sample_rate, byte_rate = rate * align, riff = 36 + data_bytes, fmt_size = 16;
 			f.write("RIFF", 4); f.write((const char*)&riff, 4); f.write("WAVEfmt ", 8); f.write((const char*)&fmt_size, 4);
 			f.write((const char*)&tag, 2); f.write((const char*)&ch, 2); f.write((const char*)&rate, 4); f.write((const char*)&byte_rate, 4);
 			f.write((const char*)&align, 2); f.write((const char*)&bits, 2); f.write("data", 4); f.write((const char*)&data_bytes, 4);
-			f.write((const char*)host.data(), data_bytes);
+			f.write((const char*)silence.data(), (std::streamsize)(silence.size() * sizeof(float)));
+			f.write((const char*)host.data(), (std::streamsize)(host.size() * sizeof(float)));
 		}
-		if (ctx->time) ctx->time->store((double)buffer->frames / (double)buffer->sample_rate);
+		// `time` ends at the end of the last frame (audio-io.cpp:838)
+		if (ctx->time) ctx->time->store(std::max(0.0, buffer->pts_seconds) + (double)buffer->frames / (double)buffer->sample_rate);
 	}
 
 	// ---------------------------------------------------------------------------------------------

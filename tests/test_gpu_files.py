@@ -1,0 +1,91 @@
+"""GPU: the PCM / WAV edges of the render.  audio_input reads canonical RIFF/WAVE files named by
+the project's file_path (PCM 16 bit and IEEE float; the reference decodes with libavformat, 1024-sample packets for
+WAV PCM); audio_output's export writes a float WAV and keeps do_export's pts rule: (int)(first pts * sample_rate)
+frames of silence in front of the stream (src/processor/audio-io.cpp:833-839)."""
+import struct
+import wave
+
+import numpy as np
+import pytest
+
+from helpers import FMT_FLT, FMT_FLTP, FMT_S16, assert_bit_equal, make_input
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_float_wav(path, x, rate):
+    data = np.ascontiguousarray(x, np.float32).tobytes()
+    ch = x.shape[1]
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 3, ch, rate, rate * 4 * ch, 4 * ch, 32))
+        f.write(b"data" + struct.pack("<I", len(data)) + data)
+
+
+def _read_float_wav(path):
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"RIFF" and raw[8:16] == b"WAVEfmt "
+    tag, ch, rate = struct.unpack("<HHI", raw[20:28])
+    assert tag == 3 and raw[36:40] == b"data"
+    n = struct.unpack("<I", raw[40:44])[0]
+    return np.frombuffer(raw[44:44 + n], np.float32).reshape(-1, ch), rate
+
+
+def test_wav_sources_through_gain_and_float_wav_export(eng_gpu, orc, tmp_path):
+    n = 30000
+    s16 = make_input(orc, FMT_S16, n, 2, track=1)
+    flt = make_input(orc, FMT_FLT, n + 500, 2, track=2)
+    with wave.open(str(tmp_path / "a.wav"), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(44100); w.writeframes(s16.tobytes())
+    _write_float_wav(str(tmp_path / "b.wav"), flt, 44100)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [str(tmp_path / "a.wav"), str(tmp_path / "b.wav")]})
+    ga = p.add("audio_volume_adjust"); gb = p.add("audio_volume_adjust")
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.5]))
+    out = p.add("audio_output")
+    p.link(src, "output_0", ga, "input"); p.link(src, "output_1", gb, "input")
+    p.link(ga, "output", mix, "input_1"); p.link(gb, "output", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_volume(ga, 0.8); e.set_volume(gb, 0.6)
+    e.set_export_path(str(tmp_path / "out.wav"))
+    e.run()
+    a = orc.gain(s16, FMT_S16, 0.8); b = orc.gain(flt, FMT_FLT, 0.6)
+    assert_bit_equal(e.product(ga, "output").numpy(), a, "gain of the 16-bit WAV source")
+    assert e.product_runs(ga, "output")[0][0] == 1024            # WAV PCM packets
+    rl, rr = orc.amix([orc.make_track(a, FMT_S16, 44100, frame_size=1024), orc.make_track(b, FMT_FLT, 44100, frame_size=1024)], [0.5, 0.5])
+    got = e.output()
+    assert_bit_equal(got.numpy(), np.stack([rl, rr]), "mix of the two files")
+    y, rate = _read_float_wav(str(tmp_path / "out.wav"))
+    assert rate == 48000
+    # amix stamps frames with their END time (App. C4), so the reference's export prepends one frame of silence
+    lead = int(got.pts * 48000)
+    assert lead == 1024 and not y[:lead].any()
+    assert_bit_equal(y[lead:], np.ascontiguousarray(np.stack([rl, rr]).T), "exported WAV")
+
+
+def test_export_pads_a_late_stream_with_silence(eng_gpu, orc, tmp_path):
+    x = make_input(orc, FMT_FLT, 5000, 2, rate=48000)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    g = p.add("audio_volume_adjust")
+    out = p.add("audio_output")
+    p.link(src, "output_0", g, "input"); p.link(g, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_export_path(str(tmp_path / "late.wav"))
+    e.bind_source(0, x, FMT_FLT, 48000, pts=0.25)
+    e.run()
+    y, _ = _read_float_wav(str(tmp_path / "late.wav"))
+    assert y.shape[0] == 12000 + 5000 and not y[:12000].any()
+    assert_bit_equal(y[12000:], x, "late stream after its silence")
+
+
+def test_missing_and_malformed_files_are_runtime_errors(eng_gpu, tmp_path):
+    (tmp_path / "bad.wav").write_bytes(b"RIFF....WAVEjunk")
+    for path, text in ((str(tmp_path / "nope.wav"), "Cannot open audio file"), (str(tmp_path / "bad.wav"), "Cannot open audio file")):
+        p = eng_gpu.Project()
+        src = p.add("audio_input", {"file_path": [path]})
+        out = p.add("audio_output")
+        p.link(src, "output_0", out, "input")
+        e = eng_gpu.Engine(p.json())
+        with pytest.raises(eng_gpu.EngineError) as x:
+            e.run()
+        assert text in x.value.message
