@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
                 const int pstep = kNB * a.D;                       // input frames between a thread's periods
                 if (CH == 2) {
                     const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
-#pragma unroll 2
+#pragma unroll 3
                     for (int m = 0; m < a.wmax; m++) {
                         const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
                         const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
                     }
                 } else {
                     const float* x1 = s_in + base;
-#pragma unroll 2
+#pragma unroll 3
                     for (int m = 0; m < a.wmax; m++) {
                         const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
                         const float4 h1 = *reinterpret_cast<const float4*>(hq + m * kG + 4);
