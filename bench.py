@@ -147,7 +147,7 @@ def kernel_algo_bytes(name, r, batch):
         "extract_planar_kernel": r.total1 * f8 * 2,
         "tds_offsets_kernel": None,                                               # filled per node below
         "st_post_kernel": None,
-        "gain_f32_kernel": r.m2 * f8 * 2,
+        "gain_f32_kernel": batch * r.m2 * f8 * 2,                                # one launch per batch of audio_volume_adjust nodes
         "to_fltp_kernel": r.m2 * f8 * 2,
         "mix_kernel": 16 * r.m2 * f8 + r.total2 * f8,
         "stft4096_kernel": r.total2 * f8 + 2 * r.spec_frames * 2049 * 8,
@@ -328,7 +328,7 @@ def run_ours(args):
                     "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}}
         # every kernel of the step against the same HBM peak: algorithmic bytes of its launches / its device time
         per_kernel = {}
-        batches = {"resample_tile_kernel": st_batch, "tds_offsets_kernel": st_batch, "st_post_kernel": st_batch}
+        batches = {"resample_tile_kernel": st_batch, "tds_offsets_kernel": st_batch, "st_post_kernel": st_batch, "gain_f32_kernel": st_batch}
         for k, v in rep.items():
             kb = kernel_algo_bytes(k, plan, batches.get(k, 1))
             if kb and v["ms"] > 0:

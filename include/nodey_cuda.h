@@ -85,6 +85,10 @@ int nodey_synth(float* dst_f32, int16_t* dst_s16, int64_t nframes, int nch, int 
  * dst[i] = T(src[i] * volume) over n_elems samples of one plane (packed: frames*channels).
  * Integer formats follow the x86 truncating conversion the reference compiles to (no clamp). */
 int nodey_gain(void* dst, const void* src, int fmt, int64_t n_elems, float volume, nodey_stream_t stream);
+/* The same for a batch of float streams in one launch (HOST arrays of ntracks entries: device pointers, sample
+ * counts, gains): the per-track audio_volume_adjust nodes of one graph level. */
+int nodey_gain_tracks(void* const* dst, const void* const* src, const int64_t* n, const float* volumes, int fmt,
+                      int ntracks, nodey_stream_t stream);
 
 /* A8  extract_samples_interleaved, src/processor/audio-velocity.cpp:150-232.
  * Any of the six formats -> interleaved float, with the reference's four integer scales. */

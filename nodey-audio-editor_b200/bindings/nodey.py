@@ -22,7 +22,7 @@ SYMBOLS = [
     "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
     "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
-    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resampler_segment", "nodey_preview_pack", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
+    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
     "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
@@ -76,6 +76,7 @@ def lib():
     L.nodey_resampler_run_mode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, i32, vp]
     L.nodey_resample_tracks.argtypes = [vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i64, C.POINTER(C.c_float), i32, i32, i64, i64, vp]
     L.nodey_preview_pack.argtypes = [vp, vp, vp, i64, vp]
+    L.nodey_gain_tracks.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_float), i32, i32, vp]
     L.nodey_resampler_segment.argtypes = [vp, i64, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.nodey_resample_mix.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
                                      C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float), i32, i32, i64, vp]

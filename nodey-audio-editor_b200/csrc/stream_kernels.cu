@@ -92,6 +92,35 @@ __global__ void __launch_bounds__(kBlock) gain_f32_kernel(float* __restrict__ ds
     for (int64_t i = nvec * 4 + tid; i < n; i += stride) dst[i] = __fmul_rn(src[i], v);
 }
 
+// a batch of float streams in one launch (the per-track audio_volume_adjust nodes of a render): blockIdx.y = stream,
+// pointers, lengths and gains ride in the kernel parameters
+constexpr int kMaxGainBatch = 256;
+struct GainBatch {
+    float* dst[kMaxGainBatch];
+    const float* src[kMaxGainBatch];
+    long long n[kMaxGainBatch];
+    float vol[kMaxGainBatch];
+    int vec[kMaxGainBatch];
+};
+
+__global__ void __launch_bounds__(kBlock) gain_f32_batch_kernel(const __grid_constant__ GainBatch b)
+{
+    const int t = blockIdx.y;
+    float* __restrict__ dst = b.dst[t];
+    const float* __restrict__ src = b.src[t];
+    const int64_t n = b.n[t];
+    const float v = b.vol[t];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nvec = b.vec[t] ? n / 4 : 0;
+    for (int64_t i = tid; i < nvec; i += stride) {
+        float4 x = ld_stream4(reinterpret_cast<const float4*>(src) + i);
+        x.x = __fmul_rn(x.x, v); x.y = __fmul_rn(x.y, v); x.z = __fmul_rn(x.z, v); x.w = __fmul_rn(x.w, v);
+        st_stream4(reinterpret_cast<float4*>(dst) + i, x);
+    }
+    for (int64_t i = nvec * 4 + tid; i < n; i += stride) dst[i] = __fmul_rn(src[i], v);
+}
+
 __device__ __forceinline__ short gain_s16_one(short s, float v)
 {
     return (short)(unsigned short)(unsigned)x86_trunc(__fmul_rn((float)s, v));
@@ -580,6 +609,34 @@ int nodey_gain(void* dst, const void* src, int fmt, int64_t n, float volume, nod
         return NODEY_E_FORMAT;
     }
     NODEY_LAUNCH_OK();
+    return NODEY_OK;
+}
+
+int nodey_gain_tracks(void* const* dst, const void* const* src, const int64_t* n, const float* volumes, int fmt, int ntracks,
+                      nodey_stream_t stream)
+{
+    NODEY_REQUIRE(dst && src && n && volumes && ntracks >= 0, NODEY_E_INVALID, "nodey_gain_tracks: null argument");
+    NODEY_REQUIRE(fmt == NODEY_FMT_FLT || fmt == NODEY_FMT_FLTP, NODEY_E_FORMAT, "nodey_gain_tracks: float streams only (format %d)", fmt);
+    cudaStream_t st = as_stream(stream);
+    static thread_local GainBatch b;
+    for (int first = 0; first < ntracks; first += kMaxGainBatch) {
+        const int cnt = ntracks - first < kMaxGainBatch ? ntracks - first : kMaxGainBatch;
+        int64_t longest = 0;
+        for (int t = 0; t < cnt; t++) {
+            NODEY_REQUIRE(n[first + t] >= 0 && (n[first + t] == 0 || (dst[first + t] && src[first + t])), NODEY_E_INVALID, "nodey_gain_tracks: null buffer or negative size");
+            b.dst[t] = (float*)dst[first + t]; b.src[t] = (const float*)src[first + t]; b.n[t] = n[first + t]; b.vol[t] = volumes[first + t];
+            b.vec[t] = aligned16(dst[first + t]) && aligned16(src[first + t]);
+            if (n[first + t] > longest) longest = n[first + t];
+        }
+        if (longest == 0) continue;
+        // about kCtasPerSm CTAs per SM in total, at least one per stream
+        int64_t gx = ((int64_t)sm_count() * kCtasPerSm + cnt - 1) / cnt;
+        const int64_t need = (longest / 4 + kBlock) / kBlock;
+        if (gx > need) gx = need;
+        if (gx < 1) gx = 1;
+        NODEY_LAUNCH("gain_f32_kernel", st, gain_f32_batch_kernel<<<dim3((unsigned)gx, (unsigned)cnt), kBlock, 0, st>>>(b));
+        NODEY_LAUNCH_OK();
+    }
     return NODEY_OK;
 }
 

@@ -677,14 +677,33 @@ namespace processor
 			bytes += Arena::padded(ins.back()->plane_bytes()) * (planar2 ? 2 : 1);
 		}
 		Arena arena(bytes);
+		// float streams (planes) of the whole batch go to ONE launch; integer formats run per stream.  Products are
+		// published after everything is enqueued: publish() records the event the consumers wait on.
+		std::vector<void*> bd; std::vector<const void*> bs; std::vector<int64_t> bn; std::vector<float> bv;
+		std::vector<std::pair<void*, void*>> planes;
 		for (size_t k = 0; k < items.size(); k++)
 		{
 			const Audio_buffer& in = *ins[k];
 			const bool planar2 = format_is_planar(in.format) && in.channels == 2;
 			void* p0 = arena.take(in.plane_bytes());
 			void* p1 = planar2 ? arena.take(in.plane_bytes()) : nullptr;
-			gain_into(in, static_cast<Audio_vol*>(items[k].processor)->volume, p0, p1);
-			publish(*items[k].output, "output", new_buffer(arena.block, p0, p1, in.format, in.sample_rate, in.channels, in.frames, in.runs, in.pts_seconds));
+			planes.emplace_back(p0, p1);
+			const float volume = static_cast<Audio_vol*>(items[k].processor)->volume;
+			if (in.format == FMT_FLT || in.format == FMT_FLTP)
+			{
+				const int64_t n = format_is_planar(in.format) ? in.frames : in.frames * in.channels;
+				bd.push_back(p0); bs.push_back(in.plane[0]); bn.push_back(n); bv.push_back(volume);
+				if (planar2) { bd.push_back(p1); bs.push_back(in.plane[1]); bn.push_back(n); bv.push_back(volume); }
+			}
+			else gain_into(in, volume, p0, p1);
+		}
+		if (!bd.empty())
+			abi(nodey_gain_tracks(bd.data(), bs.data(), bn.data(), bv.data(), FMT_FLT, (int)bd.size(), cur_stream()), "Volume adjust");
+		for (size_t k = 0; k < items.size(); k++)
+		{
+			const Audio_buffer& in = *ins[k];
+			publish(*items[k].output, "output", new_buffer(arena.block, planes[k].first, planes[k].second, in.format, in.sample_rate, in.channels,
+															   in.frames, in.runs, in.pts_seconds));
 		}
 		return true;
 	}
