@@ -127,3 +127,26 @@ def test_downmix_and_merge_segments(nd, orc):
         if l >= 0: exp[o:o + n, 0] = left[l:l + n]
         if r >= 0: exp[o:o + n, 1] = right[r:r + n]
     assert_bit_equal(out, exp, "merge")
+
+
+def test_gain_tracks_batch_ragged(nd, orc):
+    """nodey_gain_tracks: ragged float streams (one empty, one unaligned) in one launch == the oracle gain per stream"""
+    import ctypes as C
+    import torch
+    lens = [0, 1, 7, 1152, 100003, 4096]
+    vols = [0.5, 2.0, 0.25, 1.0, 0.8, 0.0]
+    xs = [orc.synth_f32(max(n, 1), 1, 48000, 40 + i)[:n, 0].copy() for i, n in enumerate(lens)]
+    srcs = [torch.from_numpy(np.concatenate([np.zeros(1, np.float32), x])).cuda()[1:] if i == 4 else torch.from_numpy(x).cuda() for i, x in enumerate(xs)]
+    dsts = [torch.empty_like(s) for s in srcs]
+    k = len(lens)
+    pd = (C.c_void_p * k)(*[d.data_ptr() if d.numel() else 0 for d in dsts])
+    ps = (C.c_void_p * k)(*[s.data_ptr() if s.numel() else 0 for s in srcs])
+    pn = (C.c_int64 * k)(*lens)
+    pv = (C.c_float * k)(*vols)
+    nd.check(nd.lib().nodey_gain_tracks(pd, ps, pn, pv, 3, k, None))
+    torch.cuda.synchronize()
+    for i in range(k):
+        ref = orc.gain(xs[i].reshape(-1, 1), 3, vols[i]).reshape(-1) if lens[i] else np.zeros(0, np.float32)
+        assert_bit_equal(dsts[i].cpu().numpy(), ref, f"stream {i}")
+    with pytest.raises(nd.NodeyError):
+        nd.check(nd.lib().nodey_gain_tracks(pd, ps, pn, pv, 1, k, None))        # integer formats go through nodey_gain
