@@ -89,3 +89,32 @@ def test_missing_and_malformed_files_are_runtime_errors(eng_gpu, tmp_path):
         with pytest.raises(eng_gpu.EngineError) as x:
             e.run()
         assert text in x.value.message
+
+
+def test_nodey_render_cli(eng_gpu, orc, tmp_path):
+    """the headless renderer: project file + WAV sources in, float WAV out, one JSON line on stdout"""
+    import json, os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "nodey-audio-editor_b200", "nodey_render")
+    assert os.path.exists(exe), "nodey_render is missing: run __graft_entry__.build()"
+    x = make_input(orc, FMT_S16, 48000, 2, rate=48000, track=7)
+    with wave.open(str(tmp_path / "in.wav"), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000); w.writeframes(x.tobytes())
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [str(tmp_path / "in.wav")]})
+    pm = p.add("pitch_modifier", {"pitch": -2.0})
+    out = p.add("audio_output")
+    p.link(src, "output_0", pm, "input"); p.link(pm, "output", out, "input")
+    (tmp_path / "project.json").write_text(json.dumps(p.json()))
+    r = subprocess.run([exe, str(tmp_path / "project.json"), str(tmp_path / "out.wav")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["nodes"] == 3 and info["links"] == 2 and info["gpu_launches"] > 0
+    y, rate = _read_float_wav(str(tmp_path / "out.wav"))
+    ref, _, _ = orc.soundtouch(orc.extract_interleaved(x, FMT_S16), 48000, 1.0, orc.pitch_node_factor(-2.0), 1152)
+    assert rate == 48000 and abs(info["audio_seconds"] - ref.shape[0] / 48000.0) < 1e-9
+    assert_bit_equal(y, ref, "nodey_render output")
+    # a project that cannot be read is an error exit with a message, not a crash
+    (tmp_path / "broken.json").write_text("{ not json")
+    r = subprocess.run([exe, str(tmp_path / "broken.json")], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0 and "Invalid File" in r.stderr
