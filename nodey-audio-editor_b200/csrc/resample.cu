@@ -65,25 +65,32 @@ static double bessel_i0(double x)
     return v;
 }
 
-// Kaiser-windowed sinc, every phase normalised to unit DC gain (libswresample build_filter()).
+// Kaiser-windowed sinc as libswresample's build_filter() stores it for FLTP (libswresample/resample.c).
+// The tap sum is taken for phase 0 only and divides every phase (so only phase 0 has exactly unit DC gain),
+// and with factor == 1 (upsampling) sin(x) comes from a per-phase value with alternating sign.  Both were
+// found by comparing impulse responses with the real library (tests/test_swr_real.py: bit identical).
 static void build_filter(float* bank, double factor, int tap_count, int alloc, int phase_count, double beta)
 {
     const int center = (tap_count - 1) / 2;
     std::vector<double> tab((size_t)tap_count);
     const int ph_nb = (phase_count % 2) ? phase_count : phase_count / 2 + 1;
+    double norm = 0;
     if (factor > 1.0) factor = 1.0;
     for (int ph = 0; ph < ph_nb; ph++) {
-        double norm = 0;
+        double s = (factor == 1.0) ? sin(M_PI * ph / phase_count) * ((center & 1) ? 1 : -1) : 0;
         for (int i = 0; i < tap_count; i++) {
             const double x = M_PI * ((double)(i - center) - (double)ph / phase_count) * factor;
-            double y = (x == 0) ? 1.0 : sin(x) / x;
+            double y;
+            if (x == 0) y = 1.0;
+            else if (factor == 1.0) { y = s / x; s = -s; }
+            else y = sin(x) / x;
             const double w = 2.0 * x / (factor * tap_count * M_PI);
             const double a = 1 - w * w;
             y *= bessel_i0(beta * sqrt(a > 0 ? a : 0));
             tab[(size_t)i] = y;
-            norm += y;
+            if (!ph) norm += y;
         }
-        for (int i = 0; i < tap_count; i++) bank[ph * alloc + i] = (float)(tab[(size_t)i] / norm);
+        for (int i = 0; i < tap_count; i++) bank[ph * alloc + i] = (float)(tab[(size_t)i] * 1.0 / norm);
         if (phase_count % 2) continue;
         for (int i = 0; i < tap_count; i++)
             bank[(phase_count - ph) * alloc + tap_count - 1 - i] = bank[ph * alloc + i];

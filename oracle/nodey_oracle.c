@@ -1,7 +1,14 @@
 /*
  * nodey_oracle.c -- CPU restatement of the reference processors (see nodey_oracle.h header).
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED (no reference fixtures exist, third-party DSP
- * libraries are restated from upstream knowledge).  Citations are relative to /root/reference.
+ * TEST INFRASTRUCTURE ONLY.  Pinning status (the reference ships no tests or fixtures):
+ *   - libswresample model: PINNED against a real libswresample (6.1.100, FFmpeg 8.0.1, found in this image;
+ *     oracle/real_swr.py, tests/golden/swr_real.npz, tests/test_swr_real.py): filter bank / positions / edges
+ *     bit exact through impulse responses, per-call sample counts exact, values within 1e-6, the audio_amix
+ *     loop and the preview conversion end to end;
+ *   - SoundTouch model (TDStretch, AAFilter, InterpolateCubic): PARITY UNPINNED -- no SoundTouch binary or
+ *     source exists in the image; restated from upstream knowledge, behavioural pins only;
+ *   - in-tree arithmetic (gain, mixers, extraction, alignment): restated literally from src/processor/.
+ * Citations are relative to /root/reference.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (oracle/Makefile).  -ffp-contract=off matters:
  * the reference builds at -O3 without -march=native / -ffast-math, so no multiply-add is ever
@@ -19,7 +26,7 @@
 #define M_PI 3.14159265358979323846
 #endif
 
-const char* orc_version(void) { return "nodey-oracle r1 (parity unpinned)"; }
+const char* orc_version(void) { return "nodey-oracle r1 (libswresample pinned to the real library; SoundTouch parity unpinned)"; }
 
 /* ======================================================================================= */
 /* synthetic source                                                                         */
@@ -219,25 +226,35 @@ static double bessel_i0(double x)
     return v;
 }
 
-/* build_filter(): windowed sinc, Kaiser, each phase normalised to unit DC gain, stored float. */
+/* build_filter() (libswresample/resample.c): windowed sinc, Kaiser window, stored as float.
+ * Two details of the real routine, both pinned against the real library's impulse responses
+ * (tests/test_swr_real.py):
+ *   - `norm` is accumulated for phase 0 ONLY (`if (!ph) norm += y;`) and every phase is divided by it,
+ *     so only phase 0 has exactly unit DC gain;
+ *   - when factor == 1 (upsampling) sin(x) is taken from a per-phase table with alternating sign:
+ *     sin(pi*(i - center) - pi*ph/P) = +-sin(pi*ph/P). */
 static void swr_build_filter(float* bank, double factor, int tap_count, int alloc, int phase_count, double beta)
 {
     const int center = (tap_count - 1) / 2;
     double* tab = (double*)malloc(sizeof(double) * (size_t)tap_count);
     const int ph_nb = (phase_count % 2) ? phase_count : phase_count / 2 + 1;
+    double norm = 0;
     if (factor > 1.0) factor = 1.0;
     for (int ph = 0; ph < ph_nb; ph++) {
-        double norm = 0;
+        double s = (factor == 1.0) ? sin(M_PI * ph / phase_count) * ((center & 1) ? 1 : -1) : 0;
         for (int i = 0; i < tap_count; i++) {
             const double x = M_PI * ((double)(i - center) - (double)ph / phase_count) * factor;
-            double y = (x == 0) ? 1.0 : sin(x) / x;
+            double y;
+            if (x == 0) y = 1.0;
+            else if (factor == 1.0) { y = s / x; s = -s; }
+            else y = sin(x) / x;
             const double w = 2.0 * x / (factor * tap_count * M_PI);
             const double a = 1 - w * w;
             y *= bessel_i0(beta * sqrt(a > 0 ? a : 0));
             tab[i] = y;
-            norm += y;
+            if (!ph) norm += y;
         }
-        for (int i = 0; i < tap_count; i++) bank[ph * alloc + i] = (float)(tab[i] / norm);
+        for (int i = 0; i < tap_count; i++) bank[ph * alloc + i] = (float)(tab[i] * 1.0 / norm);
         if (phase_count % 2) continue;
         for (int i = 0; i < tap_count; i++)
             bank[(phase_count - ph) * alloc + tap_count - 1 - i] = bank[ph * alloc + i];

@@ -6,13 +6,19 @@
  * and only as the checker or the timed CPU baseline.  The product path is the CUDA library
  * (include/nodey_cuda.h, include/nodey_engine.h) and fails loudly without it.
  *
- * PARITY UNPINNED: the reference (Stehsaer/nodey-audio-editor) ships no tests, golden vectors
+ * PINNING STATUS.  The reference (Stehsaer/nodey-audio-editor) ships no tests, golden vectors
  * or fixtures, cannot be built in this image (needs FFmpeg 7.1, SoundTouch 2.3.2, Boost.Fiber,
  * jsoncpp, SDL2, ImGui, LAME, <print>), and the heavy arithmetic lives in un-vendored
  * libraries:  libswresample (FFmpeg 7.1, xmake.lua:12) and SoundTouch 2.3.2 (xmake.lua:16).
- * Their published algorithms are restated here from upstream knowledge and anchored on the
- * reference's own call sites (cited per function).  In-tree arithmetic (gain, mixers, sample
- * extraction) is restated literally from /root/reference/src/processor/.
+ *   - libswresample: restated here and PINNED against the real library -- a stock libswresample
+ *     6.1.100 (FFmpeg 8.0.1) ships inside this image's opencv wheel; oracle/real_swr.py drives it the
+ *     way the reference's call sites do, tests/golden/swr_real.npz holds its outputs and
+ *     tests/test_swr_real.py compares (filter bank bit exact, per-call counts exact, values 1e-6).
+ *   - SoundTouch: PARITY UNPINNED.  No binary or source of it exists here; its published algorithm is
+ *     restated from upstream knowledge and anchored on the reference's call sites and on behavioural
+ *     pins (tests/test_oracle.py).
+ *   - In-tree arithmetic (gain, mixers, sample extraction) is restated literally from
+ *     /root/reference/src/processor/ (cited per function).
  *
  * Sample formats use FFmpeg's AVSampleFormat numbering so the values in reference frames map 1:1.
  */

@@ -143,3 +143,51 @@ def test_resample_tracks_rejects_plans_without_pipelined_kernel(nd, orc):
     with pytest.raises(nd.NodeyError) as e:
         r.resample_tracks([x], FMT_FLT, [1.0])
     assert e.value.code == -5
+
+
+# ---- against the REAL libswresample (tests/golden/swr_real.npz, see tests/test_swr_real.py) -----------------
+def _swr_gold():
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_swr_golden as G
+    return G, np.load(os.path.join(here, "golden", "swr_real.npz"))
+
+
+def test_cuda_impulse_response_is_the_real_filter_bank(nd):
+    """a unit impulse through the CUDA resampler returns libswresample's own coefficients, bit for bit"""
+    G, gold = _swr_gold()
+    for rate in G.IMPULSE_RATES:
+        x = np.zeros((4000, 2), np.float32)
+        x[2000, 0] = 1.0
+        r = nd.Resampler(rate, 48000)
+        got = r.run(to_dev(x), FMT_FLT, flush=True).cpu().numpy()
+        r.close()
+        assert got.shape[1] == int(gold[f"impulse_{rate}_len"]), rate
+        first, taps = int(gold[f"impulse_{rate}_first"]), gold[f"impulse_{rate}_taps"]
+        nz = np.flatnonzero(got[0])
+        assert nz[0] == first and nz[-1] == first + len(taps) - 1, rate
+        assert_bit_equal(got[0][first:first + len(taps)], taps, f"impulse response {rate}")
+        assert not got[1].any()
+
+
+def test_cuda_values_match_real_library(nd, orc):
+    """same inputs as the fixture: stream length exact, samples within 1e-6 absolute of the library's C template
+    (the task's bar is 1e-5; the residual is summation order), equal-rate conversions bit exact"""
+    G, gold = _swr_gold()
+    for i, (tag, rate, fmt, ch, n, frame) in enumerate(G.VALUE_CASES):
+        x = G.case_input(orc, rate, fmt, ch, n, 20 + i)
+        gl, gr = gold[f"{tag}_l"], gold[f"{tag}_r"]
+        r = nd.Resampler(rate, 48000)
+        assert r.out_count(n, True) == len(gl), tag
+        if len(gl) == 0:
+            r.close()
+            continue
+        got = r.run(to_dev(x), fmt, flush=True).cpu().numpy()
+        r.close()
+        assert got.shape == (2, len(gl)), tag
+        if rate == 48000:
+            assert_bit_equal(got[0], gl, tag); assert_bit_equal(got[1], gr, tag)
+        else:
+            assert np.abs(got[0] - gl).max() <= 1e-6 and np.abs(got[1] - gr).max() <= 1e-6, tag

@@ -48,7 +48,10 @@ def test_swr_plan_441_to_48(orc):
     p = orc.Swr(44100, 48000, FMT_FLT, 2).plan()
     assert (p["phase_count"], p["filter_length"], p["dst_incr_div"], p["dst_incr_mod"], p["index0"]) == (160, 32, 147, 0, 0)
     bank = orc.Swr(44100, 48000, FMT_FLT, 2).filter_bank()
-    assert np.allclose(bank[:160].sum(axis=1), 1.0, atol=1e-6)          # every phase has unit DC gain
+    # libswresample divides every phase by the tap sum of phase 0 (tests/test_swr_real.py pins the bank bit for
+    # bit against the real library): phase 0 has unit DC gain, the others are within 2e-5 of it
+    assert abs(float(bank[0].sum(dtype=np.float64)) - 1.0) < 1e-7
+    assert np.allclose(bank[:160].sum(axis=1, dtype=np.float64), 1.0, atol=2e-5)
     assert np.array_equal(bank[160 - 37, :32], bank[37, :32][::-1])     # mirrored phases
 
 
@@ -60,7 +63,8 @@ def test_swr_zero_latency_sine_and_dc(orc):
     assert len(l) == 48000
     ideal = 0.5 * np.sin(2 * np.pi * 1000 * np.arange(len(l)) / 48000)
     assert np.abs(ideal[100:-100] - l[100:-100]).max() < 2e-5
-    assert np.abs(r[100:-100] - 0.25).max() < 1e-6
+    # DC passes with the phase-dependent gain ripple of the real filter bank (phases are divided by phase 0's tap sum)
+    assert np.abs(r[100:-100] - 0.25).max() < 5e-6
 
 
 @pytest.mark.parametrize("rates", [(44100, 48000), (48000, 44100), (22050, 48000), (44099, 48000)])

@@ -1,0 +1,165 @@
+"""The oracle's libswresample model against a REAL libswresample.
+
+`tests/golden/swr_real.npz` holds outputs of the stock libswresample 6.1.100 (FFmpeg 8.0.1) found in this
+image (made by tests/golden/make_swr_golden.py through oracle/real_swr.py, configured like the reference's call
+sites audio-amix.cpp:212-240).  Pinned here:
+
+  * the filter bank, the phase positions and the edge handling, BIT EXACT: the response to a unit impulse is a
+    sequence of single filter coefficients, whatever order the library sums in;
+  * how many samples every swr_convert call returns (frame by frame, flush calls included), exact;
+  * the format conversion / rematrix front end at equal rates, bit exact;
+  * resampled values within 1e-6 absolute (signals of 0.4-0.57 peak; the bar of the task is 1e-5): the library
+    itself has several summation orders (C template with two partial sums, SSE / AVX / FMA3 assembly with 4 / 8
+    lanes), the oracle and the CUDA kernel fix one (single accumulator, ascending taps, fused multiply-add);
+  * the whole audio_amix loop (nb = min frame size, zero padding, flush iterations, sequential mix) and the
+    preview path's per-frame conversion to packed float.
+
+The live tests repeat the comparison against the library itself (C template and the assembly this CPU selects)
+where the image has it, and skip elsewhere."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_swr_golden as G  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "swr_real.npz"))
+VALUE_TOL = 1e-6
+
+
+def oracle_frames(orc, x, fmt, rate, ch, frame):
+    """feed the oracle's streaming swr like real_swr.whole: per-frame converts, then flush until 0"""
+    s = orc.Swr(rate, 48000, fmt, ch)
+    L, R, counts = [], [], []
+    for fr in G.frames_of(x, fmt, frame):
+        m = fr.shape[1] if fmt >= 5 else fr.shape[0]
+        l, r = s.convert(fr, int(m * 48000 / rate) + 4096)
+        L.append(l.copy()); R.append(r.copy()); counts.append(len(l))
+    while True:
+        l, r = s.convert(None, 1 << 16)
+        counts.append(len(l))
+        if len(l) == 0:
+            break
+        L.append(l.copy()); R.append(r.copy())
+    cat = lambda a: np.concatenate(a) if a else np.zeros(0, np.float32)
+    return cat(L), cat(R), counts
+
+
+@pytest.mark.parametrize("rate", G.IMPULSE_RATES)
+def test_impulse_response_is_the_real_filter_bank(orc, rate):
+    x = np.zeros((4000, 2), np.float32)
+    x[2000, 0] = 1.0
+    l, r = orc.swr_whole(x, orc.FMT_FLT, rate, 48000)
+    assert len(l) == int(GOLD[f"impulse_{rate}_len"])
+    nz = np.flatnonzero(l)
+    first = int(GOLD[f"impulse_{rate}_first"])
+    taps = GOLD[f"impulse_{rate}_taps"]
+    assert nz[0] == first and nz[-1] == first + len(taps) - 1
+    assert np.array_equal(l[first:first + len(taps)].view(np.uint32), taps.view(np.uint32)), \
+        "filter coefficients differ from libswresample's"
+    assert not r.any()
+
+
+@pytest.mark.parametrize("case", G.VALUE_CASES, ids=[c[0] for c in G.VALUE_CASES])
+def test_values_and_counts_match_real_library(orc, case):
+    tag, rate, fmt, ch, n, frame = case
+    x = G.case_input(orc, rate, fmt, ch, n, 20 + G.VALUE_CASES.index(case))
+    l, r, counts = oracle_frames(orc, x, fmt, rate, ch, frame)
+    assert counts == GOLD[f"{tag}_counts"].tolist(), "samples returned per swr_convert call"
+    gl, gr = GOLD[f"{tag}_l"], GOLD[f"{tag}_r"]
+    assert l.shape == gl.shape and r.shape == gr.shape
+    if rate == 48000:
+        assert np.array_equal(l.view(np.uint32), gl.view(np.uint32)) and np.array_equal(r.view(np.uint32), gr.view(np.uint32))
+    elif len(gl):
+        assert np.abs(l - gl).max() <= VALUE_TOL and np.abs(r - gr).max() <= VALUE_TOL
+        # and the whole-buffer entry point the CUDA path is compared with gives the same samples
+        wl, wr = orc.swr_whole(x, fmt, rate, 48000)
+        assert np.array_equal(wl, l) and np.array_equal(wr, r)
+
+
+@pytest.mark.parametrize("tag", sorted(G.AMIX_CASES))
+def test_amix_loop_matches_real_library(orc, tag):
+    spec, vols = G.AMIX_CASES[tag]
+    tracks = [orc.make_track(G.case_input(orc, r, f, c, n, 40 + i), f, r, frame_size=fr)
+              for i, (r, f, c, n, fr) in enumerate(spec)]
+    l, r = orc.amix(tracks, vols)
+    gl, gr = GOLD[f"{tag}_l"], GOLD[f"{tag}_r"]
+    assert len(l) == len(gl) == int(GOLD[f"{tag}_nb"].sum()), "stream length (zero padding and flush iterations included)"
+    assert np.abs(l - gl).max() <= VALUE_TOL and np.abs(r - gr).max() <= VALUE_TOL
+    assert np.array_equal(l == 0, gl == 0), "zero padding in the same places"
+
+
+@pytest.mark.parametrize("case", G.PREVIEW_CASES, ids=[c[0] for c in G.PREVIEW_CASES])
+def test_preview_conversion_matches_real_library(orc, case):
+    tag, rate, fmt, ch, n, frame = case
+    x = G.case_input(orc, rate, fmt, ch, n, 60 + G.PREVIEW_CASES.index(case))
+    s = orc.Swr(rate, 48000, fmt, ch)
+    outs, counts = [], []
+    for fr in G.frames_of(x, fmt, frame):
+        m = fr.shape[1] if fmt >= 5 else fr.shape[0]
+        cap = int(np.float32(np.float32(m) / np.float32(rate)) * 48000 * 1.5)
+        l, r = s.convert(fr, cap)
+        outs.append(np.stack([l, r], 1)); counts.append(len(l))
+    got = np.concatenate(outs)
+    assert counts == GOLD[f"{tag}_counts"].tolist()
+    ref = GOLD[f"{tag}_out"]
+    assert got.shape == ref.shape
+    if rate == 48000:
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    else:
+        assert np.abs(got - ref).max() <= VALUE_TOL
+
+
+# ---- live: the library itself, where the image has it -------------------------------------------------
+def _real():
+    from oracle import real_swr as R
+    if not R.available():
+        pytest.skip("no libswresample in this image")
+    return R
+
+
+def test_fixture_is_what_the_library_produces_now():
+    R = _real()
+    now = G.generate()
+    for k in GOLD.files:
+        if k == "meta":
+            continue
+        a, b = np.asarray(now[k]), GOLD[k]
+        assert a.shape == b.shape and np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("c_template", [True, False], ids=["c_template", "cpu_assembly"])
+def test_live_library_both_code_paths(orc, c_template):
+    """the assembly the host CPU selects (SSE / AVX / FMA3) sums in another order than the C template: both stay
+    within the same bound of the oracle, with identical counts.  One divergence is the library's own: on the
+    linearly interpolating path (47999 Hz: no exact rational within 1024 phases) the x86 assembly and the C template
+    disagree by up to 8e-6 on the first ~26 output samples and nowhere else; the oracle follows the C template
+    (1.2e-7), so against the assembly that case is held to the task's 1e-5 bar."""
+    R = _real()
+    R.force_c_path(c_template)
+    try:
+        for i, (rate, fmt, ch) in enumerate([(44100, 3, 2), (22050, 1, 1), (96000, 3, 2), (8000, 2, 2), (47999, 8, 2)]):
+            x = G.case_input(orc, rate, fmt, ch, 20000, 70 + i)
+            l, r, counts = R.whole(x, fmt, rate, 48000, ch, frame=1152)
+            ol, orr, ocounts = oracle_frames(orc, x, fmt, rate, ch, 1152)
+            assert counts == ocounts
+            tol = 1e-5 if (rate == 47999 and not c_template) else VALUE_TOL
+            assert np.abs(l - ol).max() <= tol and np.abs(r - orr).max() <= tol
+            if tol != VALUE_TOL:
+                assert np.abs(l - ol)[64:].max() <= VALUE_TOL and np.abs(r - orr)[64:].max() <= VALUE_TOL
+    finally:
+        R.force_c_path(False)
+
+
+def test_live_library_defaults_are_the_modelled_ones():
+    R = _real()
+    s = R.RealSwr(44100, 48000, 3, 2)
+    try:
+        assert (s.option("filter_size"), s.option("phase_shift"), s.option("linear_interp"), s.option("exact_rational"),
+                s.option("kaiser_beta")) == (32, 10, 1, 1, 9)
+        assert s.option("cutoff", "double") == 0.0      # 0 = "pick": swr_init uses 0.97 for the swr engine
+    finally:
+        s.close()
