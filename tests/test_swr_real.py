@@ -92,6 +92,20 @@ def test_amix_loop_matches_real_library(orc, tag):
     assert np.array_equal(l == 0, gl == 0), "zero padding in the same places"
 
 
+@pytest.mark.parametrize("tag", sorted(G.BIMIX_CASES))
+def test_bimix_loop_matches_real_library(orc, tag):
+    """orc_bimix against an independent restatement of audio-bimix.cpp:136-320 run on real SwrContexts"""
+    left, right, bias = G.BIMIX_CASES[tag]
+    tl = orc.make_track(G.case_input(orc, *left[:4], 50), left[1], left[0], frame_size=left[4])
+    tr = orc.make_track(G.case_input(orc, *right[:4], 51), right[1], right[0], frame_size=right[4])
+    l, r = orc.bimix(tl, tr, bias)
+    gl, gr = GOLD[f"{tag}_l"], GOLD[f"{tag}_r"]
+    assert len(l) == len(gl) == int(GOLD[f"{tag}_nb"].sum()), "stream length"
+    exact = left[0] == 48000 and right[0] == 48000
+    tol = 0.0 if exact else VALUE_TOL
+    assert np.abs(l - gl).max() <= tol and np.abs(r - gr).max() <= tol
+
+
 @pytest.mark.parametrize("case", G.PREVIEW_CASES, ids=[c[0] for c in G.PREVIEW_CASES])
 def test_preview_conversion_matches_real_library(orc, case):
     tag, rate, fmt, ch, n, frame = case
