@@ -92,6 +92,17 @@ def test_amix_loop_matches_real_library(orc, tag):
     assert np.array_equal(l == 0, gl == 0), "zero padding in the same places"
 
 
+@pytest.mark.parametrize("case", G.CAP_CASES, ids=[c[0] for c in G.CAP_CASES])
+def test_limited_output_capacity_matches_real_library(orc, case):
+    """swr_convert with less room than the input yields: what every call returns, how long the flush calls keep
+    returning samples, and the samples themselves"""
+    tag, rate, fmt, ch, n, frame, cap = case
+    x = G.case_input(orc, rate, fmt, ch, n, 80 + G.CAP_CASES.index(case))
+    l, r, counts = G.capped(lambda: orc.Swr(rate, 48000, fmt, ch), x, fmt, frame, cap)
+    assert counts.tolist() == GOLD[f"{tag}_counts"].tolist()
+    assert np.abs(l - GOLD[f"{tag}_l"]).max() <= VALUE_TOL and np.abs(r - GOLD[f"{tag}_r"]).max() <= VALUE_TOL
+
+
 @pytest.mark.parametrize("tag", sorted(G.BIMIX_CASES))
 def test_bimix_loop_matches_real_library(orc, tag):
     """orc_bimix against an independent restatement of audio-bimix.cpp:136-320 run on real SwrContexts"""
