@@ -35,7 +35,11 @@ _libs = None
 
 
 def find():
-    """(libavutil path, libswresample path) or None."""
+    """(libavutil path, libswresample path) or None.  NODEY_REAL_AVUTIL / NODEY_REAL_SWRESAMPLE point the checks at
+    another build (e.g. the FFmpeg 7.1 libraries the reference links: libavutil.so.59 / libswresample.so.5)."""
+    eu, es = os.environ.get("NODEY_REAL_AVUTIL"), os.environ.get("NODEY_REAL_SWRESAMPLE")
+    if eu and es and os.path.exists(eu) and os.path.exists(es):
+        return eu, es
     roots = list(site.getsitepackages()) + [p for p in sys.path if p.endswith("site-packages")]
     for r in dict.fromkeys(roots):
         d = os.path.join(r, "opencv_python_headless.libs")

@@ -302,3 +302,60 @@ def test_device_resident_render_of_128_tracks_takes_two_waves_and_matches(eng_gp
         assert_bit_equal(e.output().numpy(), two, "single-wave schedule")
     finally:
         del os.environ["NODEY_WAVE"]
+
+
+# ---- the plugin-API nodes against the REAL libswresample (tests/golden/swr_real.npz) -------------------------
+def _swr_gold():
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_swr_golden as G
+    return G, np.load(os.path.join(here, "golden", "swr_real.npz"))
+
+
+@pytest.mark.parametrize("tag", ["amix1_44100", "amix2_mixed", "amix3_rates"])
+def test_amix_node_against_real_libswresample(eng_gpu, orc, tag):
+    """project JSON -> Graph -> Runner -> Audio_amix on the GPU, compared with the reference's audio_amix loop run
+    on real SwrContexts (fixture made by tests/golden/make_swr_golden.py): stream length and zero padding exact,
+    samples within 1e-6 absolute (summation order of the FIR; the bar is 1e-5)"""
+    G, gold = _swr_gold()
+    spec, vols = G.AMIX_CASES[tag]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""] * len(spec)})
+    mix = p.add("audio_amix", eng_gpu.amix_info(list(vols)))
+    out = p.add("audio_output")
+    for i in range(len(spec)):
+        p.link(src, f"output_{i}", mix, f"input_{i + 1}")
+    p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    for i, (r, f, c, n, fr) in enumerate(spec):
+        e.bind_source(i, G.case_input(orc, r, f, c, n, 40 + i), f, r, frame_size=fr)
+    e.run()
+    got = e.output().numpy()
+    gl, gr = gold[f"{tag}_l"], gold[f"{tag}_r"]
+    assert got.shape == (2, len(gl)), "stream length (padding and flush iterations included)"
+    assert np.abs(got[0] - gl).max() <= 1e-6 and np.abs(got[1] - gr).max() <= 1e-6
+    assert np.array_equal(got[0] == 0, gl == 0)
+    e.close()
+
+
+@pytest.mark.parametrize("tag", ["bimix_mixed", "bimix_same_rate", "bimix_48k"])
+def test_bimix_node_against_real_libswresample(eng_gpu, orc, tag):
+    G, gold = _swr_gold()
+    left, right, bias = G.BIMIX_CASES[tag]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    bm = p.add("audio_bimix", {"bias": bias})
+    out = p.add("audio_output")
+    p.link(src, "output_0", bm, "input_l"); p.link(src, "output_1", bm, "input_r"); p.link(bm, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.bind_source(0, G.case_input(orc, *left[:4], 50), left[1], left[0], frame_size=left[4])
+    e.bind_source(1, G.case_input(orc, *right[:4], 51), right[1], right[0], frame_size=right[4])
+    e.run()
+    got = e.output().numpy()
+    gl, gr = gold[f"{tag}_l"], gold[f"{tag}_r"]
+    assert got.shape == (2, len(gl))
+    tol = 0.0 if (left[0] == 48000 and right[0] == 48000) else 1e-6
+    assert np.abs(got[0] - gl).max() <= tol and np.abs(got[1] - gr).max() <= tol
+    e.close()
