@@ -49,7 +49,7 @@ def workload_config(args, n_gpus):
                         "(audio_amix(1) resample -> pitch_modifier +3 -> velocity_modifier 1.25 keep_pitch -> "
                         "audio_volume_adjust -> audio_amix 16x tree -> master bus -> audio_spectrum 4096/1024)",
             "tracks": args.tracks, "track_seconds": args.seconds, "sharding": f"tracks/{n_gpus} per GPU, contiguous groups of 16",
-            "collective": "ncclReduce(sum) of the partial master bus" if n_gpus > 1 else "none",
+            "collective": "nodey_bus_reduce: ncclReduce(sum) of the partial master bus (C ABI, own communicator)" if n_gpus > 1 else "none",
             "audio_seconds_per_step": args.tracks * args.seconds,
             "l2": "inputs larger than L2 (>= 2 GB per GPU per step), no flush needed"}
 
@@ -197,6 +197,13 @@ def run_ours(args):
     L = nodey.lib()        # fails loudly when the CUDA library is missing: there is no fallback path
     engine.lib()
     nodey.check(L.nodey_set_device(local))
+    bus = None
+    if world > 1:
+        # torch.distributed is the plumbing (rendezvous, barriers, max over ranks); the bus reduce itself runs on the
+        # library's own communicator, set up from an id that rank 0 makes and the process group hands round
+        box = [nodey.bus_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        bus = nodey.Bus(box[0], rank, world)
 
     n_in = IN_RATE * args.seconds
     first, t_local = pipeline.shard_tracks(args.tracks, world, rank)
@@ -220,9 +227,9 @@ def run_ours(args):
         if world > 1:
             if bus_t[0] is None:
                 bus_t[0] = torch.empty((2, out.frames), dtype=torch.float32, device=dev)
-            nodey.check(L.nodey_memcpy_d2d(nodey._dp(bus_t[0][0]), C.c_void_p(out.p0), out.frames * 4, None))
-            nodey.check(L.nodey_memcpy_d2d(nodey._dp(bus_t[0][1]), C.c_void_p(out.p1), out.frames * 4, None))
-            dist.reduce(bus_t[0], dst=0, op=dist.ReduceOp.SUM)
+            # the only collective of the path: sum of the partial master buses straight out of the engine's planes,
+            # through the C ABI (nodey_bus_reduce: ncclReduce of both planes in one group, no staging copy)
+            bus.reduce_ptrs(out.p0, out.p1, bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr(), out.frames, root=0)
             spec_ptr, spec_elems = None, 0
             if rank == 0:
                 if len(bus_t) < 2:     # the spectrum buffer is allocated once: a fresh 221 MB cudaMalloc per step stalled rank 0 for up to 50 ms
@@ -399,6 +406,8 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     eng.close()
     if world > 1:
+        torch.cuda.synchronize()
+        bus.close()
         dist.destroy_process_group()
 
 

@@ -37,7 +37,8 @@ enum {
     NODEY_E_FORMAT = -2,       /* unsupported sample format (reference: Runtime_error "format is not support") */
     NODEY_E_CUDA = -3,         /* CUDA runtime error, text in nodey_last_error() */
     NODEY_E_NOMEM = -4,
-    NODEY_E_RANGE = -5         /* parameter outside the range the reference accepts */
+    NODEY_E_RANGE = -5,        /* parameter outside the range the reference accepts */
+    NODEY_E_COMM = -6          /* NCCL missing or an NCCL call failed (nodey_bus_*), text in nodey_last_error() */
 };
 
 #define NODEY_MAX_MIX_INPUTS 16   /* audio-amix.cpp:342 clamps input_num to 1..16 */
@@ -259,6 +260,34 @@ int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_str
 int64_t nodey_stft_frames(int64_t nframes, int nfft, int hop);
 int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int interleaved,
                int64_t plane_stride, int nfft, int hop, nodey_stream_t stream);
+
+/* Master-bus reduce across the GPUs of one box.  The reference is a single-process CPU program
+ * and has no counterpart; what is replaced is the LAST sum of the graph: the master audio_amix adds its inputs in
+ * order (audio-amix.cpp:293-307), and when the tracks are sharded over ranks (one process per GPU) every rank holds
+ * a partial FLTP bus that still has to be added.  This is the only exchange step of the render, hence the only
+ * collective: ncclReduce / ncclAllReduce(sum, float32) over NVLink, both planes in one NCCL group, asynchronous on
+ * `stream`.  The sum across ranks is not the sequential input order of the CPU mixer, so the reduced bus is compared
+ * within 1e-5, not bit for bit (deterministic for a fixed rank count).
+ * NCCL is bound at run time (dlopen of libnccl.so.2, NODEY_NCCL_LIB overrides): single-GPU users never load it, and
+ * a process that already carries an NCCL shares it.  NODEY_E_COMM when it is missing -- there is no fallback.
+ * Set-up: rank 0 calls nodey_bus_unique_id and hands the NODEY_BUS_ID_BYTES bytes to every rank (launcher, file,
+ * socket: out of band); every rank then calls nodey_bus_create on ITS device (nodey_set_device first); the call
+ * returns when all ranks have joined. */
+#define NODEY_BUS_ID_BYTES 128
+typedef struct nodey_bus nodey_bus;
+int nodey_bus_nccl_version(int* version);
+int nodey_bus_unique_id(void* id);
+int nodey_bus_create(nodey_bus** out, const void* id, int rank, int nranks);
+void nodey_bus_destroy(nodey_bus* bus);
+int nodey_bus_info(const nodey_bus* bus, int* rank, int* nranks, int* device);
+/* recv = sum over ranks of send, on `root` only (recv may be NULL elsewhere; send == recv is allowed on the root).
+ * send_r / recv_r = second plane of the FLTP bus, NULL for a mono bus.  nframes must agree on every rank. */
+int nodey_bus_reduce(nodey_bus* bus, const float* send_l, const float* send_r, float* recv_l, float* recv_r,
+                     int64_t nframes, int root, nodey_stream_t stream);
+/* the same with the sum delivered to every rank (when each rank goes on with a time slice of the bus, e.g. its share
+ * of the spectrum frames) */
+int nodey_bus_allreduce(nodey_bus* bus, const float* send_l, const float* send_r, float* recv_l, float* recv_r,
+                        int64_t nframes, nodey_stream_t stream);
 
 #ifdef __cplusplus
 }

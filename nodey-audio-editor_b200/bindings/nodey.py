@@ -29,6 +29,8 @@ SYMBOLS = [
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
     "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory",
+    "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",
+    "nodey_bus_reduce", "nodey_bus_allreduce",
     "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
 ]
 
@@ -101,6 +103,14 @@ def lib():
     L.nodey_profile_enable.restype = None
     L.nodey_profile_launches.restype = C.c_uint64
     L.nodey_profile_report.argtypes = [C.c_char_p, i32]
+    L.nodey_bus_nccl_version.argtypes = [C.POINTER(i32)]
+    L.nodey_bus_unique_id.argtypes = [vp]
+    L.nodey_bus_create.argtypes = [C.POINTER(vp), vp, i32, i32]
+    L.nodey_bus_destroy.argtypes = [vp]
+    L.nodey_bus_destroy.restype = None
+    L.nodey_bus_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.nodey_bus_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
+    L.nodey_bus_allreduce.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     _lib = L
     return L
 
@@ -483,3 +493,58 @@ class SoundTouch:
             o = offs[:, :max(nseq - 1, 0)]
             return res, (o[0] if single else o)
         return res
+
+
+BUS_ID_BYTES = 128
+
+
+def bus_unique_id():
+    """the 128 bytes rank 0 hands to every rank before Bus(...) (nodey_bus_unique_id)"""
+    buf = C.create_string_buffer(BUS_ID_BYTES)
+    check(lib().nodey_bus_unique_id(buf))
+    return buf.raw
+
+
+class Bus:
+    """Master-bus reduce across the ranks of one box (nodey_bus_*): NCCL sum of the partial FLTP buses.
+    Every rank constructs it with the same id after selecting its device; the call returns when all have joined."""
+
+    def __init__(self, unique_id, rank, nranks):
+        assert len(unique_id) == BUS_ID_BYTES
+        self.h = C.c_void_p()
+        self.rank, self.nranks = rank, nranks
+        check(lib().nodey_bus_create(C.byref(self.h), C.c_char_p(bytes(unique_id)), rank, nranks))
+
+    def close(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.nodey_bus_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def info(self):
+        r, n, d = C.c_int(), C.c_int(), C.c_int()
+        check(lib().nodey_bus_info(self.h, C.byref(r), C.byref(n), C.byref(d)))
+        return {"rank": r.value, "nranks": n.value, "device": d.value}
+
+    def reduce_ptrs(self, send_l, send_r, recv_l, recv_r, nframes, root=0, stream=None):
+        """raw device addresses (ints; 0 / None = absent plane)"""
+        vp = lambda a: C.c_void_p(a) if a else None
+        check(lib().nodey_bus_reduce(self.h, vp(send_l), vp(send_r), vp(recv_l), vp(recv_r), nframes, root,
+                                     stream if stream is not None else _stream()))
+
+    def reduce(self, send, recv, root=0):
+        """send / recv: planar [nch, frames] float32 CUDA tensors (nch 1 or 2); recv is written on the root only"""
+        nch, n = send.shape
+        assert send.stride(1) == 1 and (recv is None or recv.stride(1) == 1)
+        self.reduce_ptrs(send[0].data_ptr(), send[1].data_ptr() if nch == 2 else 0,
+                         recv[0].data_ptr() if recv is not None else 0,
+                         recv[1].data_ptr() if (recv is not None and nch == 2) else 0, n, root)
+        return recv
+
+    def allreduce(self, send, recv):
+        nch, n = send.shape
+        assert send.stride(1) == 1 and recv.stride(1) == 1
+        check(lib().nodey_bus_allreduce(self.h, _dp(send[0]), _dp(send[1]) if nch == 2 else None,
+                                        _dp(recv[0]), _dp(recv[1]) if nch == 2 else None, n, _stream()))
+        return recv
