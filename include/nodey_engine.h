@@ -60,10 +60,22 @@ int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kin
 int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames,
                         double* pts_seconds, void** plane0, void** plane1);
 /* Process_context::export_path of the sink (src/frontend/app.cpp:2067-2073): "" keeps the result in memory only, a
- * path makes the export also write an interleaved 32-bit float WAV (the reference encodes MP3 with LAME, which this
- * image does not have), with do_export's pts rule: (int)(first pts * sample_rate) frames of silence in front
- * (src/processor/audio-io.cpp:833-839). */
+ * path ending in ".wav" makes the export also write an interleaved 32-bit float WAV, with do_export's pts rule:
+ * (int)(first pts * sample_rate) frames of silence in front (src/processor/audio-io.cpp:833-839). */
 int nodey_engine_set_export_path(nodey_engine* e, const char* path);
+/* Any other non-empty path is an MP3 export like the reference's (Audio_output::do_export, audio-io.cpp:640-841): the
+ * stream goes to LAME in its own sample format, frame by frame in the sizes its producer recorded, with the same
+ * parameters (quality 2, CBR at `kbps`, 48 kHz out), the same silence rule and -- like the reference -- without a final
+ * lame_encode_flush.  libmp3lame is bound at run time (libmp3lame.so.0, NODEY_LAME_LIB overrides); when it cannot be
+ * loaded the run fails with NODEY_ENGINE_E_NODE ("MP3 encoder not available").  kbps: 8..320, default 320
+ * (src/frontend/app.cpp:595).  nodey_engine_mp3_available: 1 when the encoder library could be bound. */
+int nodey_engine_set_export_kbps(nodey_engine* e, int kbps);
+int nodey_engine_mp3_available(void);
+/* The same MP3 leg on a HOST stream (packed: plane0; planar stereo: plane0 / plane1), cut into frame_size frames:
+ * for callers that hold the rendered PCM already (e.g. the reduced master bus of a multi-GPU render).
+ * *time_inout = Process_context::time before / after (NULL = start at 0). */
+int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* plane1, int fmt, int sample_rate, int channels,
+                            int64_t frames, int frame_size, double pts_seconds, int kbps, double* time_inout);
 /* Preview instead of export (the reference's Preview state, src/frontend/app.cpp:2001-2040 -> Audio_output::do_preview,
  * src/processor/audio-io.cpp:478-638): the sink brings the stream to 48 kHz stereo float frame by frame without a
  * final flush, clamps to [-1, 1] and queues packed frames.  nodey_engine_preview returns that queue content (device

@@ -49,6 +49,8 @@ def lib():
                                       C.POINTER(vp), C.POINTER(vp)]
     L.nodey_engine_set_export_path.argtypes = [vp, cp]
     L.nodey_engine_set_preview.argtypes = [vp, i32]
+    L.nodey_engine_set_export_kbps.argtypes = [vp, i32]
+    L.nodey_engine_encode_mp3.argtypes = [cp, vp, vp, i32, i32, i32, i64, i32, C.c_double, i32, C.POINTER(C.c_double)]
     L.nodey_engine_preview.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), i32]
     _lib = L
     return L
@@ -92,6 +94,24 @@ class Product:
                 planes.append(fetch(self.p1, (self.frames,), dt))
             return np.stack(planes)
         return fetch(self.p0, (self.frames, self.ch), dt)
+
+
+def mp3_available():
+    return bool(lib().nodey_engine_mp3_available())
+
+
+def encode_mp3(path, data, fmt, rate, frame_size=1152, pts=0.0, kbps=320, time=0.0):
+    """The sink's MP3 leg on a HOST stream (numpy; packed [frames, ch] or planar [ch, frames]): do_export's LAME call
+    sequence.  Returns Process_context::time afterwards."""
+    data = np.ascontiguousarray(data)
+    planar = fmt >= 5
+    ch, frames = data.shape if planar else data.shape[::-1]
+    p0 = data.ctypes.data
+    p1 = data[1].ctypes.data if (planar and ch == 2) else 0
+    t = C.c_double(time)
+    _check(lib().nodey_engine_encode_mp3(path.encode(), C.c_void_p(p0), C.c_void_p(p1) if p1 else None, fmt, rate, ch, frames,
+                                         frame_size, pts, kbps, C.byref(t)))
+    return t.value
 
 
 class Engine:
@@ -155,8 +175,12 @@ class Engine:
         _check(lib().nodey_engine_run(self.h))
 
     def set_export_path(self, path):
-        """the sink also writes the exported stream as a 32-bit float WAV ("" = memory only)"""
+        """empty = memory only; *.wav = 32-bit float WAV; any other path = MP3 through LAME like the reference's export"""
         _check(lib().nodey_engine_set_export_path(self.h, (path or "").encode()))
+
+    def set_export_kbps(self, kbps):
+        """bit rate of an MP3 export (any export path that does not end in .wav), 8..320, default 320"""
+        _check(lib().nodey_engine_set_export_kbps(self.h, int(kbps)))
 
     def set_preview(self, on=True):
         """the next runs take the sink's preview path (swr without flush -> clamp -> packed 48 kHz stereo float)"""

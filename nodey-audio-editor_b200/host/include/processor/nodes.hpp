@@ -81,8 +81,10 @@ namespace processor
 		struct Process_context
 		{
 			bool do_export = true;
-			std::string export_path = "";                    // "" = keep in memory only; *.wav = write a float WAV
-			size_t kbps = 0;
+			// "" = keep in memory only; *.wav = interleaved float WAV; any other path = MP3 through LAME like the
+			// reference (audio-io.cpp:640-841; libmp3lame bound at run time, Runtime_error when it is absent)
+			std::string export_path = "";
+			size_t kbps = 0;                                 // MP3 bit rate (the editor passes 64..320, app.cpp:595-608)
 			std::shared_ptr<std::atomic<double>> time = std::make_shared<std::atomic<double>>(0.0);
 			std::shared_ptr<const Audio_buffer> rendered;    // OUT: what arrived at the sink (device resident)
 			// do_export == false selects the reference's preview path (audio-io.cpp:478-638): the stream is brought to
@@ -100,6 +102,22 @@ namespace processor
 		virtual Json::Value serialize() const { return {}; }
 		virtual void deserialize(const Json::Value&) {}
 	};
+
+	// ---- MP3 leg of the sink (host/src/mp3-export.cpp) ---------------------------------------------------
+	// host image of a rendered stream in its own sample format (what the reference's frames would carry)
+	struct Host_stream
+	{
+		int format = FMT_FLT, sample_rate = 48000, channels = 2;
+		int64_t frames = 0;
+		double pts_seconds = 0.0;
+		Frame_runs runs;
+		const void* plane[2] = {nullptr, nullptr};
+	};
+	// true when libmp3lame could be bound (NODEY_LAME_LIB overrides the library name); why = the loader's message
+	bool mp3_encoder_available(std::string* why = nullptr);
+	// Audio_output::do_export's LAME call sequence over the stream's frames; `time` is Process_context::time going in,
+	// the return value what it is afterwards (end of the last frame).  Throws Processor::Runtime_error like the reference.
+	double export_mp3(const Host_stream& stream, const std::string& path, size_t kbps, double time);
 
 	// ---- gain --------------------------------------------------------------------------------------
 	class Audio_vol : public infra::Processor

@@ -18,6 +18,7 @@ struct nodey_engine
 	std::shared_ptr<std::any> sink_data;
 	bool preview = false;
 	std::string export_path;
+	size_t kbps = 320;        // the editor's default bit rate (src/frontend/app.cpp:595)
 	std::vector<int64_t> preview_chunks;     // chunk sizes the preview sink callback received, in order
 };
 
@@ -164,6 +165,7 @@ int nodey_engine_run(nodey_engine* e)
 			Audio_output::Process_context ctx;
 			ctx.do_export = !e->preview;
 			ctx.export_path = e->export_path;
+			ctx.kbps = e->kbps;
 			e->preview_chunks.clear();
 			if (e->preview)
 				ctx.preview_sink = [e](const float*, int64_t frames) { e->preview_chunks.push_back(frames); return true; };
@@ -267,6 +269,39 @@ int nodey_engine_set_export_path(nodey_engine* e, const char* path)
 	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
 	e->export_path = path ? path : "";
 	return 0;
+}
+
+int nodey_engine_set_export_kbps(nodey_engine* e, int kbps)
+{
+	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
+	if (kbps < 8 || kbps > 320) return fail(NODEY_ENGINE_E_INVALID, "MP3 bit rate must be 8..320 kbps");
+	e->kbps = (size_t)kbps;
+	return 0;
+}
+
+int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* plane1, int fmt, int sample_rate, int channels,
+                            int64_t frames, int frame_size, double pts_seconds, int kbps, double* time_inout)
+{
+	if (!path || !*path || (!plane0 && frames > 0) || frames < 0 || frame_size < 1 || (channels != 1 && channels != 2) || sample_rate < 1)
+		return fail(NODEY_ENGINE_E_INVALID, "nodey_engine_encode_mp3: bad argument");
+	if (format_is_planar(fmt) && channels == 2 && !plane1 && frames > 0)
+		return fail(NODEY_ENGINE_E_INVALID, "nodey_engine_encode_mp3: planar stereo needs both planes");
+	try
+	{
+		Host_stream hs;
+		hs.format = fmt; hs.sample_rate = sample_rate; hs.channels = channels; hs.frames = frames; hs.pts_seconds = pts_seconds;
+		hs.runs = uniform_frame_runs(frames, frame_size);
+		hs.plane[0] = plane0; hs.plane[1] = plane1;
+		const double end = export_mp3(hs, path, (size_t)std::max(0, kbps), time_inout ? *time_inout : 0.0);
+		if (time_inout) *time_inout = end;
+		return 0;
+	}
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_NODE, err.what()); }
+}
+
+int nodey_engine_mp3_available(void)
+{
+	return processor::mp3_encoder_available() ? 1 : 0;
 }
 
 int nodey_engine_set_preview(nodey_engine* e, int preview)

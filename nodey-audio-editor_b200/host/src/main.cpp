@@ -1,12 +1,14 @@
 // nodey_render -- headless offline render of a Nodey project file:
-//   nodey_render project.json [out.wav] [--gpu N]
-// Sources are the WAV files named in the project's audio_input node; the sink writes a float WAV.
+//   nodey_render project.json [out.wav | out.mp3] [--gpu N] [--kbps K]
+// Sources are the WAV files named in the project's audio_input node; the sink writes a float WAV (*.wav) or, like
+// the reference's export, an MP3 through LAME (any other path; libmp3lame is bound at run time).
 #include "infra/graph.hpp"
 #include "infra/runner.hpp"
 #include "processor/nodes.hpp"
 
 #include "nodey_cuda.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -17,14 +19,16 @@ int main(int argc, char** argv)
 {
 	if (argc < 2)
 	{
-		fprintf(stderr, "usage: %s project.json [out.wav] [--gpu N]\n", argv[0]);
+		fprintf(stderr, "usage: %s project.json [out.wav | out.mp3] [--gpu N] [--kbps K]\n", argv[0]);
 		return 2;
 	}
 	std::string out_path;
 	int gpu = 0;
+	size_t kbps = 320;      // the editor's default (src/frontend/app.cpp:595)
 	for (int i = 2; i < argc; i++)
 	{
 		if (!strcmp(argv[i], "--gpu") && i + 1 < argc) gpu = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--kbps") && i + 1 < argc) kbps = (size_t)std::max(8, atoi(argv[++i]));
 		else out_path = argv[i];
 	}
 	try
@@ -47,6 +51,7 @@ int main(int argc, char** argv)
 			processor::Audio_output::Process_context ctx;
 			ctx.do_export = true;
 			ctx.export_path = out_path;
+			ctx.kbps = kbps;
 			sink = std::make_shared<std::any>(ctx);
 			node_data[it->second] = sink;
 		}

@@ -602,9 +602,38 @@ namespace processor
 			return;
 		}
 		abi(nodey_stream_synchronize(cur_stream()), "audio_output");     // the sink is where the host waits for the device
+		const auto ends_with_wav = [](const std::string& path)
+		{
+			if (path.size() < 4) return false;
+			std::string tail = path.substr(path.size() - 4);
+			for (char& c : tail) c = (char)std::tolower((unsigned char)c);
+			return tail == ".wav";
+		};
+		if (!ctx->export_path.empty() && !ends_with_wav(ctx->export_path))
+		{
+			// ---- MP3 like the reference (audio-io.cpp:640-841): the stream goes to LAME in its own sample format, in the
+			// frame sizes its producer recorded; host/src/mp3-export.cpp holds the call sequence ----
+			check_channels(*buffer, "Audio output");
+			Host_stream hs;
+			hs.format = buffer->format; hs.sample_rate = buffer->sample_rate; hs.channels = buffer->channels;
+			hs.frames = buffer->frames; hs.pts_seconds = buffer->pts_seconds; hs.runs = buffer->runs;
+			const bool planar2 = format_is_planar(buffer->format) && buffer->channels == 2;
+			const size_t plane_bytes = buffer->plane_bytes();
+			std::vector<unsigned char> host[2];
+			for (int c = 0; c < (planar2 ? 2 : 1); c++)
+			{
+				host[c].resize(std::max<size_t>(plane_bytes, 1));
+				if (plane_bytes) abi(nodey_memcpy_d2h(host[c].data(), buffer->plane[c], plane_bytes, cur_stream()), "audio_output");
+				hs.plane[c] = host[c].data();
+			}
+			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
+			const double end = export_mp3(hs, ctx->export_path, ctx->kbps, ctx->time ? ctx->time->load() : 0.0);
+			if (ctx->time) ctx->time->store(end);
+			return;
+		}
 		if (!ctx->export_path.empty())
 		{
-			// interleaved float WAV (the reference encodes MP3 with LAME; codec I/O is out of scope here)
+			// interleaved float WAV: the lossless way out for hosts without LAME, and what the parity tests read back
 			check_channels(*buffer, "Audio output");
 			infra::Device_block tmp((size_t)buffer->frames * (size_t)buffer->channels * sizeof(float));
 			abi(nodey_extract_interleaved((float*)tmp.ptr, buffer->plane[0], buffer->plane[1], buffer->format, buffer->frames, buffer->channels, cur_stream()),
