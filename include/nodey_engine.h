@@ -86,6 +86,17 @@ int nodey_engine_preview(nodey_engine* e, int64_t* frames, void** packed, int64_
 /* frame sizes (run-length encoded) of an audio product: fills up to cap pairs, returns the count */
 int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap);
 
+/* Diagnostics of the last run (the reference's overlay, src/frontend/app.cpp:1556-1592, lists node
+ * states and the fill of every link's channel -- links here are published once, so the per-link figure is replaced by
+ * the device time of every (wave, level) step of the Runner).  nodey_engine_diagnostics: the overlay's "Audio" block as
+ * text ("N Running | N Finished | N Errors", then one line per step); returns the length needed.
+ * nodey_engine_level_timings: the same figures as arrays (any pointer may be NULL); device_ms = span between the
+ * step's first and last command on its lane, start_ms = device time since the run's first command; returns the
+ * number of steps. */
+int nodey_engine_diagnostics(nodey_engine* e, char* buf, int cap);
+int nodey_engine_level_timings(nodey_engine* e, int* wave, int* level, int* lane, int* nodes, double* enqueue_ms, double* device_ms,
+                               double* start_ms, int cap);
+
 enum { NODEY_ENGINE_E_INVALID = -1, NODEY_ENGINE_E_FILE = -2, NODEY_ENGINE_E_GRAPH = -3, NODEY_ENGINE_E_NODE = -4 };
 
 #ifdef __cplusplus

@@ -50,6 +50,8 @@ def lib():
     L.nodey_engine_set_export_path.argtypes = [vp, cp]
     L.nodey_engine_set_preview.argtypes = [vp, i32]
     L.nodey_engine_set_export_kbps.argtypes = [vp, i32]
+    L.nodey_engine_diagnostics.argtypes = [vp, cp, i32]
+    L.nodey_engine_level_timings.argtypes = [vp] + [C.POINTER(i32)] * 4 + [C.POINTER(C.c_double)] * 3 + [i32]
     L.nodey_engine_encode_mp3.argtypes = [cp, vp, vp, i32, i32, i32, i64, i32, C.c_double, i32, C.POINTER(C.c_double)]
     L.nodey_engine_preview.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), i32]
     _lib = L
@@ -197,6 +199,22 @@ class Engine:
             nodey.check(nodey.lib().nodey_memcpy_d2h(out.ctypes.data_as(C.c_void_p), ptr, out.nbytes, None))
             nodey.check(nodey.lib().nodey_stream_synchronize(None))
         return out, [chunks[k] for k in range(min(n, cap))]
+
+    def diagnostics(self):
+        """the overlay's Audio block of the last run as text"""
+        n = _check(lib().nodey_engine_diagnostics(self.h, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        _check(lib().nodey_engine_diagnostics(self.h, buf, n + 1))
+        return buf.value.decode()
+
+    def level_timings(self):
+        """[{wave, level, lane, nodes, enqueue_ms, device_ms, start_ms}, ...] of the last run, in enqueue order"""
+        cap = 4096
+        iv = [(C.c_int * cap)() for _ in range(4)]
+        dv = [(C.c_double * cap)() for _ in range(3)]
+        n = _check(lib().nodey_engine_level_timings(self.h, *iv, *dv, cap))
+        keys = ("wave", "level", "lane", "nodes", "enqueue_ms", "device_ms", "start_ms")
+        return [dict(zip(keys, [a[k] for a in iv] + [a[k] for a in dv])) for k in range(min(n, cap))]
 
     def product(self, node_id, pin):
         kind, fmt, rate, ch, extra = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -37,8 +37,23 @@ namespace infra
 			std::any exception;   // Processor::Runtime_error, std::runtime_error, std::logic_error or std::exception
 		};
 
+		// Diagnostics.  The reference's overlay lists the fill of every link's 16-frame
+		// channel (src/frontend/app.cpp:1556-1592); links here are published once, so what tells a user where the
+		// time goes is the device time of every (wave, level) step: events recorded on the step's lane around its
+		// enqueue.  device_ms is the span on that lane (it includes waiting for products of other lanes).
+		struct Level_timing
+		{
+			int wave = 0, level = 0, lane = 0;
+			size_t nodes = 0;
+			std::string identifier;       // identifier of the step's first node class
+			double enqueue_ms = 0.0;      // host time spent enqueueing the step
+			double device_ms = 0.0;       // device span between the step's first and last command on its lane
+			double start_ms = 0.0;        // device time from the run's first command to the step's first
+		};
+
 	  private:
 
+		std::vector<Level_timing> level_timings;
 		std::map<Id_t, std::shared_ptr<Processor_resource>> processor_resources;
 		std::map<Id_t, std::shared_ptr<Processor::Product>> link_products;
 		std::map<Id_t, std::shared_ptr<std::any>> node_data;
@@ -71,5 +86,9 @@ namespace infra
 		bool finished() const { return done.load(); }
 		// first error in node-id order as text, empty when every node finished
 		std::string first_error() const;
+		// per-step device timings of the finished run (empty while running)
+		std::vector<Level_timing> get_level_timings() const { return done.load() ? level_timings : std::vector<Level_timing>{}; }
+		// the overlay's "Audio" block as text: node states, then one line per step
+		std::string diagnostics_text() const;
 	};
 }

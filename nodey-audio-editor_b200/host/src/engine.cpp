@@ -271,6 +271,38 @@ int nodey_engine_set_export_path(nodey_engine* e, const char* path)
 	return 0;
 }
 
+int nodey_engine_diagnostics(nodey_engine* e, char* buf, int cap)
+{
+	if (!e || !e->runner) return fail(NODEY_ENGINE_E_INVALID, "the engine has not run");
+	const std::string text = e->runner->diagnostics_text();
+	if (buf && cap > 0)
+	{
+		const size_t n = std::min(text.size(), (size_t)cap - 1);
+		memcpy(buf, text.data(), n);
+		buf[n] = 0;
+	}
+	return (int)text.size();
+}
+
+int nodey_engine_level_timings(nodey_engine* e, int* wave, int* level, int* lane, int* nodes, double* enqueue_ms, double* device_ms,
+                               double* start_ms, int cap)
+{
+	if (!e || !e->runner) return fail(NODEY_ENGINE_E_INVALID, "the engine has not run");
+	const auto timings = e->runner->get_level_timings();
+	for (int k = 0; k < (int)timings.size() && k < cap; k++)
+	{
+		const auto& t = timings[(size_t)k];
+		if (wave) wave[k] = t.wave;
+		if (level) level[k] = t.level;
+		if (lane) lane[k] = t.lane;
+		if (nodes) nodes[k] = (int)t.nodes;
+		if (enqueue_ms) enqueue_ms[k] = t.enqueue_ms;
+		if (device_ms) device_ms[k] = t.device_ms;
+		if (start_ms) start_ms[k] = t.start_ms;
+	}
+	return (int)timings.size();
+}
+
 int nodey_engine_set_export_kbps(nodey_engine* e, int kbps)
 {
 	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");

@@ -507,6 +507,22 @@ namespace infra
 		return "";
 	}
 
+	std::string Runner::diagnostics_text() const
+	{
+		// count_processor_states + the "%d Running | %d Finished | %d Errors" line of app.cpp:1558-1567
+		int running = 0, finished_count = 0, errors = 0;
+		for (const auto& [_, r] : processor_resources)
+		{
+			const State st = r->state.load();
+			running += st == State::Running; finished_count += st == State::Finished; errors += st == State::Error;
+		}
+		std::string text = std::format("{} Running | {} Finished | {} Errors\n", running, finished_count, errors);
+		for (const auto& t : get_level_timings())
+			text += std::format("W{} L{} {} x{}: {:.2f} ms (lane {}, +{:.2f} ms, enqueue {:.2f} ms)\n", t.wave, t.level, t.identifier, t.nodes,
+								t.device_ms, t.lane, t.start_ms, t.enqueue_ms);
+		return text;
+	}
+
 	namespace
 	{
 		// the catch ladder of the reference's fiber body (src/infra/runner.cpp:87-136)
@@ -620,6 +636,8 @@ namespace infra
 		// Schedule: sources first (their uploads are enqueued on the transfer lane in pin order), then wave
 		// by wave, each wave level by level on the compute lane.  A wave is the part of the graph fed by a
 		// contiguous block of source pins, so wave k computes while the uploads of wave k+1 are in flight.
+		struct Step_events { Level_timing timing; nodey_event_t begin = nullptr, end = nullptr; bool ok = false; };
+		std::vector<Step_events> steps;
 		for (int wave = 0; wave <= max_wave && !failed; wave++)
 			for (size_t level_index = wave == 0 ? 0 : 1; level_index < levels.size() && !failed; level_index++)
 			{
@@ -628,7 +646,16 @@ namespace infra
 					if (node_wave.at(id) == wave) ids.push_back(id);
 				if (ids.empty()) continue;
 				const auto t_begin = std::chrono::steady_clock::now();
-				run_group(ids, level_index == 0 ? 0 : 1 + wave % compute_lanes, (int)level_index);
+				const int lane = level_index == 0 ? 0 : 1 + wave % compute_lanes;
+				Step_events se;
+				se.timing.wave = wave; se.timing.level = (int)level_index; se.timing.lane = lane; se.timing.nodes = ids.size();
+				se.timing.identifier = processor_resources.at(ids.front())->processor->get_processor_info_non_static().identifier;
+				const bool timed = nodey_event_create(&se.begin, 1) == NODEY_OK && nodey_event_create(&se.end, 1) == NODEY_OK
+								&& nodey_event_record(se.begin, lanes[lane]) == NODEY_OK;
+				run_group(ids, lane, (int)level_index);
+				se.timing.enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+				se.ok = timed && nodey_event_record(se.end, lanes[lane]) == NODEY_OK;
+				steps.push_back(std::move(se));
 				if (trace)
 				{
 					const auto t_enq = std::chrono::steady_clock::now();
@@ -641,9 +668,20 @@ namespace infra
 				}
 			}
 		for (auto& s : lanes)
+			if (s) nodey_stream_synchronize(s);
+		// everything has drained: turn the step events into timings (the run's origin is the first step's begin)
+		for (auto& se : steps)
+		{
+			float ms = 0.0f;
+			if (se.ok && !failed && nodey_event_elapsed_ms(&ms, se.begin, se.end) == NODEY_OK) se.timing.device_ms = ms;
+			if (se.ok && !failed && steps.front().ok && nodey_event_elapsed_ms(&ms, steps.front().begin, se.begin) == NODEY_OK) se.timing.start_ms = ms;
+			if (se.begin) nodey_event_destroy(se.begin);
+			if (se.end) nodey_event_destroy(se.end);
+			level_timings.push_back(std::move(se.timing));
+		}
+		for (auto& s : lanes)
 		{
 			if (!s) continue;
-			nodey_stream_synchronize(s);
 			Lane_registry::remove(s);
 			nodey_stream_destroy(s);
 		}

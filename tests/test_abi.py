@@ -69,3 +69,15 @@ def test_amix_plan_rejects_17_inputs():
     import pytest
     with pytest.raises(nodey.NodeyError):
         nodey.amix_plan([44100] * 17, [nodey.uniform_runs(100)] * 17)
+
+
+def test_host_library_exports_every_symbol_of_the_engine_header():
+    """libnodey_host.so (the C facade of the C++ host layer) exports what include/nodey_engine.h declares"""
+    import engine
+    text = open(os.path.join(ROOT, "include", "nodey_engine.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(nodey_engine_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 20
+    lib = engine.lib()
+    for n in names:
+        assert hasattr(lib, n), f"libnodey_host.so does not export {n}"

@@ -359,3 +359,30 @@ def test_bimix_node_against_real_libswresample(eng_gpu, orc, tag):
     tol = 0.0 if (left[0] == 48000 and right[0] == 48000) else 1e-6
     assert np.abs(got[0] - gl).max() <= tol and np.abs(got[1] - gr).max() <= tol
     e.close()
+
+
+def test_diagnostics_report_every_step_of_the_run(eng_gpu, orc):
+    """the data behind the editor's overlay -- node states and the device time of every
+    (wave, level) step of the Runner (the reference shows channel fill per link, app.cpp:1556-1592)."""
+    n = 44100
+    project, ids = eng_gpu.config5_project(16, [1.0] * 16)
+    e = eng_gpu.Engine(project.json())
+    with pytest.raises(eng_gpu.EngineError):
+        e.diagnostics()                                   # nothing has run yet
+    for t in range(16):
+        e.bind_source(t, orc.synth_f32(n, 2, 44100, t), 3, 44100)
+    e.run()
+    steps = e.level_timings()
+    levels = {lvl for _, _, lvl in e.nodes()}
+    assert {s["level"] for s in steps} == levels          # every level of the graph ran as at least one step
+    assert sum(s["nodes"] for s in steps) == len(e.nodes())
+    assert steps[0]["level"] == 0 and steps[0]["lane"] == 0 and steps[0]["start_ms"] == 0.0      # sources on the transfer lane
+    assert all(s["lane"] >= 1 for s in steps[1:])
+    assert all(s["device_ms"] >= 0.0 and s["enqueue_ms"] > 0.0 and s["start_ms"] >= 0.0 for s in steps)
+    heavy = max(steps, key=lambda s: s["device_ms"])
+    assert heavy["device_ms"] > 0.05                      # the SoundTouch steps take measurable device time
+    text = e.diagnostics().splitlines()
+    assert text[0] == f"0 Running | {len(e.nodes())} Finished | 0 Errors"
+    assert len(text) == 1 + len(steps) and text[1].startswith("W0 L0 audio_input x1:")
+    assert any("pitch_modifier x16" in line for line in text)
+    e.close()
