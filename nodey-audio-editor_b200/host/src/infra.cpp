@@ -675,6 +675,9 @@ namespace infra
 			float ms = 0.0f;
 			if (se.ok && !failed && nodey_event_elapsed_ms(&ms, se.begin, se.end) == NODEY_OK) se.timing.device_ms = ms;
 			if (se.ok && !failed && steps.front().ok && nodey_event_elapsed_ms(&ms, steps.front().begin, se.begin) == NODEY_OK) se.timing.start_ms = ms;
+		}
+		for (auto& se : steps)      // only now: the first step's begin event is the origin of every start_ms above
+		{
 			if (se.begin) nodey_event_destroy(se.begin);
 			if (se.end) nodey_event_destroy(se.end);
 			level_timings.push_back(std::move(se.timing));
