@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=TRACKS, help="total tracks (development only; the contract is 256)")
     ap.add_argument("--seconds", type=int, default=SECONDS, help="track length (development only; the contract is 180)")
+    ap.add_argument("--bus", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the master bus is formed -- nccl: nodey_bus_reduce of the partial buses (1e-5 of the one-GPU bus); "
+                         "peer: the root's master mix reads every rank's group mixes over NVLink peer memory (bit identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -49,7 +52,9 @@ def workload_config(args, n_gpus):
                         "(audio_amix(1) resample -> pitch_modifier +3 -> velocity_modifier 1.25 keep_pitch -> "
                         "audio_volume_adjust -> audio_amix 16x tree -> master bus -> audio_spectrum 4096/1024)",
             "tracks": args.tracks, "track_seconds": args.seconds, "sharding": f"tracks/{n_gpus} per GPU, contiguous groups of 16",
-            "collective": "nodey_bus_reduce: ncclReduce(sum) of the partial master bus (C ABI, own communicator)" if n_gpus > 1 else "none",
+            "collective": "none" if n_gpus == 1 else (
+                "nodey_bus_reduce: ncclReduce(sum) of the partial master bus (C ABI, own communicator)" if getattr(args, "bus", "nccl") == "nccl"
+                else "none: the root's master audio_amix reads every rank's group mixes over NVLink peer memory (nodey_peer_*, one kernel)"),
             "audio_seconds_per_step": args.tracks * args.seconds,
             "l2": "inputs larger than L2 (>= 2 GB per GPU per step), no flush needed"}
 
@@ -220,6 +225,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     bus_t = [None]
+    peer = [None]
 
     def finish(want_host=None):
         """after eng.run(): reduce the partial buses (N > 1), spectrum on rank 0, optional D2H"""
@@ -227,9 +233,22 @@ def run_ours(args):
         if world > 1:
             if bus_t[0] is None:
                 bus_t[0] = torch.empty((2, out.frames), dtype=torch.float32, device=dev)
-            # the only collective of the path: sum of the partial master buses straight out of the engine's planes,
-            # through the C ABI (nodey_bus_reduce: ncclReduce of both planes in one group, no staging copy)
-            bus.reduce_ptrs(out.p0, out.p1, bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr(), out.frames, root=0)
+            if args.bus == "peer":
+                # compute + exchange in one kernel: the root's master mix over the group mixes of every rank, remote ones
+                # read through CUDA-IPC mapped pointers over NVLink, in the graph's input order (bit identical to one GPU)
+                groups = [eng.product(g, "output") for g in ids["groups"]]
+                if peer[0] is None:
+                    def exchange(obj):
+                        box = [None] * world
+                        dist.all_gather_object(box, obj)
+                        return box
+                    peer[0] = pipeline.PeerMaster(rank, world, len(groups), groups[0].frames, exchange, dist.barrier)
+                peer[0].stage(groups)
+                peer[0].mix(bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr(), out.frames, 1.0 / 16, torch.cuda.synchronize)
+            else:
+                # the only collective of the path: sum of the partial master buses straight out of the engine's planes,
+                # through the C ABI (nodey_bus_reduce: ncclReduce of both planes in one group, no staging copy)
+                bus.reduce_ptrs(out.p0, out.p1, bus_t[0][0].data_ptr(), bus_t[0][1].data_ptr(), out.frames, root=0)
             spec_ptr, spec_elems = None, 0
             if rank == 0:
                 if len(bus_t) < 2:     # the spectrum buffer is allocated once: a fresh 221 MB cudaMalloc per step stalled rank 0 for up to 50 ms
@@ -407,6 +426,9 @@ def run_ours(args):
     eng.close()
     if world > 1:
         torch.cuda.synchronize()
+        if peer[0] is not None:
+            dist.barrier()
+            peer[0].close()
         bus.close()
         dist.destroy_process_group()
 

@@ -289,6 +289,21 @@ int nodey_bus_reduce(nodey_bus* bus, const float* send_l, const float* send_r, f
 int nodey_bus_allreduce(nodey_bus* bus, const float* send_l, const float* send_r, float* recv_l, float* recv_r,
                         int64_t nframes, nodey_stream_t stream);
 
+/* Peer memory: the master mix as one kernel over NVLink instead of "mix, then reduce".  nodey_peer_alloc makes a
+ * block that can be exported to the other processes of the box (CUDA IPC; plain cudaMalloc, not the stream-ordered
+ * pool); nodey_peer_export writes its NODEY_PEER_HANDLE_BYTES handle; a rank that nodey_peer_open()s the handle holds an
+ * ordinary device pointer whose loads travel over NVLink.  nodey_mix reads its inputs wherever they live, so the root
+ * runs the graph's master audio_amix (audio-amix.cpp:293-307) over the group mixes of EVERY rank in the graph's input
+ * order: compute and exchange are one kernel, and the bus is BIT IDENTICAL to the one-GPU render (nodey_bus_reduce adds
+ * partial buses in another order: 1e-5).  Cross-process ordering is the caller's: a peer's block may be read once that
+ * peer has synchronised its writes and said so (a barrier), and rewritten once the reader has finished. */
+#define NODEY_PEER_HANDLE_BYTES 64
+int nodey_peer_alloc(void** out, size_t bytes);
+int nodey_peer_free(void* p);
+int nodey_peer_export(const void* p, void* handle);
+int nodey_peer_open(void** out, const void* handle);
+int nodey_peer_close(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ SYMBOLS = [
     "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory",
     "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",
     "nodey_bus_reduce", "nodey_bus_allreduce",
+    "nodey_peer_alloc", "nodey_peer_free", "nodey_peer_export", "nodey_peer_open", "nodey_peer_close",
     "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
 ]
 
@@ -111,6 +112,11 @@ def lib():
     L.nodey_bus_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.nodey_bus_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
     L.nodey_bus_allreduce.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+    L.nodey_peer_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.nodey_peer_free.argtypes = [vp]
+    L.nodey_peer_export.argtypes = [vp, vp]
+    L.nodey_peer_open.argtypes = [C.POINTER(vp), vp]
+    L.nodey_peer_close.argtypes = [vp]
     _lib = L
     return L
 
@@ -548,3 +554,48 @@ class Bus:
         check(lib().nodey_bus_allreduce(self.h, _dp(send[0]), _dp(send[1]) if nch == 2 else None,
                                         _dp(recv[0]), _dp(recv[1]) if nch == 2 else None, n, _stream()))
         return recv
+
+
+PEER_HANDLE_BYTES = 64
+
+
+class PeerBlock:
+    """Device block other processes of the box can map (nodey_peer_*): .ptr, .handle (64 bytes to hand round)."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib().nodey_peer_alloc(C.byref(p), nbytes))
+        self.ptr, self.nbytes = p.value, nbytes
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        check(lib().nodey_peer_export(C.c_void_p(self.ptr), buf))
+        self.handle = buf.raw
+
+    def close(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.nodey_peer_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    __del__ = close
+
+
+def peer_open(handle):
+    """device address (int) of another rank's PeerBlock in this process; nodey.peer_close() when done"""
+    assert len(handle) == PEER_HANDLE_BYTES
+    p = C.c_void_p()
+    check(lib().nodey_peer_open(C.byref(p), C.c_char_p(bytes(handle))))
+    return p.value
+
+
+def peer_close(ptr):
+    check(lib().nodey_peer_close(C.c_void_p(ptr)))
+
+
+def mix_ptrs(out_l, out_r, in_l, in_r, lens, volumes, nframes, stream=None):
+    """nodey_mix on raw device addresses (ints): local or peer-mapped inputs alike"""
+    nin = len(in_l)
+    pl = (C.c_void_p * nin)(*in_l)
+    pr = (C.c_void_p * nin)(*in_r)
+    ln = (C.c_int64 * nin)(*[int(v) for v in lens])
+    vol = (C.c_float * nin)(*[float(v) for v in volumes])
+    check(lib().nodey_mix(C.c_void_p(out_l), C.c_void_p(out_r), pl, pr, ln, vol, nin, nframes,
+                          stream if stream is not None else _stream()))

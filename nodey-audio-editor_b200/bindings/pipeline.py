@@ -126,3 +126,64 @@ class Config5Renderer:
             buses += self.render_groups(xb, first_track + s)
         bus = self.master(buses)
         return bus
+
+
+class PeerMaster:
+    """Master mix of a track-sharded render as ONE kernel over NVLink peer memory (nodey_peer_*, include/nodey_cuda.h).
+
+    Every rank stages the level-1 group mixes of its tracks (FLTP, 48 kHz) in a block the other processes can map; the
+    root then runs the graph's master audio_amix -- nodey_mix, inputs in the graph's order, audio-amix.cpp:293-307 --
+    over the groups of ALL ranks, reading the remote ones through the mapped pointers.  Compute and exchange are one
+    kernel and the bus is bit identical to the one-GPU render (a reduce of partial buses sums in another order).
+
+    exchange(obj) -> [obj of rank 0, obj of rank 1, ...] and barrier() are the caller's plumbing (torch.distributed,
+    a launcher, files): the library only needs the 64-byte handles handed round once and two barriers per step.
+    """
+
+    def __init__(self, rank, world, groups_local, group_frames, exchange, barrier, root=0):
+        self.rank, self.world, self.root = rank, world, root
+        self.groups_local, self.frames = groups_local, int(group_frames)
+        self.barrier = barrier
+        self.plane = (self.frames * 4 + 255) // 256 * 256
+        self.block = nd.PeerBlock(max(1, groups_local * 2 * self.plane))
+        handles = exchange(self.block.handle)
+        self.mapped = {}
+        if rank == root:
+            for r, h in enumerate(handles):
+                self.mapped[r] = self.block.ptr if r == rank else nd.peer_open(h)
+
+    def plane_ptr(self, base, group, ch):
+        return base + (group * 2 + ch) * self.plane
+
+    def stage(self, group_products):
+        """copy this rank's group mixes (engine products: .p0 / .p1 planes, .frames) into the exported block"""
+        import ctypes as C
+        assert len(group_products) == self.groups_local
+        for g, p in enumerate(group_products):
+            assert p.frames == self.frames and p.fmt == nd.FMT_FLTP and p.rate == 48000, "group mixes are 48 kHz FLTP of one length"
+            for ch, src in enumerate((p.p0, p.p1)):
+                nd.check(nd.lib().nodey_memcpy_d2d(C.c_void_p(self.plane_ptr(self.block.ptr, g, ch)), C.c_void_p(src), self.frames * 4,
+                                                   nd._stream()))
+
+    def mix(self, out_l, out_r, total_frames, master_vol, sync):
+        """sync(): wait for this rank's device work.  Every rank calls mix(); the root launches the kernel.
+        out_l / out_r: device addresses of the bus planes on the root (ignored elsewhere)."""
+        sync()
+        self.barrier()                      # every rank's staged groups are complete and visible
+        if self.rank == self.root:
+            in_l, in_r = [], []
+            for r in range(self.world):     # rank r holds groups [r * groups_local, (r + 1) * groups_local): the graph's input order
+                for g in range(self.groups_local):
+                    in_l.append(self.plane_ptr(self.mapped[r], g, 0))
+                    in_r.append(self.plane_ptr(self.mapped[r], g, 1))
+            n = len(in_l)
+            nd.mix_ptrs(out_l, out_r, in_l, in_r, [self.frames] * n, [master_vol] * n, total_frames)
+            sync()
+        self.barrier()                      # the root has read everything: the blocks may be rewritten
+
+    def close(self):
+        for r, p in self.mapped.items():
+            if r != self.rank:
+                nd.peer_close(p)
+        self.mapped = {}
+        self.block.close()

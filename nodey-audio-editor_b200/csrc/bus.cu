@@ -203,4 +203,51 @@ int nodey_bus_allreduce(nodey_bus* bus, const float* send_l, const float* send_r
     return bus_collective("nodey_bus_allreduce", bus, s, r, send_r ? 2 : 1, nframes, -1, stream);
 }
 
+// ---- peer memory: the master mix as ONE kernel over NVLink (no collective) ------------------------------------
+// A block made by nodey_peer_alloc can be exported to the other processes of the box (CUDA IPC); a rank that opened
+// it holds an ordinary device pointer whose loads travel over NVLink.  nodey_mix does not care where its inputs
+// live, so rank 0 can run the graph's master audio_amix over the group mixes of EVERY rank in the graph's input
+// order: compute and exchange in one kernel, and the bus is bit identical to the one-GPU render (a reduce of
+// partial buses adds in another order).  Ordering across processes is the caller's: a peer's block may be read
+// once that peer has synchronised its writes and said so (barrier), and rewritten once the reader is done.
+int nodey_peer_alloc(void** out, size_t bytes)
+{
+    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_peer_alloc: out must not be NULL");
+    *out = nullptr;
+    NODEY_CUDA_OK(cudaMalloc(out, bytes ? bytes : 1));      // plain cudaMalloc: stream-ordered pool memory cannot be exported this way
+    return NODEY_OK;
+}
+
+int nodey_peer_free(void* p)
+{
+    if (p) NODEY_CUDA_OK(cudaFree(p));
+    return NODEY_OK;
+}
+
+int nodey_peer_export(const void* p, void* handle)
+{
+    NODEY_REQUIRE(p && handle, NODEY_E_INVALID, "nodey_peer_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NODEY_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    NODEY_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(p)));
+    memcpy(handle, &h, sizeof(h));
+    return NODEY_OK;
+}
+
+int nodey_peer_open(void** out, const void* handle)
+{
+    NODEY_REQUIRE(out && handle, NODEY_E_INVALID, "nodey_peer_open: null argument");
+    *out = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    NODEY_CUDA_OK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return NODEY_OK;
+}
+
+int nodey_peer_close(void* p)
+{
+    if (p) NODEY_CUDA_OK(cudaIpcCloseMemHandle(p));
+    return NODEY_OK;
+}
+
 }  // extern "C"
