@@ -45,3 +45,44 @@ def test_collectives_reject_a_null_bus():
     L.nodey_bus_destroy(None)                          # like free(NULL)
     with pytest.raises(nodey.NodeyError):
         nodey.check(L.nodey_bus_reduce(None, p, None, p, None, 4, -1, None))
+
+
+def test_peer_master_orders_the_groups_like_the_graph(monkeypatch):
+    """host logic of pipeline.PeerMaster without a device: the root hands nodey_mix the groups of rank 0, 1, 2 ... in
+    that order (the master audio_amix's input order), each plane at its slot of the owner's block, after a barrier, and
+    releases the blocks with a second barrier; other ranks launch nothing."""
+    import nodey
+    import pipeline
+
+    class FakeBlock:
+        def __init__(self, nbytes):
+            self.ptr, self.nbytes, self.handle = 0x1000000, nbytes, b"me".ljust(64, b"\0")
+
+        def close(self):
+            self.ptr = None
+
+    opened, closed, calls, events = [], [], [], []
+    monkeypatch.setattr(nodey, "PeerBlock", FakeBlock)
+    monkeypatch.setattr(nodey, "peer_open", lambda h: opened.append(h) or 0x10000000 * (1 + int(h[:1])))
+    monkeypatch.setattr(nodey, "peer_close", lambda p: closed.append(p))
+    monkeypatch.setattr(nodey, "mix_ptrs", lambda *a, **k: calls.append(a))
+    world, groups_local, frames = 4, 4, 1000
+    handles = [str(r).encode().ljust(64, b"\0") for r in range(world)]
+    pm = pipeline.PeerMaster(0, world, groups_local, frames, lambda obj: handles, lambda: events.append("barrier"))
+    assert [h[:1] for h in opened] == [b"1", b"2", b"3"]            # the root maps every other rank's block, not its own
+    plane = pm.plane
+    assert plane % 256 == 0 and plane >= frames * 4 and pm.block.nbytes == groups_local * 2 * plane
+    pm.mix(111, 222, frames + 1152, 1.0 / 16, lambda: events.append("sync"))
+    assert events == ["sync", "barrier", "sync", "barrier"]
+    (out_l, out_r, in_l, in_r, lens, vols, total), = calls
+    assert (out_l, out_r, total) == (111, 222, frames + 1152) and lens == [frames] * 16 and vols == [1.0 / 16] * 16
+    bases = [0x1000000, 0x20000000, 0x30000000, 0x40000000]
+    assert in_l == [bases[r] + (g * 2) * plane for r in range(world) for g in range(groups_local)]
+    assert in_r == [bases[r] + (g * 2 + 1) * plane for r in range(world) for g in range(groups_local)]
+    pm.close()
+    assert sorted(closed) == bases[1:]
+    # a non-root rank: no mapping, no launch, same two barriers
+    opened.clear(); calls.clear(); events.clear()
+    other = pipeline.PeerMaster(2, world, groups_local, frames, lambda obj: handles, lambda: events.append("barrier"))
+    other.mix(0, 0, frames + 1152, 1.0 / 16, lambda: events.append("sync"))
+    assert not opened and not calls and events == ["sync", "barrier", "barrier"]
