@@ -414,8 +414,11 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         a, w = cpu_sample(16, 60, cores)
+        a1, w1 = cpu_sample(16, 20, 1)
         cpu_baseline = {"value": a / w, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "16 tracks x 60 s of the same graph, oracle port of the reference processors, one track chain per host thread"}
+                        "sample": "16 tracks x 60 s of the same graph, oracle port of the reference processors, one track chain per host thread",
+                        # the reference's Runner drives a whole graph from ONE thread: the same port on one core
+                        "single_thread": {"value": a1 / w1, "unit": UNIT, "cores": 1, "sample": "16 tracks x 20 s of the same graph"}}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
