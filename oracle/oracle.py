@@ -1,8 +1,9 @@
 """ctypes binding of the CPU oracle (oracle/nodey_oracle.c).
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs, never by the product package.  Parity unpinned: the
-reference has no fixtures and its DSP libraries are restated (see nodey_oracle.h).
+cpu_baseline / --impl reference legs, never by the product package.  Pinning: the reference has no
+fixtures; the libswresample model is pinned against a real libswresample (oracle/real_swr.py,
+tests/golden/swr_real.npz), the SoundTouch model is PARITY UNPINNED (see nodey_oracle.c / .h).
 """
 import ctypes as C
 import os
