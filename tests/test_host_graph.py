@@ -164,3 +164,19 @@ def test_example_frame_processor_registers_and_round_trips():
     again = json.loads(e.serialize())
     assert again["nodes"][str(fg)]["identifier"] == "frame_gain_example"
     assert again["nodes"][str(fg)]["info"] == {"volume": 0.25}
+
+
+def test_graph_editing_api_cpp(tmp_path):
+    """the C++ editing API the editor drives (add_node / remove_node / update_node_pin / add_link / remove_link, id
+    reuse, singleton map, links re-attached by pin name): tests/cpp/graph_edit_test.cpp against libnodey_host.so"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "nodey-audio-editor_b200")
+    exe = str(tmp_path / "graph_edit_test")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I" + os.path.join(pkg, "host", "shim"), "-I" + os.path.join(pkg, "host", "include"),
+                    "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "cpp", "graph_edit_test.cpp"),
+                    "-L" + pkg, "-lnodey_host", "-lnodey_cuda", "-Wl,-rpath," + pkg, "-lpthread"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "graph_edit_test ok" in r.stdout
