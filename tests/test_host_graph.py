@@ -180,3 +180,23 @@ def test_graph_editing_api_cpp(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stderr
     assert "graph_edit_test ok" in r.stdout
+
+
+def test_render_without_a_cuda_device_fails_loudly(eng):
+    """no CPU fallback: on a box without a CUDA device the Runner marks every node as failed with a Runtime_error that
+    says so (the product path never routes through the oracle)"""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a CUDA device")
+    p = eng.Project()
+    src = p.add("audio_input", {"file_path": [""]})
+    g = p.add("audio_volume_adjust", {"volume": 0.5})
+    out = p.add("audio_output")
+    p.link(src, "output_0", g, "input"); p.link(g, "output", out, "input")
+    e = eng.Engine(p.json())
+    e.bind_source(0, np.zeros((1000, 2), np.float32), 3, 48000)
+    with pytest.raises(eng.EngineError) as x:
+        e.run()
+    assert "No CUDA device" in x.value.message and "no CPU fallback" in x.value.message
+    assert e.diagnostics().splitlines()[0] == "0 Running | 0 Finished | 3 Errors"
