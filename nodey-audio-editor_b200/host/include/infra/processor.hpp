@@ -36,61 +36,30 @@ namespace infra
 	{
 	  public:
 
-		// what travels over a link; every product kind derives from this
-		class Product
-		{
-		  public:
-			Product() = default;
-			virtual ~Product() = default;
-			const std::type_info& get_typeinfo() const { return typeid(*this); }
-		};
+		class Product;
+		struct Info;
+		// payload maps of one node: the product on each input pin, the products (one per link) on each output pin
+		using Input_map = std::map<std::string, std::shared_ptr<Product>>;
+		using Output_map = std::map<std::string, std::set<std::shared_ptr<Product>>>;
 
-		struct Pin_attribute
-		{
-			std::string identifier;
-			std::string display_name;
-			std::reference_wrapper<const std::type_info> type;
-			bool is_input;
-			std::function<std::shared_ptr<Product>()> generate_func;
-		};
+		// ---- registry (src/infra/processor.cpp:5, include/infra/processor.hpp:116-129) ----
+		static std::map<std::string, Info> processor_map;
 
-		struct Info
-		{
-			std::string identifier;
-			std::string display_name;
-			bool singleton = false;
-			std::function<std::unique_ptr<Processor>()> generate;
-			std::string description;
-		};
+		template <typename T>
+			requires(std::is_base_of_v<Processor, T> && Has_static_processor_info_func<T, Info>)
+		static void register_processor() { add_to_registry(T::get_processor_info()); }
 
-		// user-facing fault: short message, explanation, technical detail
-		struct Runtime_error : public std::runtime_error
-		{
-			std::string message, explanation, detail;
-
-			Runtime_error(std::string message, std::string explanation, std::string detail = "") :
-				std::runtime_error(std::format("{} (Detail: {}) (Explanation: {})", message, detail, explanation)),
-				message(std::move(message)),
-				explanation(std::move(explanation)),
-				detail(std::move(detail))
-			{
-			}
-		};
-
-		static std::map<std::string, Processor::Info> processor_map;
-
+		// ---- what a node class implements ----
 		Processor() = default;
 		virtual ~Processor() = default;
 
-		virtual std::vector<Processor::Pin_attribute> get_pin_attributes() const = 0;
-		virtual Processor::Info get_processor_info_non_static() const = 0;
-		virtual Json::Value serialize() const = 0;
+		virtual Info get_processor_info_non_static() const = 0;
+		struct Pin_attribute;
+		virtual std::vector<Pin_attribute> get_pin_attributes() const = 0;
 		virtual void deserialize(const Json::Value& value) = 0;
-		virtual void draw_title() = 0;
+		virtual Json::Value serialize() const = 0;
 		virtual bool draw_content(bool readonly) = 0;
-
-		using Input_map = std::map<std::string, std::shared_ptr<Processor::Product>>;
-		using Output_map = std::map<std::string, std::set<std::shared_ptr<Processor::Product>>>;
+		virtual void draw_title() = 0;
 
 		virtual void process_payload(
 			const Input_map& input,
@@ -117,43 +86,72 @@ namespace infra
 		// The Runner pipelines the graph in waves over the source pins only when there is an upload to hide.
 		virtual size_t upload_bytes(const std::any& /*user_data*/) const { return 0; }
 
-		template <typename T>
-			requires(std::is_base_of_v<Processor, T> && Has_static_processor_info_func<T, Processor::Info>)
-		static void register_processor()
+		// ---- nested types of the API ----
+		// user-facing fault: short message, explanation, technical detail
+		struct Runtime_error : public std::runtime_error
 		{
-			const Info processor_info = T::get_processor_info();
-			if (processor_map.contains(processor_info.identifier))
-				THROW_LOGIC_ERROR("Processor with identifier '{}' already registered", processor_info.identifier)
-			processor_map[processor_info.identifier] = processor_info;
-		}
+			std::string message, explanation, detail;
+
+			// what() reads "<message> (Detail: <detail>) (Explanation: <explanation>)" like the reference's (infra.cpp)
+			Runtime_error(std::string message, std::string explanation, std::string detail = "");
+		};
+
+		// what travels over a link; every product kind derives from this
+		class Product
+		{
+		  public:
+			Product() = default;
+			virtual ~Product() = default;
+			const std::type_info& get_typeinfo() const { return typeid(*this); }
+		};
+
+		struct Info
+		{
+			std::string identifier;
+			std::string display_name;
+			bool singleton = false;
+			std::function<std::unique_ptr<Processor>()> generate;
+			std::string description;
+		};
+
+		struct Pin_attribute
+		{
+			std::string identifier;
+			std::string display_name;
+			std::reference_wrapper<const std::type_info> type;
+			bool is_input;
+			std::function<std::shared_ptr<Product>()> generate_func;
+		};
+
+	  private:
+
+		// std::logic_error when the identifier is taken (infra.cpp)
+		static void add_to_registry(Info info);
 	};
+
+	namespace detail
+	{
+		// lookups behind get_input_item / get_output_item (infra.cpp): nullptr when the key is absent from the input map;
+		// std::logic_error for a null product, a product of another type, or a key absent from the output map
+		std::shared_ptr<Processor::Product> input_product(const Processor::Input_map& input, const std::string& key,
+														  const std::type_info& expected);
+		const std::set<std::shared_ptr<Processor::Product>>& output_products(const Processor::Output_map& output, const std::string& key);
+	}
 
 	template <typename T>
 	std::optional<std::reference_wrapper<T>> get_input_item(const Processor::Input_map& input, const std::string& key)
 	{
-		const auto find = input.find(key);
-		if (find == input.end()) return std::nullopt;
-		if (find->second == nullptr) THROW_LOGIC_ERROR("Found nullptr in input map for key '{}'", key);
-		if (find->second->get_typeinfo() != typeid(T))
-			THROW_LOGIC_ERROR(
-				"Type mismatch in input map for key '{}', expected {}, got {}",
-				key, typeid(T).name(), find->second->get_typeinfo().name()
-			);
-		return *std::dynamic_pointer_cast<T>(find->second);
+		const auto product = detail::input_product(input, key, typeid(T));
+		if (!product) return std::nullopt;
+		return static_cast<T&>(*product);        // the type was checked by input_product
 	}
 
 	template <typename T>
 	std::set<std::shared_ptr<T>> get_output_item(const Processor::Output_map& output, const std::string& key)
 	{
-		const auto find = output.find(key);
-		if (find == output.end()) THROW_LOGIC_ERROR("Key '{}' not found in output map", key);
-		std::set<std::shared_ptr<T>> output_set;
-		for (auto& item : find->second)
-		{
-			if (item == nullptr) THROW_LOGIC_ERROR("Found nullptr in output map for key '{}'", key);
-			output_set.emplace(std::dynamic_pointer_cast<T>(item));
-		}
-		return output_set;
+		std::set<std::shared_ptr<T>> typed;
+		for (const auto& product : detail::output_products(output, key)) typed.emplace(std::dynamic_pointer_cast<T>(product));
+		return typed;
 	}
 
 	// registers every node class (src/register.cpp); idempotent in this engine so that a host process

@@ -18,6 +18,17 @@ namespace infra
 	{
 	  public:
 
+		// builds one product per link, starts the worker thread and returns at once (reference semantics)
+		static std::unique_ptr<Runner> create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data);
+
+		// sets every node's stop_source and joins the worker (src/infra/runner.cpp:53-63)
+		~Runner();
+		Runner() = default;
+		Runner(Runner&&) = delete;
+		Runner(const Runner&) = delete;
+		Runner& operator=(Runner&&) = delete;
+		Runner& operator=(const Runner&) = delete;
+
 		enum class State
 		{
 			Ready,
@@ -26,16 +37,26 @@ namespace infra
 			Error
 		};
 
+		// what the UI polls per node: state, stop switch and -- in State::Error -- the exception the node threw
 		struct Processor_resource
 		{
-			std::shared_ptr<Processor> processor;
-			Processor::Input_map input_payloads;
-			Processor::Output_map output_payloads;
-
-			std::atomic<bool> stop_source = false;
 			std::atomic<State> state = State::Ready;
+			std::atomic<bool> stop_source = false;
 			std::any exception;   // Processor::Runtime_error, std::runtime_error, std::logic_error or std::exception
+
+			std::shared_ptr<Processor> processor;
+			Processor::Output_map output_payloads;
+			Processor::Input_map input_payloads;
 		};
+
+		const auto& get_link_products() const { return link_products; }
+		const auto& get_processor_resources() const { return processor_resources; }
+
+		// ---- headless helpers (not in the reference, which polls the states from its UI loop) ----
+		void wait();                                   // joins the worker thread
+		bool finished() const { return done.load(); }
+		// first error in node-id order as text, empty when every node finished
+		std::string first_error() const;
 
 		// Diagnostics.  The reference's overlay lists the fill of every link's 16-frame
 		// channel (src/frontend/app.cpp:1556-1592); links here are published once, so what tells a user where the
@@ -50,45 +71,24 @@ namespace infra
 			double device_ms = 0.0;       // device span between the step's first and last command on its lane
 			double start_ms = 0.0;        // device time from the run's first command to the step's first
 		};
-
-	  private:
-
-		std::vector<Level_timing> level_timings;
-		std::map<Id_t, std::shared_ptr<Processor_resource>> processor_resources;
-		std::map<Id_t, std::shared_ptr<Processor::Product>> link_products;
-		std::map<Id_t, std::shared_ptr<std::any>> node_data;
-		std::vector<std::vector<Id_t>> levels;
-		std::map<Id_t, int> node_wave;          // which block of source pins feeds the node (see launch_threads)
-		std::thread worker;
-		std::atomic<bool> done = false;
-		int device = -1;     // CUDA device of the creating thread; the worker thread binds to it
-
-		void generate_processor_resources(const Graph& graph);
-		void launch_threads();   // body of the worker thread: walks the levels
-
-	  public:
-
-		Runner() = default;
-		Runner(const Runner&) = delete;
-		Runner(Runner&&) = delete;
-		Runner& operator=(const Runner&) = delete;
-		Runner& operator=(Runner&&) = delete;
-		~Runner();
-
-		// builds one product per link, starts the worker thread and returns at once (reference semantics)
-		static std::unique_ptr<Runner> create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data);
-
-		const auto& get_processor_resources() const { return processor_resources; }
-		const auto& get_link_products() const { return link_products; }
-
-		// headless helpers (not in the reference, which polls the states from its UI loop)
-		void wait();                                   // joins the worker thread
-		bool finished() const { return done.load(); }
-		// first error in node-id order as text, empty when every node finished
-		std::string first_error() const;
 		// per-step device timings of the finished run (empty while running)
 		std::vector<Level_timing> get_level_timings() const { return done.load() ? level_timings : std::vector<Level_timing>{}; }
 		// the overlay's "Audio" block as text: node states, then one line per step
 		std::string diagnostics_text() const;
+
+	  private:
+
+		void launch_threads();   // body of the worker thread: walks the levels
+		void generate_processor_resources(const Graph& graph);
+
+		std::thread worker;
+		std::atomic<bool> done = false;
+		int device = -1;     // CUDA device of the creating thread; the worker thread binds to it
+		std::vector<std::vector<Id_t>> levels;
+		std::map<Id_t, int> node_wave;          // which block of source pins feeds the node (see launch_threads)
+		std::vector<Level_timing> level_timings;
+		std::map<Id_t, std::shared_ptr<std::any>> node_data;
+		std::map<Id_t, std::shared_ptr<Processor::Product>> link_products;
+		std::map<Id_t, std::shared_ptr<Processor_resource>> processor_resources;
 	};
 }

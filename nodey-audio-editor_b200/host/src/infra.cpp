@@ -17,6 +17,88 @@ namespace infra
 	std::map<std::string, Processor::Info> Processor::processor_map;
 
 	// ---------------------------------------------------------------------------------------------
+	// plugin API: out-of-line parts of infra/processor.hpp and infra/graph.hpp
+	// ---------------------------------------------------------------------------------------------
+	static std::string runtime_error_text(const std::string& message, const std::string& explanation, const std::string& detail)
+	{
+		return message + " (Detail: " + detail + ") (Explanation: " + explanation + ")";
+	}
+
+	Processor::Runtime_error::Runtime_error(std::string message_, std::string explanation_, std::string detail_) :
+		std::runtime_error(runtime_error_text(message_, explanation_, detail_)),
+		message(std::move(message_)), explanation(std::move(explanation_)), detail(std::move(detail_))
+	{
+	}
+
+	void Processor::add_to_registry(Info info)
+	{
+		const std::string identifier = info.identifier;
+		if (!processor_map.try_emplace(identifier, std::move(info)).second)
+			THROW_LOGIC_ERROR("Processor with identifier '{}' already registered", identifier);
+	}
+
+	std::shared_ptr<Processor::Product> detail::input_product(const Processor::Input_map& input, const std::string& key,
+															  const std::type_info& expected)
+	{
+		const auto slot = input.find(key);
+		if (slot == input.end()) return nullptr;
+		const auto& product = slot->second;
+		if (!product) THROW_LOGIC_ERROR("Found nullptr in input map for key '{}'", key);
+		if (product->get_typeinfo() != expected)
+			THROW_LOGIC_ERROR("Type mismatch in input map for key '{}', expected {}, got {}", key, expected.name(), product->get_typeinfo().name());
+		return product;
+	}
+
+	const std::set<std::shared_ptr<Processor::Product>>& detail::output_products(const Processor::Output_map& output, const std::string& key)
+	{
+		const auto slot = output.find(key);
+		if (slot == output.end()) THROW_LOGIC_ERROR("Key '{}' not found in output map", key);
+		for (const auto& product : slot->second)
+			if (!product) THROW_LOGIC_ERROR("Found nullptr in output map for key '{}'", key);
+		return slot->second;
+	}
+
+	Graph::Mismatched_pin_error::Mismatched_pin_error(Id_t from_, Id_t to_) :
+		std::runtime_error("Mismatch Pin: " + std::to_string(from_) + ", " + std::to_string(to_)), from(from_), to(to_)
+	{
+	}
+	Graph::Loop_detected_error::Loop_detected_error() : std::runtime_error("Loop Detected") {}
+	Graph::Multiple_input_error::Multiple_input_error(Id_t pin_) :
+		std::runtime_error("Multiple Inputs in Input Pin: " + std::to_string(pin_)), pin(pin_)
+	{
+	}
+	Graph::Invalid_file_error::Invalid_file_error(std::string message_) :
+		std::runtime_error("Invalid File: " + message_), message(std::move(message_))
+	{
+	}
+
+	bool Graph::check_node_type_match(Id_t from, Id_t to) const
+	{
+		// pin types are compared by the ADDRESS of their type_info, as the reference does (include/infra/graph.hpp:167-170)
+		const std::type_info* a = &pins.at(from).attribute.type.get();
+		const std::type_info* b = &pins.at(to).attribute.type.get();
+		return a == b;
+	}
+
+	bool Graph::check_multiple_input(Id_t pin_id) const
+	{
+		const auto arrivals = std::count_if(links.begin(), links.end(), [pin_id](const auto& entry) { return entry.second.to == pin_id; });
+		return arrivals <= 1;
+	}
+
+	namespace
+	{
+		// smallest id that is not a key of the map: ids are handed out again after a removal, like the reference's
+		template <typename Map>
+		Id_t find_empty(const Map& items)
+		{
+			Id_t candidate = 0;
+			for (auto it = items.begin(); it != items.end() && it->first == candidate; ++it) ++candidate;
+			return candidate;
+		}
+	}
+
+	// ---------------------------------------------------------------------------------------------
 	// device handles over the C ABI
 	// ---------------------------------------------------------------------------------------------
 	static void abi_check(int rc, const char* what)
