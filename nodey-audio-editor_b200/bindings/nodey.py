@@ -526,7 +526,11 @@ class Bus:
             _lib.nodey_bus_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: the library or the CUDA context may be gone already
+            pass
 
     def info(self):
         r, n, d = C.c_int(), C.c_int(), C.c_int()
