@@ -184,7 +184,23 @@ def tds_fp32_ops(r, batch):
     return batch * ops
 
 
+class JsonStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is WARN or VERSION), so the real stdout is put aside for the result line and file descriptor 1 points at
+    stderr while the bench runs."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.fd, (line.rstrip("\n") + "\n").encode())
+
+
 def run_ours(args):
+    result_out = JsonStdout()
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -425,7 +441,7 @@ def run_ours(args):
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(out), flush=True)
+        result_out.emit(json.dumps(out))
     eng.close()
     if world > 1:
         torch.cuda.synchronize()

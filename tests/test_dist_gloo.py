@@ -56,3 +56,32 @@ def test_two_rank_partial_bus_reduce(tmp_path, orc):
     assert got.shape == ref.shape
     resid = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()
     assert resid <= max(1e-5 * np.abs(ref).max(), 1e-5), resid
+
+
+_EMIT = r"""
+import ctypes, json, os, sys
+sys.path.insert(0, sys.argv[1])
+import bench
+out = bench.JsonStdout()
+print('python noise')
+libc = ctypes.CDLL(None)
+libc.puts(b'NCCL version 2.28.9+cuda12.9')
+libc.fflush(None)
+os.write(1, b'raw noise\n')
+out.emit(json.dumps({'metric': 'm', 'value': 1.5}))
+print('late noise')
+"""
+
+
+def test_bench_result_line_is_the_only_thing_on_stdout(tmp_path):
+    """bench.py's JsonStdout: whatever a library prints to stdout while the bench runs (NCCL's version banner, C stdio
+    included) lands on stderr; the real stdout carries exactly the one JSON line of the contract."""
+    import json
+    import subprocess
+    script = tmp_path / "emit.py"
+    script.write_text(_EMIT)
+    r = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("\n") == 1 and json.loads(r.stdout) == {"metric": "m", "value": 1.5}
+    for noise in ("python noise", "NCCL version", "raw noise", "late noise"):
+        assert noise in r.stderr
