@@ -196,7 +196,9 @@ class JsonStdout:
 
     def emit(self, line):
         sys.stdout.flush()
-        os.write(self.fd, (line.rstrip("\n") + "\n").encode())
+        data = (line.rstrip("\n") + "\n").encode()
+        while data:
+            data = data[os.write(self.fd, data):]
 
 
 def run_ours(args):
