@@ -1,5 +1,5 @@
 // nodey_render -- headless offline render of a Nodey project file:
-//   nodey_render project.json [out.wav | out.mp3] [--gpu N] [--kbps K]
+//   nodey_render project.json [out.wav | out.mp3] [--gpu N] [--kbps K] [--diagnostics]
 // Sources are the WAV files named in the project's audio_input node; the sink writes a float WAV (*.wav) or, like
 // the reference's export, an MP3 through LAME (any other path; libmp3lame is bound at run time).
 #include "infra/graph.hpp"
@@ -19,16 +19,18 @@ int main(int argc, char** argv)
 {
 	if (argc < 2)
 	{
-		fprintf(stderr, "usage: %s project.json [out.wav | out.mp3] [--gpu N] [--kbps K]\n", argv[0]);
+		fprintf(stderr, "usage: %s project.json [out.wav | out.mp3] [--gpu N] [--kbps K] [--diagnostics]\n", argv[0]);
 		return 2;
 	}
 	std::string out_path;
 	int gpu = 0;
 	size_t kbps = 320;      // the editor's default (src/frontend/app.cpp:595)
+	bool diagnostics = false;   // print the overlay's Audio block (node states + device time per Runner step) to stderr
 	for (int i = 2; i < argc; i++)
 	{
 		if (!strcmp(argv[i], "--gpu") && i + 1 < argc) gpu = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--kbps") && i + 1 < argc) kbps = (size_t)std::max(8, atoi(argv[++i]));
+		else if (!strcmp(argv[i], "--diagnostics")) diagnostics = true;
 		else out_path = argv[i];
 	}
 	try
@@ -59,6 +61,7 @@ int main(int argc, char** argv)
 		auto runner = infra::Runner::create_and_run(graph, node_data);
 		runner->wait();
 		const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+		if (diagnostics) fputs(runner->diagnostics_text().c_str(), stderr);
 		const std::string err = runner->first_error();
 		if (!err.empty()) { fprintf(stderr, "render failed: %s\n", err.c_str()); return 1; }
 		double audio = 0;
