@@ -11,8 +11,9 @@ sites audio-amix.cpp:212-240).  Pinned here:
   * resampled values within 1e-6 absolute (signals of 0.4-0.57 peak; the bar of the task is 1e-5): the library
     itself has several summation orders (C template with two partial sums, SSE / AVX / FMA3 assembly with 4 / 8
     lanes), the oracle and the CUDA kernel fix one (single accumulator, ascending taps, fused multiply-add);
-  * the whole audio_amix loop (nb = min frame size, zero padding, flush iterations, sequential mix) and the
-    preview path's per-frame conversion to packed float.
+  * the whole audio_amix, audio_bimix and audio_bimix_v2 loops (nb = min frame size, zero padding, flush iterations,
+    sequential mix; bimix_v2's unflushed per-frame conversion, END-time stamps and pts aligner) and the preview path's
+    per-frame conversion to packed float.
 
 The live tests repeat the comparison against the library itself (C template and the assembly this CPU selects)
 where the image has it, and skip elsewhere."""
@@ -115,6 +116,36 @@ def test_bimix_loop_matches_real_library(orc, tag):
     exact = left[0] == 48000 and right[0] == 48000
     tol = 0.0 if exact else VALUE_TOL
     assert np.abs(l - gl).max() <= tol and np.abs(r - gr).max() <= tol
+
+
+GOLD2 = np.load(os.path.join(HERE, "golden", "swr_real_bimix2.npz"))
+
+
+@pytest.mark.parametrize("tag", sorted(G.BIMIX2_CASES))
+def test_bimix_v2_loop_matches_real_library(orc, tag):
+    """orc_bimix_v2 against an independent restatement of audio-bimix.cpp:536-875 run on real SwrContexts
+    (tests/golden/make_swr_golden.py: bimix_v2_real): per-frame conversion with capacity 2 * nb and no flush, mono
+    down-mix, END-time stamps, the pts aligner with its round()ed sample counts, tails with zeros on the other channel.
+    Stream length, first pts and the position of every zero exact; values within 1e-6 (bit exact at 48 kHz)."""
+    left, right, pl, pr = G.BIMIX2_CASES[tag]
+    tl = orc.make_track(G.case_input(orc, *left[:4], 70), left[1], left[0], frame_size=left[4], pts0=pl)
+    tr = orc.make_track(G.case_input(orc, *right[:4], 71), right[1], right[0], frame_size=right[4], pts0=pr)
+    out, pts = orc.bimix_v2(tl, tr)
+    gold = GOLD2[f"{tag}_out"]
+    assert out.shape == gold.shape == (int(GOLD2[f"{tag}_sizes"].sum()), 2), "stream length"
+    assert pts == float(GOLD2[f"{tag}_pts"]), "pts of the first frame"
+    assert np.array_equal(out == 0, gold == 0), "silent regions (alignment)"
+    exact = left[0] == 48000 and right[0] == 48000
+    assert np.abs(out - gold).max() <= (0.0 if exact else VALUE_TOL)
+
+
+def test_bimix_v2_fixture_is_what_the_library_produces_now():
+    from oracle import real_swr as R
+    if not R.available():
+        pytest.skip("no libswresample in this image")
+    live = G.generate_bimix2()
+    for k in GOLD2.files:
+        assert np.array_equal(live[k], GOLD2[k]), k
 
 
 @pytest.mark.parametrize("case", G.PREVIEW_CASES, ids=[c[0] for c in G.PREVIEW_CASES])
