@@ -200,3 +200,63 @@ def test_render_without_a_cuda_device_fails_loudly(eng):
         e.run()
     assert "No CUDA device" in x.value.message and "no CPU fallback" in x.value.message
     assert e.diagnostics().splitlines()[0] == "0 Running | 0 Finished | 3 Errors"
+
+
+def test_malformed_projects_are_rejected_not_crashed(eng):
+    """seeded fuzz of the project loader (json shim + Graph::deserialize + the nodes' deserialize): text-level damage
+    and structural damage (dangling link ends, unknown identifiers, wrong-typed info, huge ids) end in EngineError or
+    in a graph that still serialises -- never in a crash (a crash would take the test process down)"""
+    import random
+    rnd = random.Random(20261018)
+    p, _ = eng.config5_project(16, [1.0] * 16)
+    base = json.dumps(p.json())
+
+    def damage_text(s):
+        s = list(s)
+        for _ in range(rnd.randint(1, 6)):
+            k = rnd.randrange(len(s))
+            op = rnd.random()
+            if op < 0.3:
+                del s[k]
+            elif op < 0.6:
+                s.insert(k, rnd.choice('{}[]",:0123456789.-eE\\ntrufalse \x00\xff'))
+            elif op < 0.8:
+                s[k] = rnd.choice('{}[]",:0123456789.-eE\\ \t\n')
+            else:
+                j = rnd.randrange(len(s))
+                s[k:k] = s[j:j + rnd.randint(1, 40)]
+        return "".join(s)
+
+    def damage_structure(d):
+        d = json.loads(json.dumps(d))
+        nodes, links = d["nodes"], d["links"]
+        r = rnd.random()
+        if r < 0.2:
+            rnd.choice(links)["from"]["node"] = rnd.choice([-1, 999999, "x", None, 1.5])
+        elif r < 0.4:
+            rnd.choice(links)["to"]["pin"] = rnd.choice(["", "input_99", 5, None])
+        elif r < 0.6:
+            nodes[rnd.choice(list(nodes))]["identifier"] = rnd.choice(["", "nope", 3, None, "audio_input"])
+        elif r < 0.8:
+            nodes[rnd.choice(list(nodes))]["info"] = rnd.choice([[], 5, "s", {"input_num": -5}, {"input_num": 1e30}, {"pitch": "x"},
+                                                                  {"velocity": None}, {"file_path": 3}])
+        else:
+            nodes[str(rnd.choice([-1, 2 ** 31, 2 ** 40]))] = {"identifier": "audio_volume_adjust", "info": None, "position": {"x": "a"}}
+        return json.dumps(d)
+
+    loaded = rejected = 0
+    for i in range(300):
+        text = damage_text(base) if i % 2 else damage_structure(p.json())
+        try:
+            e = eng.Engine(text)
+        except eng.EngineError:
+            rejected += 1
+            continue
+        try:
+            e.check()
+        except eng.EngineError:
+            pass
+        json.loads(e.serialize())
+        e.close()
+        loaded += 1
+    assert rejected > 150 and loaded + rejected == 300
