@@ -118,6 +118,42 @@ def test_bimix_loop_matches_real_library(orc, tag):
     assert np.abs(l - gl).max() <= tol and np.abs(r - gr).max() <= tol
 
 
+GOLD3 = np.load(os.path.join(HERE, "golden", "swr_real_amix_capped.npz"))
+
+
+def test_amix_loop_where_capped_conversion_yields_one_more_sample(orc):
+    """audio_amix with nb = 64 next to an 88.2 kHz input cut into 3561-sample frames: the real library hands the surplus
+    out over 160 later calls and returns 10213 samples in total, one MORE than a conversion with ample capacity (10212).
+    The oracle node and the host-side plan of the CUDA engine (nodey_amix_plan) follow the loop, not the whole-stream
+    count: stream length and zero positions exact, values within 1e-6."""
+    import nodey
+    tag = "amix4_capped_surplus"
+    spec, vols = G.AMIX_CAPPED_CASES[tag]
+    assert int(GOLD3[f"{tag}_capped_total"]) == int(GOLD3[f"{tag}_whole_total"]) + 1 == 10213
+    xs = [G.case_input(orc, r, f, c, n, 40 + i) for i, (r, f, c, n, fr) in enumerate(spec)]
+    tracks = [orc.make_track(x, f, r, frame_size=fr) for x, (r, f, c, n, fr) in zip(xs, spec)]
+    l, r_ = orc.amix(tracks, vols)
+    gl, gr = GOLD3[f"{tag}_l"], GOLD3[f"{tag}_r"]
+    assert len(l) == len(gl) == int(GOLD3[f"{tag}_nb"].sum())
+    assert np.array_equal(l == 0, gl == 0) and np.array_equal(r_ == 0, gr == 0)
+    assert np.abs(l - gl).max() <= VALUE_TOL and np.abs(r_ - gr).max() <= VALUE_TOL
+    # whole-stream model of that input: one sample short of what the loop places
+    whole, _ = orc.swr_whole(xs[2], orc.FMT_FLT, 88200, 48000, flush=True)
+    assert len(whole) == 10212
+    total, segs, runs = nodey.amix_plan([s[0] for s in spec], [nodey.uniform_runs(s[3], s[4]) for s in spec])
+    assert total == len(gl) and sum(a * b for a, b in runs) == total
+    assert [seg for seg in segs if seg[0] == 2] == [(2, 0, 0, 10213)]
+
+
+def test_amix_capped_fixture_is_what_the_library_produces_now():
+    from oracle import real_swr as R
+    if not R.available():
+        pytest.skip("no libswresample in this image")
+    live = G.generate_amix_capped()
+    for k in GOLD3.files:
+        assert np.array_equal(live[k], GOLD3[k]), k
+
+
 GOLD2 = np.load(os.path.join(HERE, "golden", "swr_real_bimix2.npz"))
 
 
