@@ -226,7 +226,13 @@ def amix(tracks, volumes, quirk=0):
 
 
 def bimix(tl, tr, bias, quirk=0):
-    cap = max(int(t.nframes * 48000 // t.rate) for t in (tl, tr)) + 8 * 4096
+    # the loop emits 1152 samples per iteration while both inputs still have a frame, whatever the frame size
+    # (audio-bimix.cpp:174-181), so tiny frames make the stream far longer than the resampled inputs
+    def iterations(t):
+        if t.nruns:
+            return sum(int(t.run_count[k]) for k in range(t.nruns))
+        return -(-int(t.nframes) // max(int(t.frame_size), 1))
+    cap = max(int(t.nframes * 48000 // t.rate) for t in (tl, tr)) + 1152 * (max(iterations(tl), iterations(tr)) + 64) + 8 * 4096
     ol = np.zeros(cap, np.float32); orr = np.zeros(cap, np.float32)
     n = lib().orc_bimix(C.byref(tl), C.byref(tr), np.float32(bias), quirk, _p(ol), _p(orr), cap)
     return ol[:n], orr[:n]
