@@ -630,7 +630,10 @@ static int64_t plan_pos_index(const nodey_resampler* r, int64_t k)
 static int64_t plan_producible(const nodey_resampler* r, int64_t n, int64_t reflect)
 {
     const int64_t L = r->filter_length, P = r->phase_count, center = (L - 1) / 2;
-    if (n < L + 1) return 0;
+    // invert_initial_buffer() waits for filter_length + 1 samples, and the samples resample_flush() reflects count: a
+    // stream a little shorter than the filter (22..32 frames at 32 taps) gets there at the flush and does produce output
+    // (pinned against the real library: tests/test_swr_real.py::test_streams_shorter_than_the_filter)
+    if (n + reflect < L + 1) return 0;
     const int64_t max_s = n + reflect - L + center;
     if (max_s < 0) return 0;
     int64_t lo = 0, hi = (max_s + 2) * P / (r->dst_incr_div > 0 ? r->dst_incr_div : 1) + 4;
@@ -643,7 +646,7 @@ static int64_t plan_producible(const nodey_resampler* r, int64_t n, int64_t refl
 
 static int64_t plan_reflect(const nodey_resampler* r, int64_t n, int64_t produced)
 {
-    if (n < r->filter_length + 1) return 0;
+    if (n < r->filter_length + 1) return (n + 1) / 2;      // nothing consumed yet: in_buffer_count is the whole input
     const int64_t wstart = plan_pos_index(r, produced) / r->phase_count - (r->filter_length - 1) / 2;
     int64_t held = n - wstart;
     if (held > r->filter_length) held = r->filter_length;

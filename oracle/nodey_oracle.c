@@ -400,7 +400,10 @@ static int64_t swr_producible(const orc_swr* s)
 {
     const int64_t L = s->filter_length, P = s->phase_count;
     const int64_t center = (L - 1) / 2;
-    if (s->n_in < L + 1) return 0;                  /* invert_initial_buffer() still waiting */
+    /* invert_initial_buffer() waits until filter_length + 1 samples are there; the samples resample_flush() reflects
+     * count (a stream of 22..32 frames at 32 taps gets its 33 samples that way and DOES produce output at the flush:
+     * pinned against the real library, tests/test_swr_real.py::test_streams_shorter_than_the_filter) */
+    if (s->n_in + s->reflect < L + 1) return 0;
     /* window of output k starts at sample s_k - center; it must end inside n_in + reflect */
     const int64_t max_s = s->n_in + s->reflect - L + center;   /* s_k <= max_s */
     if (max_s < 0) return 0;
@@ -431,7 +434,10 @@ int orc_swr_convert(orc_swr* s, float* out_l, float* out_r, int out_count, const
             /* resample_flush(): reflection = (min(in_buffer_count, filter_length) + 1) / 2 where
              * in_buffer_count = samples from the next window start to the end of input */
             s->flushed = 1;
-            if (s->n_in >= s->filter_length + 1) {
+            if (s->n_in < s->filter_length + 1) {
+                /* nothing has been consumed yet: in_buffer_count is the whole input */
+                s->reflect = (s->n_in + 1) / 2;
+            } else {
                 int64_t idx; int fr; swr_pos(s, s->produced, &idx, &fr);
                 const int64_t wstart = idx / s->phase_count - (s->filter_length - 1) / 2;
                 int64_t held = s->n_in - wstart;
@@ -504,7 +510,10 @@ int64_t orc_swr_out_count(int in_rate, int out_rate, int quirk, int64_t in_frame
     else {
         s->n_in = in_frames;
         r = swr_producible(s);
-        if (do_flush && in_frames >= s->filter_length + 1) {
+        if (do_flush && in_frames < s->filter_length + 1) {
+            s->reflect = (in_frames + 1) / 2;
+            r = swr_producible(s);
+        } else if (do_flush) {
             int64_t idx; int fr; swr_pos(s, r, &idx, &fr);
             int64_t held = in_frames - (idx / s->phase_count - (s->filter_length - 1) / 2);
             if (held > s->filter_length) held = s->filter_length;

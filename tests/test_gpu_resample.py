@@ -47,7 +47,9 @@ def test_resample_other_rates_bit_exact(nd, orc, rates, flush):
     assert_bit_equal(got[1], rr, "resample R")
 
 
-@pytest.mark.parametrize("n", [0, 1, 32, 33, 34, 100, 147, 4704, 4705])
+# 21 frames: the longest stream that never produces anything (even its flush reflection stays below filter_length + 1
+# samples); 22..32 frames produce output at the flush -- that regime has its own file, tests/test_gpu_zz_short_streams.py
+@pytest.mark.parametrize("n", [0, 1, 21, 33, 34, 100, 147, 4704, 4705])
 def test_resample_short_inputs(nd, orc, n):
     if n == 0:
         r = nd.Resampler(44100, 48000)

@@ -118,6 +118,44 @@ def test_bimix_loop_matches_real_library(orc, tag):
     assert np.abs(l - gl).max() <= tol and np.abs(r - gr).max() <= tol
 
 
+GOLD4 = np.load(os.path.join(HERE, "golden", "swr_real_short.npz"))
+
+
+@pytest.mark.parametrize("rate", G.SHORT_RATES)
+def test_streams_shorter_than_the_filter(orc, rate):
+    """How many samples a whole stream of 1..80 frames yields (flush included), against the real library: nothing while
+    the stream plus its flush reflection stays below filter_length + 1 samples (1..21 frames at 32 taps), output at the
+    flush for 22..32 frames, the normal path from 33 on; longer filters (rates above 48 kHz) shift the thresholds."""
+    gold = GOLD4[f"short_counts_{rate}"]
+    got = [orc.swr_out_count(rate, 48000, n, True) for n in range(1, G.SHORT_MAX + 1)]
+    assert got == gold.tolist()
+    whole = [len(orc.swr_whole(G.case_input(orc, rate, 3, 2, n, 90), 3, rate, 48000, flush=True)[0]) for n in range(1, G.SHORT_MAX + 1)]
+    assert whole == gold.tolist()
+    if rate == 44100:
+        assert gold[20] == 0 and gold[21] == 19 and gold[31] == 35 and gold[32] == 36      # 21 / 22 / 32 / 33 frames
+
+
+@pytest.mark.parametrize("case", G.SHORT_VALUE_CASES, ids=[f"{c[0]}_{c[1]}_{c[2]}_{c[3]}" for c in G.SHORT_VALUE_CASES])
+def test_values_of_streams_shorter_than_the_filter(orc, case):
+    """the samples such a stream yields come from a buffer mirrored at BOTH ends (the initial mirror reads reflected
+    tail samples): frame-by-frame feed (7-sample frames), values within 1e-6 of the real library"""
+    rate, fmt, ch, n = case
+    x = G.case_input(orc, rate, fmt, ch, n, 91)
+    c = orc.Swr(rate, 48000, fmt, ch)
+    L, R_ = [], []
+    for fr in G.frames_of(x, fmt, 7):
+        l, r = c.convert(fr, 4096)
+        L.append(l); R_.append(r)
+    for _ in range(4):
+        l, r = c.convert(None, 4096)
+        L.append(l); R_.append(r)
+    l, r = np.concatenate(L), np.concatenate(R_)
+    gl, gr = GOLD4[f"short_{rate}_{fmt}_{ch}_{n}_l"], GOLD4[f"short_{rate}_{fmt}_{ch}_{n}_r"]
+    assert len(l) == len(gl) > 0
+    tol = VALUE_TOL if rate != 47999 else 1e-5
+    assert np.abs(l - gl).max() <= tol and np.abs(r - gr).max() <= tol
+
+
 GOLD3 = np.load(os.path.join(HERE, "golden", "swr_real_amix_capped.npz"))
 
 
