@@ -58,6 +58,12 @@ def resample_segment(plan, n_in, total_out, k0, k1):
         need = max(s_last - center + L, L + 1)
         if in0 + need <= n_in:
             in1, flush = in0 + need, False
+    # a conversion cannot start before filter_length + 1 frames are there (the initial mirror): a slice that runs to the
+    # end of a short stream and is shorter than that starts more whole periods early (tiny streams cut into many segments)
+    if in0 > 0 and in1 - in0 < L + 1:
+        lead += -(-((L + 1) - (in1 - in0)) // D)
+        in0 = 0 if periods <= lead else (periods - lead) * D
+        skip = k0 if periods <= lead else lead * P
     return dict(in0=in0, in1=in1, skip=skip, flush=flush)
 
 

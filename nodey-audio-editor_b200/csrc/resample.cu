@@ -1031,6 +1031,13 @@ int nodey_resampler_segment(const nodey_resampler* r, int64_t n_in, int64_t k0, 
         if (need < L + 1) need = L + 1;
         if (*in0 + need <= n_in) { *in1 = *in0 + need; *flush = 0; }
     }
+    // a conversion cannot start before filter_length + 1 frames are there (the initial mirror): a slice that runs to the
+    // end of a short stream and is shorter than that starts more whole periods early (tiny streams cut into many segments)
+    if (*in0 > 0 && *in1 - *in0 < L + 1) {
+        lead += ((L + 1) - (*in1 - *in0) + D - 1) / D;
+        *in0 = periods <= lead ? 0 : (periods - lead) * D;
+        *skip = periods <= lead ? k0 : lead * P;
+    }
     return NODEY_OK;
 }
 
