@@ -253,6 +253,23 @@ int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_str
                                 int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                                 int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);
 
+/* The same render cut into launches along time, so that a consumer can start before the producer has finished (the
+ * reference pipelines its nodes frame by frame, audio-velocity.cpp:286-441; here the unit is a chunk of WSOLA sequences):
+ * nodey_soundtouch_chunks plans at most want_chunks launches and returns how many there are (1 for the paths that
+ * cannot be cut: mono, rate <= 1); chunk c may run once input frames [0, in_need[c]) are final and makes output frames
+ * [0, out_ready[c]) final (the last chunk needs / makes everything).  run_chunk / run_tracks_chunk are run / run_tracks
+ * restricted to chunk `chunk` of `nchunks`; chunks run in order on one stream, with the SAME arguments, and `offsets`
+ * (required here: n_sequences - 1 ints per track, device) carries the chain from one chunk to the next.  The result is
+ * bit identical to the one-launch render. */
+int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t out_frames, int want_chunks,
+                            int64_t* in_need, int64_t* out_ready, int cap);
+int nodey_soundtouch_run_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
+                               int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream);
+int nodey_soundtouch_run_tracks_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
+                                      int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream);
+
 /* N2  audio_spectrum (new node; FFTW r2c convention, unnormalised):
  * per channel, frame m = x[m*hop .. m*hop+nfft) * periodic Hann; out[ch][m][0..nfft/2] complex64
  * (re, im interleaved).  interleaved != 0: sample f of channel c at x[f*nch + c]; otherwise planar

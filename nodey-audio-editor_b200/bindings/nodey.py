@@ -24,7 +24,7 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
@@ -96,6 +96,9 @@ def lib():
     L.nodey_soundtouch_set_unfused.argtypes = [vp, i32]
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
     L.nodey_soundtouch_run_tracks.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, vp]
+    L.nodey_soundtouch_chunks.argtypes = [vp, i64, i32, i64, i32, C.POINTER(i64), C.POINTER(i64), i32]
+    L.nodey_soundtouch_run_chunk.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, i32, i32, vp]
+    L.nodey_soundtouch_run_tracks_chunk.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, i32, i32, vp]
     L.nodey_amix_plan.argtypes = [C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32,
                                   C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64),
                                   C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64)]
@@ -480,6 +483,34 @@ class SoundTouch:
         if n < 0:
             raise NodeyError(n, "nodey_soundtouch_out_frames")
         return n, nseq.value
+
+    def chunks(self, in_frames, frame_size=1152, want=8):
+        """[(in_need, out_ready), ...]: chunk c may run once in_need input frames are final and makes out_ready output frames final"""
+        m, _ = self.out_frames(in_frames, frame_size)
+        a = (C.c_int64 * max(want, 1))(); b = (C.c_int64 * max(want, 1))()
+        n = lib().nodey_soundtouch_chunks(self.h, in_frames, frame_size, m, want, a, b, max(want, 1))
+        if n < 0:
+            raise NodeyError(n, "nodey_soundtouch_chunks")
+        return [(a[k], b[k]) for k in range(n)]
+
+    def run_chunked(self, x, nchunks, frame_size=1152, out=None, poison=None):
+        """the render of run() cut into nchunks launches (nodey_soundtouch_run_chunk).  x: [ntracks, frames, ch].
+        poison(c, in_need): optional hook called before chunk c (tests overwrite the input beyond in_need to prove that the
+        chunk does not read it).  Returns (out, offsets, chunk plan)."""
+        t = _torch()
+        assert x.dim() == 3 and x.is_contiguous() and x.shape[2] == self.ch
+        ntr, n, ch = x.shape
+        m, nseq = self.out_frames(n, frame_size)
+        plan = self.chunks(n, frame_size, nchunks)
+        if out is None:
+            out = t.empty((ntr, m, ch), dtype=t.float32, device=x.device)
+        offs = t.zeros((ntr, max(nseq - 1, 1)), dtype=t.int32, device=x.device)
+        for c in range(len(plan)):
+            if poison is not None:
+                poison(c, plan[c][0])
+            check(lib().nodey_soundtouch_run_chunk(self.h, _dp(out), out.stride(0), _dp(x), x.stride(0), ntr, n, frame_size, m,
+                                                   _dp(offs), offs.stride(0), c, len(plan), _stream()))
+        return out, offs[:, :max(nseq - 1, 0)], plan
 
     def run(self, x, frame_size=1152, want_offsets=False, out=None):
         """x: [ntracks, frames, ch] or [frames, ch] float32 (interleaved). Returns same rank."""

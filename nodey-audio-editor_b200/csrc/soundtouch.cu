@@ -33,6 +33,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -114,6 +115,8 @@ struct TdsArgs {
     int ncand_pad;             // padded candidates per CTA (correlation lane sums)
     int npm;                   // padded start positions per CTA (norm sums)
     int vec8;                  // stereo frames are 8-byte aligned in global memory
+    int seq_begin, seq_end;    // this launch searches sequences [seq_begin, seq_end) (1 <= seq_begin): a track's chain can be
+                               // cut into several launches; the only carried state is the previous offset, read from offs[]
 };
 
 // partial-sum slot of candidate cc: one word of padding per K*KT candidates makes both the strided
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         }
     };
 
-    if (a.nseq <= 1) return;                         // uniform over the cluster: nobody touches a peer
+    if (a.seq_end <= a.seq_begin) return;            // uniform over the cluster: nobody touches a peer
 
     // position weights (sequence independent): 1 - 0.25 t^2, t = (2c - L) / L
     for (int cc = tid; cc < ncand; cc += blockDim.x) {
@@ -345,30 +348,35 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
         PW[cc] = __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp));
     }
-    window_copy(1, X0);
-    mid_region_copy(a.pos[0] + temp);                // first sequence: offset 0, no search
+    window_copy(a.seq_begin, X0);
+    int moff = 0;                                    // offset of the mid buffer inside the staged region
+    if (a.seq_begin == 1) mid_region_copy(a.pos[0] + temp);       // first sequence: offset 0, no search
+    else {
+        // continuing a chain: the mid buffer was cut at the previous sequence's offset (written by the launch before)
+        mid_region_copy(a.pos[a.seq_begin - 1] + ovl + temp);
+        moff = offs[a.seq_begin - 2];
+    }
     cp_async_wait_all();
     __syncthreads();
     norm_units(X0);
     int cur = 0;
-    int moff = 0;                                    // offset of the mid buffer inside the staged region
 #ifdef NODEY_TDS_TIMING
     const bool timing_on = blockIdx.x == 0 && tid == 0;
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
 #endif
 
-    for (int i = 1; i < a.nseq; i++) {
+    for (int i = a.seq_begin; i < a.seq_end; i++) {
         const long long p0 = a.pos[i];
         const float* X = X0 + cur * 4 * plane_len;
         // ---- mid buffer: gathered from the staged region, de-interleaved by lane ----
         for (int j = tid; j < 4 * Q; j += blockDim.x) Y[(j & 3) * QP + (j >> 2)] = MR[moff * CH + j];
-        if (i + 1 < a.nseq) window_copy(i + 1, X0 + (cur ^ 1) * 4 * plane_len);
-        l2_prefetch(i + 2);
+        if (i + 1 < a.seq_end) window_copy(i + 1, X0 + (cur ^ 1) * 4 * plane_len);
+        if (i + 2 < a.seq_end) l2_prefetch(i + 2);
         TDS_T(0);
         __syncthreads();
         TDS_T(1);
-        if (i + 1 < a.nseq) mid_region_copy(p0 + ovl + temp);     // the region is free again: everybody has gathered
+        if (i + 1 < a.seq_end) mid_region_copy(p0 + ovl + temp);  // the region is free again: everybody has gathered
 
         // ---- correlation lane sums: thread = (lane l, class kappa, KT consecutive candidates of the class) ----
         for (int unit = warp; unit < nunits; unit += nwarps) {
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         cp_async_wait_all();
         __syncthreads();
         cur ^= 1;
-        if (i + 1 < a.nseq) norm_units(X0 + cur * 4 * plane_len);
+        if (i + 1 < a.seq_end) norm_units(X0 + cur * 4 * plane_len);
         if (CL > 1) {
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
             fk = xch_k[par][0]; fi = xch_i[par][0];
@@ -690,6 +698,7 @@ struct PostArgs {
     float h[kAaLen];
     unsigned long long R; int e;
     float* out; long long out_stride; long long count;     // final frames to write
+    long long tile_begin, tile_end;                         // this launch covers tiles [tile_begin, tile_end)
 };
 
 constexpr int kPostStride = kFirTileS - 8;        // FIR outputs a tile contributes to the cubic stage
@@ -739,7 +748,7 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
 
     const double inv_rate = (double)(1ull << a.e) / (double)a.R;
     // tiles until the last cubic read position is covered
-    for (long long t = blockIdx.x;; t += gridDim.x) {
+    for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
         const long long n0 = t * kPostStride;
         // cubic outputs whose read position lies in [n0, n0 + kPostStride): i in [i_lo, i_hi)
         long long i_lo = cubic_first_at(n0, a.R, a.e, inv_rate);
@@ -889,10 +898,12 @@ struct nodey_soundtouch {
     int force_unfused = 0;                     // test hook: separate assemble / FIR / cubic kernels
     float aa[kAaLen];
     float* d_fade = nullptr;
-    // sequence start positions (prefix-stable in the input length): grown on demand
-    std::vector<long long> pos;
-    long long pos_valid_for = -1;              // input length the table was built for
-    long long* d_pos = nullptr; size_t d_pos_cap = 0;
+    int device = 0;                            // the plan's tables live on the device that was current at create
+    // Sequence start positions on the device, one IMMUTABLE table per TDStretch input length: a table is uploaded
+    // once on the stream of the call that needs it first and never rewritten or freed while the plan lives, so calls
+    // on other streams (the Runner's lanes share cached plans) only have to wait for its upload event.
+    struct PosTable { long long* d = nullptr; std::vector<long long> host; cudaEvent_t ready = nullptr; };
+    std::map<long long, PosTable*> tables;
     std::mutex mu;
 };
 
@@ -999,6 +1010,7 @@ int nodey_soundtouch_create(nodey_soundtouch** out, int sample_rate, int channel
     NODEY_REQUIRE(rate_arg > 0.f && pitch_arg > 0.f, NODEY_E_RANGE, "nodey_soundtouch_create: rate and pitch must be positive");
     nodey_soundtouch* s = new nodey_soundtouch();
     s->sample_rate = sample_rate; s->ch = channels;
+    if (cudaGetDevice(&s->device) != cudaSuccess) { cudaGetLastError(); s->device = 0; }
     const double vrate = (double)rate_arg, vpitch = (double)pitch_arg;
     s->tempo = 1.0 / vpitch;              // virtualTempo = 1
     s->rate = vpitch * vrate;
@@ -1104,7 +1116,7 @@ void nodey_soundtouch_destroy(nodey_soundtouch* s)
 {
     if (!s) return;
     if (s->d_fade) cudaFree(s->d_fade);
-    if (s->d_pos) cudaFree(s->d_pos);
+    for (auto& [n, t] : s->tables) { if (t->ready) cudaEventDestroy(t->ready); if (t->d) cudaFree(t->d); delete t; }
     delete s;
 }
 
@@ -1131,12 +1143,105 @@ int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int 
     return total;
 }
 
+}  // extern "C"
+
+namespace {
+
+// the device copy of the sequence positions for a TDStretch input of `tds_in` frames (see nodey_soundtouch::tables)
+int position_table(nodey_soundtouch* s, long long tds_in, const std::vector<long long>& pos, cudaStream_t st, const long long** d_out)
+{
+    auto it = s->tables.find(tds_in);
+    if (it == s->tables.end()) {
+        if (s->tables.size() >= 64) {
+            // a plan that has seen this many different lengths: nothing may still be reading the old tables after a
+            // device-wide wait, so they can go (never happens in a render: a cached plan is keyed by its input length)
+            NODEY_CUDA_OK(cudaDeviceSynchronize());
+            for (auto& [n, t] : s->tables) { if (t->ready) cudaEventDestroy(t->ready); if (t->d) cudaFree(t->d); delete t; }
+            s->tables.clear();
+        }
+        auto* t = new nodey_soundtouch::PosTable();
+        t->host = pos;
+        if (t->host.empty()) t->host.push_back(0);
+        cudaError_t e = cudaMalloc((void**)&t->d, sizeof(long long) * t->host.size());
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(t->d, t->host.data(), sizeof(long long) * t->host.size(), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(t->ready, st);
+        if (e != cudaSuccess) {
+            if (t->ready) cudaEventDestroy(t->ready);
+            if (t->d) cudaFree(t->d);
+            delete t;
+            return cuda_fail(e, "sequence position table upload", __FILE__, __LINE__);
+        }
+        it = s->tables.emplace(tds_in, t).first;
+    }
+    NODEY_CUDA_OK(cudaStreamWaitEvent(st, it->second->ready, 0));     // no-op on the uploading stream, orders every other one
+    *d_out = it->second->d;
+    return NODEY_OK;
+}
+
+// How a render is cut into `nchunks` launches (fused stereo TDStretch-first path): chunk c searches sequences
+// [seq_begin, seq_end) and then runs the tail over the tiles whose TDStretch frames are final by then.
+struct ChunkPlan { int seq_begin, seq_end; long long tile_begin, tile_end, in_need, out_ready; };
+
+long long post_tiles_total(const StageLens& L) { return (L.l2 + kPostStride - 1) / kPostStride + 1; }
+
+bool chunkable(const nodey_soundtouch* s) { return s->td_first && s->ch == 2 && !s->force_unfused; }
+
+int effective_chunks(const nodey_soundtouch* s, const StageLens& L, int want)
+{
+    if (!chunkable(s) || want <= 1) return 1;
+    const long long nsearch = L.nseq - 1;
+    long long n = nsearch / 32;                 // at least 32 sequences per launch
+    if (n > want) n = want;
+    return n < 1 ? 1 : (int)n;
+}
+
+void chunk_plan(const nodey_soundtouch* s, const StageLens& L, const std::vector<long long>& pos, long long in_frames, long long out_frames,
+                int c, int nchunks, ChunkPlan* cp)
+{
+    const long long nsearch = L.nseq > 1 ? L.nseq - 1 : 0;
+    const auto seq_end_of = [&](int k) { return (int)(1 + (nsearch * (k + 1) + nchunks - 1) / nchunks); };
+    const long long tiles = post_tiles_total(L);
+    const int temp = s->seek_window - 2 * s->overlap, hop = s->seek_window - s->overlap;
+    const auto tile_end_of = [&](int k) -> long long {
+        if (k >= nchunks - 1) return tiles;
+        if (k < 0) return 0;
+        // TDStretch frames [0, temp + (seq_end - 1) * hop) are final; tile t reads frames up to t * stride - prefill + 2 * kFirChunks - 1
+        const long long avail = (long long)temp + (long long)(seq_end_of(k) - 1) * hop;
+        const long long room = avail + s->prefill - 2ll * kFirChunks;
+        long long t = room < 0 ? 0 : room / kPostStride + 1;
+        return t > tiles ? tiles : t;
+    };
+    cp->seq_begin = c == 0 ? 1 : seq_end_of(c - 1);
+    cp->seq_end = seq_end_of(c);
+    if (L.nseq <= 1) { cp->seq_begin = 1; cp->seq_end = 1; }
+    cp->tile_begin = tile_end_of(c - 1);
+    cp->tile_end = tile_end_of(c);
+    if (c >= nchunks - 1) { cp->in_need = in_frames; cp->out_ready = out_frames; return; }
+    // input: the search of sequence i reads its window and the region the next mid buffer comes from, the tail reads the
+    // sequence itself: all below pos[i] + seek_window + seek_length
+    long long need = (cp->seq_end >= 2 ? pos[(size_t)cp->seq_end - 1] : 0) + s->seek_window + s->seek_length + 8;
+    cp->in_need = need < in_frames ? need : in_frames;
+    // output: cubic outputs whose read position lies below tile_end * stride, i.e. i < ceil(tile_end * stride * 2^e / R)
+    const unsigned __int128 num = (unsigned __int128)(cp->tile_end * (long long)kPostStride) << s->e;
+    long long ready = (long long)((num + s->R - 1) / s->R);
+    cp->out_ready = ready < out_frames ? ready : out_frames;
+}
+
+}  // namespace
+
+// chunk < 0: the whole render in one go (nchunks ignored)
 static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride, const TrackTab* tab,
                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                               int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
 {
     NODEY_REQUIRE(s && out && (in || tab), NODEY_E_INVALID, "nodey_soundtouch_run: null argument");
     NODEY_REQUIRE(ntracks >= 1 && in_frames >= 0 && frame_size > 0, NODEY_E_INVALID, "nodey_soundtouch_run: bad size");
+    {
+        int dev = -1;
+        NODEY_CUDA_OK(cudaGetDevice(&dev));
+        NODEY_REQUIRE(dev == s->device, NODEY_E_INVALID, "nodey_soundtouch_run: plan belongs to device %d, current device is %d", s->device, dev);
+    }
     std::lock_guard<std::mutex> lock(s->mu);
     cudaStream_t st = as_stream(stream);
     StageLens L;
@@ -1147,17 +1252,23 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
     if (out_frames == 0) return NODEY_OK;
     NODEY_REQUIRE(L.nseq >= 1, NODEY_E_INVALID, "nodey_soundtouch_run: internal: output without a sequence");
     NODEY_REQUIRE(offsets == nullptr || offsets_stride >= L.nseq - 1, NODEY_E_INVALID, "nodey_soundtouch_run: offsets_stride too small");
+    ChunkPlan cp;
+    if (chunk >= 0) {
+        NODEY_REQUIRE(offsets, NODEY_E_INVALID, "nodey_soundtouch_run_chunk: the offset trace must be caller-owned (it carries the chain from chunk to chunk)");
+        NODEY_REQUIRE(nchunks >= 1 && chunk < nchunks && nchunks == effective_chunks(s, L, nchunks), NODEY_E_RANGE,
+                      "nodey_soundtouch_run_chunk: chunk %d of %d is not a chunking nodey_soundtouch_chunks returned", chunk, nchunks);
+        chunk_plan(s, L, pos, in_frames, out_frames, chunk, nchunks, &cp);
+    } else {
+        cp.seq_begin = 1; cp.seq_end = (int)L.nseq; cp.tile_begin = 0; cp.tile_end = post_tiles_total(L);
+        cp.in_need = in_frames; cp.out_ready = out_frames;
+    }
+    const bool fused = chunkable(s);
+    NODEY_REQUIRE(chunk < 0 || fused || nchunks == 1, NODEY_E_RANGE, "nodey_soundtouch_run_chunk: only the fused stereo path runs in chunks");
 
-    // sequence positions on the device (re-uploaded only when the table changed)
-    if (pos != s->pos || !s->d_pos) {
-        if (pos.size() > s->d_pos_cap) {
-            if (s->d_pos) cudaFree(s->d_pos);
-            s->d_pos = nullptr;
-            s->d_pos_cap = pos.size() + pos.size() / 4 + 64;
-            NODEY_CUDA_OK(cudaMalloc((void**)&s->d_pos, sizeof(long long) * s->d_pos_cap));
-        }
-        s->pos = pos;
-        NODEY_CUDA_OK(cudaMemcpyAsync(s->d_pos, s->pos.data(), sizeof(long long) * s->pos.size(), cudaMemcpyHostToDevice, st));
+    const long long* d_pos = nullptr;
+    {
+        const int rc = position_table(s, L.tds_in, pos, st, &d_pos);
+        if (rc != NODEY_OK) return rc;
     }
 
     const int CH = s->ch;
@@ -1169,25 +1280,26 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
     const long long s1 = ((L.l1 * CH + 3) & ~3ll) + 4, s2 = ((L.l2 * CH + 3) & ~3ll) + 4;
     float* ws = nullptr;
     int* ws_offs = nullptr;
-    {
+    if (!fused) {
         const int rc = device_alloc((void**)&ws, sizeof(float) * (size_t)((s1 + s2) * ntracks), st);
         if (rc != NODEY_OK) return rc;
     }
     if (!offsets) {
         const int rc = device_alloc((void**)&ws_offs, sizeof(int) * (size_t)(offs_stride_ws * ntracks), st);
-        if (rc != NODEY_OK) { device_free(ws, st); return rc; }
+        if (rc != NODEY_OK) { if (ws) device_free(ws, st); return rc; }
         d_offs = ws_offs;
     }
     float* b1 = ws;
-    float* b2 = ws + s1 * ntracks;
+    float* b2 = ws ? ws + s1 * ntracks : nullptr;
 
-    auto run_offsets = [&](View vin) -> int {
+    auto run_offsets = [&](View vin, int seq_begin, int seq_end) -> int {
         TdsArgs ta;
         ta.in = vin; if (vin.use_tab) ta.tt = *tab;
-        ta.pos = s->d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
+        ta.pos = d_pos; ta.offs = d_offs; ta.offs_stride = offs_stride; ta.nseq = (int)nseq;
+        ta.seq_begin = seq_begin; ta.seq_end = seq_end;
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
         ta.Q = 4 * (CH * s->overlap / 16);
-        if (nseq > 1) {
+        if (seq_end > seq_begin) {
             // cluster size: spread one track over CL SMs while the batch leaves SMs idle.  From the measured batch
             // sweep (tools/st_sweep.py, 256-thread CTAs, two per SM): 4 CTAs per track up to about 40 tracks (one CTA
             // per SM), 2 up to about 200 tracks, 1 beyond
@@ -1236,11 +1348,11 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
         return NODEY_OK;
     };
     auto run_tds = [&](View vin, float* dst, long long dst_stride, long long dst_cap) -> int {
-        const int rc0 = run_offsets(vin);
+        const int rc0 = run_offsets(vin, 1, (int)nseq);
         if (rc0 != NODEY_OK) return rc0;
         AsmArgs aa;
         aa.in = vin; if (vin.use_tab) aa.tt = *tab;
-        aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = s->d_pos;
+        aa.out = dst; aa.out_stride = dst_stride; aa.out_cap = dst_cap; aa.pos = d_pos;
         aa.offs = d_offs; aa.offs_stride = offs_stride; aa.fade = s->d_fade; aa.nseq = (int)nseq;
         aa.overlap = s->overlap; aa.seek_window = s->seek_window;
         dim3 grid((unsigned)nseq, (unsigned)ntracks);
@@ -1274,18 +1386,24 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
     };
 
     int rc = NODEY_OK;
-    if (s->td_first && CH == 2 && !s->force_unfused) {
-        // offsets, then the fused assemble + FIR + cubic tail
+    if (fused) {
+        // offsets, then the fused assemble + FIR + cubic tail, both over this chunk's range
         View v0{in, in_frames, 0, in_stride, tab ? 1 : 0};
-        rc = run_offsets(v0);
-        if (rc == NODEY_OK) {
+        if (chunk >= 0 && nchunks > 1 && chunk == 0) {
+            // the tail's interior fast path looks at the offsets of the next sequences before it knows whether it needs
+            // them: give the not yet searched ones a defined value
+            NODEY_CUDA_OK(cudaMemsetAsync(d_offs, 0, sizeof(int) * (size_t)offs_stride * (size_t)ntracks, st));
+        }
+        rc = run_offsets(v0, cp.seq_begin, cp.seq_end);
+        if (rc == NODEY_OK && cp.tile_end > cp.tile_begin) {
             PostArgs pa;
             pa.in = v0; if (v0.use_tab) pa.tt = *tab;
-            pa.pos = s->d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
+            pa.pos = d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
             pa.nseq = (int)nseq; pa.overlap = s->overlap; pa.seek_window = s->seek_window; pa.prefill = s->prefill; pa.l1 = L.l1;
             memcpy(pa.h, s->aa, sizeof(pa.h));
             pa.R = s->R; pa.e = s->e; pa.out = out; pa.out_stride = out_stride; pa.count = out_frames;
-            const long long tiles = (L.l2 + kPostStride - 1) / kPostStride + 1;
+            pa.tile_begin = cp.tile_begin; pa.tile_end = cp.tile_end;
+            const long long tiles = cp.tile_end - cp.tile_begin;
             const long long cap = (long long)sm_count() * 4;
             dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)ntracks);
             NODEY_LAUNCH("st_post_kernel", st, st_post_kernel<<<grid, kFirThreads, 0, st>>>(pa));
@@ -1306,32 +1424,81 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
         View v2{b2, L.l2, 0, s2, 0};
         if (rc == NODEY_OK) rc = run_tds(v2, out, out_stride, out_frames);
     }
-    device_free(ws, st);
+    if (ws) device_free(ws, st);
     if (ws_offs) device_free(ws_offs, st);
     return rc;
 }
+
+extern "C" {
 
 int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                          int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                          int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
 {
-    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, stream);
+    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, stream);
+}
+
+static int make_tab(const nodey_soundtouch* s, TrackTab* tab, const float* const* in_a, const float* const* in_b, int ntracks)
+{
+    NODEY_REQUIRE(s && in_a, NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null argument");
+    NODEY_REQUIRE(ntracks >= 1 && ntracks <= kMaxTabTracks, NODEY_E_RANGE, "nodey_soundtouch_run_tracks: 1..%d tracks per call", kMaxTabTracks);
+    memset(tab, 0, sizeof(*tab));
+    for (int t = 0; t < ntracks; t++) {
+        NODEY_REQUIRE(in_a[t], NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null track pointer");
+        tab->p[2 * t] = in_a[t];
+        tab->p[2 * t + 1] = (in_b && s->ch == 2) ? in_b[t] : nullptr;
+    }
+    return NODEY_OK;
 }
 
 int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
                                 int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                                 int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
 {
-    NODEY_REQUIRE(s && in_a, NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null argument");
-    NODEY_REQUIRE(ntracks >= 1 && ntracks <= kMaxTabTracks, NODEY_E_RANGE, "nodey_soundtouch_run_tracks: 1..%d tracks per call", kMaxTabTracks);
     TrackTab tab;
-    memset(&tab, 0, sizeof(tab));
-    for (int t = 0; t < ntracks; t++) {
-        NODEY_REQUIRE(in_a[t], NODEY_E_INVALID, "nodey_soundtouch_run_tracks: null track pointer");
-        tab.p[2 * t] = in_a[t];
-        tab.p[2 * t + 1] = (in_b && s->ch == 2) ? in_b[t] : nullptr;
+    const int rc = make_tab(s, &tab, in_a, in_b, ntracks);
+    if (rc != NODEY_OK) return rc;
+    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, stream);
+}
+
+int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t out_frames, int want_chunks,
+                            int64_t* in_need, int64_t* out_ready, int cap)
+{
+    NODEY_REQUIRE(s && in_frames >= 0 && frame_size > 0 && out_frames >= 0, NODEY_E_INVALID, "nodey_soundtouch_chunks: bad argument");
+    std::lock_guard<std::mutex> lock(s->mu);
+    StageLens L;
+    std::vector<long long> pos;
+    const long long total = plan_total(s, in_frames, frame_size, &L, &pos);
+    NODEY_REQUIRE(out_frames <= total, NODEY_E_RANGE, "nodey_soundtouch_chunks: out_frames %lld exceeds what SoundTouch would produce (%lld)",
+                  (long long)out_frames, total);
+    const int n = out_frames == 0 ? 1 : effective_chunks(s, L, want_chunks);
+    for (int c = 0; c < n && c < cap; c++) {
+        ChunkPlan cp;
+        if (out_frames == 0) { cp.in_need = in_frames; cp.out_ready = 0; }
+        else chunk_plan(s, L, pos, in_frames, out_frames, c, n, &cp);
+        if (in_need) in_need[c] = cp.in_need;
+        if (out_ready) out_ready[c] = cp.out_ready;
     }
-    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, stream);
+    return n;
+}
+
+int nodey_soundtouch_run_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
+                               int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(chunk >= 0, NODEY_E_INVALID, "nodey_soundtouch_run_chunk: negative chunk");
+    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, stream);
+}
+
+int nodey_soundtouch_run_tracks_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
+                                      int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
+                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(chunk >= 0, NODEY_E_INVALID, "nodey_soundtouch_run_tracks_chunk: negative chunk");
+    TrackTab tab;
+    const int rc = make_tab(s, &tab, in_a, in_b, ntracks);
+    if (rc != NODEY_OK) return rc;
+    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, stream);
 }
 
 }  // extern "C"

@@ -35,12 +35,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 
 int sm_count()
 {
-    static int cached = 0;
-    if (cached) return cached;
+    // cached per device ordinal: a process may render on several GPUs (one Runner per device)
+    static std::atomic<int> cached[64];
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64) { const int c = cached[dev].load(std::memory_order_relaxed); if (c) return c; }
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
     return n;
 }
 
@@ -78,14 +79,17 @@ constexpr int kCtasPerSm = 8;
 // ------------------------------------------------------------------------------------------------
 // gain
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) gain_f32_kernel(float* __restrict__ dst, const float* __restrict__ src,
-                                                          int64_t n, float v, int vec)
+// `vec`: bit 0 = both pointers 16-byte aligned (128-bit accesses), bit 1 = in place (dst == src): the non-coherent
+// streaming load must not be used on memory this kernel writes, so in-place calls read with plain loads.  No
+// __restrict__ on these kernels for the same reason; partially overlapping buffers are rejected by the entry points.
+__global__ void __launch_bounds__(kBlock) gain_f32_kernel(float* dst, const float* src, int64_t n, float v, int vec)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nvec = vec ? n / 4 : 0;
+    const int64_t nvec = (vec & 1) ? n / 4 : 0;
+    const bool inplace = (vec & 2) != 0;
     for (int64_t i = tid; i < nvec; i += stride) {
-        float4 x = ld_stream4(reinterpret_cast<const float4*>(src) + i);
+        float4 x = inplace ? reinterpret_cast<const float4*>(src)[i] : ld_stream4(reinterpret_cast<const float4*>(src) + i);
         x.x = __fmul_rn(x.x, v); x.y = __fmul_rn(x.y, v); x.z = __fmul_rn(x.z, v); x.w = __fmul_rn(x.w, v);
         st_stream4(reinterpret_cast<float4*>(dst) + i, x);
     }
@@ -106,15 +110,16 @@ struct GainBatch {
 __global__ void __launch_bounds__(kBlock) gain_f32_batch_kernel(const __grid_constant__ GainBatch b)
 {
     const int t = blockIdx.y;
-    float* __restrict__ dst = b.dst[t];
-    const float* __restrict__ src = b.src[t];
+    float* dst = b.dst[t];
+    const float* src = b.src[t];
     const int64_t n = b.n[t];
     const float v = b.vol[t];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nvec = b.vec[t] ? n / 4 : 0;
+    const int64_t nvec = (b.vec[t] & 1) ? n / 4 : 0;
+    const bool inplace = (b.vec[t] & 2) != 0;
     for (int64_t i = tid; i < nvec; i += stride) {
-        float4 x = ld_stream4(reinterpret_cast<const float4*>(src) + i);
+        float4 x = inplace ? reinterpret_cast<const float4*>(src)[i] : ld_stream4(reinterpret_cast<const float4*>(src) + i);
         x.x = __fmul_rn(x.x, v); x.y = __fmul_rn(x.y, v); x.z = __fmul_rn(x.z, v); x.w = __fmul_rn(x.w, v);
         st_stream4(reinterpret_cast<float4*>(dst) + i, x);
     }
@@ -126,14 +131,14 @@ __device__ __forceinline__ short gain_s16_one(short s, float v)
     return (short)(unsigned short)(unsigned)x86_trunc(__fmul_rn((float)s, v));
 }
 
-__global__ void __launch_bounds__(kBlock) gain_s16_kernel(short* __restrict__ dst, const short* __restrict__ src,
-                                                          int64_t n, float v, int vec)
+__global__ void __launch_bounds__(kBlock) gain_s16_kernel(short* dst, const short* src, int64_t n, float v, int vec)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nvec = vec ? n / 8 : 0;
+    const int64_t nvec = (vec & 1) ? n / 8 : 0;
+    const bool inplace = (vec & 2) != 0;
     for (int64_t i = tid; i < nvec; i += stride) {
-        int4 x = ld_stream4i(reinterpret_cast<const int4*>(src) + i);
+        int4 x = inplace ? reinterpret_cast<const int4*>(src)[i] : ld_stream4i(reinterpret_cast<const int4*>(src) + i);
         int* w = reinterpret_cast<int*>(&x);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -146,14 +151,14 @@ __global__ void __launch_bounds__(kBlock) gain_s16_kernel(short* __restrict__ ds
     for (int64_t i = nvec * 8 + tid; i < n; i += stride) dst[i] = gain_s16_one(src[i], v);
 }
 
-__global__ void __launch_bounds__(kBlock) gain_s32_kernel(int* __restrict__ dst, const int* __restrict__ src,
-                                                          int64_t n, float v, int vec)
+__global__ void __launch_bounds__(kBlock) gain_s32_kernel(int* dst, const int* src, int64_t n, float v, int vec)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nvec = vec ? n / 4 : 0;
+    const int64_t nvec = (vec & 1) ? n / 4 : 0;
+    const bool inplace = (vec & 2) != 0;
     for (int64_t i = tid; i < nvec; i += stride) {
-        int4 x = ld_stream4i(reinterpret_cast<const int4*>(src) + i);
+        int4 x = inplace ? reinterpret_cast<const int4*>(src)[i] : ld_stream4i(reinterpret_cast<const int4*>(src) + i);
         x.x = x86_trunc(__fmul_rn((float)x.x, v)); x.y = x86_trunc(__fmul_rn((float)x.y, v));
         x.z = x86_trunc(__fmul_rn((float)x.z, v)); x.w = x86_trunc(__fmul_rn((float)x.w, v));
         st_stream4i(reinterpret_cast<int4*>(dst) + i, x);
@@ -592,7 +597,13 @@ int nodey_gain(void* dst, const void* src, int fmt, int64_t n, float volume, nod
 {
     NODEY_REQUIRE(n >= 0 && (n == 0 || (dst && src)), NODEY_E_INVALID, "nodey_gain: null buffer or negative size");
     if (n == 0) return NODEY_OK;
-    const int vec = aligned16(dst) && aligned16(src);
+    {
+        // in place (dst == src) is allowed; any other overlap would let one thread read what another already wrote
+        const size_t bytes = (size_t)n * (size_t)(fmt_bytes(fmt) ? fmt_bytes(fmt) : 1);
+        const char* a = (const char*)dst; const char* b = (const char*)src;
+        NODEY_REQUIRE(a == b || a + bytes <= b || b + bytes <= a, NODEY_E_INVALID, "nodey_gain: dst and src overlap partially");
+    }
+    const int vec = ((aligned16(dst) && aligned16(src)) ? 1 : 0) | (dst == src ? 2 : 0);
     cudaStream_t st = as_stream(stream);
     switch (fmt) {
     case NODEY_FMT_FLT: case NODEY_FMT_FLTP:
@@ -625,7 +636,12 @@ int nodey_gain_tracks(void* const* dst, const void* const* src, const int64_t* n
         for (int t = 0; t < cnt; t++) {
             NODEY_REQUIRE(n[first + t] >= 0 && (n[first + t] == 0 || (dst[first + t] && src[first + t])), NODEY_E_INVALID, "nodey_gain_tracks: null buffer or negative size");
             b.dst[t] = (float*)dst[first + t]; b.src[t] = (const float*)src[first + t]; b.n[t] = n[first + t]; b.vol[t] = volumes[first + t];
-            b.vec[t] = aligned16(dst[first + t]) && aligned16(src[first + t]);
+            {
+                const char* pa = (const char*)dst[first + t]; const char* pb = (const char*)src[first + t];
+                const size_t bytes = (size_t)n[first + t] * sizeof(float);
+                NODEY_REQUIRE(pa == pb || pa + bytes <= pb || pb + bytes <= pa, NODEY_E_INVALID, "nodey_gain_tracks: dst and src of stream %d overlap partially", first + t);
+            }
+            b.vec[t] = ((aligned16(dst[first + t]) && aligned16(src[first + t])) ? 1 : 0) | (dst[first + t] == src[first + t] ? 2 : 0);
             if (n[first + t] > longest) longest = n[first + t];
         }
         if (longest == 0) continue;

@@ -15,6 +15,9 @@ namespace infra
 	struct Exec_context
 	{
 		Stream_handle stream = nullptr;   // launch everything of the current node (batch) on this stream
+		// second stream of the lane (may be null): a node whose input arrives chunk by chunk (Audio_buffer::progress) runs on
+		// the stream its producer does NOT use, so that the two overlap; it publishes with an event recorded there
+		Stream_handle side_stream = nullptr;
 		int level = 0;                    // graph level being executed
 		int lane = 0;                     // index of the stream inside the level
 

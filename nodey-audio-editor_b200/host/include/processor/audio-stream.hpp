@@ -41,6 +41,17 @@ namespace processor
 	Frame_runs uniform_frame_runs(int64_t frames, int64_t frame_size);
 	int64_t frame_runs_total(const Frame_runs& runs);
 
+	// A producer that renders a stream in chunks along time says so here: once points[k].event has completed, frames
+	// [0, points[k].frames) hold their final values (ascending; the last point covers the whole stream).  A consumer that
+	// can start on a prefix waits for the point it needs instead of Audio_buffer::ready -- the reference's nodes overlap the
+	// same way, frame by frame through their 16-frame channels (src/processor/audio-stream.cpp:60-80).
+	struct Stream_progress
+	{
+		struct Point { int64_t frames; std::shared_ptr<infra::Device_event> event; };
+		std::vector<Point> points;
+		infra::Stream_handle stream = nullptr;     // the stream the producer enqueued on
+	};
+
 	struct Audio_buffer
 	{
 		std::shared_ptr<infra::Device_block> block;    // owner of the memory (may be shared by a whole batch)
@@ -52,6 +63,7 @@ namespace processor
 		Frame_runs runs;                               // how the reference would have cut it into frames
 		double pts_seconds = 0.0;                      // start time of the first frame
 		std::shared_ptr<infra::Device_event> ready;    // recorded after the producing kernels were enqueued
+		std::shared_ptr<const Stream_progress> progress;   // optional: chunk-wise completion (shared by the products of a batch)
 
 		size_t plane_bytes() const { return (size_t)frames * (size_t)format_bytes(format) * (format_is_planar(format) ? 1u : (size_t)channels); }
 	};

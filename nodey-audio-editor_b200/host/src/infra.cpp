@@ -636,13 +636,33 @@ namespace infra
 		constexpr int kMaxLanes = 5;
 		const int kLanes = 1 + compute_lanes;
 		nodey_stream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+		// every compute lane has a side stream: a node that consumes a stream chunk by chunk runs there, next to its producer
+		nodey_stream_t sides[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+		const auto release_lanes = [&] {
+			for (auto* set : {&lanes, &sides})
+				for (auto& s : *set)
+				{
+					if (!s) continue;
+					Lane_registry::remove(s);
+					nodey_stream_destroy(s);
+					s = nullptr;
+				}
+		};
 		bool failed = false;
 		if (device >= 0 && nodey_set_device(device) != NODEY_OK) failed = true;
-		for (int k = 0; k < kLanes; k++)
-			if (nodey_stream_create(&lanes[k]) != NODEY_OK) failed = true;
-			else Lane_registry::add(lanes[k], k >= 1);
+		for (int k = 0; k < kLanes && !failed; k++)
+		{
+			if (nodey_stream_create(&lanes[k]) != NODEY_OK) { lanes[k] = nullptr; failed = true; break; }
+			Lane_registry::add(lanes[k], k >= 1);
+			if (k >= 1 && getenv("NODEY_NO_SIDE_STREAMS") == nullptr)
+			{
+				if (nodey_stream_create(&sides[k]) != NODEY_OK) { sides[k] = nullptr; failed = true; break; }
+				Lane_registry::add(sides[k], true);
+			}
+		}
 		if (failed)
 		{
+			release_lanes();      // lanes created before the failure must not stay registered (they would skew free_ordered)
 			for (auto& [_, r] : processor_resources)
 			{
 				r->exception = Processor::Runtime_error("No CUDA device", "The render engine needs a CUDA device; there is no CPU fallback.", nodey_last_error());
@@ -665,6 +685,7 @@ namespace infra
 				if (failed) return;
 				Exec_context& ctx = Exec_context::current();
 				ctx.stream = lanes[lane];
+				ctx.side_stream = sides[lane];
 				ctx.level = level_index;
 				ctx.lane = lane;
 
@@ -742,6 +763,7 @@ namespace infra
 				{
 					const auto t_enq = std::chrono::steady_clock::now();
 					for (auto& s : lanes) if (s) nodey_stream_synchronize(s);
+					for (auto& s : sides) if (s) nodey_stream_synchronize(s);
 					const auto t_end = std::chrono::steady_clock::now();
 					fprintf(stderr, "[nodey trace] wave %d level %zu: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", wave, level_index,
 							ids.size(), processor_resources.at(ids.front())->processor->get_processor_info_non_static().identifier.c_str(),
@@ -750,6 +772,8 @@ namespace infra
 				}
 			}
 		for (auto& s : lanes)
+			if (s) nodey_stream_synchronize(s);
+		for (auto& s : sides)
 			if (s) nodey_stream_synchronize(s);
 		// everything has drained: turn the step events into timings (the run's origin is the first step's begin)
 		for (auto& se : steps)
@@ -764,12 +788,7 @@ namespace infra
 			if (se.end) nodey_event_destroy(se.end);
 			level_timings.push_back(std::move(se.timing));
 		}
-		for (auto& s : lanes)
-		{
-			if (!s) continue;
-			Lane_registry::remove(s);
-			nodey_stream_destroy(s);
-		}
+		release_lanes();
 		done = true;
 	}
 

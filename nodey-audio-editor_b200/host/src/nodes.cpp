@@ -78,8 +78,9 @@ namespace processor
 			}
 		};
 
+		// wait = false: the caller orders itself after the producer (chunk by chunk through Audio_buffer::progress)
 		std::shared_ptr<const Audio_buffer> require_input(const Processor::Input_map& input, const std::string& key,
-														   const char* node_title)
+														   const char* node_title, bool wait = true)
 		{
 			const auto item = infra::get_input_item<Audio_stream>(input, key);
 			if (!item.has_value())
@@ -90,7 +91,7 @@ namespace processor
 			if (!buffer)
 				throw Runtime_error(std::format("{} received an empty stream", node_title),
 									"The upstream node closed its stream without publishing audio.", std::format("pin '{}'", key));
-			if (buffer->ready) buffer->ready->wait_on(cur_stream());
+			if (wait && buffer->ready) buffer->ready->wait_on(cur_stream());
 			return buffer;
 		}
 
@@ -126,35 +127,64 @@ namespace processor
 		// process-wide plan caches (plans are immutable once built; kernels in flight keep using them)
 		std::mutex plan_mutex;
 
+		// plans own device memory (filter banks, fade ramps, position tables) on the device that was current when they
+		// were built, so both caches are keyed by the device ordinal: a process may run one Runner per GPU
+		int current_device()
+		{
+			int device = 0;
+			abi(nodey_get_device(&device), "plan cache");
+			return device;
+		}
+
 		nodey_resampler* resampler_for(int in_rate)
 		{
-			static std::map<int, nodey_resampler*> cache;
+			static std::map<std::pair<int, int>, nodey_resampler*> cache;
+			const int device = current_device();
 			std::lock_guard lock(plan_mutex);
-			const auto it = cache.find(in_rate);
+			const auto it = cache.find({device, in_rate});
 			if (it != cache.end()) return it->second;
 			nodey_resampler* r = nullptr;
 			abi(nodey_resampler_create(&r, in_rate, 48000, 0), "swresample plan");
-			cache[in_rate] = r;
+			cache[{device, in_rate}] = r;
 			return r;
 		}
 
-		nodey_soundtouch* soundtouch_for(int rate_hz, int ch, float rate, float pitch, int64_t n_in)
+		// SoundTouch plans by (device, rate, channels, parameters): a plan holds one immutable position table per stream
+		// length it has rendered, so the length is not part of the key.  Bounded: the least recently used plan goes when
+		// more than kMaxSoundtouchPlans exist -- shared_ptr, so a render that is still enqueueing with it keeps it alive
+		// (kernels already enqueued only need the device tables, and nodey_soundtouch_destroy frees them with cudaFree,
+		// which waits for the device).
+		constexpr size_t kMaxSoundtouchPlans = 32;
+
+		std::shared_ptr<nodey_soundtouch> soundtouch_for(int rate_hz, int ch, float rate, float pitch)
 		{
-			static std::map<std::tuple<int, int, uint32_t, uint32_t, int64_t>, nodey_soundtouch*> cache;
+			using Key = std::tuple<int, int, int, uint32_t, uint32_t>;
+			struct Slot { std::shared_ptr<nodey_soundtouch> plan; uint64_t used; };
+			static std::map<Key, Slot> cache;
+			static uint64_t clock = 0;
 			uint32_t rb, pb;
 			memcpy(&rb, &rate, 4); memcpy(&pb, &pitch, 4);
+			const int device = current_device();
 			std::lock_guard lock(plan_mutex);
-			const auto key = std::make_tuple(rate_hz, ch, rb, pb, n_in);
+			const Key key{device, rate_hz, ch, rb, pb};
 			const auto it = cache.find(key);
-			if (it != cache.end()) return it->second;
+			if (it != cache.end()) { it->second.used = ++clock; return it->second.plan; }
 			nodey_soundtouch* s = nullptr;
 			const int rc = nodey_soundtouch_create(&s, rate_hz, ch, rate, pitch);
 			if (rc == NODEY_E_RANGE)
 				throw Runtime_error("Unsupported sample rate", std::format("{} requires a sample rate between 8000 and 48000 Hz.", rate_hz),
 									nodey_last_error());
 			abi(rc, "SoundTouch");
-			cache[key] = s;
-			return s;
+			if (cache.size() >= kMaxSoundtouchPlans)
+			{
+				auto oldest = cache.begin();
+				for (auto k = cache.begin(); k != cache.end(); ++k)
+					if (k->second.used < oldest->second.used) oldest = k;
+				cache.erase(oldest);
+			}
+			std::shared_ptr<nodey_soundtouch> plan(s, [](nodey_soundtouch* p) { nodey_soundtouch_destroy(p); });
+			cache[key] = Slot{plan, ++clock};
+			return plan;
 		}
 
 		struct Runs_flat
@@ -762,24 +792,37 @@ namespace processor
 		constexpr int kSoundtouchFrame = 1152;     // canonical putSamples / output chunk
 		constexpr size_t kMaxTracksPerLaunch = 256;
 
+		// how many launches a track's WSOLA chain is cut into (1 = whole-track launches); NODEY_ST_CHUNKS overrides
+		int soundtouch_chunk_count()
+		{
+			static const int n = [] { const char* env = getenv("NODEY_ST_CHUNKS"); return env ? std::clamp(atoi(env), 1, 64) : 8; }();
+			return n;
+		}
+
 		bool soundtouch_batch(const std::vector<Processor::Batch_item>& items, const char* title)
 		{
 			struct Entry { size_t item; std::shared_ptr<const Audio_buffer> in; Soundtouch_params prm; };
-			std::map<std::tuple<int, int, int64_t, uint32_t, uint32_t>, std::vector<Entry>> groups;
+			std::map<std::tuple<int, int, int64_t, uint32_t, uint32_t, const Stream_progress*>, std::vector<Entry>> groups;
 			for (size_t k = 0; k < items.size(); k++)
 			{
-				auto in = require_input(*items[k].input, "input", title);
+				// inputs that arrive chunk by chunk are not waited for here: the chunks below wait for the prefix they need
+				auto in = require_input(*items[k].input, "input", title, false);
+				if (!in->progress && in->ready) in->ready->wait_on(cur_stream());
 				check_channels(*in, title);
 				const Soundtouch_params prm = Soundtouch_params::of(items[k].processor);
 				uint32_t rb, pb;
 				memcpy(&rb, &prm.rate, 4); memcpy(&pb, &prm.pitch, 4);
-				groups[{in->sample_rate, in->channels, in->frames, rb, pb}].push_back({k, std::move(in), prm});
+				const Stream_progress* pg = in->progress.get();
+				groups[{in->sample_rate, in->channels, in->frames, rb, pb, pg}].push_back({k, std::move(in), prm});
 			}
+			const nodey_stream_t main_stream = cur_stream();
+			const nodey_stream_t side_stream = Exec_context::current().side_stream;
 			for (auto& [key, all] : groups)
 			{
-				const auto [rate_hz, ch, n, rb_, pb_] = key;
-				(void)rb_; (void)pb_;
-				nodey_soundtouch* st = soundtouch_for(rate_hz, ch, all.front().prm.rate, all.front().prm.pitch, n);
+				const auto [rate_hz, ch, n, rb_, pb_, pg_] = key;
+				(void)rb_; (void)pb_; (void)pg_;
+				const std::shared_ptr<nodey_soundtouch> plan = soundtouch_for(rate_hz, ch, all.front().prm.rate, all.front().prm.pitch);
+				nodey_soundtouch* st = plan.get();
 				int64_t nseq = 0;
 				const int64_t m = nodey_soundtouch_out_frames(st, n, kSoundtouchFrame, &nseq);
 				if (m < 0) abi((int)m, title);
@@ -788,17 +831,73 @@ namespace processor
 					const size_t cnt = std::min(kMaxTracksPerLaunch, all.size() - first);
 					const size_t in_stride = Arena::padded((size_t)n * ch * sizeof(float)) / sizeof(float);
 					const size_t out_stride = Arena::padded((size_t)std::max<int64_t>(m, 1) * ch * sizeof(float)) / sizeof(float);
+					const size_t offs_stride = (size_t)std::max<int64_t>(nseq - 1, 1);
 					// A8: extract_samples_interleaved is the identity on float samples: FLT / FLTP streams are read in
 					// place through per-track pointers; integer formats are converted into one contiguous batch first
-					Arena arena(out_stride * sizeof(float) * cnt);
-					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
 					bool in_place = true;
 					for (size_t k = 0; k < cnt; k++)
 					{
 						const int f = all[first + k].in->format;
 						in_place = in_place && (f == FMT_FLT || f == FMT_FLTP) && f == all[first].in->format;
 					}
-					if (in_place)
+					// chunk plan: the chain of a track runs as several launches so that the next node can start on a prefix
+					// of this node's output (and this node on a prefix of its input, when its producer works the same way)
+					const std::shared_ptr<const Stream_progress> in_progress = all[first].in->progress;
+					constexpr int kMaxChunks = 64;
+					int64_t in_need[kMaxChunks], out_ready[kMaxChunks];
+					int nchunks = 1;
+					if (in_place && m > 0)
+					{
+						nchunks = nodey_soundtouch_chunks(st, n, kSoundtouchFrame, m, soundtouch_chunk_count(), in_need, out_ready, kMaxChunks);
+						if (nchunks < 0) abi(nchunks, title);
+					}
+					const bool chunked = in_place && m > 0 && (nchunks > 1 || in_progress);
+					Arena arena(out_stride * sizeof(float) * cnt + (chunked ? Arena::padded(offs_stride * sizeof(int32_t) * cnt) : 0));
+					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
+					std::shared_ptr<Stream_progress> progress;
+					std::shared_ptr<infra::Device_event> done;
+					if (chunked)
+					{
+						int32_t* offs = (int32_t*)arena.take(offs_stride * sizeof(int32_t) * cnt);
+						// run next to a chunk-wise producer: on the lane's other stream, forked from this one (the arena above
+						// was allocated in this stream's order)
+						nodey_stream_t run = main_stream;
+						if (in_progress && side_stream) run = in_progress->stream == main_stream ? side_stream : main_stream;
+						if (run != main_stream)
+						{
+							infra::Device_event fork;
+							fork.record(main_stream);
+							fork.wait_on(run);
+						}
+						if (!in_progress && run != main_stream)
+							for (size_t k = 0; k < cnt; k++)
+								if (all[first + k].in->ready) all[first + k].in->ready->wait_on(run);
+						const bool planes = all[first].in->format == FMT_FLTP && ch == 2;
+						std::vector<const float*> pa(cnt), pb(cnt, nullptr);
+						for (size_t k = 0; k < cnt; k++)
+						{
+							pa[k] = (const float*)all[first + k].in->plane[0];
+							if (planes) pb[k] = (const float*)all[first + k].in->plane[1];
+						}
+						progress = std::make_shared<Stream_progress>();
+						progress->stream = run;
+						size_t waited = 0;      // progress points of the input already waited for
+						for (int c = 0; c < nchunks; c++)
+						{
+							if (in_progress)
+								while (waited < in_progress->points.size() && (waited == 0 || in_progress->points[waited - 1].frames < in_need[c]))
+									in_progress->points[waited++].event->wait_on(run);
+							abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
+																  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, run), title);
+							auto ev = std::make_shared<infra::Device_event>();
+							ev->record(run);
+							progress->points.push_back({out_ready[c], ev});
+						}
+						if (in_progress)      // whatever the chunk plan needed, the product is complete only after the whole input is
+							while (waited < in_progress->points.size()) in_progress->points[waited++].event->wait_on(run);
+						done = progress->points.back().event;
+					}
+					else if (in_place)
 					{
 						const bool planes = all[first].in->format == FMT_FLTP && ch == 2;
 						std::vector<const float*> pa(cnt), pb(cnt, nullptr);
@@ -817,6 +916,7 @@ namespace processor
 						for (size_t k = 0; k < cnt; k++)
 						{
 							const Audio_buffer& in = *all[first + k].in;
+							if (in.progress && in.ready) in.ready->wait_on(cur_stream());
 							abi(nodey_extract_interleaved((float*)staging.ptr + k * in_stride, in.plane[0], in.plane[1], in.format, n, ch, cur_stream()), title);
 						}
 						if (m > 0)
@@ -826,9 +926,10 @@ namespace processor
 					for (size_t k = 0; k < cnt; k++)
 					{
 						const Entry& e = all[first + k];
-						publish(*items[e.item].output, "output",
-								new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m,
-										   uniform_frame_runs(m, kSoundtouchFrame), e.in->pts_seconds));
+						auto b = new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m,
+											uniform_frame_runs(m, kSoundtouchFrame), e.in->pts_seconds);
+						if (done) { b->ready = done; b->progress = progress; }
+						publish(*items[e.item].output, "output", b);
 					}
 				}
 			}

@@ -172,3 +172,76 @@ def test_soundtouch_short_inputs(nd, orc, n, cfg):
     if m:
         assert np.array_equal(offs.cpu().numpy()[:len(ref_offs)], ref_offs)
         assert_bit_equal(got.cpu().numpy(), ref, f"short input n={n}")
+
+
+@pytest.mark.parametrize("nchunks", [2, 3, 8, 64])
+@pytest.mark.parametrize("cfg", [(48000, 1.0, 3.0, None, 12.0), (48000, 1.25, None, True, 9.0), (44100, 1.7, None, False, 7.0)])
+def test_soundtouch_chunked_render_is_bit_identical(nd, orc, nchunks, cfg):
+    """A track's WSOLA chain cut into launches (nodey_soundtouch_run_chunk): same offset trace, same samples as the
+    one-launch render and as the oracle; and chunk c really needs no more than in_need[c] input frames -- everything
+    beyond is overwritten with NaN before the chunk runs and restored afterwards."""
+    import torch
+    sr, rate, st_, keep, secs = cfg
+    pitch = orc.pitch_node_factor(st_) if st_ is not None else orc.velocity_node_pitch(rate, keep)
+    n = int(sr * secs) + 31
+    xs = np.stack([orc.synth_f32(n, 2, sr, t) for t in range(3)])
+    st = nd.SoundTouch(sr, 2, rate, pitch)
+    x = to_dev(xs)
+    whole, whole_offs = st.run(x, 1152, want_offsets=True)
+    keep_x = x.clone()
+
+    def poison(c, in_need):
+        x.copy_(keep_x)
+        x[:, in_need:, :] = float("nan")
+
+    got, offs, plan = st.run_chunked(x, nchunks, 1152, poison=poison)
+    torch.cuda.synchronize()
+    assert 1 <= len(plan) <= nchunks
+    assert plan[-1][0] == n and plan[-1][1] == whole.shape[1]
+    assert all(plan[k][0] <= plan[k + 1][0] and plan[k][1] <= plan[k + 1][1] for k in range(len(plan) - 1))
+    if secs * sr > 40 * 4000 and nchunks <= 8:
+        assert len(plan) == nchunks
+    assert torch.equal(offs, whole_offs), "offset trace of the chunked render"
+    assert_bit_equal(got.cpu().numpy(), whole.cpu().numpy(), "chunked vs one launch")
+    ref, ro, _ = orc.soundtouch(xs[1], sr, rate, pitch, 1152)
+    assert np.array_equal(offs[1].cpu().numpy(), ro)
+    assert_bit_equal(got[1].cpu().numpy(), ref, "chunked vs oracle")
+
+
+def test_soundtouch_chunk_progress_is_final(nd, orc):
+    """after chunk c, output frames [0, out_ready[c]) already hold their final values"""
+    import torch
+    sr, n = 48000, 48000 * 10
+    x = to_dev(np.stack([orc.synth_f32(n, 2, sr, t) for t in range(2)]))
+    st = nd.SoundTouch.pitch_node(sr, 2, 3.0)
+    whole = st.run(x, 1152)
+    m, nseq = st.out_frames(n, 1152)
+    plan = st.chunks(n, 1152, 6)
+    out = torch.full((2, m, 2), float("nan"), device="cuda")
+    offs = torch.zeros((2, nseq - 1), dtype=torch.int32, device="cuda")
+    import ctypes as C
+    for c in range(len(plan)):
+        nd.check(nd.lib().nodey_soundtouch_run_chunk(st.h, nd._dp(out), out.stride(0), nd._dp(x), x.stride(0), 2, n, 1152, m,
+                                                     nd._dp(offs), offs.stride(0), c, len(plan), nd._stream()))
+        torch.cuda.synchronize()
+        r = plan[c][1]
+        assert torch.equal(out[:, :r], whole[:, :r]), f"chunk {c}: frames below out_ready are not final"
+    assert plan[0][1] > 0 and plan[0][0] < n
+
+
+def test_soundtouch_chunks_of_uncuttable_paths(nd, orc):
+    """mono and the rate <= 1 order run as one chunk; a chunk count the plan did not return is rejected"""
+    st = nd.SoundTouch(48000, 1, 1.0, orc.pitch_node_factor(3.0))
+    assert len(st.chunks(48000 * 5, 1152, 8)) == 1
+    st2 = nd.SoundTouch(48000, 2, 0.8, orc.velocity_node_pitch(0.8, True))
+    assert st2.info()["tdstretch_first"] == 0 and len(st2.chunks(48000 * 5, 1152, 8)) == 1
+    st3 = nd.SoundTouch.pitch_node(48000, 2, 3.0)
+    import torch
+    x = torch.zeros((1, 48000, 2), device="cuda")          # 1 s: 14 sequences -> one chunk
+    assert len(st3.chunks(48000, 1152, 8)) == 1
+    m, nseq = st3.out_frames(48000, 1152)
+    out = torch.empty((1, m, 2), device="cuda")
+    offs = torch.zeros((1, max(nseq - 1, 1)), dtype=torch.int32, device="cuda")
+    rc = nd.lib().nodey_soundtouch_run_chunk(st3.h, nd._dp(out), out.stride(0), nd._dp(x), x.stride(0), 1, 48000, 1152, m,
+                                             nd._dp(offs), offs.stride(0), 0, 4, nd._stream())
+    assert rc == -5      # NODEY_E_RANGE
