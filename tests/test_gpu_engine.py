@@ -361,6 +361,73 @@ def test_bimix_node_against_real_libswresample(eng_gpu, orc, tag):
     e.close()
 
 
+def test_amix_node_in_the_capped_surplus_regime_against_real_libswresample(eng_gpu, orc):
+    """audio_amix with nb = 64 next to an 88.2 kHz input in 3561-sample frames (tests/golden/swr_real_amix_capped.npz):
+    the real library hands the buffered surplus out over 160 later calls and returns 10213 samples, one MORE than a
+    conversion with ample capacity -- the KERNEL has to produce that 10213th sample (audio-amix.cpp:263-290).  Stream
+    length and zero positions exact, values within 1e-6; bit exact against the oracle node."""
+    import os
+    G, _ = _swr_gold()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "swr_real_amix_capped.npz"))
+    tag = "amix4_capped_surplus"
+    spec, vols = G.AMIX_CAPPED_CASES[tag]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [""] * len(spec)})
+    mix = p.add("audio_amix", eng_gpu.amix_info(list(vols)))
+    out = p.add("audio_output")
+    for i in range(len(spec)):
+        p.link(src, f"output_{i}", mix, f"input_{i + 1}")
+    p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    xs = [G.case_input(orc, r, f, c, n, 40 + i) for i, (r, f, c, n, fr) in enumerate(spec)]
+    for i, (r, f, c, n, fr) in enumerate(spec):
+        e.bind_source(i, xs[i], f, r, frame_size=fr)
+    e.run()
+    got = e.output().numpy()
+    gl, gr = gold[f"{tag}_l"], gold[f"{tag}_r"]
+    assert int(gold[f"{tag}_capped_total"]) == 10213
+    assert got.shape == (2, len(gl)) and len(gl) == int(gold[f"{tag}_nb"].sum()), "stream length"
+    assert np.array_equal(got[0] == 0, gl == 0) and np.array_equal(got[1] == 0, gr == 0), "zero positions (the 10213th sample)"
+    assert np.abs(got[0] - gl).max() <= 1e-6 and np.abs(got[1] - gr).max() <= 1e-6
+    ol, orr = orc.amix([orc.make_track(x, f, r, frame_size=fr) for x, (r, f, c, n, fr) in zip(xs, spec)], list(vols))
+    assert_bit_equal(got, np.stack([ol, orr]), "capped amix vs oracle node")
+    e.close()
+
+
+def _bimix2_cases():
+    G, _ = _swr_gold()
+    return sorted(G.BIMIX2_CASES)
+
+
+@pytest.mark.parametrize("tag", _bimix2_cases())
+def test_bimix_v2_node_against_real_libswresample(eng_gpu, orc, tag):
+    """Audio_bimix_v2 on the GPU against the reference's loop (audio-bimix.cpp:536-875) run on real SwrContexts
+    (tests/golden/swr_real_bimix2.npz): unflushed per-frame conversion with capacity 2 * nb, mono fold, END-time stamps,
+    the pts aligner.  Stream length, first pts and every silent position exact; values 1e-6 (bit exact at 48 kHz)."""
+    import os
+    G, _ = _swr_gold()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "swr_real_bimix2.npz"))
+    left, right, pl, pr = G.BIMIX2_CASES[tag]
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    bm = p.add("audio_bimix_v2")
+    out = p.add("audio_output")
+    p.link(src, "output_0", bm, "input_l"); p.link(src, "output_1", bm, "input_r"); p.link(bm, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.bind_source(0, G.case_input(orc, *left[:4], 70), left[1], left[0], frame_size=left[4], pts=pl)
+    e.bind_source(1, G.case_input(orc, *right[:4], 71), right[1], right[0], frame_size=right[4], pts=pr)
+    e.run()
+    got = e.output()
+    ref = gold[f"{tag}_out"]
+    g = got.numpy()
+    assert g.shape == ref.shape == (int(gold[f"{tag}_sizes"].sum()), 2), "stream length"
+    assert got.pts == float(gold[f"{tag}_pts"]), "pts of the first frame"
+    assert np.array_equal(g == 0, ref == 0), "silent regions (alignment)"
+    exact = left[0] == 48000 and right[0] == 48000
+    assert np.abs(g - ref).max() <= (0.0 if exact else 1e-6)
+    e.close()
+
+
 def test_diagnostics_report_every_step_of_the_run(eng_gpu, orc):
     """the data behind the editor's overlay -- node states and the device time of every
     (wave, level) step of the Runner (the reference shows channel fill per link, app.cpp:1556-1592)."""

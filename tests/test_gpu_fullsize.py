@@ -114,3 +114,57 @@ def test_config1_60s_graph_through_engine(eng_gpu, orc):
     got = e.output()
     assert got.frames == len(rl) and got.frames >= 2880000
     assert_bit_equal(got.numpy(), np.stack([rl, rr]), "config 1 output")
+
+
+def test_config5_full_size_render_256_tracks(nd, eng_gpu, orc):
+    """configs[4] at the benchmarked size -- 256 tracks x 180 s through the plugin API (two waves, arena views, 256-wide
+    batches, chunked WSOLA chains on two streams) -- against the oracle where the oracle finishes in seconds:
+      * the per-track chains of the first and the last track (audio_amix(1) -> pitch -> tempo -> gain): bit exact;
+      * one whole level-1 group (tracks 240..255 -> audio_amix(16)): bit exact against the oracle mix of 16 oracle chains;
+      * the master bus: equal to the ordered, separately rounded sum of the 16 group mixes the engine published
+        (audio-amix.cpp:293-307), bit exact; spectrum spot frames within 1e-5 of the frame peak."""
+    import torch
+    from oracle import graph_oracle as G
+    import pipeline
+    T, n = 256, 44100 * 180
+    gains = [pipeline.track_gain(t) for t in range(T)]
+    project, ids = eng_gpu.config5_project(T, gains)
+    e = eng_gpu.Engine(project.json())
+    x = torch.empty((T, n, 2), dtype=torch.float32, device="cuda")
+    for t in range(T):
+        nd.check(nd.lib().nodey_synth(nd._dp(x[t]), None, n, 2, 44100, t, 0, None))
+    torch.cuda.synchronize()
+    for t in range(T):
+        e.bind_source(t, x[t], nd.FMT_FLT, 44100)
+    e.run()
+    # per-track chains
+    host = {t: x[t].cpu().numpy() for t in list(range(240, 256)) + [0]}
+    for t in (0, 255):
+        assert np.array_equal(host[t], orc.synth_f32(n, 2, 44100, t)), "device source differs from the oracle source"
+        ref = G.track_chain(host[t], G.track_gain(t))
+        assert_bit_equal(e.product(ids["gains"][t], "output").numpy(), ref, f"track {t} chain at full size")
+    # one whole group
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(16) as ex:
+        ys = list(ex.map(lambda t: G.track_chain(host[t], G.track_gain(t)), range(240, 256)))
+    grp, _ = G._amix_with_runs(ys, [orc.FMT_FLT] * 16, [G.uniform_runs(len(y)) for y in ys], [1.0 / 16] * 16)
+    assert_bit_equal(e.product(ids["groups"][15], "output").numpy(), grp, "level-1 mix of tracks 240..255")
+    # master bus from the published group mixes, in input order
+    bus = e.output().numpy()
+    acc = np.zeros_like(bus)
+    v = np.float32(1.0 / 16)
+    for g in ids["groups"]:
+        gm = e.product(g, "output").numpy()
+        assert gm.shape[1] <= bus.shape[1]
+        acc[:, :gm.shape[1]] = acc[:, :gm.shape[1]] + gm * v
+    assert_bit_equal(bus, acc, "master bus = ordered sum of the group mixes")
+    assert bus.shape[1] >= 48000 * 143
+    spec = e.product(ids["spectrum"], "output").numpy()
+    for f in (0, 1, spec.shape[1] // 2, spec.shape[1] - 1):
+        for c in range(2):
+            ref = orc.stft(bus[c, f * 1024:f * 1024 + 4096].copy())[0]
+            assert np.abs(spec[c, f] - ref).max() <= 1e-5 * np.abs(ref).max(), (f, c)
+    e.close()
+    del x
+    torch.cuda.empty_cache()
+    nd.check(nd.lib().nodey_trim_memory())
