@@ -155,7 +155,11 @@ int64_t nodey_resampler_out_count(const nodey_resampler* r, int64_t in_frames, i
 int64_t nodey_resampler_producible(const nodey_resampler* r, int64_t n_in, int64_t reflect);
 int64_t nodey_resampler_flush_reflect(const nodey_resampler* r, int64_t n_in, int64_t produced);
 /* Whole-track conversion: source in its native format (converted on load, mono rematrixed),
- * stereo float planar out.  out_frames <= nodey_resampler_out_count(). */
+ * stereo float planar out.  out_frames <= nodey_resampler_out_count(), with one exception the library has too: a
+ * flushed conversion that was drained through small output capacities (audio_amix's nb next to a faster input) still
+ * buffers more than filter_length frames when resample_flush() runs, reflects one frame more and can return one more
+ * output than the same input converted with ample capacity; flush = 1 accepts that count as well (the bookkeeping
+ * that says when it happens is nodey_resampler_flush_reflect / nodey_amix_plan). */
 int nodey_resampler_run(const nodey_resampler* r, float* out_l, float* out_r,
                         const void* plane0, const void* plane1, int fmt, int nch, int64_t in_frames,
                         int flush, int64_t out_frames, nodey_stream_t stream);

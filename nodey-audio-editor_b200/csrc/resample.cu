@@ -819,15 +819,46 @@ int64_t nodey_resampler_flush_reflect(const nodey_resampler* r, int64_t n_in, in
     return plan_reflect(r, n_in, produced);
 }
 
+// Reflection length of a flushed conversion that has to deliver `want` outputs.  resample_flush() appends
+// (min(in_buffer_count, filter_length) + 1) / 2 mirrored frames: a conversion drained with ample capacity holds
+// filter_length - 1 frames at that point, one drained through small output capacities (audio_amix's nb next to a
+// faster input) still holds more than filter_length and so reflects ONE frame more -- and can return one more output
+// (tests/golden/swr_real_amix_capped.npz: 10213 instead of 10212).  The mirrored frames are the same sequence either
+// way, so the shortest reflection that yields `want` reproduces the library; -1: not even the longest one does.
+static int64_t flush_reflect_for(const nodey_resampler* r, int64_t in_frames, int64_t want)
+{
+    int64_t reflect = plan_reflect(r, in_frames, plan_producible(r, in_frames, 0));
+    const int64_t longest = in_frames < r->filter_length ? (in_frames + 1) / 2 : (r->filter_length + 1) / 2;
+    while (plan_producible(r, in_frames, reflect) < want) {
+        if (reflect >= longest) return -1;
+        reflect++;
+    }
+    return reflect;
+}
+
+// outputs a conversion of in_frames frames can deliver at most (flush: with the longest reflection swr_convert can append)
+static int64_t max_out_count(const nodey_resampler* r, int64_t in_frames, int flush)
+{
+    if (!r->resample) return in_frames;
+    if (!flush) return plan_producible(r, in_frames, 0);
+    const int64_t usual = plan_reflect(r, in_frames, plan_producible(r, in_frames, 0));
+    const int64_t longest = in_frames < r->filter_length ? (in_frames + 1) / 2 : (r->filter_length + 1) / 2;
+    return plan_producible(r, in_frames, longest > usual ? longest : usual);
+}
+
 static int fill_src(SrcDesc* s, const nodey_resampler* r, const void* p0, const void* p1, int fmt, int nch,
-                    int64_t in_frames, int flush)
+                    int64_t in_frames, int flush, int64_t want = 0)
 {
     NODEY_REQUIRE(nch == 1 || nch == 2, NODEY_E_INVALID, "Invalid channel layout: %d", nch);
     NODEY_REQUIRE(fmt_bytes(fmt) != 0, NODEY_E_FORMAT, "resampler: unsupported sample format %d", fmt);
     NODEY_REQUIRE(in_frames >= 0, NODEY_E_INVALID, "resampler: negative input size");
     s->p0 = p0; s->p1 = p1; s->n = in_frames; s->fmt = fmt; s->nch = nch; s->planar = fmt_planar(fmt) ? 1 : 0;
     s->reflect = 0;
-    if (flush && r->resample) s->reflect = plan_reflect(r, in_frames, plan_producible(r, in_frames, 0));
+    if (flush && r->resample) {
+        const int64_t reflect = flush_reflect_for(r, in_frames, want);
+        NODEY_REQUIRE(reflect >= 0, NODEY_E_RANGE, "resampler: %lld outputs exceed what swr would produce from %lld frames", (long long)want, (long long)in_frames);
+        s->reflect = reflect;
+    }
     return NODEY_OK;
 }
 
@@ -909,7 +940,7 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
         NODEY_REQUIRE(out_frames <= in_frames, NODEY_E_RANGE, "nodey_resampler_run: out_frames exceeds input");
         return nodey_to_fltp_stereo(out_l, out_r, p0, p1, fmt, nch, out_frames, stream);
     }
-    const int64_t avail = nodey_resampler_out_count(r, in_frames, flush);
+    const int64_t avail = max_out_count(r, in_frames, flush);
     NODEY_REQUIRE(out_frames >= 0 && out_frames <= avail, NODEY_E_RANGE,
                   "nodey_resampler_run: out_frames %lld exceeds what swr would produce (%lld)", (long long)out_frames, (long long)avail);
     if (out_frames == 0) return NODEY_OK;
@@ -918,7 +949,7 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
         NODEY_REQUIRE(mode < 3 || tile2_ok(r), NODEY_E_RANGE, "pipelined tile kernel unavailable for this plan");
         TileArgs a;
         memset(&a, 0, sizeof(a));
-        int rc = fill_src(&a.src[0], r, p0, p1, fmt, nch, in_frames, flush);
+        int rc = fill_src(&a.src[0], r, p0, p1, fmt, nch, in_frames, flush, out_frames);
         if (rc != NODEY_OK) return rc;
         a.out_len[0] = out_frames; a.vol[0] = 1.f; a.nin = 1; a.mix = 0; a.out_frames = out_frames;
         if (mode >= 3 || (mode == 0 && tile2_ok(r))) {
@@ -930,7 +961,7 @@ int nodey_resampler_run_mode(const nodey_resampler* r, float* out_l, float* out_
         return launch_tile(r, out_l, out_r, a, nch, st);
     }
     SrcDesc s;
-    int rc = fill_src(&s, r, p0, p1, fmt, nch, in_frames, flush);
+    int rc = fill_src(&s, r, p0, p1, fmt, nch, in_frames, flush, out_frames);
     if (rc != NODEY_OK) return rc;
     PlanDev pl{r->d_bank, r->phase_count, r->filter_length, r->filter_alloc, r->dst_incr_div, r->dst_incr_mod, r->src_incr, r->index0};
     NODEY_LAUNCH("resample_generic_kernel", st, resample_generic_kernel<<<stream_grid(out_frames, 256, 8), 256, 0, st>>>(out_l, out_r, s, pl, out_frames));
@@ -958,11 +989,11 @@ int nodey_resample_mix(const nodey_resampler* r, float* out_l, float* out_r, con
     int ch = nch[0];
     for (int i = 0; i < nin; i++) {
         NODEY_REQUIRE(nch[i] == ch, NODEY_E_INVALID, "nodey_resample_mix: inputs must share a channel count");
-        int rc = fill_src(&a.src[i], r, plane0[i], plane1 ? plane1[i] : nullptr, fmt[i], nch[i], in_frames[i], flush);
-        if (rc != NODEY_OK) return rc;
-        const int64_t avail = nodey_resampler_out_count(r, in_frames[i], flush);
+        const int64_t avail = max_out_count(r, in_frames[i], flush);
         NODEY_REQUIRE(out_len[i] >= 0 && out_len[i] <= avail, NODEY_E_RANGE,
                       "nodey_resample_mix: out_len[%d]=%lld exceeds what swr would produce (%lld)", i, (long long)out_len[i], (long long)avail);
+        int rc = fill_src(&a.src[i], r, plane0[i], plane1 ? plane1[i] : nullptr, fmt[i], nch[i], in_frames[i], flush, out_len[i]);
+        if (rc != NODEY_OK) return rc;
         a.out_len[i] = out_len[i];
         a.vol[i] = volumes[i];
     }
@@ -988,11 +1019,11 @@ int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, 
     if (out_frames <= 0) return out_frames == 0 ? NODEY_OK : NODEY_E_INVALID;
     TileArgs a;
     memset(&a, 0, sizeof(a));
-    int rc = fill_src(&a.src[0], r, plane0[0], plane1 ? plane1[0] : nullptr, fmt, nch, in_frames, flush);
-    if (rc != NODEY_OK) return rc;
-    const int64_t avail = nodey_resampler_out_count(r, in_frames, flush);
+    const int64_t avail = max_out_count(r, in_frames, flush);
     NODEY_REQUIRE(out_len >= 0 && out_len <= avail, NODEY_E_RANGE,
                   "nodey_resample_tracks: out_len %lld exceeds what swr would produce (%lld)", (long long)out_len, (long long)avail);
+    int rc = fill_src(&a.src[0], r, plane0[0], plane1 ? plane1[0] : nullptr, fmt, nch, in_frames, flush, out_len);
+    if (rc != NODEY_OK) return rc;
     a.out_len[0] = out_len; a.vol[0] = volumes[0]; a.nin = 1; a.mix = 1; a.out_frames = out_frames;
     a.ntracks = ntracks; a.out_track_stride = out_track_stride;
     static thread_local TrackPlanes tp;

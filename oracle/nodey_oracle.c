@@ -1177,6 +1177,119 @@ int64_t orc_soundtouch(const float* in, int64_t nframes, int nch, int sample_rat
     return got;
 }
 
+/* ---- the streaming object itself: SoundTouch's public calls, for the reference-loop restatement below and for the
+ * stand-in library of the pin harness (tests/fake_soundtouch) ---- */
+struct orc_st { soundtouch s; int sample_rate; };
+
+orc_st* orc_st_create(int sample_rate, int nch, float rate_arg, float pitch_arg)
+{
+    orc_st* h = (orc_st*)calloc(1, sizeof(orc_st));
+    if (!h) return NULL;
+    const double vrate = (double)rate_arg, vpitch = (double)pitch_arg;
+    h->sample_rate = sample_rate;
+    h->s.ch = nch;
+    h->s.tempo = 1.0 / vpitch;
+    h->s.rate = vpitch * vrate;
+    h->s.td_first = !(h->s.rate <= 1.0f);
+    tds_init(&h->s.td, sample_rate, nch, h->s.tempo);
+    rt_init(&h->s.rt, nch, h->s.rate);
+    return h;
+}
+
+void orc_st_destroy(orc_st* h)
+{
+    if (!h) return;
+    tds_free(&h->s.td); rt_free(&h->s.rt);
+    free(h);
+}
+
+void orc_st_put(orc_st* h, const float* x, int64_t n) { if (n > 0) st_put(&h->s, x, n); }
+
+int64_t orc_st_num_samples(orc_st* h) { return st_out(&h->s)->n; }
+
+/* SoundTouch::receiveSamples(): samplesOutput counts what was handed out */
+int64_t orc_st_receive(orc_st* h, float* out, int64_t max_frames)
+{
+    fifo* o = st_out(&h->s);
+    int64_t n = o->n < max_frames ? o->n : max_frames;
+    if (n < 0) n = 0;
+    if (n > 0) memcpy(out, fifo_begin(o), sizeof(float) * (size_t)(n * h->s.ch));
+    fifo_take(o, n);
+    h->s.samples_output += (long)n;
+    return n;
+}
+
+/* SoundTouch::flush(): numStillExpected from what was RECEIVED so far; silent 128-frame blocks (at most 200) until
+ * the output holds that much; trim the output to it; clear TDStretch's input */
+void orc_st_flush(orc_st* h)
+{
+    soundtouch* s = &h->s;
+    int still = (int)((long)(s->expected_out + 0.5) - s->samples_output);
+    if (still < 0) still = 0;
+    float* zeros = (float*)calloc((size_t)(128 * s->ch), sizeof(float));
+    for (int i = 0; (still > (int)st_out(s)->n) && (i < 200); i++) st_put(s, zeros, 128);
+    free(zeros);
+    fifo* o = st_out(s);
+    if (o->n > still) o->n = still;
+    s->td.in.n = 0;                /* pTDStretch->clearInput() */
+}
+
+/* soundtouch_process_payload (audio-velocity.cpp:286-441) with a frame available at every iteration: one putSamples
+ * per loop turn, receiveSamples(min(numSamples, 3 * 1152 / velocity)) whenever more than 1152 / velocity are queued,
+ * and at end of input either the early `break` (output FIFO empty: SURVEY.md App. C7, the tail is lost) or flush() +
+ * one last receive.  chunk_sizes: the frame sizes the node pushes downstream.  *flushed: 1 when flush() was reached. */
+int64_t orc_soundtouch_reference_loop(const float* in, int64_t nframes, int nch, int sample_rate, float velocity, float pitch_arg,
+                                      int frame_size, float* out, int64_t out_cap, int64_t* chunk_sizes, int64_t chunk_cap,
+                                      int64_t* nchunks, int* flushed)
+{
+    orc_st* h = NULL;
+    const double time_ratio = 1.0f / velocity;                 /* const double time_ratio = 1.0f / velocity; (:289) */
+    int64_t pos = 0, got = 0, chunks = 0;
+    int eof = 0, did_flush = 0;
+    for (;;) {
+        if (!eof) {
+            if (pos >= nframes) eof = 1;                       /* try_pop fails and the stream is at EOF */
+            else {
+                const int64_t n = (nframes - pos) < frame_size ? (nframes - pos) : frame_size;
+                if (!h) h = orc_st_create(sample_rate, nch, velocity, pitch_arg);
+                orc_st_put(h, in + (size_t)pos * nch, n);
+                pos += n;
+            }
+        }
+        if (h) {
+            if (orc_st_num_samples(h) == 0 && eof) break;      /* :414 */
+            const uint32_t min_samples = (uint32_t)(time_ratio * 1152);
+            const uint32_t max_samples = (uint32_t)(time_ratio * 1152 * 3);
+            int64_t want = -1;
+            if ((uint64_t)orc_st_num_samples(h) > min_samples) {
+                want = orc_st_num_samples(h);
+                if (want > (int64_t)max_samples) want = max_samples;
+            } else if (eof) {
+                orc_st_flush(h);
+                did_flush = 1;
+                want = orc_st_num_samples(h);
+                if (want <= 0) break;
+            }
+            if (want > 0) {
+                int64_t room = out_cap - got;
+                float* scratch = NULL;
+                float* dst = out + (size_t)got * nch;
+                if (want > room) { scratch = (float*)malloc(sizeof(float) * (size_t)(want * nch)); dst = scratch; }
+                const int64_t n = orc_st_receive(h, dst, want);
+                if (scratch) { if (room > 0) memcpy(out + (size_t)got * nch, scratch, sizeof(float) * (size_t)(room * nch)); free(scratch); }
+                got += n < room ? n : (room > 0 ? room : 0);
+                if (chunk_sizes && chunks < chunk_cap) chunk_sizes[chunks] = n;
+                chunks++;
+                if (did_flush) break;
+            }
+        } else if (eof) break;                                 /* empty input: no SoundTouch object was ever made */
+    }
+    if (nchunks) *nchunks = chunks;
+    if (flushed) *flushed = did_flush;
+    orc_st_destroy(h);
+    return got;
+}
+
 /* ======================================================================================= */
 /* N2 spectrum (new node; FFTW's r2c convention, unnormalised, exp(-2*pi*i*k*n/N)).          */
 /* Window and windowing product are float32; the DFT itself is evaluated in double and       */

@@ -115,6 +115,21 @@ float orc_velocity_node_pitch(float velocity, int keep_pitch);
 
 /* ---- N1 channel split (new node), N2 spectrum (new node) -------------------------------- */
 void orc_split(void* dst_l, void* dst_r, const void* plane0, const void* plane1, int fmt, int64_t nframes);
+/* The streaming object (SoundTouch's public calls on the same model): what the whole-buffer function above drives
+ * eagerly.  Used by the literal restatement of the node's loop below and by the stand-in library of the pin harness. */
+typedef struct orc_st orc_st;
+orc_st* orc_st_create(int sample_rate, int nch, float rate_arg, float pitch_arg);
+void orc_st_destroy(orc_st* h);
+void orc_st_put(orc_st* h, const float* x, int64_t nframes);
+int64_t orc_st_num_samples(orc_st* h);
+int64_t orc_st_receive(orc_st* h, float* out, int64_t max_frames);
+void orc_st_flush(orc_st* h);
+/* soundtouch_process_payload, src/processor/audio-velocity.cpp:286-441, literally (one frame per loop turn): the
+ * reference's receive sizes and its early break before flush() */
+int64_t orc_soundtouch_reference_loop(const float* in, int64_t nframes, int nch, int sample_rate, float velocity, float pitch_arg,
+                                      int frame_size, float* out, int64_t out_cap, int64_t* chunk_sizes, int64_t chunk_cap,
+                                      int64_t* nchunks, int* flushed);
+
 int64_t orc_stft_frames(int64_t nframes, int nfft, int hop);
 /* out: [frames][nfft/2+1] complex64 (re,im interleaved); window: periodic Hann in float32 */
 int64_t orc_stft(const float* x, int64_t nframes, int nfft, int hop, float* out);

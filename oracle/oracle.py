@@ -77,6 +77,21 @@ def lib():
     L.orc_soundtouch.argtypes = [vp, i64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, i64, vp, i64,
                                  C.POINTER(StInfo)]
     L.orc_soundtouch.restype = i64
+    L.orc_st_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float]
+    L.orc_st_create.restype = vp
+    L.orc_st_destroy.argtypes = [vp]
+    L.orc_st_destroy.restype = None
+    L.orc_st_put.argtypes = [vp, vp, i64]
+    L.orc_st_put.restype = None
+    L.orc_st_num_samples.argtypes = [vp]
+    L.orc_st_num_samples.restype = i64
+    L.orc_st_receive.argtypes = [vp, vp, i64]
+    L.orc_st_receive.restype = i64
+    L.orc_st_flush.argtypes = [vp]
+    L.orc_st_flush.restype = None
+    L.orc_soundtouch_reference_loop.argtypes = [vp, i64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, vp, i64, vp, i64,
+                                                C.POINTER(i64), C.POINTER(C.c_int)]
+    L.orc_soundtouch_reference_loop.restype = i64
     L.orc_pitch_node_factor.argtypes = [C.c_float]
     L.orc_pitch_node_factor.restype = C.c_float
     L.orc_velocity_node_pitch.argtypes = [C.c_float, C.c_int]
@@ -259,6 +274,53 @@ def soundtouch(x, sample_rate, rate_arg, pitch_arg, frame_size=1152, want_offset
                                _p(out), cap, _p(offs) if want_offsets else None, ocap, C.byref(info))
     nseq = int(info.n_sequences)
     return out[:got], offs[:max(nseq - 1, 0)], info
+
+
+def soundtouch_reference_loop(x, sample_rate, velocity, pitch_arg, frame_size=1152):
+    """soundtouch_process_payload (audio-velocity.cpp:286-441) literally, one input frame per loop turn: returns
+    (samples, chunk sizes the node pushes downstream, flushed) -- flushed is False when the loop took the early break
+    before flush() and the tail SoundTouch still held was lost."""
+    x = np.ascontiguousarray(x, np.float32)
+    n, nch = x.shape
+    cap = int(n / max(float(velocity), 1e-3)) + 65536
+    out = np.zeros((cap, nch), np.float32)
+    ccap = n // max(frame_size, 1) + 64
+    chunks = np.zeros(ccap, np.int64)
+    nchunks = C.c_int64()
+    flushed = C.c_int()
+    got = lib().orc_soundtouch_reference_loop(_p(x), n, nch, sample_rate, np.float32(velocity), np.float32(pitch_arg), frame_size,
+                                              _p(out), cap, _p(chunks), ccap, C.byref(nchunks), C.byref(flushed))
+    return out[:got], chunks[:min(nchunks.value, ccap)].tolist(), bool(flushed.value)
+
+
+class St:
+    """the streaming SoundTouch model (SoundTouch's public calls): putSamples / numSamples / receiveSamples / flush"""
+
+    def __init__(self, sample_rate, nch, rate_arg, pitch_arg):
+        self.nch = nch
+        self.h = lib().orc_st_create(sample_rate, nch, np.float32(rate_arg), np.float32(pitch_arg))
+
+    def put(self, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.nch)
+        lib().orc_st_put(self.h, _p(x), x.shape[0])
+
+    def num_samples(self):
+        return int(lib().orc_st_num_samples(self.h))
+
+    def receive(self, max_frames):
+        out = np.zeros((max(int(max_frames), 0), self.nch), np.float32)
+        n = lib().orc_st_receive(self.h, _p(out), out.shape[0]) if out.shape[0] else 0
+        return out[:n]
+
+    def flush(self):
+        lib().orc_st_flush(self.h)
+
+    def close(self):
+        if self.h:
+            lib().orc_st_destroy(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 def pitch_node_factor(semitones):

@@ -1,0 +1,17 @@
+"""Development: diagnostics (device span per (wave, level) step) of the config-5 render, T tracks, device-resident."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
+import torch
+import nodey, engine, pipeline
+T, secs = int(os.environ.get("T", "32")), 180
+n = 44100 * secs
+x = torch.empty((T, n, 2), dtype=torch.float32, device="cuda").uniform_(-0.5, 0.5)
+p, ids = engine.config5_project(T, [pipeline.track_gain(t) for t in range(T)])
+e = engine.Engine(p.json())
+for t in range(T):
+    e.bind_source(t, x[t], 3, 44100)
+for it in range(4):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); e.run(); torch.cuda.synchronize()
+    print(f"run {it}: {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+print(e.diagnostics())
