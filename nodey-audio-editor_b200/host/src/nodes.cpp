@@ -852,6 +852,18 @@ namespace processor
 						if (nchunks < 0) abi(nchunks, title);
 					}
 					const bool chunked = in_place && m > 0 && (nchunks > 1 || in_progress);
+					// next to a chunk-wise producer this node runs on the lane's OTHER stream, so that the two overlap.  Its
+					// memory is then allocated in that stream's order too (the allocator hands a block freed on a stream
+					// straight back to that stream): nothing here may order the side stream after what the producer has
+					// already enqueued on the main one
+					nodey_stream_t run = main_stream;
+					if (chunked && in_progress && side_stream) run = in_progress->stream == main_stream ? side_stream : main_stream;
+					struct Stream_scope
+					{
+						nodey_stream_t saved;
+						explicit Stream_scope(nodey_stream_t s) : saved(Exec_context::current().stream) { Exec_context::current().stream = s; }
+						~Stream_scope() { Exec_context::current().stream = saved; }
+					} scope(run);
 					Arena arena(out_stride * sizeof(float) * cnt + (chunked ? Arena::padded(offs_stride * sizeof(int32_t) * cnt) : 0));
 					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
 					std::shared_ptr<Stream_progress> progress;
@@ -859,19 +871,6 @@ namespace processor
 					if (chunked)
 					{
 						int32_t* offs = (int32_t*)arena.take(offs_stride * sizeof(int32_t) * cnt);
-						// run next to a chunk-wise producer: on the lane's other stream, forked from this one (the arena above
-						// was allocated in this stream's order)
-						nodey_stream_t run = main_stream;
-						if (in_progress && side_stream) run = in_progress->stream == main_stream ? side_stream : main_stream;
-						if (run != main_stream)
-						{
-							infra::Device_event fork;
-							fork.record(main_stream);
-							fork.wait_on(run);
-						}
-						if (!in_progress && run != main_stream)
-							for (size_t k = 0; k < cnt; k++)
-								if (all[first + k].in->ready) all[first + k].in->ready->wait_on(run);
 						const bool planes = all[first].in->format == FMT_FLTP && ch == 2;
 						std::vector<const float*> pa(cnt), pb(cnt, nullptr);
 						for (size_t k = 0; k < cnt; k++)

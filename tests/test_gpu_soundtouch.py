@@ -199,8 +199,7 @@ def test_soundtouch_chunked_render_is_bit_identical(nd, orc, nchunks, cfg):
     assert 1 <= len(plan) <= nchunks
     assert plan[-1][0] == n and plan[-1][1] == whole.shape[1]
     assert all(plan[k][0] <= plan[k + 1][0] and plan[k][1] <= plan[k + 1][1] for k in range(len(plan) - 1))
-    if secs * sr > 40 * 4000 and nchunks <= 8:
-        assert len(plan) == nchunks
+    assert len(plan) == min(nchunks, max(1, (offs.shape[1]) // 32)), "at least 32 sequences per launch"
     assert torch.equal(offs, whole_offs), "offset trace of the chunked render"
     assert_bit_equal(got.cpu().numpy(), whole.cpu().numpy(), "chunked vs one launch")
     ref, ro, _ = orc.soundtouch(xs[1], sr, rate, pitch, 1152)
@@ -233,7 +232,7 @@ def test_soundtouch_chunks_of_uncuttable_paths(nd, orc):
     """mono and the rate <= 1 order run as one chunk; a chunk count the plan did not return is rejected"""
     st = nd.SoundTouch(48000, 1, 1.0, orc.pitch_node_factor(3.0))
     assert len(st.chunks(48000 * 5, 1152, 8)) == 1
-    st2 = nd.SoundTouch(48000, 2, 0.8, orc.velocity_node_pitch(0.8, True))
+    st2 = nd.SoundTouch(48000, 2, 0.7, 1.0)            # rate 0.7 <= 1: transposer first, TDStretch last
     assert st2.info()["tdstretch_first"] == 0 and len(st2.chunks(48000 * 5, 1152, 8)) == 1
     st3 = nd.SoundTouch.pitch_node(48000, 2, 3.0)
     import torch
