@@ -432,13 +432,17 @@ def run_ours(args):
     # The render runs as two half-size waves on two compute lanes; kernels of the two lanes overlap, so events around
     # a launch would time its share of the machine, not the kernel.  The profiled step therefore runs the same graph
     # as ONE wave on one lane (NODEY_WAVE larger than the pin count): every launch alone on the device, full batch.
+    # Likewise the WSOLA chains run as ONE launch per node there (NODEY_ST_CHUNKS=1): in the timed steps the pitch and the
+    # tempo node's chunk launches overlap on two streams.
     os.environ["NODEY_WAVE"] = "1000000"
+    os.environ["NODEY_ST_CHUNKS"] = "1"
     step_device()
     nodey.profile_enable(True)
     step_device()
     rep = nodey.profile_report()
     nodey.profile_enable(False)
     del os.environ["NODEY_WAVE"]
+    del os.environ["NODEY_ST_CHUNKS"]
     if rank == 0 and rep:
         peaks = {}
         try:

@@ -16,6 +16,7 @@ on ONE GPU and reports, as BASELINE.md section 2 asks per config:
 Only bench.py imports this module; the oracle is used as the checker and as the timed CPU baseline, never on the GPU path.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -57,10 +58,18 @@ class _Graph:
         for _ in range(2):
             self.eng.run()
         ms = _timed(torch, self.eng.run, self.reps)
+        # per-kernel device time: one launch per WSOLA chain, so that events around a launch time that kernel alone
+        saved = os.environ.get("NODEY_ST_CHUNKS")
+        os.environ["NODEY_ST_CHUNKS"] = "1"
+        self.eng.run()
         nodey.profile_enable(True)
         self.eng.run()
         kernels = nodey.profile_report()
         nodey.profile_enable(False)
+        if saved is None:
+            del os.environ["NODEY_ST_CHUNKS"]
+        else:
+            os.environ["NODEY_ST_CHUNKS"] = saved
         # end to end: pinned host sources, result copied back
         host = [(x.cpu().pin_memory(), fmt, rate) for x, fmt, rate in self.sources]
         h2d = sum(x.numel() * x.element_size() for x, _, _ in host)

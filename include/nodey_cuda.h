@@ -185,6 +185,17 @@ int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, 
                           const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
                           nodey_stream_t stream);
 
+/* nodey_resample_tracks cut into launches along time (like nodey_soundtouch_chunks): chunk c may run once input frames
+ * [0, in_need[c]) of every track are there and makes output frames [0, out_ready[c]) final; the last chunk needs the whole
+ * input (the flush reflects its end).  Chunks run in order, with the same arguments; the result is bit identical to the
+ * one-launch call.  nodey_resample_tracks_chunks returns the number of chunks (<= want_chunks, at least four tiles each). */
+int nodey_resample_tracks_chunks(const nodey_resampler* r, int nch, int64_t in_frames, int64_t out_frames, int want_chunks,
+                                 int64_t* in_need, int64_t* out_ready, int cap);
+int nodey_resample_tracks_chunk(const nodey_resampler* r, float* out_l, float* out_r, int64_t out_track_stride,
+                                const void* const* plane0, const void* const* plane1, int fmt, int nch, int64_t in_frames,
+                                const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
+                                int chunk, int nchunks, nodey_stream_t stream);
+
 /* Time-segment sharding of one long stream across GPUs: outputs [k0, k1) of the flushed
  * conversion of n_in frames depend only on the input slice [*in0, *in1).  Run the resampler on that slice with
  * flush = *flush and out_frames = *skip + (k1 - k0), drop the first *skip outputs: the rest is bit identical

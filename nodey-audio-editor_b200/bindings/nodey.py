@@ -22,7 +22,7 @@ SYMBOLS = [
     "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
     "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
-    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
+    "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resample_tracks_chunks", "nodey_resample_tracks_chunk", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
     "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
@@ -78,6 +78,8 @@ def lib():
     L.nodey_resampler_run.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, vp]
     L.nodey_resampler_run_mode.argtypes = [vp, vp, vp, vp, vp, i32, i32, i64, i32, i64, i32, vp]
     L.nodey_resample_tracks.argtypes = [vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i64, C.POINTER(C.c_float), i32, i32, i64, i64, vp]
+    L.nodey_resample_tracks_chunks.argtypes = [vp, i32, i64, i64, i32, C.POINTER(i64), C.POINTER(i64), i32]
+    L.nodey_resample_tracks_chunk.argtypes = [vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i64, C.POINTER(C.c_float), i32, i32, i64, i64, i32, i32, vp]
     L.nodey_preview_pack.argtypes = [vp, vp, vp, i64, vp]
     L.nodey_gain_tracks.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_float), i32, i32, vp]
     L.nodey_resampler_segment.argtypes = [vp, i64, i64, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
@@ -334,6 +336,35 @@ def _resample_tracks(self, inputs, fmt, volumes, flush=True, out_len=None, out_f
 
 
 Resampler.resample_tracks = _resample_tracks
+
+
+def _resample_tracks_chunked(self, inputs, fmt, volumes, nchunks, flush=True, poison=None):
+    """nodey_resample_tracks cut into chunk launches -> ([ntracks, 2, out_frames], [(in_need, out_ready), ...]).
+    poison(c, in_need): optional hook before chunk c (tests overwrite the input beyond in_need)."""
+    t = _torch()
+    ntr = len(inputs)
+    pls = [planes_of(x, fmt) for x in inputs]
+    n, nch = pls[0][2], pls[0][3]
+    m = self.out_count(n, flush)
+    a = (C.c_int64 * max(nchunks, 1))(); b = (C.c_int64 * max(nchunks, 1))()
+    k = lib().nodey_resample_tracks_chunks(self.h, nch, n, m, nchunks, a, b, max(nchunks, 1))
+    if k < 0:
+        raise NodeyError(k, "nodey_resample_tracks_chunks")
+    plan = [(a[c], b[c]) for c in range(k)]
+    stride = (m + 63) & ~63
+    out = t.full((ntr, 2, stride), float("nan"), dtype=t.float32, device=inputs[0].device)
+    p0 = (C.c_void_p * ntr)(*[p[0].data_ptr() for p in pls])
+    p1 = (C.c_void_p * ntr)(*[(p[1].data_ptr() if p[1] is not None else 0) for p in pls])
+    vol = (C.c_float * ntr)(*[float(v) for v in volumes])
+    for c in range(k):
+        if poison is not None:
+            poison(c, plan[c][0])
+        check(lib().nodey_resample_tracks_chunk(self.h, _dp(out[0, 0]), _dp(out[0, 1]), out.stride(0), p0, p1, fmt, nch, n, vol, ntr,
+                                                1 if flush else 0, m, m, c, k, _stream()))
+    return out[:, :, :m], plan
+
+
+Resampler.resample_tracks_chunked = _resample_tracks_chunked
 
 
 def _resampler_segment(self, n_in, k0, k1):

@@ -189,6 +189,8 @@ struct TileArgs {
     int vec_out;             // 128-bit stores allowed: planes 16-byte aligned and P a multiple of 4
     int ntracks;             // pipelined kernel: tracks of the batch (per-track planes in TrackPlanes), 1 otherwise
     long long out_track_stride;   // floats between the output planes of consecutive tracks
+    long long tile0, tile1;  // pipelined kernel: this launch covers tiles [tile0, tile1) of every track (tile1 = 0: all) --
+                             // a render cut along time, so that the next node can start on a prefix (nodey_resample_tracks_chunk)
 };
 
 // fast staging test: the whole tile lies inside the real input (no mirror / reflection / zero fill)
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
     const auto stage = [&](long long item, int inp, int b, int* lead) -> int {
         float* dst = s_in0 + b * buf_floats;
         *lead = 0;
-        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
+        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles + a.tile0;
         const long long k0 = tile * (long long)NBT * a.P;
         if (k0 >= a.out_len[inp]) return 0;                     // contributes zeros: nothing is read
         const long long in0 = tile * (long long)NBT * a.D + a.s0 - a.center;
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
         tma_nxt = 0; lead_nxt = 0;
         if (nitem < total) tma_nxt = stage(nitem, ninp, cur ^ 1, &lead_nxt);
 
-        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles;
+        const long long track = item / a.n_tiles, tile = item - track * a.n_tiles + a.tile0;
         const long long k0 = tile * (long long)NBT * a.P;
         const float* s_in = s_in0 + cur * buf_floats + lead_cur * CH;
         const float vol = MIX ? a.vol[inp] : tp.vol[track];
@@ -889,7 +891,9 @@ static int launch_tile(const nodey_resampler* r, float* out_l, float* out_r, Til
 // pipelined tile kernel: plans with one phase group per warp
 static bool tile2_ok(const nodey_resampler* r) { return r->tile_ok && r->n_groups <= 20; }
 
-static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, const TrackPlanes& tp, int ch, cudaStream_t st, int force_pt = 0)
+// periods per thread and shared memory of the pipelined kernel for this plan (a, ch): two periods per thread when the
+// double-buffered 64-period tile fits one SM
+static int tile2_shape(const nodey_resampler* r, TileArgs& a, int ch, int force_pt, size_t* smem_out)
 {
     a.hq = r->d_hq; a.group_start = r->d_group_start;
     tile_geometry(r, a, ch);
@@ -898,13 +902,25 @@ static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, Ti
         const size_t in_tile = (size_t)(kNB * pt - 1) * a.D + a.span + a.wmax + 1;
         return sizeof(float) * (table + 2 * (((in_tile + 2) * ch + 3) & ~(size_t)3));
     };
-    // two periods per thread when the double-buffered 64-period tile fits one SM
     int pt = smem_for(2) <= 227 * 1024 ? 2 : 1;
     if (force_pt) pt = force_pt;
-    const size_t smem = smem_for(pt);
+    *smem_out = smem_for(pt);
+    return pt;
+}
+
+static int launch_tile2(const nodey_resampler* r, float* out_l, float* out_r, TileArgs& a, const TrackPlanes& tp, int ch, cudaStream_t st, int force_pt = 0)
+{
+    size_t smem = 0;
+    const int pt = tile2_shape(r, a, ch, force_pt, &smem);
     NODEY_REQUIRE(smem <= 227 * 1024, NODEY_E_RANGE, "resample tile kernel: plan needs %zu bytes of shared memory", smem);
     const int64_t per_tile = (int64_t)kNB * pt * a.P;
-    a.n_tiles = (a.out_frames + per_tile - 1) / per_tile;
+    {
+        const int64_t all = (a.out_frames + per_tile - 1) / per_tile;
+        const int64_t t1 = a.tile1 > 0 && a.tile1 < all ? a.tile1 : all;
+        if (a.tile0 < 0) a.tile0 = 0;
+        a.n_tiles = t1 - a.tile0;
+        if (a.n_tiles <= 0) return NODEY_OK;
+    }
     if (a.ntracks < 1) a.ntracks = 1;
     a.vec_out = (((uintptr_t)out_l | (uintptr_t)out_r) & 15) == 0 && a.P % 4 == 0 && a.out_track_stride % 4 == 0;
     const bool mix = a.nin > 1;
@@ -1035,6 +1051,79 @@ int nodey_resample_tracks(const nodey_resampler* r, float* out_l, float* out_r, 
 }
 
 /* time-segment sharding of one long stream: see nodey_cuda.h */
+// chunk c of n: tiles [c * per, (c + 1) * per) of the pipelined kernel's tiling
+static void resample_chunk_range(const nodey_resampler* r, int ch, int64_t out_frames, int c, int n, int64_t* tile0, int64_t* tile1,
+                                 int64_t* per_tile_out, int64_t* in_need, int64_t in_frames)
+{
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    size_t smem = 0;
+    const int pt = tile2_shape(r, a, ch, 0, &smem);
+    const int64_t per_tile = (int64_t)kNB * pt * a.P;
+    const int64_t all = (out_frames + per_tile - 1) / per_tile;
+    const int64_t per = (all + n - 1) / n;
+    *tile0 = (int64_t)c * per < all ? (int64_t)c * per : all;
+    *tile1 = c >= n - 1 ? all : ((int64_t)(c + 1) * per < all ? (int64_t)(c + 1) * per : all);
+    *per_tile_out = per_tile;
+    // input a tile reads: in_tile frames (+ 2 for the aligned bulk copy) from tile * periods * D + s0 - center
+    const int64_t in_tile = (int64_t)(kNB * pt - 1) * a.D + a.span + a.wmax + 1;
+    const int64_t need = (*tile1 - 1) * (int64_t)kNB * pt * a.D + a.s0 - a.center + in_tile + 4;
+    *in_need = (c >= n - 1 || need > in_frames) ? in_frames : (need < 0 ? 0 : need);
+}
+
+int nodey_resample_tracks_chunks(const nodey_resampler* r, int nch, int64_t in_frames, int64_t out_frames, int want_chunks,
+                                 int64_t* in_need, int64_t* out_ready, int cap)
+{
+    NODEY_REQUIRE(r && (nch == 1 || nch == 2) && in_frames >= 0 && out_frames >= 0, NODEY_E_INVALID, "nodey_resample_tracks_chunks: bad argument");
+    NODEY_REQUIRE(r->resample && tile2_ok(r), NODEY_E_RANGE, "nodey_resample_tracks_chunks: plan has no pipelined tile kernel");
+    int64_t t0, t1, per_tile, need;
+    resample_chunk_range(r, nch, out_frames, 0, 1, &t0, &t1, &per_tile, &need, in_frames);
+    int n = want_chunks < 1 ? 1 : want_chunks;
+    if ((int64_t)n > t1 / 4) n = (int)(t1 / 4);           // at least four tiles per launch and track
+    if (n < 1) n = 1;
+    for (int c = 0; c < n && c < cap; c++) {
+        resample_chunk_range(r, nch, out_frames, c, n, &t0, &t1, &per_tile, &need, in_frames);
+        if (in_need) in_need[c] = need;
+        if (out_ready) out_ready[c] = (c == n - 1 || t1 * per_tile > out_frames) ? out_frames : t1 * per_tile;
+    }
+    return n;
+}
+
+int nodey_resample_tracks_chunk(const nodey_resampler* r, float* out_l, float* out_r, int64_t out_track_stride,
+                                const void* const* plane0, const void* const* plane1, int fmt, int nch, int64_t in_frames,
+                                const float* volumes, int ntracks, int flush, int64_t out_len, int64_t out_frames,
+                                int chunk, int nchunks, nodey_stream_t stream)
+{
+    NODEY_REQUIRE(r && out_l && out_r && plane0 && volumes, NODEY_E_INVALID, "nodey_resample_tracks_chunk: null argument");
+    NODEY_REQUIRE(ntracks >= 1 && ntracks <= kMaxResampleBatch, NODEY_E_RANGE, "nodey_resample_tracks_chunk: 1..%d tracks per call", kMaxResampleBatch);
+    NODEY_REQUIRE(r->resample && tile2_ok(r), NODEY_E_RANGE, "nodey_resample_tracks_chunk: plan has no pipelined tile kernel (use nodey_resample_mix per track)");
+    NODEY_REQUIRE(out_track_stride >= out_frames, NODEY_E_INVALID, "nodey_resample_tracks_chunk: out_track_stride smaller than out_frames");
+    NODEY_REQUIRE(nchunks >= 1 && chunk >= 0 && chunk < nchunks, NODEY_E_RANGE, "nodey_resample_tracks_chunk: chunk %d of %d", chunk, nchunks);
+    if (out_frames <= 0) return out_frames == 0 ? NODEY_OK : NODEY_E_INVALID;
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    const int64_t avail = max_out_count(r, in_frames, flush);
+    NODEY_REQUIRE(out_len >= 0 && out_len <= avail, NODEY_E_RANGE,
+                  "nodey_resample_tracks_chunk: out_len %lld exceeds what swr would produce (%lld)", (long long)out_len, (long long)avail);
+    int rc = fill_src(&a.src[0], r, plane0[0], plane1 ? plane1[0] : nullptr, fmt, nch, in_frames, flush, out_len);
+    if (rc != NODEY_OK) return rc;
+    a.out_len[0] = out_len; a.vol[0] = volumes[0]; a.nin = 1; a.mix = 1; a.out_frames = out_frames;
+    a.ntracks = ntracks; a.out_track_stride = out_track_stride;
+    int64_t per_tile, need;
+    {
+        int64_t t0, t1;
+        resample_chunk_range(r, nch, out_frames, chunk, nchunks, &t0, &t1, &per_tile, &need, in_frames);
+        if (t1 <= t0) return NODEY_OK;
+        a.tile0 = t0; a.tile1 = t1;
+    }
+    static thread_local TrackPlanes tp;
+    for (int t = 0; t < ntracks; t++) {
+        NODEY_REQUIRE(plane0[t], NODEY_E_INVALID, "nodey_resample_tracks_chunk: null plane");
+        tp.p0[t] = plane0[t]; tp.p1[t] = plane1 ? plane1[t] : nullptr; tp.vol[t] = volumes[t];
+    }
+    return launch_tile2(r, out_l, out_r, a, tp, nch, as_stream(stream));
+}
+
 int nodey_resampler_segment(const nodey_resampler* r, int64_t n_in, int64_t k0, int64_t k1,
                             int64_t* in0, int64_t* in1, int64_t* skip, int* flush)
 {

@@ -855,19 +855,37 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                 filt[threadIdx.x * (kFirS + 1) + r] = make_float2(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]));
         }
         __syncthreads();
-        // cubic transposer over the tile (InterpolateCubic::transposeStereo)
-        const double inv = 1.0 / (double)(1ull << a.e);
+        // cubic transposer over the tile (InterpolateCubic::transposeStereo).  The read position of output i is i * R in
+        // 2^-e fixed point (128 bits): one product per thread and tile, then a 128-bit add of blockDim * R per output.
+        // Fraction: (float)((double)fb * 2^-e) with fb < 2^e <= 2^53 is ONE rounding of fb * 2^-e to 24 bits, which is
+        // what the unsigned 64-bit -> float conversion does; the power-of-two scale afterwards is exact.
+        // Coefficients: y_r = ((c0*x0 + c1*x1) + c2*x2) + c3 as InterpolateCubic.cpp spells them; products with the
+        // constants 1.0f and 0.0f and the additions of the resulting +0 are dropped where that cannot change a bit: x2 is in
+        // [0, 1), so x1, x0 >= +0, 0.0f * x2 = +0, and a + (+0) differs from a only for a = -0, which none of the partial
+        // sums below can be (a sum is -0 only when both addends are; every sum here has an addend that is +0 or positive).
+        const float inv_f = __uint_as_float((unsigned)(127 - a.e) << 23);          // 2^-e, e <= 60: a normal float
+        const unsigned long long fmask = (1ull << a.e) - 1ull;
+        unsigned long long p_lo, p_hi;
+        {
+            const unsigned long long i0 = (unsigned long long)(i_lo + threadIdx.x);
+            p_lo = i0 * a.R; p_hi = __umul64hi(i0, a.R);
+        }
+        const unsigned long long step_lo = (unsigned long long)blockDim.x * a.R, step_hi = __umul64hi((unsigned long long)blockDim.x, a.R);
         for (long long i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-            const unsigned long long lo = (unsigned long long)i * a.R;
-            const long long P = cubic_pos((unsigned long long)i, a.R, a.e);
-            const unsigned long long fb = lo & ((1ull << a.e) - 1ull);
-            const float x2 = (float)((double)fb * inv);
+            const long long P = (long long)((p_lo >> a.e) | (a.e ? (p_hi << (64 - a.e)) : 0ull));
+            const unsigned long long fb = p_lo & fmask;
+            {
+                const unsigned long long n_lo = p_lo + step_lo;
+                p_hi += step_hi + (n_lo < p_lo ? 1ull : 0ull);
+                p_lo = n_lo;
+            }
+            const float x2 = __fmul_rn(__ull2float_rn(fb), inv_f);
             const float x1 = __fmul_rn(x2, x2);
             const float x0 = __fmul_rn(x1, x2);
-            const float y0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), __fmul_rn(1.0f, x1)), __fmul_rn(-0.5f, x2)), __fmul_rn(0.0f, 1.0f));
-            const float y1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(1.0f, 1.0f));
-            const float y2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2)), __fmul_rn(0.0f, 1.0f));
-            const float y3 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1)), __fmul_rn(0.0f, x2)), __fmul_rn(0.0f, 1.0f));
+            const float y0 = __fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), x1), __fmul_rn(-0.5f, x2));
+            const float y1 = __fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), 1.0f);
+            const float y2 = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2));
+            const float y3 = __fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1));
             const int q = (int)(P - n0);
             const auto at = [&](int f) { return filt[f + (f >> 3)]; };
             const float2 p0 = at(q), p1 = at(q + 1), p2 = at(q + 2), p3 = at(q + 3);

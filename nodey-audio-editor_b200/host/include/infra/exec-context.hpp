@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <vector>
 
 namespace infra
 {
@@ -15,9 +16,13 @@ namespace infra
 	struct Exec_context
 	{
 		Stream_handle stream = nullptr;   // launch everything of the current node (batch) on this stream
-		// second stream of the lane (may be null): a node whose input arrives chunk by chunk (Audio_buffer::progress) runs on
-		// the stream its producer does NOT use, so that the two overlap; it publishes with an event recorded there
-		Stream_handle side_stream = nullptr;
+		// further streams of the lane (may be null): a node whose input arrives chunk by chunk (Audio_buffer::progress) runs
+		// on the stream AFTER its producer's in the cycle stream -> side[0] -> side[1] -> stream, so that a chain of such
+		// nodes (resampler -> pitch -> tempo) overlaps stage by stage; it publishes with an event recorded there
+		Stream_handle side_stream[2] = {nullptr, nullptr};
+		// source level only: the pin positions at which the Runner's waves begin (ascending, first = 0; empty = one
+		// wave).  A source that uploads chunk by chunk interleaves the chunks of the pins of one wave.
+		const std::vector<int>* wave_begin = nullptr;
 		int level = 0;                    // graph level being executed
 		int lane = 0;                     // index of the stream inside the level
 

@@ -86,6 +86,7 @@ namespace infra
 		int device = -1;     // CUDA device of the creating thread; the worker thread binds to it
 		std::vector<std::vector<Id_t>> levels;
 		std::map<Id_t, int> node_wave;          // which block of source pins feeds the node (see launch_threads)
+		std::vector<int> wave_begin;            // first source-pin position of every wave
 		std::vector<Level_timing> level_timings;
 		std::map<Id_t, std::shared_ptr<std::any>> node_data;
 		std::map<Id_t, std::shared_ptr<Processor::Product>> link_products;

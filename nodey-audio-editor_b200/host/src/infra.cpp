@@ -502,7 +502,7 @@ namespace infra
 			for (const Id_t id : levels.front())
 				for (const auto& attribute : graph.nodes.at(id).processor->get_pin_attributes())
 					if (!attribute.is_input) source_pins++;
-		std::vector<int> wave_begin{0};      // first pin position of every wave
+		wave_begin.assign(1, 0);             // first pin position of every wave
 		if (const char* env = getenv("NODEY_WAVES"))
 		{
 			// development: explicit wave sizes "32,64,48" (the last one repeats)
@@ -637,9 +637,9 @@ namespace infra
 		const int kLanes = 1 + compute_lanes;
 		nodey_stream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 		// every compute lane has a side stream: a node that consumes a stream chunk by chunk runs there, next to its producer
-		nodey_stream_t sides[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+		nodey_stream_t sides[2][kMaxLanes] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
 		const auto release_lanes = [&] {
-			for (auto* set : {&lanes, &sides})
+			for (auto* set : {&lanes, &sides[0], &sides[1]})
 				for (auto& s : *set)
 				{
 					if (!s) continue;
@@ -655,10 +655,11 @@ namespace infra
 			if (nodey_stream_create(&lanes[k]) != NODEY_OK) { lanes[k] = nullptr; failed = true; break; }
 			Lane_registry::add(lanes[k], k >= 1);
 			if (k >= 1 && getenv("NODEY_NO_SIDE_STREAMS") == nullptr)
-			{
-				if (nodey_stream_create(&sides[k]) != NODEY_OK) { sides[k] = nullptr; failed = true; break; }
-				Lane_registry::add(sides[k], true);
-			}
+				for (auto& side : sides)
+				{
+					if (nodey_stream_create(&side[k]) != NODEY_OK) { side[k] = nullptr; failed = true; break; }
+					Lane_registry::add(side[k], true);
+				}
 		}
 		if (failed)
 		{
@@ -685,7 +686,9 @@ namespace infra
 				if (failed) return;
 				Exec_context& ctx = Exec_context::current();
 				ctx.stream = lanes[lane];
-				ctx.side_stream = sides[lane];
+				ctx.side_stream[0] = sides[0][lane];
+				ctx.side_stream[1] = sides[1][lane];
+				ctx.wave_begin = level_index == 0 ? &wave_begin : nullptr;
 				ctx.level = level_index;
 				ctx.lane = lane;
 
@@ -763,7 +766,7 @@ namespace infra
 				{
 					const auto t_enq = std::chrono::steady_clock::now();
 					for (auto& s : lanes) if (s) nodey_stream_synchronize(s);
-					for (auto& s : sides) if (s) nodey_stream_synchronize(s);
+					for (auto& side : sides) for (auto& s : side) if (s) nodey_stream_synchronize(s);
 					const auto t_end = std::chrono::steady_clock::now();
 					fprintf(stderr, "[nodey trace] wave %d level %zu: %zu nodes (%s...), enqueue %.2f ms, drained after %.2f ms\n", wave, level_index,
 							ids.size(), processor_resources.at(ids.front())->processor->get_processor_info_non_static().identifier.c_str(),
@@ -773,8 +776,9 @@ namespace infra
 			}
 		for (auto& s : lanes)
 			if (s) nodey_stream_synchronize(s);
-		for (auto& s : sides)
-			if (s) nodey_stream_synchronize(s);
+		for (auto& side : sides)
+			for (auto& s : side)
+				if (s) nodey_stream_synchronize(s);
 		// everything has drained: turn the step events into timings (the run's origin is the first step's begin)
 		for (auto& se : steps)
 		{

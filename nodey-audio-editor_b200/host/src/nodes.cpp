@@ -106,6 +106,53 @@ namespace processor
 			for (auto& stream : infra::get_output_item<Audio_stream>(output, key)) stream->publish(buffer);
 		}
 
+		// the stream a chunk-wise consumer runs on: the one after its producer's in the lane's cycle
+		// stream -> side[0] -> side[1] -> stream (a producer outside the lane, e.g. the transfer lane: the lane's own stream)
+		nodey_stream_t stream_after(const Stream_progress* producer)
+		{
+			const Exec_context& ctx = Exec_context::current();
+			if (!producer || !ctx.side_stream[0]) return ctx.stream;
+			if (producer->stream == ctx.stream) return ctx.side_stream[0];
+			if (producer->stream == ctx.side_stream[0] && ctx.side_stream[1]) return ctx.side_stream[1];
+			return ctx.stream;
+		}
+
+		// orders a stream after the progress points of a chunk-wise input, one point at a time
+		struct Progress_waiter
+		{
+			const Stream_progress* progress;
+			size_t waited = 0;
+			void need(int64_t frames, nodey_stream_t stream)
+			{
+				if (!progress) return;
+				while (waited < progress->points.size() && (waited == 0 || progress->points[waited - 1].frames < frames))
+					progress->points[waited++].event->wait_on(stream);
+			}
+			void all(nodey_stream_t stream)
+			{
+				if (!progress) return;
+				while (waited < progress->points.size()) progress->points[waited++].event->wait_on(stream);
+			}
+		};
+
+		// launches of the current node go to `s` (and its allocations follow that stream's order) while this lives
+		struct Stream_scope
+		{
+			nodey_stream_t saved;
+			explicit Stream_scope(nodey_stream_t s) : saved(Exec_context::current().stream) { Exec_context::current().stream = s; }
+			~Stream_scope() { Exec_context::current().stream = saved; }
+			Stream_scope(const Stream_scope&) = delete;
+			Stream_scope& operator=(const Stream_scope&) = delete;
+		};
+
+		// how many launches / copies a stream is cut into along time (1 = whole-track); NODEY_ST_CHUNKS overrides (read per
+		// call: bench.py times kernels one at a time with 1)
+		int stream_chunk_count()
+		{
+			const char* env = getenv("NODEY_ST_CHUNKS");
+			return env ? std::clamp(atoi(env), 1, 64) : 8;
+		}
+
 		std::shared_ptr<Audio_buffer> new_buffer(const std::shared_ptr<infra::Device_block>& block, void* p0, void* p1, int fmt, int rate,
 												 int ch, int64_t frames, Frame_runs runs, double pts)
 		{
@@ -523,32 +570,78 @@ namespace processor
 		std::unique_ptr<Arena> arena;
 		if (upload_bytes) arena = std::make_unique<Arena>(upload_bytes);
 
-		for (size_t i = 0; i < file_count; i++)
+		// Uploads go wave by wave (the blocks of pins the Runner pipelines the graph over): inside a wave whose sources
+		// have one length the copies are interleaved chunk by chunk along time -- chunk c of every track, then chunk c + 1
+		// -- and an event after each round tells the consumers which prefix has landed (Audio_buffer::progress), so the
+		// wave's resamplers and WSOLA chains start while the rest of its audio is still on the bus.
+		std::vector<int> wave_first{0};
+		if (const auto* waves = Exec_context::current().wave_begin; waves && !waves->empty()) wave_first = *waves;
+		wave_first.push_back((int)file_count);
+		constexpr size_t kMinChunkBytes = 1u << 20;
+		for (size_t w = 0; w + 1 < wave_first.size(); w++)
 		{
-			const Pcm_source& s = sources[i];
-			const std::string key = std::format("output_{}", i);
-			const auto find = output.find(key);
-			if (!s.data || find == output.end() || find->second.empty()) continue;
-			if (format_bytes(s.format) == 0 || (s.channels != 1 && s.channels != 2))
-				throw Runtime_error("Unsupported sample format", "PCM sources must be S16/S32/FLT (packed or planar), mono or stereo.", key);
-			const size_t plane_bytes = (size_t)s.frames * (size_t)format_bytes(s.format) * (format_is_planar(s.format) ? 1u : (size_t)s.channels);
-			void* p0 = const_cast<void*>(s.data);
-			void* p1 = const_cast<void*>(s.data1);
-			std::shared_ptr<infra::Device_block> owner;
-			if (!s.on_device)
+			struct Pending { size_t pin; void* p0; void* p1; size_t frame_bytes; bool planar2; std::shared_ptr<Audio_buffer> buffer; };
+			std::vector<Pending> uploads;
+			for (size_t i = (size_t)std::max(wave_first[w], 0); i < (size_t)wave_first[w + 1] && i < file_count; i++)
 			{
-				owner = arena->block;
+				const Pcm_source& s = sources[i];
+				const std::string key = std::format("output_{}", i);
+				const auto find = output.find(key);
+				if (!s.data || find == output.end() || find->second.empty()) continue;
+				if (format_bytes(s.format) == 0 || (s.channels != 1 && s.channels != 2))
+					throw Runtime_error("Unsupported sample format", "PCM sources must be S16/S32/FLT (packed or planar), mono or stereo.", key);
+				const size_t frame_bytes = (size_t)format_bytes(s.format) * (format_is_planar(s.format) ? 1u : (size_t)s.channels);
+				const size_t plane_bytes = (size_t)s.frames * frame_bytes;
+				void* p0 = const_cast<void*>(s.data);
+				void* p1 = const_cast<void*>(s.data1);
+				std::shared_ptr<infra::Device_block> owner;
 				const bool planar2 = format_is_planar(s.format) && s.channels == 2;
-				p0 = arena->take(planar2 ? 2 * Arena::padded(plane_bytes) : plane_bytes);
-				abi(nodey_memcpy_h2d(p0, s.data, plane_bytes, cur_stream()), "audio_input");
-				if (planar2)
+				if (!s.on_device)
 				{
-					p1 = (char*)p0 + Arena::padded(plane_bytes);
-					abi(nodey_memcpy_h2d(p1, s.data1, plane_bytes, cur_stream()), "audio_input");
+					owner = arena->block;
+					p0 = arena->take(planar2 ? 2 * Arena::padded(plane_bytes) : plane_bytes);
+					if (planar2) p1 = (char*)p0 + Arena::padded(plane_bytes);
 				}
+				auto buffer = new_buffer(owner, p0, p1, s.format, s.sample_rate, s.channels, s.frames, uniform_frame_runs(s.frames, s.frame_size), s.pts_seconds);
+				if (s.on_device) publish(output, key, buffer);
+				else uploads.push_back({i, p0, p1, frame_bytes, planar2, std::move(buffer)});
 			}
-			publish(output, key, new_buffer(owner, p0, p1, s.format, s.sample_rate, s.channels, s.frames,
-											uniform_frame_runs(s.frames, s.frame_size), s.pts_seconds));
+			if (uploads.empty()) continue;
+			// chunk-wise only when every upload of the wave has the same length (one progress object serves them all) and
+			// a chunk is worth a copy of its own
+			int nchunks = stream_chunk_count();
+			const int64_t frames = uploads.front().buffer->frames;
+			for (const Pending& u : uploads)
+				if (u.buffer->frames != frames) nchunks = 1;
+			while (nchunks > 1 && (size_t)(frames / nchunks) * uploads.front().frame_bytes < kMinChunkBytes) nchunks /= 2;
+			if (nchunks < 1) nchunks = 1;
+			auto progress = std::make_shared<Stream_progress>();
+			progress->stream = cur_stream();
+			for (int c = 0; c < nchunks; c++)
+			{
+				for (const Pending& u : uploads)
+				{
+					const int64_t total = u.buffer->frames;
+					const int64_t f0 = nchunks == 1 ? 0 : ((total * c / nchunks) & ~(int64_t)63);
+					const int64_t f1 = c == nchunks - 1 ? total : ((total * (c + 1) / nchunks) & ~(int64_t)63);
+					if (f1 <= f0) continue;
+					const Pcm_source& s = sources[u.pin];
+					abi(nodey_memcpy_h2d((char*)u.p0 + (size_t)f0 * u.frame_bytes, (const char*)s.data + (size_t)f0 * u.frame_bytes,
+										 (size_t)(f1 - f0) * u.frame_bytes, cur_stream()), "audio_input");
+					if (u.planar2)
+						abi(nodey_memcpy_h2d((char*)u.p1 + (size_t)f0 * u.frame_bytes, (const char*)s.data1 + (size_t)f0 * u.frame_bytes,
+											 (size_t)(f1 - f0) * u.frame_bytes, cur_stream()), "audio_input");
+				}
+				auto ev = std::make_shared<infra::Device_event>();
+				ev->record(cur_stream());
+				progress->points.push_back({c == nchunks - 1 ? frames : ((frames * (c + 1) / nchunks) & ~(int64_t)63), ev});
+			}
+			for (Pending& u : uploads)
+			{
+				u.buffer->ready = progress->points.back().event;
+				if (nchunks > 1) u.buffer->progress = progress;
+				publish(output, std::format("output_{}", u.pin), u.buffer);
+			}
 		}
 		// file payloads are pageable host memory: make sure the copies have landed before they are freed
 		if (!files.empty()) abi(nodey_stream_synchronize(cur_stream()), "audio_input");
@@ -792,13 +885,6 @@ namespace processor
 		constexpr int kSoundtouchFrame = 1152;     // canonical putSamples / output chunk
 		constexpr size_t kMaxTracksPerLaunch = 256;
 
-		// how many launches a track's WSOLA chain is cut into (1 = whole-track launches); NODEY_ST_CHUNKS overrides
-		int soundtouch_chunk_count()
-		{
-			static const int n = [] { const char* env = getenv("NODEY_ST_CHUNKS"); return env ? std::clamp(atoi(env), 1, 64) : 8; }();
-			return n;
-		}
-
 		bool soundtouch_batch(const std::vector<Processor::Batch_item>& items, const char* title)
 		{
 			struct Entry { size_t item; std::shared_ptr<const Audio_buffer> in; Soundtouch_params prm; };
@@ -816,7 +902,6 @@ namespace processor
 				groups[{in->sample_rate, in->channels, in->frames, rb, pb, pg}].push_back({k, std::move(in), prm});
 			}
 			const nodey_stream_t main_stream = cur_stream();
-			const nodey_stream_t side_stream = Exec_context::current().side_stream;
 			for (auto& [key, all] : groups)
 			{
 				const auto [rate_hz, ch, n, rb_, pb_, pg_] = key;
@@ -848,7 +933,7 @@ namespace processor
 					int nchunks = 1;
 					if (in_place && m > 0)
 					{
-						nchunks = nodey_soundtouch_chunks(st, n, kSoundtouchFrame, m, soundtouch_chunk_count(), in_need, out_ready, kMaxChunks);
+						nchunks = nodey_soundtouch_chunks(st, n, kSoundtouchFrame, m, stream_chunk_count(), in_need, out_ready, kMaxChunks);
 						if (nchunks < 0) abi(nchunks, title);
 					}
 					const bool chunked = in_place && m > 0 && (nchunks > 1 || in_progress);
@@ -856,14 +941,8 @@ namespace processor
 					// memory is then allocated in that stream's order too (the allocator hands a block freed on a stream
 					// straight back to that stream): nothing here may order the side stream after what the producer has
 					// already enqueued on the main one
-					nodey_stream_t run = main_stream;
-					if (chunked && in_progress && side_stream) run = in_progress->stream == main_stream ? side_stream : main_stream;
-					struct Stream_scope
-					{
-						nodey_stream_t saved;
-						explicit Stream_scope(nodey_stream_t s) : saved(Exec_context::current().stream) { Exec_context::current().stream = s; }
-						~Stream_scope() { Exec_context::current().stream = saved; }
-					} scope(run);
+					const nodey_stream_t run = chunked ? stream_after(in_progress.get()) : main_stream;
+					Stream_scope scope(run);
 					Arena arena(out_stride * sizeof(float) * cnt + (chunked ? Arena::padded(offs_stride * sizeof(int32_t) * cnt) : 0));
 					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
 					std::shared_ptr<Stream_progress> progress;
@@ -880,20 +959,17 @@ namespace processor
 						}
 						progress = std::make_shared<Stream_progress>();
 						progress->stream = run;
-						size_t waited = 0;      // progress points of the input already waited for
+						Progress_waiter input{in_progress.get()};
 						for (int c = 0; c < nchunks; c++)
 						{
-							if (in_progress)
-								while (waited < in_progress->points.size() && (waited == 0 || in_progress->points[waited - 1].frames < in_need[c]))
-									in_progress->points[waited++].event->wait_on(run);
+							input.need(in_need[c], run);
 							abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
 																  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, run), title);
 							auto ev = std::make_shared<infra::Device_event>();
 							ev->record(run);
 							progress->points.push_back({out_ready[c], ev});
 						}
-						if (in_progress)      // whatever the chunk plan needed, the product is complete only after the whole input is
-							while (waited < in_progress->points.size()) in_progress->points[waited++].event->wait_on(run);
+						input.all(run);       // whatever the chunk plan needed, the product is complete only after the whole input is
 						done = progress->points.back().event;
 					}
 					else if (in_place)
@@ -1127,7 +1203,10 @@ namespace processor
 			std::vector<int> rates;
 			for (int i = 0; i < nin; i++)
 			{
-				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer"));
+				// a chunk-wise input is not waited for here: the batch path below consumes it chunk by chunk, every other
+				// path waits in amix_execute
+				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer", false));
+				if (!job.ins.back()->progress && job.ins.back()->ready) job.ins.back()->ready->wait_on(cur_stream());
 				check_channels(*job.ins.back(), "Audio mixer");
 				runs.push_back(&job.ins.back()->runs);
 				rates.push_back(job.ins.back()->sample_rate);
@@ -1191,12 +1270,14 @@ namespace processor
 		}
 
 		void amix_publish(const Amix_job& job, const Processor::Output_map& output, const std::shared_ptr<infra::Device_block>& block,
-						  float* out_l, float* out_r)
+						  float* out_l, float* out_r, const std::shared_ptr<const Stream_progress>& progress = nullptr)
 		{
 			// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
 			Frame_runs out_runs = job.plan->out_runs;
 			const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;
-			publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), pts));
+			auto buffer = new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), pts);
+			if (progress && !progress->points.empty()) { buffer->ready = progress->points.back().event; buffer->progress = progress; }
+			publish(output, "output", buffer);
 		}
 
 		void amix_execute(Amix_job& job, const Processor::Output_map& output)
@@ -1206,6 +1287,8 @@ namespace processor
 			const int64_t total = job.plan->total;
 			const std::vector<Segment>& segs = job.plan->segs;
 			bool fused = job.fused;
+			for (const auto& in : ins)       // chunk-wise inputs were not waited for in amix_prepare
+				if (in->progress && in->ready) in->ready->wait_on(cur_stream());
 
 			const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
 			auto block = std::make_shared<infra::Device_block>(2 * plane);
@@ -1264,7 +1347,7 @@ namespace processor
 	{
 		constexpr size_t kMaxTracks = 256;
 		std::vector<Amix_job> jobs;
-		std::map<std::tuple<int, int, int, int64_t, int64_t, int64_t>, std::vector<size_t>> groups;
+		std::map<std::tuple<int, int, int, int64_t, int64_t, int64_t, const Stream_progress*>, std::vector<size_t>> groups;
 		for (size_t k = 0; k < items.size(); k++)
 		{
 			const auto* node = static_cast<const Audio_amix*>(items[k].processor);
@@ -1273,18 +1356,30 @@ namespace processor
 			if (job.ins.size() == 1 && job.fused)
 			{
 				const Audio_buffer& in = *job.ins[0];
-				groups[{in.sample_rate, in.format, in.channels, in.frames, job.plan->total, job.front_len[0]}].push_back(k);
+				groups[{in.sample_rate, in.format, in.channels, in.frames, job.plan->total, job.front_len[0], in.progress.get()}].push_back(k);
 			}
 		}
 		std::vector<bool> done(items.size(), false);
 		for (const auto& [key, members] : groups)
 		{
 			if (members.size() < 2) continue;
-			const auto [rate, fmt, ch, frames, total, front] = key;
+			const auto [rate, fmt, ch, frames, total, front, pg_] = key;
+			(void)pg_;
 			for (size_t first = 0; first < members.size(); first += kMaxTracks)
 			{
 				const size_t cnt = std::min(kMaxTracks, members.size() - first);
 				const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
+				// The batch is cut into launches along time: a chunk starts as soon as the prefix of the input it reads has
+				// landed (uploads arrive chunk by chunk) and tells the next node which prefix of the output is final.
+				const nodey_resampler* plan = resampler_for(rate);
+				const std::shared_ptr<const Stream_progress> in_progress = jobs[members[first]].ins[0]->progress;
+				constexpr int kMaxChunks = 64;
+				int64_t in_need[kMaxChunks], out_ready[kMaxChunks];
+				const int nchunks = nodey_resample_tracks_chunks(plan, ch, frames, total, stream_chunk_count(), in_need, out_ready, kMaxChunks);
+				if (nchunks == NODEY_E_RANGE) break;      // no pipelined kernel for this plan: the members run one by one below
+				if (nchunks < 0) abi(nchunks, "Audio mixer");
+				const nodey_stream_t run = stream_after(in_progress.get());
+				Stream_scope scope(run);
 				auto block = std::make_shared<infra::Device_block>(2 * plane * cnt);
 				float* base = (float*)block->ptr;
 				std::vector<const void*> p0(cnt), p1(cnt);
@@ -1294,16 +1389,27 @@ namespace processor
 					const Amix_job& job = jobs[members[first + t]];
 					p0[t] = job.ins[0]->plane[0]; p1[t] = job.ins[0]->plane[1]; vol[t] = job.vol[0];
 				}
-				// track t: left plane at base + 2t * plane, right plane one plane further
-				const int rc = nodey_resample_tracks(resampler_for(rate), base, base + plane / sizeof(float), (int64_t)(2 * plane / sizeof(float)),
-													 p0.data(), p1.data(), fmt, ch, frames, vol.data(), (int)cnt, 1, front, total, cur_stream());
-				if (rc == NODEY_E_RANGE) break;      // no pipelined kernel for this plan: the members run one by one below
-				abi(rc, "Audio mixer");
+				auto progress = std::make_shared<Stream_progress>();
+				progress->stream = run;
+				Progress_waiter input{in_progress.get()};
+				for (int c = 0; c < nchunks; c++)
+				{
+					input.need(in_need[c], run);
+					// track t: left plane at base + 2t * plane, right plane one plane further
+					abi(nodey_resample_tracks_chunk(plan, base, base + plane / sizeof(float), (int64_t)(2 * plane / sizeof(float)), p0.data(), p1.data(),
+													fmt, ch, frames, vol.data(), (int)cnt, 1, front, total, c, nchunks, run), "Audio mixer");
+					auto ev = std::make_shared<infra::Device_event>();
+					ev->record(run);
+					progress->points.push_back({out_ready[c], ev});
+				}
+				input.all(run);
+				if (in_progress) { auto ev = std::make_shared<infra::Device_event>(); ev->record(run); progress->points.back().event = ev; }
 				for (size_t t = 0; t < cnt; t++)
 				{
 					const size_t k = members[first + t];
 					float* out_l = base + 2 * t * (plane / sizeof(float));
-					amix_publish(jobs[k], *items[k].output, block, out_l, out_l + plane / sizeof(float));
+					amix_publish(jobs[k], *items[k].output, block, out_l, out_l + plane / sizeof(float), nchunks > 1 || in_progress ? progress : nullptr);
+					if (!(nchunks > 1 || in_progress)) { /* published with a ready event recorded by publish() on `run` */ }
 					done[k] = true;
 				}
 			}

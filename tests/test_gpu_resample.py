@@ -139,6 +139,39 @@ def test_resample_tracks_batch_matches_single_mixers(nd, orc, fmt, nch):
         assert not rl[m:].any() and not rr[m:].any()
 
 
+@pytest.mark.parametrize("fmt,nch,nchunks", [(FMT_FLT, 2, 2), (FMT_FLT, 2, 8), (FMT_FLTP, 2, 5), (FMT_S16, 1, 3), (FMT_FLT, 2, 64)])
+def test_resample_tracks_in_chunks_is_bit_identical(nd, orc, fmt, nch, nchunks):
+    """nodey_resample_tracks_chunk: the batch resampler cut into launches along time.  Same bits as the one-launch call;
+    chunk c reads nothing beyond in_need[c] (everything past it is overwritten before the chunk runs and restored after)
+    and frames below out_ready[c] are final after it."""
+    import torch
+    n = 44100 * 9 + 321
+    ntr = 3
+    vols = np.array([1.0, 0.5, 0.3], np.float32)
+    xs = [to_dev(make_input(orc, fmt, n, nch, track=i)) for i in range(ntr)]
+    r = nd.Resampler(44100, 48000)
+    whole = r.resample_tracks(xs, fmt, vols, flush=True)
+    keep = [x.clone() for x in xs]
+    planar = fmt >= 5
+    state = {"out": None}
+
+    def poison(c, in_need):
+        for x, k in zip(xs, keep):
+            x.copy_(k)
+            if x.dtype.is_floating_point:
+                (x[..., in_need:] if planar else x[in_need:]).fill_(float("nan"))
+            else:
+                (x[..., in_need:] if planar else x[in_need:]).fill_(32767)
+
+    got, plan = r.resample_tracks_chunked(xs, fmt, vols, nchunks, flush=True, poison=poison)
+    torch.cuda.synchronize()
+    assert 1 <= len(plan) <= nchunks and plan[-1] == (n, whole.shape[2])
+    assert all(plan[k][0] <= plan[k + 1][0] and plan[k][1] < plan[k + 1][1] for k in range(len(plan) - 1))
+    if nchunks <= 8:
+        assert len(plan) == nchunks and plan[0][0] < n
+    assert torch.equal(got.view(torch.int32), whole.view(torch.int32)), "chunked batch resampler differs from the one-launch result"
+
+
 def test_resample_tracks_rejects_plans_without_pipelined_kernel(nd, orc):
     x = to_dev(make_input(orc, FMT_FLT, 5000, 2, rate=22050))
     r = nd.Resampler(22050, 48000)            # 320 phases: two groups per warp -> staging-row kernel only
