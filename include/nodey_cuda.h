@@ -70,6 +70,9 @@ int nodey_stream_wait_event(nodey_stream_t s, nodey_event_t e);
 int nodey_malloc(void** out, size_t bytes, nodey_stream_t s);
 int nodey_free(void* p, nodey_stream_t s);
 int nodey_trim_memory(void);   /* return cached blocks to the driver */
+/* device memory held through nodey_malloc right now and its high-water mark (blocks >= 1 MiB); reset_peak != 0
+ * restarts the mark at the current level */
+int nodey_memory_stats(int64_t* live_bytes, int64_t* peak_bytes, int reset_peak);
 int nodey_memset(void* dst, int value, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_h2d(void* dst, const void* src_host, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_d2h(void* dst_host, const void* src, size_t bytes, nodey_stream_t s);
@@ -115,6 +118,13 @@ int nodey_to_fltp_stereo(float* dst_l, float* dst_r, const void* plane0, const v
 int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r,
               const int64_t* in_len, const float* volumes, int nin, int64_t nframes,
               nodey_stream_t stream);
+/* The same with an audio_volume_adjust node folded into every input (gains: HOST array of nin floats, NULL = none):
+ * out = sum_i (in_i * gain_i) * vol_i, the inner product rounded to float first -- exactly what the gain node's own pass
+ * would have stored (dst = T(src * volume), audio-vol.cpp:75-100) -- so the bus is bit identical and the gain pass with
+ * its intermediate stream disappears.  Float inputs only (the integer gain truncates, that stays a kernel of its own). */
+int nodey_mix_gains(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r,
+                    const int64_t* in_len, const float* volumes, const float* gains, int nin, int64_t nframes,
+                    nodey_stream_t stream);
 
 /* A5  audio_bimix mix loop, src/processor/audio-bimix.cpp:310-317.
  * outL = (ll/2 + lr/2) * (1 - bias), outR = (rl/2 + rr/2) * (1 + bias); zeros past len_l / len_r. */

@@ -83,6 +83,12 @@ int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* pl
  * value is the number of chunks. */
 int nodey_engine_set_preview(nodey_engine* e, int preview);
 int nodey_engine_preview(nodey_engine* e, int64_t* frames, void** packed, int64_t* chunk_len, int chunk_cap);
+/* Memory policy of the runs started after the call (process wide; infra::Runner::release_products).  0 (default): every
+ * link keeps its product until the next run, like the reference's channels (include/infra/runner.hpp:60-84), so any
+ * product can be read back with nodey_engine_product.  1: a link lets go of its product once its consumer has enqueued
+ * its work; only the sink's stream (nodey_engine_output) and spectrum products survive the run, and a render holds one
+ * or two levels of intermediates per wave instead of all of them. */
+int nodey_engine_set_release_products(int release);
 /* frame sizes (run-length encoded) of an audio product: fills up to cap pairs, returns the count */
 int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap);
 

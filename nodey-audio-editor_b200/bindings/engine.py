@@ -58,6 +58,11 @@ def lib():
     return L
 
 
+def set_release_products(release):
+    """memory policy of the next runs: True = links drop their products once consumed (only sink / spectrum survive)"""
+    _check(lib().nodey_engine_set_release_products(1 if release else 0))
+
+
 def register_examples():
     """registers the example processors outside the reference's set ("frame_gain_example": frame-interface node)"""
     _check(lib().nodey_engine_register_examples())

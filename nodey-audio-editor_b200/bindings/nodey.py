@@ -19,7 +19,7 @@ MAX_MIX_INPUTS = 16
 # every entry point include/nodey_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "nodey_version", "nodey_last_error", "nodey_device_info", "nodey_synth", "nodey_gain",
-    "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_bimix",
+    "nodey_extract_interleaved", "nodey_split", "nodey_to_fltp_stereo", "nodey_mix", "nodey_mix_gains", "nodey_bimix",
     "nodey_downmix_half", "nodey_merge_segments", "nodey_resampler_create", "nodey_resampler_destroy",
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resample_tracks_chunks", "nodey_resample_tracks_chunk", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
@@ -28,7 +28,7 @@ SYMBOLS = [
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
-    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory",
+    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory", "nodey_memory_stats",
     "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",
     "nodey_bus_reduce", "nodey_bus_allreduce",
     "nodey_peer_alloc", "nodey_peer_free", "nodey_peer_export", "nodey_peer_open", "nodey_peer_close",
@@ -64,6 +64,7 @@ def lib():
     L.nodey_split.argtypes = [vp, vp, vp, vp, i32, i64, vp]
     L.nodey_to_fltp_stereo.argtypes = [vp, vp, vp, vp, i32, i32, i64, vp]
     L.nodey_mix.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_float), i32, i64, vp]
+    L.nodey_mix_gains.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_float), C.POINTER(C.c_float), i32, i64, vp]
     L.nodey_bimix.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, C.c_float, i64, vp]
     L.nodey_downmix_half.argtypes = [vp, vp, vp, i64, vp]
     L.nodey_merge_segments.argtypes = [vp, vp, vp] + [C.POINTER(i64)] * 4 + [i32, vp]
@@ -431,6 +432,13 @@ def amix_plan(in_rates, in_runs, quirk=0, seg_cap=4096, run_cap=4096):
         return amix_plan(in_rates, in_runs, quirk, max(seg_cap, nseg.value), max(run_cap, nrun.value))
     return (total, [(si[k], so[k], ss[k], sl[k]) for k in range(nseg.value)],
             [(orl[k], orc[k]) for k in range(nrun.value)])
+
+
+def memory_stats(reset_peak=False):
+    """(live bytes, peak bytes) of device memory held through the library's allocator"""
+    live, peak = C.c_int64(), C.c_int64()
+    check(lib().nodey_memory_stats(C.byref(live), C.byref(peak), 1 if reset_peak else 0))
+    return live.value, peak.value
 
 
 def profile_enable(on):

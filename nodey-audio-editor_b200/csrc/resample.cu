@@ -1061,7 +1061,7 @@ static void resample_chunk_range(const nodey_resampler* r, int ch, int64_t out_f
     const int pt = tile2_shape(r, a, ch, 0, &smem);
     const int64_t per_tile = (int64_t)kNB * pt * a.P;
     const int64_t all = (out_frames + per_tile - 1) / per_tile;
-    const int64_t per = (all + n - 1) / n;
+    const int64_t per = (all + n - 1) / n > 0 ? (all + n - 1) / n : 1;
     *tile0 = (int64_t)c * per < all ? (int64_t)c * per : all;
     *tile1 = c >= n - 1 ? all : ((int64_t)(c + 1) * per < all ? (int64_t)(c + 1) * per : all);
     *per_tile_out = per_tile;
@@ -1081,6 +1081,10 @@ int nodey_resample_tracks_chunks(const nodey_resampler* r, int nch, int64_t in_f
     int n = want_chunks < 1 ? 1 : want_chunks;
     if ((int64_t)n > t1 / 4) n = (int)(t1 / 4);           // at least four tiles per launch and track
     if (n < 1) n = 1;
+    if (t1 > 0) {                                         // no empty chunk at the end: ceil(tiles / ceil(tiles / n)) launches
+        const int64_t per = (t1 + n - 1) / n;
+        n = (int)((t1 + per - 1) / per);
+    }
     for (int c = 0; c < n && c < cap; c++) {
         resample_chunk_range(r, nch, out_frames, c, n, &t0, &t1, &per_tile, &need, in_frames);
         if (in_need) in_need[c] = need;

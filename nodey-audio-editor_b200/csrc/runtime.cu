@@ -2,6 +2,7 @@
 // reference-side binding) needs nothing but include/nodey_cuda.h: no CUDA headers, no torch.
 #include "nodey_common.cuh"
 
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -17,10 +18,19 @@
 namespace nodey {
 
 namespace {
+// A render runs on up to ten streams (transfer lane + three compute lanes with two side streams each).  The driver maps
+// streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue see false dependencies --
+// a lane waiting for an upload event then holds up another lane's chain.  Ask for 32 queues unless the host chose a value;
+// this only takes effect when the library is loaded before the CUDA context exists (a host that initialises CUDA first
+// sets the variable itself: bench.py, tests/conftest.py).
+struct ConnectionsInit { ConnectionsInit() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); } } g_connections_init;
+
 struct CachedBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; int device; };
 std::mutex g_alloc_mu;
 std::multimap<size_t, CachedBlock> g_free_blocks;           // by (rounded) size
 std::map<void*, std::pair<size_t, int>> g_live_blocks;     // ptr -> (rounded size, device)
+long long g_live_bytes = 0, g_peak_bytes = 0;               // bytes of cached-allocator blocks handed out (guarded by g_alloc_mu)
+void note_live_locked(long long delta) { g_live_bytes += delta; if (g_live_bytes > g_peak_bytes) g_peak_bytes = g_live_bytes; }
 constexpr size_t kGranule = 2u << 20;
 constexpr size_t kSmall = 1u << 20;                           // below this: cudaMallocAsync (pool handles it well)
 
@@ -77,6 +87,7 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
         g_free_blocks.erase(pick);
         cudaEventDestroy(b.event);
         g_live_blocks[b.ptr] = {b.bytes, dev};
+        note_live_locked((long long)b.bytes);
         *out = b.ptr;
         return NODEY_OK;
     }
@@ -88,6 +99,7 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
     g_live_blocks[*out] = {want, dev};
+    note_live_locked((long long)want);
     return NODEY_OK;
 }
 
@@ -100,6 +112,7 @@ int device_free(void* p, cudaStream_t stream)
         if (it != g_live_blocks.end()) {
             CachedBlock b{p, it->second.first, stream, nullptr, it->second.second};
             g_live_blocks.erase(it);
+            note_live_locked(-(long long)b.bytes);
             if (cudaEventCreateWithFlags(&b.event, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(b.event, stream) != cudaSuccess) {
                 cudaGetLastError();
                 cudaStreamSynchronize(stream);
@@ -222,6 +235,17 @@ int nodey_trim_memory(void)
     NODEY_CUDA_OK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_alloc_mu);
     drop_cached_locked(dev);
+    return NODEY_OK;
+}
+
+/* bytes of device memory the library's callers hold right now (blocks of 1 MiB and more, which is where a render's
+ * footprint is) and the high-water mark since the last reset */
+int nodey_memory_stats(int64_t* live_bytes, int64_t* peak_bytes, int reset_peak)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    if (live_bytes) *live_bytes = g_live_bytes;
+    if (peak_bytes) *peak_bytes = g_peak_bytes;
+    if (reset_peak) g_peak_bytes = g_live_bytes;
     return NODEY_OK;
 }
 

@@ -317,6 +317,8 @@ struct MixArgs {
     const float* r[NODEY_MAX_MIX_INPUTS];
     long long len[NODEY_MAX_MIX_INPUTS];
     float vol[NODEY_MAX_MIX_INPUTS];
+    float gain[NODEY_MAX_MIX_INPUTS];   // gain of an audio_volume_adjust node folded into this input (1 = none)
+    int has_gain;
     int nin;
     int vec;
 };
@@ -369,6 +371,13 @@ __global__ void __launch_bounds__(kBlock) mix_kernel(float* __restrict__ out_l, 
                 const float4 f1 = load4_zero_tail(a.l[i], 2 * j + 4, 2 * a.len[i], a.vec);
                 xl = make_float4(f0.x, f0.z, f1.x, f1.z);
                 xr = make_float4(f0.y, f0.w, f1.y, f1.w);
+            }
+            if (a.has_gain) {
+                // an audio_volume_adjust node in front of this input, folded in: its product x * gain is rounded to float
+                // exactly as the node's own pass would have stored it (audio-vol.cpp:75-100), then mixed
+                const float g = a.gain[i];
+                xl = make_float4(__fmul_rn(xl.x, g), __fmul_rn(xl.y, g), __fmul_rn(xl.z, g), __fmul_rn(xl.w, g));
+                xr = make_float4(__fmul_rn(xr.x, g), __fmul_rn(xr.y, g), __fmul_rn(xr.z, g), __fmul_rn(xr.w, g));
             }
             tl = mac4(tl, xl, a.vol[i]);
             tr = mac4(tr, xr, a.vol[i]);
@@ -732,14 +741,22 @@ int nodey_to_fltp_stereo(float* dl, float* dr, const void* p0, const void* p1, i
 int nodey_mix(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r, const int64_t* in_len,
               const float* volumes, int nin, int64_t n, nodey_stream_t stream)
 {
+    return nodey_mix_gains(out_l, out_r, in_l, in_r, in_len, volumes, nullptr, nin, n, stream);
+}
+
+int nodey_mix_gains(float* out_l, float* out_r, const float* const* in_l, const float* const* in_r, const int64_t* in_len,
+                    const float* volumes, const float* gains, int nin, int64_t n, nodey_stream_t stream)
+{
     NODEY_REQUIRE(nin >= 1 && nin <= NODEY_MAX_MIX_INPUTS, NODEY_E_RANGE, "nodey_mix: input_num %d outside 1..16", nin);
     if (n <= 0) return n == 0 ? NODEY_OK : NODEY_E_INVALID;
     MixArgs a;
     memset(&a, 0, sizeof(a));
     a.nin = nin;
     a.vec = aligned16(out_l) && aligned16(out_r);
+    a.has_gain = gains != nullptr;
     for (int i = 0; i < nin; i++) {
         a.l[i] = in_l[i]; a.r[i] = in_r[i]; a.len[i] = in_len[i]; a.vol[i] = volumes[i];
+        a.gain[i] = gains ? gains[i] : 1.0f;
         a.vec = a.vec && aligned16(in_l[i]) && (in_r[i] == nullptr || aligned16(in_r[i]));
     }
     NODEY_LAUNCH("mix_kernel", as_stream(stream), mix_kernel<<<stream_grid((n + 3) / 4, kBlock, kCtasPerSm), kBlock, 0, as_stream(stream)>>>(out_l, out_r, a, n));

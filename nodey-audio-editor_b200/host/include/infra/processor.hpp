@@ -103,6 +103,9 @@ namespace infra
 			Product() = default;
 			virtual ~Product() = default;
 			const std::type_info& get_typeinfo() const { return typeid(*this); }
+			// Optional (not in the reference): the Runner calls this once the consumer of the link has enqueued its work
+			// and the run was asked to release intermediates (Runner::release_products); default: keep the payload
+			virtual void release() {}
 		};
 
 		struct Info

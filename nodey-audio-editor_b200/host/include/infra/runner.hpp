@@ -49,6 +49,12 @@ namespace infra
 			Processor::Input_map input_payloads;
 		};
 
+		// Memory policy of the runs created after the call (process wide, default: keep).  The reference keeps every link's
+		// channel until the Runner dies; with `release` a link drops its payload as soon as its consumer has enqueued its
+		// work, so a render holds one or two levels of intermediates per wave instead of all of them -- products other than
+		// the sink's are then gone after the run (get_link_products() still lists the links).
+		static void release_products(bool release);
+
 		const auto& get_link_products() const { return link_products; }
 		const auto& get_processor_resources() const { return processor_resources; }
 

@@ -52,21 +52,42 @@ namespace processor
 		infra::Stream_handle stream = nullptr;     // the stream the producer enqueued on
 	};
 
+	struct Audio_buffer;
+
+	// audio_volume_adjust on a float stream does not run its pass at once: it publishes the product LAZY -- "source times
+	// gain" -- so that a mixer behind it can fold the multiplication into its own read ((x * gain) rounded, then * volume:
+	// the bits the node's own pass would have stored, audio-vol.cpp:75-100) and the intermediate stream never exists.
+	// Every other reader gets the ordinary buffer: materialize() runs the gain kernel on first use.
+	struct Lazy_gain
+	{
+		std::mutex mutex;
+		std::shared_ptr<const Audio_buffer> source;
+		float gain = 1.0f;
+		bool done = false;                             // materialize() has filled block / plane / ready
+	};
+
 	struct Audio_buffer
 	{
-		std::shared_ptr<infra::Device_block> block;    // owner of the memory (may be shared by a whole batch)
-		void* plane[2] = {nullptr, nullptr};           // packed: plane[0]; planar: one plane per channel
+		// (mutable: filled by materialize() for a lazy product, under Lazy_gain::mutex)
+		mutable std::shared_ptr<infra::Device_block> block;    // owner of the memory (may be shared by a whole batch)
+		mutable void* plane[2] = {nullptr, nullptr};   // packed: plane[0]; planar: one plane per channel
 		int format = FMT_FLT;
 		int sample_rate = 48000;
 		int channels = 2;
 		int64_t frames = 0;                            // samples per channel
 		Frame_runs runs;                               // how the reference would have cut it into frames
 		double pts_seconds = 0.0;                      // start time of the first frame
-		std::shared_ptr<infra::Device_event> ready;    // recorded after the producing kernels were enqueued
+		mutable std::shared_ptr<infra::Device_event> ready;    // recorded after the producing kernels were enqueued
 		std::shared_ptr<const Stream_progress> progress;   // optional: chunk-wise completion (shared by the products of a batch)
+		std::shared_ptr<Lazy_gain> lazy;               // optional: see Lazy_gain
+
+		bool is_lazy() const { return lazy && !lazy->done; }
 
 		size_t plane_bytes() const { return (size_t)frames * (size_t)format_bytes(format) * (format_is_planar(format) ? 1u : (size_t)channels); }
 	};
+
+	// runs the deferred gain pass of a lazy product on `stream` (no-op otherwise); afterwards plane[] / ready are valid
+	void materialize(const Audio_buffer& buffer, infra::Stream_handle stream);
 
 	// Host-side frame of the frame-streaming compatibility mode: the AVFrame subset the reference's nodes touch
 	// (include/processor/audio-stream.hpp:22-42: format, sample_rate, channel count, nb_samples, pts, data planes).
@@ -102,6 +123,14 @@ namespace processor
 		Audio_stream() = default;
 		Audio_stream(const Audio_stream&) = delete;
 		Audio_stream& operator=(const Audio_stream&) = delete;
+
+		// Runner: every consumer of this link has enqueued its work; the link lets go of the buffer (the memory is freed
+		// in stream order once no other link holds it)
+		void release() override
+		{
+			std::lock_guard lock(mutex);
+			buffer.reset();
+		}
 
 		// producer side: hand over the rendered track and close the stream
 		void publish(std::shared_ptr<const Audio_buffer> rendered)

@@ -205,7 +205,13 @@ int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kin
 	if (const auto audio = std::dynamic_pointer_cast<Audio_stream>(product))
 	{
 		const auto b = audio->get();
-		if (!b) return fail(NODEY_ENGINE_E_NODE, "stream was closed without audio");
+		if (!b) return fail(NODEY_ENGINE_E_NODE, "stream was closed without audio (or the run released its intermediates)");
+		if (b->is_lazy())
+		{
+			// a gain product nobody materialised (its mixer folded the gain in): run the node's pass now, for the host
+			try { processor::materialize(*b, nullptr); }
+			catch (const std::exception& err) { return fail(NODEY_ENGINE_E_NODE, err.what()); }
+		}
 		if (b->ready) b->ready->synchronize();
 		if (kind) *kind = 1;
 		if (fmt) *fmt = b->format;
@@ -235,6 +241,12 @@ int nodey_engine_product(nodey_engine* e, int node_id, const char* pin, int* kin
 		return 0;
 	}
 	return fail(NODEY_ENGINE_E_INVALID, "unknown product type");
+}
+
+int nodey_engine_set_release_products(int release)
+{
+	Runner::release_products(release != 0);
+	return 0;
 }
 
 int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int64_t* run_len, int64_t* run_count, int cap)

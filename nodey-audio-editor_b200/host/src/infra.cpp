@@ -564,6 +564,9 @@ namespace infra
 			}
 	}
 
+	namespace { std::atomic<bool> g_release_products{false}; }
+	void Runner::release_products(bool release) { g_release_products = release; }
+
 	Runner::~Runner()
 	{
 		for (auto& [_, resource] : processor_resources) resource->stop_source = true;
@@ -759,6 +762,10 @@ namespace infra
 				const bool timed = nodey_event_create(&se.begin, 1) == NODEY_OK && nodey_event_create(&se.end, 1) == NODEY_OK
 								&& nodey_event_record(se.begin, lanes[lane]) == NODEY_OK;
 				run_group(ids, lane, (int)level_index);
+				if (g_release_products && !failed)
+					for (const Id_t id : ids)
+						for (auto& [pin, product] : processor_resources.at(id)->input_payloads)
+							if (product) product->release();
 				se.timing.enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
 				se.ok = timed && nodey_event_record(se.end, lanes[lane]) == NODEY_OK;
 				steps.push_back(std::move(se));

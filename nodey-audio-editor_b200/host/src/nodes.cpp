@@ -79,8 +79,9 @@ namespace processor
 		};
 
 		// wait = false: the caller orders itself after the producer (chunk by chunk through Audio_buffer::progress)
+		// accept_lazy = false: a lazy gain product (Lazy_gain) is materialised here, so the caller sees an ordinary buffer
 		std::shared_ptr<const Audio_buffer> require_input(const Processor::Input_map& input, const std::string& key,
-														   const char* node_title, bool wait = true)
+														   const char* node_title, bool wait = true, bool accept_lazy = false)
 		{
 			const auto item = infra::get_input_item<Audio_stream>(input, key);
 			if (!item.has_value())
@@ -91,6 +92,7 @@ namespace processor
 			if (!buffer)
 				throw Runtime_error(std::format("{} received an empty stream", node_title),
 									"The upstream node closed its stream without publishing audio.", std::format("pin '{}'", key));
+			if (!accept_lazy && buffer->is_lazy()) materialize(*buffer, cur_stream());
 			if (wait && buffer->ready) buffer->ready->wait_on(cur_stream());
 			return buffer;
 		}
@@ -251,6 +253,32 @@ namespace processor
 	}
 
 	// ---------------------------------------------------------------------------------------------
+	// lazy gain products (audio-stream.hpp: Lazy_gain)
+	// ---------------------------------------------------------------------------------------------
+	void materialize(const Audio_buffer& b, infra::Stream_handle stream)
+	{
+		if (!b.lazy) return;
+		std::lock_guard lock(b.lazy->mutex);
+		if (b.lazy->done) return;
+		const Audio_buffer& src = *b.lazy->source;
+		if (src.is_lazy()) materialize(src, stream);
+		Stream_scope scope(stream);
+		if (src.ready) src.ready->wait_on(stream);
+		const bool planar2 = format_is_planar(src.format) && src.channels == 2;
+		const size_t plane = Arena::padded(src.plane_bytes());
+		auto block = std::make_shared<infra::Device_block>(std::max<size_t>(plane * (planar2 ? 2 : 1), 256));
+		void* p0 = block->ptr;
+		void* p1 = planar2 ? (char*)block->ptr + plane : nullptr;
+		const int64_t n = format_is_planar(src.format) ? src.frames : src.frames * src.channels;
+		abi(nodey_gain(p0, src.plane[0], src.format, n, b.lazy->gain, stream), "Volume adjust");
+		if (planar2) abi(nodey_gain(p1, src.plane[1], src.format, n, b.lazy->gain, stream), "Volume adjust");
+		auto ev = std::make_shared<infra::Device_event>();
+		ev->record(stream);
+		b.block = std::move(block); b.plane[0] = p0; b.plane[1] = p1; b.ready = std::move(ev);
+		b.lazy->done = true;
+	}
+
+	// ---------------------------------------------------------------------------------------------
 	// frame-streaming compatibility mode of Audio_stream (reference: src/processor/audio-stream.cpp:60-80)
 	// ---------------------------------------------------------------------------------------------
 	bool Audio_stream::try_push(std::shared_ptr<const Audio_frame> frame)
@@ -330,6 +358,7 @@ namespace processor
 		if (!cur.loaded)
 		{
 			// download once; the frames below are cut from this image
+			if (b->is_lazy()) materialize(*b, cur_stream());
 			if (b->ready) b->ready->wait_on(cur_stream());
 			for (int c = 0; c < (planar2 ? 2 : 1); c++)
 			{
@@ -828,6 +857,29 @@ namespace processor
 			const bool planar2 = format_is_planar(ins.back()->format) && ins.back()->channels == 2;
 			bytes += Arena::padded(ins.back()->plane_bytes()) * (planar2 ? 2 : 1);
 		}
+		// Float streams are published LAZY (Lazy_gain): a mixer behind this node folds the gain into its own read, any
+		// other consumer triggers the pass on first use.  NODEY_EAGER_GAIN=1 runs the pass here, as round 1 did.
+		static const bool eager = getenv("NODEY_EAGER_GAIN") != nullptr;
+		if (!eager)
+		{
+			bool all_float = true;
+			for (const auto& in : ins) all_float = all_float && (in->format == FMT_FLT || in->format == FMT_FLTP);
+			if (all_float)
+			{
+				for (size_t k = 0; k < items.size(); k++)
+				{
+					const Audio_buffer& in = *ins[k];
+					auto b = new_buffer(nullptr, nullptr, nullptr, in.format, in.sample_rate, in.channels, in.frames, in.runs, in.pts_seconds);
+					b->lazy = std::make_shared<Lazy_gain>();
+					b->lazy->source = ins[k];
+					b->lazy->gain = static_cast<Audio_vol*>(items[k].processor)->volume;
+					b->ready = in.ready;          // a reader of source * gain orders itself after the source
+					if (!b->ready) { auto ev = std::make_shared<infra::Device_event>(); ev->record(cur_stream()); b->ready = ev; }
+					publish(*items[k].output, "output", b);
+				}
+				return true;
+			}
+		}
 		Arena arena(bytes);
 		// float streams (planes) of the whole batch go to ONE launch; integer formats run per stream.  Products are
 		// published after everything is enqueued: publish() records the event the consumers wait on.
@@ -1205,7 +1257,7 @@ namespace processor
 			{
 				// a chunk-wise input is not waited for here: the batch path below consumes it chunk by chunk, every other
 				// path waits in amix_execute
-				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer", false));
+				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer", false, true));
 				if (!job.ins.back()->progress && job.ins.back()->ready) job.ins.back()->ready->wait_on(cur_stream());
 				check_channels(*job.ins.back(), "Audio mixer");
 				runs.push_back(&job.ins.back()->runs);
@@ -1289,6 +1341,16 @@ namespace processor
 			bool fused = job.fused;
 			for (const auto& in : ins)       // chunk-wise inputs were not waited for in amix_prepare
 				if (in->progress && in->ready) in->ready->wait_on(cur_stream());
+			// lazy gain products: only the in-place read of the mix kernel below folds the gain in; every path that
+			// resamples or converts first wants the ordinary buffer
+			for (int i = 0; i < nin; i++)
+			{
+				const Audio_buffer& in = *ins[(size_t)i];
+				int64_t len = 0;
+				const bool in_place = !fused && in.sample_rate == 48000 && in.channels == 2 && (in.format == FMT_FLT || in.format == FMT_FLTP)
+								   && single_front_segment(segs, i, &len) && len <= in.frames;
+				if (in.is_lazy() && !in_place) { materialize(in, cur_stream()); if (in.ready) in.ready->wait_on(cur_stream()); }
+			}
 
 			const size_t plane = Arena::padded((size_t)std::max<int64_t>(total, 1) * sizeof(float));
 			auto block = std::make_shared<infra::Device_block>(2 * plane);
@@ -1310,17 +1372,22 @@ namespace processor
 				std::vector<Resampled> keep;
 				std::vector<const float*> pl, pr;
 				std::vector<int64_t> lens;
+				std::vector<float> gains((size_t)nin, 1.0f);
+				bool any_gain = false;
 				for (int i = 0; i < nin; i++)
 				{
 					int64_t len = 0;
 					const Audio_buffer& in = *ins[(size_t)i];
 					// 48 kHz stereo float that lands unbroken at 0: swr would only copy (FLTP) or de-interleave (FLT) it;
-					// the mix kernel reads it in place
+					// the mix kernel reads it in place -- and through a lazy gain product it reads the gain node's SOURCE
+					// and multiplies by the gain itself
 					if (in.sample_rate == 48000 && in.channels == 2 && (in.format == FMT_FLT || in.format == FMT_FLTP)
 						&& single_front_segment(segs, i, &len) && len <= in.frames)
 					{
-						pl.push_back((const float*)in.plane[0]);
-						pr.push_back(in.format == FMT_FLTP ? (const float*)in.plane[1] : nullptr);
+						const Audio_buffer* from = &in;
+						if (in.is_lazy()) { from = in.lazy->source.get(); gains[(size_t)i] = in.lazy->gain; any_gain = true; }
+						pl.push_back((const float*)from->plane[0]);
+						pr.push_back(in.format == FMT_FLTP ? (const float*)from->plane[1] : nullptr);
 						lens.push_back(len);
 						continue;
 					}
@@ -1329,7 +1396,8 @@ namespace processor
 					pl.push_back(r.l); pr.push_back(r.r); lens.push_back(len);
 					keep.push_back(std::move(r));
 				}
-				abi(nodey_mix(out_l, out_r, pl.data(), pr.data(), lens.data(), job.vol.data(), nin, total, cur_stream()), "Audio mixer");
+				abi(nodey_mix_gains(out_l, out_r, pl.data(), pr.data(), lens.data(), job.vol.data(), any_gain ? gains.data() : nullptr, nin, total,
+									cur_stream()), "Audio mixer");
 			}
 			amix_publish(job, output, block, out_l, out_r);
 		}

@@ -5,6 +5,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the engine runs on up to ten CUDA streams: more hardware queues than the default 8, set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "nodey-audio-editor_b200", "bindings"))
 

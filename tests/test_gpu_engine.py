@@ -453,3 +453,73 @@ def test_diagnostics_report_every_step_of_the_run(eng_gpu, orc):
     assert len(text) == 1 + len(steps) and text[1].startswith("W0 L0 audio_input x1:")
     assert any("pitch_modifier x16" in line for line in text)
     e.close()
+
+
+@pytest.mark.parametrize("fmt", [FMT_FLT, FMT_FLTP])
+def test_lazy_gain_products_fold_into_the_mixer_and_materialise_for_everyone_else(eng_gpu, orc, fmt):
+    """audio_volume_adjust on a float stream publishes "source x gain" (Lazy_gain): the amix behind it multiplies while it
+    reads ((x * g) rounded, then * volume -- the bits audio-vol.cpp:75-100 + audio-amix.cpp:296-304 give), every other
+    consumer (here: the sink of a second gain node, a spectrum node, the host reading the product back) gets the
+    ordinary buffer.  All bit exact against the oracle."""
+    n = 48000 * 2 + 77
+    xa = make_input(orc, fmt, n, 2, rate=48000, track=1); xb = make_input(orc, fmt, n - 5000, 2, rate=48000, track=2)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    ga = p.add("audio_volume_adjust", {"volume": 0.8125}); gb = p.add("audio_volume_adjust", {"volume": 1.7})
+    gc = p.add("audio_volume_adjust", {"volume": 0.3})              # gain behind a gain: the inner one materialises
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.5, 0.25, 1.0]))
+    spec = p.add("audio_spectrum", {"fft_size": 4096, "hop": 1024, "window": "hann"})
+    out = p.add("audio_output")
+    p.link(src, "output_0", ga, "input"); p.link(src, "output_1", gb, "input"); p.link(ga, "output", gc, "input")
+    p.link(ga, "output", mix, "input_1"); p.link(gb, "output", mix, "input_2"); p.link(gc, "output", mix, "input_3")
+    p.link(gb, "output", spec, "input")
+    p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.bind_source(0, xa, fmt, 48000); e.bind_source(1, xb, fmt, 48000)
+    e.run()
+    ya = orc.gain(xa, fmt, 0.8125); yb = orc.gain(xb, fmt, 1.7); yc = orc.gain(ya, fmt, 0.3)
+    rl, rr = orc.amix([orc.make_track(ya, fmt, 48000), orc.make_track(yb, fmt, 48000), orc.make_track(yc, fmt, 48000)], [0.5, 0.25, 1.0])
+    assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "amix over lazy gain products")
+    assert_bit_equal(e.product(ga, "output").numpy(), ya, "gain product read back by the host")
+    assert_bit_equal(e.product(gc, "output").numpy(), yc, "gain behind a gain")
+    sp = e.product(spec, "output").numpy()
+    yb_planar = yb if fmt == FMT_FLTP else np.ascontiguousarray(yb.T)
+    ref = orc.stft(yb_planar[0].copy())
+    assert np.abs(sp[0] - ref).max() <= 1e-5 * np.abs(ref).max()
+    e.close()
+
+
+def test_release_mode_renders_the_same_bus_with_a_smaller_footprint(nd, eng_gpu, orc):
+    """Runner::release_products: links drop their products once consumed.  Same master bus bit for bit, intermediates
+    gone after the run, lower high-water mark of device memory."""
+    import torch
+    n = 44100 * 4
+    project, ids = eng_gpu.config5_project(32, [1.0 + 0.01 * t for t in range(32)])
+    xs = [nd.synth(n, 2, 44100, track=t) for t in range(32)]
+
+    def render(release):
+        eng_gpu.set_release_products(release)
+        try:
+            e = eng_gpu.Engine(project.json())
+            for t in range(32):
+                e.bind_source(t, xs[t], nd.FMT_FLT, 44100)
+            e.run(); e.run()
+            torch.cuda.synchronize()
+            nd.memory_stats(reset_peak=True)
+            e.run()
+            torch.cuda.synchronize()
+            _, peak = nd.memory_stats()
+            return e, e.output().numpy(), peak
+        finally:
+            eng_gpu.set_release_products(False)
+
+    e0, bus0, peak0 = render(False)
+    base = nd.memory_stats()[0]
+    e0.close()
+    e1, bus1, peak1 = render(True)
+    assert_bit_equal(bus1, bus0, "bus in release mode")
+    with pytest.raises(eng_gpu.EngineError):
+        e1.product(ids["groups"][0], "output")
+    assert e1.product(ids["spectrum"], "output").frames > 0
+    assert peak1 < peak0, (peak0, peak1)
+    e1.close()
