@@ -73,6 +73,13 @@ int nodey_trim_memory(void);   /* return cached blocks to the driver */
 /* device memory held through nodey_malloc right now and its high-water mark (blocks >= 1 MiB); reset_peak != 0
  * restarts the mark at the current level */
 int nodey_memory_stats(int64_t* live_bytes, int64_t* peak_bytes, int reset_peak);
+/* device memory the library has obtained from the driver and not returned (held by callers + cached for reuse): the
+ * footprint a render really has, and its high-water mark since the last nodey_memory_stats(..., reset_peak = 1) */
+int nodey_memory_reserved(int64_t* reserved_bytes, int64_t* peak_reserved_bytes);
+/* reuse_pending != 0: nodey_malloc may hand out a block that another stream has freed although the device has not
+ * reached that free yet; the requesting stream then waits for it (less memory, more cross-stream ordering).  Default 0:
+ * such a block is only reused by the stream that freed it, or once the free has completed. */
+int nodey_set_memory_policy(int reuse_pending);
 int nodey_memset(void* dst, int value, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_h2d(void* dst, const void* src_host, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_d2h(void* dst_host, const void* src, size_t bytes, nodey_stream_t s);

@@ -28,7 +28,7 @@ SYMBOLS = [
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
-    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory", "nodey_memory_stats",
+    "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory", "nodey_memory_stats", "nodey_memory_reserved", "nodey_set_memory_policy",
     "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",
     "nodey_bus_reduce", "nodey_bus_allreduce",
     "nodey_peer_alloc", "nodey_peer_free", "nodey_peer_export", "nodey_peer_open", "nodey_peer_close",
@@ -439,6 +439,13 @@ def memory_stats(reset_peak=False):
     live, peak = C.c_int64(), C.c_int64()
     check(lib().nodey_memory_stats(C.byref(live), C.byref(peak), 1 if reset_peak else 0))
     return live.value, peak.value
+
+
+def memory_reserved():
+    """(reserved bytes, peak reserved bytes): device memory obtained from the driver through the library's allocator"""
+    r, p = C.c_int64(), C.c_int64()
+    check(lib().nodey_memory_reserved(C.byref(r), C.byref(p)))
+    return r.value, p.value
 
 
 def profile_enable(on):

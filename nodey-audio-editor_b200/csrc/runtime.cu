@@ -29,6 +29,8 @@ struct CachedBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t e
 std::mutex g_alloc_mu;
 std::multimap<size_t, CachedBlock> g_free_blocks;           // by (rounded) size
 std::map<void*, std::pair<size_t, int>> g_live_blocks;     // ptr -> (rounded size, device)
+long long g_reserved_bytes = 0, g_peak_reserved = 0;       // bytes obtained from cudaMalloc and not returned (live + cached)
+bool g_reuse_pending = false;                              // nodey_set_memory_policy: hand out blocks whose free point has not passed yet
 long long g_live_bytes = 0, g_peak_bytes = 0;               // bytes of cached-allocator blocks handed out (guarded by g_alloc_mu)
 void note_live_locked(long long delta) { g_live_bytes += delta; if (g_live_bytes > g_peak_bytes) g_peak_bytes = g_live_bytes; }
 constexpr size_t kGranule = 2u << 20;
@@ -54,6 +56,7 @@ void drop_cached_locked(int device)
             cudaEventSynchronize(it->second.event);
             cudaEventDestroy(it->second.event);
             cudaFree(it->second.ptr);
+            g_reserved_bytes -= (long long)it->second.bytes;
             it = g_free_blocks.erase(it);
         } else ++it;
     }
@@ -82,6 +85,15 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
         if (b.stream == stream) { pick = it; break; }
         if (pick == g_free_blocks.end() && cudaEventQuery(b.event) == cudaSuccess) pick = it;
     }
+    if (pick == g_free_blocks.end() && g_reuse_pending) {
+        // memory-saving policy: a block another stream has freed but whose free point the device has not reached yet is
+        // handed out too -- the requesting stream waits for that point first (stream-ordered reuse across streams)
+        for (auto it = g_free_blocks.lower_bound(want); it != g_free_blocks.end() && it->first <= want + want / 8; ++it) {
+            if (it->second.device != dev) continue;
+            if (cudaStreamWaitEvent(stream, it->second.event, 0) == cudaSuccess) { pick = it; break; }
+            cudaGetLastError();
+        }
+    }
     if (pick != g_free_blocks.end()) {
         const CachedBlock b = pick->second;
         g_free_blocks.erase(pick);
@@ -98,6 +110,8 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
         e = cudaMalloc(out, want);
     }
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    g_reserved_bytes += (long long)want;
+    if (g_reserved_bytes > g_peak_reserved) g_peak_reserved = g_reserved_bytes;
     g_live_blocks[*out] = {want, dev};
     note_live_locked((long long)want);
     return NODEY_OK;
@@ -117,6 +131,7 @@ int device_free(void* p, cudaStream_t stream)
                 cudaGetLastError();
                 cudaStreamSynchronize(stream);
                 cudaFree(p);
+                g_reserved_bytes -= (long long)b.bytes;
                 return NODEY_OK;
             }
             g_free_blocks.emplace(b.bytes, b);
@@ -245,7 +260,22 @@ int nodey_memory_stats(int64_t* live_bytes, int64_t* peak_bytes, int reset_peak)
     std::lock_guard<std::mutex> lock(g_alloc_mu);
     if (live_bytes) *live_bytes = g_live_bytes;
     if (peak_bytes) *peak_bytes = g_peak_bytes;
-    if (reset_peak) g_peak_bytes = g_live_bytes;
+    if (reset_peak) { g_peak_bytes = g_live_bytes; g_peak_reserved = g_reserved_bytes; }
+    return NODEY_OK;
+}
+
+int nodey_memory_reserved(int64_t* reserved_bytes, int64_t* peak_reserved_bytes)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    if (reserved_bytes) *reserved_bytes = g_reserved_bytes;
+    if (peak_reserved_bytes) *peak_reserved_bytes = g_peak_reserved;
+    return NODEY_OK;
+}
+
+int nodey_set_memory_policy(int reuse_pending)
+{
+    std::lock_guard<std::mutex> lock(g_alloc_mu);
+    g_reuse_pending = reuse_pending != 0;
     return NODEY_OK;
 }
 

@@ -565,7 +565,13 @@ namespace infra
 	}
 
 	namespace { std::atomic<bool> g_release_products{false}; }
-	void Runner::release_products(bool release) { g_release_products = release; }
+	void Runner::release_products(bool release)
+	{
+		g_release_products = release;
+		// released blocks are only worth something if the next allocation may take them before the device has passed the
+		// free point: the allocator then orders the taker's stream after that point
+		nodey_set_memory_policy(release ? 1 : 0);
+	}
 
 	Runner::~Runner()
 	{
