@@ -82,6 +82,8 @@ int nodey_memory_reserved(int64_t* reserved_bytes, int64_t* peak_reserved_bytes)
 int nodey_set_memory_policy(int reuse_pending);
 int nodey_memset(void* dst, int value, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_h2d(void* dst, const void* src_host, size_t bytes, nodey_stream_t s);
+/* rows x width_bytes from host rows src_pitch apart to device rows dst_pitch apart, one enqueue (cudaMemcpy2DAsync) */
+int nodey_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes, size_t rows, nodey_stream_t s);
 int nodey_memcpy_d2h(void* dst_host, const void* src, size_t bytes, nodey_stream_t s);
 int nodey_memcpy_d2d(void* dst, const void* src, size_t bytes, nodey_stream_t s);
 int nodey_host_alloc(void** out, size_t bytes);      /* pinned host memory */
@@ -284,6 +286,16 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
 int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
                                 int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                                 int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream);
+
+/* SURVEY.md App. C7 compatibility: the node loop of the reference (audio-velocity.cpp:286-441), run with an input frame
+ * available at every turn, receives min(numSamples, 3 * 1152 / velocity) samples whenever more than 1152 / velocity are
+ * queued and leaves through `if (numSamples() == 0 && input_stream_eof) break;` (:414) before flush() whenever its last
+ * receive emptied SoundTouch's output -- the normal case -- so the tail SoundTouch still holds is never emitted.  This
+ * returns what that loop emits in total (always a prefix of the canonical render: pass it to run() as out_frames) and
+ * the frame sizes it pushes downstream (run-length encoded; *n_runs receives the number of runs needed), *flushed = 1
+ * when flush() was reached.  velocity: the node's velocity (1 for pitch_modifier).  Host arithmetic only. */
+int64_t nodey_soundtouch_reference_schedule(nodey_soundtouch* s, int64_t in_frames, int frame_size, float velocity,
+                                            int64_t* run_len, int64_t* run_count, int64_t run_cap, int64_t* n_runs, int* flushed);
 
 /* The same render cut into launches along time, so that a consumer can start before the producer has finished (the
  * reference pipelines its nodes frame by frame, audio-velocity.cpp:286-441; here the unit is a chunk of WSOLA sequences):

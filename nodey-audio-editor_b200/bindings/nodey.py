@@ -24,7 +24,7 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resample_tracks_chunks", "nodey_resample_tracks_chunk", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_reference_schedule", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
@@ -32,7 +32,7 @@ SYMBOLS = [
     "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",
     "nodey_bus_reduce", "nodey_bus_allreduce",
     "nodey_peer_alloc", "nodey_peer_free", "nodey_peer_export", "nodey_peer_open", "nodey_peer_close",
-    "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
+    "nodey_memset", "nodey_memcpy_h2d", "nodey_memcpy2d_h2d", "nodey_memcpy_d2h", "nodey_memcpy_d2d", "nodey_host_alloc", "nodey_host_free",
 ]
 
 
@@ -99,6 +99,8 @@ def lib():
     L.nodey_soundtouch_set_unfused.argtypes = [vp, i32]
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
     L.nodey_soundtouch_run_tracks.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, vp]
+    L.nodey_soundtouch_reference_schedule.argtypes = [vp, i64, i32, C.c_float, C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64), C.POINTER(i32)]
+    L.nodey_soundtouch_reference_schedule.restype = i64
     L.nodey_soundtouch_chunks.argtypes = [vp, i64, i32, i64, i32, C.POINTER(i64), C.POINTER(i64), i32]
     L.nodey_soundtouch_run_chunk.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, i32, i32, vp]
     L.nodey_soundtouch_run_tracks_chunk.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, i32, i32, vp]
@@ -529,6 +531,15 @@ class SoundTouch:
         if n < 0:
             raise NodeyError(n, "nodey_soundtouch_out_frames")
         return n, nseq.value
+
+    def reference_schedule(self, in_frames, velocity, frame_size=1152, cap=1 << 16):
+        """(total frames, [(frame size, count), ...], flushed) of the reference's node loop (App. C7)"""
+        a = (C.c_int64 * cap)(); b = (C.c_int64 * cap)()
+        n, fl = C.c_int64(), C.c_int()
+        total = lib().nodey_soundtouch_reference_schedule(self.h, in_frames, frame_size, C.c_float(velocity), a, b, cap, C.byref(n), C.byref(fl))
+        if total < 0:
+            raise NodeyError(total, "nodey_soundtouch_reference_schedule")
+        return total, [(a[k], b[k]) for k in range(min(n.value, cap))], bool(fl.value)
 
     def chunks(self, in_frames, frame_size=1152, want=8):
         """[(in_need, out_ready), ...]: chunk c may run once in_need input frames are final and makes out_ready output frames final"""

@@ -291,6 +291,13 @@ int nodey_memcpy_h2d(void* dst, const void* src, size_t bytes, nodey_stream_t s)
     return NODEY_OK;
 }
 
+int nodey_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows, nodey_stream_t s)
+{
+    if (width_bytes && rows)
+        NODEY_CUDA_OK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice, as_stream(s)));
+    return NODEY_OK;
+}
+
 int nodey_memcpy_d2h(void* dst, const void* src, size_t bytes, nodey_stream_t s)
 {
     if (bytes) NODEY_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(s)));

@@ -1479,6 +1479,77 @@ int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_str
     return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, stream);
 }
 
+/* SURVEY.md App. C7.  What soundtouch_process_payload (audio-velocity.cpp:286-441) emits when an input frame is available
+ * at every turn of its loop: one putSamples per turn, then receiveSamples(min(numSamples, 3 * 1152 / velocity)) whenever more
+ * than 1152 / velocity samples are queued; at the end of the input the loop leaves through `if (numSamples() == 0 &&
+ * input_stream_eof) break;` (:414) BEFORE it ever reaches flush() whenever the last receive emptied the FIFO -- which is the
+ * normal case -- and what SoundTouch still holds is lost.  Host arithmetic on lengths only: numSamples() after k frames is
+ * the unflushed output length of the first k frames minus what was received.  Returns the total the node emits (a prefix of
+ * the canonical, always-flushed render) and its frame sizes, run-length encoded. */
+int64_t nodey_soundtouch_reference_schedule(nodey_soundtouch* s, int64_t in_frames, int frame_size, float velocity,
+                                            int64_t* run_len, int64_t* run_count, int64_t run_cap, int64_t* n_runs, int* flushed)
+{
+    if (!s || in_frames < 0 || frame_size <= 0 || !(velocity > 0.f)) return NODEY_E_INVALID;
+    std::lock_guard<std::mutex> lock(s->mu);
+    // sequence positions are prefix stable in the input length: build them once for the longest input flush() can make
+    std::vector<long long> pos;
+    {
+        StageLens Lmax;
+        stage_lengths(s, in_frames + 128ll * 200, &Lmax, &pos);
+    }
+    const auto out_len = [&](long long n_ext) -> long long {
+        // stage_lengths() with the sequence count read off the table: sequences whose window fits into the TDStretch input
+        const auto nseq_of = [&](long long tds_in) -> long long {
+            long long lo = 0, hi = (long long)pos.size();
+            while (lo < hi) { const long long mid = (lo + hi) / 2; if (pos[(size_t)mid] + s->sample_req <= tds_in) lo = mid + 1; else hi = mid; }
+            return lo;
+        };
+        if (s->td_first) return cubic_count(s, fir_count(s, s->prefill + tds_out_frames(s, nseq_of(n_ext))));
+        return tds_out_frames(s, nseq_of(fir_count(s, cubic_count(s, s->prefill + n_ext))));
+    };
+    const double time_ratio = 1.0f / velocity;
+    const unsigned min_samples = (unsigned)(time_ratio * 1152), max_samples = (unsigned)(time_ratio * 1152 * 3);
+    const double denom = s->rate * s->tempo;
+    double expected = 0;
+    long long fed = 0, received = 0;
+    bool eof = false, created = false, did_flush = false;
+    std::vector<std::pair<long long, long long>> sizes;       // frame sizes the node pushes, run-length encoded
+    const auto emit = [&](long long n) {
+        if (!sizes.empty() && sizes.back().first == n) sizes.back().second++;
+        else sizes.emplace_back(n, 1);
+    };
+    for (;;) {
+        if (!eof) {
+            if (fed >= in_frames) eof = true;
+            else {
+                const long long n = (in_frames - fed) < frame_size ? (in_frames - fed) : frame_size;
+                fed += n; expected += (double)n / denom; created = true;
+            }
+        }
+        if (!created) { if (eof) break; continue; }
+        long long avail = out_len(fed) - received;
+        if (avail == 0 && eof) break;
+        if ((unsigned long long)avail > min_samples) {
+            const long long take = avail < (long long)max_samples ? avail : (long long)max_samples;
+            received += take; emit(take);
+        } else if (eof) {
+            int still = (int)((long)(expected + 0.5) - (long)received);
+            if (still < 0) still = 0;
+            long long ext = fed;
+            for (int i = 0; still > (int)(out_len(ext) - received) && i < 200; i++) ext += 128;
+            avail = out_len(ext) - received;
+            if (avail > still) avail = still;
+            did_flush = true;
+            if (avail > 0) { received += avail; emit(avail); }
+            break;
+        }
+    }
+    for (size_t k = 0; k < sizes.size() && (long long)k < run_cap && run_len && run_count; k++) { run_len[k] = sizes[k].first; run_count[k] = sizes[k].second; }
+    if (n_runs) *n_runs = (long long)sizes.size();
+    if (flushed) *flushed = did_flush ? 1 : 0;
+    return received;
+}
+
 int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t out_frames, int want_chunks,
                             int64_t* in_need, int64_t* out_ready, int cap)
 {

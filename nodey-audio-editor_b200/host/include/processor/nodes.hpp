@@ -140,6 +140,11 @@ namespace processor
 	{
 		float velocity = 1;
 		bool keep_pitch = false;
+		// SURVEY.md App. C7 switch (optional JSON key "reference_schedule", default off; NODEY_REFERENCE_SCHEDULE=1 turns it on
+		// for every node): emit what the reference's node loop emits -- its receive sizes as frame sizes and NO flushed tail
+		// when the loop leaves through its early break (audio-velocity.cpp:414) -- instead of the canonical 1152-sample
+		// frames of the complete, always flushed render
+		bool reference_schedule = false;
 
 	  public:
 		Velocity_modifier() = default;
@@ -154,6 +159,7 @@ namespace processor
 	class Pitch_modifier : public infra::Processor
 	{
 		float pitch = 0;
+		bool reference_schedule = false;     // see Velocity_modifier
 
 	  public:
 		Pitch_modifier() = default;

@@ -595,7 +595,13 @@ namespace processor
 		// one arena for every host source that has to be uploaded
 		size_t upload_bytes = 0;
 		for (const auto& s : sources)
-			if (s.data && !s.on_device) upload_bytes += Arena::padded((size_t)s.frames * (size_t)format_bytes(s.format) * (size_t)s.channels);
+			if (s.data && !s.on_device)
+			{
+				// the same arithmetic as the take() below: a planar stereo source is two padded planes
+				const bool planar2 = format_is_planar(s.format) && s.channels == 2;
+				const size_t plane_bytes = (size_t)s.frames * (size_t)format_bytes(s.format) * (format_is_planar(s.format) ? 1u : (size_t)s.channels);
+				upload_bytes += planar2 ? 2 * Arena::padded(plane_bytes) : Arena::padded(plane_bytes);
+			}
 		std::unique_ptr<Arena> arena;
 		if (upload_bytes) arena = std::make_unique<Arena>(upload_bytes);
 
@@ -644,10 +650,38 @@ namespace processor
 				if (u.buffer->frames != frames) nchunks = 1;
 			while (nchunks > 1 && (size_t)(frames / nchunks) * uploads.front().frame_bytes < kMinChunkBytes) nchunks /= 2;
 			if (nchunks < 1) nchunks = 1;
+			// One copy per chunk ROUND when the wave's sources sit at a constant pitch in host memory (rows of one pinned
+			// block: what a host that batches its tracks has) and -- always true here -- in the arena: a 2-D copy whose rows
+			// are the tracks.  Thousands of separate copies would fill the driver's copy queue and block this thread (the
+			// enqueue of everything downstream with it) until half of the audio has gone over the bus.
+			bool rows = uploads.size() > 1 && !uploads.front().planar2;
+			ptrdiff_t src_pitch = 0, dst_pitch = 0;
+			if (rows)
+			{
+				src_pitch = (const char*)sources[uploads[1].pin].data - (const char*)sources[uploads[0].pin].data;
+				dst_pitch = (const char*)uploads[1].p0 - (const char*)uploads[0].p0;
+				for (size_t k = 1; k < uploads.size() && rows; k++)
+					rows = uploads[k].frame_bytes == uploads[0].frame_bytes && !uploads[k].planar2 && uploads[k].buffer->frames == frames
+						&& (const char*)sources[uploads[k].pin].data - (const char*)sources[uploads[k - 1].pin].data == src_pitch
+						&& (const char*)uploads[k].p0 - (const char*)uploads[k - 1].p0 == dst_pitch;
+				rows = rows && src_pitch > 0 && dst_pitch > 0 && (size_t)src_pitch >= (size_t)frames * uploads[0].frame_bytes;
+			}
+			if (!rows)      // separate copies: keep their number per render in the hundreds
+				while (nchunks > 1 && (size_t)nchunks * file_count > 512) nchunks /= 2;
 			auto progress = std::make_shared<Stream_progress>();
 			progress->stream = cur_stream();
 			for (int c = 0; c < nchunks; c++)
 			{
+				if (rows)
+				{
+					const int64_t f0 = nchunks == 1 ? 0 : ((frames * c / nchunks) & ~(int64_t)63);
+					const int64_t f1 = c == nchunks - 1 ? frames : ((frames * (c + 1) / nchunks) & ~(int64_t)63);
+					const size_t fb = uploads[0].frame_bytes;
+					if (f1 > f0)
+						abi(nodey_memcpy2d_h2d((char*)uploads[0].p0 + (size_t)f0 * fb, (size_t)dst_pitch, (const char*)sources[uploads[0].pin].data + (size_t)f0 * fb,
+											   (size_t)src_pitch, (size_t)(f1 - f0) * fb, uploads.size(), cur_stream()), "audio_input");
+				}
+				else
 				for (const Pending& u : uploads)
 				{
 					const int64_t total = u.buffer->frames;
@@ -923,12 +957,14 @@ namespace processor
 	struct Soundtouch_params
 	{
 		float rate, pitch;
+		bool reference_schedule;
 		static Soundtouch_params of(const Processor* p)
 		{
+			static const bool everywhere = getenv("NODEY_REFERENCE_SCHEDULE") != nullptr;
 			if (const auto* v = dynamic_cast<const Velocity_modifier*>(p))
-				return {v->velocity, v->keep_pitch ? 1 / v->velocity : 1};                 // audio-velocity.cpp:457
+				return {v->velocity, v->keep_pitch ? 1 / v->velocity : 1, v->reference_schedule || everywhere};   // audio-velocity.cpp:457
 			const auto* q = dynamic_cast<const Pitch_modifier*>(p);
-			return {1.0f, std::pow(2.0f, q->pitch / 12.0f)};                                // audio-velocity.cpp:473-474
+			return {1.0f, std::pow(2.0f, q->pitch / 12.0f), q->reference_schedule || everywhere};                 // audio-velocity.cpp:473-474
 		}
 	};
 
@@ -940,7 +976,7 @@ namespace processor
 		bool soundtouch_batch(const std::vector<Processor::Batch_item>& items, const char* title)
 		{
 			struct Entry { size_t item; std::shared_ptr<const Audio_buffer> in; Soundtouch_params prm; };
-			std::map<std::tuple<int, int, int64_t, uint32_t, uint32_t, const Stream_progress*>, std::vector<Entry>> groups;
+			std::map<std::tuple<int, int, int64_t, uint32_t, uint32_t, const Stream_progress*, bool>, std::vector<Entry>> groups;
 			for (size_t k = 0; k < items.size(); k++)
 			{
 				// inputs that arrive chunk by chunk are not waited for here: the chunks below wait for the prefix they need
@@ -951,18 +987,40 @@ namespace processor
 				uint32_t rb, pb;
 				memcpy(&rb, &prm.rate, 4); memcpy(&pb, &prm.pitch, 4);
 				const Stream_progress* pg = in->progress.get();
-				groups[{in->sample_rate, in->channels, in->frames, rb, pb, pg}].push_back({k, std::move(in), prm});
+				groups[{in->sample_rate, in->channels, in->frames, rb, pb, pg, prm.reference_schedule}].push_back({k, std::move(in), prm});
 			}
 			const nodey_stream_t main_stream = cur_stream();
 			for (auto& [key, all] : groups)
 			{
-				const auto [rate_hz, ch, n, rb_, pb_, pg_] = key;
+				const auto [rate_hz, ch, n, rb_, pb_, pg_, ref_schedule] = key;
 				(void)rb_; (void)pb_; (void)pg_;
 				const std::shared_ptr<nodey_soundtouch> plan = soundtouch_for(rate_hz, ch, all.front().prm.rate, all.front().prm.pitch);
 				nodey_soundtouch* st = plan.get();
 				int64_t nseq = 0;
-				const int64_t m = nodey_soundtouch_out_frames(st, n, kSoundtouchFrame, &nseq);
+				int64_t m = nodey_soundtouch_out_frames(st, n, kSoundtouchFrame, &nseq);
 				if (m < 0) abi((int)m, title);
+				// frame sizes of the product: canonical 1152-sample frames of the complete render, or -- App. C7 switch --
+				// what the reference's loop receives, without the tail it never flushes (a prefix of the same samples)
+				Frame_runs out_runs = uniform_frame_runs(m, kSoundtouchFrame);
+				if (ref_schedule)
+				{
+					std::vector<int64_t> rl(64), rc(64);
+					int64_t n_runs = 0;
+					int flushed = 0;
+					int64_t total = 0;
+					for (int attempt = 0; attempt < 2; attempt++)
+					{
+						total = nodey_soundtouch_reference_schedule(st, n, kSoundtouchFrame, all.front().prm.rate, rl.data(), rc.data(), (int64_t)rl.size(),
+																	&n_runs, &flushed);
+						if (total < 0) abi((int)total, title);
+						if (n_runs <= (int64_t)rl.size()) break;
+						rl.resize((size_t)n_runs); rc.resize((size_t)n_runs);
+					}
+					if (total > m) THROW_LOGIC_ERROR("reference schedule yields {} frames, the complete render {}", total, m);
+					m = total;
+					out_runs.clear();
+					for (int64_t k = 0; k < n_runs; k++) out_runs.emplace_back(rl[(size_t)k], rc[(size_t)k]);
+				}
 				for (size_t first = 0; first < all.size(); first += kMaxTracksPerLaunch)
 				{
 					const size_t cnt = std::min(kMaxTracksPerLaunch, all.size() - first);
@@ -1053,8 +1111,10 @@ namespace processor
 					for (size_t k = 0; k < cnt; k++)
 					{
 						const Entry& e = all[first + k];
-						auto b = new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m,
-											uniform_frame_runs(m, kSoundtouchFrame), e.in->pts_seconds);
+						// App. C8 (same switch): the reference stamps its frames with (int64_t)(float)(seconds * 1e6) microseconds
+						// (construct_audio_frame_float takes `float time_us`, audio-velocity.cpp:234-250); canonical: the exact start
+						const double pts = ref_schedule ? (double)(int64_t)(float)(e.in->pts_seconds * 1000000) / 1000000.0 : e.in->pts_seconds;
+						auto b = new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m, out_runs, pts);
 						if (done) { b->ready = done; b->progress = progress; }
 						publish(*items[e.item].output, "output", b);
 					}
@@ -1080,12 +1140,14 @@ namespace processor
 		Json::Value value;
 		value["velocity"] = velocity;
 		value["keep_pitch"] = keep_pitch;
+		if (reference_schedule) value["reference_schedule"] = true;      // written only when set: reference files stay as they are
 		return value;
 	}
 	void Velocity_modifier::deserialize(const Json::Value& value)
 	{
 		if (value.isMember("velocity") && value["velocity"].isDouble()) velocity = value["velocity"].asFloat();
 		if (value.isMember("keep_pitch") && value["keep_pitch"].isBool()) keep_pitch = value["keep_pitch"].asBool();
+		if (value.isMember("reference_schedule") && value["reference_schedule"].isBool()) reference_schedule = value["reference_schedule"].asBool();
 	}
 	bool Velocity_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Velocity modifier"); }
 	void Velocity_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
@@ -1107,11 +1169,13 @@ namespace processor
 	{
 		Json::Value value;
 		value["pitch"] = pitch;
+		if (reference_schedule) value["reference_schedule"] = true;
 		return value;
 	}
 	void Pitch_modifier::deserialize(const Json::Value& value)
 	{
 		if (value.isMember("pitch") && value["pitch"].isDouble()) pitch = value["pitch"].asFloat();
+		if (value.isMember("reference_schedule") && value["reference_schedule"].isBool()) reference_schedule = value["reference_schedule"].asBool();
 	}
 	bool Pitch_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Pitch modifier"); }
 	void Pitch_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)

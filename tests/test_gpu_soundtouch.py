@@ -244,3 +244,65 @@ def test_soundtouch_chunks_of_uncuttable_paths(nd, orc):
     rc = nd.lib().nodey_soundtouch_run_chunk(st3.h, nd._dp(out), out.stride(0), nd._dp(x), x.stride(0), 1, 48000, 1152, m,
                                              nd._dp(offs), offs.stride(0), 0, 4, nd._stream())
     assert rc == -5      # NODEY_E_RANGE
+
+
+@pytest.mark.parametrize("cfg", [(48000, 2, 1.0, ("st", 3.0), 4.0), (48000, 2, 1.25, ("keep", 1.25), 4.0), (44100, 2, 0.7, ("none", 0), 3.0),
+                                 (48000, 1, 1.0, ("st", 3.0), 3.0), (22050, 1, 1.5, ("keep", 1.5), 3.0), (48000, 2, 2.0, ("keep", 2.0), 2.5),
+                                 (48000, 2, 1.0, ("st", 3.0), 0.05)])
+def test_reference_schedule_matches_the_restated_node_loop(nd, orc, cfg):
+    """SURVEY.md App. C7 switch: nodey_soundtouch_reference_schedule (host arithmetic on lengths) against the literal
+    restatement of soundtouch_process_payload on the oracle's streaming model (orc_soundtouch_reference_loop): total
+    frames, every receive size, whether flush() was reached; and the kernels' render cut to that total is the loop's output."""
+    sr, ch, velocity, spec, secs = cfg
+    n = int(sr * secs) + 17
+    x = orc.synth_f32(n, ch, sr, 9)
+    pitch = _pitch(orc, spec, velocity)
+    ref, sizes, flushed = orc.soundtouch_reference_loop(x, sr, velocity, pitch, 1152)
+    st = nd.SoundTouch(sr, ch, velocity, pitch)
+    total, runs, fl = st.reference_schedule(n, velocity)
+    assert total == ref.shape[0]
+    assert [s for s, c in runs for _ in range(c)] == list(sizes)
+    assert fl == flushed
+    canonical = st.run(to_dev(x), 1152).cpu().numpy()
+    assert total <= canonical.shape[0]
+    assert_bit_equal(canonical[:total], ref, "reference-loop output = prefix of the canonical render")
+
+
+def test_reference_schedule_switch_on_the_nodes(eng_gpu, orc):  # noqa: C901
+    """project JSON key "reference_schedule": the pitch and the tempo node emit the reference loop's frames (sizes and
+    count) instead of the canonical ones; off by default and absent from serialised projects unless set"""
+    import json
+    sr, n = 48000, 48000 * 3 + 5
+    x = orc.synth_f32(n, 2, sr, 4)
+
+    def render(flag):
+        p = eng_gpu.Project()
+        src = p.add("audio_input", {"file_path": [""]})
+        pm = p.add("pitch_modifier", dict({"pitch": 3.0}, **({"reference_schedule": True} if flag else {})))
+        vm = p.add("velocity_modifier", dict({"velocity": 1.25, "keep_pitch": True}, **({"reference_schedule": True} if flag else {})))
+        out = p.add("audio_output")
+        p.link(src, "output_0", pm, "input"); p.link(pm, "output", vm, "input"); p.link(vm, "output", out, "input")
+        e = eng_gpu.Engine(p.json())
+        e.bind_source(0, x, FMT_FLT_, sr)
+        e.run()
+        text = json.loads(e.serialize())
+        return e, pm, vm, text
+
+    e, pm, vm, text = render(True)
+    y1, s1, _ = orc.soundtouch_reference_loop(x, sr, 1.0, orc.pitch_node_factor(3.0), 1152)
+    y2, s2, _ = orc.soundtouch_reference_loop(y1, sr, 1.25, orc.velocity_node_pitch(1.25, True), 1152)
+    assert_bit_equal(e.product(pm, "output").numpy(), y1, "pitch node, reference schedule")
+    assert [s for s, c in e.product_runs(pm, "output") for _ in range(c)] == list(s1)
+    assert_bit_equal(e.output().numpy(), y2, "tempo node, reference schedule")
+    assert [s for s, c in e.product_runs(vm, "output") for _ in range(c)] == list(s2)
+    assert text["nodes"][str(pm)]["info"]["reference_schedule"] is True
+    e.close()
+    e, pm, vm, text = render(False)
+    c1, _, _ = orc.soundtouch(x, sr, 1.0, orc.pitch_node_factor(3.0), 1152)
+    c2, _, _ = orc.soundtouch(c1, sr, 1.25, orc.velocity_node_pitch(1.25, True), 1152)
+    assert_bit_equal(e.output().numpy(), c2, "canonical render")
+    assert len(c2) > len(y2) and "reference_schedule" not in text["nodes"][str(pm)]["info"]
+    e.close()
+
+
+FMT_FLT_ = 3
