@@ -431,9 +431,9 @@ def run_ours(args):
 
     # ---- per-kernel device time of one step (events around every launch; not part of the timed runs) ----
     roofline = None
-    # The render runs as two half-size waves on two compute lanes; kernels of the two lanes overlap, so events around
-    # a launch would time its share of the machine, not the kernel.  The profiled step therefore runs the same graph
-    # as ONE wave on one lane (NODEY_WAVE larger than the pin count): every launch alone on the device, full batch.
+    # In the timed steps the nodes of a track chain overlap chunk by chunk on the lane's three streams, so events around a
+    # launch would time its share of the machine, not the kernel.  The profiled step therefore runs the same graph with
+    # whole-track launches (NODEY_ST_CHUNKS=1) as ONE wave on one lane: every launch alone on the device, full batch.
     # Likewise the WSOLA chains run as ONE launch per node there (NODEY_ST_CHUNKS=1): in the timed steps the pitch and the
     # tempo node's chunk launches overlap on two streams.
     os.environ["NODEY_WAVE"] = "1000000"

@@ -88,7 +88,8 @@ int device_alloc(void** out, size_t bytes, cudaStream_t stream)
     if (pick == g_free_blocks.end() && g_reuse_pending) {
         // memory-saving policy: a block another stream has freed but whose free point the device has not reached yet is
         // handed out too -- the requesting stream waits for that point first (stream-ordered reuse across streams)
-        for (auto it = g_free_blocks.lower_bound(want); it != g_free_blocks.end() && it->first <= want + want / 8; ++it) {
+        // (any block up to twice the size: in this mode a smaller footprint is worth more than a tight fit)
+        for (auto it = g_free_blocks.lower_bound(want); it != g_free_blocks.end() && it->first <= 2 * want; ++it) {
             if (it->second.device != dev) continue;
             if (cudaStreamWaitEvent(stream, it->second.event, 0) == cudaSuccess) { pick = it; break; }
             cudaGetLastError();

@@ -496,7 +496,7 @@ namespace infra
 		// NODEY_WAVES="a,b,c" an explicit pattern.
 		const bool pipelined = upload >= (1u << 30);
 		int uniform = 0;
-		if (const char* env = getenv("NODEY_WAVE")) uniform = std::max(1, atoi(env));
+		if (const char* env = getenv("NODEY_WAVE"); env && *env) uniform = std::max(1, atoi(env));
 		int source_pins = 0;
 		if (!levels.empty())
 			for (const Id_t id : levels.front())
@@ -518,14 +518,9 @@ namespace infra
 		}
 		else if (uniform > 0)
 			for (int p = uniform; p < source_pins; p += uniform) wave_begin.push_back(p);
-		else if (!pipelined && source_pins >= 128)
-		{
-			// sources already in HBM: two half-size waves on two lanes.  The batched kernels lose nothing at 64+ tracks,
-			// and the second lane fills what a single stream leaves idle -- the SMs that hold one WSOLA CTA instead of
-			// two, the tail of every kernel (256 tracks: 241 -> 233 ms, 128 tracks: 129 -> 126 ms; 64 tracks lose 3 %,
-			// tools/value_waves.py)
-			wave_begin.push_back(((source_pins / 2 + 15) / 16) * 16);
-		}
+		// (sources already in HBM: ONE wave.  Round 1 split such a render into two half-size waves on two lanes to fill
+		// what a single stream left idle; now the nodes of a track chain overlap chunk by chunk on the lane's three streams,
+		// which fills the same gaps with full-size batches: 256 tracks 216 ms as one wave, 230 ms as two.)
 		else if (pipelined && source_pins > 32)
 		{
 			constexpr int kEdge = 32, kBody = 32;

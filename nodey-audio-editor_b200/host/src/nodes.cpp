@@ -152,7 +152,7 @@ namespace processor
 		int stream_chunk_count()
 		{
 			const char* env = getenv("NODEY_ST_CHUNKS");
-			return env ? std::clamp(atoi(env), 1, 64) : 8;
+			return env && *env ? std::clamp(atoi(env), 1, 64) : 16;
 		}
 
 		std::shared_ptr<Audio_buffer> new_buffer(const std::shared_ptr<infra::Device_block>& block, void* p0, void* p1, int fmt, int rate,
