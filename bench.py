@@ -298,6 +298,53 @@ def check_parity(args, world, rank, dev, eng, ids, first, t_local, bus_t, finish
     return res
 
 
+def measure_footprint(args, dev, eng, t_local):
+    """High-water mark of device memory the library obtained from the driver for ONE render of the workload (sources
+    resident, their 16.3 GB belong to the caller and are not counted), from an empty allocator cache, under both memory
+    policies: keep (every link's product lives until the next run, like the reference's link_products) and release
+    (infra::Runner::release_products: a link lets go once its consumer has enqueued; freed blocks are reused in stream
+    order).  The timed steps use `keep`."""
+    import torch
+    import nodey
+    import engine
+    L = nodey.lib()
+    n_in = IN_RATE * args.seconds
+    eng._keep = []                         # sources bound earlier (parity check) may go
+    torch.cuda.empty_cache()
+    x = torch.empty((t_local, n_in, 2), dtype=torch.float32, device=dev)
+    for t in range(t_local):
+        nodey.check(L.nodey_synth(nodey._dp(x[t]), None, n_in, 2, IN_RATE, t, 0, None))
+    for t in range(t_local):
+        eng.bind_source(t, x[t], nodey.FMT_FLT, IN_RATE)
+    out = {}
+    for policy in ("keep", "release"):
+        engine.set_release_products(policy == "release")
+        try:
+            eng.run()                      # drops the previous run's products
+            torch.cuda.synchronize()
+            if policy == "release":
+                eng.run()
+                torch.cuda.synchronize()
+            nodey.check(L.nodey_trim_memory())
+            held, _ = nodey.memory_reserved()      # what the last run still holds (sink, spectrum; every product under `keep`)
+            nodey.memory_stats(reset_peak=True)
+            t0 = time.perf_counter()
+            eng.run()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3
+            _, peak = nodey.memory_reserved()
+            out[policy] = {"peak_gb": round(peak / 1e9, 2), "held_before_gb": round(held / 1e9, 2), "cold_cache_run_ms": round(ms, 1)}
+        finally:
+            engine.set_release_products(False)
+    out["note"] = "peak_gb: device memory obtained through the library's allocator during one render that starts from an empty cache (it " \
+                  "includes what the previous run's surviving products still held: held_before_gb); the caller's sources (%.1f GB) are " \
+                  "not counted; cold_cache_run_ms is that render's wall time with every block freshly cudaMalloc'ed" % (t_local * n_in * 8 / 1e9)
+    eng.run()
+    torch.cuda.synchronize()
+    del x
+    return out
+
+
 def run_ours(args):
     result_out = JsonStdout()
     import ctypes as C
@@ -544,6 +591,11 @@ def run_ours(args):
     if not args.no_parity:
         parity = check_parity(args, world, rank, dev, eng, ids, first, t_local, bus_t, finish, bind)
 
+    # ---- device-memory footprint of one render under both memory policies (not timed) ----
+    memory = None
+    if world == 1 and not args.no_parity and not args.no_e2e:
+        memory = measure_footprint(args, dev, eng, t_local)
+
     configs = segments = None
     if not args.no_configs:
         eng.close()
@@ -564,7 +616,7 @@ def run_ours(args):
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
                "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-               "parity": parity, "configs": configs, "segments": segments}
+               "parity": parity, "memory": memory, "configs": configs, "segments": segments}
         result_out.emit(json.dumps(out))
     eng.close()
     if world > 1:

@@ -304,15 +304,19 @@ int64_t nodey_soundtouch_reference_schedule(nodey_soundtouch* s, int64_t in_fram
  * [0, out_ready[c]) final (the last chunk needs / makes everything).  run_chunk / run_tracks_chunk are run / run_tracks
  * restricted to chunk `chunk` of `nchunks`; chunks run in order on one stream, with the SAME arguments, and `offsets`
  * (required here: n_sequences - 1 ints per track, device) carries the chain from one chunk to the next.  The result is
- * bit identical to the one-launch render. */
+ * bit identical to the one-launch render.
+ * phase: 0 = the chunk's WSOLA search and its tail (cross-fade + AA FIR + cubic transposer over the tiles those sequences
+ * complete) on `stream`; 1 = the search only, 2 = the tail only -- so that a caller can keep the sequential search chain
+ * on a stream of its own, back to back, and run the tails next to it (tail c after search c; search c + 1 does not wait
+ * for tail c).  A chunk's input and output ranges (in_need / out_ready) are those of both phases together. */
 int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_size, int64_t out_frames, int want_chunks,
                             int64_t* in_need, int64_t* out_ready, int cap);
 int nodey_soundtouch_run_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream);
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, int phase, nodey_stream_t stream);
 int nodey_soundtouch_run_tracks_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
                                       int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream);
+                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, int phase, nodey_stream_t stream);
 
 /* N2  audio_spectrum (new node; FFTW r2c convention, unnormalised):
  * per channel, frame m = x[m*hop .. m*hop+nfft) * periodic Hann; out[ch][m][0..nfft/2] complex64

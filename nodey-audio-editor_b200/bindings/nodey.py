@@ -102,8 +102,8 @@ def lib():
     L.nodey_soundtouch_reference_schedule.argtypes = [vp, i64, i32, C.c_float, C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64), C.POINTER(i32)]
     L.nodey_soundtouch_reference_schedule.restype = i64
     L.nodey_soundtouch_chunks.argtypes = [vp, i64, i32, i64, i32, C.POINTER(i64), C.POINTER(i64), i32]
-    L.nodey_soundtouch_run_chunk.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, i32, i32, vp]
-    L.nodey_soundtouch_run_tracks_chunk.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, i32, i32, vp]
+    L.nodey_soundtouch_run_chunk.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, i32, i32, i32, vp]
+    L.nodey_soundtouch_run_tracks_chunk.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, i32, i32, i32, vp]
     L.nodey_amix_plan.argtypes = [C.POINTER(i32), i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i32,
                                   C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64),
                                   C.POINTER(i64), C.POINTER(i64), i64, C.POINTER(i64)]
@@ -566,7 +566,7 @@ class SoundTouch:
             if poison is not None:
                 poison(c, plan[c][0])
             check(lib().nodey_soundtouch_run_chunk(self.h, _dp(out), out.stride(0), _dp(x), x.stride(0), ntr, n, frame_size, m,
-                                                   _dp(offs), offs.stride(0), c, len(plan), _stream()))
+                                                   _dp(offs), offs.stride(0), c, len(plan), 0, _stream()))
         return out, offs[:, :max(nseq - 1, 0)], plan
 
     def run(self, x, frame_size=1152, want_offsets=False, out=None):

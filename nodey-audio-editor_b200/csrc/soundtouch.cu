@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -796,7 +797,7 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                             const long long mid = j == 0 ? mid_j[0] : (j == 1 ? mid_j[1] : mid_j[2]);
                             const float2 m = planar ? make_float2(__ldg(pl + mid + k), __ldg(pr + mid + k)) : __ldg(b2 + mid + k);
                             const float f1 = a.fade[k], f2 = a.fade[ovl + k];
-                            x = make_float2(__fadd_rn(__fmul_rn(x.x, f1), __fmul_rn(m.x, f2)), __fadd_rn(__fmul_rn(x.y, f1), __fmul_rn(m.y, f2)));
+                            x = __fadd2_rn(__fmul2_rn(x, make_float2(f1, f1)), __fmul2_rn(m, make_float2(f2, f2)));
                         }
                         f[u] = x;
                     }
@@ -827,9 +828,14 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
         }
         __syncthreads();
         {
-            float e0[kFirS], e1[kFirS], o0[kFirS], o1[kFirS];
+            // Both channels of a frame meet the same tap, so the two rounded multiplies and the two rounded adds of a tap
+            // are ONE packed instruction each (mul.rn.f32x2 / add.rn.f32x2: per component the same result as the scalar
+            // operations, sm_100).  The FP32 pipe does the same work, but the kernel was ISSUE bound with 40 % of its issue
+            // slots going to everything that is not FIR arithmetic (ncu, round 1: issue 88 %, FMA pipe 55 %): the packed
+            // form needs half the slots for the FIR.
+            float2 e[kFirS], o[kFirS];
 #pragma unroll
-            for (int r = 0; r < kFirS; r++) { e0[r] = e1[r] = o0[r] = o1[r] = 0.f; }
+            for (int r = 0; r < kFirS; r++) { e[r] = make_float2(0.f, 0.f); o[r] = make_float2(0.f, 0.f); }
             float4 w[5];
             const int c0 = threadIdx.x * (kFirS / 2);
 #pragma unroll
@@ -837,22 +843,20 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
 #pragma unroll
             for (int step = 0; step < kAaLen / 2; step++) {
                 const float h0 = a.h[2 * step], h1 = a.h[2 * step + 1];
+                const float2 hh0 = make_float2(h0, h0), hh1 = make_float2(h1, h1);
 #pragma unroll
                 for (int r = 0; r < kFirS; r++) {
                     const float4 ce = w[(step + r / 2) % 5], co = w[(step + (r + 1) / 2) % 5];
-                    const float xe0 = (r & 1) ? ce.z : ce.x, xe1 = (r & 1) ? ce.w : ce.y;
-                    const float xo0 = ((r + 1) & 1) ? co.z : co.x, xo1 = ((r + 1) & 1) ? co.w : co.y;
-                    e0[r] = __fadd_rn(e0[r], __fmul_rn(xe0, h0));
-                    e1[r] = __fadd_rn(e1[r], __fmul_rn(xe1, h0));
-                    o0[r] = __fadd_rn(o0[r], __fmul_rn(xo0, h1));
-                    o1[r] = __fadd_rn(o1[r], __fmul_rn(xo1, h1));
+                    const float2 xe = (r & 1) ? make_float2(ce.z, ce.w) : make_float2(ce.x, ce.y);
+                    const float2 xo = ((r + 1) & 1) ? make_float2(co.z, co.w) : make_float2(co.x, co.y);
+                    e[r] = __fadd2_rn(e[r], __fmul2_rn(xe, hh0));
+                    o[r] = __fadd2_rn(o[r], __fmul2_rn(xo, hh1));
                 }
                 if (step + 1 < kAaLen / 2) w[step % 5] = tile[fir_chunk(c0 + step + 5)];
             }
             // park the filtered frames (frame q of the tile lives at q + q/8)
 #pragma unroll
-            for (int r = 0; r < kFirS; r++)
-                filt[threadIdx.x * (kFirS + 1) + r] = make_float2(__fadd_rn(o0[r], e0[r]), __fadd_rn(o1[r], e1[r]));
+            for (int r = 0; r < kFirS; r++) filt[threadIdx.x * (kFirS + 1) + r] = __fadd2_rn(o[r], e[r]);
         }
         __syncthreads();
         // cubic transposer over the tile (InterpolateCubic::transposeStereo).  The read position of output i is i * R in
@@ -889,9 +893,8 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             const int q = (int)(P - n0);
             const auto at = [&](int f) { return filt[f + (f >> 3)]; };
             const float2 p0 = at(q), p1 = at(q + 1), p2 = at(q + 2), p3 = at(q + 3);
-            float2 o;
-            o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.x), __fmul_rn(y1, p1.x)), __fmul_rn(y2, p2.x)), __fmul_rn(y3, p3.x));
-            o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(y0, p0.y), __fmul_rn(y1, p1.y)), __fmul_rn(y2, p2.y)), __fmul_rn(y3, p3.y));
+            const float2 o = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(p0, make_float2(y0, y0)), __fmul2_rn(p1, make_float2(y1, y1))),
+                                                   __fmul2_rn(p2, make_float2(y2, y2))), __fmul2_rn(p3, make_float2(y3, y3)));
             reinterpret_cast<float2*>(out)[i] = o;
         }
     }
@@ -922,6 +925,10 @@ struct nodey_soundtouch {
     // on other streams (the Runner's lanes share cached plans) only have to wait for its upload event.
     struct PosTable { long long* d = nullptr; std::vector<long long> host; cudaEvent_t ready = nullptr; };
     std::map<long long, PosTable*> tables;
+    // host-side length bookkeeping of a render (flush iterations included) by (input frames, putSamples chunk): a chunked
+    // render asks for it once per launch, and walking the sequence table a few dozen times costs more than the launch
+    struct LenPlan { long long n_ext, l1, l2, l3, nseq, tds_in, total; std::vector<long long> pos; };
+    std::map<std::pair<long long, int>, std::shared_ptr<const LenPlan>> len_plans;
     std::mutex mu;
 };
 
@@ -1012,6 +1019,21 @@ long long plan_total(nodey_soundtouch* s, long long in_frames, int frame_size, S
         if (L->l3 >= want) return want;
     }
     return L->l3;
+}
+
+// plan_total() with its result remembered in the plan object (caller holds s->mu)
+std::shared_ptr<const nodey_soundtouch::LenPlan> cached_lengths(nodey_soundtouch* s, long long in_frames, int frame_size)
+{
+    const auto key = std::make_pair(in_frames, frame_size);
+    const auto it = s->len_plans.find(key);
+    if (it != s->len_plans.end()) return it->second;
+    auto p = std::make_shared<nodey_soundtouch::LenPlan>();
+    StageLens L;
+    p->total = plan_total(s, in_frames, frame_size, &L, &p->pos);
+    p->n_ext = L.n_ext; p->l1 = L.l1; p->l2 = L.l2; p->l3 = L.l3; p->nseq = L.nseq; p->tds_in = L.tds_in;
+    if (s->len_plans.size() >= 16) s->len_plans.clear();
+    s->len_plans[key] = p;
+    return p;
 }
 
 }  // namespace
@@ -1155,10 +1177,9 @@ int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int 
 {
     if (!s || in_frames < 0 || frame_size <= 0) return NODEY_E_INVALID;
     std::lock_guard<std::mutex> lock(s->mu);
-    StageLens L;
-    const long long total = plan_total(s, in_frames, frame_size, &L, nullptr);
-    if (n_sequences) *n_sequences = L.nseq;
-    return total;
+    const std::shared_ptr<const nodey_soundtouch::LenPlan> lp = cached_lengths(s, in_frames, frame_size);
+    if (n_sequences) *n_sequences = lp->nseq;
+    return lp->total;
 }
 
 }  // extern "C"
@@ -1248,10 +1269,11 @@ void chunk_plan(const nodey_soundtouch* s, const StageLens& L, const std::vector
 
 }  // namespace
 
-// chunk < 0: the whole render in one go (nchunks ignored)
+// chunk < 0: the whole render in one go (nchunks ignored).  phase (chunked fused path): 0 = search + tail, 1 = the WSOLA
+// search of the chunk only, 2 = its tail only (cross-fade + FIR + cubic over the tiles the searched sequences complete)
 static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride, const TrackTab* tab,
                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, int phase, nodey_stream_t stream)
 {
     NODEY_REQUIRE(s && out && (in || tab), NODEY_E_INVALID, "nodey_soundtouch_run: null argument");
     NODEY_REQUIRE(ntracks >= 1 && in_frames >= 0 && frame_size > 0, NODEY_E_INVALID, "nodey_soundtouch_run: bad size");
@@ -1262,9 +1284,10 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
     }
     std::lock_guard<std::mutex> lock(s->mu);
     cudaStream_t st = as_stream(stream);
-    StageLens L;
-    std::vector<long long> pos;
-    const long long total = plan_total(s, in_frames, frame_size, &L, &pos);
+    const std::shared_ptr<const nodey_soundtouch::LenPlan> lp = cached_lengths(s, in_frames, frame_size);
+    StageLens L{lp->n_ext, lp->l1, lp->l2, lp->l3, lp->nseq, lp->tds_in};
+    const std::vector<long long>& pos = lp->pos;
+    const long long total = lp->total;
     NODEY_REQUIRE(out_frames >= 0 && out_frames <= total, NODEY_E_RANGE,
                   "nodey_soundtouch_run: out_frames %lld exceeds what SoundTouch would produce (%lld)", (long long)out_frames, total);
     if (out_frames == 0) return NODEY_OK;
@@ -1407,13 +1430,13 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
     if (fused) {
         // offsets, then the fused assemble + FIR + cubic tail, both over this chunk's range
         View v0{in, in_frames, 0, in_stride, tab ? 1 : 0};
-        if (chunk >= 0 && nchunks > 1 && chunk == 0) {
+        if (chunk >= 0 && nchunks > 1 && chunk == 0 && phase != 2) {
             // the tail's interior fast path looks at the offsets of the next sequences before it knows whether it needs
             // them: give the not yet searched ones a defined value
             NODEY_CUDA_OK(cudaMemsetAsync(d_offs, 0, sizeof(int) * (size_t)offs_stride * (size_t)ntracks, st));
         }
-        rc = run_offsets(v0, cp.seq_begin, cp.seq_end);
-        if (rc == NODEY_OK && cp.tile_end > cp.tile_begin) {
+        if (phase != 2) rc = run_offsets(v0, cp.seq_begin, cp.seq_end);
+        if (rc == NODEY_OK && phase != 1 && cp.tile_end > cp.tile_begin) {
             PostArgs pa;
             pa.in = v0; if (v0.use_tab) pa.tt = *tab;
             pa.pos = d_pos; pa.offs = d_offs; pa.offs_stride = offs_stride; pa.fade = s->d_fade;
@@ -1453,7 +1476,7 @@ int nodey_soundtouch_run(nodey_soundtouch* s, float* out, int64_t out_stride, co
                          int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
                          int32_t* offsets, int64_t offsets_stride, nodey_stream_t stream)
 {
-    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, stream);
+    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, 0, stream);
 }
 
 static int make_tab(const nodey_soundtouch* s, TrackTab* tab, const float* const* in_a, const float* const* in_b, int ntracks)
@@ -1476,7 +1499,7 @@ int nodey_soundtouch_run_tracks(nodey_soundtouch* s, float* out, int64_t out_str
     TrackTab tab;
     const int rc = make_tab(s, &tab, in_a, in_b, ntracks);
     if (rc != NODEY_OK) return rc;
-    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, stream);
+    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, -1, 1, 0, stream);
 }
 
 /* SURVEY.md App. C7.  What soundtouch_process_payload (audio-velocity.cpp:286-441) emits when an input frame is available
@@ -1555,9 +1578,10 @@ int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_si
 {
     NODEY_REQUIRE(s && in_frames >= 0 && frame_size > 0 && out_frames >= 0, NODEY_E_INVALID, "nodey_soundtouch_chunks: bad argument");
     std::lock_guard<std::mutex> lock(s->mu);
-    StageLens L;
-    std::vector<long long> pos;
-    const long long total = plan_total(s, in_frames, frame_size, &L, &pos);
+    const std::shared_ptr<const nodey_soundtouch::LenPlan> lp = cached_lengths(s, in_frames, frame_size);
+    StageLens L{lp->n_ext, lp->l1, lp->l2, lp->l3, lp->nseq, lp->tds_in};
+    const std::vector<long long>& pos = lp->pos;
+    const long long total = lp->total;
     NODEY_REQUIRE(out_frames <= total, NODEY_E_RANGE, "nodey_soundtouch_chunks: out_frames %lld exceeds what SoundTouch would produce (%lld)",
                   (long long)out_frames, total);
     const int n = out_frames == 0 ? 1 : effective_chunks(s, L, want_chunks);
@@ -1573,21 +1597,21 @@ int nodey_soundtouch_chunks(nodey_soundtouch* s, int64_t in_frames, int frame_si
 
 int nodey_soundtouch_run_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* in, int64_t in_stride,
                                int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
+                               int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, int phase, nodey_stream_t stream)
 {
-    NODEY_REQUIRE(chunk >= 0, NODEY_E_INVALID, "nodey_soundtouch_run_chunk: negative chunk");
-    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, stream);
+    NODEY_REQUIRE(chunk >= 0 && phase >= 0 && phase <= 2, NODEY_E_INVALID, "nodey_soundtouch_run_chunk: bad chunk or phase");
+    return soundtouch_run_impl(s, out, out_stride, in, in_stride, nullptr, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, phase, stream);
 }
 
 int nodey_soundtouch_run_tracks_chunk(nodey_soundtouch* s, float* out, int64_t out_stride, const float* const* in_a, const float* const* in_b,
                                       int ntracks, int64_t in_frames, int frame_size, int64_t out_frames,
-                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, nodey_stream_t stream)
+                                      int32_t* offsets, int64_t offsets_stride, int chunk, int nchunks, int phase, nodey_stream_t stream)
 {
-    NODEY_REQUIRE(chunk >= 0, NODEY_E_INVALID, "nodey_soundtouch_run_tracks_chunk: negative chunk");
+    NODEY_REQUIRE(chunk >= 0 && phase >= 0 && phase <= 2, NODEY_E_INVALID, "nodey_soundtouch_run_tracks_chunk: bad chunk or phase");
     TrackTab tab;
     const int rc = make_tab(s, &tab, in_a, in_b, ntracks);
     if (rc != NODEY_OK) return rc;
-    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, stream);
+    return soundtouch_run_impl(s, out, out_stride, nullptr, 0, &tab, ntracks, in_frames, frame_size, out_frames, offsets, offsets_stride, chunk, nchunks, phase, stream);
 }
 
 }  // extern "C"

@@ -17,9 +17,12 @@ namespace infra
 	{
 		Stream_handle stream = nullptr;   // launch everything of the current node (batch) on this stream
 		// further streams of the lane (may be null): a node whose input arrives chunk by chunk (Audio_buffer::progress) runs
-		// on the stream AFTER its producer's in the cycle stream -> side[0] -> side[1] -> stream, so that a chain of such
-		// nodes (resampler -> pitch -> tempo) overlaps stage by stage; it publishes with an event recorded there
-		Stream_handle side_stream[2] = {nullptr, nullptr};
+		// on the stream(s) AFTER its producer's in the cycle stream -> side[0] -> ... -> side[3] -> stream, so that a chain of
+		// such nodes (resampler -> pitch -> tempo) overlaps stage by stage; a SoundTouch node takes two: one for its
+		// sequential WSOLA search, which must never wait for anything but its input, one for the tails.  Products are
+		// published with events recorded on those streams.
+		static constexpr int kSideStreams = 4;
+		Stream_handle side_stream[kSideStreams] = {nullptr, nullptr, nullptr, nullptr};
 		// source level only: the pin positions at which the Runner's waves begin (ascending, first = 0; empty = one
 		// wave).  A source that uploads chunk by chunk interleaves the chunks of the pins of one wave.
 		const std::vector<int>* wave_begin = nullptr;

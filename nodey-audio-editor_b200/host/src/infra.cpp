@@ -641,16 +641,18 @@ namespace infra
 		const int kLanes = 1 + compute_lanes;
 		nodey_stream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 		// every compute lane has a side stream: a node that consumes a stream chunk by chunk runs there, next to its producer
-		nodey_stream_t sides[2][kMaxLanes] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}};
+		constexpr int kSides = Exec_context::kSideStreams;
+		nodey_stream_t sides[kSides][kMaxLanes] = {};
 		const auto release_lanes = [&] {
-			for (auto* set : {&lanes, &sides[0], &sides[1]})
-				for (auto& s : *set)
-				{
-					if (!s) continue;
-					Lane_registry::remove(s);
-					nodey_stream_destroy(s);
-					s = nullptr;
-				}
+			const auto drop = [](nodey_stream_t& s) {
+				if (!s) return;
+				Lane_registry::remove(s);
+				nodey_stream_destroy(s);
+				s = nullptr;
+			};
+			for (auto& s : lanes) drop(s);
+			for (auto& side : sides)
+				for (auto& s : side) drop(s);
 		};
 		bool failed = false;
 		if (device >= 0 && nodey_set_device(device) != NODEY_OK) failed = true;
@@ -690,8 +692,7 @@ namespace infra
 				if (failed) return;
 				Exec_context& ctx = Exec_context::current();
 				ctx.stream = lanes[lane];
-				ctx.side_stream[0] = sides[0][lane];
-				ctx.side_stream[1] = sides[1][lane];
+				for (int k = 0; k < kSides; k++) ctx.side_stream[k] = sides[k][lane];
 				ctx.wave_begin = level_index == 0 ? &wave_begin : nullptr;
 				ctx.level = level_index;
 				ctx.lane = lane;

@@ -108,15 +108,22 @@ namespace processor
 			for (auto& stream : infra::get_output_item<Audio_stream>(output, key)) stream->publish(buffer);
 		}
 
-		// the stream a chunk-wise consumer runs on: the one after its producer's in the lane's cycle
-		// stream -> side[0] -> side[1] -> stream (a producer outside the lane, e.g. the transfer lane: the lane's own stream)
-		nodey_stream_t stream_after(const Stream_progress* producer)
+		// the stream after `s` in the lane's cycle  stream -> side[0] -> ... -> side[3] -> stream  (a stream outside the
+		// lane, e.g. the transfer lane's, is followed by the lane's own stream)
+		nodey_stream_t next_in_cycle(nodey_stream_t s)
 		{
 			const Exec_context& ctx = Exec_context::current();
-			if (!producer || !ctx.side_stream[0]) return ctx.stream;
-			if (producer->stream == ctx.stream) return ctx.side_stream[0];
-			if (producer->stream == ctx.side_stream[0] && ctx.side_stream[1]) return ctx.side_stream[1];
+			constexpr int n = Exec_context::kSideStreams;
+			if (s == ctx.stream) return ctx.side_stream[0] ? ctx.side_stream[0] : ctx.stream;
+			for (int k = 0; k < n; k++)
+				if (s == ctx.side_stream[k]) return k + 1 < n && ctx.side_stream[k + 1] ? ctx.side_stream[k + 1] : ctx.stream;
 			return ctx.stream;
+		}
+
+		// the stream a chunk-wise consumer runs on: the one after its producer's (no chunk-wise producer: the lane's own)
+		nodey_stream_t stream_after(const Stream_progress* producer)
+		{
+			return producer ? next_in_cycle(producer->stream) : Exec_context::current().stream;
 		}
 
 		// orders a stream after the progress points of a chunk-wise input, one point at a time
@@ -1051,15 +1058,25 @@ namespace processor
 					// memory is then allocated in that stream's order too (the allocator hands a block freed on a stream
 					// straight back to that stream): nothing here may order the side stream after what the producer has
 					// already enqueued on the main one
-					const nodey_stream_t run = chunked ? stream_after(in_progress.get()) : main_stream;
+					// Two streams when chunked: `search` carries the sequential WSOLA chain, chunk after chunk with nothing in
+					// between (it only ever waits for input), `run` the tails (cross-fade + FIR + cubic of chunk c after search
+					// c) and the node's progress events.  Without side streams both are the lane's stream.
+					const nodey_stream_t search = chunked ? stream_after(in_progress.get()) : main_stream;
+					const nodey_stream_t run = chunked && search != main_stream ? next_in_cycle(search) : search;
+					std::shared_ptr<infra::Device_block> offs_block;
+					if (chunked)
+					{
+						Stream_scope on_search(search);     // the offset trace is first written (cleared) on the search stream
+						offs_block = std::make_shared<infra::Device_block>(Arena::padded(offs_stride * sizeof(int32_t) * cnt));
+					}
 					Stream_scope scope(run);
-					Arena arena(out_stride * sizeof(float) * cnt + (chunked ? Arena::padded(offs_stride * sizeof(int32_t) * cnt) : 0));
+					Arena arena(out_stride * sizeof(float) * cnt);
 					float* out_base = (float*)arena.take(out_stride * sizeof(float) * cnt);
 					std::shared_ptr<Stream_progress> progress;
 					std::shared_ptr<infra::Device_event> done;
 					if (chunked)
 					{
-						int32_t* offs = (int32_t*)arena.take(offs_stride * sizeof(int32_t) * cnt);
+						int32_t* offs = (int32_t*)offs_block->ptr;
 						const bool planes = all[first].in->format == FMT_FLTP && ch == 2;
 						std::vector<const float*> pa(cnt), pb(cnt, nullptr);
 						for (size_t k = 0; k < cnt; k++)
@@ -1070,17 +1087,46 @@ namespace processor
 						progress = std::make_shared<Stream_progress>();
 						progress->stream = run;
 						Progress_waiter input{in_progress.get()};
-						for (int c = 0; c < nchunks; c++)
+						const bool split = search != run;
+						if (split)
 						{
-							input.need(in_need[c], run);
-							abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
-																  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, run), title);
-							auto ev = std::make_shared<infra::Device_event>();
-							ev->record(run);
-							progress->points.push_back({out_ready[c], ev});
+							// the whole chain first (host order = device order on `search`), an event after every chunk
+							std::vector<std::shared_ptr<infra::Device_event>> searched;
+							for (int c = 0; c < nchunks; c++)
+							{
+								input.need(in_need[c], search);
+								abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
+																	  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, 1, search), title);
+								searched.push_back(std::make_shared<infra::Device_event>());
+								searched.back()->record(search);
+							}
+							input.all(search);
+							for (int c = 0; c < nchunks; c++)
+							{
+								searched[(size_t)c]->wait_on(run);       // also orders the tail after the input prefix the search waited for
+								abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
+																	  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, 2, run), title);
+								auto ev = std::make_shared<infra::Device_event>();
+								ev->record(run);
+								progress->points.push_back({out_ready[c], ev});
+							}
 						}
-						input.all(run);       // whatever the chunk plan needed, the product is complete only after the whole input is
+						else
+						{
+							for (int c = 0; c < nchunks; c++)
+							{
+								input.need(in_need[c], run);
+								abi(nodey_soundtouch_run_tracks_chunk(st, out_base, (int64_t)out_stride, pa.data(), planes ? pb.data() : nullptr, (int)cnt, n,
+																	  kSoundtouchFrame, m, offs, (int64_t)offs_stride, c, nchunks, 0, run), title);
+								auto ev = std::make_shared<infra::Device_event>();
+								ev->record(run);
+								progress->points.push_back({out_ready[c], ev});
+							}
+							input.all(run);       // whatever the chunk plan needed, the product is complete only after the whole input is
+						}
 						done = progress->points.back().event;
+						// (the offset trace goes out of scope below: Device_block frees are ordered after everything enqueued on
+						// every stream of the lane, Lane_registry::free_ordered)
 					}
 					else if (in_place)
 					{

@@ -221,7 +221,7 @@ def test_soundtouch_chunk_progress_is_final(nd, orc):
     import ctypes as C
     for c in range(len(plan)):
         nd.check(nd.lib().nodey_soundtouch_run_chunk(st.h, nd._dp(out), out.stride(0), nd._dp(x), x.stride(0), 2, n, 1152, m,
-                                                     nd._dp(offs), offs.stride(0), c, len(plan), nd._stream()))
+                                                     nd._dp(offs), offs.stride(0), c, len(plan), 0, nd._stream()))
         torch.cuda.synchronize()
         r = plan[c][1]
         assert torch.equal(out[:, :r], whole[:, :r]), f"chunk {c}: frames below out_ready are not final"
@@ -242,7 +242,7 @@ def test_soundtouch_chunks_of_uncuttable_paths(nd, orc):
     out = torch.empty((1, m, 2), device="cuda")
     offs = torch.zeros((1, max(nseq - 1, 1)), dtype=torch.int32, device="cuda")
     rc = nd.lib().nodey_soundtouch_run_chunk(st3.h, nd._dp(out), out.stride(0), nd._dp(x), x.stride(0), 1, 48000, 1152, m,
-                                             nd._dp(offs), offs.stride(0), 0, 4, nd._stream())
+                                             nd._dp(offs), offs.stride(0), 0, 4, 0, nd._stream())
     assert rc == -5      # NODEY_E_RANGE
 
 

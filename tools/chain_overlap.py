@@ -22,7 +22,7 @@ sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
 
 def chunk(st, out, xin, nin, m, offs, c, nc, stream):
     nd.check(L.nodey_soundtouch_run_chunk(st.h, nd._dp(out), out.stride(0), nd._dp(xin), xin.stride(0), T, nin, 1152, m,
-                                          nd._dp(offs), offs.stride(0), c, nc, C.c_void_p(stream.cuda_stream)))
+                                          nd._dp(offs), offs.stride(0), c, nc, 0, C.c_void_p(stream.cuda_stream)))
 
 def serial():
     for c in range(len(p1)): chunk(st1, y1, x, n, m1, o1, c, len(p1), sA)
