@@ -541,7 +541,14 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
                 const int base = lane * a.D + s_gs[q];
                 const int pstep = kNB * a.D;                       // input frames between a thread's periods
                 if (CH == 2) {
+                    // both channels of a frame meet the same tap: ONE packed fused multiply-add (fma.rn.f32x2, per component
+                    // the fmaf the oracle's FIR is defined with) with the tap as a scalar operand -- half the issue slots
                     const float2* x2 = reinterpret_cast<const float2*>(s_in) + base;
+                    float2 a2[PT][kG];
+#pragma unroll
+                    for (int p = 0; p < PT; p++)
+#pragma unroll
+                        for (int g = 0; g < kG; g++) a2[p][g] = make_float2(0.f, 0.f);
 #pragma unroll 3
                     for (int m = 0; m < a.wmax; m++) {
                         const float4 h0 = *reinterpret_cast<const float4*>(hq + m * kG);
@@ -549,16 +556,20 @@ __global__ void __launch_bounds__(640, (MIX || PT > 1) ? 1 : 2) resample_tile2_k
 #pragma unroll
                         for (int p = 0; p < PT; p++) {
                             const float2 x = x2[m + p * pstep];
-                            acc[p][0][0] = __fmaf_rn(x.x, h0.x, acc[p][0][0]); acc[p][0][CH - 1] = __fmaf_rn(x.y, h0.x, acc[p][0][CH - 1]);
-                            acc[p][1][0] = __fmaf_rn(x.x, h0.y, acc[p][1][0]); acc[p][1][CH - 1] = __fmaf_rn(x.y, h0.y, acc[p][1][CH - 1]);
-                            acc[p][2][0] = __fmaf_rn(x.x, h0.z, acc[p][2][0]); acc[p][2][CH - 1] = __fmaf_rn(x.y, h0.z, acc[p][2][CH - 1]);
-                            acc[p][3][0] = __fmaf_rn(x.x, h0.w, acc[p][3][0]); acc[p][3][CH - 1] = __fmaf_rn(x.y, h0.w, acc[p][3][CH - 1]);
-                            acc[p][4][0] = __fmaf_rn(x.x, h1.x, acc[p][4][0]); acc[p][4][CH - 1] = __fmaf_rn(x.y, h1.x, acc[p][4][CH - 1]);
-                            acc[p][5][0] = __fmaf_rn(x.x, h1.y, acc[p][5][0]); acc[p][5][CH - 1] = __fmaf_rn(x.y, h1.y, acc[p][5][CH - 1]);
-                            acc[p][6][0] = __fmaf_rn(x.x, h1.z, acc[p][6][0]); acc[p][6][CH - 1] = __fmaf_rn(x.y, h1.z, acc[p][6][CH - 1]);
-                            acc[p][7][0] = __fmaf_rn(x.x, h1.w, acc[p][7][0]); acc[p][7][CH - 1] = __fmaf_rn(x.y, h1.w, acc[p][7][CH - 1]);
+                            a2[p][0] = __ffma2_rn(x, make_float2(h0.x, h0.x), a2[p][0]);
+                            a2[p][1] = __ffma2_rn(x, make_float2(h0.y, h0.y), a2[p][1]);
+                            a2[p][2] = __ffma2_rn(x, make_float2(h0.z, h0.z), a2[p][2]);
+                            a2[p][3] = __ffma2_rn(x, make_float2(h0.w, h0.w), a2[p][3]);
+                            a2[p][4] = __ffma2_rn(x, make_float2(h1.x, h1.x), a2[p][4]);
+                            a2[p][5] = __ffma2_rn(x, make_float2(h1.y, h1.y), a2[p][5]);
+                            a2[p][6] = __ffma2_rn(x, make_float2(h1.z, h1.z), a2[p][6]);
+                            a2[p][7] = __ffma2_rn(x, make_float2(h1.w, h1.w), a2[p][7]);
                         }
                     }
+#pragma unroll
+                    for (int p = 0; p < PT; p++)
+#pragma unroll
+                        for (int g = 0; g < kG; g++) { acc[p][g][0] = a2[p][g].x; acc[p][g][CH - 1] = a2[p][g].y; }
                 } else {
                     const float* x1 = s_in + base;
 #pragma unroll 3

@@ -690,6 +690,19 @@ __global__ void __launch_bounds__(256) cubic_kernel(const __grid_constant__ Cubi
 // falls into the tile.  Same rounding sequence as the three separate kernels; their two intermediate
 // streams (2 x 8 B per frame, written and read) never touch HBM.
 // ---------------------------------------------------------------------------------------------
+// Packed multiply and add, each rounded separately, both channels of a frame in one instruction.  ptxas (12.9) contracts a
+// mul.rn.f32x2 feeding an add.rn.f32x2 into ONE fma.rn.f32x2 -- explicit .rn and --fmad false notwithstanding, and also
+// when the two are spelled fma(x, y, -0) and fma(a, 1, b) with literal constants (measured: the fused tail came out 1 ulp
+// off in half of its samples; SASS showed one FFMA2 per tap).  The scalar forms are protected against that.  So the two
+// neutral operands are RUN-TIME values (kernel parameters -0.0f and 1.0f): the assembler cannot know them, cannot simplify
+// the two fused multiply-adds and cannot merge them, and the bits are those of the separate operations:
+//   x * y = fma(x, y, -0)   one rounding of the exact product; adding -0 keeps the sign of a zero product
+//   a + b = fma(a, 1, b)    a * 1 is exact
+// tools/micro/f32x2_check.cu compares both with the scalar operations on the GPU (signed zeros, denormals, infinities).
+struct Neutral { float neg_zero, one; };
+__device__ __forceinline__ float2 mul2_rn(float2 x, float2 y, const Neutral& u) { return __ffma2_rn(x, y, make_float2(u.neg_zero, u.neg_zero)); }
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b, const Neutral& u) { return __ffma2_rn(a, make_float2(u.one, u.one), b); }
+
 struct PostArgs {
     View in; TrackTab tt;
     const long long* pos; const int* offs; long long offs_stride;
@@ -700,6 +713,7 @@ struct PostArgs {
     unsigned long long R; int e;
     float* out; long long out_stride; long long count;     // final frames to write
     long long tile_begin, tile_end;                         // this launch covers tiles [tile_begin, tile_end)
+    Neutral u;                                              // -0.0f and 1.0f as run-time values (see mul2_rn / add2_rn)
 };
 
 constexpr int kPostStride = kFirTileS - 8;        // FIR outputs a tile contributes to the cubic stage
@@ -797,7 +811,7 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                             const long long mid = j == 0 ? mid_j[0] : (j == 1 ? mid_j[1] : mid_j[2]);
                             const float2 m = planar ? make_float2(__ldg(pl + mid + k), __ldg(pr + mid + k)) : __ldg(b2 + mid + k);
                             const float f1 = a.fade[k], f2 = a.fade[ovl + k];
-                            x = __fadd2_rn(__fmul2_rn(x, make_float2(f1, f1)), __fmul2_rn(m, make_float2(f2, f2)));
+                            x = add2_rn(mul2_rn(x, make_float2(f1, f1), a.u), mul2_rn(m, make_float2(f2, f2), a.u), a.u);
                         }
                         f[u] = x;
                     }
@@ -849,14 +863,14 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                     const float4 ce = w[(step + r / 2) % 5], co = w[(step + (r + 1) / 2) % 5];
                     const float2 xe = (r & 1) ? make_float2(ce.z, ce.w) : make_float2(ce.x, ce.y);
                     const float2 xo = ((r + 1) & 1) ? make_float2(co.z, co.w) : make_float2(co.x, co.y);
-                    e[r] = __fadd2_rn(e[r], __fmul2_rn(xe, hh0));
-                    o[r] = __fadd2_rn(o[r], __fmul2_rn(xo, hh1));
+                    e[r] = add2_rn(e[r], mul2_rn(xe, hh0, a.u), a.u);
+                    o[r] = add2_rn(o[r], mul2_rn(xo, hh1, a.u), a.u);
                 }
                 if (step + 1 < kAaLen / 2) w[step % 5] = tile[fir_chunk(c0 + step + 5)];
             }
             // park the filtered frames (frame q of the tile lives at q + q/8)
 #pragma unroll
-            for (int r = 0; r < kFirS; r++) filt[threadIdx.x * (kFirS + 1) + r] = __fadd2_rn(o[r], e[r]);
+            for (int r = 0; r < kFirS; r++) filt[threadIdx.x * (kFirS + 1) + r] = add2_rn(o[r], e[r], a.u);
         }
         __syncthreads();
         // cubic transposer over the tile (InterpolateCubic::transposeStereo).  The read position of output i is i * R in
@@ -893,8 +907,8 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             const int q = (int)(P - n0);
             const auto at = [&](int f) { return filt[f + (f >> 3)]; };
             const float2 p0 = at(q), p1 = at(q + 1), p2 = at(q + 2), p3 = at(q + 3);
-            const float2 o = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(p0, make_float2(y0, y0)), __fmul2_rn(p1, make_float2(y1, y1))),
-                                                   __fmul2_rn(p2, make_float2(y2, y2))), __fmul2_rn(p3, make_float2(y3, y3)));
+            const float2 o = add2_rn(add2_rn(add2_rn(mul2_rn(p0, make_float2(y0, y0), a.u), mul2_rn(p1, make_float2(y1, y1), a.u), a.u),
+                                             mul2_rn(p2, make_float2(y2, y2), a.u), a.u), mul2_rn(p3, make_float2(y3, y3), a.u), a.u);
             reinterpret_cast<float2*>(out)[i] = o;
         }
     }
@@ -1444,6 +1458,7 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             memcpy(pa.h, s->aa, sizeof(pa.h));
             pa.R = s->R; pa.e = s->e; pa.out = out; pa.out_stride = out_stride; pa.count = out_frames;
             pa.tile_begin = cp.tile_begin; pa.tile_end = cp.tile_end;
+            pa.u.neg_zero = -0.0f; pa.u.one = 1.0f;
             const long long tiles = cp.tile_end - cp.tile_begin;
             const long long cap = (long long)sm_count() * 4;
             dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)ntracks);
