@@ -59,6 +59,7 @@ int nodey_get_device(int* ordinal);
 int nodey_device_count(int* count);
 int nodey_device_synchronize(void);
 int nodey_stream_create(nodey_stream_t* out);
+int nodey_stream_create_priority(nodey_stream_t* out, int high_priority);   /* high: scheduled first when SM slots free up */
 int nodey_stream_destroy(nodey_stream_t s);
 int nodey_stream_synchronize(nodey_stream_t s);
 int nodey_event_create(nodey_event_t* out, int timing);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
     "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_reference_schedule", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
-    "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_destroy",
+    "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_create_priority", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
     "nodey_event_synchronize", "nodey_event_elapsed_ms", "nodey_stream_wait_event", "nodey_malloc", "nodey_free", "nodey_trim_memory", "nodey_memory_stats", "nodey_memory_reserved", "nodey_set_memory_policy",
     "nodey_bus_nccl_version", "nodey_bus_unique_id", "nodey_bus_create", "nodey_bus_destroy", "nodey_bus_info",

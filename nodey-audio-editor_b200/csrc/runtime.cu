@@ -184,6 +184,19 @@ int nodey_stream_create(nodey_stream_t* out)
     return NODEY_OK;
 }
 
+/* high_priority != 0: the stream's kernels are picked first when SM slots free up (cudaStreamCreateWithPriority) -- for
+ * latency-critical chains that share the device with bulk kernels */
+int nodey_stream_create_priority(nodey_stream_t* out, int high_priority)
+{
+    NODEY_REQUIRE(out, NODEY_E_INVALID, "nodey_stream_create_priority: null argument");
+    int lo = 0, hi = 0;
+    NODEY_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // numerically lower = higher priority
+    cudaStream_t s;
+    NODEY_CUDA_OK(cudaStreamCreateWithPriority(&s, cudaStreamDefault, high_priority ? hi : lo));
+    *out = (nodey_stream_t)s;
+    return NODEY_OK;
+}
+
 int nodey_stream_destroy(nodey_stream_t s)
 {
     if (s) NODEY_CUDA_OK(cudaStreamDestroy(as_stream(s)));

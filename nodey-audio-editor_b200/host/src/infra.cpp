@@ -661,11 +661,18 @@ namespace infra
 			if (nodey_stream_create(&lanes[k]) != NODEY_OK) { lanes[k] = nullptr; failed = true; break; }
 			Lane_registry::add(lanes[k], k >= 1);
 			if (k >= 1 && getenv("NODEY_NO_SIDE_STREAMS") == nullptr)
-				for (auto& side : sides)
+			{
+				// sides 0 and 2 carry the sequential WSOLA searches of a resampler -> pitch -> tempo chain (nodes.cpp: the
+				// search runs on the stream after the producer's, the tails on the next one): high priority, so that a
+				// chain's next launch gets its SM slots ahead of the thousands of tail CTAs it competes with
+				static const bool prio = getenv("NODEY_NO_STREAM_PRIORITY") == nullptr || !*getenv("NODEY_NO_STREAM_PRIORITY");
+				for (int j = 0; j < kSides; j++)
 				{
-					if (nodey_stream_create(&side[k]) != NODEY_OK) { side[k] = nullptr; failed = true; break; }
-					Lane_registry::add(side[k], true);
+					const int rc = prio ? nodey_stream_create_priority(&sides[j][k], j % 2 == 0) : nodey_stream_create(&sides[j][k]);
+					if (rc != NODEY_OK) { sides[j][k] = nullptr; failed = true; break; }
+					Lane_registry::add(sides[j][k], true);
 				}
+			}
 		}
 		if (failed)
 		{
