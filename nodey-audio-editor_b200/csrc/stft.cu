@@ -115,6 +115,7 @@ struct StftArgs {
     const float2* tw;       // W_4096^i, i < 4096
     const float* win;       // periodic Hann, float
     int vec_ok;             // float2 loads allowed (x_stride == 1, 8-byte aligned, even hop)
+    int inter2;             // interleaved stereo, 16-byte aligned, even hop: one float4 load = two frames of both channels
 };
 
 __device__ __forceinline__ void st_bin(float2* p, float2 v)
@@ -131,8 +132,11 @@ __device__ __forceinline__ void untangle_pair(float2 zk, float2 zmc, float2 w, f
     xm = make_float2(0.5f * (e.x - t.y), -0.5f * (e.y + t.x));
 }
 
-// VEC: channel samples are contiguous and 8-byte aligned (planar input): one 64-bit load per complex point
-template <bool VEC>
+// VEC 1: channel samples are contiguous and 8-byte aligned (planar input): one 64-bit load per complex point
+// VEC 2: interleaved stereo: one 128-bit load holds the complex point of BOTH channels; a CTA transforms the two channels
+//        of a frame back to back, so the second channel's loads hit the lines the first one brought into L1
+//        (the scalar path issues two strided 32-bit loads per point: twice the instructions and wavefronts)
+template <int VEC>
 __global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_constant__ StftArgs a)
 {
     extern __shared__ __align__(16) float2 stft_smem[];      // 51 KB: above the static limit
@@ -150,7 +154,17 @@ __global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_cons
     for (int i = j; i < 7 * 256; i += kThreads) { const int r = i / 256 + 1, jb = i % 256; tw3[r - 1][jb] = a.tw[jb * r * 2]; }
     // (the first barrier of the item loop orders these stores before their first use in pass 2)
 
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    // item -> (frame, channel): channel fastest within a CTA's own sequence of items when VEC == 2 (see above), otherwise
+    // across CTAs (consecutive CTAs take the channels of one frame)
+    for (long long it = blockIdx.x; it < items; it += (VEC == 2 ? 1 : gridDim.x)) {
+        long long item = it;
+        if (VEC == 2) {
+            // CTA b owns frames b, b + grid, ...; `it` walks 2 * (its frames)
+            const long long local = it - blockIdx.x;                 // 0, 1, 2, ... within this CTA
+            const long long frame_v = blockIdx.x + (local >> 1) * (long long)gridDim.x;
+            if (frame_v >= a.frames) break;
+            item = frame_v * 2 + (local & 1);
+        }
         const long long frame = item / a.nch;
         const int c = (int)(item - frame * a.nch);
         const float* p = a.x + (long long)c * a.ch_stride + frame * (long long)a.hop * a.x_stride;
@@ -161,7 +175,11 @@ __global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_cons
         for (int r = 0; r < 16; r++) {
             const int n = 2 * (j + 128 * r);
             float2 s;
-            if (VEC) s = __ldg(reinterpret_cast<const float2*>(p + n));
+            if (VEC == 1) s = __ldg(reinterpret_cast<const float2*>(p + n));
+            else if (VEC == 2) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (frame * (long long)a.hop + n) * 2));
+                s = c ? make_float2(q.y, q.w) : make_float2(q.x, q.z);
+            }
             else { s.x = __ldg(p + n * a.x_stride); s.y = __ldg(p + (n + 1) * a.x_stride); }
             const float2 w = __ldg(reinterpret_cast<const float2*>(a.win + n));
             v[r] = make_float2(__fmul_rn(s.x, w.x), __fmul_rn(s.y, w.y));
@@ -302,11 +320,12 @@ int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int
     a.ch_stride = interleaved ? 1 : plane_stride;
     a.tw = t.tw; a.win = t.win;
     a.vec_ok = (a.x_stride == 1) && (((uintptr_t)x & 7) == 0) && (hop % 2 == 0) && (a.ch_stride % 2 == 0);
+    a.inter2 = interleaved && nch == 2 && (((uintptr_t)x & 15) == 0) && (hop % 2 == 0);
     const int64_t items = frames * nch;
     const int64_t cap = (int64_t)sm_count() * 4;
     const int grid = (int)(items < cap ? items : cap);
     constexpr size_t smem = sizeof(float2) * (2 * kBufLen + 15 * 16 + 7 * 256);
-    void (*kern)(StftArgs) = a.vec_ok ? stft4096_kernel<true> : stft4096_kernel<false>;
+    void (*kern)(StftArgs) = a.inter2 ? stft4096_kernel<2> : (a.vec_ok ? stft4096_kernel<1> : stft4096_kernel<0>);
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     NODEY_LAUNCH("stft4096_kernel", as_stream(stream), kern<<<grid, kThreads, smem, as_stream(stream)>>>(a));

@@ -3,7 +3,7 @@
 # printed under a profiler is never a bench value), then the launch list and one --set full capture per main kernel.
 # usage (from the repo root, on the GPU box): bash tools/profile_round.sh <tag>
 set -u
-tag=${1:-r1}
+tag=${1:-r2}
 out=gpurun_out
 mkdir -p $out
 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err || exit 1
