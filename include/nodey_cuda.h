@@ -274,6 +274,9 @@ int64_t nodey_soundtouch_out_frames(nodey_soundtouch* s, int64_t in_frames, int 
 /* Test hook: cluster size of the WSOLA offsets kernel (thread-block cluster of 1, 2 or 4 CTAs per track;
  * 0 = automatic: the largest that keeps tracks * cluster * 2 <= SM count). */
 int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster);
+/* Test hook: candidates per thread of the WSOLA offsets kernel (4, 8 or 11..16; 0 = automatic: the smallest count that
+ * fits one (SSE lane, candidate class) stream into one warp when a track runs on one CTA, 8 resp. 4 with clusters). */
+int nodey_soundtouch_set_candidates_per_thread(nodey_soundtouch* s, int kt);
 /* Test hook: 1 = run cross-fade, AA FIR and cubic transposer as separate kernels even where the fused
  * tail kernel applies (stereo, TDStretch-first order). */
 int nodey_soundtouch_set_unfused(nodey_soundtouch* s, int unfused);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "nodey_resampler_info", "nodey_resampler_filter_bank", "nodey_resampler_out_count", "nodey_resampler_run",
     "nodey_resampler_run_mode", "nodey_resample_mix", "nodey_resample_tracks", "nodey_resample_tracks_chunks", "nodey_resample_tracks_chunk", "nodey_resampler_segment", "nodey_preview_pack", "nodey_gain_tracks", "nodey_resampler_producible", "nodey_resampler_flush_reflect", "nodey_stft_frames", "nodey_stft",
     "nodey_soundtouch_create", "nodey_soundtouch_destroy", "nodey_soundtouch_info", "nodey_soundtouch_out_frames",
-    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_reference_schedule", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
+    "nodey_soundtouch_run", "nodey_soundtouch_run_tracks", "nodey_soundtouch_reference_schedule", "nodey_soundtouch_chunks", "nodey_soundtouch_run_chunk", "nodey_soundtouch_run_tracks_chunk", "nodey_soundtouch_set_cluster", "nodey_soundtouch_set_candidates_per_thread", "nodey_soundtouch_set_unfused", "nodey_amix_plan", "nodey_profile_enable", "nodey_profile_launches",
     "nodey_profile_report",
     "nodey_set_device", "nodey_get_device", "nodey_device_count", "nodey_device_synchronize", "nodey_stream_create", "nodey_stream_create_priority", "nodey_stream_destroy",
     "nodey_stream_synchronize", "nodey_event_create", "nodey_event_destroy", "nodey_event_record",
@@ -96,6 +96,7 @@ def lib():
     L.nodey_soundtouch_out_frames.argtypes = [vp, i64, i32, C.POINTER(i64)]
     L.nodey_soundtouch_out_frames.restype = i64
     L.nodey_soundtouch_set_cluster.argtypes = [vp, i32]
+    L.nodey_soundtouch_set_candidates_per_thread.argtypes = [vp, i32]
     L.nodey_soundtouch_set_unfused.argtypes = [vp, i32]
     L.nodey_soundtouch_run.argtypes = [vp, vp, i64, vp, i64, i32, i64, i32, i64, vp, i64, vp]
     L.nodey_soundtouch_run_tracks.argtypes = [vp, vp, i64, vp, vp, i32, i64, i32, i64, vp, i64, vp]
@@ -494,6 +495,9 @@ class SoundTouch:
 
     def set_cluster(self, cluster):
         check(lib().nodey_soundtouch_set_cluster(self.h, cluster))
+
+    def set_candidates_per_thread(self, kt):
+        check(lib().nodey_soundtouch_set_candidates_per_thread(self.h, kt))
 
     def set_unfused(self, unfused):
         check(lib().nodey_soundtouch_set_unfused(self.h, 1 if unfused else 0))

@@ -111,6 +111,7 @@ struct TdsArgs {
     int nseq;
     int overlap, seek_window, seek_length;
     int Q;                     // lane steps = 4 * (CH*overlap/16)
+    int qp;                    // words per lane row of the staged mid buffer (groups of KT steps, each padded to a multiple of 4)
     int tb_per;                // candidate blocks per CTA of the cluster
     int sk;                    // floats per sub-plane
     int ncand_pad;             // padded candidates per CTA (correlation lane sums)
@@ -122,8 +123,10 @@ struct TdsArgs {
 
 // partial-sum slot of candidate cc: one word of padding per K*KT candidates makes both the strided
 // stores of the lane-sum phase (stride K*KT) and the unit-stride loads of the combine phase conflict free
+// (two words when S is odd, so that the stride S + pad stays odd)
 template <int S>
-__device__ __forceinline__ int ps_slot(int cc) { return cc + cc / S; }
+__device__ __forceinline__ int ps_slot(int cc) { return cc + (cc / S) * ((S & 1) ? 2 : 1); }
+
 
 #ifdef NODEY_TDS_TIMING
 // development build only (tools/micro/Makefile): clock64 deltas of the phases of one sequence, thread 0 of CTA 0
@@ -133,34 +136,36 @@ __device__ unsigned long long g_tds_phase[8];
 #define TDS_T(k) do { } while (0)
 #endif
 
-// One group of NS lane steps for KT consecutive candidates of one (lane, class) stream.
+// One group of NS lane steps for KT consecutive stream positions of one (lane, class) stream.
 // Window = two blocks of KT samples (w[CUR] current, w[CUR^1] next); sample idx = s + k of the
-// window feeds candidate k at step s.  Block b of a thread's stream lives at
-// plane[((OFF + k) % KT) * sk + (OFF + k) / KT + b]: consecutive threads -> consecutive words.
+// window feeds position k at step s.  Block b of a thread's stream lives at
+// plane[k * sk + b]: consecutive threads -> consecutive words.
 // MODE 0: correlation lane sums only (acc[k] += x * y); MODE 1: norm sums only (acc[k] += x * x).
 // The norm of a candidate does not involve the mid buffer, and candidates of different (lane, class)
 // pairs walk the same squared samples: it is computed once per sample stream (plane) and start
 // position instead of once per (lane, class) -- see tds_offsets_kernel.
-template <int KT, int OFF, int CUR, int NS, int MODE>
+// PARTIAL: only the first `nsteps` (< KT) steps run -- the last group of a row when KT does not divide Q.
+template <int KT, int CUR, int MODE, bool PARTIAL>
 __device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&acc)[KT], const float* __restrict__ xnext, int sk,
-                                          const float* __restrict__ yq)
+                                          const float* __restrict__ yq, int nsteps = KT)
 {
     constexpr int NXT = CUR ^ 1;
 #pragma unroll
     for (int k = 0; k < KT; k++) {
-        const float v = xnext[((OFF + k) % KT) * sk + (OFF + k) / KT];
+        const float v = xnext[k * sk];
         w[NXT][k] = MODE == 0 ? v : __fmul_rn(v, v);
     }
-    float y[NS];
+    float y[(KT + 3) & ~3];
     if (MODE == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; s += 4) {
+        for (int s = 0; s < KT; s += 4) {
             const float4 t = *reinterpret_cast<const float4*>(yq + s);
             y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
         }
     }
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
+    for (int s = 0; s < KT; s++) {
+        if (PARTIAL && s >= nsteps) break;
 #pragma unroll
         for (int k = 0; k < KT; k++) {
             const int idx = s + k;
@@ -170,30 +175,50 @@ __device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&acc)[KT], c
     }
 }
 
-template <int KT, int OFF, int MODE>
-__device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int sk, const float* __restrict__ yp, int Q,
+// rows of the mid buffer are stored in groups of KT steps padded to a multiple of four words, so that every group
+// starts 16-byte aligned whatever KT is
+template <int KT> __host__ __device__ constexpr int tds_ktp() { return (KT + 3) & ~3; }
+
+// ROT = false: the loop body holds two groups (the window blocks swap roles, no moves); ROT = true: one group per
+// iteration and KT register moves -- half the code.  A body of two groups of KT = 15 is 15 KB of instructions per variant,
+// and the variants live in the SM's 32 KB instruction cache together: measured, the large-KT kernels lost more to
+// instruction fetch than they saved in issued instructions until their bodies were halved.
+template <int KT, int MODE, int SK, bool ROT>
+__device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int sk_rt, const float* __restrict__ yp, int Q,
                                               float (&acc)[KT])
 {
+    const int sk = SK ? SK : sk_rt;                 // compile-time sub-plane stride: every window load is base + immediate
+    constexpr int KTP = tds_ktp<KT>();
     float w[2][KT];
 #pragma unroll
     for (int k = 0; k < KT; k++) acc[k] = 0.f;
 #pragma unroll
     for (int k = 0; k < KT; k++) {
-        const float v = xb[((OFF + k) % KT) * sk + (OFF + k) / KT];
+        const float v = xb[k * sk];
         w[0][k] = MODE == 0 ? v : __fmul_rn(v, v);
     }
-    const int NG = Q / KT, tail = Q - NG * KT;      // tail is 0 or 4 (Q is a multiple of 4)
+    const int NG = Q / KT, tail = Q - NG * KT;
     int G = 0;
-    for (; G + 2 <= NG; G += 2) {
-        tds_group<KT, OFF, 0, KT, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
-        tds_group<KT, OFF, 1, KT, MODE>(w, acc, xb + G + 2, sk, yp + (G + 1) * KT);
-    }
-    if (G < NG) {
-        tds_group<KT, OFF, 0, KT, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
-        G++;
-        if (tail) tds_group<KT, OFF, 1, 4, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
-    } else if (tail) {
-        tds_group<KT, OFF, 0, 4, MODE>(w, acc, xb + G + 1, sk, yp + G * KT);
+    if constexpr (ROT) {
+#pragma unroll 1
+        for (; G < NG; G++) {
+            tds_group<KT, 0, MODE, false>(w, acc, xb + G + 1, sk, yp + G * KTP);
+#pragma unroll
+            for (int k = 0; k < KT; k++) w[0][k] = w[1][k];
+        }
+        if (tail) tds_group<KT, 0, MODE, true>(w, acc, xb + G + 1, sk, yp + G * KTP, tail);
+    } else {
+        for (; G + 2 <= NG; G += 2) {
+            tds_group<KT, 0, MODE, false>(w, acc, xb + G + 1, sk, yp + G * KTP);
+            tds_group<KT, 1, MODE, false>(w, acc, xb + G + 2, sk, yp + (G + 1) * KTP);
+        }
+        if (G < NG) {
+            tds_group<KT, 0, MODE, false>(w, acc, xb + G + 1, sk, yp + G * KTP);
+            G++;
+            if (tail) tds_group<KT, 1, MODE, true>(w, acc, xb + G + 1, sk, yp + G * KTP, tail);
+        } else if (tail) {
+            tds_group<KT, 0, MODE, true>(w, acc, xb + G + 1, sk, yp + G * KTP, tail);
+        }
     }
 }
 
@@ -234,7 +259,8 @@ __device__ __forceinline__ unsigned long long argmax_key(double v)
 //   * the norm sums of sequence i+1 (no mid buffer involved) are computed between the arrive and the wait
 //     of the cluster barrier that publishes offset i;
 //   * the position weights 1 - 0.25 t^2 are tabulated once.
-template <int CH, int KT>
+// SK > 0: the sub-plane stride is a compile-time constant (a.sk == SK), 0: run-time a.sk
+template <int CH, int KT, int SK>
 __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
 {
     namespace cg = cooperative_groups;
@@ -244,8 +270,10 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     extern __shared__ __align__(16) float smem[];
     constexpr int K = 4 / CH;                       // candidate classes per lane
     const int L = a.seek_length, ovl = a.overlap, Q = a.Q;
-    const int QP = Q + 8;                           // padded lane row: the de-interleaving stores hit 32 banks
-    const int plane_len = KT * a.sk;
+    constexpr int KTP = tds_ktp<KT>();
+    const int QP = a.qp;                            // padded lane row ((Q + KT - 1) / KT groups of KTP words + 8): the de-interleaving stores hit 32 banks
+    const int sk = SK ? SK : a.sk;
+    const int plane_len = KT * sk;
     const int mreg = L + ovl;                       // frames the next mid buffer can come from
     float* X0 = smem;                               // 2 x [4 planes][KT sub-planes][sk] (double buffered)
     float* Y = X0 + 8 * plane_len;                  // [4][QP]
@@ -269,7 +297,8 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     const int tblocks = (tcount + KT - 1) / KT;
     const int tb_lo = (int)crank * a.tb_per;
     int ntb = tblocks - tb_lo; if (ntb > a.tb_per) ntb = a.tb_per; if (ntb < 0) ntb = 0;
-    const int wpc = (ntb + 31) / 32;                 // warps per (lane, class) combo
+    constexpr bool ROT = KT > 8;                     // large bodies: one group per loop iteration (instruction cache)
+    const int wpc = (ntb + 1 + 31) / 32;             // warps per (lane, class) combo (streams that start one element late need one more block)
     const int nunits = 4 * K * wpc;
     const int wpn = (ntb + 1 + 31) / 32;             // warps per plane for the norm sums (ntb + 1 position blocks)
     const int nnorm = 4 * wpn;
@@ -289,13 +318,13 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             const long long go = ok ? g : 0;
             if (CH == 2) {
                 const int m = fr >> 1, pl = (fr & 1) * 2;
-                float* d = Xb + pl * plane_len + (m % KT) * a.sk + m / KT;
+                float* d = Xb + pl * plane_len + (m % KT) * sk + m / KT;
                 cp_async4(d, base.b ? base.a + go : base.a + 2 * go, ok);
                 cp_async4(d + plane_len, base.b ? base.b + go : base.a + 2 * go + 1, ok);
             } else {
                 const float* src = base.a + go;
                 const int m = fr >> 2;
-                cp_async4(Xb + (fr & 3) * plane_len + (m % KT) * a.sk + m / KT, src, ok);
+                cp_async4(Xb + (fr & 3) * plane_len + (m % KT) * sk + m / KT, src, ok);
             }
         }
     };
@@ -334,7 +363,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             const int rho = v / wpn, mb = (v - rho * wpn) * 32 + lane;
             if (mb <= ntb) {
                 float nr[KT];
-                tds_lane_sums<KT, 0, 1>(X + rho * plane_len + mb, a.sk, nullptr, Q, nr);
+                tds_lane_sums<KT, 1, SK, ROT>(X + rho * plane_len + mb, sk, nullptr, Q, nr);
 #pragma unroll
                 for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
             }
@@ -371,7 +400,10 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         const long long p0 = a.pos[i];
         const float* X = X0 + cur * 4 * plane_len;
         // ---- mid buffer: gathered from the staged region, de-interleaved by lane ----
-        for (int j = tid; j < 4 * Q; j += blockDim.x) Y[(j & 3) * QP + (j >> 2)] = MR[moff * CH + j];
+        for (int j = tid; j < 4 * Q; j += blockDim.x) {
+            const int q = j >> 2;
+            Y[(j & 3) * QP + (KTP == KT ? q : (q / KT) * KTP + q % KT)] = MR[moff * CH + j];
+        }
         if (i + 1 < a.seq_end) window_copy(i + 1, X0 + (cur ^ 1) * 4 * plane_len);
         if (i + 2 < a.seq_end) l2_prefetch(i + 2);
         TDS_T(0);
@@ -384,17 +416,20 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
             const int combo = unit / wpc, wsub = unit - combo * wpc;
             const int l = combo & 3, kappa = combo >> 2;
             const int tb = wsub * 32 + lane;
-            if (tb < ntb) {
-                const int u0 = CH * kappa + l;
+            // stream of (l, kappa): plane (CH*kappa + l) & 3, starting `off` = 0 or 1 elements behind the candidate's index.
+            // Slot k of thread tb walks the elements KT*tb + k + s; it belongs to candidate KT*tb + k - off of the class,
+            // so that both kinds of stream run the same code with the same immediate offsets.
+            const int u0 = CH * kappa + l, off = u0 >> 2;
+            if (tb < ntb + off) {
                 const float* xb = X + (u0 & 3) * plane_len + tb;
                 const float* yp = Y + l * QP;
                 float acc[KT];
-                if (u0 >> 2) tds_lane_sums<KT, 1, 0>(xb, a.sk, yp, Q, acc);
-                else tds_lane_sums<KT, 0, 0>(xb, a.sk, yp, Q, acc);
+                tds_lane_sums<KT, 0, SK, ROT>(xb, sk, yp, Q, acc);
 #pragma unroll
                 for (int k = 0; k < KT; k++) {
-                    const int cc = kappa + K * (KT * tb + k);
-                    if (cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
+                    const int tl = KT * tb + k - off;
+                    const int cc = kappa + K * tl;
+                    if (tl >= 0 && cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
                 }
             }
         }
@@ -473,6 +508,31 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
         for (int k = 0; k < 8; k++) g_tds_phase[k] = (unsigned long long)tacc[k];
 #endif
 }
+
+typedef void (*TdsKernel)(TdsArgs);
+// KT = 11..16 exist for stereo with the compile-time stride only (mono streams fit one warp at KT = 8; anything that does
+// not fit the fixed stride runs with KT = 8 and the run-time stride)
+template <int CH>
+static TdsKernel tds_kernel_ch(int KT, bool fixed)
+{
+    switch (KT) {
+    case 4:  return fixed ? tds_offsets_kernel<CH, 4, 84> : tds_offsets_kernel<CH, 4, 0>;
+    case 8:  return fixed ? tds_offsets_kernel<CH, 8, 92> : tds_offsets_kernel<CH, 8, 0>;
+    }
+    if constexpr (CH == 2) {
+        if (!fixed) return nullptr;
+        switch (KT) {
+        case 11: return tds_offsets_kernel<CH, 11, 61>;
+        case 12: return tds_offsets_kernel<CH, 12, 61>;
+        case 13: return tds_offsets_kernel<CH, 13, 61>;
+        case 14: return tds_offsets_kernel<CH, 14, 61>;
+        case 15: return tds_offsets_kernel<CH, 15, 61>;
+        case 16: return tds_offsets_kernel<CH, 16, 61>;
+        }
+    }
+    return nullptr;
+}
+static TdsKernel tds_kernel_for(int CH, int KT, bool fixed) { return CH == 2 ? tds_kernel_ch<2>(KT, fixed) : tds_kernel_ch<1>(KT, fixed); }
 
 // ---------------------------------------------------------------------------------------------
 // TDStretch assemble: overlap (cross-fade) + copy of every sequence, one CTA per (sequence, track)
@@ -930,6 +990,7 @@ struct nodey_soundtouch {
     unsigned long long R = 0; int e = 0;       // rate = R * 2^-e exactly
     int prefill = 0;                           // silent frames in front of the RateTransposer input
     int force_cluster = 0;                     // test hook: 0 = automatic cluster size for the offsets kernel
+    int force_kt = 0;                          // test hook: 0 = automatic number of candidates per thread of the offsets kernel
     int force_unfused = 0;                     // test hook: separate assemble / FIR / cubic kernels
     float aa[kAaLen];
     float* d_fade = nullptr;
@@ -1166,6 +1227,15 @@ int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster)
     return NODEY_OK;
 }
 
+/* test hook: force the number of candidates a thread of the offsets kernel owns (4, 8, 11..16; 0 = automatic) */
+int nodey_soundtouch_set_candidates_per_thread(nodey_soundtouch* s, int kt)
+{
+    NODEY_REQUIRE(s && (kt == 0 || kt == 4 || kt == 8 || (kt >= 11 && kt <= 16)), NODEY_E_INVALID,
+                  "nodey_soundtouch_set_candidates_per_thread: must be 0, 4, 8 or 11..16");
+    s->force_kt = kt;
+    return NODEY_OK;
+}
+
 void nodey_soundtouch_destroy(nodey_soundtouch* s)
 {
     if (!s) return;
@@ -1363,27 +1433,43 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             else if ((long long)ntracks * 2 <= 400ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
             if (const char* env = getenv("NODEY_TDS_CLUSTER")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) CL = v; }   // development override
-            const int KT = CL >= 4 ? 4 : 8;
             const int K = 4 / CH;
-            const int tcount = (s->seek_length + K - 1) / K, tblocks = (tcount + KT - 1) / KT;
+            const int tcount = (s->seek_length + K - 1) / K;
+            // candidates per thread: a (lane, class) stream of tcount candidates is walked by whole warps, so the cost of a
+            // sequence goes with warps x KT.  One CTA per track: the smallest KT that fits the stream into ONE warp
+            // (456 candidates: 31 lanes x 15 instead of 57 lanes of two warps x 8 -- 6 % fewer rounded operations issued
+            // and half the window loads per operation); clusters split the stream first (29 lanes x 8 resp. x 4)
+            int KT = CL >= 4 ? 4 : 8;
+            if (CL == 1 && CH == 2) { const int k1 = (tcount + 30) / 31; if (k1 >= 11 && k1 <= 16) KT = k1; }   // 31 blocks + 1 (streams that start one element late)
+            if (s->force_kt > 0) KT = s->force_kt;
+            if (const char* env = getenv("NODEY_TDS_KT")) { const int v = atoi(env); if (v == 4 || v == 8 || (v >= 11 && v <= 16)) KT = v; }   // development override
+            if (KT > 8 && (CH != 2 || (tcount + KT - 1) / KT / CL + ta.Q / KT + 5 > 61 || getenv("NODEY_TDS_RUNTIME_SK"))) KT = 8;
+            const int tblocks = (tcount + KT - 1) / KT;
             ta.tb_per = (tblocks + CL - 1) / CL;
+            const int ngroups = (ta.Q + KT - 1) / KT;
             int sk = ta.tb_per + ta.Q / KT + 4;
-            while ((sk & 7) != 4) sk++;
+            // compile-time sub-plane strides (window loads become base + immediate); odd resp. 4 mod 8 so that the staging
+            // stores of consecutive sub-planes spread over the banks
+            const int sk_fixed = KT == 4 ? 84 : KT == 8 ? 92 : 61;
+            bool fixed = sk <= sk_fixed && !getenv("NODEY_TDS_RUNTIME_SK");
+            if (fixed) sk = sk_fixed; else if (KT > 8) sk |= 1; else while ((sk & 7) != 4) sk++;
             ta.sk = sk;
-            ta.ncand_pad = (K * KT * ta.tb_per + ta.tb_per + 4 + 3) & ~3;      // + one pad word per K*KT candidates
-            ta.npm = (KT * (ta.tb_per + 1) + ta.tb_per + 1 + 4 + 3) & ~3;
+            ta.qp = ngroups * ((KT + 3) & ~3) + 8;
+            const int pad_c = (K * KT) & 1 ? 2 : 1, pad_n = KT & 1 ? 2 : 1;
+            ta.ncand_pad = (K * KT * ta.tb_per + pad_c * ta.tb_per + 4 + 3) & ~3;      // + pad words per K*KT candidates
+            ta.npm = (KT * (ta.tb_per + 1) + pad_n * (ta.tb_per + 1) + 4 + 3) & ~3;
             const int mreg = s->seek_length + s->overlap;
             ta.vec8 = (CH == 2 && (((uintptr_t)vin.p) & 7) == 0 && (vin.stride % 2) == 0) ? 1 : 0;
             if (vin.use_tab) {
                 ta.vec8 = CH == 2 ? 1 : 0;
                 for (int t = 0; t < ntracks; t++) if (((uintptr_t)tab->p[2 * t]) & 7) ta.vec8 = 0;
             }
-            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * (ta.Q + 8) + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
+            const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.qp + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
                                                  (size_t)((mreg * CH + 3) & ~3)) + sizeof(double) * (size_t)(K * KT * ta.tb_per);
             NODEY_REQUIRE(smem <= 110 * 1024, NODEY_E_RANGE, "tds_offsets: %zu bytes of shared memory per CTA exceed the two-per-SM budget", smem);
-            NODEY_REQUIRE(KT * sk * 4 / CH <= 2048, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
-            void (*kern)(TdsArgs) = CH == 2 ? (KT == 8 ? tds_offsets_kernel<2, 8> : tds_offsets_kernel<2, 4>)
-                                            : (KT == 8 ? tds_offsets_kernel<1, 8> : tds_offsets_kernel<1, 4>);
+            NODEY_REQUIRE(KT * (ta.tb_per + ta.Q / KT + 4) * 4 / CH <= 2048 + 64 * KT, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
+            void (*kern)(TdsArgs) = tds_kernel_for(CH, KT, fixed);
+            NODEY_REQUIRE(kern, NODEY_E_INVALID, "tds_offsets: internal: no kernel for %d candidates per thread", KT);
             NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             cudaLaunchConfig_t cfg;

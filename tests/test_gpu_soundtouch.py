@@ -70,6 +70,33 @@ def test_soundtouch_cluster_sizes(nd, orc, cluster, cfg):
         assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t}")
 
 
+@pytest.mark.parametrize("kt", [4, 8, 11, 12, 13, 14, 15, 16])
+def test_soundtouch_candidates_per_thread(nd, orc, kt):
+    """every (candidates per thread, cluster size) variant of the WSOLA search gives the oracle's trace: the pitch node's
+    912 candidates and the tempo node's 864 at 48 kHz, 44.1 kHz (810 / 793) and the run-time stride"""
+    import os
+    cases = [(48000, 1.0, orc.pitch_node_factor(3.0)), (48000, 1.25, orc.velocity_node_pitch(1.25, True)),
+             (44100, 1.0, orc.pitch_node_factor(-5.0))]
+    for sr, rate, pitch in cases:
+        n = sr * 2 + 77
+        xs = np.stack([orc.synth_f32(n, 2, sr, 20 + t) for t in range(2)])
+        refs = [orc.soundtouch(xs[t], sr, rate, pitch, 1152) for t in range(2)]
+        st = nd.SoundTouch(sr, 2, rate, pitch)
+        st.set_candidates_per_thread(kt)
+        for cluster in (1, 2, 4):
+            st.set_cluster(cluster)
+            for runtime_sk in (False, True):
+                if runtime_sk:
+                    os.environ["NODEY_TDS_RUNTIME_SK"] = "1"
+                try:
+                    got, offs = st.run(to_dev(xs), 1152, want_offsets=True)
+                finally:
+                    os.environ.pop("NODEY_TDS_RUNTIME_SK", None)
+                for t in range(2):
+                    assert np.array_equal(offs[t].cpu().numpy(), refs[t][1]), f"offset trace: kt {kt} cluster {cluster} sr {sr} rate {rate} track {t}"
+                    assert_bit_equal(got[t].cpu().numpy(), refs[t][0], f"kt {kt} cluster {cluster} track {t}")
+
+
 @pytest.mark.parametrize("cfg", [(48000, 1.0, 3.0, None), (48000, 1.25, None, True), (44100, 1.7, None, False), (8000, 1.0, 11.0, None)])
 def test_soundtouch_fused_and_unfused_tails_agree(nd, orc, cfg):
     """stereo, TDStretch-first: the fused cross-fade + FIR + cubic kernel and the three separate kernels"""
