@@ -13,16 +13,24 @@
 //           registers, a pair (k, M-k) shares its sums, and the 2049 bins go straight to global memory.
 // Two shared-memory exchanges and two barriers per item (the first version ran 8 x 8 x 8 x 4 with four exchanges,
 // four barriers and a separate untangling read: 147 KB of shared traffic per item, now 64 KB; ncu had it latency
-// bound at 34 % issue utilisation).  Twiddles and window come from double-precision tables rounded once to
-// float; the twiddles of passes 2 and 3 are re-laid out per CTA in shared memory (16 KB), window and untangling
-// twiddles are read coalesced through L1.  HBM traffic per item: 4 KB of new input (each sample is reused by 4 overlapping
-// frames out of L2) + 16.4 KB of output -> write-dominated.
+// bound at 34 % issue utilisation).  Nothing that is the same for every item is loaded (round 2; ncu had the L1 / shared
+// data pipe at 71 % of its wavefront peak with twiddle and window loads a third of the wavefronts): five unit phasors per
+// thread, read once from a double-precision table rounded to float, stay in registers, and the twiddles of passes 2 and 3,
+// the untangling twiddles and the Hann window are computed from them per item (powers with chains of at most four
+// multiplications, rotations by sixteenth roots of unity; measured error 3.7e-7 of the frame peak against the 1e-5 bar).
+// Exchange slots are per-thread base pointers plus compile-time offsets; complex additions and subtractions are packed
+// (add.rn.f32x2 / fma.rn.f32x2 with -1: the same roundings as the scalar forms, half the issue slots).
+// HBM traffic per item: 4 KB of new input (each sample is reused by 4 overlapping frames out of L2) + 16.4 KB of output
+// -> write-dominated.  A pure write stream reaches 3.9 TB/s on this GPU (memset / fill, tools/write_peak.py) against the
+// 6.5 TB/s of a copy that counts read + write bytes, so the ceiling of this 1 : 4 read : write mix is about 4.9 TB/s =
+// 75 % of the copy peak the roofline fraction is quoted against.
 //
 // This file is compiled WITHOUT -fmad=false: the oracle evaluates the DFT in double, so the float
 // FFT is a tolerance comparison and fused multiply-adds only make it more accurate.
 #include "nodey_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 
 #ifndef M_PI
@@ -35,14 +43,19 @@ constexpr int kNfft = 4096;
 constexpr int kM = kNfft / 2;        // complex points
 constexpr int kBins = kNfft / 2 + 1;
 constexpr int kThreads = 128;
+// resident CTAs per SM (80 registers, 35 KB of shared memory each).  Measured, 10 min stereo: 4, 5 and 6 CTAs within 2 % of each
+// other, also with the next item's samples prefetched into registers or the twiddle powers kept in registers across items
+// (4 CTAs, 128 registers): the kernel is bound by its own instruction stream -- without its stores it takes 0.297 of
+// 0.337 ms, without its loads 0.28 ms
+constexpr int kStftResident = 6;
 
 // one float2 of padding per 16 keeps the strided stores of the exchanges at the 2-wavefront minimum of a
 // 256-byte warp access
 __device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
 constexpr int kBufLen = kM + (kM >> 4);
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
@@ -105,6 +118,41 @@ __device__ __forceinline__ void fft16(float2 (&a)[16])
     t = a[11]; a[11] = a[14]; a[14] = t;
 }
 
+__device__ __forceinline__ float2 csqr(float2 a) { return make_float2(a.x * a.x - a.y * a.y, (a.x + a.x) * a.y); }
+__host__ __device__ constexpr int top_bit(int r) { int h = 1; while (2 * h <= r) h *= 2; return h; }
+// powers b^1 .. b^(N-1) of a unit phasor: even powers by squaring, odd ones as b^(top bit) * b^(rest), so no chain is longer
+// than four multiplications for N = 16 (a power is within a few ulp of the rounded exact value; the 1e-5 bar of the
+// spectrum is against the frame's peak).  p[0] is not used.
+template <int N>
+__device__ __forceinline__ void cpowers(float2 b, float2 (&p)[N])
+{
+    p[1] = b;
+#pragma unroll
+    for (int r = 2; r < N; r++) p[r] = (r & 1) ? cmul(p[top_bit(r)], p[r - top_bit(r)]) : csqr(p[r / 2]);
+}
+
+// a * e^{-i pi q / 8} for a compile-time q (the sixteenth roots of unity): trivial factors cost no multiplication
+template <int Q>
+__device__ __forceinline__ float2 mul_w16(float2 a)
+{
+    constexpr int q = ((Q % 16) + 16) % 16;
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    if constexpr (q == 0) return a;
+    else if constexpr (q == 4) return mul_mi(a);
+    else if constexpr (q == 8) return make_float2(-a.x, -a.y);
+    else if constexpr (q == 12) return make_float2(-a.y, a.x);
+    else if constexpr (q == 2) return make_float2(h * (a.x + a.y), h * (a.y - a.x));
+    else if constexpr (q == 6) return make_float2(h * (a.y - a.x), -h * (a.x + a.y));
+    else if constexpr (q == 10) return make_float2(-h * (a.x + a.y), h * (a.x - a.y));
+    else if constexpr (q == 14) return make_float2(h * (a.x - a.y), h * (a.x + a.y));
+    else {
+        // e^{-i pi q / 8} = (cos, -sin)
+        constexpr float cs[16] = {1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1, -h, -s1, 0.f, s1, h, c1};
+        constexpr float sn[16] = {0.f, s1, h, c1, 1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1, -h, -s1};
+        return cmul(a, make_float2(cs[q], -sn[q]));
+    }
+}
+
 struct StftArgs {
     float2* out;            // [nch][frames][kBins]
     const float* x;
@@ -132,101 +180,180 @@ __device__ __forceinline__ void untangle_pair(float2 zk, float2 zmc, float2 w, f
     xm = make_float2(0.5f * (e.x - t.y), -0.5f * (e.y + t.x));
 }
 
+// periodic Hann value at n = n0 + 256 R (n0 = 2j or 2j + 1): 0.5 - 0.5 cos(theta0 + R pi/8) = 0.5 + ce C_R + se S_R with
+// ce = -0.5 cos(theta0), se = 0.5 sin(theta0) held per thread -- two fused multiply-adds instead of a load per sample
+template <int R>
+__device__ __forceinline__ float hann_at(float ce, float se)
+{
+    constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+    constexpr float C[16] = {1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1, -h, -s1, 0.f, s1, h, c1};
+    constexpr float S[16] = {0.f, s1, h, c1, 1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1, -h, -s1};
+    if constexpr (R == 0) return 0.5f + ce;
+    else if constexpr (R == 8) return 0.5f - ce;
+    else if constexpr (R == 4) return 0.5f + se;
+    else if constexpr (R == 12) return 0.5f - se;
+    else return fmaf(se, S[R], fmaf(ce, C[R], 0.5f));
+}
+
+template <int VEC, int R>
+__device__ __forceinline__ float2 load_point(const StftArgs& a, const float* p, long long frame, int c, int j)
+{
+    const int n = 2 * (j + 128 * R);
+    if (VEC == 1) return __ldg(reinterpret_cast<const float2*>(p + n));
+    if (VEC == 2) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (frame * (long long)a.hop + n) * 2));
+        return c ? make_float2(q.y, q.w) : make_float2(q.x, q.z);
+    }
+    return make_float2(__ldg(p + n * a.x_stride), __ldg(p + (n + 1) * a.x_stride));
+}
+
+template <int VEC, int R = 0>
+__device__ __forceinline__ void load_raw(float2 (&v)[16], const StftArgs& a, const float* p, long long frame, int c, int j)
+{
+    if constexpr (R < 16) {
+        v[R] = load_point<VEC, R>(a, p, frame, c, j);
+        load_raw<VEC, R + 1>(v, a, p, frame, c, j);
+    }
+}
+
+template <int R = 0>
+__device__ __forceinline__ void apply_window(float2 (&v)[16], const float2 (&raw)[16], float ce0, float se0, float ce1, float se1)
+{
+    if constexpr (R < 16) {
+        v[R] = make_float2(raw[R].x * hann_at<R>(ce0, se0), raw[R].y * hann_at<R>(ce1, se1));
+        apply_window<R + 1>(v, raw, ce0, se0, ce1, se1);
+    }
+}
+
+template <int R = 1>
+__device__ __forceinline__ void twiddle_mirror(float2 (&w)[8], const float2 (&p3)[8], bool first)
+{
+    // butterfly 256 - j: W_2048^{(256 - j) r} = e^{-i pi r / 4} conj(W_2048^{j r});  thread 0 takes butterfly 128: e^{-i pi r / 8}
+    if constexpr (R < 8) {
+        w[R] = first ? mul_w16<R>(w[R]) : cmul(w[R], mul_w16<2 * R>(cconj(p3[R])));
+        twiddle_mirror<R + 1>(w, p3, first);
+    }
+}
+
+template <int R = 0>
+__device__ __forceinline__ void untangle_store(float2* o, const float2 (&u)[8], const float2 (&w)[8], float2 bu, int j)
+{
+    // Z[j + 256 r] = u[r];  its partner Z[2048 - j - 256 r] = Z[(256 - j) + 256 (7 - r)] = w[7 - r];  W_4096^{j + 256 r} = W_4096^j e^{-i pi r / 8}
+    if constexpr (R < 8) {
+        const int k = j + 256 * R;
+        float2 xk, xm;
+        untangle_pair(u[R], cconj(w[7 - R]), mul_w16<R>(bu), xk, xm);
+        st_bin(o + k, xk);
+        st_bin(o + (kM - k), xm);
+        untangle_store<R + 1>(o, u, w, bu, j);
+    }
+}
+
 // VEC 1: channel samples are contiguous and 8-byte aligned (planar input): one 64-bit load per complex point
 // VEC 2: interleaved stereo: one 128-bit load holds the complex point of BOTH channels; a CTA transforms the two channels
 //        of a frame back to back, so the second channel's loads hit the lines the first one brought into L1
 //        (the scalar path issues two strided 32-bit loads per point: twice the instructions and wavefronts)
+//
+// The kernel is bound by the L1 / shared-memory data pipe (ncu: 71 % of its wavefront peak at 47 % issue utilisation, with
+// twiddle and window loads a third of the wavefronts), so everything that does not depend on the item is COMPUTED from five
+// per-thread phasors held in registers instead of loaded: the twiddles of pass 2 (powers of W_256^k), of pass 3 (powers of
+// W_2048^j; the mirror butterfly's are their conjugates times an eighth root of unity), of the untangling (W_4096^j times
+// a sixteenth root of unity) and the Hann window (a rotation by r pi/8 of the thread's cos / sin pair).
 template <int VEC>
-__global__ void __launch_bounds__(kThreads, 4) stft4096_kernel(const __grid_constant__ StftArgs a)
+__global__ void __launch_bounds__(kThreads, kStftResident) stft4096_kernel(const __grid_constant__ StftArgs a)
 {
-    extern __shared__ __align__(16) float2 stft_smem[];      // 51 KB: above the static limit
+    extern __shared__ __align__(16) float2 stft_smem[];      // 35 KB
     float2* bufA = stft_smem;
     float2* bufB = bufA + kBufLen;
-    float2 (*tw2)[16] = reinterpret_cast<float2 (*)[16]>(bufB + kBufLen);
-    float2 (*tw3)[256] = reinterpret_cast<float2 (*)[256]>(bufB + kBufLen + 15 * 16);
-    // twiddles of passes 2 and 3 by (r, butterfly): consecutive threads read consecutive words.  Read straight from
-    // the W_4096 table they were strided by 16 r resp. 2 r entries across a warp -- one L1 wavefront per lane, and ncu
-    // showed the L1 data pipe 91 % busy with the kernel at 35 % issue utilisation.
-    // tw2[15][16]: W_256^{k r}, r = 1..15, k < 16;  tw3[7][256]: W_2048^{jb r}, r = 1..7, jb < 256
     const int j = threadIdx.x;
     const long long items = a.frames * a.nch;
-    for (int i = j; i < 15 * 16; i += kThreads) { const int r = i / 16 + 1, k = i % 16; tw2[r - 1][k] = a.tw[k * r * 16]; }
-    for (int i = j; i < 7 * 256; i += kThreads) { const int r = i / 256 + 1, jb = i % 256; tw3[r - 1][jb] = a.tw[jb * r * 2]; }
-    // (the first barrier of the item loop orders these stores before their first use in pass 2)
+    const float2 b2 = __ldg(a.tw + (j & 15) * 16);           // W_256^k, k = j & 15
+    const float2 b3 = __ldg(a.tw + 2 * j);                   // W_2048^j = (cos, -sin)(2 pi 2j / 4096): also the window phasor of n = 2j
+    const float2 bu = __ldg(a.tw + j);                       // W_4096^j
+    const float2 b1 = __ldg(a.tw + 2 * j + 1);               // window phasor of n = 2j + 1
+    const float ce0 = -0.5f * b3.x, se0 = -0.5f * b3.y, ce1 = -0.5f * b1.x, se1 = -0.5f * b1.y;
+    // padded exchange slots as base + compile-time offset: pad(i) = i + (i >> 4), and every index below is a per-thread
+    // constant plus a multiple of 16 (pad(c + 16 m) = pad(c) + 17 m when c < 16 ... in general the shift distributes because
+    // the per-thread parts are multiples of 16 or stay below 16)
+    const int jb0 = j, jb1 = j ? 256 - j : 128;
+    float2* const s1 = bufA + 17 * j;                                   // pass 1 stores: pad(16 j + r) = 17 j + r
+    const float2* const l2 = bufA + j + (j >> 4);                       // pass 2 loads:  pad(j + 128 r) = pad(j) + 136 r
+    float2* const s2 = bufB + (j & ~15) * 17 + (j & 15);                // pass 2 stores: pad((j & ~15) 16 + k + 16 r) = 17 (j & ~15) + k + 17 r
+    const float2* const l3a = bufB + jb0 + (jb0 >> 4);                  // pass 3 loads:  pad(jb + 256 r) = pad(jb) + 272 r
+    const float2* const l3b = bufB + jb1 + (jb1 >> 4);
 
     // item -> (frame, channel): channel fastest within a CTA's own sequence of items when VEC == 2 (see above), otherwise
     // across CTAs (consecutive CTAs take the channels of one frame)
-    for (long long it = blockIdx.x; it < items; it += (VEC == 2 ? 1 : gridDim.x)) {
+    const auto locate = [&](long long it, long long& frame, int& c) -> bool {
+        if (it >= items) return false;
         long long item = it;
         if (VEC == 2) {
             // CTA b owns frames b, b + grid, ...; `it` walks 2 * (its frames)
             const long long local = it - blockIdx.x;                 // 0, 1, 2, ... within this CTA
             const long long frame_v = blockIdx.x + (local >> 1) * (long long)gridDim.x;
-            if (frame_v >= a.frames) break;
+            if (frame_v >= a.frames) return false;
             item = frame_v * 2 + (local & 1);
         }
-        const long long frame = item / a.nch;
-        const int c = (int)(item - frame * a.nch);
-        const float* p = a.x + (long long)c * a.ch_stride + frame * (long long)a.hop * a.x_stride;
-
+        frame = item / a.nch;
+        c = (int)(item - frame * a.nch);
+        return true;
+    };
+    const auto fetch = [&](float2 (&raw)[16], long long frame, int c) {
+        load_raw<VEC>(raw, a, a.x + (long long)c * a.ch_stride + frame * (long long)a.hop * a.x_stride, frame, c, j);
+    };
+    const long long step = VEC == 2 ? 1 : gridDim.x;
+    long long it = blockIdx.x, frame = 0; int c = 0;
+    bool valid = locate(it, frame, c);
+    while (valid) {
         float2 v[16];
-        // ---- pass 1: radix 16, Ns = 1 (no twiddles); window fused into the load ----
-#pragma unroll
-        for (int r = 0; r < 16; r++) {
-            const int n = 2 * (j + 128 * r);
-            float2 s;
-            if (VEC == 1) s = __ldg(reinterpret_cast<const float2*>(p + n));
-            else if (VEC == 2) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (frame * (long long)a.hop + n) * 2));
-                s = c ? make_float2(q.y, q.w) : make_float2(q.x, q.z);
-            }
-            else { s.x = __ldg(p + n * a.x_stride); s.y = __ldg(p + (n + 1) * a.x_stride); }
-            const float2 w = __ldg(reinterpret_cast<const float2*>(a.win + n));
-            v[r] = make_float2(__fmul_rn(s.x, w.x), __fmul_rn(s.y, w.y));
+        // ---- pass 1: radix 16, Ns = 1 (no twiddles); window applied to the loaded samples ----
+        {
+            float2 raw[16];
+            fetch(raw, frame, c);
+            apply_window(v, raw, ce0, se0, ce1, se1);
         }
         fft16(v);
 #pragma unroll
-        for (int r = 0; r < 16; r++) bufA[pad(16 * j + r)] = v[r];
+        for (int r = 0; r < 16; r++) s1[r] = v[r];
         __syncthreads();
+        const long long frame_cur = frame; const int c_cur = c;
+        it += step;
+        valid = locate(it, frame, c);
 
-        // ---- pass 2: radix 16, Ns = 16: W_256^{k r} = W_4096^{16 k r} ----
+        // ---- pass 2: radix 16, Ns = 16: twiddles W_256^{k r} ----
         {
-            const int k = j & 15;
+            float2 p2[16];
+            cpowers<16>(b2, p2);
 #pragma unroll
             for (int r = 0; r < 16; r++) {
-                v[r] = bufA[pad(j + 128 * r)];
-                if (r) v[r] = cmul(v[r], tw2[r - 1][k]);
+                v[r] = l2[136 * r];
+                if (r) v[r] = cmul(v[r], p2[r]);
             }
             fft16(v);
-            const int base = (j & ~15) * 16 + k;
 #pragma unroll
-            for (int r = 0; r < 16; r++) bufB[pad(base + 16 * r)] = v[r];
+            for (int r = 0; r < 16; r++) s2[17 * r] = v[r];
         }
         __syncthreads();
 
-        // ---- pass 3: radix 8, Ns = 256: W_2048^{jb r} = W_4096^{2 jb r}; butterflies jb0 and its mirror jb1 ----
-        const int jb0 = j, jb1 = j ? 256 - j : 128;
+        // ---- pass 3: radix 8, Ns = 256: twiddles W_2048^{jb r}; butterflies jb0 = j and its mirror jb1 ----
         float2 u[8], w[8];
+        {
+            float2 p3[8];
+            cpowers<8>(b3, p3);
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            u[r] = bufB[pad(jb0 + 256 * r)];
-            w[r] = bufB[pad(jb1 + 256 * r)];
-            if (r) { u[r] = cmul(u[r], tw3[r - 1][jb0]); w[r] = cmul(w[r], tw3[r - 1][jb1]); }
+            for (int r = 0; r < 8; r++) {
+                u[r] = l3a[272 * r];
+                w[r] = l3b[272 * r];
+                if (r) u[r] = cmul(u[r], p3[r]);
+            }
+            twiddle_mirror(w, p3, j == 0);
         }
         fft8(u);
         fft8(w);
         // ---- real-input untangling in registers, bins straight to global memory ----
-        float2* o = a.out + ((long long)c * a.frames + frame) * kBins;
+        float2* o = a.out + ((long long)c_cur * a.frames + frame_cur) * kBins;
         if (j) {
-            // Z[j + 256 r] = u[r];  its partner Z[2048 - j - 256 r] = Z[(256 - j) + 256 (7 - r)] = w[7 - r]
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int k = j + 256 * r;
-                float2 xk, xm;
-                untangle_pair(u[r], cconj(w[7 - r]), __ldg(a.tw + k), xk, xm);
-                st_bin(o + k, xk);
-                st_bin(o + (kM - k), xm);
-            }
+            untangle_store(o, u, w, bu, j);
         } else {
             // butterfly 0: Z[256 r] = u[r], partner Z[256 (8 - r)]; bins 0 and 2048 are real; bin 1024 is its own partner
             st_bin(o, make_float2(u[0].x + u[0].y, 0.f));
@@ -322,9 +449,9 @@ int nodey_stft(float* out_complex, const float* x, int64_t nframes, int nch, int
     a.vec_ok = (a.x_stride == 1) && (((uintptr_t)x & 7) == 0) && (hop % 2 == 0) && (a.ch_stride % 2 == 0);
     a.inter2 = interleaved && nch == 2 && (((uintptr_t)x & 15) == 0) && (hop % 2 == 0);
     const int64_t items = frames * nch;
-    const int64_t cap = (int64_t)sm_count() * 4;
+    const int64_t cap = (int64_t)sm_count() * kStftResident;
     const int grid = (int)(items < cap ? items : cap);
-    constexpr size_t smem = sizeof(float2) * (2 * kBufLen + 15 * 16 + 7 * 256);
+    constexpr size_t smem = sizeof(float2) * (2 * kBufLen);
     void (*kern)(StftArgs) = a.inter2 ? stft4096_kernel<2> : (a.vec_ok ? stft4096_kernel<1> : stft4096_kernel<0>);
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NODEY_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
