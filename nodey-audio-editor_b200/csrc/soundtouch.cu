@@ -1438,12 +1438,14 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
         ta.overlap = s->overlap; ta.seek_window = s->seek_window; ta.seek_length = s->seek_length;
         ta.Q = 4 * (CH * s->overlap / 16);
         if (seq_end > seq_begin) {
-            // cluster size: spread one track over CL SMs while the batch leaves SMs idle.  From the measured batch
-            // sweep (tools/st_sweep.py, 256-thread CTAs, two per SM): 4 CTAs per track up to about 40 tracks (one CTA
-            // per SM), 2 up to about 200 tracks, 1 beyond
+            // cluster size: spread one track over CL SMs while the batch leaves SMs idle.  Measured in the engine, where the
+            // pitch and the tempo node's chains of a batch run side by side (tools/chain_trace.py, 256-thread CTAs, two per
+            // SM; ms for CL = 1 / 2 / 4): 32 tracks 50.5 / 43.2 / 33.1, 48 tracks - / 46.2 / 48.6, 64 tracks 71.4 / 53.5 / 63.7,
+            // 96 tracks 79.3 / 78.7 / -, 112 tracks 86.1 / 90.8 / -, 128 tracks 94.4 / 104.7 / 125.9.  So: 4 CTAs per track
+            // up to 40 tracks, 2 up to about 100 (round 1, with the KT = 8 single-CTA kernel: up to 200), 1 beyond
             int CL = 1;
             if ((long long)ntracks * 4 <= 160ll * sm_count() / 148) CL = 4;
-            else if ((long long)ntracks * 2 <= 400ll * sm_count() / 148) CL = 2;
+            else if ((long long)ntracks * 2 <= 208ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
             if (const char* env = getenv("NODEY_TDS_CLUSTER")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) CL = v; }   // development override
             const int K = 4 / CH;
