@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
     const int nnorm = 4 * wpn;
     const int m_lo = KT * tb_lo;                     // first plane element this CTA stages
     const int f_lo = 4 * m_lo / CH;                  // ... and the first frame
-    const int nfr = plane_len * 4 / CH;              // frames covered by the staged planes
+    // frames to stage: what the lane sums can read (blocks 0 .. tb_per + Q/KT + 2 of a sub-plane), not the whole plane -- with
+    // the compile-time stride the planes are larger than one window
+    const int need = KT * (a.tb_per + Q / KT + 3);
+    const int nfr = (need < plane_len ? need : plane_len) * 4 / CH;
     const int c_base = K * KT * tb_lo;               // first candidate of this CTA
     int ncand = K * KT * ntb; if (c_base + ncand > L) ncand = L - c_base; if (ncand < 0) ncand = 0;
 

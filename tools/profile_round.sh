@@ -16,5 +16,7 @@ N=256 SECS=180 python tools/prof_st.py || exit 1
 N=256 SECS=180 ncu --set full --clock-control none --import-source on -k regex:tds_offsets -c 1 -o $out/${tag}_tds_offsets_fullsize -f python tools/prof_st.py > $out/${tag}_ncu_tds.log 2>&1
 N=256 SECS=60 ncu --set full --clock-control none --import-source on -k regex:st_post -c 1 -o $out/${tag}_st_post -f python tools/prof_st.py > $out/${tag}_ncu_post.log 2>&1
 python tools/prof_resample.py > /dev/null || exit 1
-ncu --set full --clock-control none --import-source on -k regex:"resample_tile2|stft4096" -c 3 -o $out/${tag}_resample_stft -f python tools/prof_resample.py > $out/${tag}_ncu_rs.log 2>&1
-tail -q -n 2 $out/${tag}_ncu_tds.log $out/${tag}_ncu_post.log $out/${tag}_ncu_rs.log
+ncu --set full --clock-control none --import-source on -k regex:"resample_tile2" -c 2 -o $out/${tag}_resample -f python tools/prof_resample.py > $out/${tag}_ncu_rs.log 2>&1
+python tools/prof_stft.py > $out/${tag}_stft_timing.txt || exit 1
+ncu --set full --clock-control none --import-source on -k regex:"stft4096" -c 2 -o $out/${tag}_stft -f python tools/prof_stft.py > $out/${tag}_ncu_stft.log 2>&1
+tail -q -n 2 $out/${tag}_ncu_tds.log $out/${tag}_ncu_post.log $out/${tag}_ncu_rs.log $out/${tag}_ncu_stft.log

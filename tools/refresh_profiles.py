@@ -8,7 +8,7 @@ shutil.copy(f"{G}/{tag}_bench_n1.json", f"{P}/{R}_bench_n1.json")
 shutil.copy(f"{G}/{tag}_kbench.txt", f"{P}/{R}_kbench.txt")
 shutil.copy(f"{G}/{tag}_launches_bench.csv", f"{P}/{R}_launches_bench.csv")
 for rep, out in ((f"{tag}_tds_offsets_fullsize", f"{R}_tds_offsets_fullsize_ncu_raw.csv"), (f"{tag}_st_post", f"{R}_st_post_ncu_raw.csv"),
-                 (f"{tag}_resample_stft", f"{R}_resample_stft_ncu_raw.csv")):
+                 (f"{tag}_resample", f"{R}_resample_ncu_raw.csv"), (f"{tag}_stft", f"{R}_stft_ncu_raw.csv")):
     with open(f"{P}/{out}", "w") as f:
         subprocess.run(["ncu", "-i", f"{G}/{rep}.ncu-rep", "--page", "raw", "--csv"], stdout=f, stderr=subprocess.DEVNULL, check=True)
 rows = list(csv.reader(open(f"{P}/{R}_launches_bench.csv")))
@@ -43,7 +43,8 @@ j = json.load(open(f"{P}/{R}_bench_n1.json"))
 print("value", j["value"], "ms", j["ms_per_step"], "e2e", j["e2e"]["value"], j["e2e"]["ms_per_step"], "launches", j["gpu_launches"], "cpu", j["cpu_baseline"]["value"])
 print(json.dumps(j["roofline"], indent=0)[:1500])
 print(open(f"{P}/{R}_kbench.txt").read())
-for f in (f"{R}_tds_offsets_fullsize_ncu_raw.csv", f"{R}_st_post_ncu_raw.csv", f"{R}_resample_stft_ncu_raw.csv"):
+shutil.copy(f"{G}/{tag}_stft_timing.txt", f"{P}/{R}_stft_timing.txt")
+for f in (f"{R}_tds_offsets_fullsize_ncu_raw.csv", f"{R}_st_post_ncu_raw.csv", f"{R}_resample_ncu_raw.csv", f"{R}_stft_ncu_raw.csv"):
     rows = list(csv.reader(open(f"{P}/{f}")))
     for r in rows[2:]:
         d, u = dict(zip(rows[0], r)), dict(zip(rows[0], rows[1]))
