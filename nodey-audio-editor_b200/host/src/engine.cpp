@@ -5,6 +5,7 @@
 
 #include "nodey_engine.h"
 
+#include <chrono>
 #include <cstring>
 
 using namespace infra;
@@ -156,7 +157,10 @@ int nodey_engine_run(nodey_engine* e)
 	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
 	try
 	{
+		const bool timing = getenv("NODEY_ENGINE_TIMING") != nullptr;      // development: host-side phases of a run on stderr
+		const auto t0 = std::chrono::steady_clock::now();
 		e->runner.reset();
+		const auto t1 = std::chrono::steady_clock::now();
 		std::map<Id_t, std::shared_ptr<std::any>> node_data;
 		if (const auto in = e->graph.singleton_node_map.find("audio_input"); in != e->graph.singleton_node_map.end())
 			node_data[in->second] = std::make_shared<std::any>(e->sources);
@@ -173,7 +177,14 @@ int nodey_engine_run(nodey_engine* e)
 			node_data[out->second] = e->sink_data;
 		}
 		e->runner = Runner::create_and_run(e->graph, std::move(node_data));
+		const auto t2 = std::chrono::steady_clock::now();
 		e->runner->wait();
+		if (timing)
+		{
+			const auto t3 = std::chrono::steady_clock::now();
+			const auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+			fprintf(stderr, "[nodey engine] drop previous run %.2f ms, resources + start %.2f ms, run + drain %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+		}
 		const std::string err = e->runner->first_error();
 		if (!err.empty()) return fail(NODEY_ENGINE_E_NODE, err);
 		return 0;

@@ -311,23 +311,27 @@ namespace infra
 
 	std::vector<std::vector<Id_t>> Graph::topological_levels() const
 	{
-		std::map<Id_t, std::set<Id_t>> successors;
+		// A render checks and levels its graph on every run, so this is linear work on flat arrays (the 256-track project has
+		// 1044 nodes and 1300 links; the first version -- check_multiple_input() per link, maps of sets -- took 10 ms per run).
+		std::map<Id_t, int> arrivals;            // links per input pin
+		for (const auto& [_, link] : links) arrivals[link.to]++;
+		const size_t slots = nodes.empty() ? 0 : (size_t)nodes.rbegin()->first + 1;      // node ids are small non-negative integers
+		std::vector<std::vector<Id_t>> successors(slots);
+		std::vector<int> pending(slots, 0);      // links that still have to be satisfied (a producer linked twice counts twice, on both sides)
 		for (const auto& [_, link] : links)
 		{
 			if (!check_node_type_match(link.from, link.to)) throw Mismatched_pin_error{link.from, link.to};
-			if (!check_multiple_input(link.to)) throw Multiple_input_error(link.to);
-			successors[pins.at(link.from).parent].insert(pins.at(link.to).parent);
+			if (arrivals.at(link.to) > 1) throw Multiple_input_error(link.to);
+			const Id_t from = pins.at(link.from).parent, to = pins.at(link.to).parent;
+			if (from < 0 || to < 0 || (size_t)from >= slots || (size_t)to >= slots) THROW_LOGIC_ERROR("Link between unknown nodes {} -> {}", from, to);
+			successors[from].push_back(to);
+			pending[to]++;
 		}
-		// Kahn's algorithm on node level: a node is ready when all producer nodes are placed
-		std::map<Id_t, std::set<Id_t>> producers;
-		for (const auto& [_, link] : links) producers[pins.at(link.to).parent].insert(pins.at(link.from).parent);
-		std::map<Id_t, size_t> pending;
-		for (const auto& [id, _] : nodes) pending[id] = producers.contains(id) ? producers.at(id).size() : 0;
-
+		// Kahn's algorithm on node level: a node is ready when all its producers are placed
 		std::vector<std::vector<Id_t>> levels;
 		std::vector<Id_t> frontier;
-		for (const auto& [id, n] : pending)
-			if (n == 0) frontier.push_back(id);
+		for (const auto& [id, _] : nodes)
+			if (pending[id] == 0) frontier.push_back(id);
 		if (!nodes.empty() && frontier.empty()) throw Loop_detected_error{};
 		size_t placed = 0;
 		while (!frontier.empty())
@@ -336,12 +340,8 @@ namespace infra
 			placed += frontier.size();
 			std::vector<Id_t> next;
 			for (const Id_t id : frontier)
-			{
-				const auto succ = successors.find(id);
-				if (succ == successors.end()) continue;
-				for (const Id_t s : succ->second)
+				for (const Id_t s : successors[id])
 					if (--pending[s] == 0) next.push_back(s);
-			}
 			std::sort(next.begin(), next.end());
 			frontier = std::move(next);
 		}
@@ -450,7 +450,11 @@ namespace infra
 	// ---------------------------------------------------------------------------------------------
 	void Runner::generate_processor_resources(const Graph& graph)
 	{
+		const auto T0 = std::chrono::steady_clock::now();
+		auto TP = T0;
+		const auto lap = [&](const char* what) { const auto n = std::chrono::steady_clock::now(); if (getenv("NODEY_ENGINE_TIMING")) fprintf(stderr, "  [resources] %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - TP).count()); TP = n; };
 		levels = graph.topological_levels();   // = check_graph(), and the schedule
+		lap("levels");
 
 		for (const auto& [id, node] : graph.nodes)
 		{
@@ -464,6 +468,7 @@ namespace infra
 			processor_resources.emplace(id, std::move(resource));
 		}
 
+		lap("resources");
 		// one product per link, generated by the source pin; fan-out = several products on one output pin
 		for (const auto& [idx, link] : graph.links)
 		{
@@ -475,6 +480,7 @@ namespace infra
 			link_products.emplace(idx, product);
 		}
 
+		lap("products");
 		// waves: links leaving a source node (level 0) belong to wave (position of the pin among the node's
 		// output pins) / wave_size; every other node runs in the latest wave among its inputs
 		// Waves hide the host -> device upload behind compute; smaller batches cost some kernel efficiency, so a render
@@ -529,16 +535,19 @@ namespace infra
 			wave_begin.push_back(p);
 			if (source_pins - p > kBody) wave_begin.push_back(source_pins - kEdge);
 		}
+		lap("wave sizes");
 		const auto wave_of_pin = [&](int position) {
 			return (int)(std::upper_bound(wave_begin.begin(), wave_begin.end(), position) - wave_begin.begin()) - 1;
 		};
-		std::map<Id_t, int> pin_position;     // output pin -> index in its node's attribute order
-		for (const auto& [id, node] : graph.nodes)
-		{
-			int k = 0;
-			for (const auto& attribute : node.processor->get_pin_attributes())
-				if (!attribute.is_input) pin_position[node.pin_name_map.at(attribute.identifier)] = k++;
-		}
+		std::map<Id_t, int> pin_position;     // output pin of a source node -> index in its node's attribute order
+		if (!levels.empty())
+			for (const Id_t id : levels.front())
+			{
+				const auto& node = graph.nodes.at(id);
+				int k = 0;
+				for (const auto& attribute : node.processor->get_pin_attributes())
+					if (!attribute.is_input) pin_position[node.pin_name_map.at(attribute.identifier)] = k++;
+			}
 		std::set<Id_t> sources(levels.empty() ? std::vector<Id_t>{}.begin() : levels.front().begin(),
 							   levels.empty() ? std::vector<Id_t>{}.end() : levels.front().end());
 		for (const auto& [id, _] : graph.nodes) node_wave[id] = 0;
@@ -557,6 +566,7 @@ namespace infra
 					}
 				node_wave[id] = wave;
 			}
+		lap("node waves");
 	}
 
 	namespace { std::atomic<bool> g_release_products{false}; }
