@@ -50,7 +50,10 @@ constexpr int kAaLen = 64;
 #ifndef NODEY_TDS_THREADS
 #define NODEY_TDS_THREADS 256
 #endif
-constexpr int kTdsThreads = NODEY_TDS_THREADS;      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
+constexpr int kTdsThreads = NODEY_TDS_THREADS;
+#ifndef NODEY_TDS_RESIDENT
+#define NODEY_TDS_RESIDENT 2
+#endif      // two CTAs (two tracks, or two slices of one) share an SM and fill each other's staging / reduction gaps
 
 // frames of a (possibly batched) stream with virtual silence: `prefix` silent frames in front
 // (RateTransposer latency pre-fill) and silence after `n` real frames (flush blocks).
@@ -261,7 +264,7 @@ __device__ __forceinline__ unsigned long long argmax_key(double v)
 //   * the position weights 1 - 0.25 t^2 are tabulated once.
 // SK > 0: the sub-plane stride is a compile-time constant (a.sk == SK), 0: run-time a.sk
 template <int CH, int KT, int SK>
-__global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+__global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(kTdsThreads, 2) tds_offsets_kernel(const __gri
 #endif
 }
 
+constexpr int kTdsSkLarge = 51;      // compile-time sub-plane stride of the KT = 11..16 kernels (odd; 32 candidate blocks + 13 groups + margin)
 typedef void (*TdsKernel)(TdsArgs);
 // KT = 11..16 exist for stereo with the compile-time stride only (mono streams fit one warp at KT = 8; anything that does
 // not fit the fixed stride runs with KT = 8 and the run-time stride)
@@ -525,12 +529,12 @@ static TdsKernel tds_kernel_ch(int KT, bool fixed)
     if constexpr (CH == 2) {
         if (!fixed) return nullptr;
         switch (KT) {
-        case 11: return tds_offsets_kernel<CH, 11, 61>;
-        case 12: return tds_offsets_kernel<CH, 12, 61>;
-        case 13: return tds_offsets_kernel<CH, 13, 61>;
-        case 14: return tds_offsets_kernel<CH, 14, 61>;
-        case 15: return tds_offsets_kernel<CH, 15, 61>;
-        case 16: return tds_offsets_kernel<CH, 16, 61>;
+        case 11: return tds_offsets_kernel<CH, 11, kTdsSkLarge>;
+        case 12: return tds_offsets_kernel<CH, 12, kTdsSkLarge>;
+        case 13: return tds_offsets_kernel<CH, 13, kTdsSkLarge>;
+        case 14: return tds_offsets_kernel<CH, 14, kTdsSkLarge>;
+        case 15: return tds_offsets_kernel<CH, 15, kTdsSkLarge>;
+        case 16: return tds_offsets_kernel<CH, 16, kTdsSkLarge>;
         }
     }
     return nullptr;
@@ -1461,14 +1465,14 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             if (CL == 1 && CH == 2) { const int k1 = (tcount + 30) / 31; if (k1 >= 11 && k1 <= 16) KT = k1; }   // 31 blocks + 1 (streams that start one element late)
             if (s->force_kt > 0) KT = s->force_kt;
             if (const char* env = getenv("NODEY_TDS_KT")) { const int v = atoi(env); if (v == 4 || v == 8 || (v >= 11 && v <= 16)) KT = v; }   // development override
-            if (KT > 8 && (CH != 2 || (tcount + KT - 1) / KT / CL + ta.Q / KT + 5 > 61 || getenv("NODEY_TDS_RUNTIME_SK"))) KT = 8;
+            if (KT > 8 && (CH != 2 || (tcount + KT - 1) / KT / CL + ta.Q / KT + 5 > kTdsSkLarge || getenv("NODEY_TDS_RUNTIME_SK"))) KT = 8;
             const int tblocks = (tcount + KT - 1) / KT;
             ta.tb_per = (tblocks + CL - 1) / CL;
             const int ngroups = (ta.Q + KT - 1) / KT;
             int sk = ta.tb_per + ta.Q / KT + 4;
             // compile-time sub-plane strides (window loads become base + immediate); odd resp. 4 mod 8 so that the staging
             // stores of consecutive sub-planes spread over the banks
-            const int sk_fixed = KT == 4 ? 84 : KT == 8 ? 92 : 61;
+            const int sk_fixed = KT == 4 ? 84 : KT == 8 ? 92 : kTdsSkLarge;
             bool fixed = sk <= sk_fixed && !getenv("NODEY_TDS_RUNTIME_SK");
             if (fixed) sk = sk_fixed; else if (KT > 8) sk |= 1; else while ((sk & 7) != 4) sk++;
             ta.sk = sk;
