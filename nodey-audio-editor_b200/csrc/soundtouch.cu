@@ -315,8 +315,8 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
     int ncand = K * KT * ntb; if (c_base + ncand > L) ncand = L - c_base; if (ncand < 0) ncand = 0;
 
     // ---- staging (all asynchronous) ----
-    const auto window_copy = [&](int seq, float* Xb) {
-        const long long p0 = a.pos[seq] - a.in.prefix;
+    const auto window_copy = [&](long long pos_seq, float* Xb) {
+        const long long p0 = pos_seq - a.in.prefix;
         for (int fr = tid; fr < nfr; fr += kTdsThreads) {
             const int f = f_lo + fr;
             const long long g = p0 + f;
@@ -347,9 +347,8 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
             } else cp_async4(MR + fr, base.a + go, ok);
         }
     };
-    const auto l2_prefetch = [&](int seq) {
-        if (seq >= a.nseq) return;
-        const long long q0 = a.pos[seq] + f_lo - a.in.prefix;
+    const auto l2_prefetch = [&](long long pos_seq) {
+        const long long q0 = pos_seq + f_lo - a.in.prefix;
         const int lines = (nfr * CH * 4 + 127) / 128 + 1;
         for (int t = tid; t < lines; t += blockDim.x) {
             const long long f = q0 + (long long)t * (32 / CH);
@@ -384,7 +383,12 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
         const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
         PW[cc] = __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp));
     }
-    window_copy(a.seq_begin, X0);
+    // sequence positions ride two iterations ahead in registers: a load of pos[] at the top of an iteration put an L2 round
+    // trip on the chain's critical path (phase timers: 0.5 k of the 12.7 k clocks of a sequence at 32 tracks)
+    long long pos_cur = a.pos[a.seq_begin];
+    long long pos_n1 = a.seq_begin + 1 < a.seq_end ? a.pos[a.seq_begin + 1] : 0;
+    long long pos_n2 = a.seq_begin + 2 < a.seq_end ? a.pos[a.seq_begin + 2] : 0;
+    window_copy(pos_cur, X0);
     int moff = 0;                                    // offset of the mid buffer inside the staged region
     if (a.seq_begin == 1) mid_region_copy(a.pos[0] + temp);       // first sequence: offset 0, no search
     else {
@@ -403,15 +407,17 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
 #endif
 
     for (int i = a.seq_begin; i < a.seq_end; i++) {
-        const long long p0 = a.pos[i];
+        const long long p0 = pos_cur;
         const float* X = X0 + cur * 4 * plane_len;
         // ---- mid buffer: gathered from the staged region, de-interleaved by lane ----
         for (int j = tid; j < 4 * Q; j += blockDim.x) {
             const int q = j >> 2;
             Y[(j & 3) * QP + (KTP == KT ? q : (q / KT) * KTP + q % KT)] = MR[moff * CH + j];
         }
-        if (i + 1 < a.seq_end) window_copy(i + 1, X0 + (cur ^ 1) * 4 * plane_len);
-        if (i + 2 < a.seq_end) l2_prefetch(i + 2);
+        if (i + 1 < a.seq_end) window_copy(pos_n1, X0 + (cur ^ 1) * 4 * plane_len);
+        if (i + 2 < a.seq_end) l2_prefetch(pos_n2);
+        pos_cur = pos_n1; pos_n1 = pos_n2;
+        if (i + 3 < a.seq_end) pos_n2 = a.pos[i + 3];
         TDS_T(0);
         __syncthreads();
         TDS_T(1);
@@ -473,10 +479,17 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
         TDS_T(4);
         __syncthreads();
         TDS_T(5);
-        unsigned long long fk = red_k[0]; int fi = red_i[0];
-        for (int w = 1; w < nwarps; w++) {
-            const unsigned long long k = red_k[w]; const int ix = red_i[w];
-            if (k > fk || (k == fk && ix < fi)) { fk = k; fi = ix; }
+        // every warp reduces the per-warp results itself, with the same three integer reductions (no serial walk over the
+        // warps, no second barrier): largest key, lowest index among equals
+        unsigned long long fk; int fi;
+        {
+            const unsigned long long k = lane < nwarps ? red_k[lane] : 0ull;
+            const int ix = lane < nwarps ? red_i[lane] : 0x7fffffff;
+            const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            fi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? ix : 0x7fffffff);
+            fk = ((unsigned long long)mh << 32) | ml;
         }
         const int par = i & 1;
         if (CL > 1) {

@@ -66,6 +66,17 @@ def fam_soundtouch():
         st.set_cluster(cluster)
         st.run(x, want_offsets=True)
         st.close()
+    for kt, cluster in ((8, 1), (12, 2), (16, 1), (13, 4), (4, 4)):     # every code shape of the search: full / partial last group, rotating / two-group bodies
+        st = nd.SoundTouch.pitch_node(48000, 2, 3.0)
+        st.set_candidates_per_thread(kt)
+        st.set_cluster(cluster)
+        st.run(x, want_offsets=True)
+        st.close()
+    os.environ["NODEY_TDS_RUNTIME_SK"] = "1"                          # run-time sub-plane stride
+    st = nd.SoundTouch.pitch_node(48000, 2, 3.0)
+    st.run(x)
+    st.close()
+    os.environ.pop("NODEY_TDS_RUNTIME_SK")
     st = nd.SoundTouch.velocity_node(48000, 2, 1.25, True)
     st.run(x)
     st.set_unfused(1)
