@@ -61,7 +61,8 @@ int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channe
                         double* pts_seconds, void** plane0, void** plane1);
 /* Process_context::export_path of the sink (src/frontend/app.cpp:2067-2073): "" keeps the result in memory only, a
  * path ending in ".wav" makes the export also write an interleaved 32-bit float WAV, with do_export's pts rule:
- * (int)(first pts * sample_rate) frames of silence in front (src/processor/audio-io.cpp:833-839). */
+ * (int)((frame stamp - time) * sample_rate) frames of silence in front of every frame where that is positive
+ * (src/processor/audio-io.cpp:833-839; nodey_engine_export_plan below states the arithmetic). */
 int nodey_engine_set_export_path(nodey_engine* e, const char* path);
 /* Any other non-empty path is an MP3 export like the reference's (Audio_output::do_export, audio-io.cpp:640-841): the
  * stream goes to LAME in its own sample format, frame by frame in the sizes its producer recorded, with the same
@@ -76,6 +77,16 @@ int nodey_engine_mp3_available(void);
  * *time_inout = Process_context::time before / after (NULL = start at 0). */
 int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* plane1, int fmt, int sample_rate, int channels,
                             int64_t frames, int frame_size, double pts_seconds, int kbps, double* time_inout);
+/* do_export's per-frame bookkeeping as plain arithmetic (audio-io.cpp:826-839): for a stream of `frames` samples per channel
+ * cut into the given frame runs, whose frames are stamped by rule `stamp` -- 0: exact start times from `origin` (decoder
+ * stamps), 1: running END time from `origin` truncated to whole microseconds (audio_amix / audio_bimix,
+ * audio-amix.cpp:199-201), 2: running start time from `origin` through a float of microseconds (SoundTouch nodes,
+ * audio-velocity.cpp:238-249, 313-318) -- fills silence[k] = samples of silence the export encodes in front of frame k
+ * (up to cap entries; any of the output pointers may be NULL) and *time_inout = Process_context::time before / after.
+ * Returns the number of frames.  nodey_engine_product_stamp: rule and origin of an audio product of the last run. */
+int nodey_engine_export_plan(int stamp, double origin, int sample_rate, int64_t frames, const int64_t* run_len, const int64_t* run_count,
+                             int n_runs, double* time_inout, int64_t* silence, double* frame_pts, int cap);
+int nodey_engine_product_stamp(nodey_engine* e, int node_id, const char* pin, int* stamp, double* origin);
 /* Preview instead of export (the reference's Preview state, src/frontend/app.cpp:2001-2040 -> Audio_output::do_preview,
  * src/processor/audio-io.cpp:478-638): the sink brings the stream to 48 kHz stereo float frame by frame without a
  * final flush, clamps to [-1, 1] and queues packed frames.  nodey_engine_preview returns that queue content (device
@@ -83,6 +94,13 @@ int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* pl
  * value is the number of chunks. */
 int nodey_engine_set_preview(nodey_engine* e, int preview);
 int nodey_engine_preview(nodey_engine* e, int64_t* frames, void** packed, int64_t* chunk_len, int chunk_cap);
+/* Scheduling knobs of this engine's runs (infra::Runner::Schedule): "wave_pins" (waves of n source pins), "wave_pattern"
+ * ("32,64,48": explicit wave sizes, the last one repeats), "compute_lanes" (1..4), "side_streams" (0: no chunk-wise overlap
+ * of a chain's nodes), "stream_priority" (0: no priority for the WSOLA search streams), "stream_chunks" (1..64 launches a
+ * stream is cut into along time), "trace" / "timing" (development output on stderr).  0 resp. -1 = automatic: the values
+ * DESIGN.md 2.1 measured for BASELINE's render shapes on a B200.  The NODEY_* environment variables of the same names are
+ * development overrides read once per run; an explicit setting wins over them. */
+int nodey_engine_set_schedule(nodey_engine* e, const char* key, const char* value);
 /* Memory policy of the runs started after the call (process wide; infra::Runner::release_products).  0 (default): every
  * link keeps its product until the next run, like the reference's channels (include/infra/runner.hpp:60-84), so any
  * product can be read back with nodey_engine_product.  1: a link lets go of its product once its consumer has enqueued

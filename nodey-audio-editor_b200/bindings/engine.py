@@ -54,6 +54,10 @@ def lib():
     L.nodey_engine_level_timings.argtypes = [vp] + [C.POINTER(i32)] * 4 + [C.POINTER(C.c_double)] * 3 + [i32]
     L.nodey_engine_encode_mp3.argtypes = [cp, vp, vp, i32, i32, i32, i64, i32, C.c_double, i32, C.POINTER(C.c_double)]
     L.nodey_engine_preview.argtypes = [vp, C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), i32]
+    L.nodey_engine_set_schedule.argtypes = [vp, cp, cp]
+    L.nodey_engine_export_plan.argtypes = [i32, C.c_double, i32, i64, C.POINTER(i64), C.POINTER(i64), i32, C.POINTER(C.c_double),
+                                           C.POINTER(i64), C.POINTER(C.c_double), i32]
+    L.nodey_engine_product_stamp.argtypes = [vp, i32, cp, C.POINTER(i32), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -119,6 +123,24 @@ def encode_mp3(path, data, fmt, rate, frame_size=1152, pts=0.0, kbps=320, time=0
     _check(lib().nodey_engine_encode_mp3(path.encode(), C.c_void_p(p0), C.c_void_p(p1) if p1 else None, fmt, rate, ch, frames,
                                          frame_size, pts, kbps, C.byref(t)))
     return t.value
+
+
+STAMP_START, STAMP_END_US, STAMP_START_FLOAT_US = 0, 1, 2
+
+
+def export_plan(stamp, origin, rate, runs, frames=None, time=0.0):
+    """do_export's bookkeeping for a stream cut into `runs` = [(frame size, count), ...] whose frames are stamped by rule
+    `stamp` (include/nodey_engine.h): (silence samples in front of every frame, every frame's stamp in seconds, time after)"""
+    n = len(runs)
+    rl = (C.c_int64 * max(n, 1))(*[r[0] for r in runs])
+    rc = (C.c_int64 * max(n, 1))(*[r[1] for r in runs])
+    total = sum(a * b for a, b in runs) if frames is None else frames
+    cap = sum(b for _, b in runs)
+    sil = (C.c_int64 * max(cap, 1))()
+    pts = (C.c_double * max(cap, 1))()
+    t = C.c_double(time)
+    k = _check(lib().nodey_engine_export_plan(stamp, origin, rate, total, rl, rc, n, C.byref(t), sil, pts, cap))
+    return list(sil[:k]), list(pts[:k]), t.value
 
 
 class Engine:
@@ -233,6 +255,19 @@ class Engine:
         a = (C.c_int64 * 4096)(); b = (C.c_int64 * 4096)()
         n = _check(lib().nodey_engine_product_runs(self.h, node_id, pin.encode(), a, b, 4096))
         return [(a[k], b[k]) for k in range(min(n, 4096))]
+
+    def set_schedule(self, **settings):
+        """infra::Runner::Schedule of this engine's runs, e.g. set_schedule(wave_pins=8, compute_lanes=2, stream_chunks=4,
+        wave_pattern="32,64")"""
+        for key, value in settings.items():
+            text = ",".join(str(v) for v in value) if isinstance(value, (list, tuple)) else str(int(value) if isinstance(value, bool) else value)
+            _check(lib().nodey_engine_set_schedule(self.h, key.encode(), text.encode()))
+
+    def product_stamp(self, node_id, pin):
+        """(rule, origin) by which the product's frames are stamped (STAMP_*)"""
+        st, og = C.c_int(), C.c_double()
+        _check(lib().nodey_engine_product_stamp(self.h, node_id, pin.encode(), C.byref(st), C.byref(og)))
+        return st.value, og.value
 
     def output(self):
         fmt, rate, ch = C.c_int(), C.c_int(), C.c_int()

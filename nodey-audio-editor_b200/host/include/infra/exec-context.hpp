@@ -28,6 +28,7 @@ namespace infra
 		const std::vector<int>* wave_begin = nullptr;
 		int level = 0;                    // graph level being executed
 		int lane = 0;                     // index of the stream inside the level
+		int stream_chunks = 0;            // Runner::Schedule::stream_chunks of the run (0: the nodes' default)
 
 		// the context of the calling thread (set by the Runner around process_payload / process_batch)
 		static Exec_context& current();

@@ -18,8 +18,31 @@ namespace infra
 	{
 	  public:
 
-		// builds one product per link, starts the worker thread and returns at once (reference semantics)
+		// Scheduling knobs of one run.  0 / -1 / empty = automatic: what the measurements behind DESIGN.md 2.1 chose on a
+		// 148-SM B200 for renders shaped like BASELINE's (waves of 32 source pins on three compute lanes once the sources
+		// have to be uploaded, one wave otherwise; 24 chunks along time).  A host with other shapes sets them here instead
+		// of through the process environment.
+		struct Schedule
+		{
+			int wave_pins = 0;                 // > 0: waves of that many source pins
+			std::vector<int> wave_pattern;     // explicit wave sizes (the last one repeats); wins over wave_pins
+			int compute_lanes = 0;             // 1..4 compute lanes the waves rotate over
+			int side_streams = -1;             // 0: nodes of a chain run on their lane's one stream (no chunk-wise overlap)
+			int stream_priority = -1;          // 0: the WSOLA search streams get no priority over the tails
+			int stream_chunks = 0;             // 1..64 launches / copies a stream is cut into along time
+			bool trace = false;                // per-step wall times on stderr (serialises the steps)
+			bool timing = false;               // host phases of the set-up on stderr
+			// development aid: NODEY_WAVE, NODEY_WAVES, NODEY_COMPUTE_LANES, NODEY_NO_SIDE_STREAMS, NODEY_NO_STREAM_PRIORITY,
+			// NODEY_ST_CHUNKS, NODEY_TRACE, NODEY_ENGINE_TIMING -- read ONCE per call, never inside a run
+			static Schedule from_environment();
+			// fields set in `over` (non-automatic) replace this one's
+			Schedule& overlay(const Schedule& over);
+		};
+
+		// builds one product per link, starts the worker thread and returns at once (reference semantics); the two-argument
+		// form of the reference schedules by Schedule::from_environment()
 		static std::unique_ptr<Runner> create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data);
+		static std::unique_ptr<Runner> create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data, const Schedule& schedule);
 
 		// sets every node's stop_source and joins the worker (src/infra/runner.cpp:53-63)
 		~Runner();
@@ -90,6 +113,7 @@ namespace infra
 		std::thread worker;
 		std::atomic<bool> done = false;
 		int device = -1;     // CUDA device of the creating thread; the worker thread binds to it
+		Schedule schedule;
 		std::vector<std::vector<Id_t>> levels;
 		std::map<Id_t, int> node_wave;          // which block of source pins feeds the node (see launch_threads)
 		std::vector<int> wave_begin;            // first source-pin position of every wave

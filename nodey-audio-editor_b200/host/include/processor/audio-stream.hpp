@@ -11,6 +11,7 @@
 #include "infra/processor.hpp"
 
 #include <cstdint>
+#include <memory>
 #include <mutex>
 #include <optional>
 #include <utility>
@@ -40,6 +41,56 @@ namespace processor
 	using Frame_runs = std::vector<std::pair<int64_t, int64_t>>;
 	Frame_runs uniform_frame_runs(int64_t frames, int64_t frame_size);
 	int64_t frame_runs_total(const Frame_runs& runs);
+
+	// How the producer of a stream stamped its frames.  The reference's sinks read PER-FRAME stamps (do_export encodes
+	// (int)((frame.pts * time_base - time) * rate) samples of silence before every frame, audio-io.cpp:833-839), and its
+	// nodes stamp in three different ways, so the rule travels with the stream:
+	enum Pts_stamp : int
+	{
+		STAMP_START = 0,           // decoder stamps and everything that forwards them: frame k starts at pts + at_k / rate
+		STAMP_END_US = 1,          // audio_amix / audio_bimix: the running END time, `time_seconds += nb / double(rate); pts =
+		                           // time_seconds * 1000000` truncated to whole microseconds (audio-amix.cpp:199-201,
+		                           // audio-bimix.cpp:188-191, App. C4)
+		STAMP_START_FLOAT_US = 2,  // SoundTouch nodes under the reference schedule: running START time handed on as a FLOAT of
+		                           // microseconds (audio-velocity.cpp:238-249, 313-318, App. C8): 64 us steps after 10 minutes
+		STAMP_LIST = 3             // frames pushed one by one by a node in the reference's style: every frame's own pts is kept
+	};
+
+	// Walks a stream's frames and returns what `frame.pts * av_q2d(frame.time_base)` is in the reference for each of them
+	// (plain double arithmetic, in the reference's order of operations).
+	class Frame_clock
+	{
+		int stamp; double origin; double rate; double t; int64_t at = 0;
+		std::shared_ptr<const std::vector<double>> list; size_t index = 0;
+	  public:
+		// origin: STAMP_START: pts of the first frame; STAMP_END_US: the node's time_seconds before its first frame (0);
+		// STAMP_START_FLOAT_US: the node's time_seconds at its first frame (= the first input frame's stamp)
+		Frame_clock(int stamp, double origin, int sample_rate, std::shared_ptr<const std::vector<double>> list = nullptr)
+			: stamp(stamp), origin(origin), rate((double)sample_rate), t(origin), list(std::move(list)) {}
+		double next(int64_t nb)
+		{
+			double pts;
+			switch (stamp)
+			{
+			case STAMP_END_US:
+				t += (double)nb / rate;
+				pts = (double)(int64_t)(t * 1000000) * (1 / (double)1000000);
+				break;
+			case STAMP_START_FLOAT_US:
+				pts = (double)(int64_t)(float)(t * 1000000) * (1 / (double)1000000);
+				t += (double)nb / rate;
+				break;
+			case STAMP_LIST:
+				if (list && index < list->size()) { pts = (*list)[index++]; break; }
+				[[fallthrough]];
+			default:
+				pts = origin + (double)at / rate;
+				break;
+			}
+			at += nb;
+			return pts;
+		}
+	};
 
 	// A producer that renders a stream in chunks along time says so here: once points[k].event has completed, frames
 	// [0, points[k].frames) hold their final values (ascending; the last point covers the whole stream).  A consumer that
@@ -76,7 +127,15 @@ namespace processor
 		int channels = 2;
 		int64_t frames = 0;                            // samples per channel
 		Frame_runs runs;                               // how the reference would have cut it into frames
-		double pts_seconds = 0.0;                      // start time of the first frame
+		double pts_seconds = 0.0;                      // stamp of the first frame as a consumer reads it
+		int stamp = STAMP_START;                       // how the producer stamped its frames (Pts_stamp)
+		double stamp_origin = 0.0;                     // Frame_clock origin for the END_US / START_FLOAT_US rules
+		std::shared_ptr<const std::vector<double>> frame_pts;      // STAMP_LIST: one stamp per frame
+		Frame_clock clock() const
+		{
+			const bool from_first = stamp == STAMP_START || stamp == STAMP_LIST;
+			return Frame_clock(stamp, from_first ? pts_seconds : stamp_origin, sample_rate, frame_pts);
+		}
 		mutable std::shared_ptr<infra::Device_event> ready;    // recorded after the producing kernels were enqueued
 		std::shared_ptr<const Stream_progress> progress;   // optional: chunk-wise completion (shared by the products of a batch)
 		std::shared_ptr<Lazy_gain> lazy;               // optional: see Lazy_gain
@@ -113,7 +172,7 @@ namespace processor
 		// frame-streaming compatibility mode: a consumer written against the reference's
 		// try_pop() sees the published device buffer cut into its frames (downloaded once, on first use); a
 		// producer written against try_push() has its frames collected and uploaded as one buffer at set_eof()
-		struct Frame_cursor { std::vector<uint8_t> host[2]; size_t run = 0; int64_t left = 0, done = 0; bool loaded = false; };
+		struct Frame_cursor { std::vector<uint8_t> host[2]; size_t run = 0; int64_t left = 0, done = 0; bool loaded = false; std::unique_ptr<Frame_clock> clock; };
 		std::unique_ptr<Frame_cursor> cursor;
 		std::vector<std::shared_ptr<const Audio_frame>> pushed;
 		void upload_pushed();

@@ -112,7 +112,20 @@ namespace processor
 		double pts_seconds = 0.0;
 		Frame_runs runs;
 		const void* plane[2] = {nullptr, nullptr};
+		int stamp = STAMP_START;            // how the producer stamped its frames (Audio_buffer::stamp / stamp_origin)
+		double stamp_origin = 0.0;
+		std::shared_ptr<const std::vector<double>> frame_pts;
+		Frame_clock clock() const
+		{
+			const bool from_first = stamp == STAMP_START || stamp == STAMP_LIST;
+			return Frame_clock(stamp, from_first ? pts_seconds : stamp_origin, sample_rate, frame_pts);
+		}
 	};
+	// Audio_output::do_export's bookkeeping over the frames of a stream (audio-io.cpp:826-839): before a frame,
+	// (int)((frame_begin - time) * sample_rate) samples of silence when that is positive; afterwards time = frame_begin +
+	// nb / rate.  frame_begin is the frame's own stamp (Frame_clock).  Returns `time` after the last frame.
+	struct Export_step { int64_t at; int nb; int silence; };
+	double export_steps(const Frame_runs& runs, int64_t frames, Frame_clock clock, int sample_rate, double time, std::vector<Export_step>& steps);
 	// true when libmp3lame could be bound (NODEY_LAME_LIB overrides the library name); why = the loader's message
 	bool mp3_encoder_available(std::string* why = nullptr);
 	// Audio_output::do_export's LAME call sequence over the stream's frames; `time` is Process_context::time going in,

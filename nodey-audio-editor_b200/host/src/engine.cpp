@@ -21,6 +21,7 @@ struct nodey_engine
 	std::string export_path;
 	size_t kbps = 320;        // the editor's default bit rate (src/frontend/app.cpp:595)
 	std::vector<int64_t> preview_chunks;     // chunk sizes the preview sink callback received, in order
+	Runner::Schedule schedule;               // explicit settings (nodey_engine_set_schedule); automatic where unset
 };
 
 namespace
@@ -157,7 +158,9 @@ int nodey_engine_run(nodey_engine* e)
 	if (!e) return fail(NODEY_ENGINE_E_INVALID, "null engine");
 	try
 	{
-		const bool timing = getenv("NODEY_ENGINE_TIMING") != nullptr;      // development: host-side phases of a run on stderr
+		// the environment's development overrides are read here, once per run; what the caller set explicitly wins
+		const Runner::Schedule schedule = Runner::Schedule::from_environment().overlay(e->schedule);
+		const bool timing = schedule.timing;      // development: host-side phases of a run on stderr
 		const auto t0 = std::chrono::steady_clock::now();
 		e->runner.reset();
 		const auto t1 = std::chrono::steady_clock::now();
@@ -176,7 +179,7 @@ int nodey_engine_run(nodey_engine* e)
 			e->sink_data = std::make_shared<std::any>(ctx);
 			node_data[out->second] = e->sink_data;
 		}
-		e->runner = Runner::create_and_run(e->graph, std::move(node_data));
+		e->runner = Runner::create_and_run(e->graph, std::move(node_data), schedule);
 		const auto t2 = std::chrono::steady_clock::now();
 		e->runner->wait();
 		if (timing)
@@ -270,6 +273,38 @@ int nodey_engine_product_runs(nodey_engine* e, int node_id, const char* pin, int
 	return (int)runs.size();
 }
 
+int nodey_engine_product_stamp(nodey_engine* e, int node_id, const char* pin, int* stamp, double* origin)
+{
+	if (!e || !pin) return fail(NODEY_ENGINE_E_INVALID, "null argument");
+	const auto audio = std::dynamic_pointer_cast<Audio_stream>(find_product(e, node_id, pin));
+	if (!audio || !audio->get()) return fail(NODEY_ENGINE_E_INVALID, "no audio product on that pin");
+	const auto b = audio->get();
+	if (stamp) *stamp = b->stamp;
+	if (origin) *origin = (b->stamp == STAMP_START || b->stamp == STAMP_LIST) ? b->pts_seconds : b->stamp_origin;
+	return 0;
+}
+
+int nodey_engine_export_plan(int stamp, double origin, int sample_rate, int64_t frames, const int64_t* run_len, const int64_t* run_count,
+							 int n_runs, double* time_inout, int64_t* silence, double* frame_pts, int cap)
+{
+	if (stamp < STAMP_START || stamp > STAMP_START_FLOAT_US || sample_rate < 1 || frames < 0 || n_runs < 0 || (n_runs > 0 && (!run_len || !run_count)))
+		return fail(NODEY_ENGINE_E_INVALID, "nodey_engine_export_plan: bad argument");
+	Frame_runs runs;
+	for (int k = 0; k < n_runs; k++) runs.emplace_back(run_len[k], run_count[k]);
+	std::vector<Export_step> steps;
+	const double end = export_steps(runs, frames, Frame_clock(stamp, origin, sample_rate), sample_rate, time_inout ? *time_inout : 0.0, steps);
+	if (time_inout) *time_inout = end;
+	Frame_clock clock(stamp, origin, sample_rate);
+	for (size_t k = 0; k < steps.size(); k++)
+	{
+		const double pts = clock.next(steps[k].nb);
+		if ((int)k >= cap) continue;
+		if (silence) silence[k] = steps[k].silence;
+		if (frame_pts) frame_pts[k] = pts;
+	}
+	return (int)steps.size();
+}
+
 int nodey_engine_output(nodey_engine* e, int* fmt, int* sample_rate, int* channels, int64_t* frames, double* pts_seconds, void** plane0,
 						void** plane1)
 {
@@ -324,6 +359,35 @@ int nodey_engine_level_timings(nodey_engine* e, int* wave, int* level, int* lane
 		if (start_ms) start_ms[k] = t.start_ms;
 	}
 	return (int)timings.size();
+}
+
+int nodey_engine_set_schedule(nodey_engine* e, const char* key, const char* value)
+{
+	if (!e || !key || !value) return fail(NODEY_ENGINE_E_INVALID, "null argument");
+	const std::string k = key;
+	const int v = atoi(value);
+	Runner::Schedule& s = e->schedule;
+	if (k == "wave_pins") s.wave_pins = std::max(0, v);
+	else if (k == "wave_pattern")
+	{
+		s.wave_pattern.clear();
+		for (const char* c = value; *c;)
+		{
+			const int size = atoi(c);
+			if (size < 1) return fail(NODEY_ENGINE_E_INVALID, "wave_pattern: sizes must be positive, e.g. \"32,64,48\"");
+			s.wave_pattern.push_back(size);
+			while (*c && *c != ',') c++;
+			if (*c == ',') c++;
+		}
+	}
+	else if (k == "compute_lanes") { if (v < 0 || v > 4) return fail(NODEY_ENGINE_E_INVALID, "compute_lanes: 0 (automatic) .. 4"); s.compute_lanes = v; }
+	else if (k == "side_streams") s.side_streams = v < 0 ? -1 : (v ? 1 : 0);
+	else if (k == "stream_priority") s.stream_priority = v < 0 ? -1 : (v ? 1 : 0);
+	else if (k == "stream_chunks") { if (v < 0 || v > 64) return fail(NODEY_ENGINE_E_INVALID, "stream_chunks: 0 (automatic) .. 64"); s.stream_chunks = v; }
+	else if (k == "trace") s.trace = v != 0;
+	else if (k == "timing") s.timing = v != 0;
+	else return fail(NODEY_ENGINE_E_INVALID, "unknown schedule key: " + k);
+	return 0;
 }
 
 int nodey_engine_set_export_kbps(nodey_engine* e, int kbps)

@@ -452,7 +452,8 @@ namespace infra
 	{
 		const auto T0 = std::chrono::steady_clock::now();
 		auto TP = T0;
-		const auto lap = [&](const char* what) { const auto n = std::chrono::steady_clock::now(); if (getenv("NODEY_ENGINE_TIMING")) fprintf(stderr, "  [resources] %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - TP).count()); TP = n; };
+		const bool timing = schedule.timing;
+		const auto lap = [&](const char* what) { const auto n = std::chrono::steady_clock::now(); if (timing) fprintf(stderr, "  [resources] %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(n - TP).count()); TP = n; };
 		levels = graph.topological_levels();   // = check_graph(), and the schedule
 		lap("levels");
 
@@ -498,26 +499,24 @@ namespace infra
 		// tracks (sequential per track), so waves of 32 source pins are the smallest that still pay; consecutive waves
 		// run on three rotating compute lanes so that a wave's sequential chains do not leave the SMs idle.  Measured on
 		// the 256-track render (tools/e2e_trace.py): 364 ms for 32-pin waves on three lanes, 379 ms for 32/64/64/64/32 on
-		// two, 437 ms for 32/96/128 on one; the 16.26 GB upload alone takes 294 ms.  NODEY_WAVE=n forces waves of n pins,
-		// NODEY_WAVES="a,b,c" an explicit pattern.
+		// two, 437 ms for 32/96/128 on one; the 16.26 GB upload alone takes 294 ms.  Schedule::wave_pins forces waves of n
+		// pins, Schedule::wave_pattern an explicit pattern.
 		const bool pipelined = upload >= (1u << 30);
-		int uniform = 0;
-		if (const char* env = getenv("NODEY_WAVE"); env && *env) uniform = std::max(1, atoi(env));
+		const int uniform = std::max(0, schedule.wave_pins);
 		int source_pins = 0;
 		if (!levels.empty())
 			for (const Id_t id : levels.front())
 				for (const auto& attribute : graph.nodes.at(id).processor->get_pin_attributes())
 					if (!attribute.is_input) source_pins++;
 		wave_begin.assign(1, 0);             // first pin position of every wave
-		if (const char* env = getenv("NODEY_WAVES"))
+		if (!schedule.wave_pattern.empty())
 		{
-			// development: explicit wave sizes "32,64,48" (the last one repeats)
-			int p = 0, size = 0;
-			const char* c = env;
+			// explicit wave sizes, e.g. {32, 64, 48} (the last one repeats)
+			int p = 0;
+			size_t k = 0;
 			while (p < source_pins)
 			{
-				if (*c) { size = std::max(1, atoi(c)); while (*c && *c != ',') c++; if (*c == ',') c++; }
-				if (size <= 0) break;
+				const int size = std::max(1, schedule.wave_pattern[std::min(k++, schedule.wave_pattern.size() - 1)]);
 				p += size;
 				if (p < source_pins) wave_begin.push_back(p);
 			}
@@ -646,7 +645,7 @@ namespace infra
 		int max_wave = 0;
 		for (const auto& [_, w] : node_wave) max_wave = std::max(max_wave, w);
 		int compute_lanes = max_wave > 1 ? 3 : (max_wave > 0 ? 2 : 1);
-		if (const char* env = getenv("NODEY_COMPUTE_LANES")) compute_lanes = std::clamp(atoi(env), 1, 4);
+		if (schedule.compute_lanes > 0) compute_lanes = std::clamp(schedule.compute_lanes, 1, 4);
 		constexpr int kMaxLanes = 5;
 		const int kLanes = 1 + compute_lanes;
 		nodey_stream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -670,12 +669,12 @@ namespace infra
 		{
 			if (nodey_stream_create(&lanes[k]) != NODEY_OK) { lanes[k] = nullptr; failed = true; break; }
 			Lane_registry::add(lanes[k], k >= 1);
-			if (k >= 1 && getenv("NODEY_NO_SIDE_STREAMS") == nullptr)
+			if (k >= 1 && schedule.side_streams != 0)
 			{
 				// sides 0 and 2 carry the sequential WSOLA searches of a resampler -> pitch -> tempo chain (nodes.cpp: the
 				// search runs on the stream after the producer's, the tails on the next one): high priority, so that a
 				// chain's next launch gets its SM slots ahead of the thousands of tail CTAs it competes with
-				static const bool prio = getenv("NODEY_NO_STREAM_PRIORITY") == nullptr || !*getenv("NODEY_NO_STREAM_PRIORITY");
+				const bool prio = schedule.stream_priority != 0;
 				for (int j = 0; j < kSides; j++)
 				{
 					const int rc = prio ? nodey_stream_create_priority(&sides[j][k], j % 2 == 0) : nodey_stream_create(&sides[j][k]);
@@ -698,7 +697,7 @@ namespace infra
 
 		std::any fallback;
 		// NODEY_TRACE=1: per-step wall time (host enqueue, then device drain) on stderr; serialises the steps
-		const bool trace = getenv("NODEY_TRACE") != nullptr;
+		const bool trace = schedule.trace;
 
 		// run one batch per node class of `ids` on lane `lane`
 		const auto run_group = [&](const std::vector<Id_t>& all_ids, int lane, int level_index) {
@@ -713,6 +712,7 @@ namespace infra
 				ctx.wave_begin = level_index == 0 ? &wave_begin : nullptr;
 				ctx.level = level_index;
 				ctx.lane = lane;
+				ctx.stream_chunks = schedule.stream_chunks;
 
 				std::vector<Processor::Batch_item> items;
 				for (const Id_t id : ids)
@@ -822,9 +822,49 @@ namespace infra
 		done = true;
 	}
 
+	Runner::Schedule Runner::Schedule::from_environment()
+	{
+		Schedule s;
+		const auto text = [](const char* name) -> const char* { const char* v = getenv(name); return v && *v ? v : nullptr; };
+		if (const char* v = text("NODEY_WAVE")) s.wave_pins = std::max(1, atoi(v));
+		if (const char* v = text("NODEY_WAVES"))
+			for (const char* c = v; *c;)
+			{
+				s.wave_pattern.push_back(std::max(1, atoi(c)));
+				while (*c && *c != ',') c++;
+				if (*c == ',') c++;
+			}
+		if (const char* v = text("NODEY_COMPUTE_LANES")) s.compute_lanes = std::clamp(atoi(v), 1, 4);
+		if (getenv("NODEY_NO_SIDE_STREAMS")) s.side_streams = 0;
+		if (text("NODEY_NO_STREAM_PRIORITY")) s.stream_priority = 0;
+		if (const char* v = text("NODEY_ST_CHUNKS")) s.stream_chunks = std::clamp(atoi(v), 1, 64);
+		s.trace = getenv("NODEY_TRACE") != nullptr;
+		s.timing = getenv("NODEY_ENGINE_TIMING") != nullptr;
+		return s;
+	}
+
+	Runner::Schedule& Runner::Schedule::overlay(const Schedule& over)
+	{
+		if (over.wave_pins > 0) wave_pins = over.wave_pins;
+		if (!over.wave_pattern.empty()) wave_pattern = over.wave_pattern;
+		if (over.compute_lanes > 0) compute_lanes = over.compute_lanes;
+		if (over.side_streams >= 0) side_streams = over.side_streams;
+		if (over.stream_priority >= 0) stream_priority = over.stream_priority;
+		if (over.stream_chunks > 0) stream_chunks = over.stream_chunks;
+		trace = trace || over.trace;
+		timing = timing || over.timing;
+		return *this;
+	}
+
 	std::unique_ptr<Runner> Runner::create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data)
 	{
+		return create_and_run(graph, std::move(node_data), Schedule::from_environment());
+	}
+
+	std::unique_ptr<Runner> Runner::create_and_run(const Graph& graph, std::map<Id_t, std::shared_ptr<std::any>> node_data, const Schedule& schedule)
+	{
 		auto runner = std::make_unique<Runner>();
+		runner->schedule = schedule;
 		runner->node_data = std::move(node_data);
 		runner->generate_processor_resources(graph);
 		if (nodey_get_device(&runner->device) != NODEY_OK) runner->device = -1;

@@ -149,11 +149,13 @@ namespace processor
 		const int bps = format_bytes(s.format);
 		const bool planar = format_is_planar(s.format);
 		const size_t stride = planar ? (size_t)bps : (size_t)bps * (size_t)s.channels;     // bytes per frame inside a plane
-		int64_t at = 0;
-		for (const auto& [len, count] : s.runs)
-			for (int64_t k = 0; k < count && at < s.frames; k++)
+		// the frames, their own stamps and the silence in front of each (audio-io.cpp:826-839)
+		std::vector<Export_step> steps;
+		const double end_time = export_steps(s.runs, s.frames, s.clock(), s.sample_rate, time, steps);
+		for (const Export_step& step : steps)
 			{
-				const int nb = (int)std::min<int64_t>(len, s.frames - at);
+				const int nb = step.nb;
+				const int64_t at = step.at;
 				if (!lame_param_set)      // audio-io.cpp:805-822: parameters come from the first frame
 				{
 					lame_param_set = true;
@@ -168,10 +170,7 @@ namespace processor
 						throw Runtime_error("Failed to initialize LAME parameters",
 											"Cannot set LAME parameters for encoding. Internal error may have occurred.", "");
 				}
-				// audio-io.cpp:826-836
-				const double frame_begin = s.pts_seconds + (double)at / (double)s.sample_rate;
-				const double frame_end = frame_begin + nb / (double)s.sample_rate;
-				const int silence_samples = static_cast<int>((frame_begin - time) * s.sample_rate);
+				const int silence_samples = step.silence;
 				if (silence_samples > 0)      // push_silence, :664-693: always two channels of 16-bit zeros
 				{
 					const int buffer_size = (int)(1.25 * silence_samples + 7200);
@@ -205,6 +204,23 @@ namespace processor
 					}
 					write_out(written, "Failed to encode audio frame", "Cannot encode the audio frame. Internal error may have occurred.");
 				}
+			}
+		return end_time;
+	}
+
+	double export_steps(const Frame_runs& runs, int64_t frames, Frame_clock clock, int sample_rate, double time, std::vector<Export_step>& steps)
+	{
+		int64_t at = 0;
+		for (const auto& [len, count] : runs)
+			for (int64_t k = 0; k < count && at < frames; k++)
+			{
+				const int nb = (int)std::min<int64_t>(len, frames - at);
+				// audio-io.cpp:833-838
+				const double frame_begin = clock.next(nb);
+				const double frame_end = frame_begin + nb / (double)sample_rate;
+				const double silence_time = frame_begin - time;
+				const int silence_samples = static_cast<int>(silence_time * sample_rate);      // push_silence, :664-667
+				steps.push_back({at, nb, silence_samples > 0 ? silence_samples : 0});
 				time = frame_end;
 				at += nb;
 			}

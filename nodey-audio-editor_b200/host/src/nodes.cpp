@@ -154,14 +154,14 @@ namespace processor
 			Stream_scope& operator=(const Stream_scope&) = delete;
 		};
 
-		// how many launches / copies a stream is cut into along time (1 = whole-track); NODEY_ST_CHUNKS overrides (read per
-		// call: bench.py times kernels one at a time with 1).  24: the 256 x 180 s render end to end 317 ms with 16 chunks,
+		// how many launches / copies a stream is cut into along time (1 = whole-track); Runner::Schedule::stream_chunks
+		// overrides (bench.py times kernels one at a time with 1).  24: the 256 x 180 s render end to end 317 ms with 16 chunks,
 		// 311 ms with 24, 32, 48 or 64 (what is exposed after the last uploaded byte is one chunk of every stage); with the
 		// sources resident 16..64 chunks are within 1 ms of each other (191 ms, 33 ms at 32 tracks)
 		int stream_chunk_count()
 		{
-			const char* env = getenv("NODEY_ST_CHUNKS");
-			return env && *env ? std::clamp(atoi(env), 1, 64) : 24;
+			const int set = Exec_context::current().stream_chunks;
+			return set > 0 ? std::clamp(set, 1, 64) : 24;
 		}
 
 		std::shared_ptr<Audio_buffer> new_buffer(const std::shared_ptr<infra::Device_block>& block, void* p0, void* p1, int fmt, int rate,
@@ -170,6 +170,22 @@ namespace processor
 			auto b = std::make_shared<Audio_buffer>();
 			b->block = block; b->plane[0] = p0; b->plane[1] = p1; b->format = fmt; b->sample_rate = rate; b->channels = ch;
 			b->frames = frames; b->runs = std::move(runs); b->pts_seconds = pts;
+			return b;
+		}
+
+		// frames forwarded with their stamps (gain, split: `out_frame->pts = src_frame.pts`, audio-vol.cpp:170-171)
+		std::shared_ptr<Audio_buffer> inherit_stamps(std::shared_ptr<Audio_buffer> b, const Audio_buffer& in)
+		{
+			b->stamp = in.stamp; b->stamp_origin = in.stamp_origin; b->frame_pts = in.frame_pts;
+			return b;
+		}
+
+		// audio_amix / audio_bimix: running END time from 0 in whole microseconds (App. C3 / C4); pts_seconds = the first stamp
+		std::shared_ptr<Audio_buffer> end_time_stamps(std::shared_ptr<Audio_buffer> b)
+		{
+			b->stamp = STAMP_END_US; b->stamp_origin = 0.0;
+			b->pts_seconds = 0.0;
+			if (!b->runs.empty() && b->frames > 0) b->pts_seconds = b->clock().next(std::min<int64_t>(b->runs.front().first, b->frames));
 			return b;
 		}
 
@@ -346,6 +362,14 @@ namespace processor
 		}
 		auto b = new_buffer(block, block->ptr, planar2 ? (char*)block->ptr + plane : nullptr, first.format, first.sample_rate, first.channels,
 							total, std::move(runs), first.pts_seconds);
+		{
+			// every pushed frame keeps its own stamp (a node in the reference's style forwards or makes them as it likes)
+			auto stamps = std::make_shared<std::vector<double>>();
+			for (const auto& f : pushed)
+				if (f->nb_samples != 0) stamps->push_back(f->pts_seconds);
+			if (!stamps->empty()) b->pts_seconds = stamps->front();
+			b->stamp = STAMP_LIST; b->frame_pts = std::move(stamps);
+		}
 		auto ev = std::make_shared<infra::Device_event>();
 		ev->record(cur_stream());
 		b->ready = std::move(ev);
@@ -376,6 +400,7 @@ namespace processor
 			}
 			abi(nodey_stream_synchronize(cur_stream()), "frame download");
 			cur.loaded = true;
+			cur.clock = std::make_unique<Frame_clock>(b->clock());
 			cur.run = 0;
 			cur.left = b->runs.empty() ? 0 : b->runs[0].second;
 		}
@@ -388,7 +413,7 @@ namespace processor
 		const int64_t n = std::min<int64_t>(b->runs[cur.run].first, b->frames - cur.done);
 		auto f = std::make_shared<Audio_frame>();
 		f->format = b->format; f->sample_rate = b->sample_rate; f->channels = b->channels; f->nb_samples = n;
-		f->pts_seconds = b->pts_seconds + (double)cur.done / (double)b->sample_rate;
+		f->pts_seconds = cur.clock->next(n);           // the frame's own stamp, by the producer's rule
 		for (int c = 0; c < (planar2 ? 2 : 1); c++)
 			f->data[c].assign(cur.host[c].begin() + (size_t)cur.done * sample, cur.host[c].begin() + (size_t)(cur.done + n) * sample);
 		cur.done += n;
@@ -812,6 +837,7 @@ namespace processor
 			Host_stream hs;
 			hs.format = buffer->format; hs.sample_rate = buffer->sample_rate; hs.channels = buffer->channels;
 			hs.frames = buffer->frames; hs.pts_seconds = buffer->pts_seconds; hs.runs = buffer->runs;
+			hs.stamp = buffer->stamp; hs.stamp_origin = buffer->stamp_origin; hs.frame_pts = buffer->frame_pts;
 			const bool planar2 = format_is_planar(buffer->format) && buffer->channels == 2;
 			const size_t plane_bytes = buffer->plane_bytes();
 			std::vector<unsigned char> host[2];
@@ -838,23 +864,40 @@ namespace processor
 			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
 			std::ofstream f(ctx->export_path, std::ios::binary);
 			if (!f) throw Runtime_error("Cannot write output file", "The export path could not be opened for writing.", ctx->export_path);
-			// do_export's pts rule (audio-io.cpp:833-839): before a frame, (int)((frame_begin - time) * sample_rate) samples of
-			// silence are encoded; `time` starts at 0 and then follows the frame ends, so what matters is the stream's
-			// first pts -- including the end-time stamps of amix / bimix (App. C4), which make the reference prepend one
-			// frame of silence to their exports
-			const int lead = std::max(0, (int)(buffer->pts_seconds * (double)buffer->sample_rate));
-			const std::vector<float> silence((size_t)lead * (size_t)buffer->channels, 0.0f);
-			const uint32_t data_bytes = (uint32_t)((host.size() + silence.size()) * sizeof(float));
+			// do_export's pts rule (audio-io.cpp:833-839): before EVERY frame, (int)((frame_begin - time) * sample_rate) samples of
+			// silence are encoded when that is positive; `time` then follows the frame ends.  frame_begin is the frame's own
+			// stamp, by its producer's rule (Frame_clock): the end-time stamps of amix / bimix (App. C4) make the reference
+			// prepend almost one frame of silence to their exports (1023 samples in front of 1024-sample frames: the stamp is
+			// truncated to microseconds) and another len_k - len_{k-1} samples wherever their frame size grows
+			std::vector<Export_step> steps;
+			const double end_time = export_steps(buffer->runs, buffer->frames, buffer->clock(), buffer->sample_rate, ctx->time ? ctx->time->load() : 0.0, steps);
+			int64_t silence_total = 0;
+			for (const Export_step& step : steps) silence_total += step.silence;
+			const uint32_t data_bytes = (uint32_t)((host.size() + (size_t)silence_total * (size_t)buffer->channels) * sizeof(float));
 			const uint16_t tag = 3, ch = (uint16_t)buffer->channels, bits = 32, align = (uint16_t)(4 * buffer->channels);
 			const uint32_t rate = (uint32_t)buffer->sample_rate, byte_rate = rate * align, riff = 36 + data_bytes, fmt_size = 16;
 			f.write("RIFF", 4); f.write((const char*)&riff, 4); f.write("WAVEfmt ", 8); f.write((const char*)&fmt_size, 4);
 			f.write((const char*)&tag, 2); f.write((const char*)&ch, 2); f.write((const char*)&rate, 4); f.write((const char*)&byte_rate, 4);
 			f.write((const char*)&align, 2); f.write((const char*)&bits, 2); f.write("data", 4); f.write((const char*)&data_bytes, 4);
-			f.write((const char*)silence.data(), (std::streamsize)(silence.size() * sizeof(float)));
-			f.write((const char*)host.data(), (std::streamsize)(host.size() * sizeof(float)));
+			std::vector<float> silence;
+			for (const Export_step& step : steps)
+			{
+				if (step.silence > 0)
+				{
+					silence.assign((size_t)step.silence * (size_t)buffer->channels, 0.0f);
+					f.write((const char*)silence.data(), (std::streamsize)(silence.size() * sizeof(float)));
+				}
+				f.write((const char*)(host.data() + (size_t)step.at * (size_t)buffer->channels), (std::streamsize)((size_t)step.nb * (size_t)buffer->channels * sizeof(float)));
+			}
+			if (ctx->time) ctx->time->store(end_time);      // `time` ends at the end of the last frame (audio-io.cpp:838)
+			return;
 		}
-		// `time` ends at the end of the last frame (audio-io.cpp:838)
-		if (ctx->time) ctx->time->store(std::max(0.0, buffer->pts_seconds) + (double)buffer->frames / (double)buffer->sample_rate);
+		// no export: `time` still ends where the last frame does
+		if (ctx->time)
+		{
+			std::vector<Export_step> steps;
+			ctx->time->store(export_steps(buffer->runs, buffer->frames, buffer->clock(), buffer->sample_rate, ctx->time->load(), steps));
+		}
 	}
 
 	// ---------------------------------------------------------------------------------------------
@@ -912,7 +955,7 @@ namespace processor
 				for (size_t k = 0; k < items.size(); k++)
 				{
 					const Audio_buffer& in = *ins[k];
-					auto b = new_buffer(nullptr, nullptr, nullptr, in.format, in.sample_rate, in.channels, in.frames, in.runs, in.pts_seconds);
+					auto b = inherit_stamps(new_buffer(nullptr, nullptr, nullptr, in.format, in.sample_rate, in.channels, in.frames, in.runs, in.pts_seconds), in);
 					b->lazy = std::make_shared<Lazy_gain>();
 					b->lazy->source = ins[k];
 					b->lazy->gain = static_cast<Audio_vol*>(items[k].processor)->volume;
@@ -949,8 +992,8 @@ namespace processor
 		for (size_t k = 0; k < items.size(); k++)
 		{
 			const Audio_buffer& in = *ins[k];
-			publish(*items[k].output, "output", new_buffer(arena.block, planes[k].first, planes[k].second, in.format, in.sample_rate, in.channels,
-															   in.frames, in.runs, in.pts_seconds));
+			publish(*items[k].output, "output", inherit_stamps(new_buffer(arena.block, planes[k].first, planes[k].second, in.format, in.sample_rate,
+																			  in.channels, in.frames, in.runs, in.pts_seconds), in));
 		}
 		return true;
 	}
@@ -1161,8 +1204,13 @@ namespace processor
 						const Entry& e = all[first + k];
 						// App. C8 (same switch): the reference stamps its frames with (int64_t)(float)(seconds * 1e6) microseconds
 						// (construct_audio_frame_float takes `float time_us`, audio-velocity.cpp:234-250); canonical: the exact start
-						const double pts = ref_schedule ? (double)(int64_t)(float)(e.in->pts_seconds * 1000000) / 1000000.0 : e.in->pts_seconds;
-						auto b = new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m, out_runs, pts);
+						// -- for EVERY frame, from a running double of seconds that starts at the first input frame's stamp (:388, :313-318)
+						auto b = new_buffer(arena.block, out_base + k * out_stride, nullptr, FMT_FLT, rate_hz, ch, m, out_runs, e.in->pts_seconds);
+						if (ref_schedule)
+						{
+							b->stamp = STAMP_START_FLOAT_US; b->stamp_origin = e.in->pts_seconds;
+							b->pts_seconds = Frame_clock(STAMP_START_FLOAT_US, e.in->pts_seconds, rate_hz).next(0);
+						}
 						if (done) { b->ready = done; b->progress = progress; }
 						publish(*items[e.item].output, "output", b);
 					}
@@ -1438,8 +1486,7 @@ namespace processor
 		{
 			// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
 			Frame_runs out_runs = job.plan->out_runs;
-			const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;
-			auto buffer = new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), pts);
+			auto buffer = end_time_stamps(new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), 0.0));
 			if (progress && !progress->points.empty()) { buffer->ready = progress->points.back().event; buffer->progress = progress; }
 			publish(output, "output", buffer);
 		}
@@ -1732,8 +1779,8 @@ namespace processor
 		float* out_l = (float*)block->ptr;
 		float* out_r = (float*)((char*)block->ptr + plane);
 		if (total > 0) abi(nodey_bimix(out_l, out_r, rl.l, rl.r, len_l, rr.l, rr.r, len_r, bias, total, cur_stream()), "Audio bimix");
-		const double pts = out_runs.empty() ? 0.0 : (double)out_runs.front().first / 48000.0;     // App. C3: starts at 0, C4: end time
-		publish(output, "output", new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), pts));
+		// App. C3: the running time starts at 0; C4: frames carry their END time
+		publish(output, "output", end_time_stamps(new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), 0.0)));
 	}
 
 	// ---------------------------------------------------------------------------------------------
@@ -1892,8 +1939,8 @@ namespace processor
 		if (in->frames > 0) abi(nodey_split(l, r, in->plane[0], in->plane[1], in->format, in->frames, cur_stream()), "Channel split");
 		auto ev = std::make_shared<infra::Device_event>();
 		ev->record(cur_stream());
-		auto bl = new_buffer(arena.block, l, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds);
-		auto br = new_buffer(arena.block, r, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds);
+		auto bl = inherit_stamps(new_buffer(arena.block, l, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds), *in);
+		auto br = inherit_stamps(new_buffer(arena.block, r, nullptr, in->format, in->sample_rate, 1, in->frames, in->runs, in->pts_seconds), *in);
 		bl->ready = ev; br->ready = ev;
 		publish(output, "output_l", bl);
 		publish(output, "output_r", br);

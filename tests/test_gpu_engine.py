@@ -277,6 +277,37 @@ def test_config5_graph_in_waves_on_several_lanes(eng_gpu, orc, env, monkeypatch)
     assert (np.abs(spec - ref_spec) <= 1e-5 * np.maximum(peak, 1e-30)).all()
 
 
+@pytest.mark.parametrize("settings,waves,lanes", [
+    (dict(wave_pins=16), 2, 2),
+    (dict(wave_pattern=[16, 8, 8], compute_lanes=3), 3, 3),
+    (dict(wave_pins=8, compute_lanes=1, stream_chunks=3, side_streams=0), 4, 1),
+    (dict(wave_pattern="8,24", stream_priority=0, stream_chunks=64), 2, 2)],
+    ids=["two-waves", "three-waves-three-lanes", "four-waves-one-lane-no-side-streams", "uneven-waves-64-chunks"])
+def test_schedule_set_through_the_api(eng_gpu, orc, settings, waves, lanes, monkeypatch):
+    """infra::Runner::Schedule through nodey_engine_set_schedule: the same knobs as the development environment
+    variables, per engine; an explicit setting wins over the environment.  No schedule may change a bit of the result."""
+    from oracle import graph_oracle as G
+    monkeypatch.setenv("NODEY_WAVE", "1000000")       # would make it one wave: must lose against the explicit setting
+    n = 44100 + 333
+    tracks = [orc.synth_f32(n, 2, 44100, t) for t in range(32)]
+    p, ids = eng_gpu.config5_project(32, [G.track_gain(t) for t in range(32)])
+    e = eng_gpu.Engine(p.json())
+    e.set_schedule(**settings)
+    for t, x in enumerate(tracks):
+        e.bind_source(t, x, FMT_FLT, 44100)
+    ref_bus, _ = G.render(tracks, threads=8, spectrum=False)
+    e.run()
+    assert_bit_equal(e.output().numpy(), ref_bus, f"master bus with {settings}")
+    steps = e.level_timings()
+    assert len({s["wave"] for s in steps}) == waves
+    assert len({s["lane"] for s in steps if s["level"] > 0}) == lanes
+    with pytest.raises(eng_gpu.EngineError, match="unknown schedule key"):
+        e.set_schedule(no_such_knob=1)
+    with pytest.raises(eng_gpu.EngineError, match="compute_lanes"):
+        e.set_schedule(compute_lanes=9)
+    e.close()
+
+
 def test_device_resident_render_of_128_tracks_takes_two_waves_and_matches(eng_gpu, orc, nd):
     """from 128 source pins on, a render whose sources are already in HBM runs as two half-size waves on two lanes (the
     default the bench uses at 256 tracks): same bits as the oracle graph and as the single-wave schedule"""

@@ -1,7 +1,8 @@
 """GPU: the PCM / WAV edges of the render.  audio_input reads canonical RIFF/WAVE files named by
 the project's file_path (PCM 16 bit and IEEE float; the reference decodes with libavformat, 1024-sample packets for
-WAV PCM); audio_output's export writes a float WAV and keeps do_export's pts rule: (int)(first pts * sample_rate)
-frames of silence in front of the stream (src/processor/audio-io.cpp:833-839)."""
+WAV PCM); audio_output's export writes a float WAV and keeps do_export's pts rule: (int)((frame stamp - time) * sample_rate)
+samples of silence in front of every frame where that is positive (src/processor/audio-io.cpp:833-839), with the stamps
+the producing node would have put on its frames (tests/test_export_stamps.py has the arithmetic)."""
 import struct
 import wave
 
@@ -56,10 +57,62 @@ def test_wav_sources_through_gain_and_float_wav_export(eng_gpu, orc, tmp_path):
     assert_bit_equal(got.numpy(), np.stack([rl, rr]), "mix of the two files")
     y, rate = _read_float_wav(str(tmp_path / "out.wav"))
     assert rate == 48000
-    # amix stamps frames with their END time (App. C4), so the reference's export prepends one frame of silence
+    # amix stamps frames with their END time (App. C4), truncated to whole microseconds (audio-amix.cpp:199-201): 1024 / 48000 s
+    # = 21333.33 us -> 21333 us, and do_export's (int)((frame_begin - 0) * 48000) = (int)1023.98 -> the reference's export starts
+    # with 1023 samples of silence, not 1024
+    assert got.pts == 21333 * (1 / 1000000.0)
     lead = int(got.pts * 48000)
-    assert lead == 1024 and not y[:lead].any()
-    assert_bit_equal(y[lead:], np.ascontiguousarray(np.stack([rl, rr]).T), "exported WAV")
+    assert lead == 1023 and not y[:lead].any()
+    assert e.product_stamp(mix, "output") == (eng_gpu.STAMP_END_US, 0.0)
+    # ... and more silence wherever amix's frame size grows: after the last (short) input frames come the flush frames of
+    # 1152 samples (audio-amix.cpp:195), whose end-time stamps run ahead of the export's `time` (audio-io.cpp:833-839)
+    from test_export_stamps import frames_of, ref_export, ref_stamps_end_us
+    sizes = frames_of(e.product_runs(mix, "output"))
+    silence, _ = ref_export(ref_stamps_end_us(sizes, 48000), sizes, 48000)
+    assert silence[0] == lead
+    mixed = np.ascontiguousarray(np.stack([rl, rr]).T)
+    parts, at = [], 0
+    for nb, n0 in zip(sizes, silence):
+        parts += [np.zeros((n0, 2), np.float32), mixed[at:at + nb]]
+        at += nb
+    assert at == mixed.shape[0]
+    assert_bit_equal(y, np.concatenate(parts), "exported WAV")
+
+
+def test_export_of_an_amix_whose_frame_size_grows(eng_gpu, orc, tmp_path):
+    """audio_amix cuts its output into frames as long as the shortest live input frame (audio-amix.cpp:190-195); when a
+    1024-sample input ends before an 1152-sample one the end-time stamps jump ahead of the export's `time`, and do_export
+    encodes the difference as silence IN THE MIDDLE of the stream (audio-io.cpp:833-839) -- reproduced frame by frame."""
+    from test_export_stamps import frames_of, ref_export, ref_stamps_end_us
+    short = make_input(orc, FMT_FLT, 48000 // 3, 2, rate=48000, track=3)
+    long_ = make_input(orc, FMT_FLT, 48000, 2, rate=48000, track=4)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    mix = p.add("audio_amix", eng_gpu.amix_info([0.7, 0.4]))
+    out = p.add("audio_output")
+    p.link(src, "output_0", mix, "input_1"); p.link(src, "output_1", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_export_path(str(tmp_path / "grow.wav"))
+    e.bind_source(0, short, FMT_FLT, 48000, frame_size=1024)
+    e.bind_source(1, long_, FMT_FLT, 48000, frame_size=1152)
+    e.run()
+    rl, rr = orc.amix([orc.make_track(short, FMT_FLT, 48000, frame_size=1024), orc.make_track(long_, FMT_FLT, 48000, frame_size=1152)], [0.7, 0.4])
+    mixed = np.ascontiguousarray(np.stack([rl, rr]).T)
+    assert_bit_equal(e.output().numpy(), np.stack([rl, rr]), "mix")
+    runs = e.product_runs(mix, "output")
+    sizes = frames_of(runs)
+    assert sizes[0] == 1024 and 1152 in sizes
+    silence, _ = ref_export(ref_stamps_end_us(sizes, 48000), sizes, 48000)
+    assert silence[0] == 1023 and sum(1 for n in silence if n) >= 2, "lead-in and at least the growth step"
+    assert eng_gpu.export_plan(eng_gpu.STAMP_END_US, 0.0, 48000, runs)[0] == silence
+    parts, at = [], 0
+    for nb, n in zip(sizes, silence):
+        parts.append(np.zeros((n, 2), np.float32))
+        parts.append(mixed[at:at + nb])
+        at += nb
+    y, rate = _read_float_wav(str(tmp_path / "grow.wav"))
+    assert rate == 48000
+    assert_bit_equal(y, np.concatenate(parts), "exported WAV with the reference's silence")
 
 
 def test_export_pads_a_late_stream_with_silence(eng_gpu, orc, tmp_path):

@@ -60,3 +60,9 @@ def test_frame_node_fan_out_and_resampled_input(eng_gpu, orc):
     assert_bit_equal(e.output().numpy(), ref, "fan-out link a")
     assert_bit_equal(e.product(fg, "output").numpy(), ref, "frame node product (first link)")
     assert e.product_runs(fg, "output") == e.product_runs(mix, "output")
+    # the frames travel with their own stamps: amix's end-time stamps (whole microseconds, App. C4) come out of the frame
+    # node and of the gain behind it unchanged (`out_frame->pts = src_frame.pts`, audio-vol.cpp:170)
+    first = int(1152 / 48000.0 * 1000000) * (1 / 1000000.0)
+    assert e.product(mix, "output").pts == first and e.product(fg, "output").pts == first and e.output().pts == first
+    assert e.product_stamp(mix, "output") == (eng_gpu.STAMP_END_US, 0.0)
+    assert e.product_stamp(ga, "output")[0] == 3     # per-frame list kept from the pushed frames

@@ -310,7 +310,7 @@ def test_reference_schedule_switch_on_the_nodes(eng_gpu, orc):  # noqa: C901
         out = p.add("audio_output")
         p.link(src, "output_0", pm, "input"); p.link(pm, "output", vm, "input"); p.link(vm, "output", out, "input")
         e = eng_gpu.Engine(p.json())
-        e.bind_source(0, x, FMT_FLT_, sr)
+        e.bind_source(0, x, FMT_FLT_, sr, pts=0.37)
         e.run()
         text = json.loads(e.serialize())
         return e, pm, vm, text
@@ -323,8 +323,15 @@ def test_reference_schedule_switch_on_the_nodes(eng_gpu, orc):  # noqa: C901
     assert_bit_equal(e.output().numpy(), y2, "tempo node, reference schedule")
     assert [s for s, c in e.product_runs(vm, "output") for _ in range(c)] == list(s2)
     assert text["nodes"][str(pm)]["info"]["reference_schedule"] is True
+    # App. C8 (same switch): frames stamped through a float of microseconds, from a running time that starts at the first
+    # input frame's stamp (audio-velocity.cpp:238-249, 313-318, 388); the tempo node starts from the pitch node's first stamp
+    first = int(np.float32(0.37 * 1000000)) * (1 / 1000000.0)
+    assert e.product_stamp(pm, "output") == (eng_gpu.STAMP_START_FLOAT_US, 0.37) and e.product(pm, "output").pts == first
+    second = int(np.float32(first * 1000000)) * (1 / 1000000.0)
+    assert e.product_stamp(vm, "output") == (eng_gpu.STAMP_START_FLOAT_US, first) and e.output().pts == second
     e.close()
     e, pm, vm, text = render(False)
+    assert e.product_stamp(vm, "output") == (eng_gpu.STAMP_START, 0.37) and e.output().pts == 0.37
     c1, _, _ = orc.soundtouch(x, sr, 1.0, orc.pitch_node_factor(3.0), 1152)
     c2, _, _ = orc.soundtouch(c1, sr, 1.25, orc.velocity_node_pitch(1.25, True), 1152)
     assert_bit_equal(e.output().numpy(), c2, "canonical render")
