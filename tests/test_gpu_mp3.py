@@ -66,11 +66,20 @@ def test_amix_output_goes_to_the_planar_entry_point_after_one_frame_of_silence(e
     rec = records(str(tmp_path / "mix.mp3"))
     runs = e.product_runs(mix, "output")
     frames = [l for l, c in runs for _ in range(c)]
-    # amix stamps frames with their END time (App. C4): the reference's export starts with one frame of silence
-    assert rec[0][:2] == (1, int(got.pts * 48000)) and rec[0][1] == frames[0]
-    assert [(k, m) for k, m, _ in rec[1:]] == [(6, m) for m in frames]
+    # amix stamps frames with their END time (App. C4): the reference's export starts with one frame of silence, and encodes
+    # more silence wherever amix's frame size grows (the last short frame is followed by 1152-sample flush frames whose
+    # stamps run ahead of the export's `time`, audio-io.cpp:833-839) -- tests/test_export_stamps.py has the arithmetic
+    from test_export_stamps import ref_export, ref_stamps_end_us
+    silence, _ = ref_export(ref_stamps_end_us(frames, 48000), frames, 48000)
+    assert rec[0][:2] == (1, int(got.pts * 48000)) and rec[0][1] == frames[0] == silence[0]
+    want = []
+    for m, quiet in zip(frames, silence):
+        want += ([(1, quiet)] if quiet else []) + [(6, m)]
+    assert [(k, m) for k, m, _ in rec] == want
     at = 0
-    for (_, m, s) in rec[1:]:
+    for (k, m, s) in rec:
+        if k == 1:
+            continue
         assert close(s, scale(rl[at:at + m]).sum() + scale(rr[at:at + m]).sum())
         at += m
     assert "set_brate 320" in lame()                     # the editor's default bit rate

@@ -4,7 +4,7 @@
 set -u
 tag=${1:-dev}; shift || true
 out=gpurun_out; mkdir -p $out
-timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 4 $out/${tag}_pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 4 $out/${tag}_pytest_gpu.log
 for what in "$@"; do
   case $what in
     big)   timeout 600 python tools/big_render.py > $out/${tag}_big_render.json 2> $out/${tag}_big_render.err; echo "big rc=$?"; tail -c 1500 $out/${tag}_big_render.json; tail -n 5 $out/${tag}_big_render.err;;
