@@ -160,10 +160,15 @@ __device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&acc)[KT], c
     }
     float y[(KT + 3) & ~3];
     if (MODE == 0) {
+        if constexpr (KT == 2) {
+            const float2 t = *reinterpret_cast<const float2*>(yq);       // rows in groups of two words (tds_ktp)
+            y[0] = t.x; y[1] = t.y;
+        } else {
 #pragma unroll
-        for (int s = 0; s < KT; s += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(yq + s);
-            y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
+            for (int s = 0; s < KT; s += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(yq + s);
+                y[s] = t.x; y[s + 1] = t.y; y[s + 2] = t.z; y[s + 3] = t.w;
+            }
         }
     }
 #pragma unroll
@@ -179,8 +184,84 @@ __device__ __forceinline__ void tds_group(float (&w)[2][KT], float (&acc)[KT], c
 }
 
 // rows of the mid buffer are stored in groups of KT steps padded to a multiple of four words, so that every group
-// starts 16-byte aligned whatever KT is
-template <int KT> __host__ __device__ constexpr int tds_ktp() { return (KT + 3) & ~3; }
+// starts 16-byte aligned whatever KT is (KT = 2: groups of two words, read as 64-bit pairs)
+template <int KT> __host__ __device__ constexpr int tds_ktp() { return KT == 2 ? 2 : (KT + 3) & ~3; }
+static int tds_ktp_rt(int KT) { return KT == 2 ? 2 : (KT + 3) & ~3; }
+
+// Small-batch variant for KT = 4 (four CTAs per track): with one or two warps per scheduler a group's window block and mid
+// buffer words were used a few multiplies after their loads were issued and the warp sat out the shared-memory latency
+// every 37 instructions.  Here both ride one group ahead in registers: a ring of THREE window blocks and two mid-buffer
+// groups (24 registers in all); six groups per iteration bring the ring back to its start, so every index is static.
+// WI = ring slot of the current block, YI = slot of the current mid-buffer group.
+template <int KT, int MODE, int WI, int YI>
+__device__ __forceinline__ void tds_group_ahead(float (&w)[3][KT], float (&y)[2][KT], float (&acc)[KT], const float* __restrict__ xahead, int sk,
+                                                const float* __restrict__ ynext)
+{
+    constexpr int NXT = (WI + 1) % 3, AH = (WI + 2) % 3;
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        const float v = xahead[k * sk];
+        w[AH][k] = MODE == 0 ? v : __fmul_rn(v, v);
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int s = 0; s < KT; s += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(ynext + s);
+            y[YI ^ 1][s] = t.x; y[YI ^ 1][s + 1] = t.y; y[YI ^ 1][s + 2] = t.z; y[YI ^ 1][s + 3] = t.w;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < KT; s++) {
+#pragma unroll
+        for (int k = 0; k < KT; k++) {
+            const int idx = s + k;
+            const float x = idx < KT ? w[WI][idx] : w[NXT][idx - KT];
+            acc[k] = __fadd_rn(acc[k], MODE == 0 ? __fmul_rn(x, y[YI][s]) : x);
+        }
+    }
+}
+
+// block G + 2 and mid-buffer group G + 1 are loaded while group G is summed: the staged window holds Q / KT + 3 blocks per
+// thread and a mid-buffer row eight spare words, so the loads of the last groups stay inside the arrays (values unused)
+template <int KT, int MODE, int SK>
+__device__ __forceinline__ void tds_lane_sums_ahead(const float* __restrict__ xb, int sk_rt, const float* __restrict__ yp, int Q, float (&acc)[KT])
+{
+    static_assert(KT % 4 == 0, "mid-buffer groups are read as 128-bit words");
+    const int sk = SK ? SK : sk_rt;
+    float w[3][KT], y[2][KT];
+#pragma unroll
+    for (int k = 0; k < KT; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+        const float v0 = xb[k * sk], v1 = xb[k * sk + 1];
+        w[0][k] = MODE == 0 ? v0 : __fmul_rn(v0, v0);
+        w[1][k] = MODE == 0 ? v1 : __fmul_rn(v1, v1);
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int s = 0; s < KT; s += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(yp + s);
+            y[0][s] = t.x; y[0][s + 1] = t.y; y[0][s + 2] = t.z; y[0][s + 3] = t.w;
+        }
+    }
+    const int NG = Q / KT;                          // KT divides Q (Q is a multiple of four)
+    int G = 0;
+#pragma unroll 1
+    for (; G + 6 <= NG; G += 6) {
+        tds_group_ahead<KT, MODE, 0, 0>(w, y, acc, xb + G + 2, sk, yp + (G + 1) * KT);
+        tds_group_ahead<KT, MODE, 1, 1>(w, y, acc, xb + G + 3, sk, yp + (G + 2) * KT);
+        tds_group_ahead<KT, MODE, 2, 0>(w, y, acc, xb + G + 4, sk, yp + (G + 3) * KT);
+        tds_group_ahead<KT, MODE, 0, 1>(w, y, acc, xb + G + 5, sk, yp + (G + 4) * KT);
+        tds_group_ahead<KT, MODE, 1, 0>(w, y, acc, xb + G + 6, sk, yp + (G + 5) * KT);
+        tds_group_ahead<KT, MODE, 2, 1>(w, y, acc, xb + G + 7, sk, yp + (G + 6) * KT);
+    }
+    const int r = NG - G;
+    if (r > 0) tds_group_ahead<KT, MODE, 0, 0>(w, y, acc, xb + G + 2, sk, yp + (G + 1) * KT);
+    if (r > 1) tds_group_ahead<KT, MODE, 1, 1>(w, y, acc, xb + G + 3, sk, yp + (G + 2) * KT);
+    if (r > 2) tds_group_ahead<KT, MODE, 2, 0>(w, y, acc, xb + G + 4, sk, yp + (G + 3) * KT);
+    if (r > 3) tds_group_ahead<KT, MODE, 0, 1>(w, y, acc, xb + G + 5, sk, yp + (G + 4) * KT);
+    if (r > 4) tds_group_ahead<KT, MODE, 1, 0>(w, y, acc, xb + G + 6, sk, yp + (G + 5) * KT);
+}
 
 // ROT = false: the loop body holds two groups (the window blocks swap roles, no moves); ROT = true: one group per
 // iteration and KT register moves -- half the code.  A body of two groups of KT = 15 is 15 KB of instructions per variant,
@@ -211,6 +292,17 @@ __device__ __forceinline__ void tds_lane_sums(const float* __restrict__ xb, int 
         }
         if (tail) tds_group<KT, 0, MODE, true>(w, acc, xb + G + 1, sk, yp + G * KTP, tail);
     } else {
+        if constexpr (KT == 2) {
+            // a group of two steps is eight operations: four pairs of groups per iteration keep the loop overhead small
+#pragma unroll 1
+            for (; G + 8 <= NG; G += 8) {
+#pragma unroll
+                for (int g = 0; g < 8; g += 2) {
+                    tds_group<KT, 0, MODE, false>(w, acc, xb + G + g + 1, sk, yp + (G + g) * KTP);
+                    tds_group<KT, 1, MODE, false>(w, acc, xb + G + g + 2, sk, yp + (G + g + 1) * KTP);
+                }
+            }
+        }
         for (; G + 2 <= NG; G += 2) {
             tds_group<KT, 0, MODE, false>(w, acc, xb + G + 1, sk, yp + G * KTP);
             tds_group<KT, 1, MODE, false>(w, acc, xb + G + 2, sk, yp + (G + 1) * KTP);
@@ -295,7 +387,7 @@ __device__ __forceinline__ unsigned long long argmax_key(double v)
 //   * the position weights 1 - 0.25 t^2 are tabulated once.
 // SK > 0: the sub-plane stride is a compile-time constant (a.sk == SK), 0: run-time a.sk
 template <int CH, int KT, int SK>
-__global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
+__global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT) tds_offsets_kernel(const __grid_constant__ TdsArgs a)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -332,6 +424,9 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
     const int tb_lo = (int)crank * a.tb_per;
     int ntb = tblocks - tb_lo; if (ntb > a.tb_per) ntb = a.tb_per; if (ntb < 0) ntb = 0;
     constexpr bool ROT = KT > 8;                     // large bodies: one group per loop iteration (instruction cache)
+    // four CTAs per track (few tracks per GPU): loads ride one group ahead (tds_lane_sums_ahead).  Measured in the engine: 16 tracks
+    // 22.95 -> 20.16 ms, 32 tracks 31.1 -> 30.2 ms; the same ring for KT = 8 (two CTAs per track) made 64 tracks 2 % slower (50.9 -> 52.0 ms)
+    constexpr bool kAhead = KT == 4;
     const int wpc = (ntb + 1 + 31) / 32;             // warps per (lane, class) combo (streams that start one element late need one more block)
     const int nunits = 4 * K * wpc;
     const int wpn = (ntb + 1 + 31) / 32;             // warps per plane for the norm sums (ntb + 1 position blocks)
@@ -399,7 +494,9 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
             const int rho = v / wpn, mb = (v - rho * wpn) * 32 + lane;
             if (mb <= ntb) {
                 float nr[KT];
-                tds_lane_sums<KT, 1, SK, ROT>(X + rho * plane_len + mb, sk, nullptr, Q, nr);
+                bool summed = false;
+                if constexpr (kAhead) { if (Q % KT == 0) { tds_lane_sums_ahead<KT, 1, SK>(X + rho * plane_len + mb, sk, nullptr, Q, nr); summed = true; } }
+                if (!summed) tds_lane_sums<KT, 1, SK, ROT>(X + rho * plane_len + mb, sk, nullptr, Q, nr);
 #pragma unroll
                 for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
             }
@@ -474,7 +571,9 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
                 const float* xb = X + (u0 & 3) * plane_len + tb;
                 const float* yp = Y + l * QP;
                 float acc[KT];
-                tds_lane_sums<KT, 0, SK, ROT>(xb, sk, yp, Q, acc);
+                bool summed = false;
+                if constexpr (kAhead) { if (Q % KT == 0) { tds_lane_sums_ahead<KT, 0, SK>(xb, sk, yp, Q, acc); summed = true; } }
+                if (!summed) tds_lane_sums<KT, 0, SK, ROT>(xb, sk, yp, Q, acc);
 #pragma unroll
                 for (int k = 0; k < KT; k++) {
                     const int tl = KT * tb + k - off;
@@ -568,6 +667,12 @@ __global__ void __launch_bounds__(kTdsThreads, NODEY_TDS_RESIDENT) tds_offsets_k
 #endif
 }
 
+// eight CTAs per track (KT = 2, four CTAs per SM) up to this many tracks per launch on a 148-SM GPU.  Measured in the engine
+// (bench.py --tracks n, both nodes' chains side by side): 32 tracks 41.0 ms against 31.1 ms with four CTAs per track, 16
+// tracks 27.0 against 23.0 ms -- a sequence's fixed costs (gather, exchange, barriers) do not shrink with the slice and two
+// accumulators per thread leave the FP32 pipe waiting on its own latency
+constexpr long long kTdsCluster8Tracks = 0;       // measured: never; the variant stays selectable for tests
+constexpr int kTdsSkPair = 132;      // compile-time sub-plane stride of the KT = 2 kernel (eight CTAs per track: 29 candidate blocks + 96 groups + margin; 4 mod 8)
 constexpr int kTdsSkLarge = 51;      // compile-time sub-plane stride of the KT = 11..16 kernels (odd; 32 candidate blocks + 13 groups + margin)
 typedef void (*TdsKernel)(TdsArgs);
 // KT = 11..16 exist for stereo with the compile-time stride only (mono streams fit one warp at KT = 8; anything that does
@@ -576,6 +681,7 @@ template <int CH>
 static TdsKernel tds_kernel_ch(int KT, bool fixed)
 {
     switch (KT) {
+    case 2:  return fixed ? tds_offsets_kernel<CH, 2, kTdsSkPair> : tds_offsets_kernel<CH, 2, 0>;
     case 4:  return fixed ? tds_offsets_kernel<CH, 4, 84> : tds_offsets_kernel<CH, 4, 0>;
     case 8:  return fixed ? tds_offsets_kernel<CH, 8, 92> : tds_offsets_kernel<CH, 8, 0>;
     }
@@ -1291,20 +1397,20 @@ int nodey_debug_tds_phases(unsigned long long out[8])
 }
 #endif
 
-/* test hook: force the cluster size (1, 2 or 4; 0 = automatic) of the offsets kernel */
+/* test hook: force the cluster size (1, 2, 4 or 8; 0 = automatic) of the offsets kernel */
 int nodey_soundtouch_set_cluster(nodey_soundtouch* s, int cluster)
 {
-    NODEY_REQUIRE(s && (cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4), NODEY_E_INVALID,
-                  "nodey_soundtouch_set_cluster: cluster must be 0, 1, 2 or 4");
+    NODEY_REQUIRE(s && (cluster == 0 || cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8), NODEY_E_INVALID,
+                  "nodey_soundtouch_set_cluster: cluster must be 0, 1, 2, 4 or 8");
     s->force_cluster = cluster;
     return NODEY_OK;
 }
 
-/* test hook: force the number of candidates a thread of the offsets kernel owns (4, 8, 11..16; 0 = automatic) */
+/* test hook: force the number of candidates a thread of the offsets kernel owns (2, 4, 8, 11..16; 0 = automatic) */
 int nodey_soundtouch_set_candidates_per_thread(nodey_soundtouch* s, int kt)
 {
-    NODEY_REQUIRE(s && (kt == 0 || kt == 4 || kt == 8 || (kt >= 11 && kt <= 16)), NODEY_E_INVALID,
-                  "nodey_soundtouch_set_candidates_per_thread: must be 0, 4, 8 or 11..16");
+    NODEY_REQUIRE(s && (kt == 0 || kt == 2 || kt == 4 || kt == 8 || (kt >= 11 && kt <= 16)), NODEY_E_INVALID,
+                  "nodey_soundtouch_set_candidates_per_thread: must be 0, 2, 4, 8 or 11..16");
     s->force_kt = kt;
     return NODEY_OK;
 }
@@ -1504,20 +1610,21 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             // 96 tracks 79.3 / 78.7 / -, 112 tracks 86.1 / 90.8 / -, 128 tracks 94.4 / 104.7 / 125.9.  So: 4 CTAs per track
             // up to 40 tracks, 2 up to about 100 (round 1, with the KT = 8 single-CTA kernel: up to 200), 1 beyond
             int CL = 1;
-            if ((long long)ntracks * 4 <= 160ll * sm_count() / 148) CL = 4;
+            if ((long long)ntracks * 8 <= kTdsCluster8Tracks * 8ll * sm_count() / 148) CL = 8;
+            else if ((long long)ntracks * 4 <= 160ll * sm_count() / 148) CL = 4;
             else if ((long long)ntracks * 2 <= 208ll * sm_count() / 148) CL = 2;
             if (s->force_cluster > 0) CL = s->force_cluster;
-            if (const char* env = getenv("NODEY_TDS_CLUSTER")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) CL = v; }   // development override
+            if (const char* env = getenv("NODEY_TDS_CLUSTER")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) CL = v; }   // development override
             const int K = 4 / CH;
             const int tcount = (s->seek_length + K - 1) / K;
             // candidates per thread: a (lane, class) stream of tcount candidates is walked by whole warps, so the cost of a
             // sequence goes with warps x KT.  One CTA per track: the smallest KT that fits the stream into ONE warp
             // (456 candidates: 31 lanes x 15 instead of 57 lanes of two warps x 8 -- 6 % fewer rounded operations issued
             // and half the window loads per operation); clusters split the stream first (29 lanes x 8 resp. x 4)
-            int KT = CL >= 4 ? 4 : 8;
+            int KT = CL >= 8 ? 2 : CL >= 4 ? 4 : 8;
             if (CL == 1 && CH == 2) { const int k1 = (tcount + 30) / 31; if (k1 >= 11 && k1 <= 16) KT = k1; }   // 31 blocks + 1 (streams that start one element late)
             if (s->force_kt > 0) KT = s->force_kt;
-            if (const char* env = getenv("NODEY_TDS_KT")) { const int v = atoi(env); if (v == 4 || v == 8 || (v >= 11 && v <= 16)) KT = v; }   // development override
+            if (const char* env = getenv("NODEY_TDS_KT")) { const int v = atoi(env); if (v == 2 || v == 4 || v == 8 || (v >= 11 && v <= 16)) KT = v; }   // development override
             if (KT > 8 && (CH != 2 || (tcount + KT - 1) / KT / CL + ta.Q / KT + 5 > kTdsSkLarge || getenv("NODEY_TDS_RUNTIME_SK"))) KT = 8;
             const int tblocks = (tcount + KT - 1) / KT;
             ta.tb_per = (tblocks + CL - 1) / CL;
@@ -1525,11 +1632,11 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             int sk = ta.tb_per + ta.Q / KT + 4;
             // compile-time sub-plane strides (window loads become base + immediate); odd resp. 4 mod 8 so that the staging
             // stores of consecutive sub-planes spread over the banks
-            const int sk_fixed = KT == 4 ? 84 : KT == 8 ? 92 : kTdsSkLarge;
+            const int sk_fixed = KT == 2 ? kTdsSkPair : KT == 4 ? 84 : KT == 8 ? 92 : kTdsSkLarge;
             bool fixed = sk <= sk_fixed && !getenv("NODEY_TDS_RUNTIME_SK");
             if (fixed) sk = sk_fixed; else if (KT > 8) sk |= 1; else while ((sk & 7) != 4) sk++;
             ta.sk = sk;
-            ta.qp = ngroups * ((KT + 3) & ~3) + 8;
+            ta.qp = ngroups * tds_ktp_rt(KT) + 8;
             const int pad_c = (K * KT) & 1 ? 2 : 1, pad_n = KT & 1 ? 2 : 1;
             ta.ncand_pad = (K * KT * ta.tb_per + pad_c * ta.tb_per + 4 + 3) & ~3;      // + pad words per K*KT candidates
             ta.npm = (KT * (ta.tb_per + 1) + pad_n * (ta.tb_per + 1) + 4 + 3) & ~3;
@@ -1542,6 +1649,7 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.qp + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
                                                  (size_t)((mreg * CH + 3) & ~3)) + sizeof(double) * (size_t)(K * KT * ta.tb_per);
             NODEY_REQUIRE(smem <= 110 * 1024, NODEY_E_RANGE, "tds_offsets: %zu bytes of shared memory per CTA exceed the two-per-SM budget", smem);
+            // (KT = 2 runs four CTAs per SM when its 27 KB allow it; with a larger window it is simply less resident)
             NODEY_REQUIRE(KT * (ta.tb_per + ta.Q / KT + 4) * 4 / CH <= 2048 + 64 * KT, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
             void (*kern)(TdsArgs) = tds_kernel_for(CH, KT, fixed);
             NODEY_REQUIRE(kern, NODEY_E_INVALID, "tds_offsets: internal: no kernel for %d candidates per thread", KT);

@@ -53,7 +53,7 @@ def test_soundtouch_matches_oracle(nd, orc, case):
     assert_bit_equal(got.cpu().numpy(), ref, "soundtouch samples")
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("cfg", [(48000, 2, 1.0, 3.0), (44100, 1, 1.0, -4.0), (11025, 2, 1.0, 2.0)])
 def test_soundtouch_cluster_sizes(nd, orc, cluster, cfg):
     """the WSOLA search split over a thread-block cluster must give the same trace as one CTA"""
@@ -70,7 +70,7 @@ def test_soundtouch_cluster_sizes(nd, orc, cluster, cfg):
         assert_bit_equal(got[t].cpu().numpy(), ref, f"track {t}")
 
 
-@pytest.mark.parametrize("kt", [4, 8, 11, 12, 13, 14, 15, 16])
+@pytest.mark.parametrize("kt", [2, 4, 8, 11, 12, 13, 14, 15, 16])
 def test_soundtouch_candidates_per_thread(nd, orc, kt):
     """every (candidates per thread, cluster size) variant of the WSOLA search gives the oracle's trace: the pitch node's
     912 candidates and the tempo node's 864 at 48 kHz, 44.1 kHz (810 / 793) and the run-time stride"""
@@ -83,7 +83,7 @@ def test_soundtouch_candidates_per_thread(nd, orc, kt):
         refs = [orc.soundtouch(xs[t], sr, rate, pitch, 1152) for t in range(2)]
         st = nd.SoundTouch(sr, 2, rate, pitch)
         st.set_candidates_per_thread(kt)
-        for cluster in (1, 2, 4):
+        for cluster in (1, 2, 4, 8):
             st.set_cluster(cluster)
             for runtime_sk in (False, True):
                 if runtime_sk:

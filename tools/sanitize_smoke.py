@@ -61,12 +61,12 @@ def fam_resample():
 
 def fam_soundtouch():
     x = torch.stack([nd.synth(48000, 2, 48000, track=k) for k in range(3)])
-    for cluster in (1, 2, 4):
+    for cluster in (1, 2, 4, 8):
         st = nd.SoundTouch.pitch_node(48000, 2, 3.0)
         st.set_cluster(cluster)
         st.run(x, want_offsets=True)
         st.close()
-    for kt, cluster in ((8, 1), (12, 2), (16, 1), (13, 4), (4, 4)):     # every code shape of the search: full / partial last group, rotating / two-group bodies
+    for kt, cluster in ((8, 1), (12, 2), (16, 1), (13, 4), (4, 4), (2, 8), (2, 1), (4, 8)):     # every code shape of the search: full / partial last group, rotating / two-group bodies
         st = nd.SoundTouch.pitch_node(48000, 2, 3.0)
         st.set_candidates_per_thread(kt)
         st.set_cluster(cluster)
