@@ -182,6 +182,22 @@ def test_graph_editing_api_cpp(tmp_path):
     assert "graph_edit_test ok" in r.stdout
 
 
+def test_schedule_and_frame_clock_cpp(tmp_path):
+    """infra::Runner::Schedule (environment overrides read once per run, explicit settings win) and processor::Frame_clock
+    (per-frame stamps by the producing node's rule): tests/cpp/schedule_clock_test.cpp against libnodey_host.so"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "nodey-audio-editor_b200")
+    exe = str(tmp_path / "schedule_clock_test")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-I" + os.path.join(pkg, "host", "shim"), "-I" + os.path.join(pkg, "host", "include"),
+                    "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "cpp", "schedule_clock_test.cpp"),
+                    "-L" + pkg, "-lnodey_host", "-lnodey_cuda", "-Wl,-rpath," + pkg, "-lpthread"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "schedule_clock_test ok" in r.stdout
+
+
 def test_render_without_a_cuda_device_fails_loudly(eng):
     """no CPU fallback: on a box without a CUDA device the Runner marks every node as failed with a Runtime_error that
     says so (the product path never routes through the oracle)"""
