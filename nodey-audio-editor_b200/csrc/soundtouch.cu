@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(kFirThreads) aa_fir_mono_kernel(const __grid_c
 constexpr int kFirS = 8;                              // outputs per thread
 constexpr int kFirTileS = kFirS * kFirThreads;        // 2048 outputs per CTA
 constexpr int kFirChunks = (kFirTileS + kAaLen + 8) / 2;
+static_assert(kFirThreads % 128 == 0, "st_post advances tile slots by kFirThreads frames: the chunk swizzle must repeat");
 
 __device__ __forceinline__ int fir_chunk(int chunk) { return (chunk & ~7) | ((chunk ^ (chunk >> 3)) & 7); }
 
@@ -937,6 +938,7 @@ struct PostArgs {
     long long l1;               // TDStretch output frames
     float h[kAaLen];
     unsigned long long R; int e;
+    long long tile_outputs;                                 // floor(kPostStride * 2^e / R): cubic outputs per tile, or one more
     float* out; long long out_stride; long long count;     // final frames to write
     long long tile_begin, tile_end;                         // this launch covers tiles [tile_begin, tile_end)
     Neutral u;                                              // -0.0f and 1.0f as run-time values (see mul2_rn / add2_rn)
@@ -956,7 +958,9 @@ __device__ __forceinline__ long long cubic_pos(unsigned long long i, unsigned lo
 __device__ __forceinline__ long long cubic_first_at(long long n, unsigned long long R, int e, double inv_rate)
 {
     if (n <= 0) return 0;
-    long long i = (long long)((double)n * inv_rate);
+    // the estimate is floor-ish: one above it is the answer nearly always, which the two loops then confirm with one
+    // evaluation each (starting AT the estimate took three)
+    long long i = (long long)((double)n * inv_rate) + 1;
     if (i < 0) i = 0;
     while (cubic_pos((unsigned long long)i, R, e) < n) i++;
     while (i > 0 && cubic_pos((unsigned long long)(i - 1), R, e) >= n) i--;
@@ -992,8 +996,11 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
         const long long n0 = t * kPostStride;
         // cubic outputs whose read position lies in [n0, n0 + kPostStride): i in [i_lo, i_hi)
-        long long i_lo = cubic_first_at(n0, a.R, a.e, inv_rate);
-        long long i_hi = cubic_first_at(n0 + kPostStride, a.R, a.e, inv_rate);
+        // i_lo = ceil(n0 * 2^e / R) by an exact search; i_hi = ceil((n0 + stride) * 2^e / R) is i_lo + floor(stride * 2^e / R)
+        // or one more (difference of two ceilings): one evaluation decides
+        const long long i_lo = cubic_first_at(n0, a.R, a.e, inv_rate);
+        long long i_hi = i_lo + a.tile_outputs;
+        if (cubic_pos((unsigned long long)i_hi, a.R, a.e) < n0 + kPostStride) i_hi++;
         if (i_lo >= a.count) break;
         if (i_hi > a.count) i_hi = a.count;
         __syncthreads();
@@ -1042,6 +1049,8 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                     const int fj = j * hop - kf;                                  // tile frame where sequence i_first + j starts
                     const long long so = src_j[j] - fj, mo = mid_j[j] - fj;       // source / partner frame of tile frame 0
                     const int cs = fj > 0 ? fj : 0, ce = fj + ovl < F ? fj + ovl : F;
+                    // (a thread's frames are kFirThreads = 256 apart, and slot(f + 256) = slot(f) + 256: the swizzle looks at
+                    // bits 1..6 of f only -- one slot computation per run, running pointers after that)
                     for (int f = cs + (int)threadIdx.x; f < ce; f += kFirThreads) {
                         const int k = f - fj;
                         const float2 x = planar ? make_float2(__ldg(pl + so + f), __ldg(pr + so + f)) : __ldg(b2 + so + f);
@@ -1050,15 +1059,22 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
                         tile2[slot(f)] = add2_rn(mul2_rn(x, make_float2(f1, f1), a.u), mul2_rn(m, make_float2(f2, f2), a.u), a.u);
                     }
                     const int ps = fj + ovl > 0 ? fj + ovl : 0, pe = fj + hop < F ? fj + hop : F;
-                    if (planar) {
-                        for (int f = ps + (int)threadIdx.x; f < pe; f += kFirThreads) {
-                            float* d = reinterpret_cast<float*>(tile2 + slot(f));
-                            cp_async4(d, pl + so + f, true);
-                            cp_async4(d + 1, pr + so + f, true);
+                    const int f0 = ps + (int)threadIdx.x;
+                    if (f0 < pe) {
+                        float2* d = tile2 + slot(f0);
+                        const int n_it = (pe - f0 + kFirThreads - 1) / kFirThreads;
+                        if (planar) {
+                            const float* sl = pl + so + f0;
+                            const float* sr = pr + so + f0;
+                            for (int it = 0; it < n_it; it++, d += kFirThreads, sl += kFirThreads, sr += kFirThreads) {
+                                cp_async4(reinterpret_cast<float*>(d), sl, true);
+                                cp_async4(reinterpret_cast<float*>(d) + 1, sr, true);
+                            }
+                        } else {
+                            const float2* sp = b2 + so + f0;
+                            for (int it = 0; it < n_it; it++, d += kFirThreads, sp += kFirThreads)
+                                cp_async8(reinterpret_cast<float*>(d), reinterpret_cast<const float*>(sp), true);
                         }
-                    } else {
-                        for (int f = ps + (int)threadIdx.x; f < pe; f += kFirThreads)
-                            cp_async8(reinterpret_cast<float*>(tile2 + slot(f)), reinterpret_cast<const float*>(b2 + so + f), true);
                     }
                 }
                 cp_async_wait_all();
@@ -1128,30 +1144,35 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
         // sums below can be (a sum is -0 only when both addends are; every sum here has an addend that is +0 or positive).
         const float inv_f = __uint_as_float((unsigned)(127 - a.e) << 23);          // 2^-e, e <= 60: a normal float
         const unsigned long long fmask = (1ull << a.e) - 1ull;
-        unsigned long long p_lo, p_hi;
+        // position = (tile-relative integer part q, fraction fb < 2^e): the product once, then q += step_int + carry and
+        // fb = (fb + step_frac) mod 2^e per output -- the same integers as the 128-bit running sum, half the instructions
+        int q; unsigned long long fb;
         {
             const unsigned long long i0 = (unsigned long long)(i_lo + threadIdx.x);
-            p_lo = i0 * a.R; p_hi = __umul64hi(i0, a.R);
+            const unsigned long long p_lo = i0 * a.R, p_hi = __umul64hi(i0, a.R);
+            q = (int)((long long)((p_lo >> a.e) | (a.e ? (p_hi << (64 - a.e)) : 0ull)) - n0);
+            fb = p_lo & fmask;
         }
         const unsigned long long step_lo = (unsigned long long)blockDim.x * a.R, step_hi = __umul64hi((unsigned long long)blockDim.x, a.R);
+        const int step_int = (int)((step_lo >> a.e) | (a.e ? (step_hi << (64 - a.e)) : 0ull));
+        const unsigned long long step_frac = step_lo & fmask;
         for (long long i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-            const long long P = (long long)((p_lo >> a.e) | (a.e ? (p_hi << (64 - a.e)) : 0ull));
-            const unsigned long long fb = p_lo & fmask;
+            const int q_cur = q;
+            const unsigned long long fb_cur = fb;
             {
-                const unsigned long long n_lo = p_lo + step_lo;
-                p_hi += step_hi + (n_lo < p_lo ? 1ull : 0ull);
-                p_lo = n_lo;
+                const unsigned long long sum = fb + step_frac;            // < 2^(e+1), e <= 60: no overflow
+                q += step_int + (int)(sum >> a.e);
+                fb = sum & fmask;
             }
-            const float x2 = __fmul_rn(__ull2float_rn(fb), inv_f);
+            const float x2 = __fmul_rn(__ull2float_rn(fb_cur), inv_f);
             const float x1 = __fmul_rn(x2, x2);
             const float x0 = __fmul_rn(x1, x2);
             const float y0 = __fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), x1), __fmul_rn(-0.5f, x2));
             const float y1 = __fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), 1.0f);
             const float y2 = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2));
             const float y3 = __fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1));
-            const int q = (int)(P - n0);
             const auto at = [&](int f) { return filt[f + (f >> 3)]; };
-            const float2 p0 = at(q), p1 = at(q + 1), p2 = at(q + 2), p3 = at(q + 3);
+            const float2 p0 = at(q_cur), p1 = at(q_cur + 1), p2 = at(q_cur + 2), p3 = at(q_cur + 3);
             const float2 o = add2_rn(add2_rn(add2_rn(mul2_rn(p0, make_float2(y0, y0), a.u), mul2_rn(p1, make_float2(y1, y1), a.u), a.u),
                                              mul2_rn(p2, make_float2(y2, y2), a.u), a.u), mul2_rn(p3, make_float2(y3, y3), a.u), a.u);
             reinterpret_cast<float2*>(out)[i] = o;
@@ -1732,6 +1753,7 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
             pa.nseq = (int)nseq; pa.overlap = s->overlap; pa.seek_window = s->seek_window; pa.prefill = s->prefill; pa.l1 = L.l1;
             memcpy(pa.h, s->aa, sizeof(pa.h));
             pa.R = s->R; pa.e = s->e; pa.out = out; pa.out_stride = out_stride; pa.count = out_frames;
+            pa.tile_outputs = (long long)((((unsigned __int128)kPostStride) << s->e) / s->R);
             pa.tile_begin = cp.tile_begin; pa.tile_end = cp.tile_end;
             pa.u.neg_zero = -0.0f; pa.u.one = 1.0f;
             const long long tiles = cp.tile_end - cp.tile_begin;
