@@ -1020,7 +1020,12 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             long long src_j[kMaxSeq], mid_j[kMaxSeq];
             const int i_base = i_first > 0 ? i_first : 1;
 #pragma unroll
-            for (int j = 0; j < kMaxSeq; j++) { src_j[j] = seq_src(i_base + j); mid_j[j] = seq_mid(i_base + j); }
+            for (int j = 0; j < kMaxSeq; j++) src_j[j] = seq_src(i_base + j);
+            // the cross-fade partner of sequence i >= 2 starts ovl + temp behind the source of sequence i - 1 (seq_mid):
+            // one pair of loads per sequence instead of two
+            mid_j[0] = seq_mid(i_base);
+#pragma unroll
+            for (int j = 1; j < kMaxSeq; j++) mid_j[j] = i_base + j >= a.nseq ? 0ll : src_j[j - 1] + ovl + temp;
             const long long pos0 = a.pos[0];
             // interior tile: every frame it can touch lies inside the real input and inside sequences >= 1 that
             // were fetched above -> no bounds checks, 32-bit stepping
@@ -1029,8 +1034,10 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             bool interior = i_first >= 1 && o_last < a.l1 && i_first + kMaxSeq - 1 < a.nseq && 2 * kFirChunks + k_first < (long long)kMaxSeq * hop;
 #pragma unroll
             for (int j = 0; j < kMaxSeq; j++)
-                interior = interior && src_j[j] - a.in.prefix >= 0 && src_j[j] - a.in.prefix + reach <= a.in.n
-                                    && mid_j[j] - a.in.prefix >= 0 && mid_j[j] - a.in.prefix + ovl <= a.in.n;
+                interior = interior && src_j[j] - a.in.prefix >= 0 && src_j[j] - a.in.prefix + reach <= a.in.n;
+            // partners: mid_j[j >= 1] = src_j[j - 1] + ovl + temp lies inside what the source checks cover (2 ovl + temp =
+            // hop + ovl <= reach); the first one is on its own
+            interior = interior && mid_j[0] - a.in.prefix >= 0 && mid_j[0] - a.in.prefix + ovl <= a.in.n;
             if (interior) {
                 // The tile's frames fall into at most three sequences, each a cross-faded run of `ovl` frames followed by a
                 // plain copy of `hop - ovl` frames: six runs with warp-uniform source pointers.  The copies (87 % of the
@@ -1156,7 +1163,9 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
         const unsigned long long step_lo = (unsigned long long)blockDim.x * a.R, step_hi = __umul64hi((unsigned long long)blockDim.x, a.R);
         const int step_int = (int)((step_lo >> a.e) | (a.e ? (step_hi << (64 - a.e)) : 0ull));
         const unsigned long long step_frac = step_lo & fmask;
-        for (long long i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        const int n_out = (int)(i_hi - i_lo);                  // at most tile_outputs + 1
+        float2* op = reinterpret_cast<float2*>(out) + i_lo + threadIdx.x;
+        for (int k = (int)threadIdx.x; k < n_out; k += (int)blockDim.x, op += blockDim.x) {
             const int q_cur = q;
             const unsigned long long fb_cur = fb;
             {
@@ -1175,7 +1184,7 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             const float2 p0 = at(q_cur), p1 = at(q_cur + 1), p2 = at(q_cur + 2), p3 = at(q_cur + 3);
             const float2 o = add2_rn(add2_rn(add2_rn(mul2_rn(p0, make_float2(y0, y0), a.u), mul2_rn(p1, make_float2(y1, y1), a.u), a.u),
                                              mul2_rn(p2, make_float2(y2, y2), a.u), a.u), mul2_rn(p3, make_float2(y3, y3), a.u), a.u);
-            reinterpret_cast<float2*>(out)[i] = o;
+            *op = o;
         }
     }
 }
