@@ -192,6 +192,11 @@ namespace processor
 		std::vector<bool> locks;
 
 	  public:
+		// SURVEY.md App. C4 switch (optional JSON key "start_time_stamps", default off): the reference stamps the mixer's
+		// frames with their END time, truncated to microseconds (audio-amix.cpp:199-201), which makes its export start with
+		// almost one frame of silence and insert more wherever the frame size grows.  Set, the frames carry exact START
+		// times from 0 and an export is the mix and nothing else.  Samples are the same either way.
+		bool start_time_stamps = false;
 		Audio_amix();
 		virtual ~Audio_amix() = default;
 		NODEY_NODE_COMMON(Audio_amix)
@@ -205,6 +210,7 @@ namespace processor
 		float bias = 0.0f;
 
 	  public:
+		bool start_time_stamps = false;      // see Audio_amix (audio-bimix.cpp:188-191 stamps the same way)
 		Audio_bimix() = default;
 		virtual ~Audio_bimix() = default;
 		NODEY_NODE_COMMON(Audio_bimix)

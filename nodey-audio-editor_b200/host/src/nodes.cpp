@@ -1375,6 +1375,7 @@ namespace processor
 			value[std::format("volumes{}", i)] = i < (int)volumes.size() ? volumes[(size_t)i] : 1.0f;
 			value[std::format("locks{}", i)] = i < (int)locks.size() ? (bool)locks[(size_t)i] : false;
 		}
+		if (start_time_stamps) value["start_time_stamps"] = true;      // written only when set: reference files stay as they are
 		return value;
 	}
 
@@ -1391,6 +1392,7 @@ namespace processor
 			volumes.push_back(value[std::format("volumes{}", i)].asFloat());
 			locks.push_back(value[std::format("locks{}", i)].asBool());
 		}
+		start_time_stamps = value.isMember("start_time_stamps") && value["start_time_stamps"].isBool() && value["start_time_stamps"].asBool();
 	}
 
 	namespace
@@ -1404,6 +1406,7 @@ namespace processor
 			std::vector<std::shared_ptr<const Audio_buffer>> ins;
 			std::vector<float> vol;
 			std::shared_ptr<const Amix_plan> plan;
+			bool start_stamps = false;   // Audio_amix::start_time_stamps
 			bool fused = false;     // same-rate inputs that need resampling, each landing unbroken at 0, exact-rational plan
 			std::vector<int64_t> front_len;
 		};
@@ -1486,7 +1489,8 @@ namespace processor
 		{
 			// pts: the reference stamps each frame with the running END time (audio-amix.cpp:199-201, App. C4)
 			Frame_runs out_runs = job.plan->out_runs;
-			auto buffer = end_time_stamps(new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), 0.0));
+			auto buffer = new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, job.plan->total, std::move(out_runs), 0.0);
+			if (!job.start_stamps) buffer = end_time_stamps(std::move(buffer));       // the reference's stamps unless the node opts out
 			if (progress && !progress->points.empty()) { buffer->ready = progress->points.back().event; buffer->progress = progress; }
 			publish(output, "output", buffer);
 		}
@@ -1565,6 +1569,7 @@ namespace processor
 	void Audio_amix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
 	{
 		Amix_job job = amix_prepare(input_num, volumes, input);
+		job.start_stamps = start_time_stamps;
 		amix_execute(job, output);
 	}
 
@@ -1579,6 +1584,7 @@ namespace processor
 		{
 			const auto* node = static_cast<const Audio_amix*>(items[k].processor);
 			jobs.push_back(amix_prepare(node->input_num, node->volumes, *items[k].input));
+			jobs.back().start_stamps = node->start_time_stamps;
 			const Amix_job& job = jobs.back();
 			if (job.ins.size() == 1 && job.fused)
 			{
@@ -1663,6 +1669,7 @@ namespace processor
 	{
 		Json::Value value;
 		value["bias"] = bias;
+		if (start_time_stamps) value["start_time_stamps"] = true;
 		return value;
 	}
 	void Audio_bimix::deserialize(const Json::Value& value)
@@ -1671,6 +1678,7 @@ namespace processor
 			throw Runtime_error("Failed to deserialize JSON file",
 								"Audio_bimix failed to serialize the JSON input because of missing or invalid fields.", "Wrong field: bias");
 		bias = std::clamp<float>((float)value["bias"].asDouble(), -1, 1);
+		start_time_stamps = value.isMember("start_time_stamps") && value["start_time_stamps"].isBool() && value["start_time_stamps"].asBool();
 	}
 
 	namespace
@@ -1780,7 +1788,8 @@ namespace processor
 		float* out_r = (float*)((char*)block->ptr + plane);
 		if (total > 0) abi(nodey_bimix(out_l, out_r, rl.l, rl.r, len_l, rr.l, rr.r, len_r, bias, total, cur_stream()), "Audio bimix");
 		// App. C3: the running time starts at 0; C4: frames carry their END time
-		publish(output, "output", end_time_stamps(new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), 0.0)));
+		auto mixed = new_buffer(block, out_l, out_r, FMT_FLTP, 48000, 2, total, std::move(out_runs), 0.0);
+		publish(output, "output", start_time_stamps ? mixed : end_time_stamps(std::move(mixed)));
 	}
 
 	// ---------------------------------------------------------------------------------------------

@@ -115,6 +115,30 @@ def test_export_of_an_amix_whose_frame_size_grows(eng_gpu, orc, tmp_path):
     assert_bit_equal(y, np.concatenate(parts), "exported WAV with the reference's silence")
 
 
+def test_start_time_stamps_switch_exports_the_mix_and_nothing_else(eng_gpu, orc, tmp_path):
+    """SURVEY.md App. C4 switch (JSON key "start_time_stamps" on audio_amix / audio_bimix): frames stamped with exact start
+    times from 0 instead of the reference's truncated end times -- same samples, no silence in the export"""
+    short = make_input(orc, FMT_FLT, 48000 // 3, 2, rate=48000, track=3)
+    long_ = make_input(orc, FMT_FLT, 48000, 2, rate=48000, track=4)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": ["", ""]})
+    mix = p.add("audio_amix", dict(eng_gpu.amix_info([0.7, 0.4]), start_time_stamps=True))
+    out = p.add("audio_output")
+    p.link(src, "output_0", mix, "input_1"); p.link(src, "output_1", mix, "input_2"); p.link(mix, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_export_path(str(tmp_path / "plain.wav"))
+    e.bind_source(0, short, FMT_FLT, 48000, frame_size=1024)
+    e.bind_source(1, long_, FMT_FLT, 48000, frame_size=1152)
+    e.run()
+    rl, rr = orc.amix([orc.make_track(short, FMT_FLT, 48000, frame_size=1024), orc.make_track(long_, FMT_FLT, 48000, frame_size=1152)], [0.7, 0.4])
+    got = e.output()
+    assert got.pts == 0.0 and e.product_stamp(mix, "output") == (eng_gpu.STAMP_START, 0.0)
+    assert_bit_equal(got.numpy(), np.stack([rl, rr]), "mix")
+    y, rate = _read_float_wav(str(tmp_path / "plain.wav"))
+    assert rate == 48000
+    assert_bit_equal(y, np.ascontiguousarray(np.stack([rl, rr]).T), "exported WAV without any silence")
+
+
 def test_export_pads_a_late_stream_with_silence(eng_gpu, orc, tmp_path):
     x = make_input(orc, FMT_FLT, 5000, 2, rate=48000)
     p = eng_gpu.Project()

@@ -148,6 +148,30 @@ def test_config5_project_shape(eng):
     assert levels[ids["input"]] == 0 and levels[ids["master"]] == 6 and levels[ids["output"]] == 7
 
 
+def test_compat_switches_are_written_only_when_set(eng):
+    """the optional JSON keys of the quirk switches: absent from serialised projects unless
+    set, so files written by the reference round-trip unchanged; set, they survive a round trip"""
+    def build(flags):
+        p = eng.Project()
+        src = p.add("audio_input", {"file_path": ["", ""]})
+        mix = p.add("audio_amix", dict(eng.amix_info([1.0, 1.0]), **({"start_time_stamps": True} if flags else {})))
+        bi = p.add("audio_bimix", dict({"bias": 0.0}, **({"start_time_stamps": True} if flags else {})))
+        pm = p.add("pitch_modifier", dict({"pitch": 1.0}, **({"reference_schedule": True} if flags else {})))
+        out = p.add("audio_output")
+        p.link(src, "output_0", mix, "input_1"); p.link(src, "output_1", mix, "input_2")
+        p.link(mix, "output", pm, "input"); p.link(pm, "output", out, "input")
+        p.link(src, "output_0", bi, "input_l"); p.link(src, "output_1", bi, "input_r")
+        return p, mix, bi, pm
+    for flags in (False, True):
+        p, mix, bi, pm = build(flags)
+        text = json.loads(eng.Engine(p.json()).serialize())
+        again = json.loads(eng.Engine(json.dumps(text)).serialize())
+        assert again == text
+        for node, key in ((mix, "start_time_stamps"), (bi, "start_time_stamps"), (pm, "reference_schedule")):
+            info = text["nodes"][str(node)]["info"]
+            assert (info.get(key) is True) if flags else (key not in info)
+
+
 def test_example_frame_processor_registers_and_round_trips():
     """frame-streaming compatibility mode: the frame-interface example node is outside the reference's set until the
     host registers it; afterwards it loads from project JSON like any other processor"""
