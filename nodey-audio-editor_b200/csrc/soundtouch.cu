@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT)
                 if constexpr (kAhead) { if (Q % KT == 0) { tds_lane_sums_ahead<KT, 1, SK>(X + rho * plane_len + mb, sk, nullptr, Q, nr); summed = true; } }
                 if (!summed) tds_lane_sums<KT, 1, SK, ROT>(X + rho * plane_len + mb, sk, nullptr, Q, nr);
 #pragma unroll
-                for (int k = 0; k < KT; k++) PN[rho * a.npm + ps_slot<KT>(KT * mb + k)] = nr[k];
+                for (int k = 0; k < KT; k++) PN[rho * a.npm + KT * mb + k + mb * ((KT & 1) ? 2 : 1)] = nr[k];      // = ps_slot<KT>(KT * mb + k)
             }
         }
     };
@@ -574,11 +574,16 @@ __global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT)
                 bool summed = false;
                 if constexpr (kAhead) { if (Q % KT == 0) { tds_lane_sums_ahead<KT, 0, SK>(xb, sk, yp, Q, acc); summed = true; } }
                 if (!summed) tds_lane_sums<KT, 0, SK, ROT>(xb, sk, yp, Q, acc);
+                // candidate cc = K*KT*tb + (kappa + K*(k - off)): its pad count cc / (K*KT) is tb, or tb - 1 for the one slot of a
+                // late stream that belongs to the block before (k = 0, off = 1) -- no division per store
+                constexpr int S = K * KT, PADW = (S & 1) ? 2 : 1;
+                const int cc0 = S * tb + kappa - K * off;
+                float* ps_row = PS + l * a.ncand_pad + cc0 + PADW * tb;
 #pragma unroll
                 for (int k = 0; k < KT; k++) {
                     const int tl = KT * tb + k - off;
-                    const int cc = kappa + K * tl;
-                    if (tl >= 0 && cc < ncand) PS[l * a.ncand_pad + ps_slot<K * KT>(cc)] = acc[k];
+                    const int cc = cc0 + K * k;
+                    if (tl >= 0 && cc < ncand) ps_row[K * k - (k == 0 ? PADW * off : 0)] = acc[k];
                 }
             }
         }
