@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT)
     float* PN = PS + 4 * a.ncand_pad;               // [4 planes][npm] norm sums by start position
     float* MR = PN + 4 * a.npm;                     // [mreg * CH] interleaved frames: mid-buffer region
     double* PW = reinterpret_cast<double*>(MR + ((mreg * CH + 3) & ~3));   // [ncand] position weights
+    int* SLT = reinterpret_cast<int*>(PW + K * KT * a.tb_per);               // [ncand][5] partial-sum slots of a candidate (see the combine phase)
     __shared__ unsigned long long red_k[kTdsThreads / 32];
     __shared__ int red_i[kTdsThreads / 32];
     __shared__ __align__(16) unsigned long long xch[2][8][2];     // [parity][sender rank]{key, index}: written by the peers (st.async)
@@ -517,6 +518,15 @@ __global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT)
         const int c = c_base + cc;
         const double tmp = __ddiv_rn((double)(2 * c - L), (double)L);
         PW[cc] = __dsub_rn(1.0, __dmul_rn(__dmul_rn(0.25, tmp), tmp));
+        // where the candidate's correlation lane sum and its four norm lane sums live: sequence independent, so the
+        // divisions by K*KT and KT of the padded layouts are done once per launch, not once per candidate and sequence
+        SLT[5 * cc] = ps_slot<K * KT>(cc);
+        const int kap = cc % K, trel = cc / K;
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const int u0 = CH * kap + l;
+            SLT[5 * cc + 1 + l] = (u0 & 3) * a.npm + ps_slot<KT>(trel + (u0 >> 2));
+        }
     }
     // sequence positions ride two iterations ahead in registers: a load of pos[] at the top of an iteration put an L2 round
     // trip on the chain's critical path (phase timers: 0.5 k of the 12.7 k clocks of a sequence at 32 tracks)
@@ -594,15 +604,11 @@ __global__ void __launch_bounds__(kTdsThreads, KT == 2 ? 4 : NODEY_TDS_RESIDENT)
         // ---- per candidate: horizontal add in the SSE order, normalise, weight; arg-max (first wins) ----
         unsigned long long bk = 0ull; int bi = 0x7fffffff;
         for (int cc = tid; cc < ncand; cc += blockDim.x) {
-            const int np = a.ncand_pad, sl = ps_slot<K * KT>(cc);
+            const int np = a.ncand_pad, sl = SLT[5 * cc];
             const float sum = __fadd_rn(__fadd_rn(__fadd_rn(PS[sl], PS[np + sl]), PS[2 * np + sl]), PS[3 * np + sl]);
-            const int kap = cc % K, trel = cc / K;
             float nl[4];
 #pragma unroll
-            for (int l = 0; l < 4; l++) {
-                const int u0 = CH * kap + l;
-                nl[l] = PN[(u0 & 3) * a.npm + ps_slot<KT>(trel + (u0 >> 2))];
-            }
+            for (int l = 0; l < 4; l++) nl[l] = PN[SLT[5 * cc + 1 + l]];
             const float nr = __fadd_rn(__fadd_rn(__fadd_rn(nl[0], nl[1]), nl[2]), nl[3]);
             const double dn = (double)nr;
             double corr = __ddiv_rn((double)sum, __dsqrt_rn(dn < 1e-9 ? 1.0 : dn));
@@ -1688,7 +1694,7 @@ static int soundtouch_run_impl(nodey_soundtouch* s, float* out, int64_t out_stri
                 for (int t = 0; t < ntracks; t++) if (((uintptr_t)tab->p[2 * t]) & 7) ta.vec8 = 0;
             }
             const size_t smem = sizeof(float) * ((size_t)8 * KT * sk + (size_t)4 * ta.qp + (size_t)4 * ta.ncand_pad + (size_t)4 * ta.npm +
-                                                 (size_t)((mreg * CH + 3) & ~3)) + sizeof(double) * (size_t)(K * KT * ta.tb_per);
+                                                 (size_t)((mreg * CH + 3) & ~3)) + (sizeof(double) + 5 * sizeof(int)) * (size_t)(K * KT * ta.tb_per);
             NODEY_REQUIRE(smem <= 110 * 1024, NODEY_E_RANGE, "tds_offsets: %zu bytes of shared memory per CTA exceed the two-per-SM budget", smem);
             // (KT = 2 runs four CTAs per SM when its 27 KB allow it; with a larger window it is simply less resident)
             NODEY_REQUIRE(KT * (ta.tb_per + ta.Q / KT + 4) * 4 / CH <= 2048 + 64 * KT, NODEY_E_RANGE, "tds_offsets: search window of %d frames exceeds the staged maximum", KT * sk * 4 / CH);
