@@ -1187,10 +1187,12 @@ __global__ void __launch_bounds__(kFirThreads) st_post_kernel(const __grid_const
             const float x2 = __fmul_rn(__ull2float_rn(fb_cur), inv_f);
             const float x1 = __fmul_rn(x2, x2);
             const float x0 = __fmul_rn(x1, x2);
-            const float y0 = __fadd_rn(__fadd_rn(__fmul_rn(-0.5f, x0), x1), __fmul_rn(-0.5f, x2));
-            const float y1 = __fadd_rn(__fadd_rn(__fmul_rn(1.5f, x0), __fmul_rn(-2.5f, x1)), 1.0f);
-            const float y2 = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, x0), __fmul_rn(2.0f, x1)), __fmul_rn(0.5f, x2));
-            const float y3 = __fadd_rn(__fmul_rn(0.5f, x0), __fmul_rn(-0.5f, x1));
+            // (a product with -c is the negated product with c, bit for bit: three multiplications serve six terms)
+            const float h0 = __fmul_rn(0.5f, x0), h2 = __fmul_rn(0.5f, x2), t0 = __fmul_rn(1.5f, x0);
+            const float y0 = __fadd_rn(__fadd_rn(-h0, x1), -h2);
+            const float y1 = __fadd_rn(__fadd_rn(t0, __fmul_rn(-2.5f, x1)), 1.0f);
+            const float y2 = __fadd_rn(__fadd_rn(-t0, __fmul_rn(2.0f, x1)), h2);
+            const float y3 = __fadd_rn(h0, __fmul_rn(-0.5f, x1));
             const auto at = [&](int f) { return filt[f + (f >> 3)]; };
             const float2 p0 = at(q_cur), p1 = at(q_cur + 1), p2 = at(q_cur + 2), p3 = at(q_cur + 3);
             const float2 o = add2_rn(add2_rn(add2_rn(mul2_rn(p0, make_float2(y0, y0), a.u), mul2_rn(p1, make_float2(y1, y1), a.u), a.u),
