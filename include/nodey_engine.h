@@ -77,6 +77,14 @@ int nodey_engine_mp3_available(void);
  * *time_inout = Process_context::time before / after (NULL = start at 0). */
 int nodey_engine_encode_mp3(const char* path, const void* plane0, const void* plane1, int fmt, int sample_rate, int channels,
                             int64_t frames, int frame_size, double pts_seconds, int kbps, double* time_inout);
+/* What the audio_input node publishes for a RIFF/WAVE file, from the header alone (no device needed): the sample format as
+ * the reference's decoder would hand it on (PCM 16 -> S16, PCM 24 / 32 -> S32 with 24-bit samples in the upper three bytes,
+ * IEEE float 32 -> FLT: libavcodec/pcm.c), rate, channels, sample frames, and the frame size of the stream -- libavformat's
+ * wav demuxer reads packets of 4096 bytes rounded down to whole blocks and the PCM decoder returns one frame per packet
+ * (src/processor/audio-io.cpp:176-222 pushes every decoded frame as it is), i.e. 4096 / block_align sample frames: 1024 for
+ * 16-bit stereo, 512 for float stereo, 682 for 24-bit stereo.  Any output pointer may be NULL.
+ * NODEY_ENGINE_E_FILE for files the source node refuses ("Cannot open audio file"). */
+int nodey_engine_probe_wav(const char* path, int* fmt, int* sample_rate, int* channels, int64_t* frames, int* frame_size);
 /* do_export's per-frame bookkeeping as plain arithmetic (audio-io.cpp:826-839): for a stream of `frames` samples per channel
  * cut into the given frame runs, whose frames are stamped by rule `stamp` -- 0: exact start times from `origin` (decoder
  * stamps), 1: running END time from `origin` truncated to whole microseconds (audio_amix / audio_bimix,

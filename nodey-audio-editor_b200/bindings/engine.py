@@ -58,8 +58,17 @@ def lib():
     L.nodey_engine_export_plan.argtypes = [i32, C.c_double, i32, i64, C.POINTER(i64), C.POINTER(i64), i32, C.POINTER(C.c_double),
                                            C.POINTER(i64), C.POINTER(C.c_double), i32]
     L.nodey_engine_product_stamp.argtypes = [vp, i32, cp, C.POINTER(i32), C.POINTER(C.c_double)]
+    L.nodey_engine_probe_wav.argtypes = [cp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
     _lib = L
     return L
+
+
+def probe_wav(path):
+    """(format, sample_rate, channels, frames, frame_size) audio_input would publish for a RIFF/WAVE file; header only"""
+    f, r, c, fs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    n = C.c_int64()
+    _check(lib().nodey_engine_probe_wav(os.fsencode(path), C.byref(f), C.byref(r), C.byref(c), C.byref(n), C.byref(fs)))
+    return f.value, r.value, c.value, n.value, fs.value
 
 
 def set_release_products(release):

@@ -41,7 +41,8 @@ namespace processor
 	// ---- source ------------------------------------------------------------------------------------
 	// One PCM source per output pin.  The reference demuxes/decodes files with libavformat/libavcodec
 	// (not available here); this engine takes raw PCM handed in through user_data (Pcm_source_list) or
-	// reads canonical RIFF/WAVE files named by file_path (PCM 16/32 bit, IEEE float 32).
+	// reads canonical RIFF/WAVE files named by file_path (PCM 16/24/32 bit, IEEE float 32) with the sample formats and
+	// frame sizes libavformat's wav demuxer + PCM decoders would hand out (4096-byte packets: 4096 / block_align frames).
 	struct Pcm_source
 	{
 		const void* data = nullptr;     // packed samples (planar: plane 0), host or device memory
@@ -49,13 +50,17 @@ namespace processor
 		bool on_device = false;
 		int format = FMT_FLT, sample_rate = 48000, channels = 2;
 		int64_t frames = 0;
-		int frame_size = 1152;          // decoder frame size the reference would see (1152 MP3, 1024 WAV, 4096 FLAC)
+		int frame_size = 1152;          // decoder frame size the reference would see (1152 MP3, 4096 / block_align WAV, 4096 FLAC)
 		double pts_seconds = 0.0;
 	};
 	struct Pcm_source_list
 	{
 		std::vector<Pcm_source> sources;    // index i feeds pin output_{i}
 	};
+	// What audio_input would publish for a RIFF/WAVE file (header only, no device needed): sample format as decoded
+	// (24-bit PCM arrives as S32), rate, channels, sample frames and the frame size of the decoder's packets.
+	// Throws Processor::Runtime_error("Cannot open audio file", ...) like the source node.
+	void probe_wav(const std::string& path, int& format, int& sample_rate, int& channels, int64_t& frames, int& frame_size);
 
 	class Audio_input : public infra::Processor
 	{

@@ -284,6 +284,25 @@ int nodey_engine_product_stamp(nodey_engine* e, int node_id, const char* pin, in
 	return 0;
 }
 
+int nodey_engine_probe_wav(const char* path, int* fmt, int* sample_rate, int* channels, int64_t* frames, int* frame_size)
+{
+	if (!path) return fail(NODEY_ENGINE_E_INVALID, "nodey_engine_probe_wav: null path");
+	try
+	{
+		int f = 0, r = 0, c = 0, fs = 0;
+		int64_t n = 0;
+		processor::probe_wav(path, f, r, c, n, fs);
+		if (fmt) *fmt = f;
+		if (sample_rate) *sample_rate = r;
+		if (channels) *channels = c;
+		if (frames) *frames = n;
+		if (frame_size) *frame_size = fs;
+		return 0;
+	}
+	catch (const Processor::Runtime_error& err) { return fail(NODEY_ENGINE_E_FILE, err.what()); }
+	catch (const std::exception& err) { return fail(NODEY_ENGINE_E_INVALID, err.what()); }
+}
+
 int nodey_engine_export_plan(int stamp, double origin, int sample_rate, int64_t frames, const int64_t* run_len, const int64_t* run_count,
 							 int n_runs, double* time_inout, int64_t* silence, double* frame_pts, int cap)
 {

@@ -536,10 +536,31 @@ namespace processor
 
 	namespace
 	{
-		// canonical RIFF/WAVE reader: PCM 16 / 32 bit and IEEE float 32
-		struct Wav_data { std::vector<char> samples; int format = FMT_S16, rate = 0, channels = 0; int64_t frames = 0; };
+		// canonical RIFF/WAVE reader: PCM 16 / 24 / 32 bit and IEEE float 32 -- what the reference's libavformat / libavcodec
+		// path (audio-io.cpp:69-227) hands to the nodes for such files:
+		//  * sample formats: pcm_s16le -> S16, pcm_s32le -> S32, pcm_f32le -> FLT, pcm_s24le -> S32 with the 24 bits in the
+		//    upper three bytes (libavcodec/pcm.c decodes le24 with a shift of 8); u8 and f64 files decode to formats every
+		//    node of the reference refuses ("Audio format is not support"), here they are refused at the source;
+		//  * frame sizes: the wav demuxer cuts the data chunk into packets of max_size = 4096 bytes rounded down to whole
+		//    blocks (libavformat/wavdec.c, wav_read_packet) and the PCM decoder returns one frame per packet, so a frame
+		//    holds 4096 / block_align sample frames: 1024 for 16-bit stereo, 2048 for 16-bit mono, 512 for 32-bit or float
+		//    stereo, 682 for 24-bit stereo; the last frame takes the rest.  audio_amix's `nb` follows its inputs' frame sizes
+		//    (audio-amix.cpp:190-196), so the size is part of the result.
+		struct Wav_data { std::vector<char> samples; int format = FMT_S16, rate = 0, channels = 0, frame_size = 1024; int64_t frames = 0; };
 
-		Wav_data read_wav(const std::string& path)
+		int wav_packet_frames(int file_bytes_per_sample, int channels)
+		{
+			const int block = file_bytes_per_sample * channels;
+			int size = 4096;
+			if (block > 1)
+			{
+				if (size < block) size = block;
+				size = (size / block) * block;
+			}
+			return std::max(size / block, 1);
+		}
+
+		Wav_data read_wav(const std::string& path, bool header_only = false)
 		{
 			const auto fail = [&](const std::string& why) {
 				return Runtime_error("Cannot open audio file", std::format("'{}' is not a PCM/float RIFF WAVE file this engine can read.", path), why);
@@ -550,7 +571,8 @@ namespace processor
 			if (!f.read(hdr, 12) || memcmp(hdr, "RIFF", 4) || memcmp(hdr + 8, "WAVE", 4)) throw fail("missing RIFF/WAVE header");
 			Wav_data w;
 			int tag = 0, bits = 0;
-			bool have_fmt = false;
+			bool have_fmt = false, have_data = false;
+			uint64_t data_bytes = 0;
 			for (;;)
 			{
 				char ck[8];
@@ -558,31 +580,68 @@ namespace processor
 				uint32_t size; memcpy(&size, ck + 4, 4);
 				if (!memcmp(ck, "fmt ", 4))
 				{
+					if (size < 16 || size > 4096) throw fail("fmt chunk of an impossible size");
 					std::vector<char> b(size);
-					if (!f.read(b.data(), size) || size < 16) throw fail("truncated fmt chunk");
+					if (!f.read(b.data(), size)) throw fail("truncated fmt chunk");
 					uint16_t t, c, bp; uint32_t r;
 					memcpy(&t, b.data(), 2); memcpy(&c, b.data() + 2, 2); memcpy(&r, b.data() + 4, 4); memcpy(&bp, b.data() + 14, 2);
 					if (t == 0xFFFE && size >= 26) memcpy(&t, b.data() + 24, 2);   // WAVE_FORMAT_EXTENSIBLE sub-format
 					tag = t; w.channels = c; w.rate = (int)r; bits = bp; have_fmt = true;
+					if (size & 1) f.seekg(1, std::ios::cur);
 				}
 				else if (!memcmp(ck, "data", 4))
 				{
 					if (!have_fmt) throw fail("data chunk before fmt chunk");
-					w.samples.resize(size);
-					f.read(w.samples.data(), size);
-					w.samples.resize((size_t)f.gcount());
+					have_data = true;
+					// what is really there counts (a recording that was cut off); a size of 0 or 0xFFFFFFFF is a streamed file
+					// whose writer never patched the header: the demuxer reads such a chunk to the end of the file
+					const auto at = f.tellg();
+					f.seekg(0, std::ios::end);
+					const uint64_t rest = (uint64_t)(f.tellg() - at);
+					f.seekg(at);
+					data_bytes = (size == 0 || size == 0xFFFFFFFFu) ? rest : std::min<uint64_t>(size, rest);
+					if (!header_only)
+					{
+						w.samples.resize((size_t)data_bytes);
+						f.read(w.samples.data(), (std::streamsize)data_bytes);
+						w.samples.resize((size_t)f.gcount());
+						data_bytes = w.samples.size();
+					}
 					break;
 				}
 				else f.seekg(size + (size & 1), std::ios::cur);
 			}
 			if (!have_fmt || w.channels < 1 || w.channels > 2) throw fail("unsupported channel count");
-			if (tag == 1 && bits == 16) w.format = FMT_S16;
-			else if (tag == 1 && bits == 32) w.format = FMT_S32;
-			else if (tag == 3 && bits == 32) w.format = FMT_FLT;
+			if (!have_data) throw fail("no data chunk");
+			int file_bytes = 0;
+			if (tag == 1 && bits == 16) { w.format = FMT_S16; file_bytes = 2; }
+			else if (tag == 1 && bits == 24) { w.format = FMT_S32; file_bytes = 3; }
+			else if (tag == 1 && bits == 32) { w.format = FMT_S32; file_bytes = 4; }
+			else if (tag == 3 && bits == 32) { w.format = FMT_FLT; file_bytes = 4; }
 			else throw fail(std::format("unsupported encoding (tag {}, {} bits)", tag, bits));
-			w.frames = (int64_t)(w.samples.size() / (size_t)(format_bytes(w.format) * w.channels));
+			w.frame_size = wav_packet_frames(file_bytes, w.channels);
+			w.frames = (int64_t)(data_bytes / (size_t)(file_bytes * w.channels));
+			if (file_bytes == 3 && !header_only)
+			{
+				// pcm_s24le: the three little-endian bytes become the upper three bytes of a 32-bit sample
+				const size_t n = (size_t)w.frames * (size_t)w.channels;
+				std::vector<char> wide(n * 4);
+				const unsigned char* src = (const unsigned char*)w.samples.data();
+				for (size_t i = 0; i < n; i++)
+				{
+					const uint32_t v = ((uint32_t)src[3 * i] << 8) | ((uint32_t)src[3 * i + 1] << 16) | ((uint32_t)src[3 * i + 2] << 24);
+					memcpy(wide.data() + 4 * i, &v, 4);
+				}
+				w.samples.swap(wide);
+			}
 			return w;
 		}
+	}
+
+	void probe_wav(const std::string& path, int& format, int& sample_rate, int& channels, int64_t& frames, int& frame_size)
+	{
+		const Wav_data w = read_wav(path, true);
+		format = w.format; sample_rate = w.rate; channels = w.channels; frames = w.frames; frame_size = w.frame_size;
 	}
 
 	size_t Audio_input::upload_bytes(const std::any& user_data) const
@@ -623,7 +682,7 @@ namespace processor
 			files.push_back(read_wav(file_paths[i]));
 			const Wav_data& w = files.back();
 			sources[i].data = w.samples.data(); sources[i].format = w.format; sources[i].sample_rate = w.rate;
-			sources[i].channels = w.channels; sources[i].frames = w.frames; sources[i].frame_size = 1024;
+			sources[i].channels = w.channels; sources[i].frames = w.frames; sources[i].frame_size = w.frame_size;
 		}
 
 		// one arena for every host source that has to be uploaded

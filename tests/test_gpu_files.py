@@ -1,6 +1,7 @@
 """GPU: the PCM / WAV edges of the render.  audio_input reads canonical RIFF/WAVE files named by
-the project's file_path (PCM 16 bit and IEEE float; the reference decodes with libavformat, 1024-sample packets for
-WAV PCM); audio_output's export writes a float WAV and keeps do_export's pts rule: (int)((frame stamp - time) * sample_rate)
+the project's file_path (PCM 16 / 24 / 32 bit and IEEE float; the reference decodes with libavformat, whose wav demuxer
+hands out 4096-byte packets: 1024 sample frames for 16-bit stereo, 512 for float stereo, 682 for 24-bit stereo -- CPU side in
+tests/test_wav_probe.py); audio_output's export writes a float WAV and keeps do_export's pts rule: (int)((frame stamp - time) * sample_rate)
 samples of silence in front of every frame where that is positive (src/processor/audio-io.cpp:833-839), with the stamps
 the producing node would have put on its frames (tests/test_export_stamps.py has the arithmetic)."""
 import struct
@@ -9,7 +10,7 @@ import wave
 import numpy as np
 import pytest
 
-from helpers import FMT_FLT, FMT_FLTP, FMT_S16, assert_bit_equal, make_input
+from helpers import FMT_FLT, FMT_FLTP, FMT_S16, FMT_S32, assert_bit_equal, make_input
 
 pytestmark = pytest.mark.gpu
 
@@ -51,21 +52,23 @@ def test_wav_sources_through_gain_and_float_wav_export(eng_gpu, orc, tmp_path):
     e.run()
     a = orc.gain(s16, FMT_S16, 0.8); b = orc.gain(flt, FMT_FLT, 0.6)
     assert_bit_equal(e.product(ga, "output").numpy(), a, "gain of the 16-bit WAV source")
-    assert e.product_runs(ga, "output")[0][0] == 1024            # WAV PCM packets
-    rl, rr = orc.amix([orc.make_track(a, FMT_S16, 44100, frame_size=1024), orc.make_track(b, FMT_FLT, 44100, frame_size=1024)], [0.5, 0.5])
+    assert e.product_runs(ga, "output")[0][0] == 1024            # WAV packets: 4096 bytes of 16-bit stereo
+    assert e.product_runs(gb, "output")[0][0] == 512             # ... and of float stereo
+    rl, rr = orc.amix([orc.make_track(a, FMT_S16, 44100, frame_size=1024), orc.make_track(b, FMT_FLT, 44100, frame_size=512)], [0.5, 0.5])
     got = e.output()
     assert_bit_equal(got.numpy(), np.stack([rl, rr]), "mix of the two files")
     y, rate = _read_float_wav(str(tmp_path / "out.wav"))
     assert rate == 48000
-    # amix stamps frames with their END time (App. C4), truncated to whole microseconds (audio-amix.cpp:199-201): 1024 / 48000 s
-    # = 21333.33 us -> 21333 us, and do_export's (int)((frame_begin - 0) * 48000) = (int)1023.98 -> the reference's export starts
-    # with 1023 samples of silence, not 1024
-    assert got.pts == 21333 * (1 / 1000000.0)
+    # amix's frames are as long as the shortest front frame of its live inputs (audio-amix.cpp:190-193): 512 here, the float
+    # file's packets.  It stamps them with their END time (App. C4), truncated to whole microseconds (audio-amix.cpp:199-201):
+    # 512 / 48000 s = 10666.67 us -> 10666 us, and do_export's (int)((frame_begin - 0) * 48000) = (int)511.97 -> the reference's
+    # export starts with 511 samples of silence, not 512
+    assert got.pts == 10666 * (1 / 1000000.0)
     lead = int(got.pts * 48000)
-    assert lead == 1023 and not y[:lead].any()
+    assert lead == 511 and not y[:lead].any()
     assert e.product_stamp(mix, "output") == (eng_gpu.STAMP_END_US, 0.0)
-    # ... and more silence wherever amix's frame size grows: after the last (short) input frames come the flush frames of
-    # 1152 samples (audio-amix.cpp:195), whose end-time stamps run ahead of the export's `time` (audio-io.cpp:833-839)
+    # ... and more silence wherever amix's frame size grows: after the 16-bit file's last frame (304 samples) the 512-sample
+    # frames resume, and after the last (short) input frames come the flush frames of 1152 samples (audio-amix.cpp:195), whose end-time stamps run ahead of the export's `time` (audio-io.cpp:833-839)
     from test_export_stamps import frames_of, ref_export, ref_stamps_end_us
     sizes = frames_of(e.product_runs(mix, "output"))
     silence, _ = ref_export(ref_stamps_end_us(sizes, 48000), sizes, 48000)
@@ -77,6 +80,39 @@ def test_wav_sources_through_gain_and_float_wav_export(eng_gpu, orc, tmp_path):
         at += nb
     assert at == mixed.shape[0]
     assert_bit_equal(y, np.concatenate(parts), "exported WAV")
+
+
+def test_24_bit_wav_source_arrives_as_s32(eng_gpu, orc, tmp_path):
+    """pcm_s24le decodes to AV_SAMPLE_FMT_S32 with the sample in the upper three bytes (libavcodec/pcm.c), in frames of
+    4092 / 6 = 682 sample frames; the gain node then scales 32-bit integers (audio-vol.cpp:75-100)"""
+    n = 5000
+    rng = np.random.default_rng(24)
+    s24 = rng.integers(-(1 << 23), 1 << 23, (n, 2), dtype=np.int64)
+    raw = np.zeros((n, 2, 3), np.uint8)
+    for k in range(3):
+        raw[:, :, k] = (s24 >> (8 * k)) & 0xFF
+    data = raw.tobytes()
+    with open(str(tmp_path / "s24.wav"), "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 2, 48000, 48000 * 6, 6, 24))
+        f.write(b"data" + struct.pack("<I", len(data)) + data)
+    assert eng_gpu.probe_wav(str(tmp_path / "s24.wav")) == (FMT_S32, 48000, 2, n, 682)
+    p = eng_gpu.Project()
+    src = p.add("audio_input", {"file_path": [str(tmp_path / "s24.wav")]})
+    g = p.add("audio_volume_adjust")
+    out = p.add("audio_output")
+    p.link(src, "output_0", g, "input"); p.link(g, "output", out, "input")
+    e = eng_gpu.Engine(p.json())
+    e.set_volume(g, 0.37)
+    e.run()
+    s32 = (s24 << 8).astype(np.int32)
+    got = e.output()
+    assert (got.fmt, got.rate, got.ch, got.frames) == (FMT_S32, 48000, 2, n)
+    assert_bit_equal(got.numpy(), orc.gain(s32, FMT_S32, 0.37), "gain of the 24-bit samples widened to 32 bits")
+    assert frames_of_runs(e.product_runs(g, "output")) == [682] * 7 + [n - 7 * 682]
+
+
+def frames_of_runs(runs):
+    return [int(l) for l, c in runs for _ in range(int(c))]
 
 
 def test_export_of_an_amix_whose_frame_size_grows(eng_gpu, orc, tmp_path):
