@@ -80,14 +80,19 @@ namespace processor
 
 		// wait = false: the caller orders itself after the producer (chunk by chunk through Audio_buffer::progress)
 		// accept_lazy = false: a lazy gain product (Lazy_gain) is materialised here, so the caller sees an ordinary buffer
+		// The "no input" error reads as the reference's does, word for word (audio-vol.cpp:113-117, audio-amix.cpp:122-126,
+		// audio-bimix.cpp:110-114 and 486-490, audio-io.cpp:858-862, audio-velocity.cpp:278-282): `explain_title` and `detail_key`
+		// carry the two places where the reference's own strings differ from the pattern (bimix writes "Audio channel mix
+		// processor" in the explanation and names the pin 'input' whichever side is missing).
 		std::shared_ptr<const Audio_buffer> require_input(const Processor::Input_map& input, const std::string& key,
-														   const char* node_title, bool wait = true, bool accept_lazy = false)
+														   const char* node_title, bool wait = true, bool accept_lazy = false,
+														   const char* explain_title = nullptr, const char* detail_key = nullptr)
 		{
 			const auto item = infra::get_input_item<Audio_stream>(input, key);
 			if (!item.has_value())
 				throw Runtime_error(std::format("{} has no input", node_title),
-									std::format("{} requires an audio stream on pin '{}'.", node_title, key),
-									std::format("Input item '{}' not found", key));
+									std::format("{} requires an audio stream input to function properly.", explain_title ? explain_title : node_title),
+									std::format("Input item '{}' not found", detail_key ? std::string(detail_key) : key));
 			auto buffer = item->get().get();
 			if (!buffer)
 				throw Runtime_error(std::format("{} received an empty stream", node_title),
@@ -189,13 +194,39 @@ namespace processor
 			return b;
 		}
 
-		void check_channels(const Audio_buffer& b, const char* node)
+		// libavutil's names of the sample formats (av_get_sample_fmt_name), for the reference's "Sample format: {}" detail
+		const char* sample_format_name(int format)
+		{
+			static const char* const names[] = {"u8", "s16", "s32", "flt", "dbl", "u8p", "s16p", "s32p", "fltp", "dblp", "s64", "s64p"};
+			return format >= 0 && format < 12 ? names[format] : "(null)";
+		}
+
+		// Streams a node cannot take.  The three nodes whose reference code checks by itself fail with its words:
+		// audio_volume_adjust (audio-vol.cpp:177-182, 238-243), the SoundTouch nodes (extract_samples_interleaved,
+		// audio-velocity.cpp:223-228) and audio_bimix_v2 (audio-bimix.cpp:555-560); the others leave it to swr_init.
+		enum class Node_kind { other, volume, soundtouch, bimix_v2 };
+
+		void check_channels(const Audio_buffer& b, const char* node, Node_kind kind = Node_kind::other)
 		{
 			if (b.channels != 1 && b.channels != 2)
+			{
+				if (kind == Node_kind::volume)
+					throw Runtime_error("Invalid channel count", "Only mono and stereo audio are supported.", std::format("Got {} channels", b.channels));
+				if (kind == Node_kind::bimix_v2)
+					throw Runtime_error("Invalid audio channel layout", "Audio channel layout must be stereo or mono.",
+										std::format("Invalid channel layout: {}", b.channels));
 				throw Runtime_error("Invalid channel layout", std::format("{} handles mono and stereo streams.", node), std::format("channels: {}", b.channels));
+			}
 			if (format_bytes(b.format) == 0)
+			{
+				if (kind == Node_kind::volume)
+					throw Runtime_error("Audio format is not support", "Audio volume processor requires an audio format properly.", "Include FLT, S16, S32");
+				if (kind == Node_kind::soundtouch)
+					throw Runtime_error("Unsupported sample format", "The processors do not support the given sample format.",
+										std::format("Sample format: {}", sample_format_name(b.format)));
 				throw Runtime_error("Audio format is not support (Include FLT, S16, S32)", std::format("{} cannot process this sample format.", node),
 									std::format("AVSampleFormat {}", b.format));
+			}
 		}
 
 		// process-wide plan caches (plans are immutable once built; kernels in flight keep using them)
@@ -816,7 +847,7 @@ namespace processor
 
 	void Audio_output::process_payload(const Input_map& input, const Output_map&, const std::atomic<bool>&, std::any& user_data)
 	{
-		auto buffer = require_input(input, "input", "Audio output");
+		auto buffer = require_input(input, "input", "Audio output processor");
 		Process_context* ctx = std::any_cast<Process_context>(&user_data);
 		if (!ctx) throw std::bad_any_cast();
 		ctx->rendered = buffer;
@@ -998,7 +1029,7 @@ namespace processor
 		for (const auto& it : items)
 		{
 			ins.push_back(require_input(*it.input, "input", "Volume adjust processor"));
-			check_channels(*ins.back(), "Volume adjust");
+			check_channels(*ins.back(), "Volume adjust", Node_kind::volume);
 			const bool planar2 = format_is_planar(ins.back()->format) && ins.back()->channels == 2;
 			bytes += Arena::padded(ins.back()->plane_bytes()) * (planar2 ? 2 : 1);
 		}
@@ -1093,7 +1124,7 @@ namespace processor
 				// inputs that arrive chunk by chunk are not waited for here: the chunks below wait for the prefix they need
 				auto in = require_input(*items[k].input, "input", title, false);
 				if (!in->progress && in->ready) in->ready->wait_on(cur_stream());
-				check_channels(*in, title);
+				check_channels(*in, title, Node_kind::soundtouch);
 				const Soundtouch_params prm = Soundtouch_params::of(items[k].processor);
 				uint32_t rb, pb;
 				memcpy(&rb, &prm.rate, 4); memcpy(&pb, &prm.pitch, 4);
@@ -1304,10 +1335,10 @@ namespace processor
 		if (value.isMember("keep_pitch") && value["keep_pitch"].isBool()) keep_pitch = value["keep_pitch"].asBool();
 		if (value.isMember("reference_schedule") && value["reference_schedule"].isBool()) reference_schedule = value["reference_schedule"].asBool();
 	}
-	bool Velocity_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Velocity modifier"); }
+	bool Velocity_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Velocity Modifier"); }
 	void Velocity_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
 	{
-		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Velocity modifier");
+		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Velocity Modifier");
 	}
 
 	infra::Processor::Info Pitch_modifier::get_processor_info()
@@ -1332,10 +1363,10 @@ namespace processor
 		if (value.isMember("pitch") && value["pitch"].isDouble()) pitch = value["pitch"].asFloat();
 		if (value.isMember("reference_schedule") && value["reference_schedule"].isBool()) reference_schedule = value["reference_schedule"].asBool();
 	}
-	bool Pitch_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Pitch modifier"); }
+	bool Pitch_modifier::process_batch(const std::vector<Batch_item>& items) { return soundtouch_batch(items, "Pitch Modifier"); }
 	void Pitch_modifier::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>& stop, std::any& user_data)
 	{
-		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Pitch modifier");
+		soundtouch_batch({Batch_item{this, &input, &output, &stop, &user_data}}, "Pitch Modifier");
 	}
 
 	// ---------------------------------------------------------------------------------------------
@@ -1479,7 +1510,7 @@ namespace processor
 			{
 				// a chunk-wise input is not waited for here: the batch path below consumes it chunk by chunk, every other
 				// path waits in amix_execute
-				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio mixer", false, true));
+				job.ins.push_back(require_input(input, std::format("input_{}", i + 1), "Audio Mixer processor", false, true));
 				if (!job.ins.back()->progress && job.ins.back()->ready) job.ins.back()->ready->wait_on(cur_stream());
 				check_channels(*job.ins.back(), "Audio mixer");
 				runs.push_back(&job.ins.back()->runs);
@@ -1801,8 +1832,8 @@ namespace processor
 
 	void Audio_bimix::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
 	{
-		auto in_l = require_input(input, "input_l", "Audio bimix");
-		auto in_r = require_input(input, "input_r", "Audio bimix");
+		auto in_l = require_input(input, "input_l", "Audio Channel mix processor", true, false, "Audio channel mix processor", "input");
+		auto in_r = require_input(input, "input_r", "Audio Channel mix processor", true, false, "Audio channel mix processor", "input");
 		check_channels(*in_l, "Audio bimix");
 		check_channels(*in_r, "Audio bimix");
 
@@ -1867,9 +1898,10 @@ namespace processor
 
 	void Audio_bimix_v2::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)
 	{
-		std::shared_ptr<const Audio_buffer> in[2] = {require_input(input, "input_l", "Audio bimix v2"), require_input(input, "input_r", "Audio bimix v2")};
-		check_channels(*in[0], "Audio bimix v2");
-		check_channels(*in[1], "Audio bimix v2");
+		std::shared_ptr<const Audio_buffer> in[2] = {require_input(input, "input_l", "Audio Channel mix processor", true, false, "Audio channel mix processor", "input"),
+													   require_input(input, "input_r", "Audio Channel mix processor", true, false, "Audio channel mix processor", "input")};
+		check_channels(*in[0], "Audio bimix v2", Node_kind::bimix_v2);
+		check_channels(*in[1], "Audio bimix v2", Node_kind::bimix_v2);
 
 		// per side: list of resampled frames {source offset, length, END time of the block (App. C12)}
 		struct Piece { int64_t src, n; double t; };

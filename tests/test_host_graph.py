@@ -222,6 +222,22 @@ def test_schedule_and_frame_clock_cpp(tmp_path):
     assert "schedule_clock_test ok" in r.stdout
 
 
+def test_node_faults_read_like_the_reference_cpp(tmp_path):
+    """unlinked input pins and streams a node cannot take: Processor::Runtime_error with the reference's own message,
+    explanation and detail, word for word (tests/cpp/node_errors_test.cpp against libnodey_host.so; no device needed)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "nodey-audio-editor_b200")
+    exe = str(tmp_path / "node_errors_test")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I" + os.path.join(pkg, "host", "shim"), "-I" + os.path.join(pkg, "host", "include"),
+                    "-I" + os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "cpp", "node_errors_test.cpp"),
+                    "-L" + pkg, "-lnodey_host", "-lnodey_cuda", "-Wl,-rpath," + pkg, "-lpthread"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert "node_errors_test ok" in r.stdout
+
+
 def test_render_without_a_cuda_device_fails_loudly(eng):
     """no CPU fallback: on a box without a CUDA device the Runner marks every node as failed with a Runtime_error that
     says so (the product path never routes through the oracle)"""
