@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <mutex>
 #include <tuple>
@@ -698,6 +699,18 @@ namespace processor
 		const Pcm_source_list* bound = std::any_cast<Pcm_source_list>(&user_data);
 		if (!bound)
 			if (const auto* sp = std::any_cast<std::shared_ptr<Pcm_source_list>>(&user_data)) bound = sp->get();
+
+		// Every slot that names a file must name a regular file, linked or not (audio-io.cpp:232-239, checked before any
+		// file is opened); slots served by a bound PCM source (this engine's extension) or left empty are not files.
+		for (size_t i = 0; i < file_count; i++)
+		{
+			if (bound && i < bound->sources.size() && bound->sources[i].data) continue;
+			if (file_paths[i].empty()) continue;
+			std::error_code ec;
+			if (!std::filesystem::exists(file_paths[i], ec) || !std::filesystem::is_regular_file(file_paths[i], ec))
+				throw Runtime_error(std::format("Invalid file path in slot {}", i + 1), "The specified audio file does not exist or is not a regular file.",
+									std::format("File path: {}", file_paths[i]));
+		}
 
 		std::vector<Wav_data> files;     // keeps file payloads alive until the copies are enqueued... and landed
 		std::vector<Pcm_source> sources(file_count);
@@ -1473,7 +1486,8 @@ namespace processor
 	{
 		if (!value.isMember("input_num"))
 			throw Runtime_error("Failed to deserialize JSON file",
-								"Audio_amix failed to serialize the JSON input because of missing or invalid fields.", "Wrong field: input_num");
+								// (the reference's text names Audio_bimix here: audio-amix.cpp:412)
+								"Audio_bimix failed to serialize the JSON input because of missing or invalid fields.", "Wrong field: input_num");
 		input_num = std::clamp(value["input_num"].asInt(), 1, NODEY_MAX_MIX_INPUTS);       // audio-amix.cpp:342
 		locks.clear();
 		volumes.clear();

@@ -3,7 +3,7 @@
 // (message, explanation, detail) -- the editor shows them verbatim (src/frontend/app.cpp error popup).  Every check
 // below fails before the node touches the device, so no GPU is needed.  Reference strings:
 //   audio-vol.cpp:113-117, 177-182, 238-243; audio-amix.cpp:122-126; audio-bimix.cpp:110-114, 486-490, 555-560;
-//   audio-io.cpp:858-862; audio-velocity.cpp:223-228, 278-282 (processor_name = Info::display_name, :458 / :475).
+//   audio-io.cpp:232-239, 858-862; audio-velocity.cpp:223-228, 278-282 (processor_name = Info::display_name, :458 / :475).
 // Built and run by tests/test_host_graph.py.
 #include "infra/processor.hpp"
 #include "processor/audio-stream.hpp"
@@ -98,6 +98,20 @@ int main()
              "The processors do not support the given sample format.", "Sample format: u8"));
     CHECK(is(run("audio_bimix_v2", {{"input_l", stream_of(FMT_FLT, 2)}, {"input_r", stream_of(FMT_FLT, 3)}}), "Invalid audio channel layout",
              "Audio channel layout must be stereo or mono.", "Invalid channel layout: 3"));
+
+    // ---- audio_input: every slot that names a file must name a regular file, linked or not (audio-io.cpp:232-239) ----
+    {
+        Json::Value info(Json::objectValue), paths(Json::arrayValue);
+        paths.append(""); paths.append("/nonexistent/dir/take.wav");
+        info["file_path"] = paths;
+        CHECK(is(run("audio_input", none, &info), "Invalid file path in slot 2", "The specified audio file does not exist or is not a regular file.",
+                 "File path: /nonexistent/dir/take.wav"));
+        Json::Value dir(Json::objectValue), one(Json::arrayValue);
+        one.append("/tmp");
+        dir["file_path"] = one;
+        CHECK(is(run("audio_input", none, &dir), "Invalid file path in slot 1", "The specified audio file does not exist or is not a regular file.",
+                 "File path: /tmp"));
+    }
 
     if (failures) { std::fprintf(stderr, "%d failure(s)\n", failures); return 1; }
     std::printf("node_errors_test ok\n");
