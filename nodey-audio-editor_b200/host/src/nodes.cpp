@@ -530,7 +530,7 @@ namespace processor
 	std::vector<Processor::Pin_attribute> Audio_input::get_pin_attributes() const
 	{
 		std::vector<Processor::Pin_attribute> pins;
-		for (size_t i = 0; i < file_count; i++) pins.push_back(Pin_type::audio(std::format("output_{}", i), std::format("Output {}", i), false));
+		for (size_t i = 0; i < file_count; i++) pins.push_back(Pin_type::audio(std::format("output_{}", i), std::format("Output {}", i + 1), false));
 		return pins;
 	}
 
@@ -721,7 +721,7 @@ namespace processor
 			if (bound && i < bound->sources.size() && bound->sources[i].data) { sources[i] = bound->sources[i]; continue; }
 			if (!used) continue;
 			if (file_paths[i].empty())
-				throw Runtime_error("No input source", std::format("Output {} of the audio input node is linked but has neither a PCM source nor a file.", i),
+				throw Runtime_error("No input source", std::format("Output {} of the audio input node is linked but has neither a PCM source nor a file.", i + 1),
 									std::format("pin output_{}", i));
 			files.push_back(read_wav(file_paths[i]));
 			const Wav_data& w = files.back();
@@ -1008,7 +1008,7 @@ namespace processor
 	// ---------------------------------------------------------------------------------------------
 	infra::Processor::Info Audio_vol::get_processor_info()
 	{
-		return {.identifier = "audio_volume_adjust", .display_name = "Volume Adjust", .singleton = false, .generate = std::make_unique<Audio_vol>,
+		return {.identifier = "audio_volume_adjust", .display_name = "Adjust Volume", .singleton = false, .generate = std::make_unique<Audio_vol>,
 				.description = "Multiplies every sample by the gain (0..10). Integer formats are scaled in float and truncated like the reference; "
 							   "format, layout and rate pass through."};
 	}
@@ -1767,7 +1767,7 @@ namespace processor
 	}
 	std::vector<Processor::Pin_attribute> Audio_bimix::get_pin_attributes() const
 	{
-		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Input L", true), Pin_type::audio("input_r", "Input R", true)};
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Left", true), Pin_type::audio("input_r", "Right", true)};
 	}
 	Json::Value Audio_bimix::serialize() const
 	{
@@ -1907,7 +1907,7 @@ namespace processor
 	}
 	std::vector<Processor::Pin_attribute> Audio_bimix_v2::get_pin_attributes() const
 	{
-		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Input L", true), Pin_type::audio("input_r", "Input R", true)};
+		return {Pin_type::audio("output", "Output", false), Pin_type::audio("input_l", "Left", true), Pin_type::audio("input_r", "Right", true)};
 	}
 
 	void Audio_bimix_v2::process_payload(const Input_map& input, const Output_map& output, const std::atomic<bool>&, std::any&)

@@ -1,4 +1,4 @@
-// CPU unit test of the nodes' user-facing faults: a node whose input pin is not linked, or whose input stream has a
+// CPU unit test of the nodes' user-facing faults and names: a node whose input pin is not linked, or whose input stream has a
 // channel count / sample format it cannot take, throws Processor::Runtime_error with the reference's own three strings
 // (message, explanation, detail) -- the editor shows them verbatim (src/frontend/app.cpp error popup).  Every check
 // below fails before the node touches the device, so no GPU is needed.  Reference strings:
@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <map>
 #include <string>
 
 using namespace infra;
@@ -111,6 +112,39 @@ int main()
         dir["file_path"] = one;
         CHECK(is(run("audio_input", none, &dir), "Invalid file path in slot 1", "The specified audio file does not exist or is not a regular file.",
                  "File path: /tmp"));
+    }
+
+    // ---- what the editor's menus and pins show (Info::display_name, Pin_attribute::display_name; same files, :26-100) ----
+    {
+        const std::map<std::string, std::string> names{{"audio_input", "Audio Input"}, {"audio_output", "Audio Output"},
+            {"audio_volume_adjust", "Adjust Volume"}, {"velocity_modifier", "Velocity Modifier"}, {"pitch_modifier", "Pitch Modifier"},
+            {"audio_amix", "Audio Amix"}, {"audio_bimix", "Audio Bimix"}, {"audio_bimix_v2", "Audio Bimix V2"}};
+        for (const auto& [identifier, shown] : names)
+        {
+            const auto& info = Processor::processor_map.at(identifier);
+            CHECK(info.display_name == shown && info.identifier == identifier);
+            CHECK(info.singleton == (identifier == "audio_input" || identifier == "audio_output"));
+        }
+        const auto pins_of = [](const char* identifier, const Json::Value* info = nullptr) {
+            auto node = Processor::processor_map.at(identifier).generate();
+            if (info) node->deserialize(*info);
+            std::string text;
+            for (const auto& p : node->get_pin_attributes()) text += p.identifier + "=" + p.display_name + (p.is_input ? "<" : ">") + " ";
+            return text;
+        };
+        CHECK(pins_of("audio_volume_adjust") == "output=Output> input=Input< ");
+        CHECK(pins_of("pitch_modifier") == "output=Output> input=Input< " && pins_of("velocity_modifier") == "output=Output> input=Input< ");
+        CHECK(pins_of("audio_bimix") == "output=Output> input_l=Left< input_r=Right< ");
+        CHECK(pins_of("audio_bimix_v2") == "output=Output> input_l=Left< input_r=Right< ");
+        CHECK(pins_of("audio_output") == "input=Input< ");
+        Json::Value two(Json::objectValue), paths(Json::arrayValue);
+        paths.append(""); paths.append("");
+        two["file_path"] = paths;
+        CHECK(pins_of("audio_input", &two) == "output_0=Output 1> output_1=Output 2> ");      // 0-based pins, 1-based labels (audio-io.cpp:54-55)
+        Json::Value mix(Json::objectValue);
+        mix["input_num"] = 2;
+        for (int i = 0; i < 2; i++) { mix["volumes" + std::to_string(i)] = 0.5; mix["locks" + std::to_string(i)] = false; }
+        CHECK(pins_of("audio_amix", &mix) == "output=Output> input_1=Input 1< input_2=Input 2< ");
     }
 
     if (failures) { std::fprintf(stderr, "%d failure(s)\n", failures); return 1; }
