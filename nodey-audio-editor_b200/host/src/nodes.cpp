@@ -278,8 +278,9 @@ namespace processor
 			nodey_soundtouch* s = nullptr;
 			const int rc = nodey_soundtouch_create(&s, rate_hz, ch, rate, pitch);
 			if (rc == NODEY_E_RANGE)
+				// audio-velocity.cpp:371-379, word for word (the explanation names the rate where a node name was meant)
 				throw Runtime_error("Unsupported sample rate", std::format("{} requires a sample rate between 8000 and 48000 Hz.", rate_hz),
-									nodey_last_error());
+									std::format("Sample rate: {}", rate_hz));
 			abi(rc, "SoundTouch");
 			if (cache.size() >= kMaxSoundtouchPlans)
 			{
