@@ -967,7 +967,9 @@ namespace processor
 			abi(nodey_memcpy_d2h(host.data(), tmp.ptr, host.size() * sizeof(float), cur_stream()), "audio_output");
 			abi(nodey_stream_synchronize(cur_stream()), "audio_output");
 			std::ofstream f(ctx->export_path, std::ios::binary);
-			if (!f) throw Runtime_error("Cannot write output file", "The export path could not be opened for writing.", ctx->export_path);
+			if (!f)                                                      // audio-io.cpp:648-654
+				throw Runtime_error("Failed to open output file", "Cannot open the output file for writing. Check if the path is valid and writable.",
+									std::format("Output path: {}", ctx->export_path));
 			// do_export's pts rule (audio-io.cpp:833-839): before EVERY frame, (int)((frame_begin - time) * sample_rate) samples of
 			// silence are encoded when that is positive; `time` then follows the frame ends.  frame_begin is the frame's own
 			// stamp, by its producer's rule (Frame_clock): the end-time stamps of amix / bimix (App. C4) make the reference
