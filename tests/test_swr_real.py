@@ -350,3 +350,30 @@ def test_live_randomised_loops_against_the_library(orc, seed):
                 assert pts == gpts and np.array_equal(out == 0, gold == 0) and np.abs(out - gold).max() <= VALUE_TOL, ("bimix_v2", left, right, pl, pr)
     finally:
         R.force_c_path(False)
+
+
+@pytest.mark.parametrize("case", [
+    # (rate, format, channels, frames, frame size) per input: what audio_input publishes for WAV files (libavformat's
+    # 4096-byte packets: 1024 frames of 16-bit stereo, 512 of float stereo, 682 of 24-bit stereo, 2048 of 16-bit mono,
+    # 1365 of 24-bit mono) -- mixed in one audio_amix, so that the output is cut by the SHORTER frames and the inputs with
+    # longer frames are drained through a capped output, surplus buffered inside the resampler
+    ("s16_stereo+flt_stereo", [(44100, 1, 2, 30000, 1024), (44100, 3, 2, 30500, 512)]),
+    ("s24_stereo+s16_mono", [(48000, 2, 2, 20000, 682), (44100, 1, 1, 25000, 2048)]),
+    ("flt_stereo+s24_mono+s16_stereo", [(22050, 3, 2, 9000, 512), (44100, 2, 1, 21000, 1365), (96000, 1, 2, 40000, 1024)]),
+], ids=lambda c: c[0] if isinstance(c, tuple) else None)
+def test_live_amix_of_wav_packet_sizes_against_the_library(orc, case):
+    from oracle import real_swr as R
+    if not R.available():
+        pytest.skip("no libswresample in this image")
+    _, specs = case
+    vols = [0.5, 0.8, 0.25][:len(specs)]
+    R.force_c_path(True)
+    try:
+        gl, gr, _ = G.amix_real(R, orc, specs, vols)
+    finally:
+        R.force_c_path(False)
+    # the same inputs as amix_real makes for itself (track seeds 40 + i)
+    tracks = [orc.make_track(G.case_input(orc, r, f, c, n, 40 + i), f, r, frame_size=fr) for i, (r, f, c, n, fr) in enumerate(specs)]
+    l, r_ = orc.amix(tracks, vols)
+    assert len(l) == len(gl), ("amix length", specs)
+    assert np.array_equal(l == 0, gl == 0) and max(np.abs(l - gl).max(), np.abs(r_ - gr).max()) <= VALUE_TOL
